@@ -1,0 +1,296 @@
+// Fused CD-k driver for the binary-binary RBM on the tcgen05 path (rbm.py:628-646 chain, rbm.py:664
+// cd_loss and the gradient TF autodiff derives from it — closed form in SURVEY.md §8 R9).
+//
+// Data layout in HBM (per rank; N = local batch rows, NP = N rounded up to 64):
+//   weight cache : W  as fp16 hi/lo [V,H]  and  W^T as fp16 hi/lo [H,V], pre-scaled by 2^e (e chosen
+//                  from max|W| on the device), refreshed once per optimizer step, read 2k+1 times.
+//   V0b, Vb      : [N,V] fp16 binary states (data / current chain visibles)  -> B operand of "up"
+//   Hb           : [N,H] fp16 binary chain hiddens (or the caller's PCD state) -> B operand of "down"
+//   VT           : [V, 2*NP] fp16, data and model visibles, 64-column interleaved -> B operand of dW
+//   PT_hi, PT_lo : [H, 2*NP] fp16, +p0 and -pk scaled by 2^14, interleaved alike   -> A operand of dW
+// Every GEMM is  D[units, batch] = REAL_split[units, K] * BINARY[batch, K]^T  (gemm_tc.cu), so the
+// chain is 2k+1 launches + 1 dW launch + 3 small memory-bound kernels.
+#include "context.h"
+#include "gemm_tc.cuh"
+
+namespace db {
+namespace {
+
+constexpr float kProbScale = 16384.0f;   // 2^14: p in (0,1) -> fp16 normal range, hi+lo >= 22 bits
+
+struct WeightCacheHeader {
+  float scale;       // 2^e
+  float inv_scale;   // 2^-e
+  unsigned int max_bits;
+  unsigned int pad[61];
+};
+static_assert(sizeof(WeightCacheHeader) == 256, "header is one 256-byte slot");
+
+inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct WeightCacheView {
+  WeightCacheHeader* hdr;
+  __half *w_hi, *w_lo;     // [V,H]
+  __half *wt_hi, *wt_lo;   // [H,V]
+};
+inline WeightCacheView weight_cache_view(void* cache, int V, int H) {
+  WeightCacheView v;
+  uint8_t* p = static_cast<uint8_t*>(cache);
+  const size_t mat = align256((size_t)V * H * sizeof(__half));
+  v.hdr = reinterpret_cast<WeightCacheHeader*>(p); p += 256;
+  v.w_hi = reinterpret_cast<__half*>(p); p += mat;
+  v.w_lo = reinterpret_cast<__half*>(p); p += mat;
+  v.wt_hi = reinterpret_cast<__half*>(p); p += mat;
+  v.wt_lo = reinterpret_cast<__half*>(p);
+  return v;
+}
+
+struct ChainWorkspace {
+  __half *v0b, *vb, *hb, *vt, *pt_hi, *pt_lo;
+  int NP;
+  size_t bytes;
+};
+inline ChainWorkspace chain_workspace(void* ws, int N, int V, int H) {
+  ChainWorkspace w;
+  w.NP = (N + 63) / 64 * 64;
+  uint8_t* p = static_cast<uint8_t*>(ws);
+  uint8_t* p0 = p;
+  w.v0b = reinterpret_cast<__half*>(p); p += align256((size_t)N * V * 2);
+  w.vb = reinterpret_cast<__half*>(p); p += align256((size_t)N * V * 2);
+  w.hb = reinterpret_cast<__half*>(p); p += align256((size_t)N * H * 2);
+  w.vt = reinterpret_cast<__half*>(p); p += align256((size_t)V * 2 * w.NP * 2);
+  w.pt_hi = reinterpret_cast<__half*>(p); p += align256((size_t)H * 2 * w.NP * 2);
+  w.pt_lo = reinterpret_cast<__half*>(p); p += align256((size_t)H * 2 * w.NP * 2);
+  w.bytes = (size_t)(p - p0);
+  return w;
+}
+
+// ---- max |W| and the power-of-two scale ----------------------------------------------------------
+__global__ void absmax_kernel(const float* __restrict__ x, size_t n, unsigned int* __restrict__ out_bits) {
+  float m = 0.0f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(__ldg(x + i)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));   // non-negative floats order as uints
+}
+__global__ void choose_scale_kernel(WeightCacheHeader* hdr) {
+  const float m = __uint_as_float(hdr->max_bits);
+  int e = 0;
+  if (m > 0.0f && isfinite(m)) {
+    int q; frexpf(m, &q);           // m = f * 2^q, f in [0.5, 1)  ->  m * 2^(14-q) in [2^13, 2^14)
+    e = 14 - q;
+    e = max(-100, min(100, e));
+  }
+  hdr->scale = ldexpf(1.0f, e);
+  hdr->inv_scale = ldexpf(1.0f, -e);
+}
+
+// ---- fp32 [R,C] -> fp16 row-major copy and/or fp16 transposed copy, optional hi/lo split ----------
+// t_interleave_phase >= 0: the transposed copy is written at tc_interleaved_col(r, phase) (CD "T" layout)
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) cvt_transpose_kernel(const float* __restrict__ src, int R, int C,
+                                                            const float* __restrict__ scale_dev, __half* __restrict__ d_hi,
+                                                            __half* __restrict__ d_lo, int ldd, __half* __restrict__ t_hi,
+                                                            __half* __restrict__ t_lo, int ldt, int t_interleave_phase) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const float s = scale_dev ? __ldg(scale_dev) : 1.0f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + 8 * i, c = c0 + tx;
+    float v = (r < R && c < C) ? __ldg(src + (size_t)r * C + c) * s : 0.0f;
+    tile[ty + 8 * i][tx] = v;
+    if (d_hi != nullptr && r < R && c < C) {
+      if (SPLIT) { __half hi, lo; split_f16(v, hi, lo); d_hi[(size_t)r * ldd + c] = hi; d_lo[(size_t)r * ldd + c] = lo; }
+      else d_hi[(size_t)r * ldd + c] = __float2half_rn(v);
+    }
+  }
+  __syncthreads();
+  if (t_hi != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = c0 + ty + 8 * i, r = r0 + tx;
+      if (c < C && r < R) {
+        const float v = tile[tx][ty + 8 * i];
+        const int col = t_interleave_phase >= 0 ? tc_interleaved_col(r, t_interleave_phase) : r;
+        if (SPLIT) { __half hi, lo; split_f16(v, hi, lo); t_hi[(size_t)c * ldt + col] = hi; t_lo[(size_t)c * ldt + col] = lo; }
+        else t_hi[(size_t)c * ldt + col] = __float2half_rn(v);
+      }
+    }
+  }
+}
+
+// ---- bias gradients from the interleaved T buffers: one warp per unit ------------------------------
+// gb[v] = -inv_n * (sum_n v0[n,v] - sum_n vk[n,v])          (sign from the phase of each 64-block)
+// gc[h] = -inv_n * 2^-14 * sum_cols (PT_hi + PT_lo)[h,:]     (phase-1 entries are stored negated)
+__global__ void tc_bias_grads_kernel(const __half* __restrict__ vt, const __half* __restrict__ pt_hi,
+                                     const __half* __restrict__ pt_lo, int V, int H, int ld, float inv_n,
+                                     float* __restrict__ gb, float* __restrict__ gc) {
+  const int unit = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x & 31;
+  if (unit >= V + H) return;
+  float s = 0.0f;
+  if (unit < V) {
+    const __half* row = vt + (size_t)unit * ld;
+    for (int c = lane * 8; c < ld; c += 256) {
+      const uint4 q = *reinterpret_cast<const uint4*>(row + c);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&q);
+      float t = 0.0f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h2[e]); t += f.x + f.y; }
+      s += ((c >> 6) & 1) ? -t : t;
+    }
+    s = warp_sum(s);
+    if (lane == 0) gb[unit] = -inv_n * s;
+  } else {
+    const int hrow = unit - V;
+    const __half* rh = pt_hi + (size_t)hrow * ld;
+    const __half* rl = pt_lo + (size_t)hrow * ld;
+    float shi = 0.0f, slo = 0.0f;
+    for (int c = lane * 8; c < ld; c += 256) {
+      const uint4 qh = *reinterpret_cast<const uint4*>(rh + c);
+      const uint4 ql = *reinterpret_cast<const uint4*>(rl + c);
+      const __half2* a = reinterpret_cast<const __half2*>(&qh);
+      const __half2* b = reinterpret_cast<const __half2*>(&ql);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 fa = __half22float2(a[e]), fb = __half22float2(b[e]);
+        shi += fa.x + fa.y; slo += fb.x + fb.y;
+      }
+    }
+    s = warp_sum(shi) + warp_sum(slo);
+    if (lane == 0) gc[hrow] = -inv_n * (1.0f / kProbScale) * s;
+  }
+}
+
+__global__ void half_to_float_kernel(const __half* __restrict__ src, size_t n, float* __restrict__ dst) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = __half2float(src[i]);
+}
+
+inline int ew_grid(size_t n, int num_sms) {
+  size_t blocks = (n + 255) / 256, cap = (size_t)num_sms * 8;
+  return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+inline bool tc_shape_ok(int N, int V, int H) { return N >= 8 && (N % 8 == 0) && (V % 8 == 0) && (H % 8 == 0) && V >= 8 && H >= 8; }
+
+}  // namespace
+}  // namespace db
+
+using namespace db;
+
+extern "C" size_t db_cd_tc_workspace_bytes(const db_cd_tc_desc_t* d) {
+  if (!d || !tc_shape_ok(d->N, d->V, d->H)) return 0;
+  return chain_workspace(nullptr, d->N, d->V, d->H).bytes;
+}
+
+extern "C" size_t db_cd_tc_weight_cache_bytes(int V, int H) {
+  return 256 + 4 * align256((size_t)V * H * sizeof(__half));
+}
+
+extern "C" int db_cd_tc_refresh_weights(db_handle_t h, db_stream_t stream, const float* W, int V, int H, void* cache) {
+  DB_REQUIRE(h, W && cache && V > 0 && H > 0, "null operand or empty shape");
+  if (h->cc_major < 10) return set_err(h, DB_ERR_UNSUPPORTED, "tcgen05 path needs sm_100a (device is sm_%d%d)", h->cc_major, h->cc_minor);
+  cudaStream_t st = (cudaStream_t)stream;
+  WeightCacheView wc = weight_cache_view(cache, V, H);
+  cudaMemsetAsync(&wc.hdr->max_bits, 0, sizeof(unsigned int), st);
+  const size_t n = (size_t)V * H;
+  absmax_kernel<<<ew_grid(n, h->num_sms), 256, 0, st>>>(W, n, &wc.hdr->max_bits);
+  choose_scale_kernel<<<1, 1, 0, st>>>(wc.hdr);
+  dim3 grid((H + 31) / 32, (V + 31) / 32);
+  cvt_transpose_kernel<true><<<grid, 256, 0, st>>>(W, V, H, &wc.hdr->scale, wc.w_hi, wc.w_lo, H, wc.wt_hi, wc.wt_lo, V, -1);
+  return check_launch(h, "cd_tc_refresh_weights");
+}
+
+extern "C" int db_cd_tc_step(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, const float* v0,
+                             const float* params, const void* weight_cache, void* pcd_state, const float* injected,
+                             const db_rng_t* rng, void* workspace, float* grad, float* vk_out, float* hk_out,
+                             float* p0_out, float* pk_out) {
+  DB_REQUIRE(h, d && v0 && params && weight_cache && workspace && grad, "null operand");
+  DB_REQUIRE(h, d->k >= 1, "k must be > 0");   // rbm.py:364
+  DB_REQUIRE(h, injected || rng, "sampling needs injected draws or an rng");
+  DB_REQUIRE(h, !d->pcd || pcd_state, "pcd=1 needs the persistent chain state");
+  if (h->cc_major < 10) return set_err(h, DB_ERR_UNSUPPORTED, "tcgen05 path needs sm_100a (device is sm_%d%d)", h->cc_major, h->cc_minor);
+  const int N = d->N, V = d->V, H = d->H, k = d->k;
+  if (!tc_shape_ok(N, V, H)) return set_err(h, DB_ERR_UNSUPPORTED, "tensor path needs N, V, H multiples of 8 (got %d, %d, %d)", N, V, H);
+  if (!injected && (rng->row_offset & 3u)) return set_err(h, DB_ERR_UNSUPPORTED, "row_offset must be a multiple of 4");
+  cudaStream_t st = (cudaStream_t)stream;
+
+  WeightCacheView wc = weight_cache_view(const_cast<void*>(weight_cache), V, H);
+  ChainWorkspace ws = chain_workspace(workspace, N, V, H);
+  const int ldT = 2 * ws.NP;
+  const float* b = params + (size_t)V * H;
+  const float* c = b + V;
+  float* gW = grad; float* gb = grad + (size_t)V * H; float* gc = gb + V;
+  __half* hstate = d->pcd ? static_cast<__half*>(pcd_state) : ws.hb;
+
+  RngArgs r; to_rng(rng, r);
+  const uint64_t draw0 = rng ? rng->draw : 0;
+  auto set_draw = [&](TcGemmParams& p, uint64_t i) {
+    p.rng = r; const uint64_t dr = draw0 + i; p.rng.draw_lo = (uint32_t)dr; p.rng.draw_hi = (uint32_t)(dr >> 32);
+  };
+  const size_t NH = (size_t)N * H, NV = (size_t)N * V;
+
+  if (N != ws.NP) {   // padded columns of the interleaved buffers must not contribute to dW
+    cudaMemsetAsync(ws.vt, 0, (size_t)V * ldT * 2, st);
+    cudaMemsetAsync(ws.pt_hi, 0, (size_t)H * ldT * 2, st);
+    cudaMemsetAsync(ws.pt_lo, 0, (size_t)H * ldT * 2, st);
+  }
+  {  // data batch -> fp16 [N,V] and interleaved phase 0 of VT
+    dim3 grid((V + 31) / 32, (N + 31) / 32);
+    cvt_transpose_kernel<false><<<grid, 256, 0, st>>>(v0, N, V, nullptr, ws.v0b, nullptr, V, ws.vt, nullptr, ldT, 0);
+  }
+
+  auto up = [&](const __half* vin, int phase /*-1: middle of chain*/, bool write_sample, const float* U, uint64_t draw_i,
+                float* p_out) -> int {
+    TcGemmParams p{};
+    p.Ma = H; p.Nb = N; p.K = V;
+    p.a_hi = wc.wt_hi; p.a_lo = wc.wt_lo; p.lda = V; p.b = vin; p.ldb = V;
+    p.acc_scale = 1.0f; p.acc_scale_dev = &wc.hdr->inv_scale; p.bias = c; p.act = 1;
+    p.sample = write_sample ? 1 : 0; p.U = U; p.ldu = H; set_draw(p, draw_i);
+    p.out32 = p_out; p.ld32 = H;
+    p.out_s16 = write_sample ? hstate : nullptr; p.lds16 = H;
+    if (phase >= 0) {
+      p.out_pT_hi = ws.pt_hi; p.out_pT_lo = ws.pt_lo; p.ldpT = ldT; p.pT_phase = phase;
+      p.pT_scale = phase == 0 ? kProbScale : -kProbScale;
+    }
+    return tc_gemm_launch(p, h->num_sms, st);
+  };
+  auto down = [&](bool last, const float* U, uint64_t draw_i) -> int {
+    TcGemmParams p{};
+    p.Ma = V; p.Nb = N; p.K = H;
+    p.a_hi = wc.w_hi; p.a_lo = wc.w_lo; p.lda = H; p.b = hstate; p.ldb = H;
+    p.acc_scale = 1.0f; p.acc_scale_dev = &wc.hdr->inv_scale; p.bias = b; p.act = 1;
+    p.sample = 1; p.U = U; p.ldu = V; set_draw(p, draw_i);
+    p.out_s16 = ws.vb; p.lds16 = V;
+    if (last) { p.out_sT16 = ws.vt; p.ldsT = ldT; p.sT_phase = 1; }
+    return tc_gemm_launch(p, h->num_sms, st);
+  };
+
+  int rc = up(ws.v0b, 0, !d->pcd, injected, 0, p0_out);
+  if (rc) return set_err(h, rc == -1000 ? DB_ERR_UNSUPPORTED : DB_ERR_CUDA, "cd_tc up(v0) launch failed (%d)", rc);
+  for (int s = 1; s <= k; ++s) {
+    const float* Uv = injected ? injected + NH + (size_t)(s - 1) * (NV + NH) : nullptr;
+    const float* Uh = injected ? Uv + NV : nullptr;
+    rc = down(s == k, Uv, (uint64_t)(2 * s - 1));
+    if (rc) return set_err(h, DB_ERR_CUDA, "cd_tc down launch failed (%d)", rc);
+    rc = up(ws.vb, s == k ? 1 : -1, true, Uh, (uint64_t)(2 * s), s == k ? pk_out : nullptr);
+    if (rc) return set_err(h, DB_ERR_CUDA, "cd_tc up launch failed (%d)", rc);
+  }
+  {  // dW[v,h] = -(1/N) (v0^T p0 - vk^T pk): one GEMM over the interleaved K = 2*NP axis
+    TcGemmParams p{};
+    p.Ma = H; p.Nb = V; p.K = ldT;
+    p.a_hi = ws.pt_hi; p.a_lo = ws.pt_lo; p.lda = ldT; p.b = ws.vt; p.ldb = ldT;
+    p.acc_scale = -d->inv_global_n / kProbScale; p.act = 0; p.sample = 0;
+    p.out32 = gW; p.ld32 = H;
+    rc = tc_gemm_launch(p, h->num_sms, st);
+    if (rc) return set_err(h, DB_ERR_CUDA, "cd_tc dW launch failed (%d)", rc);
+  }
+  tc_bias_grads_kernel<<<(V + H + 7) / 8, 256, 0, st>>>(ws.vt, ws.pt_hi, ws.pt_lo, V, H, ldT, d->inv_global_n, gb, gc);
+  if (vk_out) half_to_float_kernel<<<ew_grid(NV, h->num_sms), 256, 0, st>>>(ws.vb, NV, vk_out);
+  if (hk_out) half_to_float_kernel<<<ew_grid(NH, h->num_sms), 256, 0, st>>>(hstate, NH, hk_out);
+  return check_launch(h, "cd_tc_step");
+}

@@ -1,0 +1,47 @@
+// Internal: the opaque handle behind db_handle_t and the error-reporting helpers of the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/deepbelief_b200.h"
+#include "common.cuh"
+
+struct db_context_s {
+  int device;
+  int num_sms;
+  int cc_major, cc_minor;
+  char err[512];
+};
+
+namespace db {
+
+inline int set_err(db_handle_t h, int code, const char* fmt, ...) {
+  if (h) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(h->err, sizeof(h->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+inline int check_launch(db_handle_t h, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_err(h, DB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return DB_OK;
+}
+
+inline void to_rng(const db_rng_t* r, RngArgs& o) {
+  if (r) {
+    o.seed_lo = (uint32_t)r->seed; o.seed_hi = (uint32_t)(r->seed >> 32);
+    o.draw_lo = (uint32_t)r->draw; o.draw_hi = (uint32_t)(r->draw >> 32);
+    o.row_offset = r->row_offset;
+  } else {
+    o.seed_lo = o.seed_hi = o.draw_lo = o.draw_hi = o.row_offset = 0;
+  }
+}
+
+}  // namespace db
+
+#define DB_REQUIRE(h, cond, msg) \
+  do { if (!(cond)) return db::set_err((h), DB_ERR_BAD_ARG, "%s: %s", __func__, (msg)); } while (0)

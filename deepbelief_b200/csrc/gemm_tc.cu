@@ -1,0 +1,355 @@
+// K1/K2 tensor-core form: persistent, warp-specialised tcgen05 GEMM for the binary-RBM CD chain.
+//
+//   D[Ma, Nb] = A[Ma, K] * B[Nb, K]^T      (fp16 operands, fp32 accumulate in TMEM)
+//
+// Replaces the TF ops behind rbm.py:129-131 (v@W+c), rbm.py:143-147 (W@h^T+b), rbm.py:160/174
+// (sigmoid), rbm.py:202-208/230-236 (uniform draw + strict compare) and the two dW products TF
+// autodiff derives from rbm.py:388-415 — one launch each, nothing materialised in between.
+//
+// Precision: one operand of every CD GEMM of a binary-binary RBM is exactly {0,1} (SURVEY.md §7
+// hard part 1), so only the real operand (W, or the probabilities in dW) is split: x*2^s = hi + lo
+// in fp16 (>= 22 significant bits), two kind::f16 MMA passes accumulate into the same TMEM tile.
+// That is fp32-level accuracy at 2 fp16 passes = the cost of ONE TF32 pass (fp16 runs at 2x TF32).
+//
+// Roles (256 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0   : TMA producer   (A_hi, A_lo, B tiles -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1   : MMA issuer     (one elected thread: tcgen05.mma, tcgen05.commit)
+//   warp 2   : TMEM allocator (512 columns = 2 accumulator stages of 128x256 fp32)
+//   warps 4-7: epilogue       (tcgen05.ld -> scale+bias -> logistic -> Philox/injected uniform ->
+//                              compare -> global stores), overlapped with the next tile's MMAs.
+#include "gemm_tc.cuh"
+#include "ptx.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace db {
+
+namespace {
+
+constexpr int BLOCK_M = 128;   // rows of A per tile  (TMEM lanes)
+constexpr int BLOCK_N = 256;   // rows of B per tile  (TMEM columns)
+constexpr int BLOCK_K = 64;    // fp16 elements = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 3;
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
+constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KB
+constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + B_TILE_BYTES;   // 64 KB
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;       // 512
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+constexpr int GROUP_M = 8;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct TileCoord { int m_blk, n_blk; };
+
+__device__ __forceinline__ TileCoord tile_coord(int t, int tiles_m, int tiles_n) {
+  // groups of GROUP_M row-blocks sweep all column-blocks: CTAs running together share A and B tiles in L2
+  const int group_size = GROUP_M * tiles_n;
+  const int g = t / group_size;
+  const int first_m = g * GROUP_M;
+  const int gm = min(tiles_m - first_m, GROUP_M);
+  const int in_g = t - g * group_size;
+  TileCoord c;
+  c.m_blk = first_m + in_g % gm;
+  c.n_blk = in_g / gm;
+  return c;
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+               const __grid_constant__ CUtensorMap tm_b, const TcGemmParams p) {
+#if defined(DB_SM100)
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle atoms need 1024-byte aligned tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;                       // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;             // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;         // [ACC_STAGES]
+  uint64_t* tempty_bar = tfull_bar + ACC_STAGES;   // [ACC_STAGES]
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tempty_bar + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const bool two_pass = p.a_lo != nullptr;
+
+  const int tiles_m = (p.Ma + BLOCK_M - 1) / BLOCK_M;
+  const int tiles_n = (p.Nb + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    ptx::tma_prefetch_desc(&tm_a_hi);
+    if (two_pass) ptx::tma_prefetch_desc(&tm_a_lo);
+    ptx::tma_prefetch_desc(&tm_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < ACC_STAGES; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 128); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_base_smem, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t tx_bytes = (two_pass ? 2 * A_TILE_BYTES : A_TILE_BYTES) + B_TILE_BYTES;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const TileCoord tc = tile_coord(t, tiles_m, tiles_n);
+        const int m0 = tc.m_blk * BLOCK_M, n0 = tc.n_blk * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          ptx::tma_load_2d(st, &tm_a_hi, &full_bar[stage], kb * BLOCK_K, m0);
+          if (two_pass) ptx::tma_load_2d(st + A_TILE_BYTES, &tm_a_lo, &full_bar[stage], kb * BLOCK_K, m0);
+          ptx::tma_load_2d(st + 2 * A_TILE_BYTES, &tm_b, &full_bar[stage], kb * BLOCK_K, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc(/*F16*/ 0, BLOCK_M, BLOCK_N);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);          // TMA bytes have landed
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
+          const uint64_t d_ahi = ptx::umma_desc_k_sw128(sa);
+          const uint64_t d_alo = ptx::umma_desc_k_sw128(sa + A_TILE_BYTES);
+          const uint64_t d_b = ptx::umma_desc_k_sw128(sa + 2 * A_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // advance inside the swizzle row
+            ptx::mma_f16_ss(tmem_d, d_ahi + koff, d_b + koff, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (two_pass) ptx::mma_f16_ss(tmem_d, d_alo + koff, d_b + koff, idesc, 1u);
+          }
+          ptx::mma_commit(&empty_bar[stage]);               // frees the smem slot when the MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::mma_commit(&tfull_bar[acc]);                   // accumulator complete -> epilogue
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===================== epilogue =====================
+    const int quarter = warp & 3;                   // TMEM lane quarter this warp may read
+    int acc = 0; uint32_t acc_phase = 0;
+    const float inv_pT = p.pT_scale;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const TileCoord tc = tile_coord(t, tiles_m, tiles_n);
+      const int m = tc.m_blk * BLOCK_M + quarter * 32 + lane;
+      const bool m_ok = m < p.Ma;
+      const int n_tile0 = tc.n_blk * BLOCK_N;
+      const float bias_m = (p.bias != nullptr && m_ok) ? __ldg(p.bias + m) : 0.0f;
+      const float acc_scale = p.acc_scale_dev ? p.acc_scale * __ldg(p.acc_scale_dev) : p.acc_scale;
+
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+
+#pragma unroll 1
+      for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+        const int nb0 = n_tile0 + chunk * 32;
+        if (nb0 >= p.Nb) break;                     // warp-uniform
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(taddr0 + (uint32_t)(chunk * 32), r);
+        ptx::tmem_ld_wait();
+
+        float val[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = fmaf(__uint_as_float(r[j]), acc_scale, bias_m);
+          val[j] = p.act ? __fdividef(1.0f, 1.0f + __expf(-x)) : x;
+        }
+
+        uint32_t sbits = 0;
+        if (p.sample) {
+          if (p.U != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int nb = nb0 + j;
+              float u = (m_ok && nb < p.Nb) ? __ldg(p.U + (size_t)nb * p.ldu + m) : 2.0f;
+              sbits |= (val[j] > u ? 1u : 0u) << j;
+            }
+          } else {
+            const uint32_t grow0 = p.rng.row_offset + (uint32_t)nb0;   // multiple of 4 by construction
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              Philox4 o = philox4x32_10((uint32_t)m, (grow0 >> 2) + q, p.rng.draw_lo, p.rng.draw_hi,
+                                        p.rng.seed_lo, p.rng.seed_hi);
+              sbits |= (val[4 * q + 0] > u32_to_uniform(o.x) ? 1u : 0u) << (4 * q + 0);
+              sbits |= (val[4 * q + 1] > u32_to_uniform(o.y) ? 1u : 0u) << (4 * q + 1);
+              sbits |= (val[4 * q + 2] > u32_to_uniform(o.z) ? 1u : 0u) << (4 * q + 2);
+              sbits |= (val[4 * q + 3] > u32_to_uniform(o.w) ? 1u : 0u) << (4 * q + 3);
+            }
+          }
+        }
+
+        // ---- [Nb, Ma] outputs: for fixed j the 32 lanes write 32 consecutive units ----
+        if (p.out32 != nullptr && m_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb0 + j < p.Nb) p.out32[(size_t)(nb0 + j) * p.ld32 + m] = val[j];
+        }
+        if (p.out_s16 != nullptr && m_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb0 + j < p.Nb) {
+              float s = p.sample ? (float)((sbits >> j) & 1u) : val[j];
+              p.out_s16[(size_t)(nb0 + j) * p.lds16 + m] = __float2half_rn(s);
+            }
+        }
+        // ---- [Ma, Nb] "T" outputs: each thread owns 32 consecutive columns of its row ----
+        const bool full_chunk = nb0 + 32 <= p.Nb;
+        if (p.out_sT16 != nullptr && m_ok) {
+          __half* dst = p.out_sT16 + (size_t)m * p.ldsT + tc_interleaved_col(nb0, p.sT_phase);
+          if (full_chunk) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 v;
+              uint32_t b = sbits >> (8 * g);
+              v.x = pack_h2((float)(b & 1u), (float)((b >> 1) & 1u));
+              v.y = pack_h2((float)((b >> 2) & 1u), (float)((b >> 3) & 1u));
+              v.z = pack_h2((float)((b >> 4) & 1u), (float)((b >> 5) & 1u));
+              v.w = pack_h2((float)((b >> 6) & 1u), (float)((b >> 7) & 1u));
+              reinterpret_cast<uint4*>(dst)[g] = v;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb0 + j < p.Nb) dst[j] = __float2half_rn((float)((sbits >> j) & 1u));
+          }
+        }
+        if (p.out_pT_hi != nullptr && m_ok) {
+          __half* dhi = p.out_pT_hi + (size_t)m * p.ldpT + tc_interleaved_col(nb0, p.pT_phase);
+          __half* dlo = p.out_pT_lo + (size_t)m * p.ldpT + tc_interleaved_col(nb0, p.pT_phase);
+          if (full_chunk) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __half h0, l0, h1, l1;
+                split_f16(val[8 * g + 2 * e] * inv_pT, h0, l0);
+                split_f16(val[8 * g + 2 * e + 1] * inv_pT, h1, l1);
+                __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+                hi[e] = *reinterpret_cast<uint32_t*>(&hh);
+                lo[e] = *reinterpret_cast<uint32_t*>(&ll);
+              }
+              reinterpret_cast<uint4*>(dhi)[g] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              reinterpret_cast<uint4*>(dlo)[g] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb0 + j < p.Nb) {
+                __half h0, l0;
+                split_f16(val[j] * inv_pT, h0, l0);
+                dhi[j] = h0; dlo[j] = l0;
+              }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tempty_bar[acc]);           // 128 arrivals release the accumulator
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps
+// ------------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  });
+  return fn;
+}
+
+// fp16 [rows, cols] row-major with leading dimension ld (elements); box = [box_rows, 64], 128B swizzle
+bool make_tmap_f16(CUtensorMap* tm, const void* base, int rows, int cols, int ld, int box_rows) {
+  auto enc = get_encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+bool tc_gemm_supported(int Ma, int Nb, int K, int lda, int ldb) {
+  // TMA: 16-byte aligned row pitch; everything else (ragged Ma/Nb/K) is handled by OOB zero fill + masks
+  return Ma > 0 && Nb > 0 && K > 0 && (lda % 8 == 0) && (ldb % 8 == 0) && lda >= K && ldb >= K;
+}
+
+int tc_gemm_launch(const TcGemmParams& p, int num_sms, cudaStream_t stream) {
+  if (!tc_gemm_supported(p.Ma, p.Nb, p.K, p.lda, p.ldb)) return -1000;
+  if ((reinterpret_cast<uintptr_t>(p.a_hi) | reinterpret_cast<uintptr_t>(p.b) |
+       reinterpret_cast<uintptr_t>(p.a_lo)) & 15) return -1000;
+  if (p.sample && p.U == nullptr && (p.rng.row_offset & 3u)) return -1000;
+  if (p.out_sT16 && ((p.ldsT % 8) || (reinterpret_cast<uintptr_t>(p.out_sT16) & 15))) return -1000;
+  if (p.out_pT_hi && ((p.ldpT % 8) || (reinterpret_cast<uintptr_t>(p.out_pT_hi) & 15) ||
+                      (reinterpret_cast<uintptr_t>(p.out_pT_lo) & 15))) return -1000;
+
+  CUtensorMap tm_a_hi, tm_a_lo, tm_b;
+  if (!make_tmap_f16(&tm_a_hi, p.a_hi, p.Ma, p.K, p.lda, BLOCK_M)) return -1001;
+  if (!make_tmap_f16(&tm_a_lo, p.a_lo ? p.a_lo : p.a_hi, p.Ma, p.K, p.lda, BLOCK_M)) return -1001;
+  if (!make_tmap_f16(&tm_b, p.b, p.Nb, p.K, p.ldb, BLOCK_N)) return -1001;
+
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+  });
+  if (attr_err != cudaSuccess) return (int)attr_err;
+
+  const int tiles = ((p.Ma + BLOCK_M - 1) / BLOCK_M) * ((p.Nb + BLOCK_N - 1) / BLOCK_N);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  tc_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_a_hi, tm_a_lo, tm_b, p);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace db

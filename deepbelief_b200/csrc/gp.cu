@@ -1,0 +1,723 @@
+// GP path: RBF Gram (K3), blocked Cholesky (K4), triangular solves / inverse (K5) and the fused
+// log-marginal-likelihood + analytic gradient (K6) behind gplvm.py:61-86, 210-288 and gprbm.py:193-245.
+// All fp32 SIMT; nothing here calls cuBLAS / cuSOLVER.
+//
+// Pipeline of one LML+gradient evaluation (N points, D outputs, Q latent dims):
+//   hyp      = softplus(opt) (+ jitter)                                    gplvm.py:39,49,152,219-221
+//   K        = alpha * exp(-|xi-xj|^2 / (2 gamma^2)) + noise * I           gplvm.py:61-86, 218-224
+//   L        = chol(K)           right-looking, 64-wide panels             gplvm.py:212
+//   Linv     = L^-1              recursive block inversion (log-depth, batched GEMMs)
+//   S        = Linv Y ; |S|^2 ; logdet = 2 sum log Lii                     gplvm.py:226-236
+//   A        = Linv^T S = K^-1 Y
+//   G        = 0.5 (D Linv^T Linv - A A^T), W = G o K_f  -> dX, d alpha, d gamma, d noise, all in ONE
+//              kernel over the lower tile pairs; neither K^-1 nor G is ever written to HBM.
+// Algorithmic work: N^3 + 3 N^2 D FLOP (SURVEY.md §8 d).
+#include "context.h"
+#include "simt_gemm.cuh"
+
+namespace db {
+namespace {
+
+constexpr int NB = 64;          // Cholesky panel width / diagonal block size
+constexpr int MAXQ = 8;         // latent dimensionality supported by the fused gradient kernel
+
+// scalars accumulated on the device during one evaluation
+struct GpAccum {
+  float ssq;        // |L^-1 Y|_F^2
+  float logdet;     // 2 sum log Lii
+  float trG;        // tr G
+  float sumW;       // sum_ij G_ij Kf_ij
+  float sumWr2;     // sum_ij G_ij Kf_ij |xi-xj|^2
+  float xsq;        // |X|_F^2
+  float pad[2];
+};
+
+__global__ void effective_hyp_kernel(const float* __restrict__ opt, int flags, float fixed_noise, float jitter,
+                                     float* __restrict__ hyp) {
+  // alpha=False / gamma=False are the constant 1.0 (gplvm.py:31-32,41-42)
+  hyp[0] = (flags & 1) ? softplusf_(opt[0]) : 1.0f;
+  hyp[1] = (flags & 2) ? softplusf_(opt[1]) : 1.0f;
+  // jitter only when the noise variance is trainable (gplvm.py:141-152,219-221)
+  hyp[2] = (flags & 4) ? softplusf_(opt[2]) + jitter : fixed_noise;
+}
+
+// ---- K3: Gram -------------------------------------------------------------------------------------
+// 32 x 256 tile per CTA; thread = 4 consecutive columns x 8 rows -> 16-byte coalesced stores.
+// Squared distances use the difference form (exact 0 on the diagonal; the reference's expanded form
+// gplvm.py:67-82 leaves +-2e-6 there in fp32, SURVEY.md §7 hard part 3).
+__global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, const float* __restrict__ Y, int N, int M,
+                                                   int Q, const float* __restrict__ hyp, int add_noise,
+                                                   float* __restrict__ out, int ldo) {
+  extern __shared__ float gsm[];
+  float* xs = gsm;                 // [32][Q]
+  float* ys = gsm + 32 * Q;        // [256][Q]
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 256;
+  const float alpha = __ldg(hyp), inv_gamma = 1.0f / __ldg(hyp + 1), noise = __ldg(hyp + 2);
+  const float* Ysrc = Y ? Y : X;
+  for (int t = threadIdx.x; t < 32 * Q; t += 256) {
+    const int r = i0 + t / Q;
+    xs[t] = r < N ? __ldg(X + (size_t)r * Q + t % Q) * inv_gamma : 0.0f;
+  }
+  for (int t = threadIdx.x; t < 256 * Q; t += 256) {
+    const int r = j0 + t / Q;
+    ys[t] = r < M ? __ldg(Ysrc + (size_t)r * Q + t % Q) * inv_gamma : 0.0f;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int j = j0 + 4 * tx;
+  if (j >= M) return;
+#pragma unroll 1
+  for (int rr = 0; rr < 8; ++rr) {
+    const int il = ty + 4 * rr, i = i0 + il;
+    if (i >= N) break;
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int q = 0; q < Q; ++q) {
+      const float xv = xs[il * Q + q];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float t = xv - ys[(4 * tx + e) * Q + q]; d[e] = fmaf(t, t, d[e]); }
+    }
+    float kv[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      kv[e] = alpha * __expf(-0.5f * d[e]);
+      if (add_noise && Y == nullptr && i == j + e) kv[e] += noise;
+    }
+    float* o = out + (size_t)i * ldo + j;
+    if (j + 3 < M && (ldo % 4 == 0)) {
+      *reinterpret_cast<float4*>(o) = make_float4(kv[0], kv[1], kv[2], kv[3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) if (j + e < M) o[e] = kv[e];
+    }
+  }
+}
+
+// ---- K4: Cholesky ---------------------------------------------------------------------------------
+// factorise the nb x nb block held in shared memory (row-major, pitch NB+1); returns failing column+1 or 0
+__device__ int potrf_block_smem(float (*D)[NB + 1], int nb) {
+  __shared__ int s_fail;
+  if (threadIdx.x == 0) s_fail = 0;
+  __syncthreads();
+  for (int c = 0; c < nb; ++c) {
+    if (threadIdx.x == 0) {
+      const float d = D[c][c];
+      if (!(d > 0.0f) && s_fail == 0) s_fail = c + 1;
+      D[c][c] = sqrtf(d);
+    }
+    __syncthreads();
+    const float inv = 1.0f / D[c][c];
+    for (int r = c + 1 + threadIdx.x; r < nb; r += blockDim.x) D[r][c] *= inv;
+    __syncthreads();
+    // trailing update of the lower triangle: D[r][cc] -= D[r][c] * D[cc][c], c < cc <= r
+    const int rem = nb - c - 1;
+    for (int t = threadIdx.x; t < rem * rem; t += blockDim.x) {
+      const int r = c + 1 + t / rem, cc = c + 1 + t % rem;
+      if (cc <= r) D[r][cc] = fmaf(-D[r][c], D[cc][c], D[r][cc]);
+    }
+    __syncthreads();
+  }
+  return s_fail;
+}
+
+// Panel step j, kernel 1: factorise the diagonal block (one CTA).
+__global__ void __launch_bounds__(256) potrf_diag_kernel(float* __restrict__ A, int lda, int N, int j, int* __restrict__ info) {
+  __shared__ float D[NB][NB + 1];
+  const int nb = min(NB, N - j);
+  for (int t = threadIdx.x; t < NB * NB; t += 256) {
+    const int r = t / NB, c = t % NB;
+    D[r][c] = (r < nb && c <= r) ? A[(size_t)(j + r) * lda + j + c] : 0.0f;
+  }
+  __syncthreads();
+  const int fail = potrf_block_smem(D, nb);
+  for (int t = threadIdx.x; t < NB * NB; t += 256) {
+    const int r = t / NB, c = t % NB;
+    if (r < nb && c <= r) A[(size_t)(j + r) * lda + j + c] = D[r][c];
+  }
+  if (threadIdx.x == 0 && fail) atomicCAS(info, 0, j + fail);
+}
+// Panel step j, kernel 2: CTA b solves its 64 rows of the panel against the factorised block (X L^T = R).
+__global__ void __launch_bounds__(256) potrf_panel_kernel(float* __restrict__ A, int lda, int N, int j) {
+  __shared__ float D[NB][NB + 1];
+  __shared__ float R[NB][NB + 1];
+  const int nb = min(NB, N - j);
+  const int r0 = j + NB + blockIdx.x * NB;
+  const int nr = min(NB, N - r0);
+  for (int t = threadIdx.x; t < NB * NB; t += 256) {
+    const int r = t / NB, c = t % NB;
+    D[r][c] = (r < nb && c <= r) ? A[(size_t)(j + r) * lda + j + c] : 0.0f;
+    R[r][c] = (r < nr && c < nb) ? A[(size_t)(r0 + r) * lda + j + c] : 0.0f;
+  }
+  __syncthreads();
+  for (int c = 0; c < nb; ++c) {
+    const float inv = 1.0f / D[c][c];
+    for (int r = threadIdx.x; r < nr; r += 256) R[r][c] *= inv;
+    __syncthreads();
+    const int rem = nb - c - 1;
+    for (int t = threadIdx.x; t < nr * rem; t += 256) {
+      const int r = t / rem, cc = c + 1 + t % rem;
+      R[r][cc] = fmaf(-R[r][c], D[cc][c], R[r][cc]);
+    }
+    __syncthreads();
+  }
+  for (int t = threadIdx.x; t < NB * NB; t += 256) {
+    const int r = t / NB, c = t % NB;
+    if (r < nr && c < nb) A[(size_t)(r0 + r) * lda + j + c] = R[r][c];
+  }
+}
+
+// trailing update: C = A[j2:, j2:] (lower) -= P P^T with P = A[j2:, j:j+NB], j2 = j + NB
+struct LoadPanelA {
+  static constexpr bool k_contig = true;
+  const float* P; int lda; int rows;
+  __device__ __forceinline__ float operator()(int m, int k) const { return m < rows ? __ldg(P + (size_t)m * lda + k) : 0.0f; }
+};
+struct LoadPanelB {
+  static constexpr bool k_contig = true;
+  const float* P; int lda; int rows;
+  __device__ __forceinline__ float operator()(int k, int n) const { return n < rows ? __ldg(P + (size_t)n * lda + k) : 0.0f; }
+};
+__global__ void __launch_bounds__(256) syrk_update_kernel(float* __restrict__ A, int lda, int N, int j) {
+  using T = TileLarge;
+  if (blockIdx.x > blockIdx.y) return;          // lower tile pairs only
+  __shared__ typename T::Smem sm;
+  const int j2 = j + NB;
+  const int rows = N - j2;
+  const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
+  const float* P = A + (size_t)j2 * lda + j;
+  LoadPanelA a{P, lda, rows};
+  LoadPanelB b{P, lda, rows};
+  float acc[T::TM][T::TN];
+  simt_gemm_tile<T>(sm, a, b, m0, n0, 0, NB, acc);
+#pragma unroll
+  for (int i = 0; i < T::TM; ++i) {
+    const int m = simt_row<T>(m0, i);
+    if (m >= rows) continue;
+#pragma unroll
+    for (int jj = 0; jj < T::TN; ++jj) {
+      const int n = simt_col<T>(n0, jj);
+      if (n <= m) A[(size_t)(j2 + m) * lda + j2 + n] -= acc[i][jj];
+    }
+  }
+}
+
+// ---- K5: triangular solves ------------------------------------------------------------------------
+// diagonal-block solve of the blocked substitution: B_i <- L_ii^-1 B_i (trans=0) or L_ii^-T B_i (trans=1)
+__global__ void __launch_bounds__(256) trsm_diag_kernel(const float* __restrict__ L, int ldl, int N, int i0, float* __restrict__ B,
+                                                        int ldb, int nrhs, int trans) {
+  __shared__ float D[NB][NB + 1];
+  const int nb = min(NB, N - i0);
+  for (int t = threadIdx.x; t < NB * NB; t += 256) {
+    const int r = t / NB, c = t % NB;
+    D[r][c] = (r < nb && c <= r) ? __ldg(L + (size_t)(i0 + r) * ldl + i0 + c) : 0.0f;
+  }
+  __syncthreads();
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col >= nrhs) return;
+  float x[NB];
+  if (!trans) {
+#pragma unroll 1
+    for (int r = 0; r < nb; ++r) {
+      float s = B[(size_t)(i0 + r) * ldb + col];
+      for (int k = 0; k < r; ++k) s = fmaf(-D[r][k], x[k], s);
+      x[r] = s / D[r][r];
+    }
+  } else {
+#pragma unroll 1
+    for (int r = nb - 1; r >= 0; --r) {
+      float s = B[(size_t)(i0 + r) * ldb + col];
+      for (int k = r + 1; k < nb; ++k) s = fmaf(-D[k][r], x[k], s);
+      x[r] = s / D[r][r];
+    }
+  }
+  for (int r = 0; r < nb; ++r) B[(size_t)(i0 + r) * ldb + col] = x[r];
+}
+// B[rows] -= Lblk * B_i : trans=0 rows below block i use L[rows, i]; trans=1 rows above use L[i, rows]^T
+struct LoadTrsmA {
+  const float* L; int ldl; int trans; int r0, i0, nrows, nb;
+  static constexpr bool k_contig = true;   // exact only for trans=0; correctness does not depend on it
+  __device__ __forceinline__ float operator()(int m, int k) const {
+    if (m >= nrows || k >= nb) return 0.0f;
+    return trans ? __ldg(L + (size_t)(i0 + k) * ldl + r0 + m) : __ldg(L + (size_t)(r0 + m) * ldl + i0 + k);
+  }
+};
+struct LoadTrsmB {
+  const float* B; int ldb; int i0, nb, nrhs;
+  static constexpr bool k_contig = false;
+  __device__ __forceinline__ float operator()(int k, int n) const {
+    return (k < nb && n < nrhs) ? B[(size_t)(i0 + k) * ldb + n] : 0.0f;
+  }
+};
+__global__ void __launch_bounds__(256) trsm_update_kernel(const float* __restrict__ L, int ldl, int i0, int nb, int r0, int nrows,
+                                                          float* __restrict__ B, int ldb, int nrhs, int trans) {
+  using T = TileSmall;
+  __shared__ typename T::Smem sm;
+  const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
+  LoadTrsmA a{L, ldl, trans, r0, i0, nrows, nb};
+  LoadTrsmB b{B, ldb, i0, nb, nrhs};
+  float acc[T::TM][T::TN];
+  simt_gemm_tile<T>(sm, a, b, m0, n0, 0, nb, acc);
+#pragma unroll
+  for (int i = 0; i < T::TM; ++i) {
+    const int m = simt_row<T>(m0, i);
+    if (m >= nrows) continue;
+#pragma unroll
+    for (int jj = 0; jj < T::TN; ++jj) {
+      const int n = simt_col<T>(n0, jj);
+      if (n < nrhs) B[(size_t)(r0 + m) * ldb + n] -= acc[i][jj];
+    }
+  }
+}
+
+// ---- triangular inverse ---------------------------------------------------------------------------
+// level 0: invert every 64x64 diagonal block (one CTA each; thread c solves column c of L_bb X = I)
+__global__ void __launch_bounds__(64) trinv_diag_kernel(const float* __restrict__ L, int ldl, int N, float* __restrict__ Li, int ldi) {
+  __shared__ float D[NB][NB + 1];
+  const int i0 = blockIdx.x * NB;
+  const int nb = min(NB, N - i0);
+  for (int t = threadIdx.x; t < NB * NB; t += 64) {
+    const int r = t / NB, c = t % NB;
+    D[r][c] = (r < nb && c <= r) ? __ldg(L + (size_t)(i0 + r) * ldl + i0 + c) : 0.0f;
+  }
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (c >= nb) return;
+  float x[NB];
+#pragma unroll 1
+  for (int r = c; r < nb; ++r) {
+    float s = (r == c) ? 1.0f : 0.0f;
+    for (int k = c; k < r; ++k) s = fmaf(-D[r][k], x[k], s);
+    x[r] = s / D[r][r];
+  }
+  for (int r = c; r < nb; ++r) Li[(size_t)(i0 + r) * ldi + i0 + c] = x[r];
+}
+// level with half-size s: for pair p, rows R = [(2p+1)s, min(N,(2p+2)s)), cols C = [2ps, (2p+1)s):
+//   T = L[R, C] * Linv[C, C]          (Linv[C,C] lower triangular: k >= column)
+//   Linv[R, C] = -Linv[R, R] * T      (Linv[R,R] lower triangular: k <= row)
+struct LoadMat {      // element (m,k) of a row-major sub-matrix
+  static constexpr bool k_contig = true;
+  const float* P; int ld; int rows, cols;
+  __device__ __forceinline__ float operator()(int m, int k) const { return (m < rows && k < cols) ? __ldg(P + (size_t)m * ld + k) : 0.0f; }
+};
+struct LoadMatB {     // element (k,n) of a row-major sub-matrix
+  static constexpr bool k_contig = false;
+  const float* P; int ld; int rows, cols;
+  __device__ __forceinline__ float operator()(int k, int n) const { return (k < rows && n < cols) ? __ldg(P + (size_t)k * ld + n) : 0.0f; }
+};
+template <int STEP>
+__global__ void __launch_bounds__(256) trinv_level_kernel(const float* __restrict__ L, int ldl, int N, int s, float* __restrict__ Li,
+                                                          int ldi, float* __restrict__ Tmp, int ldt) {
+  using T = TileSmall;
+  __shared__ typename T::Smem sm;
+  const int p = blockIdx.z;
+  const int c0 = 2 * p * s, r0 = c0 + s;
+  if (r0 >= N) return;
+  const int nr = min(s, N - r0);
+  const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
+  if (m0 >= nr || n0 >= s) return;
+  float acc[T::TM][T::TN];
+  if (STEP == 0) {
+    LoadMat a{L + (size_t)r0 * ldl + c0, ldl, nr, s};
+    LoadMatB b{Li + (size_t)c0 * ldi + c0, ldi, s, s};
+    simt_gemm_tile<T>(sm, a, b, m0, n0, n0 /*k >= first column of the tile*/, s, acc);
+  } else {
+    LoadMat a{Li + (size_t)r0 * ldi + r0, ldi, nr, nr};
+    LoadMatB b{Tmp + (size_t)r0 * ldt + c0, ldt, nr, s};
+    simt_gemm_tile<T>(sm, a, b, m0, n0, 0, min(nr, m0 + T::BM) /*k <= last row of the tile*/, acc);
+  }
+#pragma unroll
+  for (int i = 0; i < T::TM; ++i) {
+    const int m = simt_row<T>(m0, i);
+    if (m >= nr) continue;
+#pragma unroll
+    for (int jj = 0; jj < T::TN; ++jj) {
+      const int n = simt_col<T>(n0, jj);
+      if (n >= s) continue;
+      if (STEP == 0) Tmp[(size_t)(r0 + m) * ldt + c0 + n] = acc[i][jj];
+      else Li[(size_t)(r0 + m) * ldi + c0 + n] = -acc[i][jj];
+    }
+  }
+}
+
+// ---- triangular products with Linv ------------------------------------------------------------------
+// out = Linv * B (trans=0, k <= row) or Linv^T * B (trans=1, k >= row); optional sum of squares of out
+template <int TRANS>
+struct LoadLinvA {
+  static constexpr bool k_contig = (TRANS == 0);
+  const float* Li; int ldi; int N;
+  __device__ __forceinline__ float operator()(int m, int k) const {
+    if (m >= N || k >= N) return 0.0f;
+    return TRANS ? __ldg(Li + (size_t)k * ldi + m) : __ldg(Li + (size_t)m * ldi + k);
+  }
+};
+template <int TRANS, class T>
+__global__ void __launch_bounds__(256) trmm_kernel(const float* __restrict__ Li, int ldi, int N, const float* __restrict__ B, int ldb,
+                                                   int nrhs, float* __restrict__ out, int ldo, float* __restrict__ ssq) {
+  __shared__ typename T::Smem sm;
+  __shared__ float red[8];
+  const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
+  LoadLinvA<TRANS> a{Li, ldi, N};
+  LoadMatB b{B, ldb, N, nrhs};
+  float acc[T::TM][T::TN];
+  const int kb = TRANS ? m0 : 0;
+  const int ke = TRANS ? N : min(N, m0 + T::BM);
+  simt_gemm_tile<T>(sm, a, b, m0, n0, kb, ke, acc);
+  float local = 0.0f;
+#pragma unroll
+  for (int i = 0; i < T::TM; ++i) {
+    const int m = simt_row<T>(m0, i);
+    if (m >= N) continue;
+#pragma unroll
+    for (int jj = 0; jj < T::TN; ++jj) {
+      const int n = simt_col<T>(n0, jj);
+      if (n < nrhs) { out[(size_t)m * ldo + n] = acc[i][jj]; local = fmaf(acc[i][jj], acc[i][jj], local); }
+    }
+  }
+  if (ssq != nullptr) {
+    local = warp_sum(local);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.0f;
+      for (int w = 0; w < 8; ++w) t += red[w];
+      atomicAdd(ssq, t);
+    }
+  }
+}
+
+__global__ void logdet_xsq_kernel(const float* __restrict__ L, int ldl, int N, const float* __restrict__ X, int nx, GpAccum* acc) {
+  float s = 0.0f, x2 = 0.0f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s += logf(__ldg(L + (size_t)i * ldl + i));
+  for (int i = threadIdx.x; i < nx; i += blockDim.x) { const float v = __ldg(X + i); x2 = fmaf(v, v, x2); }
+  __shared__ float r1[32], r2[32];
+  s = warp_sum(s); x2 = warp_sum(x2);
+  if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = s; r2[threadIdx.x >> 5] = x2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.0f, b = 0.0f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += r1[w]; b += r2[w]; }
+    acc->logdet = 2.0f * a;      // gplvm.py:226-228
+    acc->xsq = b;
+  }
+}
+
+// ---- K6: fused gradient -------------------------------------------------------------------------------
+// Tile (I >= J) of G = 0.5 (D * Linv^T Linv - A A^T), multiplied by K_f on the fly, reduced into
+// dX (atomics), tr G, sum W, sum W r^2.   
+struct LoadLinvT_A {   // a(m,k) = (D/2) * Linv[k, m]
+  static constexpr bool k_contig = false;
+  const float* Li; int ldi; int N; float scale;
+  __device__ __forceinline__ float operator()(int m, int k) const { return (m < N && k < N) ? scale * __ldg(Li + (size_t)k * ldi + m) : 0.0f; }
+};
+struct LoadLinvT_B {   // b(k,n) = Linv[k, n]
+  static constexpr bool k_contig = false;
+  const float* Li; int ldi; int N;
+  __device__ __forceinline__ float operator()(int k, int n) const { return (n < N && k < N) ? __ldg(Li + (size_t)k * ldi + n) : 0.0f; }
+};
+struct LoadA_A {       // a(m,k) = -0.5 * Avec[m, k]
+  static constexpr bool k_contig = true;
+  const float* A; int ld; int N, D;
+  __device__ __forceinline__ float operator()(int m, int k) const { return (m < N && k < D) ? -0.5f * __ldg(A + (size_t)m * ld + k) : 0.0f; }
+};
+struct LoadA_B {       // b(k,n) = Avec[n, k]
+  static constexpr bool k_contig = true;
+  const float* A; int ld; int N, D;
+  __device__ __forceinline__ float operator()(int k, int n) const { return (n < N && k < D) ? __ldg(A + (size_t)n * ld + k) : 0.0f; }
+};
+
+__global__ void __launch_bounds__(256) gp_grad_kernel(const float* __restrict__ Li, int ldi, const float* __restrict__ Av, int lda,
+                                                      const float* __restrict__ X, int N, int Q, int D,
+                                                      const float* __restrict__ hyp, float* __restrict__ dXacc, GpAccum* accum) {
+  using T = TileLarge;
+  if (blockIdx.x > blockIdx.y) return;
+  __shared__ typename T::Smem sm;
+  __shared__ float rowacc[T::BM][MAXQ];
+  __shared__ float colacc[T::BN][MAXQ];
+  __shared__ float red[3][8];
+  const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
+  const bool diag_tile = blockIdx.x == blockIdx.y;
+  for (int t = threadIdx.x; t < T::BM * MAXQ; t += 256) { (&rowacc[0][0])[t] = 0.0f; (&colacc[0][0])[t] = 0.0f; }
+
+  float gacc[T::TM][T::TN];   // G tile = (D/2) Linv^T Linv - (1/2) A A^T, one accumulator for both products
+  {
+    LoadLinvT_A a{Li, ldi, N, 0.5f * (float)D};
+    LoadLinvT_B b{Li, ldi, N};
+    simt_gemm_tile<T>(sm, a, b, m0, n0, m0 /* Linv[k,i] = 0 for k < i and i >= m0 */, N, gacc);
+  }
+  __syncthreads();
+  {
+    LoadA_A a{Av, lda, N, D};
+    LoadA_B b{Av, lda, N, D};
+    simt_gemm_tile<T, LoadA_A, LoadA_B, false>(sm, a, b, m0, n0, 0, D, gacc);
+  }
+  const float alpha = __ldg(hyp), inv_g2 = 1.0f / (__ldg(hyp + 1) * __ldg(hyp + 1));
+  float trg = 0.0f, sw = 0.0f, swr = 0.0f;
+#pragma unroll
+  for (int i = 0; i < T::TM; ++i) {
+    const int m = simt_row<T>(m0, i);
+    if (m >= N) continue;
+    float xm[MAXQ];
+    for (int q = 0; q < Q; ++q) xm[q] = __ldg(X + (size_t)m * Q + q);
+#pragma unroll
+    for (int jj = 0; jj < T::TN; ++jj) {
+      const int n = simt_col<T>(n0, jj);
+      if (n >= N || (diag_tile && n > m)) continue;
+      const float g = gacc[i][jj];
+      if (m == n) { trg += g; sw += g * alpha; continue; }   // Kf_ii = alpha, r = 0: no dX contribution
+      float r2 = 0.0f, df[MAXQ];
+      for (int q = 0; q < Q; ++q) { df[q] = xm[q] - __ldg(X + (size_t)n * Q + q); r2 = fmaf(df[q], df[q], r2); }
+      const float w = g * alpha * __expf(-0.5f * r2 * inv_g2);
+      sw += 2.0f * w; swr += 2.0f * w * r2;                  // (i,j) and (j,i)
+      for (int q = 0; q < Q; ++q) {
+        atomicAdd(&rowacc[m - m0][q], w * df[q]);
+        atomicAdd(&colacc[n - n0][q], -w * df[q]);
+      }
+    }
+  }
+  __syncthreads();
+  // dX_i = -(2/gamma^2) sum_j W_ij (x_i - x_j); each unordered pair was visited once -> both rows updated
+  const float sc = -2.0f * inv_g2;
+  for (int t = threadIdx.x; t < T::BM * Q; t += 256) {
+    const int r = t / Q, q = t % Q;
+    if (m0 + r < N) atomicAdd(dXacc + (size_t)(m0 + r) * Q + q, sc * rowacc[r][q]);
+    if (n0 + r < N) atomicAdd(dXacc + (size_t)(n0 + r) * Q + q, sc * colacc[r][q]);
+  }
+  trg = warp_sum(trg); sw = warp_sum(sw); swr = warp_sum(swr);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = trg; red[1][threadIdx.x >> 5] = sw; red[2][threadIdx.x >> 5] = swr; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f, c = 0.f;
+    for (int w = 0; w < 8; ++w) { a += red[0][w]; b += red[1][w]; c += red[2][w]; }
+    atomicAdd(&accum->trG, a); atomicAdd(&accum->sumW, b); atomicAdd(&accum->sumWr2, c);
+  }
+}
+
+// scalars + prior term of dX
+__global__ void gp_finalize_kernel(const GpAccum* __restrict__ acc, const float* __restrict__ hyp, const float* __restrict__ opt,
+                                   int flags, int N, int Q, int D, float x_prior_w, int include_const, int want_grad,
+                                   const float* __restrict__ X, const float* __restrict__ dXacc, float* __restrict__ dX,
+                                   float* __restrict__ out) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (want_grad && dX != nullptr)
+    for (int i = tid; i < N * Q; i += gridDim.x * blockDim.x) dX[i] = dXacc[i] + 2.0f * x_prior_w * __ldg(X + i);
+  if (tid == 0) {
+    const float alpha = hyp[0], gamma = hyp[1];
+    float loss = 0.5f * (acc->ssq + (float)D * acc->logdet);
+    if (include_const) loss += 0.5f * (float)((double)D * (double)N * 1.8378770664093453);   // D N log(2 pi), gplvm.py:238
+    loss += x_prior_w * acc->xsq;                                                          // gprbm.py:242
+    out[0] = loss; out[1] = acc->logdet; out[2] = acc->ssq;
+    out[3] = (flags & 1) ? (acc->sumW / alpha) * sigmoidf_(opt[0]) : 0.0f;
+    out[4] = (flags & 2) ? (acc->sumWr2 / (gamma * gamma * gamma)) * sigmoidf_(opt[1]) : 0.0f;
+    out[5] = (flags & 4) ? acc->trG * sigmoidf_(opt[2]) : 0.0f;
+    out[6] = alpha; out[7] = hyp[2];
+  }
+}
+
+// predictive variance: var[m] = alpha - sum_k V1[k,m]^2 ; flags the first negative entry (gplvm.py:283-286)
+__global__ void pred_var_kernel(const float* __restrict__ V1, int N, int M, const float* __restrict__ hyp, float* __restrict__ var,
+                                int* __restrict__ info) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float s = 0.0f;
+  for (int k = 0; k < N; ++k) { const float v = __ldg(V1 + (size_t)k * M + m); s = fmaf(v, v, s); }
+  const float pv = __ldg(hyp) - s;
+  var[m] = pv;
+  if (pv < 0.0f && info) atomicCAS(info, 0, m + 1);
+}
+// mean[m,d] = sum_k V1[k,m] S[k,d] + y_mean[d]
+struct LoadV1T {
+  static constexpr bool k_contig = false;
+  const float* V1; int N, M;
+  __device__ __forceinline__ float operator()(int m, int k) const { return (m < M && k < N) ? __ldg(V1 + (size_t)k * M + m) : 0.0f; }
+};
+__global__ void __launch_bounds__(256) pred_mean_kernel(const float* __restrict__ V1, const float* __restrict__ S, int N, int M, int D,
+                                                        const float* __restrict__ y_mean, float* __restrict__ mean) {
+  using T = TileSmall;
+  __shared__ typename T::Smem sm;
+  const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
+  LoadV1T a{V1, N, M};
+  LoadMatB b{S, D, N, D};
+  float acc[T::TM][T::TN];
+  simt_gemm_tile<T>(sm, a, b, m0, n0, 0, N, acc);
+#pragma unroll
+  for (int i = 0; i < T::TM; ++i) {
+    const int m = simt_row<T>(m0, i);
+    if (m >= M) continue;
+#pragma unroll
+    for (int jj = 0; jj < T::TN; ++jj) {
+      const int n = simt_col<T>(n0, jj);
+      if (n < D) mean[(size_t)m * D + n] = acc[i][jj] + (y_mean ? __ldg(y_mean + n) : 0.0f);
+    }
+  }
+}
+
+// ---- host-side building blocks -----------------------------------------------------------------------
+int run_gram(db_handle_t h, cudaStream_t st, const float* X, const float* Y, int N, int M, int Q, const float* hyp,
+             int add_noise, float* out, int ldo) {
+  dim3 grid((M + 255) / 256, (N + 31) / 32);
+  gram_kernel<<<grid, 256, sizeof(float) * 288 * Q, st>>>(X, Y, N, M, Q, hyp, add_noise, out, ldo);
+  return check_launch(h, "gram_rbf");
+}
+
+int run_potrf(db_handle_t h, cudaStream_t st, float* A, int lda, int N, int* info) {
+  cudaMemsetAsync(info, 0, sizeof(int), st);
+  for (int j = 0; j < N; j += NB) {
+    const int below = N - j - NB;
+    potrf_diag_kernel<<<1, 256, 0, st>>>(A, lda, N, j, info);
+    if (below > 0) {
+      potrf_panel_kernel<<<(below + NB - 1) / NB, 256, 0, st>>>(A, lda, N, j);
+      const int tiles = (below + TileLarge::BM - 1) / TileLarge::BM;
+      syrk_update_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(A, lda, N, j);
+    }
+  }
+  return check_launch(h, "potrf_lower");
+}
+
+int run_trinv(db_handle_t h, cudaStream_t st, const float* L, int ldl, int N, float* Li, float* Tmp) {
+  cudaMemsetAsync(Li, 0, sizeof(float) * (size_t)N * N, st);
+  const int nblk = (N + NB - 1) / NB;
+  trinv_diag_kernel<<<nblk, 64, 0, st>>>(L, ldl, N, Li, N);
+  for (int s = NB; s < N; s *= 2) {
+    const int pairs = (N + 2 * s - 1) / (2 * s);
+    dim3 grid((s + TileSmall::BN - 1) / TileSmall::BN, (s + TileSmall::BM - 1) / TileSmall::BM, pairs);
+    trinv_level_kernel<0><<<grid, 256, 0, st>>>(L, ldl, N, s, Li, N, Tmp, N);
+    trinv_level_kernel<1><<<grid, 256, 0, st>>>(L, ldl, N, s, Li, N, Tmp, N);
+  }
+  return check_launch(h, "trinv_lower");
+}
+
+template <int TRANS>
+int run_trmm(db_handle_t h, cudaStream_t st, const float* Li, int N, const float* B, int ldb, int nrhs, float* out, int ldo,
+             float* ssq) {
+  if (nrhs >= 256) {
+    using T = TileLarge;
+    dim3 grid((nrhs + T::BN - 1) / T::BN, (N + T::BM - 1) / T::BM);
+    trmm_kernel<TRANS, T><<<grid, 256, 0, st>>>(Li, N, N, B, ldb, nrhs, out, ldo, ssq);
+  } else {
+    using T = TileSmall;
+    dim3 grid((nrhs + T::BN - 1) / T::BN, (N + T::BM - 1) / T::BM);
+    trmm_kernel<TRANS, T><<<grid, 256, 0, st>>>(Li, N, N, B, ldb, nrhs, out, ldo, ssq);
+  }
+  return check_launch(h, "trmm");
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct GplvmWorkspace {
+  float *K, *Li, *Tmp, *S, *Av, *dXacc, *hyp;
+  GpAccum* acc;
+  size_t bytes;
+};
+GplvmWorkspace gplvm_workspace(void* ws, int N, int Q, int D) {
+  GplvmWorkspace w;
+  uint8_t* p = static_cast<uint8_t*>(ws);
+  uint8_t* p0 = p;
+  const size_t nn = align256(sizeof(float) * (size_t)N * N), nd = align256(sizeof(float) * (size_t)N * D);
+  w.K = reinterpret_cast<float*>(p); p += nn;
+  w.Li = reinterpret_cast<float*>(p); p += nn;
+  w.Tmp = reinterpret_cast<float*>(p); p += nn;
+  w.S = reinterpret_cast<float*>(p); p += nd;
+  w.Av = reinterpret_cast<float*>(p); p += nd;
+  w.dXacc = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)N * Q);
+  w.hyp = reinterpret_cast<float*>(p); p += 256;
+  w.acc = reinterpret_cast<GpAccum*>(p); p += 256;
+  w.bytes = (size_t)(p - p0);
+  return w;
+}
+
+}  // namespace
+}  // namespace db
+
+using namespace db;
+
+extern "C" int db_gp_effective_hyp(db_handle_t h, db_stream_t stream, const float* hyp_opt, int flags, float fixed_noise,
+                                   float jitter, float* hyp_out) {
+  DB_REQUIRE(h, hyp_opt && hyp_out, "null operand");
+  effective_hyp_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyp_opt, flags, fixed_noise, jitter, hyp_out);
+  return check_launch(h, "gp_effective_hyp");
+}
+
+extern "C" int db_gram_rbf(db_handle_t h, db_stream_t stream, const float* X, const float* Y, int N, int M, int Q,
+                           const float* hyp, int add_noise, float* out, int ldo) {
+  DB_REQUIRE(h, X && hyp && out && N > 0 && M > 0 && Q > 0 && ldo >= M, "null operand or bad shape");
+  DB_REQUIRE(h, Y != nullptr || M == N, "K(X) needs M == N");
+  DB_REQUIRE(h, Q <= 40, "latent dimensionality above 40 is not supported");
+  return run_gram(h, (cudaStream_t)stream, X, Y, N, M, Q, hyp, add_noise, out, ldo);
+}
+
+extern "C" int db_potrf_lower(db_handle_t h, db_stream_t stream, float* A, int lda, int N, int* info) {
+  DB_REQUIRE(h, A && info && N > 0 && lda >= N, "null operand or bad shape");
+  return run_potrf(h, (cudaStream_t)stream, A, lda, N, info);
+}
+
+extern "C" int db_trsm_lower(db_handle_t h, db_stream_t stream, const float* L, int ldl, int N, float* B, int ldb, int nrhs,
+                             int trans) {
+  DB_REQUIRE(h, L && B && N > 0 && nrhs > 0 && ldl >= N && ldb >= nrhs, "null operand or bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblk = (N + NB - 1) / NB;
+  for (int bi = 0; bi < nblk; ++bi) {
+    const int blk = trans ? nblk - 1 - bi : bi;
+    const int i0 = blk * NB, nb = N - i0 < NB ? N - i0 : NB;
+    trsm_diag_kernel<<<(nrhs + 255) / 256, 256, 0, st>>>(L, ldl, N, i0, B, ldb, nrhs, trans);
+    const int r0 = trans ? 0 : i0 + nb;
+    const int nrows = trans ? i0 : N - r0;
+    if (nrows > 0) {
+      dim3 grid((nrhs + TileSmall::BN - 1) / TileSmall::BN, (nrows + TileSmall::BM - 1) / TileSmall::BM);
+      trsm_update_kernel<<<grid, 256, 0, st>>>(L, ldl, i0, nb, r0, nrows, B, ldb, nrhs, trans);
+    }
+  }
+  return check_launch(h, "trsm_lower");
+}
+
+extern "C" size_t db_gplvm_workspace_bytes(int N, int Q, int D) {
+  if (N <= 0 || Q <= 0 || D <= 0) return 0;
+  return gplvm_workspace(nullptr, N, Q, D).bytes;
+}
+
+extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float* X, const float* Y, int N, int Q, int D,
+                                 const float* hyp_opt, int flags, float fixed_noise, float jitter, float x_prior_weight,
+                                 int include_const, int want_grad, void* workspace, float* out_scalars, float* dX,
+                                 float* L_out, int* info) {
+  DB_REQUIRE(h, X && Y && hyp_opt && workspace && out_scalars && info, "null operand");
+  DB_REQUIRE(h, N > 1 && Q > 0 && D > 0, "bad shape");
+  DB_REQUIRE(h, Q <= MAXQ, "latent dimensionality above 8 is not supported by the fused gradient");
+  DB_REQUIRE(h, !want_grad || dX, "dX required when want_grad");
+  cudaStream_t st = (cudaStream_t)stream;
+  GplvmWorkspace w = gplvm_workspace(workspace, N, Q, D);
+  int rc;
+  effective_hyp_kernel<<<1, 1, 0, st>>>(hyp_opt, flags, fixed_noise, jitter, w.hyp);
+  cudaMemsetAsync(w.acc, 0, sizeof(GpAccum), st);
+  if ((rc = run_gram(h, st, X, nullptr, N, N, Q, w.hyp, 1, w.K, N))) return rc;
+  if ((rc = run_potrf(h, st, w.K, N, N, info))) return rc;
+  if (L_out) cudaMemcpyAsync(L_out, w.K, sizeof(float) * (size_t)N * N, cudaMemcpyDeviceToDevice, st);
+  logdet_xsq_kernel<<<1, 1024, 0, st>>>(w.K, N, N, X, N * Q, w.acc);
+  if ((rc = run_trinv(h, st, w.K, N, N, w.Li, w.Tmp))) return rc;
+  if ((rc = run_trmm<0>(h, st, w.Li, N, Y, D, D, w.S, D, &w.acc->ssq))) return rc;
+  if (want_grad) {
+    if ((rc = run_trmm<1>(h, st, w.Li, N, w.S, D, D, w.Av, D, nullptr))) return rc;
+    cudaMemsetAsync(w.dXacc, 0, sizeof(float) * (size_t)N * Q, st);
+    const int tiles = (N + TileLarge::BM - 1) / TileLarge::BM;
+    gp_grad_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(w.Li, N, w.Av, D, X, N, Q, D, w.hyp, w.dXacc, w.acc);
+  }
+  gp_finalize_kernel<<<(N * Q + 255) / 256, 256, 0, st>>>(w.acc, w.hyp, hyp_opt, flags, N, Q, D, x_prior_weight, include_const,
+                                                       want_grad, X, w.dXacc, dX, out_scalars);
+  return check_launch(h, "gplvm_lml_grad");
+}
+
+extern "C" int db_gp_predict(db_handle_t h, db_stream_t stream, const float* X, const float* L, const float* S,
+                             const float* y_mean, const float* xstar, int N, int Q, int D, int M, const float* hyp,
+                             float* workspace, float* mean, float* var, int* info) {
+  DB_REQUIRE(h, X && L && xstar && hyp && workspace && N > 0 && Q > 0 && M > 0, "null operand or bad shape");
+  DB_REQUIRE(h, mean == nullptr || (S != nullptr && D > 0), "mean needs S = L^-1 Y");
+  DB_REQUIRE(h, mean || var, "no output requested");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (info) cudaMemsetAsync(info, 0, sizeof(int), st);
+  if ((rc = run_gram(h, st, X, xstar, N, M, Q, hyp, 0, workspace, M))) return rc;   // K_Xx [N,M]
+  if ((rc = db_trsm_lower(h, stream, L, N, N, workspace, M, M, 0))) return rc;      // V1 = L^-1 K_Xx
+  if (var) pred_var_kernel<<<(M + 127) / 128, 128, 0, st>>>(workspace, N, M, hyp, var, info);
+  if (mean) {
+    dim3 grid((D + TileSmall::BN - 1) / TileSmall::BN, (M + TileSmall::BM - 1) / TileSmall::BM);
+    pred_mean_kernel<<<grid, 256, 0, st>>>(workspace, S, N, M, D, y_mean, mean);
+  }
+  return check_launch(h, "gp_predict");
+}

@@ -1,0 +1,423 @@
+// SIMT (fp32 FFMA) form of the RBM-family kernels: used for small / ragged layers (the reference's
+// own test shapes are 6x5, tests/test_rbm.py:10-16), for the real-valued layer kinds (BGRBM / GBRBM /
+// GGRBM / Concrete units), and as the general form of the CD gradient. Large binary RBMs go through
+// the tcgen05 path (gemm_tc.cu / cd_chain.cu).
+#include "context.h"
+#include "simt_gemm.cuh"
+
+namespace db {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// K1 (SIMT): out = sample(act(col_scale * ((A / a_div) @ op(W)) + bias))
+// ------------------------------------------------------------------------------------------------
+struct LayerFwdParams {
+  const float* A; int lda; const float* a_div; int a_div_mode;
+  const float* W; int ldw;
+  const float* col_scale; int col_scale_mode; const float* bias;
+  int M, N, K; int act; int sample_kind; float inv_temp;
+  const float* noise_scale; int noise_scale_mode; const float* injected; RngArgs rng;
+  float* out_act; float* out_sample;
+};
+
+struct ALoadLayer {
+  static constexpr bool k_contig = true;
+  const float* A; int lda; const float* div; int div_mode; int M, K;
+  __device__ __forceinline__ float operator()(int m, int k) const {
+    if (m >= M || k >= K) return 0.0f;
+    float v = __ldg(A + (size_t)m * lda + k);
+    if (div_mode == DB_BCAST_ROW) v = v / __ldg(div + k);
+    else if (div_mode == DB_BCAST_FULL) v = v / __ldg(div + (size_t)m * lda + k);
+    return v;
+  }
+};
+template <bool TRANS>
+struct BLoadW {
+  static constexpr bool k_contig = TRANS;
+  const float* W; int ldw; int K, N;
+  __device__ __forceinline__ float operator()(int k, int n) const {
+    if (k >= K || n >= N) return 0.0f;
+    return TRANS ? __ldg(W + (size_t)n * ldw + k) : __ldg(W + (size_t)k * ldw + n);
+  }
+};
+
+__device__ __forceinline__ float draw_sample(int kind, float val, float inv_temp, float noise, const float* injected,
+                                             const RngArgs& rng, int m, int n, size_t idx) {
+  if (kind == DB_SAMPLE_BERNOULLI) {
+    float u = injected ? __ldg(injected + idx) : philox_uniform_at(rng, rng.row_offset + (uint32_t)m, (uint32_t)n);
+    return val > u ? 1.0f : 0.0f;
+  } else if (kind == DB_SAMPLE_CONCRETE) {
+    float u = injected ? __ldg(injected + idx) : philox_uniform_at(rng, rng.row_offset + (uint32_t)m, (uint32_t)n);
+    return concrete_sample(val, u, inv_temp);
+  } else if (kind == DB_SAMPLE_GAUSSIAN) {
+    float e = injected ? __ldg(injected + idx) : philox_normal_at(rng, rng.row_offset + (uint32_t)m, (uint32_t)n);
+    return fmaf(noise, e, val);
+  }
+  return val;
+}
+
+template <bool TRANS>
+__global__ void __launch_bounds__(256) layer_forward_kernel(const LayerFwdParams p) {
+  using T = TileSmall;
+  __shared__ typename T::Smem sm;
+  const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
+  ALoadLayer a{p.A, p.lda, p.a_div, p.a_div_mode, p.M, p.K};
+  BLoadW<TRANS> b{p.W, p.ldw, p.K, p.N};
+  float acc[T::TM][T::TN];
+  simt_gemm_tile<T>(sm, a, b, m0, n0, 0, p.K, acc);
+#pragma unroll
+  for (int i = 0; i < T::TM; ++i) {
+    const int m = simt_row<T>(m0, i);
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < T::TN; ++j) {
+      const int n = simt_col<T>(n0, j);
+      if (n >= p.N) continue;
+      const size_t idx = (size_t)m * p.N + n;
+      float x = acc[i][j];
+      if (p.col_scale_mode == DB_BCAST_ROW) x *= __ldg(p.col_scale + n);
+      else if (p.col_scale_mode == DB_BCAST_FULL) x *= __ldg(p.col_scale + idx);
+      if (p.bias) x += __ldg(p.bias + n);
+      const float val = p.act == DB_ACT_SIGMOID ? sigmoidf_(x) : x;
+      if (p.out_act) p.out_act[idx] = val;
+      if (p.out_sample) {
+        float ns = 0.0f;
+        if (p.noise_scale_mode == DB_BCAST_ROW) ns = __ldg(p.noise_scale + n);
+        else if (p.noise_scale_mode == DB_BCAST_FULL) ns = __ldg(p.noise_scale + idx);
+        p.out_sample[idx] = draw_sample(p.sample_kind, val, p.inv_temp, ns, p.injected, p.rng, m, n, idx);
+      }
+    }
+  }
+}
+
+__global__ void sample_kernel(const float* __restrict__ P, int M, int N, int kind, float inv_temp,
+                              const float* __restrict__ noise_scale, int ns_mode, const float* __restrict__ injected,
+                              RngArgs rng, float* __restrict__ out) {
+  const size_t total = (size_t)M * N;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int m = (int)(idx / N), n = (int)(idx % N);
+    float ns = 0.0f;
+    if (ns_mode == DB_BCAST_ROW) ns = __ldg(noise_scale + n);
+    else if (ns_mode == DB_BCAST_FULL) ns = __ldg(noise_scale + idx);
+    out[idx] = draw_sample(kind, __ldg(P + idx), inv_temp, ns, injected, rng, m, n, idx);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// free energy row reduction: one warp per datapoint
+// ------------------------------------------------------------------------------------------------
+__global__ void free_energy_reduce_kernel(int gaussian_hidden, const float* __restrict__ v, const float* __restrict__ x,
+                                          int N, int V, int H, const float* __restrict__ b, const float* __restrict__ c,
+                                          const float* __restrict__ sigma, float* __restrict__ out) {
+  const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  float s = 0.0f;
+  for (int i = lane; i < V; i += 32) s = fmaf(__ldg(v + (size_t)row * V + i), __ldg(b + i), s);
+  for (int j = lane; j < H; j += 32) {
+    const float xj = __ldg(x + (size_t)row * H + j);
+    if (gaussian_hidden) {
+      // bgrbm.py:143-151: 0.5*x^2 + (c/sigma)*x
+      s += 0.5f * xj * xj + (__ldg(c + j) / __ldg(sigma + j)) * xj;
+    } else {
+      s += softplusf_(xj + __ldg(c + j));   // rbm.py:388-389
+    }
+  }
+  s = warp_sum(s);
+  if (lane == 0) out[row] = -s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CD gradient (general form)
+// ------------------------------------------------------------------------------------------------
+// q = sigmoid(x + c) (Bernoulli hidden) or x + c/sigma (Gaussian hidden); in place on x [N,H]
+__global__ void cd_hidden_term_kernel(int gaussian_hidden, float* __restrict__ x, int N, int H, const float* __restrict__ c,
+                                      const float* __restrict__ sigma) {
+  const size_t total = (size_t)N * H;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % H);
+    const float xv = x[idx];
+    x[idx] = gaussian_hidden ? xv + __ldg(c + j) / __ldg(sigma + j) : sigmoidf_(xv + __ldg(c + j));
+  }
+}
+
+// dW[v,h] = -inv_n * sum_n (v0[n,v] q0[n,h] - vk[n,v] qk[n,h])   as one GEMM with K = 2N
+struct ALoadVT {
+  static constexpr bool k_contig = false;   // for fixed k (=n) memory is contiguous along m (=v)
+  const float* v0; const float* vk; int N, V;
+  __device__ __forceinline__ float operator()(int m, int k) const {
+    if (m >= V || k >= 2 * N) return 0.0f;
+    return k < N ? __ldg(v0 + (size_t)k * V + m) : __ldg(vk + (size_t)(k - N) * V + m);
+  }
+};
+struct BLoadQ {
+  static constexpr bool k_contig = false;
+  const float* q0; const float* qk; int N, H;
+  __device__ __forceinline__ float operator()(int k, int n) const {
+    if (n >= H || k >= 2 * N) return 0.0f;
+    return k < N ? __ldg(q0 + (size_t)k * H + n) : -__ldg(qk + (size_t)(k - N) * H + n);
+  }
+};
+__global__ void __launch_bounds__(256) cd_dw_kernel(const float* v0, const float* vk, const float* q0, const float* qk,
+                                                    int N, int V, int H, float scale, float* __restrict__ dW) {
+  using T = TileSmall;
+  __shared__ typename T::Smem sm;
+  const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
+  ALoadVT a{v0, vk, N, V};
+  BLoadQ b{q0, qk, N, H};
+  float acc[T::TM][T::TN];
+  simt_gemm_tile<T>(sm, a, b, m0, n0, 0, 2 * N, acc);
+#pragma unroll
+  for (int i = 0; i < T::TM; ++i) {
+    const int m = simt_row<T>(m0, i);
+    if (m >= V) continue;
+#pragma unroll
+    for (int j = 0; j < T::TN; ++j) {
+      const int n = simt_col<T>(n0, j);
+      if (n < H) dW[(size_t)m * H + n] = scale * acc[i][j];
+    }
+  }
+}
+
+// out[c] += scale * sum_{n in chunk} (a[n,c] - b[n,c]);  out must be zeroed first
+__global__ void colsum_diff_kernel(const float* __restrict__ a, const float* __restrict__ b, int N, int C, float scale,
+                                   float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int rows_per = (N + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(N, r0 + rows_per);
+  float s = 0.0f;
+  for (int n = r0; n < r1; ++n) s += __ldg(a + (size_t)n * C + c) - __ldg(b + (size_t)n * C + c);
+  atomicAdd(out + c, scale * s);
+}
+
+// Gaussian-hidden bias / sigma gradients from d[j] = inv_n * sum_n (x0 - xk)[n,j]  (held in gc on entry)
+//   dc = -d/sigma ; dsigma = +(c/sigma^2) d ; dopt_sigma = dsigma * sigmoid(opt_sigma)   
+__global__ void cd_gaussian_hidden_grads_kernel(int H, const float* __restrict__ c, const float* __restrict__ opt_sigma,
+                                                float* __restrict__ gc, float* __restrict__ gsig) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= H) return;
+  const float d = -gc[j];   // colsum kernel stored -inv_n * sum(x0 - xk)
+  const float os = __ldg(opt_sigma + j);
+  const float sig = softplusf_(os);
+  gc[j] = -d / sig;
+  gsig[j] = (__ldg(c + j) / (sig * sig)) * d * sigmoidf_(os);
+}
+
+__global__ void softplus_vec_kernel(const float* __restrict__ x, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = softplusf_(x[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// optimizer
+// ------------------------------------------------------------------------------------------------
+__global__ void optimizer_kernel(db_opt_t o, float lr_t, float* __restrict__ p, const float* __restrict__ g,
+                                 float* __restrict__ st, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float th = p[i];
+    float gi = __ldg(g + i) + o.weight_decay * th;
+    if (o.kind == DB_OPT_SGD) {
+      th -= o.lr * gi;
+    } else if (o.kind == DB_OPT_MOMENTUM) {
+      float a = o.momentum * st[i] + gi;
+      st[i] = a;
+      th -= o.lr * a;
+    } else {
+      float m = o.beta1 * st[i] + (1.0f - o.beta1) * gi;
+      float v = o.beta2 * st[n + i] + (1.0f - o.beta2) * gi * gi;
+      st[i] = m; st[n + i] = v;
+      th -= lr_t * m / (sqrtf(v) + o.eps);
+    }
+    p[i] = th;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dist.py reductions
+// ------------------------------------------------------------------------------------------------
+__global__ void mse_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t total, float scale,
+                           float* __restrict__ out) {
+  float s = 0.0f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const float d = __ldg(a + i) - __ldg(b + i);
+    s = fmaf(d, d, s);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, s * scale);
+}
+__global__ void cross_entropy_kernel(const float* __restrict__ probs, const float* __restrict__ t, size_t total, float scale,
+                                     float* __restrict__ out) {
+  float s = 0.0f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const float e0 = 1.0e-6f;                              // dist.py:25 (10e-7)
+    float p = fminf(fmaxf(__ldg(probs + i), e0), 1.0f - e0);
+    float x = logf(p / (1.0f - p));                        // dist.py:27
+    float z = __ldg(t + i);
+    s += fmaxf(x, 0.0f) - x * z + log1pf(__expf(-fabsf(x)));   // sigmoid_cross_entropy_with_logits [TF]
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, s * scale);
+}
+
+inline int ew_grid(size_t n, int num_sms) {
+  size_t blocks = (n + 255) / 256;
+  size_t cap = (size_t)num_sms * 8;
+  return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+}  // namespace
+
+// internal entry used by cd_chain.cu as well
+int launch_layer_forward(db_handle_t h, cudaStream_t st, const LayerFwdParams& p, int transW) {
+  dim3 grid((p.N + TileSmall::BN - 1) / TileSmall::BN, (p.M + TileSmall::BM - 1) / TileSmall::BM);
+  if (transW) layer_forward_kernel<true><<<grid, 256, 0, st>>>(p);
+  else layer_forward_kernel<false><<<grid, 256, 0, st>>>(p);
+  return check_launch(h, "layer_forward");
+}
+
+}  // namespace db
+
+using namespace db;
+
+extern "C" int db_layer_forward(db_handle_t h, db_stream_t stream, const float* A, int lda, const float* a_div,
+                                int a_div_mode, const float* W, int ldw, int transW, const float* col_scale,
+                                int col_scale_mode, const float* bias, int M, int N, int K, int act, int sample_kind,
+                                float temperature, const float* noise_scale, int noise_scale_mode,
+                                const float* injected, const db_rng_t* rng, float* out_act, float* out_sample) {
+  DB_REQUIRE(h, A && W && M > 0 && N > 0 && K > 0, "null operand or empty shape");
+  DB_REQUIRE(h, out_act || out_sample, "no output requested");
+  DB_REQUIRE(h, (a_div_mode == DB_BCAST_NONE) == (a_div == nullptr), "a_div / a_div_mode mismatch");
+  DB_REQUIRE(h, (col_scale_mode == DB_BCAST_NONE) == (col_scale == nullptr), "col_scale / mode mismatch");
+  DB_REQUIRE(h, sample_kind >= DB_SAMPLE_NONE && sample_kind <= DB_SAMPLE_GAUSSIAN, "bad sample_kind");
+  DB_REQUIRE(h, sample_kind != DB_SAMPLE_CONCRETE || temperature > 0.0f, "Concrete units need temperature > 0");
+  DB_REQUIRE(h, sample_kind != DB_SAMPLE_GAUSSIAN || noise_scale != nullptr, "Gaussian sampling needs noise_scale");
+  DB_REQUIRE(h, sample_kind == DB_SAMPLE_NONE || injected || rng, "sampling needs injected draws or an rng");
+  LayerFwdParams p;
+  p.A = A; p.lda = lda; p.a_div = a_div; p.a_div_mode = a_div_mode; p.W = W; p.ldw = ldw;
+  p.col_scale = col_scale; p.col_scale_mode = col_scale_mode; p.bias = bias; p.M = M; p.N = N; p.K = K;
+  p.act = act; p.sample_kind = sample_kind; p.inv_temp = temperature > 0.0f ? 1.0f / temperature : 0.0f;
+  p.noise_scale = noise_scale; p.noise_scale_mode = noise_scale ? noise_scale_mode : DB_BCAST_NONE;
+  p.injected = injected; to_rng(rng, p.rng); p.out_act = out_act; p.out_sample = out_sample;
+  return launch_layer_forward(h, (cudaStream_t)stream, p, transW);
+}
+
+extern "C" int db_sample(db_handle_t h, db_stream_t stream, const float* P, int M, int N, int sample_kind,
+                         float temperature, const float* noise_scale, int noise_scale_mode, const float* injected,
+                         const db_rng_t* rng, float* out) {
+  DB_REQUIRE(h, P && out && M > 0 && N > 0, "null operand or empty shape");
+  DB_REQUIRE(h, sample_kind >= DB_SAMPLE_NONE && sample_kind <= DB_SAMPLE_GAUSSIAN, "bad sample_kind");
+  DB_REQUIRE(h, sample_kind != DB_SAMPLE_CONCRETE || temperature > 0.0f, "Concrete units need temperature > 0");
+  DB_REQUIRE(h, sample_kind != DB_SAMPLE_GAUSSIAN || noise_scale != nullptr, "Gaussian sampling needs noise_scale");
+  DB_REQUIRE(h, sample_kind == DB_SAMPLE_NONE || injected || rng, "sampling needs injected draws or an rng");
+  RngArgs r; to_rng(rng, r);
+  const size_t total = (size_t)M * N;
+  sample_kernel<<<ew_grid(total, h->num_sms), 256, 0, (cudaStream_t)stream>>>(
+      P, M, N, sample_kind, temperature > 0.0f ? 1.0f / temperature : 0.0f, noise_scale,
+      noise_scale ? noise_scale_mode : DB_BCAST_NONE, injected, r, out);
+  return check_launch(h, "sample");
+}
+
+static bool gaussian_hidden(int kind) { return kind == DB_LAYER_BGRBM || kind == DB_LAYER_GGRBM; }
+
+extern "C" int db_free_energy(db_handle_t h, db_stream_t stream, int layer_kind, const float* v, int N, int V, int H,
+                              const float* W, const float* b, const float* c, const float* sigma_h, float* workspace,
+                              float* out) {
+  DB_REQUIRE(h, v && W && b && c && workspace && out && N > 0 && V > 0 && H > 0, "null operand or empty shape");
+  DB_REQUIRE(h, !gaussian_hidden(layer_kind) || sigma_h, "Gaussian hidden units need sigma_h");
+  cudaStream_t st = (cudaStream_t)stream;
+  LayerFwdParams p{};
+  p.A = v; p.lda = V; p.W = W; p.ldw = H; p.M = N; p.N = H; p.K = V; p.act = DB_ACT_LINEAR;
+  p.out_act = workspace;
+  int rc = launch_layer_forward(h, st, p, 0);
+  if (rc) return rc;
+  free_energy_reduce_kernel<<<(N + 7) / 8, 256, 0, st>>>(gaussian_hidden(layer_kind) ? 1 : 0, v, workspace, N, V, H, b, c,
+                                                       sigma_h, out);
+  return check_launch(h, "free_energy_reduce");
+}
+
+extern "C" size_t db_cd_param_count(int layer_kind, int V, int H) {
+  size_t n = (size_t)V * H + V + H;
+  if (gaussian_hidden(layer_kind)) n += H;
+  return n;
+}
+
+extern "C" int db_cd_gradients(db_handle_t h, db_stream_t stream, int layer_kind, const float* v0, const float* vk, int N,
+                               int V, int H, const float* params, float inv_global_n, float* workspace, float* grad) {
+  DB_REQUIRE(h, v0 && vk && params && workspace && grad && N > 0 && V > 0 && H > 0, "null operand or empty shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* W = params;
+  const float* c = params + (size_t)V * H + V;
+  const float* opt_sigma = c + H;
+  float* gW = grad; float* gb = grad + (size_t)V * H; float* gc = gb + V; float* gsig = gc + H;
+  float* q0 = workspace; float* qk = workspace + (size_t)N * H;
+  const bool gh = gaussian_hidden(layer_kind);
+  float* sigma = nullptr;
+  if (gh) {
+    // effective sigma_h = softplus(opt_sigma_h) (bgrbm.py:51), staged in the gsig slot until the end
+    sigma = gsig;
+    softplus_vec_kernel<<<(H + 255) / 256, 256, 0, st>>>(opt_sigma, H, sigma);
+  }
+  for (int side = 0; side < 2; ++side) {
+    LayerFwdParams p{};
+    p.A = side ? vk : v0; p.lda = V; p.W = W; p.ldw = H; p.M = N; p.N = H; p.K = V; p.act = DB_ACT_LINEAR;
+    p.out_act = side ? qk : q0;
+    int rc = launch_layer_forward(h, st, p, 0);
+    if (rc) return rc;
+  }
+  // bias sums first (Gaussian hiddens need x0 - xk, i.e. before c/sigma is added; the shift cancels anyway)
+  cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)(V + H), st);
+  {
+    dim3 g((V + 255) / 256, N >= 4096 ? 32 : (N >= 512 ? 8 : 1));
+    colsum_diff_kernel<<<g, 256, 0, st>>>(v0, vk, N, V, -inv_global_n, gb);
+  }
+  const size_t nh = (size_t)N * H;
+  cd_hidden_term_kernel<<<ew_grid(nh, h->num_sms), 256, 0, st>>>(gh ? 1 : 0, q0, N, H, c, sigma);
+  cd_hidden_term_kernel<<<ew_grid(nh, h->num_sms), 256, 0, st>>>(gh ? 1 : 0, qk, N, H, c, sigma);
+  {
+    dim3 g((H + 255) / 256, N >= 4096 ? 32 : (N >= 512 ? 8 : 1));
+    colsum_diff_kernel<<<g, 256, 0, st>>>(q0, qk, N, H, -inv_global_n, gc);
+  }
+  {
+    dim3 g((H + TileSmall::BN - 1) / TileSmall::BN, (V + TileSmall::BM - 1) / TileSmall::BM);
+    cd_dw_kernel<<<g, 256, 0, st>>>(v0, vk, q0, qk, N, V, H, -inv_global_n, gW);
+  }
+  if (gh) cd_gaussian_hidden_grads_kernel<<<(H + 255) / 256, 256, 0, st>>>(H, c, opt_sigma, gc, gsig);
+  return check_launch(h, "cd_gradients");
+}
+
+extern "C" int db_optimizer_step(db_handle_t h, db_stream_t stream, const db_opt_t* opt, float* params, const float* grad,
+                                 float* state, size_t n) {
+  DB_REQUIRE(h, opt && params && grad && n > 0, "null operand");
+  DB_REQUIRE(h, opt->kind == DB_OPT_SGD || state, "optimizer state required");
+  DB_REQUIRE(h, opt->kind >= DB_OPT_SGD && opt->kind <= DB_OPT_ADAM, "bad optimizer kind");
+  float lr_t = opt->lr;
+  if (opt->kind == DB_OPT_ADAM) {
+    DB_REQUIRE(h, opt->step >= 1, "Adam needs step >= 1");
+    // lr * sqrt(1 - b2^t) / (1 - b1^t), epsilon outside the root [TF AdamOptimizer, not vendored]
+    const double b1t = pow((double)opt->beta1, opt->step), b2t = pow((double)opt->beta2, opt->step);
+    lr_t = (float)((double)opt->lr * sqrt(1.0 - b2t) / (1.0 - b1t));
+  }
+  optimizer_kernel<<<ew_grid(n, h->num_sms), 256, 0, (cudaStream_t)stream>>>(*opt, lr_t, params, grad, state, n);
+  return check_launch(h, "optimizer_step");
+}
+
+extern "C" int db_mse(db_handle_t h, db_stream_t stream, const float* a, const float* b, int N, int D, float* out) {
+  DB_REQUIRE(h, a && b && out && N > 0 && D > 0, "null operand or empty shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(out, 0, sizeof(float), st);
+  const size_t total = (size_t)N * D;
+  mse_kernel<<<ew_grid(total, h->num_sms), 256, 0, st>>>(a, b, total, 1.0f / (float)N, out);
+  return check_launch(h, "mse");
+}
+
+extern "C" int db_cross_entropy(db_handle_t h, db_stream_t stream, const float* probs, const float* targets, int N, int D,
+                                int reduce_mean, float* out) {
+  DB_REQUIRE(h, probs && targets && out && N > 0 && D > 0, "null operand or empty shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(out, 0, sizeof(float), st);
+  const size_t total = (size_t)N * D;
+  cross_entropy_kernel<<<ew_grid(total, h->num_sms), 256, 0, st>>>(probs, targets, total,
+                                                                   reduce_mean ? 1.0f / (float)N : 1.0f, out);
+  return check_launch(h, "cross_entropy");
+}

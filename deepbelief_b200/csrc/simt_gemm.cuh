@@ -1,0 +1,126 @@
+// fp32 SIMT GEMM tile core shared by the small-layer RBM kernels (layer_simt.cu) and the GP chain
+// (gp.cu). 256 threads compute a BM x BN tile, each thread a TM x TN micro-tile, operands staged
+// through padded shared memory with register double-buffering of the global loads.
+//
+// Operands are abstracted as loaders  a(m, k) / b(k, n)  that return 0 outside the matrix, so the
+// callers can fuse prologues (bgrbm.py:126 h/sigma_h), transposed or triangular views, and on-the-fly
+// operands (e.g. the RBF Gram entries) without materialising them.
+#pragma once
+#include "common.cuh"
+
+namespace db {
+
+template <int BM_, int BN_, int BK_, int TM_, int TN_>
+struct SimtTile {
+  static constexpr int BM = BM_, BN = BN_, BK = BK_, TM = TM_, TN = TN_;
+  static constexpr int THREADS = (BM / TM) * (BN / TN);
+  static constexpr int PAD = 4;
+  static constexpr int A_PER_THREAD = BM * BK / THREADS;
+  static constexpr int B_PER_THREAD = BN * BK / THREADS;
+  static_assert(THREADS == 256, "tile shapes are chosen for 256 threads");
+  static_assert(TM % 4 == 0 && TN % 4 == 0, "float4 smem reads");
+  struct Smem {
+    float a[BK][BM + PAD];
+    float b[BK][BN + PAD];
+  };
+};
+
+// acc is zero-initialised unless ZERO_INIT=false (then the products are added to its contents).
+// ALoad: float operator()(int m, int k) const;  static constexpr bool k_contig (global memory is
+// contiguous along k for fixed m). BLoad: float operator()(int k, int n) const; static constexpr bool
+// k_contig likewise.
+template <class T, class ALoad, class BLoad, bool ZERO_INIT = true>
+__device__ __forceinline__ void simt_gemm_tile(typename T::Smem& sm, const ALoad& a, const BLoad& b, int m0, int n0,
+                                               int k_begin, int k_end, float (&acc)[T::TM][T::TN]) {
+  const int tid = threadIdx.x;
+  const int tx = tid % (T::BN / T::TN);
+  const int ty = tid / (T::BN / T::TN);
+  if (ZERO_INIT) {
+#pragma unroll
+    for (int i = 0; i < T::TM; ++i)
+#pragma unroll
+      for (int j = 0; j < T::TN; ++j) acc[i][j] = 0.0f;
+  }
+
+  float ra[T::A_PER_THREAD], rb[T::B_PER_THREAD];
+
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < T::A_PER_THREAD; ++i) {
+      const int idx = tid + i * T::THREADS;
+      int mm, kk;
+      if (ALoad::k_contig) { kk = idx % T::BK; mm = idx / T::BK; } else { mm = idx % T::BM; kk = idx / T::BM; }
+      const int k = k0 + kk;
+      ra[i] = (k < k_end) ? a(m0 + mm, k) : 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < T::B_PER_THREAD; ++i) {
+      const int idx = tid + i * T::THREADS;
+      int nn, kk;
+      if (BLoad::k_contig) { kk = idx % T::BK; nn = idx / T::BK; } else { nn = idx % T::BN; kk = idx / T::BN; }
+      const int k = k0 + kk;
+      rb[i] = (k < k_end) ? b(k, n0 + nn) : 0.0f;
+    }
+  };
+  auto sstore = [&]() {
+#pragma unroll
+    for (int i = 0; i < T::A_PER_THREAD; ++i) {
+      const int idx = tid + i * T::THREADS;
+      int mm, kk;
+      if (ALoad::k_contig) { kk = idx % T::BK; mm = idx / T::BK; } else { mm = idx % T::BM; kk = idx / T::BM; }
+      sm.a[kk][mm] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < T::B_PER_THREAD; ++i) {
+      const int idx = tid + i * T::THREADS;
+      int nn, kk;
+      if (BLoad::k_contig) { kk = idx % T::BK; nn = idx / T::BK; } else { nn = idx % T::BN; kk = idx / T::BN; }
+      sm.b[kk][nn] = rb[i];
+    }
+  };
+
+  if (k_begin >= k_end) return;
+  gload(k_begin);
+  for (int k0 = k_begin; k0 < k_end; k0 += T::BK) {
+    __syncthreads();           // previous tile fully consumed
+    sstore();
+    __syncthreads();
+    if (k0 + T::BK < k_end) gload(k0 + T::BK);   // overlaps with the FMAs below
+#pragma unroll
+    for (int kk = 0; kk < T::BK; ++kk) {
+      float av[T::TM], bv[T::TN];
+      // micro-tile rows: TM/4 groups of 4, strided by BM/(TM/4) to keep smem reads conflict-free
+#pragma unroll
+      for (int g = 0; g < T::TM / 4; ++g) {
+        const float4 v = *reinterpret_cast<const float4*>(&sm.a[kk][g * (T::BM / (T::TM / 4)) + ty * 4]);
+        av[4 * g + 0] = v.x; av[4 * g + 1] = v.y; av[4 * g + 2] = v.z; av[4 * g + 3] = v.w;
+      }
+#pragma unroll
+      for (int g = 0; g < T::TN / 4; ++g) {
+        const float4 v = *reinterpret_cast<const float4*>(&sm.b[kk][g * (T::BN / (T::TN / 4)) + tx * 4]);
+        bv[4 * g + 0] = v.x; bv[4 * g + 1] = v.y; bv[4 * g + 2] = v.z; bv[4 * g + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = 0; i < T::TM; ++i)
+#pragma unroll
+        for (int j = 0; j < T::TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+  }
+}
+
+// global (m, n) of micro-tile element (i, j) for the calling thread
+template <class T>
+__device__ __forceinline__ int simt_row(int m0, int i) {
+  const int ty = threadIdx.x / (T::BN / T::TN);
+  return m0 + (i / 4) * (T::BM / (T::TM / 4)) + ty * 4 + (i % 4);
+}
+template <class T>
+__device__ __forceinline__ int simt_col(int n0, int j) {
+  const int tx = threadIdx.x % (T::BN / T::TN);
+  return n0 + (j / 4) * (T::BN / (T::TN / 4)) + tx * 4 + (j % 4);
+}
+
+using TileSmall = SimtTile<64, 64, 16, 4, 4>;     // small layers / ragged shapes: more CTAs
+using TileLarge = SimtTile<128, 128, 8, 8, 8>;    // GP chain at N ~ 5000
+
+}  // namespace db

@@ -1,0 +1,247 @@
+"""Tensor-level wrappers of the C ABI: torch tensors in, torch tensors out, CUDA kernels in between.
+
+These are the calls the layer classes (deepbelief_b200.layers) are built from. Every function
+launches hand-written sm_100a kernels through `libdeepbelief_b200.so`; torch only allocates.
+"""
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+
+def _f32(t):
+    assert isinstance(t, torch.Tensor) and t.is_cuda, 'expected a CUDA tensor'
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.to(torch.float32).contiguous()
+    return t
+
+
+def _bcast_mode(t, rows, cols):
+    """DB_BCAST_* mode of an optional scale tensor shaped [cols], [1, cols] or [rows, cols]."""
+    if t is None:
+        return L.BCAST_NONE
+    n = t.numel()
+    if n == cols:
+        return L.BCAST_ROW
+    assert n == rows * cols, 'scale operand has %d elements, expected %d or %d' % (n, cols, rows * cols)
+    return L.BCAST_FULL
+
+
+class Rng:
+    """Counter-based Philox stream: one `draw` id per sampling call (see csrc/common.cuh)."""
+
+    def __init__(self, seed=0, row_offset=0):
+        self.seed = int(seed)
+        self.draw = 0
+        self.row_offset = int(row_offset)
+
+    def next(self, count=1):
+        r = L.make_rng(self.seed, self.draw, self.row_offset)
+        self.draw += count
+        return r
+
+
+def layer_forward(A, W, bias, trans_w, act, sample_kind=L.SAMPLE_NONE, temperature=None, a_div=None,
+                  col_scale=None, noise_scale=None, injected=None, rng=None, want_act=True, want_sample=None):
+    """sample(act(col_scale * ((A / a_div) @ op(W)) + bias)) -> (act or None, sample or None)."""
+    A = _f32(A)
+    W = _f32(W)
+    M, K = A.shape
+    N = W.shape[0] if trans_w else W.shape[1]
+    assert (W.shape[1] if trans_w else W.shape[0]) == K, 'inner dimensions differ: %s vs %s' % (A.shape, W.shape)
+    if want_sample is None:
+        want_sample = sample_kind != L.SAMPLE_NONE
+    bias = _f32(bias).reshape(-1) if bias is not None else None
+    a_div = _f32(a_div) if a_div is not None else None
+    col_scale = _f32(col_scale) if col_scale is not None else None
+    noise_scale = _f32(noise_scale) if noise_scale is not None else None
+    injected = _f32(injected) if injected is not None else None
+    out_act = torch.empty((M, N), device=A.device, dtype=torch.float32) if want_act else None
+    out_s = torch.empty((M, N), device=A.device, dtype=torch.float32) if want_sample else None
+    r = rng.next() if (rng is not None and injected is None and want_sample) else None
+    rc = L.lib().db_layer_forward(
+        L.handle(), L.stream(), L.fptr(A), K, L.fptr(a_div), _bcast_mode(a_div, M, K),
+        L.fptr(W), W.shape[1], 1 if trans_w else 0, L.fptr(col_scale), _bcast_mode(col_scale, M, N),
+        L.fptr(bias), M, N, K, act, sample_kind, float(temperature or 0.0),
+        L.fptr(noise_scale), _bcast_mode(noise_scale, M, N), L.fptr(injected),
+        ctypes.byref(r) if r is not None else None, L.fptr(out_act), L.fptr(out_s))
+    L.check(rc, 'db_layer_forward')
+    return out_act, out_s
+
+
+def sample(P, sample_kind, temperature=None, noise_scale=None, injected=None, rng=None):
+    P = _f32(P)
+    M, N = P.shape
+    noise_scale = _f32(noise_scale) if noise_scale is not None else None
+    injected = _f32(injected) if injected is not None else None
+    out = torch.empty_like(P)
+    r = rng.next() if (rng is not None and injected is None) else None
+    rc = L.lib().db_sample(L.handle(), L.stream(), L.fptr(P), M, N, sample_kind, float(temperature or 0.0),
+                           L.fptr(noise_scale), _bcast_mode(noise_scale, M, N), L.fptr(injected),
+                           ctypes.byref(r) if r is not None else None, L.fptr(out))
+    L.check(rc, 'db_sample')
+    return out
+
+
+def free_energy(layer_kind, v, W, b, c, sigma_h=None):
+    v = _f32(v)
+    N, V = v.shape
+    H = W.shape[1]
+    ws = torch.empty((N, H), device=v.device, dtype=torch.float32)
+    out = torch.empty((N, 1), device=v.device, dtype=torch.float32)
+    rc = L.lib().db_free_energy(L.handle(), L.stream(), layer_kind, L.fptr(v), N, V, H, L.fptr(_f32(W)),
+                                L.fptr(_f32(b).reshape(-1)), L.fptr(_f32(c).reshape(-1)),
+                                L.fptr(_f32(sigma_h).reshape(-1)) if sigma_h is not None else None,
+                                L.fptr(ws), L.fptr(out))
+    L.check(rc, 'db_free_energy')
+    return out
+
+
+def cd_param_count(layer_kind, V, H):
+    return int(L.lib().db_cd_param_count(layer_kind, V, H))
+
+
+def cd_gradients(layer_kind, v0, vk, params, V, H, inv_global_n=None, grad=None):
+    """Packed CD gradient (W|b|c[|opt_sigma_h]) from the two ends of the chain."""
+    v0 = _f32(v0)
+    vk = _f32(vk)
+    N = v0.shape[0]
+    if grad is None:
+        grad = torch.empty_like(params)
+    ws = torch.empty((2, N, H), device=v0.device, dtype=torch.float32)
+    rc = L.lib().db_cd_gradients(L.handle(), L.stream(), layer_kind, L.fptr(v0), L.fptr(vk), N, V, H,
+                                 L.fptr(params), float(inv_global_n if inv_global_n is not None else 1.0 / N),
+                                 L.fptr(ws), L.fptr(grad))
+    L.check(rc, 'db_cd_gradients')
+    return grad
+
+
+def optimizer_step(opt, params, grad, state):
+    rc = L.lib().db_optimizer_step(L.handle(), L.stream(), ctypes.byref(opt), L.fptr(params), L.fptr(grad),
+                                   L.fptr(state), params.numel())
+    L.check(rc, 'db_optimizer_step')
+
+
+def mse(a, b):
+    a = _f32(a)
+    b = _f32(b)
+    out = torch.empty((), device=a.device, dtype=torch.float32)
+    L.check(L.lib().db_mse(L.handle(), L.stream(), L.fptr(a), L.fptr(b), a.shape[0], a.shape[1], L.fptr(out)), 'db_mse')
+    return out
+
+
+def cross_entropy(probs, targets, reduce_mean=True):
+    probs = _f32(probs)
+    targets = _f32(targets)
+    if targets.shape != probs.shape:
+        targets = targets.expand_as(probs).contiguous()
+    out = torch.empty((), device=probs.device, dtype=torch.float32)
+    L.check(L.lib().db_cross_entropy(L.handle(), L.stream(), L.fptr(probs), L.fptr(targets), probs.shape[0],
+                                     probs.shape[1], 1 if reduce_mean else 0, L.fptr(out)), 'db_cross_entropy')
+    return out
+
+
+# ---- tensor-core CD chain --------------------------------------------------------------------------
+class CdTcPlan:
+    """Owns the workspace / split-weight cache of the fused tcgen05 CD-k step for one (N, V, H, k)."""
+
+    def __init__(self, N, V, H, k, pcd=False, n_global=None, device='cuda'):
+        self.desc = L.db_cd_tc_desc_t(N, V, H, k, 1 if pcd else 0, 1.0 / float(n_global or N))
+        wb = int(L.lib().db_cd_tc_workspace_bytes(ctypes.byref(self.desc)))
+        if wb == 0:
+            raise ValueError('tensor-core CD path needs N, V, H multiples of 8 (got %d, %d, %d)' % (N, V, H))
+        self.workspace = torch.empty(wb, dtype=torch.uint8, device=device)
+        self.cache = torch.empty(int(L.lib().db_cd_tc_weight_cache_bytes(V, H)), dtype=torch.uint8, device=device)
+        self.pcd_state = torch.zeros((N, H), dtype=torch.float16, device=device) if pcd else None
+        self.N, self.V, self.H, self.k = N, V, H, k
+
+    def refresh_weights(self, params):
+        rc = L.lib().db_cd_tc_refresh_weights(L.handle(), L.stream(), L.fptr(params), self.V, self.H, L.ptr(self.cache))
+        L.check(rc, 'db_cd_tc_refresh_weights')
+
+    def step(self, v0, params, grad, injected=None, rng=None, vk_out=None, hk_out=None, p0_out=None, pk_out=None):
+        r = rng.next(2 * self.k + 1) if (rng is not None and injected is None) else None
+        rc = L.lib().db_cd_tc_step(
+            L.handle(), L.stream(), ctypes.byref(self.desc), L.fptr(v0), L.fptr(params), L.ptr(self.cache),
+            L.ptr(self.pcd_state), L.fptr(injected), ctypes.byref(r) if r is not None else None,
+            L.ptr(self.workspace), L.fptr(grad), L.fptr(vk_out), L.fptr(hk_out), L.fptr(p0_out), L.fptr(pk_out))
+        L.check(rc, 'db_cd_tc_step')
+        return grad
+
+
+# ---- GP ---------------------------------------------------------------------------------------------
+def gp_effective_hyp(hyp_opt, flags, fixed_noise, jitter):
+    out = torch.empty(3, device=hyp_opt.device, dtype=torch.float32)
+    L.check(L.lib().db_gp_effective_hyp(L.handle(), L.stream(), L.fptr(hyp_opt), flags, float(fixed_noise),
+                                        float(jitter), L.fptr(out)), 'db_gp_effective_hyp')
+    return out
+
+
+def gram_rbf(X, Y, hyp, add_noise=False):
+    X = _f32(X)
+    N, Q = X.shape
+    if Y is not None:
+        Y = _f32(Y)
+        assert Y.shape[1] == Q
+    M = N if Y is None else Y.shape[0]
+    out = torch.empty((N, M), device=X.device, dtype=torch.float32)
+    L.check(L.lib().db_gram_rbf(L.handle(), L.stream(), L.fptr(X), L.fptr(Y), N, M, Q, L.fptr(hyp),
+                                1 if add_noise else 0, L.fptr(out), M), 'db_gram_rbf')
+    return out
+
+
+def potrf_lower(A):
+    """In-place lower Cholesky of A [N,N]; returns the device info scalar (0 = ok)."""
+    N = A.shape[0]
+    info = torch.zeros(1, dtype=torch.int32, device=A.device)
+    L.check(L.lib().db_potrf_lower(L.handle(), L.stream(), L.fptr(A), N, N, L.ptr(info)), 'db_potrf_lower')
+    return info
+
+
+def trsm_lower(Lmat, B, trans=False):
+    """In-place B <- L^-1 B (or L^-T B)."""
+    N = Lmat.shape[0]
+    L.check(L.lib().db_trsm_lower(L.handle(), L.stream(), L.fptr(Lmat), N, N, L.fptr(B), B.shape[1], B.shape[1],
+                                  1 if trans else 0), 'db_trsm_lower')
+    return B
+
+
+class GplvmPlan:
+    """Workspace owner for the fused LML + gradient evaluation at a fixed (N, Q, D)."""
+
+    def __init__(self, N, Q, D, device='cuda'):
+        self.N, self.Q, self.D = N, Q, D
+        nbytes = int(L.lib().db_gplvm_workspace_bytes(N, Q, D))
+        self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.scalars = torch.zeros(8, dtype=torch.float32, device=device)
+        self.dX = torch.zeros((N, Q), dtype=torch.float32, device=device)
+        self.info = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def evaluate(self, X, Y, hyp_opt, flags, fixed_noise=0.0, jitter=1e-6, x_prior_weight=0.0, include_const=True,
+                 want_grad=True, L_out=None):
+        rc = L.lib().db_gplvm_lml_grad(
+            L.handle(), L.stream(), L.fptr(X), L.fptr(Y), self.N, self.Q, self.D, L.fptr(hyp_opt), int(flags),
+            float(fixed_noise), float(jitter), float(x_prior_weight), 1 if include_const else 0,
+            1 if want_grad else 0, L.ptr(self.workspace), L.fptr(self.scalars), L.fptr(self.dX), L.fptr(L_out),
+            L.ptr(self.info))
+        L.check(rc, 'db_gplvm_lml_grad')
+        return self.scalars, self.dX, self.info
+
+
+def gp_predict(X, Lmat, S, y_mean, xstar, hyp, want_mean=True, want_var=True):
+    X = _f32(X)
+    xstar = _f32(xstar)
+    N, Q = X.shape
+    M = xstar.shape[0]
+    D = S.shape[1] if S is not None else 0
+    ws = torch.empty((N, M), device=X.device, dtype=torch.float32)
+    mean = torch.empty((M, D), device=X.device, dtype=torch.float32) if want_mean else None
+    var = torch.empty((M,), device=X.device, dtype=torch.float32) if want_var else None
+    info = torch.zeros(1, dtype=torch.int32, device=X.device)
+    rc = L.lib().db_gp_predict(L.handle(), L.stream(), L.fptr(X), L.fptr(Lmat), L.fptr(S) if want_mean else None,
+                               L.fptr(y_mean.reshape(-1)) if (y_mean is not None and want_mean) else None,
+                               L.fptr(xstar), N, Q, D, M, L.fptr(hyp), L.fptr(ws), L.fptr(mean), L.fptr(var),
+                               L.ptr(info))
+    L.check(rc, 'db_gp_predict')
+    return mean, var, info

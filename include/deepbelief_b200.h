@@ -1,0 +1,215 @@
+/* deepbelief_b200 — C ABI of the B200-native hot paths of zeis/deepbelief.
+ *
+ * The reference has no FFI layer: its hot path is the TensorFlow graph built by the
+ * Python classes in deepbelief/layers. The boundary kept is that Python API (deepbelief_b200.layers);
+ * this header is what its ctypes loader (deepbelief_b200/_lib.py) binds, one call per fused stage.
+ * Every entry cites the reference lines whose TF ops it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *   - all matrices fp32, row-major, device pointers, leading dimension in elements (config.py:1);
+ *   - the library never allocates or frees device memory: callers pass outputs and a workspace
+ *     (size from the matching *_workspace_bytes); calls are asynchronous on `stream`;
+ *   - return value: 0 ok; < 0 error (DB_ERR_*), message via db_last_error(); > 0 LAPACK-style info
+ *     (1-based index of the failing Cholesky pivot / first negative predictive variance);
+ *   - no entry point has a CPU fallback: without a CUDA device db_create fails.
+ */
+#ifndef DEEPBELIEF_B200_H
+#define DEEPBELIEF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct db_context_s* db_handle_t;
+typedef void* db_stream_t; /* cudaStream_t */
+
+enum {
+  DB_OK = 0,
+  DB_ERR_BAD_ARG = -1,
+  DB_ERR_CUDA = -2,
+  DB_ERR_UNSUPPORTED = -3,
+  DB_ERR_WORKSPACE = -4
+};
+
+/* activation of a unit layer */
+enum { DB_ACT_LINEAR = 0, DB_ACT_SIGMOID = 1 };
+/* sampling rule applied to the activation */
+enum {
+  DB_SAMPLE_NONE = 0,      /* return the probabilities / means (sample=False, rbm.py:209-210) */
+  DB_SAMPLE_BERNOULLI = 1, /* float(p > u), strict (rbm.py:206-208, 234-236) */
+  DB_SAMPLE_CONCRETE = 2,  /* relaxed Bernoulli with temperature (rbm.py:243-275) */
+  DB_SAMPLE_GAUSSIAN = 3   /* mean + sigma * eps (bgrbm.py:106-110) */
+};
+/* broadcast mode of an optional scale operand */
+enum { DB_BCAST_NONE = 0, DB_BCAST_ROW = 1 /* [1, n] */, DB_BCAST_FULL = 2 /* [m, n] */ };
+/* RBM family member: decides activations and the free-energy / CD-gradient form */
+enum {
+  DB_LAYER_RBM = 0,   /* rbm.py   : Bernoulli visible, Bernoulli hidden */
+  DB_LAYER_BGRBM = 1, /* bgrbm.py : Bernoulli visible, Gaussian hidden (sigma_h) */
+  DB_LAYER_GBRBM = 2, /* gbrbm.py : Gaussian (unit variance, noise-free mean) visible, Bernoulli hidden */
+  DB_LAYER_GGRBM = 3  /* ggrbm.py : Gaussian visible, Gaussian hidden */
+};
+/* optimizer rule (rbm.py:666-670 takes any TF optimizer; [TF, not vendored] update rules restated) */
+enum {
+  DB_OPT_SGD = 0,      /* theta -= lr * g                                   (GradientDescentOptimizer) */
+  DB_OPT_MOMENTUM = 1, /* a = mu*a + g; theta -= lr * a                     (MomentumOptimizer)        */
+  DB_OPT_ADAM = 2      /* m,v moments; theta -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps) (AdamOptimizer) */
+};
+
+/* Counter-based RNG state: Philox4x32-10 keyed by `seed`; `draw` identifies one sampling call (the
+ * caller increments it per call); `row_offset` is the global index of local row 0 so that a
+ * row-sharded batch draws the same numbers on any number of GPUs. */
+typedef struct {
+  uint64_t seed;
+  uint64_t draw;
+  uint32_t row_offset;
+  uint32_t reserved;
+} db_rng_t;
+
+typedef struct {
+  int kind;            /* DB_OPT_* */
+  float lr;
+  float momentum;      /* DB_OPT_MOMENTUM */
+  float beta1, beta2, eps; /* DB_OPT_ADAM */
+  float weight_decay;  /* g += weight_decay * theta (builder-defined extension) */
+  int step;            /* 1-based step number t (Adam bias correction) */
+} db_opt_t;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int db_create(db_handle_t* out, int device);
+int db_destroy(db_handle_t h);
+const char* db_last_error(db_handle_t h);
+int db_version(void);
+int db_num_sms(db_handle_t h);
+
+/* ---- K1: fused unit layer  out = sample(act(col_scale * ((A / a_div) @ op(W)) + bias)) --------
+ * Replaces, in one launch: rbm.py:119-131 h_net_input, rbm.py:133-147 v_net_input (transW=1, no
+ * materialised transposes), rbm.py:149-175 sigmoid, rbm.py:187-275 sampling; bgrbm.py:69-82 (col_scale =
+ * sigma_h), bgrbm.py:116-131 (a_div = sigma_h), bgrbm.py:96-114 (Gaussian sample), gbrbm.py:56-64.
+ *   A [M,K]; W is [K,N] (transW=0) or [N,K] used transposed (transW=1); bias [N] or NULL.
+ *   a_div / col_scale / noise_scale: NULL or vector [K]/[N] (DB_BCAST_ROW) or matrix (DB_BCAST_FULL,
+ *   same leading dimension as the tensor they scale: lda for a_div, N for the others).
+ *   injected: uniforms U (Bernoulli/Concrete) or standard normals (Gaussian) [M,N], or NULL -> Philox.
+ *   out_act (value after activation) and out_sample may each be NULL. */
+int db_layer_forward(db_handle_t h, db_stream_t stream,
+                     const float* A, int lda, const float* a_div, int a_div_mode,
+                     const float* W, int ldw, int transW,
+                     const float* col_scale, int col_scale_mode, const float* bias,
+                     int M, int N, int K, int act, int sample_kind, float temperature,
+                     const float* noise_scale, int noise_scale_mode,
+                     const float* injected, const db_rng_t* rng,
+                     float* out_act, float* out_sample);
+
+/* Elementwise sampling of given probabilities/means (rbm.py:177-275 sample_h / sample_v called on a
+ * tensor; bgrbm.py:96-114). P, out: [M,N] contiguous. */
+int db_sample(db_handle_t h, db_stream_t stream, const float* P, int M, int N, int sample_kind,
+              float temperature, const float* noise_scale, int noise_scale_mode,
+              const float* injected, const db_rng_t* rng, float* out);
+
+/* Free energy per datapoint, out[N] (rbm.py:378-396; bgrbm.py:133-153 when layer_kind has Gaussian
+ * hiddens, sigma_h [H] required then). workspace: N*H floats. */
+int db_free_energy(db_handle_t h, db_stream_t stream, int layer_kind, const float* v, int N, int V, int H,
+                   const float* W, const float* b, const float* c, const float* sigma_h,
+                   float* workspace, float* out);
+
+/* ---- K2: CD gradient + optimizer ------------------------------------------------------------- */
+/* Packed parameter / gradient layout used by db_cd_gradients and db_optimizer_step:
+ *   [ W (V*H) | b (V) | c (H) | opt_sigma_h (H, only BGRBM/GGRBM) ]                                    */
+size_t db_cd_param_count(int layer_kind, int V, int H);
+
+/* Gradient of cd_loss (rbm.py:398-415, closed form SURVEY.md §8 R9 / B2) from the two ends of the
+ * chain: v0, vk [N,V]. Writes SUMS scaled by inv_global_n (= 1/N over all ranks) into grad (packed),
+ * so a sum-allreduce over row shards yields the reference's mean gradient. workspace: 2*N*H floats. */
+int db_cd_gradients(db_handle_t h, db_stream_t stream, int layer_kind,
+                    const float* v0, const float* vk, int N, int V, int H,
+                    const float* params, float inv_global_n, float* workspace, float* grad);
+
+/* One optimizer step over n packed elements; state: Momentum n floats, Adam 2n floats (m | v). */
+int db_optimizer_step(db_handle_t h, db_stream_t stream, const db_opt_t* opt, float* params,
+                      const float* grad, float* state, size_t n);
+
+/* ---- fused CD-k chain for the binary RBM on tensor cores (tcgen05) ----------------------------
+ * One call = positive phase + k Gibbs steps + dW/db/dc (rbm.py:628-646, 664 + autodiff), using fp16
+ * hi/lo split operands so results hold fp32 tolerance. Falls back to nothing: returns
+ * DB_ERR_UNSUPPORTED when the shape does not qualify (caller then uses db_layer_forward et al.). */
+typedef struct {
+  int N;              /* local batch rows (multiple of 8) */
+  int V, H;           /* multiples of 8 */
+  int k;              /* Gibbs steps >= 1 */
+  int pcd;            /* 1: chain starts from (and updates) the persistent hidden state */
+  float inv_global_n; /* 1 / (batch rows over all ranks) */
+} db_cd_tc_desc_t;
+
+size_t db_cd_tc_workspace_bytes(const db_cd_tc_desc_t* d);
+/* bytes of the persistent split-weight cache (W and W^T as fp16 hi/lo + scale) */
+size_t db_cd_tc_weight_cache_bytes(int V, int H);
+/* refresh the cache after W changed (optimizer step / restore) */
+int db_cd_tc_refresh_weights(db_handle_t h, db_stream_t stream, const float* W, int V, int H, void* cache);
+/* v0: [N,V] fp32 {0,1}. params packed (W|b|c). pcd_state: [N,H] fp16 persistent chain (pcd=1) or NULL.
+ * injected: NULL (Philox) or uniforms laid out [U_h0 (N*H) | per step: U_v (N*V), U_h (N*H)].
+ * grad: packed (W|b|c) sums * inv_global_n. Optional fp32 exports (may be NULL): vk_out [N,V],
+ * hk_out [N,H] (last samples), p0_out / pk_out [N,H] (hidden probabilities at both chain ends). */
+int db_cd_tc_step(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, const float* v0,
+                  const float* params, const void* weight_cache, void* pcd_state,
+                  const float* injected, const db_rng_t* rng, void* workspace, float* grad,
+                  float* vk_out, float* hk_out, float* p0_out, float* pk_out);
+
+/* ---- GP path (gplvm.py / gprbm.py) ----------------------------------------------------------- */
+/* hyp (device, 3 floats + workspace use): effective kernel variance alpha, length-scale gamma, noise
+ * variance (+jitter) AFTER softplus, i.e. the values gplvm.py:39,49,152,219-221 produce. */
+
+/* K3: RBF Gram  K[i,j] = alpha * exp(-0.5 * |x_i/gamma - y_j/gamma|^2) (+ noise on the diagonal when
+ * Y == NULL)  — gplvm.py:61-86 + 218-224. X [N,Q], Y [M,Q] or NULL (then M = N). out [N,M]. */
+int db_gram_rbf(db_handle_t h, db_stream_t stream, const float* X, const float* Y, int N, int M, int Q,
+                const float* hyp, int add_noise, float* out, int ldo);
+
+/* K4: in-place lower Cholesky (tf.cholesky, gplvm.py:212 / gprbm.py:109). The strict upper triangle is
+ * left untouched. info (device int): 0 or 1-based index of the first non-positive pivot. */
+int db_potrf_lower(db_handle_t h, db_stream_t stream, float* A, int lda, int N, int* info);
+
+/* K5: triangular solve with the Cholesky factor (tf.matrix_triangular_solve, gplvm.py:235,248-249,281).
+ * trans=0: B <- L^-1 B; trans=1: B <- L^-T B. B [N,nrhs]. */
+int db_trsm_lower(db_handle_t h, db_stream_t stream, const float* L, int ldl, int N, float* B, int ldb,
+                  int nrhs, int trans);
+
+/* K3-K6 fused pipeline: GPLVM negative log marginal likelihood and its gradient (gplvm.py:210-244 +
+ * the autodiff of gplvm.py:425-428; closed forms SURVEY.md §8 GP6/GP7).
+ *   X [N,Q], Y [N,D] (already centred), hyp_opt (device): [opt_alpha, opt_gamma, opt_noise] pre-softplus.
+ *   flags bit0: alpha trainable, bit1: gamma trainable, bit2: noise trainable (=> + jitter);
+ *   untrainable alpha/gamma are the constant 1.0 (gplvm.py:31-32,41-42); untrainable noise = fixed_noise.
+ *   x_prior_weight: adds w*|X|^2 (gprbm.py:238-242); include_const: add D*N*log(2*pi) (gplvm.py:238).
+ *   out_scalars (device, 8 floats): [loss, logdet, |L^-1 Y|^2, d/dopt_alpha, d/dopt_gamma, d/dopt_noise, alpha, noise_eff]
+ *   dX [N,Q]. L_out (optional, [N,N]) receives the Cholesky factor for later prediction calls. */
+size_t db_gplvm_workspace_bytes(int N, int Q, int D);
+int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float* X, const float* Y, int N, int Q, int D,
+                      const float* hyp_opt, int flags, float fixed_noise, float jitter,
+                      float x_prior_weight, int include_const, int want_grad,
+                      void* workspace, float* out_scalars, float* dX, float* L_out, int* info);
+
+/* GP prediction at M test latents (gplvm.py:246-254, 278-288; gprbm.py:208-232):
+ *   S = L^-1 Yc [N,D] cached by the caller (db_trsm_lower), L [N,N].
+ *   mean [M,D] = (L^-1 K_Xx)^T S (+ y_mean [D] if not NULL); var [M] = alpha - colsum((L^-1 K_Xx)^2).
+ *   info: 1-based index of the first negative variance (tf.assert_non_negative), else 0.
+ *   workspace: N*M floats. */
+int db_gp_predict(db_handle_t h, db_stream_t stream, const float* X, const float* L, const float* S,
+                  const float* y_mean, const float* xstar, int N, int Q, int D, int M, const float* hyp,
+                  float* workspace, float* mean, float* var, int* info);
+
+/* effective hyper-parameters from optimisation variables: hyp_out[3] = [alpha, gamma, noise(+jitter)] */
+int db_gp_effective_hyp(db_handle_t h, db_stream_t stream, const float* hyp_opt, int flags, float fixed_noise,
+                        float jitter, float* hyp_out);
+
+/* ---- small fused helpers used by the layer API ------------------------------------------------ */
+/* mean over rows of the sum over columns of (a-b)^2 — dist.py:5-21. out: device float. */
+int db_mse(db_handle_t h, db_stream_t stream, const float* a, const float* b, int N, int D, float* out);
+/* dist.py:24-35 cross entropy with clipping to [1e-6, 1-1e-6]; reduce_mean=1: mean of row sums, 0: total. */
+int db_cross_entropy(db_handle_t h, db_stream_t stream, const float* probs, const float* targets, int N, int D,
+                     int reduce_mean, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPBELIEF_B200_H */
