@@ -1,0 +1,285 @@
+"""Generate the golden vectors in tests/golden/*.npz by EXECUTING THE REFERENCE'S OWN SOURCE FILES.
+
+Run in the build container (needs /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference modules are imported unmodified from /root/reference on top of tf_numpy_shim (a numpy
+stand-in for the `tensorflow` module, see its docstring), in both fp32 (deepbelief/config.py default)
+and fp64 (config.float_type patched). All random draws are injected. Gradients, which the reference
+obtains from TF autodiff, are recorded as central finite differences (fp64) of the reference's own
+loss functions.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import tf_numpy_shim as shim  # noqa: E402
+
+tf = shim.install()
+sys.path.insert(0, '/root/reference')
+import deepbelief.config as cfg  # noqa: E402
+from deepbelief import dist, preprocessing  # noqa: E402
+from deepbelief.layers import rbm as ref_rbm, bgrbm as ref_bgrbm, gbrbm as ref_gbrbm, ggrbm as ref_ggrbm  # noqa: E402
+from deepbelief.layers import gplvm as ref_gplvm  # noqa: E402
+
+sys.path.insert(0, os.path.join(HERE, '..', '..'))
+from deepbelief_b200 import hdf5  # noqa: E402  (only the HDF5 reader; h5py is unavailable)
+
+KINDS = {'rbm': ref_rbm.RBM, 'bgrbm': ref_bgrbm.BGRBM, 'gbrbm': ref_gbrbm.GBRBM, 'ggrbm': ref_ggrbm.GGRBM}
+
+
+def set_dtype(name):
+    cfg.float_type = name
+
+
+def make_layer(kind, V, H, W, b, c, opt_sigma, temperature=None, bottom=None, name='L'):
+    sess = tf.Session()
+    kw = dict(num_v=V, num_h=H, session=sess, name=name, bottom=bottom)
+    if kind != 'ggrbm':
+        kw['temperature'] = temperature
+    layer = KINDS[kind](**kw)
+    dt = np.dtype(cfg.float_type)
+    layer.W = W.astype(dt)
+    layer.b = b.astype(dt).reshape(V, 1)
+    layer.c = c.astype(dt).reshape(1, H)
+    if kind in ('bgrbm', 'ggrbm'):
+        layer.opt_sigma_h = opt_sigma.astype(dt).reshape(1, H)
+        layer.sigma_h = tf.nn.softplus(layer.opt_sigma_h)      # bgrbm.py:51
+    return layer
+
+
+def rbm_goldens(out):
+    rs = np.random.RandomState(1234)
+    for tag, (V, H, N) in {'toy': (6, 5, 20), 'mid': (40, 24, 16)}.items():
+        W = rs.normal(size=(V, H)) * 0.3
+        b = rs.normal(size=V) * 0.2
+        c = rs.normal(size=H) * 0.2
+        opt_sigma = rs.normal(size=H) * 0.3 + 0.5
+        v_bin = rs.binomial(1, 0.5, size=(N, V)).astype(np.float64)
+        v_real = rs.normal(size=(N, V))
+        h_bin = rs.binomial(1, 0.5, size=(N, H)).astype(np.float64)
+        h_real = rs.normal(size=(N, H))
+        vk_bin = rs.binomial(1, 0.5, size=(N, V)).astype(np.float64)
+        k = 3
+        U_h = rs.uniform(size=(N, H))
+        U_v = rs.uniform(size=(N, V))
+        # bgrbm.py:108 draws float32 normals whatever config.float_type is: keep them fp32-representable
+        E_h = rs.normal(size=(N, H)).astype(np.float32).astype(np.float64)
+        chain_v = rs.uniform(size=(k, N, V))
+        chain_h_u = rs.uniform(size=(k, N, H))
+        chain_h_e = rs.normal(size=(k, N, H)).astype(np.float32).astype(np.float64)
+        base = {'W': W, 'b': b, 'c': c, 'opt_sigma': opt_sigma, 'v_bin': v_bin, 'v_real': v_real, 'h_bin': h_bin,
+                'h_real': h_real, 'vk_bin': vk_bin, 'U_h': U_h, 'U_v': U_v, 'E_h': E_h, 'chain_v': chain_v,
+                'chain_h_u': chain_h_u, 'chain_h_e': chain_h_e, 'k': np.array(k)}
+        for kk, vv in base.items():
+            out['%s/%s' % (tag, kk)] = vv
+        for kind in KINDS:
+            gv = kind in ('gbrbm', 'ggrbm')
+            gh = kind in ('bgrbm', 'ggrbm')
+            for dname in ('float32', 'float64'):
+                set_dtype(dname)
+                dt = np.dtype(dname)
+                layer = make_layer(kind, V, H, W, b, c, opt_sigma)
+                v = (v_real if gv else v_bin).astype(dt)
+                h = (h_real if gh else h_bin).astype(dt)
+                vk = (v_real[::-1] if gv else vk_bin).astype(dt)
+                pre = '%s/%s/%s/' % (tag, kind, dname)
+                hp = layer.h_probs(v)
+                vp = layer.v_probs(h)
+                out[pre + 'h_net_input'] = layer.h_net_input(v)
+                out[pre + 'v_net_input'] = layer.v_net_input(h)
+                out[pre + 'h_probs'] = hp
+                out[pre + 'v_probs'] = vp
+                shim.RANDOM_QUEUE[:] = [E_h if gh else U_h]
+                out[pre + 'sample_h'] = layer.sample_h(hp)
+                shim.RANDOM_QUEUE[:] = [] if gv else [U_v]
+                out[pre + 'sample_v'] = layer.sample_v(vp)
+                out[pre + 'free_energy'] = layer.free_energy(v)
+                out[pre + 'cd_loss'] = np.asarray(layer.cd_loss(v, vk))
+                # k-step chain (rbm.py:351-376): draws consumed in the order v, h, v, h, ...
+                q = []
+                for s in range(k):
+                    if not gv:
+                        q.append(chain_v[s])
+                    q.append(chain_h_e[s] if gh else chain_h_u[s])
+                shim.RANDOM_QUEUE[:] = q
+                gvp, gvs, ghp, ghs = layer.gibbs_sample(h, k=k)
+                assert not shim.RANDOM_QUEUE
+                out[pre + 'gibbs_v_probs'], out[pre + 'gibbs_v'] = gvp, gvs
+                out[pre + 'gibbs_h_probs'], out[pre + 'gibbs_h'] = ghp, ghs
+                # Concrete units (rbm.py:243-275); GGRBM takes no temperature
+                if kind != 'ggrbm':
+                    lc = make_layer(kind, V, H, W, b, c, opt_sigma, temperature=0.1)
+                    if not gh:
+                        shim.RANDOM_QUEUE[:] = [U_h]
+                        out[pre + 'concrete_h'] = lc.sample_h(hp)
+                    if not gv:
+                        shim.RANDOM_QUEUE[:] = [U_v]
+                        out[pre + 'concrete_v'] = lc.sample_v(vp)
+                shim.RANDOM_QUEUE[:] = []
+            # finite-difference gradient of the reference's cd_loss (fp64), toy shape only
+            if tag == 'toy':
+                set_dtype('float64')
+                v = (v_real if gv else v_bin)
+                vk = (v_real[::-1] if gv else vk_bin)
+                theta = [W.copy(), b.copy(), c.copy()] + ([opt_sigma.copy()] if gh else [])
+
+                def f(parts):
+                    lay = make_layer(kind, V, H, parts[0], parts[1], parts[2], parts[3] if gh else opt_sigma)
+                    return float(lay.cd_loss(v, vk))
+                grads = []
+                eps = 1e-6
+                for pi, par in enumerate(theta):
+                    g = np.zeros_like(par)
+                    it = np.nditer(par, flags=['multi_index'])
+                    for _ in it:
+                        idx = it.multi_index
+                        old = par[idx]
+                        par[idx] = old + eps
+                        fp = f(theta)
+                        par[idx] = old - eps
+                        fm = f(theta)
+                        par[idx] = old
+                        g[idx] = (fp - fm) / (2 * eps)
+                    grads.append(g)
+                out['%s/%s/fd_grad_W' % (tag, kind)] = grads[0]
+                out['%s/%s/fd_grad_b' % (tag, kind)] = grads[1]
+                out['%s/%s/fd_grad_c' % (tag, kind)] = grads[2]
+                if gh:
+                    out['%s/%s/fd_grad_opt_sigma' % (tag, kind)] = grads[3]
+    # two-layer stack: upprop / downprop recursion (rbm.py:277-325)
+    set_dtype('float64')
+    rs = np.random.RandomState(77)
+    V, H1, H2, N = 12, 8, 5, 9
+    W1, b1, c1 = rs.normal(size=(V, H1)) * 0.4, rs.normal(size=V) * 0.1, rs.normal(size=H1) * 0.1
+    W2, b2, c2 = rs.normal(size=(H1, H2)) * 0.4, rs.normal(size=H1) * 0.1, rs.normal(size=H2) * 0.1
+    l1 = make_layer('rbm', V, H1, W1, b1, c1, None, name='l1')
+    l2 = make_layer('rbm', H1, H2, W2, b2, c2, None, bottom=l1, name='l2')
+    v = rs.binomial(1, 0.5, size=(N, V)).astype(np.float64)
+    u1, u2, u3, u4 = rs.uniform(size=(N, H1)), rs.uniform(size=(N, H2)), rs.uniform(size=(N, H1)), rs.uniform(size=(N, V))
+    shim.RANDOM_QUEUE[:] = [u1, u2]
+    up = l2.upprop(v)
+    shim.RANDOM_QUEUE[:] = [u3, u4]
+    down = l2.downprop(up)
+    for kk, vv in dict(W1=W1, b1=b1, c1=c1, W2=W2, b2=b2, c2=c2, v=v, u1=u1, u2=u2, u3=u3, u4=u4, up=up, down=down).items():
+        out['stack/' + kk] = vv
+
+
+def gp_goldens(out):
+    rs = np.random.RandomState(4321)
+    # SEKernel (tests/test_gplvm.py shapes + a 2-D case)
+    for tag, (n, m, q) in {'k83': (8, 8, 3), 'k30': (30, 11, 2)}.items():
+        X, Y = rs.uniform(size=(n, q)), rs.uniform(size=(m, q))
+        out['%s/X' % tag], out['%s/Y' % tag] = X, Y
+        for dname in ('float32', 'float64'):
+            set_dtype(dname)
+            for an, (alpha, gamma) in {'unit': (1.0, 1.0), 'ag': (1.7, 0.6)}.items():
+                kern = ref_gplvm.SEKernel(alpha=alpha, gamma=gamma, session=tf.Session())
+                dt = np.dtype(dname)
+                pre = '%s/%s/%s/' % (tag, dname, an)
+                out[pre + 'K_X'] = kern.K(X.astype(dt))
+                out[pre + 'K_XY'] = kern.K(X.astype(dt), Y.astype(dt))
+                out[pre + 'K_X_diag'] = kern.K(X.astype(dt), diag=True)
+                if n == m:
+                    out[pre + 'K_XY_diag'] = kern.K(X.astype(dt), Y.astype(dt), diag=True)
+    # GPLVM: loss, K, L, prediction; finite-difference gradient
+    cases = {'trainable': dict(noise_variance=0.7, fixed_noise_variance=False, alpha=1.3, gamma=0.8),
+             'gpdbn': dict(noise_variance=0.01, fixed_noise_variance=True, alpha=False, gamma=False)}
+    N, D, Q, M = 30, 12, 2, 7
+    Yd = rs.normal(size=(N, D))
+    xs = rs.normal(size=(M, Q))
+    out['gplvm/Y'], out['gplvm/xstar'] = Yd, xs
+    for cname, kw in cases.items():
+        for dname in ('float32', 'float64'):
+            set_dtype(dname)
+            dt = np.dtype(dname)
+            sess = tf.Session()
+            kern = ref_gplvm.SEKernel(alpha=kw['alpha'], gamma=kw['gamma'], session=sess)
+            g = ref_gplvm.GPLVM(Yd.astype(dt), Q, kern=kern, noise_variance=kw['noise_variance'],
+                                fixed_noise_variance=kw['fixed_noise_variance'], x_test_var=xs.astype(dt), session=sess)
+            g.build_model()
+            pre = 'gplvm/%s/%s/' % (cname, dname)
+            out[pre + 'X0'] = np.asarray(g.X)
+            out[pre + 'Y_centered'] = np.asarray(g.Y)
+            out[pre + 'Y_mean'] = np.asarray(g.Y_mean)
+            out[pre + 'K'], out[pre + 'L'] = g.K, g.L
+            out[pre + 'loss'], out[pre + 'log_det'] = np.asarray(g.loss), np.asarray(g.log_det)
+            out[pre + 'pred_mean'], out[pre + 'pred_var'] = g.pred_mean, g.pred_var
+        # fd gradient in fp64 wrt X and the optimisation variables
+        set_dtype('float64')
+        sess = tf.Session()
+        X0 = out['gplvm/%s/float64/X0' % cname].copy()
+        isp = lambda v: np.log(np.exp(v) - 1.0)  # noqa: E731
+
+        def loss_at(X, oa, og, on):
+            kern = ref_gplvm.SEKernel(alpha=kw['alpha'], gamma=kw['gamma'], session=sess)
+            g = ref_gplvm.GPLVM(Yd, Q, X0=X, kern=kern, noise_variance=kw['noise_variance'],
+                                fixed_noise_variance=kw['fixed_noise_variance'], x_test_var=xs, session=sess)
+            if kw['alpha'] is not False:
+                kern.opt_alpha = np.float64(oa); kern.alpha = tf.nn.softplus(kern.opt_alpha)
+            if kw['gamma'] is not False:
+                kern.opt_gamma = np.float64(og); kern.gamma = tf.nn.softplus(kern.opt_gamma)
+            if not kw['fixed_noise_variance']:
+                g.opt_noise_variance = np.float64(on); g.noise_variance = tf.nn.softplus(g.opt_noise_variance)
+            g.K = g.build_K(); g.L = tf.cholesky(g.K); g.log_det = g.build_log_det()
+            return float(g.build_loss())
+        oa = isp(kw['alpha']) if kw['alpha'] is not False else 0.0
+        og = isp(kw['gamma']) if kw['gamma'] is not False else 0.0
+        on = isp(kw['noise_variance'])
+        eps = 1e-6
+        gX = np.zeros_like(X0)
+        for i in range(N):
+            for qd in range(Q):
+                Xp, Xm = X0.copy(), X0.copy()
+                Xp[i, qd] += eps; Xm[i, qd] -= eps
+                gX[i, qd] = (loss_at(Xp, oa, og, on) - loss_at(Xm, oa, og, on)) / (2 * eps)
+        out['gplvm/%s/fd_dX' % cname] = gX
+        out['gplvm/%s/fd_dopt' % cname] = np.array([
+            (loss_at(X0, oa + eps, og, on) - loss_at(X0, oa - eps, og, on)) / (2 * eps),
+            (loss_at(X0, oa, og + eps, on) - loss_at(X0, oa, og - eps, on)) / (2 * eps),
+            (loss_at(X0, oa, og, on + eps) - loss_at(X0, oa, og, on - eps)) / (2 * eps)])
+        out['gplvm/%s/opt' % cname] = np.array([oa, og, on])
+    # GPLVM at construction on the bundled horses data (anchor (3) of SURVEY.md §8c), reference code, fp64 + fp32
+    horses = hdf5.File(os.path.join(HERE, 'datasets', 'weizmann_horses_training_328x1024_binary.h5'))['datapoints']
+    for dname in ('float32', 'float64'):
+        set_dtype(dname)
+        sess = tf.Session()
+        g = ref_gplvm.GPLVM(horses.astype(np.dtype(dname)), 2, noise_variance=1.0, session=sess,
+                            x_test_var=np.zeros((1, 2), dtype=np.dtype(dname)))
+        g.build_model()
+        out['horses/%s/loss' % dname] = np.asarray(g.loss)
+        out['horses/%s/log_det' % dname] = np.asarray(g.log_det)
+        out['horses/%s/X0' % dname] = np.asarray(g.X)
+
+
+def misc_goldens(out):
+    rs = np.random.RandomState(99)
+    set_dtype('float64')
+    p = rs.uniform(size=(7, 9)); p[0, 0] = 0.0; p[1, 1] = 1.0
+    t = rs.binomial(1, 0.5, size=(7, 9)).astype(np.float64)
+    out['dist/p'], out['dist/t'] = p, t
+    out['dist/mse'] = np.asarray(dist.mse(p, t))
+    out['dist/ce_mean'] = np.asarray(dist.cross_entropy(p, t))
+    out['dist/ce_sum'] = np.asarray(dist.cross_entropy(p, t, reduce_mean=False))
+    A = rs.normal(size=(25, 6)) * np.array([3.0, 2.0, 1.0, 0.5, 0.2, 0.1])
+    out['pre/A'] = A
+    out['pre/pca2'] = preprocessing.PCA(A, 2)
+    out['pre/std'] = preprocessing.standardize(A.copy())
+    out['pre/inv_softplus'] = np.asarray(preprocessing.inverse_softplus(np.array([0.3, 1.0, 2.5])))
+
+
+def main():
+    for fn, name in ((rbm_goldens, 'rbm_golden.npz'), (gp_goldens, 'gp_golden.npz'), (misc_goldens, 'misc_golden.npz')):
+        out = {}
+        fn(out)
+        path = os.path.join(HERE, name)
+        np.savez_compressed(path, **{k.replace('/', '__'): np.asarray(v) for k, v in out.items()})
+        print('wrote %s: %d arrays, %d bytes' % (name, len(out), os.path.getsize(path)))
+
+
+if __name__ == '__main__':
+    main()
