@@ -80,6 +80,7 @@ SIGNATURES = {
     'db_gp_predict': (c_int, [c_void_p, c_void_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_int,
                               c_int, c_int, c_int, c_float_p, c_float_p, c_float_p, c_float_p, c_void_p]),
     'db_gp_effective_hyp': (c_int, [c_void_p, c_void_p, c_float_p, c_int, c_float, c_float, c_float_p]),
+    'db_softplus': (c_int, [c_void_p, c_void_p, c_float_p, c_int, c_float_p]),
     'db_mse': (c_int, [c_void_p, c_void_p, c_float_p, c_float_p, c_int, c_int, c_float_p]),
     'db_cross_entropy': (c_int, [c_void_p, c_void_p, c_float_p, c_float_p, c_int, c_int, c_int, c_float_p]),
 }

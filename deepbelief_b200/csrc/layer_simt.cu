@@ -147,7 +147,8 @@ struct ALoadVT {
   const float* v0; const float* vk; int N, V;
   __device__ __forceinline__ float operator()(int m, int k) const {
     if (m >= V || k >= 2 * N) return 0.0f;
-    return k < N ? __ldg(v0 + (size_t)k * V + m) : __ldg(vk + (size_t)(k - N) * V + m);
+    // k = 2n + phase: data and model terms alternate so the fp32 partial sums of the difference stay small
+    return (k & 1) ? __ldg(vk + (size_t)(k >> 1) * V + m) : __ldg(v0 + (size_t)(k >> 1) * V + m);
   }
 };
 struct BLoadQ {
@@ -155,7 +156,7 @@ struct BLoadQ {
   const float* q0; const float* qk; int N, H;
   __device__ __forceinline__ float operator()(int k, int n) const {
     if (n >= H || k >= 2 * N) return 0.0f;
-    return k < N ? __ldg(q0 + (size_t)k * H + n) : -__ldg(qk + (size_t)(k - N) * H + n);
+    return (k & 1) ? -__ldg(qk + (size_t)(k >> 1) * H + n) : __ldg(q0 + (size_t)(k >> 1) * H + n);
   }
 };
 __global__ void __launch_bounds__(256) cd_dw_kernel(const float* v0, const float* vk, const float* q0, const float* qk,
@@ -268,7 +269,6 @@ inline int ew_grid(size_t n, int num_sms) {
 
 }  // namespace
 
-// internal entry used by cd_chain.cu as well
 int launch_layer_forward(db_handle_t h, cudaStream_t st, const LayerFwdParams& p, int transW) {
   dim3 grid((p.N + TileSmall::BN - 1) / TileSmall::BN, (p.M + TileSmall::BM - 1) / TileSmall::BM);
   if (transW) layer_forward_kernel<true><<<grid, 256, 0, st>>>(p);
@@ -420,4 +420,10 @@ extern "C" int db_cross_entropy(db_handle_t h, db_stream_t stream, const float* 
   cross_entropy_kernel<<<ew_grid(total, h->num_sms), 256, 0, st>>>(probs, targets, total,
                                                                    reduce_mean ? 1.0f / (float)N : 1.0f, out);
   return check_launch(h, "cross_entropy");
+}
+
+extern "C" int db_softplus(db_handle_t h, db_stream_t stream, const float* x, int n, float* out) {
+  DB_REQUIRE(h, x && out && n > 0, "null operand or empty shape");
+  softplus_vec_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x, n, out);
+  return check_launch(h, "softplus");
 }

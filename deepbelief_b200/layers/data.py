@@ -1,0 +1,112 @@
+"""In-memory dataset with the reference's epoch/batch contract, fed from the built-in HDF5 reader.
+
+Contract kept from deepbelief/layers/data.py (reference):
+  * a batch is `batch_size` rows picked through an index permutation, and the picked row numbers
+    are SORTED before the gather (data.py:92-93);
+  * when the next window would run past the end, the partial tail is dropped, `epoch` increments and
+    the permutation is reshuffled with the global `np.random` state (data.py:84-90);
+  * the first epoch uses the identity permutation unless `shuffle_first` (data.py:64-66);
+  * `has_labels` makes `next_batch()` return `(datapoints, labels)`.
+Added for the GPU path: `next_batch_device()` stages the batch through a reusable pinned host buffer
+and issues an asynchronous host->device copy on the current stream.
+"""
+import json
+import logging
+import os
+
+import numpy as np
+
+from .. import hdf5
+
+
+class _EpochCursor:
+    """Produces the sorted row indices of successive batches."""
+
+    def __init__(self, num_rows, batch_size, shuffle_first):
+        self.order = np.arange(num_rows)
+        self.num_rows, self.batch_size = num_rows, batch_size
+        self.start = 0        # first position of the NEXT window inside `order`
+        self.epoch = 0
+        if shuffle_first:
+            np.random.shuffle(self.order)
+
+    def advance(self):
+        lo, hi = self.start, self.start + self.batch_size
+        wrapped = hi > self.num_rows
+        if wrapped:           # drop the tail, start a new shuffled epoch
+            self.epoch += 1
+            lo, hi = 0, self.batch_size
+            np.random.shuffle(self.order)
+        self.start = hi
+        return np.sort(self.order[lo:hi]), wrapped
+
+
+class Data:
+    """Args as in the reference (data.py:28-34): data_fname, has_labels=False, shuffle_first=False,
+    batch_size=1, log_epochs=True, name='Data'."""
+
+    def __init__(self, data_fname, has_labels=False, shuffle_first=False, batch_size=1, log_epochs=True,
+                 name='Data'):
+        if not os.path.isfile(data_fname):
+            raise AssertionError('The file does not exist: %s' % data_fname)
+        self.name = name
+        self.logger = logging.getLogger(name)
+        self.has_labels = bool(has_labels)
+        self.batch_size = int(batch_size)
+        self.log_epochs = log_epochs
+
+        contents = hdf5.File(data_fname)
+        self.datapoints = contents['datapoints']
+        self.labels = contents['labels'] if self.has_labels else None
+        self.num_datapoints, self.datapoint_size = self.datapoints.shape
+        if self.batch_size > self.num_datapoints:
+            raise AssertionError('batch_size %d exceeds the %d datapoints' % (self.batch_size, self.num_datapoints))
+
+        self._cursor = _EpochCursor(self.num_datapoints, self.batch_size, shuffle_first)
+        self._pinned = None
+        self.logger.debug(self)
+
+    # attributes the reference exposes
+    @property
+    def epoch(self):
+        return self._cursor.epoch
+
+    @property
+    def next_batch_start(self):
+        return self._cursor.start
+
+    @property
+    def _index_map(self):
+        return self._cursor.order
+
+    def batch_shape(self):
+        return self.batch_size, self.datapoint_size
+
+    def next_batch(self):
+        rows, wrapped = self._cursor.advance()
+        if wrapped and self.log_epochs:
+            self.logger.info('Epoch: %d', self._cursor.epoch)
+        if self.has_labels:
+            return self.datapoints[rows], self.labels[rows]
+        return self.datapoints[rows]
+
+    def next_batch_device(self, device='cuda'):
+        """Same batch as next_batch(), delivered as a CUDA tensor via pinned staging (datapoints only)."""
+        import torch
+        rows, wrapped = self._cursor.advance()
+        if wrapped and self.log_epochs:
+            self.logger.info('Epoch: %d', self._cursor.epoch)
+        if self._pinned is None:
+            self._pinned = torch.empty((self.batch_size, self.datapoint_size), dtype=torch.float32).pin_memory()
+        np.take(self.datapoints, rows, axis=0, out=self._pinned.numpy())
+        return self._pinned.to(device, non_blocking=True)
+
+    def __str__(self):
+        def stats(arr, tag):
+            return {tag + '_array_dtype': str(arr.dtype), tag + '_array_min': float(arr.min()),
+                    tag + '_array_max': float(arr.max())}
+        d = dict(batch_size=self.batch_size, num_datapoints=self.num_datapoints, datapoint_size=self.datapoint_size)
+        d.update(stats(self.datapoints, 'datapoint'))
+        if self.has_labels:
+            d.update(stats(self.labels, 'label'))
+        return json.dumps(d, indent=4, sort_keys=True)

@@ -1,0 +1,375 @@
+"""RBF kernel and GP-LVM layer — the B200 counterpart of deepbelief/layers/gplvm.py.
+
+`SEKernel` and `GPLVM` keep the reference constructors and method names (gplvm.py:11-17, 91-108 and
+SURVEY.md §8b). The arithmetic is the CUDA GP chain behind the C ABI: db_gram_rbf (K3),
+db_potrf_lower (K4), db_trsm_lower (K5), db_gplvm_lml_grad (fused K3-K6: loss and its analytic
+gradient, replacing TF autodiff of gplvm.py:425-428) and db_gp_predict.
+
+Eager semantics: attributes the reference builds as graph tensors (`K`, `L`, `loss`, `pred_mean`,
+`pred_var`, …) are `compat.Lazy` values here — re-evaluated whenever a `Session.run` (or `.eval()`)
+asks for them, exactly as a TF graph node would be.
+Not supported: ARD length-scales (gplvm.py:24-28) — no example or test of the reference uses them.
+"""
+import pickle
+
+import numpy as np
+import torch
+
+from .. import compat, dist, ops, preprocessing
+from . import layer
+from .layer import to_device, to_numpy
+
+_FLAG_ALPHA, _FLAG_GAMMA, _FLAG_NOISE = 1, 2, 4
+
+
+def _inv_softplus(v):
+    return float(preprocessing.inverse_softplus(np.float64(v)))
+
+
+class SEKernel(layer.Stateful):
+    """K(x, y) = alpha * exp(-0.5 * |x/gamma - y/gamma|^2); alpha / gamma are softplus-constrained
+    optimisation variables, or the constant 1.0 when passed as False (gplvm.py:18-49)."""
+
+    def __init__(self, alpha=1.0, gamma=1.0, ARD=False, Q=None, session=None, name='SEKernel', device='cuda'):
+        if ARD and gamma is not False:
+            raise NotImplementedError('ARD length-scales are not supported by the CUDA GP path')
+        self.Q = Q
+        self.device = device
+        self.flags = (0 if alpha is False else _FLAG_ALPHA) | (0 if gamma is False else _FLAG_GAMMA)
+        # [opt_alpha, opt_gamma, (noise slot, owned by the GP layer)]
+        self._hyp = torch.zeros(3, dtype=torch.float32, device=device)
+        self._hyp[0] = _inv_softplus(alpha) if alpha is not False else 0.0
+        self._hyp[1] = _inv_softplus(gamma) if gamma is not False else 0.0
+        super().__init__(params={'alpha': lambda: self.alpha, 'gamma': lambda: self.gamma}, session=session, name=name)
+
+    def bind(self, storage):
+        """Move the optimisation variables into `storage` (a 3-float view of the GP layer's packed parameters)."""
+        storage[:2].copy_(self._hyp[:2])
+        self._hyp = storage
+
+    @property
+    def opt_alpha(self):
+        return self._hyp[0]
+
+    @property
+    def opt_gamma(self):
+        return self._hyp[1]
+
+    def effective(self, noise_flags=0, fixed_noise=0.0, jitter=0.0):
+        """Device tensor [alpha, gamma, noise] after the softplus / constant rules."""
+        return ops.gp_effective_hyp(self._hyp, self.flags | noise_flags, fixed_noise, jitter)
+
+    @property
+    def alpha(self):
+        return self.effective()[0]
+
+    @property
+    def gamma(self):
+        return self.effective()[1]
+
+    def state_tensors(self):
+        return {'hyp': self._hyp}
+
+    def K(self, x, y=None, diag=False):
+        """gplvm.py:84-86. diag=True with y=None is exactly alpha (gplvm.py:64-66)."""
+        x = to_device(x, self.device)
+        hyp = self.effective()
+        if diag and y is None:
+            return hyp[0].expand(x.shape[0]).contiguous()
+        full = ops.gram_rbf(x, to_device(y, self.device) if y is not None else None, hyp, add_noise=False)
+        if diag:
+            return torch.diagonal(full).contiguous()
+        return full
+
+
+class GPLVM(layer.Layer):
+    def __init__(self, Y, Q, Y_labels=None, X0=None, kern=None, noise_variance=1.0, fixed_noise_variance=False,
+                 noise_jitter=1e-6, bottom=None, x_test_var=None, subtract_Y_mean=True, uppropagate_Y=True,
+                 latent_point_plotter=None, latent_sample_plotter=None, latent_space_explorer=None, session=None,
+                 name='GPLVM', device='cuda'):
+        assert type(Y) == np.ndarray, 'Y must be of type numpy.ndarray'
+        assert Y.ndim == 2, 'Y must be 2-dimensional numpy.ndarray'
+        self.Q = Q
+        self.Y_labels = Y_labels
+        self.subtract_Y_mean = subtract_Y_mean
+        self.device = device
+
+        Y_np = Y.astype(np.float32)
+        if uppropagate_Y and bottom is not None:
+            # the reference keeps this as a stochastic graph tensor re-sampled per run (gplvm.py:117-118,
+            # SURVEY §8 a'.10, exercised by no example); here it is one draw
+            Y_np = to_numpy(bottom.upprop(Y_np))
+        if self.subtract_Y_mean:
+            self.Y_mean = to_device(Y_np.mean(axis=0, keepdims=True), device)      # gplvm.py:122-124
+            Y_np = Y_np - Y_np.mean(axis=0, keepdims=True)
+        else:
+            self.Y_mean = None
+        self.Y_np = Y_np
+        self.Y = to_device(Y_np, device)
+
+        if X0 is not None:
+            self.X0 = np.asarray(X0, dtype=np.float32)
+        else:
+            self.X0 = preprocessing.standardize(preprocessing.PCA(self.Y_np, self.Q))   # gplvm.py:131-132
+        assert self.X0.shape[0] == self.Y_np.shape[0]
+        assert self.X0.shape[1] == self.Q
+        self.N, self.D = self.X0.shape[0], self.Y_np.shape[1]
+
+        # packed trainables [X | opt_alpha, opt_gamma, opt_noise]
+        nq = self.N * self.Q
+        self._params = torch.zeros(nq + 3, dtype=torch.float32, device=device)
+        self.X = self._params[:nq].view(self.N, self.Q)
+        self.X.copy_(to_device(self.X0, device))
+        self._hyp = self._params[nq:nq + 3]
+        self.fixed_noise = float(noise_variance)
+        if fixed_noise_variance is True:
+            self.noise_jitter = None                                   # gplvm.py:141-143: constant, no jitter
+            self._noise_flag = 0
+        else:
+            self.noise_jitter = noise_jitter
+            self._noise_flag = _FLAG_NOISE
+            self._hyp[2] = _inv_softplus(noise_variance)               # gplvm.py:145-152
+
+        self.kern = kern or SEKernel(session=session, Q=self.Q, device=device)
+        self.kern.bind(self._hyp)
+
+        if x_test_var is not None:
+            self.x_test = x_test_var
+            self.x_ph = x_test_var
+        else:
+            self.x_test = None
+            self.x_ph = compat.Placeholder(shape=(None, self.Q), name='x_ph')
+
+        self.lp_plotter = latent_point_plotter
+        self.ls_plotter = latent_sample_plotter
+        self.latent_space_explorer = latent_space_explorer
+        self.eval_interval = None
+        self.loss_values_fname = None
+        self.loss_values = None
+
+        self._plan = ops.GplvmPlan(self.N, self.Q, self.D, device=device)
+        self._L = torch.zeros((self.N, self.N), dtype=torch.float32, device=device)
+        self._S = None
+        self._version = 0
+        self._factor_version = -1
+        params = {'X': self.X, 'noise_variance': lambda: self.noise_variance}
+        super().__init__(params=params, bottom=bottom, session=session, name=name)
+
+    # ---- hyper-parameters -------------------------------------------------------------------------------------
+    @property
+    def flags(self):
+        return self.kern.flags | self._noise_flag
+
+    def _effective_hyp(self):
+        return ops.gp_effective_hyp(self._hyp, self.flags, self.fixed_noise, self.noise_jitter or 0.0)
+
+    @property
+    def noise_variance(self):
+        """softplus(opt_noise_variance), or the fixed constant (gplvm.py:143,152); jitter is added in build_K only."""
+        if self._noise_flag:
+            return ops.softplus(self._hyp[2:3])[0]
+        return torch.tensor(self.fixed_noise, device=self.device)
+
+    @property
+    def opt_noise_variance(self):
+        return self._hyp[2]
+
+    def state_tensors(self):
+        return {'params': self._params}
+
+    def _after_restore(self):
+        self._version += 1
+
+    def set_latents(self, X):
+        self.X.copy_(to_device(X, self.device))
+        self._version += 1
+
+    def param_dict(self):
+        d = super().param_dict()
+        d[self.kern.name] = self.kern.param_dict()
+        return d
+
+    # ---- model ---------------------------------------------------------------------------------------------------
+    def _evaluate(self, want_grad=False, need_factor=False):
+        scal, dX, info = self._plan.evaluate(self.X, self.Y, self._hyp, self.flags, fixed_noise=self.fixed_noise,
+                                             jitter=self.noise_jitter or 0.0, x_prior_weight=0.0, include_const=True,
+                                             want_grad=want_grad, L_out=self._L if need_factor else None)
+        return scal, dX, info
+
+    def _factor(self):
+        """Cholesky factor and S = L^-1 Y for the current parameters (cached until they change)."""
+        if self._factor_version != self._version:
+            _, _, info = self._evaluate(want_grad=False, need_factor=True)
+            pivot = int(info.item())
+            if pivot:
+                raise RuntimeError('Cholesky decomposition was not successful: pivot %d is not positive' % pivot)
+            self._S = ops.trsm_lower(self._L, self.Y.clone())
+            self._factor_version = self._version
+        return self._L, self._S
+
+    def build_model(self):
+        """gplvm.py:210-216 — binds the lazily evaluated model quantities."""
+        self.K = compat.Lazy(self.build_K)
+        self.L = compat.Lazy(lambda: torch.tril(self._factor()[0]))
+        self.log_det = compat.Lazy(self.build_log_det)
+        self.loss = compat.Lazy(self.build_loss)
+        self.pred_mean = compat.Lazy(self.build_pred_mean)
+        self.pred_var = compat.Lazy(self.build_pred_var)
+
+    def build_K(self):
+        """K_f(X) + (noise [+ jitter]) I (gplvm.py:218-224)."""
+        return ops.gram_rbf(self.X, None, self._effective_hyp(), add_noise=True)
+
+    def build_log_det(self):
+        """2 sum log L_ii (gplvm.py:226-228)."""
+        return self._evaluate()[0][1].clone()
+
+    def build_X_prior(self):
+        return (self.X * self.X).sum()
+
+    def build_loss(self, summary=True):
+        """0.5 (|L^-1 Y|^2 + D logdet + D N log 2pi) (gplvm.py:233-244)."""
+        scal, _, info = self._evaluate()
+        return scal[0].clone()
+
+    def loss_and_grad(self):
+        """(loss, dX [N,Q], d/d(opt_alpha, opt_gamma, opt_noise) [3]) — K3-K6 in one call."""
+        scal, dX, info = self._evaluate(want_grad=True)
+        return scal[0], dX, scal[3:6]
+
+    def _xstar(self, x=None):
+        if x is None:
+            x = self.x_ph.value
+        assert x is not None, 'no test latent points: feed x_ph or pass x_test_var'
+        return to_device(np.array(to_numpy(x), ndmin=2) if not isinstance(x, torch.Tensor) else x, self.device)
+
+    def build_pred_mean(self, x=None):
+        """(L^-1 K_Xx)^T (L^-1 Y) + Y_mean (gplvm.py:246-254)."""
+        Lf, S = self._factor()
+        mean, _, _ = ops.gp_predict(self.X, Lf, S, self.Y_mean, self._xstar(x), self._effective_hyp(), want_var=False)
+        return mean
+
+    def build_pred_var(self, x=None):
+        """alpha - colsum((L^-1 K_Xx)^2); noise not added back; asserts >= 0 (gplvm.py:278-288)."""
+        Lf, S = self._factor()
+        _, var, info = ops.gp_predict(self.X, Lf, None, None, self._xstar(x), self._effective_hyp(), want_mean=False)
+        bad = int(info.item())
+        if bad:
+            raise RuntimeError('assert_non_negative(pred_var) failed at test point %d' % (bad - 1))
+        return var
+
+    def build_pred_mean_thresholded(self, pred_mean):
+        return torch.tanh(pred_mean)
+
+    def build_pred_mean_normalized(self, pred_mean):
+        lo, hi = pred_mean.min(), pred_mean.max()
+        return (pred_mean - lo) / (hi - lo)
+
+    def predict_mean(self, x):
+        return to_numpy(self.build_pred_mean(np.array(x, ndmin=2)))
+
+    def predict_variance(self, x):
+        return to_numpy(self.build_pred_var(np.array(x, ndmin=2)))[:, np.newaxis]
+
+    def datapoint_len(self):
+        if self.bottom:
+            return self.bottom.layers[-1].num_v
+        return self.D
+
+    def downprop_latent(self, x, num_samples_to_average=100):
+        """Down-propagate the predictive mean and average (gplvm.py:314-338)."""
+        assert type(x) == np.ndarray
+        assert x.ndim == 1 or x.ndim == 2
+        if x.ndim == 1:
+            x = x[np.newaxis, :]
+        mean = self.build_pred_mean(x)
+        if not self.bottom:
+            return to_numpy(mean)[0] if x.shape[0] == 1 else to_numpy(mean)
+        if x.shape[0] == 1:
+            tiled = mean.expand(num_samples_to_average, -1).contiguous()
+            return to_numpy(self.bottom.downprop(tiled)).mean(axis=0)
+        acc = torch.zeros((x.shape[0], self.datapoint_len()), dtype=torch.float32, device=self.device)
+        for _ in range(num_samples_to_average):
+            acc += self.bottom.downprop(mean)
+        return to_numpy(acc) / num_samples_to_average
+
+    # ---- plotting hooks (accepted, off the hot path) ----------------------------------------------------------------
+    def plot_latent_points(self, iteration=None):
+        assert self.lp_plotter is not None
+        var_diag = to_numpy(self.build_pred_var(self.lp_plotter.grid))
+        fig_name = 'latent_points' + ('' if iteration is None else '-' + str(iteration))
+        self.lp_plotter.plot(to_numpy(self.X), np.log(var_diag), fig_name, self.Y_labels)
+
+    def plot_latent_samples(self, iteration=None):
+        assert self.ls_plotter is not None
+        v_vecs = self.downprop_latent(self.ls_plotter.grid, self.ls_plotter.num_samples_to_average)
+        fig_name = 'latent_samples' + ('' if iteration is None else '-' + str(iteration))
+        self.ls_plotter.plot(v_vecs, fig_name)
+
+    def explore_latent_space(self):
+        assert self.latent_space_explorer is not None
+        self.latent_space_explorer.set_sample_callback(self.downprop_latent)
+        self.latent_space_explorer.set_variance_callback(self.predict_variance)
+        self.latent_space_explorer.plot()
+
+    def save_loss_values(self, loss, iteration):
+        idx = iteration // self.eval_interval
+        self.loss_values[idx] = (iteration, loss)
+        np.save(self.loss_values_fname, self.loss_values[:idx + 1])
+
+    def _eval_step(self, i):
+        loss = float(self.build_loss())
+        self.logger.info('Iteration: %d, Loss: %f', i, loss)
+        self.logger.debug(self)
+        if self.loss_values_fname:
+            self.save_loss_values(loss, i)
+        if self.lp_plotter:
+            self.plot_latent_points(i)
+        if self.ls_plotter:
+            self.plot_latent_samples(iteration=i)
+        return loss
+
+    # ---- optimisation ---------------------------------------------------------------------------------------------------
+    def optimize(self, optimizer, num_iterations=100, eval_interval=0, ckpt_interval=0, ckpt_dir=None,
+                 summary_writer=None, loss_values_fname=None):
+        """Gradient loop over {X, opt_noise, opt_alpha, opt_gamma} (gplvm.py:414-468): each iteration is
+        one fused LML+gradient evaluation and one optimizer kernel on the packed parameters."""
+        optimizer.reset()                                   # fresh slots (gplvm.py:386-396, 430)
+        state = torch.zeros(max(optimizer.state_multiple(), 1) * self._params.numel(), dtype=torch.float32,
+                            device=self.device)
+        grad = torch.zeros_like(self._params)
+        nq = self.N * self.Q
+        i = 0
+        if eval_interval:
+            self.eval_interval = eval_interval
+            if loss_values_fname:
+                self.loss_values_fname = loss_values_fname
+                self.loss_values = np.zeros(shape=(int(np.floor(num_iterations / eval_interval) + 1), 2))
+            self._eval_step(i)
+        try:
+            for i in range(1, num_iterations + 1):
+                scal, dX, info = self._evaluate(want_grad=True)
+                grad[:nq].copy_(dX.view(-1))
+                grad[nq:nq + 3].copy_(scal[3:6])
+                ops.optimizer_step(optimizer.descriptor(), self._params, grad, state)
+                self._version += 1
+                if eval_interval and i % eval_interval == 0:
+                    self._eval_step(i)
+                if ckpt_dir and ckpt_interval and i % ckpt_interval == 0:
+                    self.save_all(i, ckpt_dir)
+                    self.kern.save(i, ckpt_dir)
+        except KeyboardInterrupt:
+            self.logger.info('Training interrupted')
+            if eval_interval:
+                self._eval_step(i)
+            if ckpt_dir and ckpt_interval:
+                self.save_all(i, ckpt_dir)
+                self.kern.save(i, ckpt_dir)
+        pivot = int(self._plan.info.item())
+        if pivot:
+            raise RuntimeError('Cholesky decomposition was not successful: pivot %d is not positive' % pivot)
+
+    def test_generalisation(self, test_data, output_table_path, optimizer, log_var_scaling=0.1, num_iterations=1000,
+                            num_runs=1):
+        """Latent-point search for test images (gplvm.py:470-541) — scope row f2."""
+        raise NotImplementedError('GPLVM.test_generalisation is outside the round-1 hot-path scope (SURVEY.md §8 f2)')

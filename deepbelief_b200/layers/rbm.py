@@ -1,0 +1,433 @@
+"""Binary RBM layer and the CD-k / PCD-k trainer — the B200 counterpart of deepbelief/layers/rbm.py.
+
+Same constructor, method names, argument meaning and return shapes as the reference class
+(rbm.py:29-42 and the method list in SURVEY.md §8b), but eager: methods take / return fp32 CUDA
+tensors [N, units] and run hand-written CUDA through the C ABI:
+  * h_probs / v_probs / sample_* / upprop / downprop / gibbs_sample -> db_layer_forward (one fused
+    GEMM + bias + logistic + sampling launch per call; no materialised transposes, rbm.py:143-147);
+  * train -> the tcgen05 fused chain db_cd_tc_step for binary layers whose sizes are multiples of 8,
+    otherwise the general SIMT path (db_layer_forward chain + db_cd_gradients), then
+    db_optimizer_step; under torch.distributed the packed gradient is sum-all-reduced over NCCL
+    between the two (data-parallel CD).
+Randomness: a counter-based Philox stream per layer (`seed`), or injected draws via the keyword-only
+`draw=` arguments (parity tests).
+"""
+import pickle
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+from .. import dist, ops, preprocessing
+from . import layer
+from .layer import to_device, to_numpy
+
+
+from ..parallel import dist_info as _dist_info, all_reduce_sum_
+
+
+class RBM(layer.Layer):
+    """Binary-binary RBM. Args as the reference: num_v, num_h, W_std=0.1, lr=0.1, temperature=None
+    (Concrete units when set), bottom=None, plotters (accepted, may be None), session (ignored), name.
+    Extra keyword `seed` selects the Philox stream."""
+
+    layer_kind = L.LAYER_RBM
+    visible_act = L.ACT_SIGMOID
+    hidden_act = L.ACT_SIGMOID
+
+    def __init__(self, num_v, num_h, W_std=0.1, lr=0.1, temperature=None, bottom=None, loss_plotter=None,
+                 distr_plotter=None, filter_plotter=None, latent_sample_plotter=None, latent_space_explorer=None,
+                 session=None, name='RBM', seed=0, device='cuda'):
+        assert isinstance(num_v, int) and num_v > 1
+        assert isinstance(num_h, int) and num_h > 1
+        self.num_v, self.num_h = num_v, num_h
+        self.temperature = temperature
+        self.loss_plotter, self.distr_plotter, self.filter_plotter = loss_plotter, distr_plotter, filter_plotter
+        self.ls_plotter = latent_sample_plotter
+        self.latent_space_explorer = latent_space_explorer
+        self.device = device
+        self.rng = ops.Rng(seed=seed)
+
+        # one packed buffer [W | b | c | (opt_sigma_h)] so the optimizer / all-reduce see a single array
+        n = ops.cd_param_count(self.layer_kind, num_v, num_h)
+        self._params = torch.zeros(n, dtype=torch.float32, device=device)
+        vh = num_v * num_h
+        self.W = self._params[:vh].view(num_v, num_h)
+        self.b = self._params[vh:vh + num_v].view(num_v, 1)
+        self.c = self._params[vh + num_v:vh + num_v + num_h].view(1, num_h)
+        # truncated normal, +-2 sigma redraw (rbm.py:59-62) — host RNG, parity runs inject W
+        w0 = np.random.normal(size=(num_v, num_h))
+        bad = np.abs(w0) > 2.0
+        while bad.any():
+            w0[bad] = np.random.normal(size=int(bad.sum()))
+            bad = np.abs(w0) > 2.0
+        self.W.copy_(torch.as_tensor((w0 * W_std).astype(np.float32)))
+        self._init_extra_params()
+
+        self.lr = float(lr)                  # rbm.py:74-78; only changed by lr_drop
+        self.checkpoint_iter = 1             # rbm.py:80-85
+        self.iter = 0
+        self.loss_x_vals = self.loss_y_vals = None
+        self._tc_plan = None
+        self._weights_version = 0
+        params = {'W': self.W, 'b': self.b, 'c': self.c}
+        super().__init__(params, bottom, session, name)
+
+    def _init_extra_params(self):
+        pass
+
+    # ---- state ----------------------------------------------------------------------------------------------
+    def state_tensors(self):
+        return {'params': self._params}
+
+    def save(self, i, ckpt_dir):
+        import os
+        assert os.path.isdir(ckpt_dir), 'The directory does not exist: %s' % ckpt_dir
+        path = os.path.join(ckpt_dir, '%s-%d' % (self.name, i))
+        torch.save({'params': self._params.detach().cpu(), 'ckpt_iter': self.checkpoint_iter, 'lr': self.lr}, path)
+        self.logger.info('State saved')
+        return path
+
+    def restore(self, ckpt_fname):
+        state = torch.load(ckpt_fname, map_location='cpu')
+        self._params.copy_(state['params'].to(self._params.device))
+        self.checkpoint_iter = int(state.get('ckpt_iter', 1))
+        self.lr = float(state.get('lr', self.lr))
+        self._weights_version += 1
+
+    def set_weights(self, W=None, b=None, c=None):
+        """Overwrite parameters (parity runs inject them: TF's initial W cannot be seeded)."""
+        if W is not None:
+            self.W.copy_(to_device(W, self.device).reshape(self.num_v, self.num_h))
+        if b is not None:
+            self.b.copy_(to_device(b, self.device).reshape(self.num_v, 1))
+        if c is not None:
+            self.c.copy_(to_device(c, self.device).reshape(1, self.num_h))
+        self._weights_version += 1
+
+    # ---- hooks specialised by the Gaussian variants ------------------------------------------------------------
+    def _h_scale(self):      # multiplies v@W before the bias (bgrbm.py:80)
+        return None
+
+    def _v_div(self):        # divides h before W@h^T (bgrbm.py:126)
+        return None
+
+    def _hidden_sampling(self, sample):
+        """(sample_kind, noise_scale) for hidden units."""
+        if self.temperature is not None:
+            return L.SAMPLE_CONCRETE, None                                   # rbm.py:178-179
+        return (L.SAMPLE_BERNOULLI if sample else L.SAMPLE_NONE), None
+
+    def _visible_sampling(self, sample):
+        if self.temperature is not None:
+            return L.SAMPLE_CONCRETE, None                                   # rbm.py:183-184
+        return (L.SAMPLE_BERNOULLI if sample else L.SAMPLE_NONE), None
+
+    # ---- net inputs and probabilities ----------------------------------------------------------------------------
+    def _up(self, v_batch, act, sample_kind=L.SAMPLE_NONE, noise=None, draw=None, want_act=True):
+        return ops.layer_forward(to_device(v_batch, self.device), self.W, self.c, False, act, sample_kind,
+                                 self.temperature, col_scale=self._h_scale(), noise_scale=noise, injected=draw,
+                                 rng=self.rng, want_act=want_act)
+
+    def _down(self, h_batch, act, sample_kind=L.SAMPLE_NONE, noise=None, draw=None, want_act=True):
+        return ops.layer_forward(to_device(h_batch, self.device), self.W, self.b, True, act, sample_kind,
+                                 self.temperature, a_div=self._v_div(), noise_scale=noise, injected=draw,
+                                 rng=self.rng, want_act=want_act)
+
+    def h_net_input(self, v_batch):
+        """v @ W + c -> [N, H] (rbm.py:119-131)."""
+        return self._up(v_batch, L.ACT_LINEAR)[0]
+
+    def v_net_input(self, h_batch):
+        """(W @ h^T + b)^T -> [N, V] (rbm.py:133-147)."""
+        return self._down(h_batch, L.ACT_LINEAR)[0]
+
+    def h_probs(self, v_batch):
+        """sigmoid(h_net_input) (rbm.py:149-161)."""
+        return self._up(v_batch, self.hidden_act)[0]
+
+    def v_probs(self, h_batch):
+        """sigmoid(v_net_input) (rbm.py:163-175)."""
+        return self._down(h_batch, self.visible_act)[0]
+
+    # ---- sampling ------------------------------------------------------------------------------------------------------
+    def sample_h(self, h_probs, sample=True, summary=True, *, draw=None):
+        """Bernoulli `p > u` (rbm.py:187-213), Concrete when temperature is set (rbm.py:243-258)."""
+        kind, noise = self._hidden_sampling(sample)
+        if kind == L.SAMPLE_NONE:
+            return to_device(h_probs, self.device)
+        return ops.sample(to_device(h_probs, self.device), kind, self.temperature, noise_scale=noise, injected=draw,
+                          rng=self.rng)
+
+    def sample_v(self, v_probs, sample=True, summary=True, *, draw=None):
+        kind, noise = self._visible_sampling(sample)
+        if kind == L.SAMPLE_NONE:
+            return to_device(v_probs, self.device)
+        return ops.sample(to_device(v_probs, self.device), kind, self.temperature, noise_scale=noise, injected=draw,
+                          rng=self.rng)
+
+    def _sample_h(self, h_probs, sample=True, summary=True, *, draw=None):
+        return RBM.sample_h(self, h_probs, sample, summary, draw=draw)
+
+    def _sample_v(self, v_probs, sample=True, summary=True, *, draw=None):
+        return RBM.sample_v(self, v_probs, sample, summary, draw=draw)
+
+    # fused probability + sample (one launch): what upprop / downprop / gibbs_sample use internally
+    def _up_sample(self, v_batch, sample=True, draw=None, want_probs=False):
+        kind, noise = self._hidden_sampling(sample)
+        act, s = self._up(v_batch, self.hidden_act, kind, noise, draw, want_act=(want_probs or kind == L.SAMPLE_NONE))
+        return act, (s if s is not None else act)
+
+    def _down_sample(self, h_batch, sample=True, draw=None, want_probs=False):
+        kind, noise = self._visible_sampling(sample)
+        act, s = self._down(h_batch, self.visible_act, kind, noise, draw, want_act=(want_probs or kind == L.SAMPLE_NONE))
+        return act, (s if s is not None else act)
+
+    # ---- stack traversal ---------------------------------------------------------------------------------------------
+    def upprop(self, v_batch, sample=True, summary=True, *, draws=None):
+        """Sample of this layer's hidden units from a batch fed to the LOWEST layer (rbm.py:277-300).
+        draws: optional list of injected draws, one per layer from the bottom up."""
+        draws = list(draws) if draws is not None else None
+        if self.bottom:
+            v_batch = self.bottom.upprop(v_batch, sample, summary, draws=draws[:-1] if draws else None)
+        return self._up_sample(v_batch, sample, draws[-1] if draws else None)[1]
+
+    def downprop(self, h_batch, sample=True, summary=True, *, draws=None):
+        """Sample of the LOWEST layer's visibles from this layer's hiddens (rbm.py:302-325).
+        draws: optional injected draws, this layer first."""
+        draws = list(draws) if draws is not None else None
+        v_batch = self._down_sample(h_batch, sample, draws[0] if draws else None)[1]
+        if self.bottom:
+            v_batch = self.bottom.downprop(v_batch, sample, summary, draws=draws[1:] if draws else None)
+        return v_batch
+
+    def propagate(self, v_batch, k=1, sample=True, summary=True):
+        """k cycles of upprop + downprop (rbm.py:327-349)."""
+        assert k > 0, 'k must be > 0'
+        for _ in range(k):
+            v_batch = self.downprop(self.upprop(v_batch, sample, summary), sample, summary)
+        return v_batch
+
+    def gibbs_sample(self, h_batch, k=1, summary=True, *, draws=None):
+        """k Gibbs steps; returns the LAST (v_probs, v, h_probs, h). Always samples — the reference
+        passes `summary` into the `sample` slot (rbm.py:368,370; SURVEY §8 a'.1).
+        draws: optional list of k (draw_v, draw_h)."""
+        assert k > 0, 'k must be > 0'
+        for s in range(k):
+            dv, dh = draws[s] if draws is not None else (None, None)
+            last = s == k - 1
+            v_probs, v_batch = self._down_sample(h_batch, True, dv, want_probs=last)
+            h_probs, h_batch = self._up_sample(v_batch, True, dh, want_probs=last)
+        return v_probs, v_batch, h_probs, h_batch
+
+    # ---- energies ------------------------------------------------------------------------------------------------------
+    def free_energy(self, v_batch):
+        """F(v) = -(v b + sum_j softplus((vW + c)_j)) -> [N, 1] (rbm.py:378-396)."""
+        return ops.free_energy(self.layer_kind, to_device(v_batch, self.device), self.W, self.b, self.c,
+                               self._sigma_vector())
+
+    def _sigma_vector(self):
+        return None
+
+    def cd_loss(self, v_0_batch, v_k_batch):
+        """mean F(v0) - mean F(vk) as a 0-d tensor (rbm.py:398-415)."""
+        f0 = self.free_energy(v_0_batch)
+        fk = self.free_energy(v_k_batch)
+        return (f0.sum() - fk.sum()) / f0.shape[0]
+
+    def cd_gradient(self, v_0_batch, v_k_batch, inv_global_n=None):
+        """Packed gradient of cd_loss wrt (W | b | c [| opt_sigma_h]) — what TF autodiff of rbm.py:664
+        produces."""
+        return ops.cd_gradients(self.layer_kind, to_device(v_0_batch, self.device), to_device(v_k_batch, self.device),
+                                self._params, self.num_v, self.num_h, inv_global_n)
+
+    # ---- generation helpers ---------------------------------------------------------------------------------------------
+    def datapoint_len(self):
+        if self.bottom:
+            return self.bottom.layers[-1].num_v
+        return self.num_v
+
+    def downprop_latent(self, x, num_samples_to_average=100):
+        """Average of down-propagated samples from hidden configurations x (rbm.py:437-458)."""
+        assert type(x) == np.ndarray
+        assert x.ndim == 1 or x.ndim == 2
+        if x.ndim == 1:
+            x = x[np.newaxis, :]
+        if x.shape[0] == 1:
+            x_batch = np.tile(x, (num_samples_to_average, 1))
+            return np.mean(to_numpy(self.downprop(x_batch, True)), axis=0)
+        acc = torch.zeros((x.shape[0], self.datapoint_len()), dtype=torch.float32, device=self.device)
+        xd = to_device(x, self.device)
+        for _ in range(num_samples_to_average):
+            acc += self.downprop(xd, True)
+        return to_numpy(acc) / num_samples_to_average
+
+    def plot_latent_samples(self, iteration=None):
+        assert self.ls_plotter is not None
+        v_vecs = self.downprop_latent(self.ls_plotter.grid, self.ls_plotter.num_samples_to_average)
+        fig_name = 'latent_samples' + ('' if iteration is None else '-' + str(iteration))
+        self.ls_plotter.plot(v_vecs, fig_name)
+
+    def explore_latent_space(self):
+        self.latent_space_explorer.set_sample_callback(self.downprop_latent)
+        self.latent_space_explorer.plot()
+
+    def test_generalisation(self, test_data, output_table_path, num_iterations=1000, num_runs=1,
+                            num_samples_to_average=100):
+        """Gibbs-chain reconstruction of each test point (rbm.py:470-521): a chain of
+        `num_samples_to_average` copies is propagated up and down; the distance is the cross entropy
+        between the chain average and the test point."""
+        table = []
+        for idx in range(test_data.shape[0]):
+            test_point = np.reshape(test_data[idx], (1, test_data.shape[1])).astype(np.float32)
+            tp = to_device(test_point, self.device)
+            datapoint = to_device(np.tile(test_point, (num_samples_to_average, 1)), self.device)
+            prev_dist = 10e7
+            for run in range(num_runs):
+                for _ in range(num_iterations):
+                    datapoint = self.downprop(self.upprop(datapoint, True), True)
+                model_point = to_numpy(self.downprop(self.upprop(datapoint, True), True)).mean(axis=0)
+                distance = float(dist.cross_entropy(datapoint.mean(dim=0, keepdim=True), tp))
+                if distance < prev_dist:
+                    if table and table[-1][0] == idx:
+                        del table[-1]
+                    table.append((idx, distance, test_point, model_point))
+                    prev_dist = distance
+                self.logger.info('Test point: {}, Run: {}, Distance: {}'.format(idx, run, distance))
+        with open(output_table_path, 'wb') as f:
+            pickle.dump(table, f)
+
+    # ---- evaluation ------------------------------------------------------------------------------------------------------
+    def _eval_step(self, test_data, test_mean_fname=None, test_std_fname=None):
+        """One-step reconstruction MSE on a test batch, pushed down to the pixels (rbm.py:648-662, 534-578)."""
+        test_batch = to_device(test_data.next_batch(), self.device)
+        v0 = self.bottom.upprop(test_batch) if self.bottom else test_batch
+        h0 = self._up_sample(v0, True)[1]
+        v1 = self.downprop(h0)
+        test_loss = float(dist.mse(v1, test_batch))
+        self.logger.info('Iteration: %d, Test loss: %f', self.iter, test_loss)
+        self.logger.debug(self)
+        self.loss_x_vals.append(self.iter)
+        self.loss_y_vals.append(test_loss)
+        if self.loss_plotter:
+            self.loss_plotter.set_data(self.loss_x_vals, self.loss_y_vals, 'loss_' + self.name)
+        if self.distr_plotter:
+            data_distr = test_batch.mean(dim=0, keepdim=True)
+            model_distr = v1.mean(dim=0, keepdim=True)
+            if test_mean_fname and test_std_fname:
+                data_distr = preprocessing.unstandardize(data_distr, test_mean_fname, test_std_fname)
+                model_distr = preprocessing.unstandardize(model_distr, test_mean_fname, test_std_fname)
+            self.distr_plotter.set_data((to_numpy(data_distr), to_numpy(model_distr)),
+                                        'distr_' + self.name + '_' + str(self.iter))
+        if self.filter_plotter:
+            self.filter_plotter.set_data(to_numpy(self.W), 'filters_' + self.name + '_' + str(self.iter))
+        return test_loss
+
+    # ---- training ----------------------------------------------------------------------------------------------------------
+    def _tc_eligible(self, n_rows):
+        return (self.layer_kind == L.LAYER_RBM and self.temperature is None and n_rows % 8 == 0 and
+                self.num_v % 8 == 0 and self.num_h % 8 == 0 and n_rows >= 8)
+
+    def cd_step(self, v_0_batch, k=1, persistent=None, *, grad=None, n_global=None, injected=None, force_simt=False):
+        """Positive phase + k Gibbs steps + packed CD gradient for one (local) batch; returns
+        (grad, v_k, h_k). `persistent`: PCD chain state to start from and update (fp32 [N,H] tensor,
+        general path only — the tensor-core path keeps its own fp16 state in the plan)."""
+        v0 = to_device(v_0_batch, self.device)
+        n = v0.shape[0]
+        inv_n = 1.0 / float(n_global or n)
+        if grad is None:
+            grad = torch.empty_like(self._params)
+        if self._tc_eligible(n) and not force_simt and persistent is None:
+            plan = self._tc_plan
+            if plan is None or (plan.N, plan.k, plan.n_global) != (n, k, n_global or n):
+                plan = self._tc_plan = ops.CdTcPlan(n, self.num_v, self.num_h, k, pcd=False, n_global=n_global or n,
+                                                    device=self.device)
+                plan.n_global = n_global or n
+                plan.version = -1
+            if plan.version != self._weights_version:
+                plan.refresh_weights(self._params)
+                plan.version = self._weights_version
+            plan.step(v0, self._params, grad, injected=injected, rng=self.rng)
+            return grad, None, None
+        # general path: one fused launch per half Gibbs step
+        off = 0
+
+        def take(count):
+            nonlocal off
+            if injected is None:
+                return None
+            d = injected[off:off + count].view(n, -1)
+            off += count
+            return d
+        h0 = self._up_sample(v0, True, take(n * self.num_h))[1]
+        h = h0 if persistent is None else persistent
+        draws = None
+        if injected is not None:
+            draws = []
+            for _ in range(k):
+                dv = take(n * self.num_v) if self._visible_sampling(True)[0] != L.SAMPLE_NONE else None
+                draws.append((dv, take(n * self.num_h)))
+        _, vk, _, hk = self.gibbs_sample(h, k, draws=draws)
+        if persistent is not None:
+            persistent.copy_(hk)
+        ops.cd_gradients(self.layer_kind, v0, vk, self._params, self.num_v, self.num_h, inv_n, grad)
+        return grad, vk, hk
+
+    def apply_gradient(self, optimizer, grad, opt_state, lr=None):
+        """All-reduce (data parallel) + optimizer step on the packed parameters."""
+        all_reduce_sum_(grad)
+        ops.optimizer_step(optimizer.descriptor(lr), self._params, grad, opt_state)
+        self._weights_version += 1
+
+    def new_optimizer_state(self, optimizer):
+        optimizer.reset()                                    # fresh slots per train() (rbm.py:107-117, 670)
+        mult = optimizer.state_multiple()
+        return torch.zeros(max(mult, 1) * self._params.numel(), dtype=torch.float32, device=self.device)
+
+    def train(self, optimizer, training_data, test_data, num_gibbs_steps=1, pcd=True, lr_interval=None,
+              lr_drop=None, test_mean_fname=None, test_std_fname=None, max_iterations=1000, eval_interval=0,
+              ckpt_interval=0, ckpt_dir=None):
+        """CD-k / PCD-k training loop (rbm.py:595-711). One iteration = next batch -> (lower layers
+        re-sampled, rbm.py:621-623) -> chain -> gradient -> optimizer. Under torch.distributed every
+        rank feeds its own row shard and the packed gradient is summed over NCCL."""
+        rank, world = _dist_info()
+        opt_state = self.new_optimizer_state(optimizer)
+        n_local = training_data.batch_shape()[0]
+        n_global = n_local * world
+        self.rng.row_offset = rank * n_local            # G-invariant draws
+        grad = torch.empty_like(self._params)
+
+        persistent = None
+        if pcd:
+            # the first batch only initialises the persistent chain and is discarded (rbm.py:631-641)
+            first = to_device(training_data.next_batch(), self.device)
+            v_first = self.bottom.upprop(first) if self.bottom else first
+            persistent = self._up_sample(v_first, True)[1].clone()
+
+        start_iter = self.checkpoint_iter
+        max_iter = max_iterations + 1
+        if eval_interval:
+            self.loss_x_vals, self.loss_y_vals = [], []
+            self.iter = start_iter - 1                     # first evaluation before any update (rbm.py:684-686)
+            self._eval_step(test_data, test_mean_fname, test_std_fname)
+
+        lr_now = optimizer.learning_rate
+        for self.iter in range(start_iter, max_iter):
+            batch = to_device(training_data.next_batch(), self.device)
+            v0 = self.bottom.upprop(batch) if self.bottom else batch
+            self.cd_step(v0, num_gibbs_steps, persistent, grad=grad, n_global=n_global)
+            self.apply_gradient(optimizer, grad, opt_state, lr_now)
+            if lr_interval and lr_drop and self.iter % lr_interval == 0:
+                self.lr *= lr_drop                         # rbm.py:672-673, 703-704: only layer.lr changes
+            if eval_interval and self.iter % eval_interval == 0:
+                self._eval_step(test_data, test_mean_fname, test_std_fname)
+            if ckpt_dir and ckpt_interval and self.iter % ckpt_interval == 0:
+                self.checkpoint_iter += ckpt_interval      # rbm.py:676, 709-711
+                self.save(self.iter, ckpt_dir)
+
+    def backprop(self, training_data, test_data, training_sampling=True, training_num_propagation_cycles=5,
+                 test_num_propagation_cycles=5, learning_rate=0.1, max_iterations=1000, ignore_ckpt_iter=False,
+                 eval_interval=0, ckpt_interval=0, ckpt_dir=None):
+        """Cross-entropy fine-tuning through propagate() (rbm.py:713-789) — a 'next' row of the scope
+        table; not part of the accelerated hot path yet."""
+        raise NotImplementedError('RBM.backprop is outside the round-1 hot-path scope (SURVEY.md §8 f4)')

@@ -123,6 +123,13 @@ def optimizer_step(opt, params, grad, state):
     L.check(rc, 'db_optimizer_step')
 
 
+def softplus(x):
+    x = _f32(x)
+    out = torch.empty_like(x)
+    L.check(L.lib().db_softplus(L.handle(), L.stream(), L.fptr(x), x.numel(), L.fptr(out)), 'db_softplus')
+    return out
+
+
 def mse(a, b):
     a = _f32(a)
     b = _f32(b)

@@ -1,0 +1,61 @@
+"""Data-parallel contrastive divergence: host-side plumbing (new work — the reference is single
+device).
+
+Rows of the minibatch are independent given (W, b, c), so rank g owns rows
+[g*N/G, (g+1)*N/G) of every batch; parameters and optimizer state are replicated. The only exchange
+per iteration is a sum-all-reduce of the packed gradient [dW | db | dc], each rank having scaled its
+local sums by 1/N_global, after which every rank applies the identical optimizer step (replicas stay
+bit-identical). Philox counters are keyed by the GLOBAL row (`row_offset`), so the samples do not
+depend on the number of GPUs.
+"""
+import os
+
+import torch
+import torch.distributed as td
+
+
+def dist_info():
+    """(rank, world_size); (0, 1) when torch.distributed is not initialised."""
+    if td.is_available() and td.is_initialized():
+        return td.get_rank(), td.get_world_size()
+    return 0, 1
+
+
+def init_from_env(backend=None):
+    """Initialise the default process group from torchrun's environment (RANK / WORLD_SIZE / MASTER_*)."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world <= 1 or (td.is_available() and td.is_initialized()):
+        return dist_info()
+    if backend is None:
+        backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+    if backend == 'nccl':
+        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    td.init_process_group(backend=backend)
+    return dist_info()
+
+
+def shard_bounds(n_global, rank, world):
+    """Row range [lo, hi) of `rank`: equal shards, N_global must divide evenly (keeps Philox rows aligned)."""
+    if n_global % world:
+        raise ValueError('global batch %d is not divisible by %d ranks' % (n_global, world))
+    per = n_global // world
+    return rank * per, (rank + 1) * per
+
+
+def all_reduce_sum_(tensor):
+    """In-place sum over the data-parallel group (NCCL on GPUs, gloo in the CPU tests)."""
+    _, world = dist_info()
+    if world > 1:
+        td.all_reduce(tensor, op=td.ReduceOp.SUM)
+    return tensor
+
+
+def max_over_ranks(value, device=None):
+    """Max of a python float over ranks (timing: a step is as slow as its slowest rank)."""
+    _, world = dist_info()
+    if world == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64,
+                     device=device or ('cuda' if td.get_backend() == 'nccl' else 'cpu'))
+    td.all_reduce(t, op=td.ReduceOp.MAX)
+    return float(t.item())

@@ -202,6 +202,9 @@ int db_gp_predict(db_handle_t h, db_stream_t stream, const float* X, const float
 int db_gp_effective_hyp(db_handle_t h, db_stream_t stream, const float* hyp_opt, int flags, float fixed_noise,
                         float jitter, float* hyp_out);
 
+/* out[i] = softplus(x[i]) — the positivity constraint of sigma_h / alpha_h (bgrbm.py:51, gprbm.py:83). */
+int db_softplus(db_handle_t h, db_stream_t stream, const float* x, int n, float* out);
+
 /* ---- small fused helpers used by the layer API ------------------------------------------------ */
 /* mean over rows of the sum over columns of (a-b)^2 — dist.py:5-21. out: device float. */
 int db_mse(db_handle_t h, db_stream_t stream, const float* a, const float* b, int N, int D, float* out);
