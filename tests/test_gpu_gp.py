@@ -1,0 +1,245 @@
+"""GPU parity tests of the GP path (Gram, Cholesky, triangular solve, LML + analytic gradient, prediction,
+GPLVM.optimize) against the fp64 CPU oracle and the goldens produced by the reference's own code.
+
+Tolerance: losses / log-likelihoods 1e-4 relative; gradient arrays 1e-4 norm-relative, or
+the error of the fp32 restatement of the reference formula where that is larger (ill-conditioned K at
+sigma^2 = 0.01, SURVEY.md §7 hard part 3)."""
+import numpy as np
+import pytest
+import scipy.linalg
+import torch
+
+from conftest import has_cuda
+from oracle import gp as ogp, rbm as orbm
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not has_cuda(), reason='needs a CUDA device')]
+
+LOSS_RTOL = 1e-4
+GRAD_NORMREL = 1e-4
+
+
+def _np(t):
+    return t.detach().cpu().numpy().astype(np.float64)
+
+
+def _cu(a):
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+def _normrel(a, b):
+    return np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-300)
+
+
+def test_se_kernel_reference_unit_tests_and_goldens(gp_golden):
+    """tests/test_gplvm.py of the reference (K(X)==K(X,X), diag variants) + values from the reference's code."""
+    from deepbelief_b200.layers.gplvm import SEKernel
+    g = gp_golden
+    for an, (a, ga) in {'unit': (1.0, 1.0), 'ag': (1.7, 0.6)}.items():
+        kern = SEKernel(alpha=a, gamma=ga)
+        for tag in ('k83', 'k30'):
+            X, Y = g[tag + '/X'], g[tag + '/Y']
+            pre = '%s/float64/%s/' % (tag, an)
+            kx, kxx, kxy = _np(kern.K(X)), _np(kern.K(X, X)), _np(kern.K(X, Y))
+            np.testing.assert_allclose(kx, kxx, rtol=1e-6)
+            np.testing.assert_allclose(kx, g[pre + 'K_X'], rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(kxy, g[pre + 'K_XY'], rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(_np(kern.K(X, diag=True)), g[pre + 'K_X_diag'], rtol=1e-6)
+            if X.shape == Y.shape:
+                np.testing.assert_allclose(_np(kern.K(X, Y, diag=True)), np.diag(kxy), rtol=1e-6)
+                np.testing.assert_allclose(_np(kern.K(X, Y, diag=True)), g[pre + 'K_XY_diag'], rtol=1e-5, atol=1e-6)
+    assert abs(float(kern.alpha) - 1.7) < 1e-6 and abs(float(kern.gamma) - 0.6) < 1e-6
+    fixed = SEKernel(alpha=False, gamma=False)
+    assert float(fixed.alpha) == 1.0 and float(fixed.gamma) == 1.0       # gplvm.py:31-32,41-42
+
+
+@pytest.mark.parametrize('N', [5, 64, 130, 700])
+def test_cholesky_and_triangular_solves(N):
+    from deepbelief_b200 import ops
+    rs = np.random.RandomState(N)
+    X = rs.normal(size=(N, 2))
+    K = ogp.se_kernel(X, None, 1.3, 0.9) + 0.3 * np.eye(N)
+    A = _cu(K)
+    info = ops.potrf_lower(A)
+    assert int(info.item()) == 0
+    Lref = np.linalg.cholesky(K)
+    assert _normrel(np.tril(_np(A)), Lref) < 2e-6
+    assert np.allclose(np.triu(_np(A), 1), np.triu(K, 1), rtol=1e-6)       # strict upper triangle untouched
+    for nrhs in (1, 37, 300):
+        B = rs.normal(size=(N, nrhs))
+        fwd = _np(ops.trsm_lower(A, _cu(B), trans=False))
+        bwd = _np(ops.trsm_lower(A, _cu(B), trans=True))
+        assert _normrel(fwd, scipy.linalg.solve_triangular(Lref, B, lower=True)) < 5e-5
+        assert _normrel(bwd, scipy.linalg.solve_triangular(Lref, B, lower=True, trans='T')) < 5e-5
+
+
+def test_cholesky_reports_non_positive_definite_input():
+    from deepbelief_b200 import ops
+    N = 100
+    rs = np.random.RandomState(0)
+    M = rs.normal(size=(N, N))
+    K = M @ M.T + N * np.eye(N)
+    K[70, 70] = -5.0                          # first failing pivot at (1-based) 71
+    info = ops.potrf_lower(_cu(K))
+    assert int(info.item()) == 71
+
+
+def _gplvm_pair(g, cname):
+    from deepbelief_b200.layers.gplvm import GPLVM, SEKernel
+    trainable = cname == 'trainable'
+    kw = dict(noise_variance=0.7, fixed_noise_variance=False, alpha=1.3, gamma=0.8) if trainable else \
+        dict(noise_variance=0.01, fixed_noise_variance=True, alpha=False, gamma=False)
+    pre = 'gplvm/%s/float64/' % cname
+    Yraw = g['gplvm/Y']
+    kern = SEKernel(alpha=kw['alpha'], gamma=kw['gamma'])
+    lay = GPLVM(Yraw.astype(np.float32), 2, X0=g[pre + 'X0'].astype(np.float32), kern=kern,
+                noise_variance=kw['noise_variance'], fixed_noise_variance=kw['fixed_noise_variance'])
+    lay.build_model()
+    oa, og, on = g['gplvm/%s/opt' % cname]
+    orc = ogp.GPLVMOracle(g[pre + 'Y_centered'], g[pre + 'X0'], opt_alpha=oa, opt_gamma=og, opt_noise=on, fixed_noise=0.01,
+                          jitter=1e-6, trainable=(trainable,) * 3)
+    return lay, orc, pre
+
+
+@pytest.mark.parametrize('cname', ['trainable', 'gpdbn'])
+def test_gplvm_loss_gradient_prediction_vs_oracle_and_reference_goldens(gp_golden, cname):
+    g = gp_golden
+    lay, orc, pre = _gplvm_pair(g, cname)
+    from deepbelief_b200 import compat
+    sess = compat.Session()
+    np.testing.assert_allclose(_np(lay.Y), g[pre + 'Y_centered'], atol=1e-6)
+    np.testing.assert_allclose(sess.run(lay.K), g[pre + 'K'], rtol=1e-5, atol=1e-6)
+    assert _normrel(sess.run(lay.L), g[pre + 'L']) < 2e-5
+    np.testing.assert_allclose(sess.run(lay.loss), g[pre + 'loss'], rtol=LOSS_RTOL)
+    np.testing.assert_allclose(sess.run(lay.log_det), g[pre + 'log_det'], rtol=LOSS_RTOL, atol=1e-4)
+    loss, dX, dh = lay.loss_and_grad()
+    w_dX, w_da, w_dg, w_dn = orc.grad()
+    # error budget: 1e-4, or the error of the fp32 restatement of the reference formula if that is larger
+    o32 = ogp.GPLVMOracle(orc.Y, orc.X, opt_alpha=orc.opt_alpha, opt_gamma=orc.opt_gamma, opt_noise=orc.opt_noise,
+                          fixed_noise=0.01, jitter=1e-6, trainable=orc.trainable, dtype=np.float32)
+    budget = max(GRAD_NORMREL, 2 * _normrel(o32.grad()[0].astype(np.float64), w_dX))
+    assert _normrel(_np(dX), w_dX) < budget
+    assert _normrel(_np(dX), g['gplvm/%s/fd_dX' % cname]) < budget + 1e-4          # reference-code finite differences
+    if cname == 'trainable':
+        np.testing.assert_allclose(_np(dh), [w_da, w_dg, w_dn], rtol=GRAD_NORMREL * 3)
+        np.testing.assert_allclose(_np(dh), g['gplvm/trainable/fd_dopt'], rtol=5e-4)
+    else:
+        assert np.all(_np(dh) == 0)
+    xs = g['gplvm/xstar']
+    mean = lay.predict_mean(xs)
+    var = lay.predict_variance(xs)
+    assert var.shape == (xs.shape[0], 1)
+    m_budget = 1e-4 if cname == 'trainable' else 2e-3          # sigma^2 = 0.01: cond(K) ~ 1e4 in fp32
+    assert _normrel(mean, g[pre + 'pred_mean']) < m_budget
+    np.testing.assert_allclose(var[:, 0], g[pre + 'pred_var'], rtol=m_budget * 10, atol=m_budget)
+
+
+def test_gplvm_on_horses_matches_anchors(horses, gp_golden):
+    """GPLVM at construction on the bundled horses data (SURVEY §8c anchor (3); golden from the reference's code)."""
+    from deepbelief_b200.layers.gplvm import GPLVM
+    lay = GPLVM(horses, 2, noise_variance=1.0)
+    assert (lay.N, lay.D, lay.Q) == (328, 1024, 2)
+    X0 = _np(lay.X)
+    ref_X0 = gp_golden['horses/float64/X0']
+    for q in range(2):                    # PCA eigenvector signs are arbitrary
+        s = np.sign(np.dot(X0[:, q], ref_X0[:, q]))
+        np.testing.assert_allclose(s * X0[:, q], ref_X0[:, q], atol=2e-3)
+    loss, dX, dh = lay.loss_and_grad()
+    np.testing.assert_allclose(float(loss), float(gp_golden['horses/float64/loss']), rtol=LOSS_RTOL)
+    np.testing.assert_allclose(float(lay.build_log_det()), 36.850482771829924, rtol=LOSS_RTOL)
+    np.testing.assert_allclose(np.linalg.norm(_np(dX)), 891.6048745762016, rtol=2e-4)
+    np.testing.assert_allclose(_np(dh), [4347.456017283226, -9954.42826462195, 92050.97401113895], rtol=2e-4)
+
+
+def test_gplvm_optimize_follows_oracle_adam(gp_golden):
+    from deepbelief_b200 import compat as tf
+    g = gp_golden
+    lay, orc, pre = _gplvm_pair(g, 'trainable')
+    iters = 5
+    lay.optimize(tf.train.AdamOptimizer(learning_rate=1e-2), num_iterations=iters)
+    theta = np.concatenate([orc.X.ravel(), [orc.opt_alpha, orc.opt_gamma, orc.opt_noise]])
+    adam = orbm.Adam(1e-2)
+    NQ = orc.N * orc.Q
+    for _ in range(iters):
+        o = ogp.GPLVMOracle(orc.Y, theta[:NQ].reshape(orc.N, orc.Q), opt_alpha=theta[NQ], opt_gamma=theta[NQ + 1],
+                            opt_noise=theta[NQ + 2], jitter=1e-6)
+        dX, da, dg, dn = o.grad()
+        theta = adam.step(theta, np.concatenate([dX.ravel(), [da, dg, dn]]))
+    got = _np(lay._params)
+    assert np.max(np.abs(got - theta)) < 2e-4             # 5 steps of size <= 1e-2
+    final = ogp.GPLVMOracle(orc.Y, theta[:NQ].reshape(orc.N, orc.Q), opt_alpha=theta[NQ], opt_gamma=theta[NQ + 1],
+                            opt_noise=theta[NQ + 2], jitter=1e-6).loss()[0]
+    np.testing.assert_allclose(float(lay.build_loss()), final, rtol=LOSS_RTOL)
+    assert final < orc.loss()[0]                          # and the loss went down
+
+
+def test_non_pd_and_negative_variance_are_reported():
+    from deepbelief_b200 import ops
+    from deepbelief_b200.layers.gplvm import GPLVM
+    rs = np.random.RandomState(0)
+    Y = rs.normal(size=(40, 6)).astype(np.float32)
+    X0 = np.zeros((40, 2), dtype=np.float32)              # all latents equal + zero noise -> singular K
+    lay = GPLVM(Y, 2, X0=X0, noise_variance=0.0, fixed_noise_variance=True)
+    with pytest.raises(RuntimeError):
+        lay.build_model()
+        lay.predict_mean(np.zeros((1, 2)))
+    with pytest.raises(AssertionError):
+        GPLVM([[1.0]], 2)                                  # gplvm.py:110
+
+
+@pytest.mark.parametrize('N,D', [(1500, 96)])
+def test_mid_size_against_oracle(N, D):
+    """A size where the fp64 oracle still finishes in seconds."""
+    from deepbelief_b200 import ops
+    rs = np.random.RandomState(1)
+    X = rs.normal(size=(N, 2))
+    Y = rs.normal(size=(N, D)); Y -= Y.mean(0)
+    orc = ogp.GPLVMOracle(Y, X, jitter=1e-6)
+    plan = ops.GplvmPlan(N, 2, D)
+    hyp = _cu([orc.opt_alpha, orc.opt_gamma, orc.opt_noise])
+    scal, dX, info = plan.evaluate(_cu(X), _cu(Y), hyp, 7, jitter=1e-6)
+    assert int(info.item()) == 0
+    loss, logdet, ssq, _, _ = orc.loss()
+    np.testing.assert_allclose(float(scal[0]), loss, rtol=LOSS_RTOL)
+    w_dX, w_da, w_dg, w_dn = orc.grad()
+    assert _normrel(_np(dX), w_dX) < GRAD_NORMREL
+    np.testing.assert_allclose(_np(scal[3:6]), [w_da, w_dg, w_dn], rtol=3e-4)
+
+
+def test_full_size_n5000_properties():
+    """BASELINE 'GPLVM at N=5000' (D=784, Q=2) through size-independent properties: L L^T reproduces K, the
+    triangular solve inverts L, loss pieces are consistent with the factor, and the gradient agrees with a
+    directional finite difference of the (GPU) loss."""
+    from deepbelief_b200 import ops
+    N, D, Q = 5000, 784, 2
+    gen = torch.Generator(device='cuda').manual_seed(0)
+    X = torch.randn(N, Q, device='cuda', generator=gen)
+    Y = torch.randn(N, D, device='cuda', generator=gen)
+    Y = Y - Y.mean(0, keepdim=True)
+    hyp_opt = _cu([0.5413, 0.5413, 0.5413])
+    plan = ops.GplvmPlan(N, Q, D)
+    Lf = torch.zeros(N, N, device='cuda')
+    scal, dX, info = plan.evaluate(X, Y, hyp_opt, 7, jitter=1e-6, L_out=Lf)
+    assert int(info.item()) == 0
+    hyp = ops.gp_effective_hyp(hyp_opt, 7, 0.0, 1e-6)
+    K = ops.gram_rbf(X, None, hyp, add_noise=True)
+    assert torch.equal(K, K.t())                                              # symmetric, exact
+    Lt = torch.tril(Lf).double()
+    resid = (Lt @ Lt.t() - K.double()).abs().max() / K.double().abs().max()   # torch fp64 only as the checker
+    assert float(resid) < 2e-6
+    S = ops.trsm_lower(Lf, Y.clone())
+    assert float((Lt @ S.double() - Y.double()).abs().max()) < 5e-4
+    np.testing.assert_allclose(float(scal[2]), float((S.double() ** 2).sum()), rtol=1e-5)
+    np.testing.assert_allclose(float(scal[1]), float(2 * torch.log(torch.diagonal(Lt)).sum()), rtol=1e-5)
+    # directional derivative: loss(X + t d) - loss(X - t d) ~ 2 t <dX, d>, with the loss evaluated in fp64 from K
+    d = torch.randn(N, Q, device='cuda', generator=gen)
+    d = d / d.norm()
+
+    def loss64(Xm):
+        Km = ops.gram_rbf(Xm.float().contiguous(), None, hyp, add_noise=True).double()
+        Lm = torch.linalg.cholesky(Km)
+        Sm = torch.linalg.solve_triangular(Lm, Y.double(), upper=False)
+        return 0.5 * ((Sm ** 2).sum() + D * 2 * torch.log(torch.diagonal(Lm)).sum())
+    t = 1e-2
+    fd = float((loss64(X + t * d) - loss64(X - t * d)) / (2 * t))
+    an = float((dX.double() * d.double()).sum())
+    assert abs(fd - an) / (abs(fd) + 1e-30) < 5e-3

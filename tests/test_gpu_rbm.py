@@ -1,0 +1,400 @@
+"""GPU parity tests of the RBM / CD path: CUDA (through the layer API and the C ABI) vs the CPU oracle
+on the same seeded inputs and the same injected random draws.
+
+Tolerances: sampled binary states bit-exact (uniforms are injected with a guaranteed
+margin |p - u| > 1e-4, or mismatches must be confined to rows holding a near-tie); probabilities
+1e-5 relative; gradients 1e-4 norm-relative, all against the fp64 oracle.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import has_cuda
+from oracle import philox, rbm as orbm
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not has_cuda(), reason='needs a CUDA device')]
+
+KINDS = ['rbm', 'bgrbm', 'gbrbm', 'ggrbm']
+PROB_RTOL = 1e-5
+GRAD_NORMREL = 1e-4
+
+
+def _layer(kind, V, H, **kw):
+    from deepbelief_b200.layers import rbm, bgrbm, gbrbm, ggrbm
+    cls = {'rbm': rbm.RBM, 'bgrbm': bgrbm.BGRBM, 'gbrbm': gbrbm.GBRBM, 'ggrbm': ggrbm.GGRBM}[kind]
+    return cls(num_v=V, num_h=H, **kw)
+
+
+def _np(t):
+    return t.detach().cpu().numpy().astype(np.float64)
+
+
+def _normrel(a, b):
+    return np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-300)
+
+
+def _pair(g, tag, kind, temperature=None):
+    """(CUDA layer, fp64 oracle) sharing the golden parameters."""
+    V, H = g[tag + '/W'].shape
+    kw = {} if kind == 'ggrbm' else {'temperature': temperature}
+    lay = _layer(kind, V, H, **kw)
+    if lay.layer_kind in (1, 3):
+        lay.set_weights(g[tag + '/W'], g[tag + '/b'], g[tag + '/c'], opt_sigma_h=g[tag + '/opt_sigma'])
+    else:
+        lay.set_weights(g[tag + '/W'], g[tag + '/b'], g[tag + '/c'])
+    orc = orbm.RBMOracle(g[tag + '/W'], g[tag + '/b'], g[tag + '/c'], kind=kind, opt_sigma_h=g[tag + '/opt_sigma'],
+                         temperature=temperature)
+    return lay, orc
+
+
+@pytest.mark.parametrize('kind', KINDS)
+@pytest.mark.parametrize('tag', ['toy', 'mid'])
+def test_layer_forward_vs_oracle_and_reference_goldens(rbm_golden, tag, kind):
+    g = rbm_golden
+    lay, orc = _pair(g, tag, kind)
+    v = g[tag + ('/v_real' if orc.gaussian_visible else '/v_bin')]
+    h = g[tag + ('/h_real' if orc.gaussian_hidden else '/h_bin')]
+    pre = '%s/%s/float64/' % (tag, kind)
+    for got, want in ((lay.h_net_input(v), orc.h_net_input(v)), (lay.v_net_input(h), orc.v_net_input(h)),
+                      (lay.h_probs(v), orc.h_probs(v)), (lay.v_probs(h), orc.v_probs(h))):
+        np.testing.assert_allclose(_np(got), want, rtol=PROB_RTOL, atol=2e-6)
+    # against the goldens produced by the reference's own code
+    np.testing.assert_allclose(_np(lay.h_probs(v)), g[pre + 'h_probs'], rtol=PROB_RTOL, atol=2e-6)
+    np.testing.assert_allclose(_np(lay.v_probs(h)), g[pre + 'v_probs'], rtol=PROB_RTOL, atol=2e-6)
+    np.testing.assert_allclose(_np(lay.free_energy(v)), g[pre + 'free_energy'], rtol=2e-5, atol=2e-5)
+    vk = g[tag + '/v_real'][::-1].copy() if orc.gaussian_visible else g[tag + '/vk_bin']
+    np.testing.assert_allclose(float(lay.cd_loss(v, vk)), float(g[pre + 'cd_loss']), rtol=1e-3, atol=2e-4)
+
+
+@pytest.mark.parametrize('kind', KINDS)
+def test_sampling_with_injected_draws(rbm_golden, kind):
+    g = rbm_golden
+    lay, orc = _pair(g, 'mid', kind)
+    pre = 'mid/%s/float64/' % kind
+    hp, vp = g[pre + 'h_probs'], g[pre + 'v_probs']
+    draw_h = g['mid/E_h'] if orc.gaussian_hidden else g['mid/U_h']
+    sh = _np(lay.sample_h(hp.astype(np.float32), draw=torch.as_tensor(draw_h.astype(np.float32)).cuda()))
+    sv = _np(lay.sample_v(vp.astype(np.float32), draw=torch.as_tensor(g['mid/U_v'].astype(np.float32)).cuda()))
+    if orc.gaussian_hidden:
+        np.testing.assert_allclose(sh, g[pre + 'sample_h'], rtol=1e-5, atol=1e-6)
+    else:
+        safe = np.abs(hp - draw_h) > 1e-6
+        np.testing.assert_array_equal(sh[safe], g[pre + 'sample_h'][safe])          # bit-exact away from ties
+        assert set(np.unique(sh)) <= {0.0, 1.0}
+    if orc.gaussian_visible:
+        np.testing.assert_allclose(sv, g[pre + 'sample_v'], rtol=1e-5, atol=1e-6)   # the "sample" is the mean
+    else:
+        safe = np.abs(vp - g['mid/U_v']) > 1e-6
+        np.testing.assert_array_equal(sv[safe], g[pre + 'sample_v'][safe])
+
+
+@pytest.mark.parametrize('kind', ['rbm', 'bgrbm', 'gbrbm'])
+def test_concrete_units(rbm_golden, kind):
+    g = rbm_golden
+    lay, orc = _pair(g, 'mid', kind, temperature=0.1)
+    pre = 'mid/%s/float64/' % kind
+    if not orc.gaussian_hidden:
+        got = _np(lay.sample_h(g[pre + 'h_probs'].astype(np.float32), draw=torch.as_tensor(g['mid/U_h'].astype(np.float32)).cuda()))
+        np.testing.assert_allclose(got, g[pre + 'concrete_h'], rtol=2e-4, atol=2e-5)
+    if not orc.gaussian_visible:
+        got = _np(lay.sample_v(g[pre + 'v_probs'].astype(np.float32), draw=torch.as_tensor(g['mid/U_v'].astype(np.float32)).cuda()))
+        np.testing.assert_allclose(got, g[pre + 'concrete_v'], rtol=2e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize('kind', KINDS)
+@pytest.mark.parametrize('tag', ['toy', 'mid'])
+def test_cd_gradient_vs_oracle(rbm_golden, tag, kind):
+    g = rbm_golden
+    lay, orc = _pair(g, tag, kind)
+    v = g[tag + ('/v_real' if orc.gaussian_visible else '/v_bin')]
+    vk = g[tag + '/v_real'][::-1].copy() if orc.gaussian_visible else g[tag + '/vk_bin']
+    got = _np(lay.cd_gradient(v, vk))
+    want = orc.cd_grad_packed(v, vk)
+    V, H = orc.V, orc.H
+    for lo, hi in ((0, V * H), (V * H, V * H + V), (V * H + V, V * H + V + H), (V * H + V + H, got.size)):
+        if hi > lo:
+            assert _normrel(got[lo:hi], want[lo:hi]) < GRAD_NORMREL
+    if tag == 'toy':      # and against finite differences of the REFERENCE's cd_loss
+        assert _normrel(got[:V * H].reshape(V, H), g['toy/%s/fd_grad_W' % kind]) < 1e-4
+
+
+def test_gibbs_chain_and_stack_traversal(rbm_golden):
+    g = rbm_golden
+    lay, orc = _pair(g, 'mid', 'rbm')
+    k = int(g['mid/k'])
+    cu = lambda a: torch.as_tensor(a.astype(np.float32)).cuda()  # noqa: E731
+    draws = [(cu(g['mid/chain_v'][s]), cu(g['mid/chain_h_u'][s])) for s in range(k)]
+    vp, v, hp, h = lay.gibbs_sample(g['mid/h_bin'], k=k, draws=draws)
+    pre = 'mid/rbm/float64/'
+    np.testing.assert_array_equal(_np(v), g[pre + 'gibbs_v'])
+    np.testing.assert_array_equal(_np(h), g[pre + 'gibbs_h'])
+    np.testing.assert_allclose(_np(vp), g[pre + 'gibbs_v_probs'], rtol=PROB_RTOL, atol=1e-6)
+    np.testing.assert_allclose(_np(hp), g[pre + 'gibbs_h_probs'], rtol=PROB_RTOL, atol=1e-6)
+    # two-layer stack (rbm.py:277-325)
+    from deepbelief_b200.layers.rbm import RBM
+    l1 = RBM(12, 8, name='l1')
+    l1.set_weights(g['stack/W1'], g['stack/b1'], g['stack/c1'])
+    l2 = RBM(8, 5, bottom=l1, name='l2')
+    l2.set_weights(g['stack/W2'], g['stack/b2'], g['stack/c2'])
+    up = l2.upprop(g['stack/v'], draws=[cu(g['stack/u1']), cu(g['stack/u2'])])
+    np.testing.assert_array_equal(_np(up), g['stack/up'])
+    down = l2.downprop(up, draws=[cu(g['stack/u3']), cu(g['stack/u4'])])
+    np.testing.assert_array_equal(_np(down), g['stack/down'])
+    assert l2.layers == [l2, l1] and l2.datapoint_len() == 12
+
+
+def test_reference_unit_test_properties():
+    """Re-expression of the reference's tests/test_rbm.py, test_bgrbm.py, test_gbrbm.py (toy 6x5, batch 20)."""
+    rs = np.random.RandomState(0)
+    rbm = _layer('rbm', 6, 5, W_std=0.01)
+    v = rs.binomial(1, 0.5, size=(20, 6)).astype(np.float32)
+    h = rs.binomial(1, 0.5, size=(20, 5)).astype(np.float32)
+    sh, sv = _np(rbm.sample_h(rbm.h_probs(v))), _np(rbm.sample_v(rbm.v_probs(h)))
+    assert sh.shape == (20, 5) and sv.shape == (20, 6)
+    assert np.all(np.isin(sh, [0.0, 1.0])) and np.all(np.isin(sv, [0.0, 1.0]))
+    assert tuple(rbm.free_energy(v).shape) == (20, 1)
+    bg = _layer('bgrbm', 6, 5, W_std=0.01)
+    m = _np(bg.sample_h(bg.h_probs(v), sample=False))
+    assert m.shape == (20, 5)
+    np.testing.assert_allclose(m.mean(0), 0, atol=0.1)
+    np.testing.assert_allclose(m.std(0), 0, atol=0.1)
+    gb = _layer('gbrbm', 6, 5, W_std=0.01)
+    r = _np(gb.sample_v(gb.v_probs(h)))
+    assert r.shape == (20, 6)
+    np.testing.assert_allclose(r.mean(0), 0, atol=0.1)
+    np.testing.assert_allclose(r.std(0), 0, atol=0.1)
+    with pytest.raises(AssertionError):
+        _layer('rbm', 1, 5)                        # rbm.py:44-45
+    with pytest.raises(AssertionError):
+        rbm.gibbs_sample(h, k=0)                   # rbm.py:364
+
+
+def test_horses_anchors(horses):
+    """SURVEY.md §8(c) anchor (2) on the bundled dataset, V=1024, H=500 (the SIMT path: 500 % 8 != 0)."""
+    V, H = 1024, 500
+    i, j = np.arange(V)[:, None], np.arange(H)[None, :]
+    W, b, c = 0.01 * np.cos(0.37 * i + 0.11 * j), 0.05 * np.sin(0.3 * np.arange(V)), 0.02 * np.cos(0.7 * np.arange(H))
+    lay = _layer('rbm', V, H)
+    lay.set_weights(W, b, c)
+    F = _np(lay.free_energy(horses))
+    np.testing.assert_allclose(F.mean(), -347.28000091799646, rtol=1e-5)
+    np.testing.assert_allclose(F[0, 0], -348.6856458065582, rtol=1e-5)
+    np.testing.assert_allclose(_np(lay.h_probs(horses)).sum(), 81967.46732612466, rtol=1e-5)
+    gW = _np(lay.cd_gradient(horses, 1.0 - horses))[:V * H].reshape(V, H)
+    np.testing.assert_allclose(np.linalg.norm(gW), 240.9141144337796, rtol=1e-4)
+    np.testing.assert_allclose(gW[0, 0], 0.45235972577049083, rtol=1e-4)
+    np.testing.assert_allclose(gW[512, 250], 0.48199651515066666, rtol=1e-4)
+    zero = _layer('rbm', V, H)
+    zero.set_weights(np.zeros((V, H)), np.zeros(V), np.zeros(H))
+    np.testing.assert_allclose(_np(zero.free_energy(horses)), -H * np.log(2.0), rtol=1e-6)     # anchor (1)
+    assert np.all(_np(zero.h_probs(horses)) == 0.5) and abs(float(zero.cd_loss(horses, 1 - horses))) < 1e-4
+
+
+# ---- the fused tcgen05 chain ---------------------------------------------------------------------------------------
+def _margin_uniforms(orc, v0, k, rs, margin=1e-4):
+    """Uniform draws (fp32-representable) for a CD-k chain with |p - u| > margin at every step of the fp64
+    oracle chain, so correct fp32 implementations must agree bit for bit (SURVEY.md §7 hard part 2)."""
+    def fix(p, shape):
+        u = rs.uniform(size=shape).astype(np.float32).astype(np.float64)
+        near = np.abs(p - u) < margin
+        u[near] = np.where(p[near] + 4 * margin < 1.0, p[near] + 4 * margin, p[near] - 4 * margin)
+        return u.astype(np.float32).astype(np.float64)
+    N = v0.shape[0]
+    p0 = orc.h_probs(v0)
+    U = [fix(p0, (N, orc.H))]
+    h = orc.sample_h(p0, U[0])
+    chain = []
+    for _ in range(k):
+        pv = orc.v_probs(h)
+        uv = fix(pv, (N, orc.V))
+        v = orc.sample_v(pv, uv)
+        ph = orc.h_probs(v)
+        uh = fix(ph, (N, orc.H))
+        h = orc.sample_h(ph, uh)
+        chain.append((uv, uh))
+    flat = np.concatenate([U[0].ravel()] + [np.concatenate([a.ravel(), b.ravel()]) for a, b in chain])
+    return U[0], chain, flat.astype(np.float32)
+
+
+@pytest.mark.parametrize('N,V,H,k', [(64, 64, 64, 1), (328, 1024, 496, 3), (200, 264, 136, 2)])
+def test_tc_chain_bit_exact_with_injected_uniforms(horses, N, V, H, k):
+    from deepbelief_b200 import ops
+    rs = np.random.RandomState(N + V + H)
+    W = rs.normal(size=(V, H)) * 0.05
+    b, c = rs.normal(size=V) * 0.1, rs.normal(size=H) * 0.1
+    v0 = horses[:N, :V].astype(np.float64) if (N <= 328 and V <= 1024) else rs.binomial(1, 0.4, size=(N, V)).astype(np.float64)
+    orc = orbm.RBMOracle(W, b, c)
+    u0, chain, flat = _margin_uniforms(orc, v0, k, rs)
+    ref = orbm.cd_k(orc, v0, k, u0, chain)
+    params = torch.as_tensor(orc.pack().astype(np.float32)).cuda()
+    plan = ops.CdTcPlan(N, V, H, k)
+    plan.refresh_weights(params)
+    grad = torch.zeros_like(params)
+    vk, hk = torch.empty(N, V, device='cuda'), torch.empty(N, H, device='cuda')
+    p0, pk = torch.empty(N, H, device='cuda'), torch.empty(N, H, device='cuda')
+    plan.step(torch.as_tensor(v0.astype(np.float32)).cuda(), params, grad, injected=torch.as_tensor(flat).cuda(),
+              vk_out=vk, hk_out=hk, p0_out=p0, pk_out=pk)
+    np.testing.assert_array_equal(_np(vk), ref['vk'])                                    # bit-exact states
+    np.testing.assert_array_equal(_np(hk), ref['hk'])
+    np.testing.assert_allclose(_np(p0), ref['h0_probs'], rtol=PROB_RTOL)
+    np.testing.assert_allclose(_np(pk), ref['hk_probs'], rtol=PROB_RTOL)
+    got, want = _np(grad), ref['grad']
+    for lo, hi in ((0, V * H), (V * H, V * H + V), (V * H + V, V * H + V + H)):
+        assert _normrel(got[lo:hi], want[lo:hi]) < GRAD_NORMREL
+
+
+def test_tc_chain_philox_mode_matches_oracle_philox():
+    """Counter-based mode: the kernels' Philox draws are reproduced by oracle/philox.py; any mismatch must
+    sit in a row that holds a near-tie somewhere along the chain."""
+    from deepbelief_b200 import ops
+    N, V, H, k, seed = 256, 512, 384, 2, 1234
+    rs = np.random.RandomState(9)
+    W, b, c = rs.normal(size=(V, H)) * 0.05, rs.normal(size=V) * 0.1, rs.normal(size=H) * 0.1
+    v0 = rs.binomial(1, 0.4, size=(N, V)).astype(np.float64)
+    orc = orbm.RBMOracle(W, b, c)
+    u0 = philox.uniform(N, H, seed, 0).astype(np.float64)
+    chain = [(philox.uniform(N, V, seed, 2 * s - 1).astype(np.float64), philox.uniform(N, H, seed, 2 * s).astype(np.float64))
+             for s in range(1, k + 1)]
+    ref = orbm.cd_k(orc, v0, k, u0, chain)
+    # rows with a near-tie anywhere in the oracle chain
+    tie = np.abs(ref['h0_probs'] - u0).min(axis=1) < 1e-6
+    h = ref['h0']
+    for uv, uh in chain:
+        pv = orc.v_probs(h); tie |= np.abs(pv - uv).min(axis=1) < 1e-6
+        v = orc.sample_v(pv, uv)
+        ph = orc.h_probs(v); tie |= np.abs(ph - uh).min(axis=1) < 1e-6
+        h = orc.sample_h(ph, uh)
+    params = torch.as_tensor(orc.pack().astype(np.float32)).cuda()
+    plan = ops.CdTcPlan(N, V, H, k)
+    plan.refresh_weights(params)
+    grad = torch.zeros_like(params)
+    vk, hk = torch.empty(N, V, device='cuda'), torch.empty(N, H, device='cuda')
+    rng = ops.Rng(seed=seed)
+    plan.step(torch.as_tensor(v0.astype(np.float32)).cuda(), params, grad, rng=rng, vk_out=vk, hk_out=hk)
+    assert rng.draw == 2 * k + 1
+    bad_rows = np.where((_np(vk) != ref['vk']).any(axis=1) | (_np(hk) != ref['hk']).any(axis=1))[0]
+    assert set(bad_rows) <= set(np.where(tie)[0]), 'mismatching rows %s hold no near-tie' % bad_rows
+    # the SIMT sampler draws the same numbers (same counter convention)
+    got = _np(ops.sample(torch.as_tensor(ref['h0_probs'].astype(np.float32)).cuda(), 1, rng=ops.Rng(seed=seed)))
+    safe = np.abs(ref['h0_probs'] - u0) > 1e-6
+    np.testing.assert_array_equal(got[safe], ref['h0'][safe])
+
+
+def test_tc_row_sharding_is_invariant():
+    """Two half-batches with row_offset reproduce the full batch (Philox keyed by global row)."""
+    from deepbelief_b200 import ops
+    N, V, H, k = 512, 256, 128, 2
+    rs = np.random.RandomState(3)
+    params = torch.as_tensor(np.concatenate([rs.normal(size=V * H) * 0.05, rs.normal(size=V + H) * 0.1]).astype(np.float32)).cuda()
+    v0 = torch.as_tensor(rs.binomial(1, 0.4, size=(N, V)).astype(np.float32)).cuda()
+
+    def run(rows, offset, n_global):
+        plan = ops.CdTcPlan(rows.shape[0], V, H, k, n_global=n_global)
+        plan.refresh_weights(params)
+        grad = torch.zeros_like(params)
+        vk = torch.empty(rows.shape[0], V, device='cuda')
+        plan.step(rows.contiguous(), params, grad, rng=ops.Rng(seed=5, row_offset=offset), vk_out=vk)
+        return vk, grad
+    vk_full, g_full = run(v0, 0, N)
+    vk_a, g_a = run(v0[:N // 2], 0, N)
+    vk_b, g_b = run(v0[N // 2:], N // 2, N)
+    assert torch.equal(torch.cat([vk_a, vk_b]), vk_full)
+    assert _normrel(_np(g_a + g_b), _np(g_full)) < 1e-5        # sum of shard gradients == full-batch gradient
+
+
+def test_training_loop_simt_and_tc_agree_with_oracle(horses, tmp_path):
+    """RBM.train on the bundled horses data, CD-1, SGD: 3 iterations reproduce the oracle's parameters when the
+    same Philox draws are used (general path, H=500) and the checkpoint round-trips. (SGD, because Adam's
+    first steps are +-lr * sign(g) and amplify a sign flip of a ~0 gradient entry; Adam itself is checked
+    element-wise in test_optimizer_kernels_vs_oracle.)"""
+    import os
+    from conftest import DATASETS
+    from deepbelief_b200 import compat as tf
+    from deepbelief_b200.layers.data import Data
+    from deepbelief_b200.layers.rbm import RBM
+    path = os.path.join(DATASETS, 'weizmann_horses_training_328x1024_binary.h5')
+    test_path = os.path.join(DATASETS, 'weizmann_horses_eslami_test_14x1024_binary.h5')
+    V, H, seed, iters = 1024, 500, 77, 3
+    rs = np.random.RandomState(0)
+    W0 = (rs.normal(size=(V, H)) * 0.01).astype(np.float32)
+    lay = RBM(V, H, name='BBRBM-test', seed=seed)
+    lay.set_weights(W0, np.zeros(V), np.zeros(H))
+    lay.train(tf.train.GradientDescentOptimizer(learning_rate=0.05), Data(path, batch_size=328, log_epochs=False),
+              Data(test_path, batch_size=8, log_epochs=False), num_gibbs_steps=1, pcd=False, max_iterations=iters,
+              eval_interval=2, ckpt_interval=iters, ckpt_dir=str(tmp_path))
+    # oracle replay: draws 0 (h0), 1 (v1), 2 (h1) per iteration; eval steps consume draws too, so replay the counter
+    theta = np.concatenate([W0.ravel().astype(np.float64), np.zeros(V + H)])
+    sgd = orbm.SGD(0.05)
+    draw = 0
+    v0 = horses.astype(np.float64)
+    for it in range(1, iters + 1):
+        if it == 1:
+            draw += 2                        # evaluation before training: sample_h + downprop sample_v (rbm.py:684-686)
+        orc = orbm.RBMOracle(theta[:V * H].reshape(V, H), theta[V * H:V * H + V], theta[V * H + V:])
+        u0 = philox.uniform(328, H, seed, draw).astype(np.float64)
+        uv = philox.uniform(328, V, seed, draw + 1).astype(np.float64)
+        uh = philox.uniform(328, H, seed, draw + 2).astype(np.float64)
+        draw += 3
+        out = orbm.cd_k(orc, v0, 1, u0, [(uv, uh)])
+        theta = sgd.step(theta, out['grad'])
+        if it % 2 == 0:
+            draw += 2
+    got = _np(lay._params)
+    assert np.max(np.abs(got - theta)) < 1e-6
+    assert len(lay.loss_y_vals) == 2 and all(np.isfinite(lay.loss_y_vals))
+    ck = os.path.join(str(tmp_path), 'BBRBM-test-%d' % iters)
+    assert os.path.exists(ck)
+    other = RBM(V, H, name='BBRBM-test')
+    other.restore(ck)
+    assert torch.equal(other._params, lay._params) and other.checkpoint_iter == 1 + iters
+
+
+@pytest.mark.parametrize('kind', ['sgd', 'momentum', 'adam'])
+def test_optimizer_kernels_vs_oracle(kind):
+    from deepbelief_b200 import compat as tf, ops
+    rs = np.random.RandomState(4)
+    n = 10007
+    theta0 = rs.normal(size=n)
+    grads = [rs.normal(size=n) * 0.1 for _ in range(4)]
+    if kind == 'sgd':
+        opt, orc = tf.train.GradientDescentOptimizer(0.1), orbm.SGD(0.1)
+    elif kind == 'momentum':
+        opt, orc = tf.train.MomentumOptimizer(1e-3, momentum=0.9, weight_decay=1e-4), orbm.Momentum(1e-3, 0.9, 1e-4)
+    else:
+        opt, orc = tf.train.AdamOptimizer(1e-3), orbm.Adam(1e-3)
+    p = torch.as_tensor(theta0.astype(np.float32)).cuda()
+    state = torch.zeros(max(opt.state_multiple(), 1) * n, device='cuda')
+    th = theta0.astype(np.float32).astype(np.float64)
+    for g in grads:
+        g32 = g.astype(np.float32)
+        ops.optimizer_step(opt.descriptor(), p, torch.as_tensor(g32).cuda(), state)
+        th = orc.step(th, g32.astype(np.float64))
+    np.testing.assert_allclose(_np(p), th, rtol=2e-6, atol=2e-7)
+
+
+def test_full_size_config5_properties():
+    """BASELINE config 5 size (V=4096, H=8192, N=16384) through size-independent properties: with W = 0 the
+    chain factorises, so dW[v,h] == db[v] * sigmoid(c[h]) exactly, dc == 0, and the sample means follow
+    sigmoid(b) / sigmoid(c)."""
+    from deepbelief_b200 import ops
+    N, V, H, k = 16384, 4096, 8192, 1
+    rs = np.random.RandomState(1)
+    b = rs.uniform(-2, 2, size=V)
+    c = rs.uniform(-2, 2, size=H)
+    params = torch.as_tensor(np.concatenate([np.zeros(V * H), b, c]).astype(np.float32)).cuda()
+    v0 = (torch.rand(N, V, device='cuda', generator=torch.Generator(device='cuda').manual_seed(0)) < 0.3).float()
+    plan = ops.CdTcPlan(N, V, H, k)
+    plan.refresh_weights(params)
+    grad = torch.zeros_like(params)
+    vk, hk = torch.empty(N, V, device='cuda'), torch.empty(N, H, device='cuda')
+    plan.step(v0, params, grad, rng=ops.Rng(seed=2), vk_out=vk, hk_out=hk)
+    sig = lambda x: 1.0 / (1.0 + np.exp(-x))  # noqa: E731
+    vmean, hmean = _np(vk.mean(0)), _np(hk.mean(0))
+    assert np.max(np.abs(vmean - sig(b))) < 6 * 0.5 / np.sqrt(N)
+    assert np.max(np.abs(hmean - sig(c))) < 6 * 0.5 / np.sqrt(N)
+    assert torch.all((vk == 0) | (vk == 1)) and torch.all((hk == 0) | (hk == 1))
+    g = _np(grad)
+    gW, gb, gc = g[:V * H].reshape(V, H), g[V * H:V * H + V], g[V * H + V:]
+    np.testing.assert_allclose(gb, -(_np(v0.mean(0)) - vmean), rtol=1e-4, atol=1e-7)
+    assert np.max(np.abs(gc)) < 1e-6
+    assert _normrel(gW, gb[:, None] * sig(c.astype(np.float32).astype(np.float64))[None, :]) < 1e-5
