@@ -7,8 +7,9 @@ Contract kept from deepbelief/layers/data.py (reference):
     the permutation is reshuffled with the global `np.random` state (data.py:84-90);
   * the first epoch uses the identity permutation unless `shuffle_first` (data.py:64-66);
   * `has_labels` makes `next_batch()` return `(datapoints, labels)`.
-Added for the GPU path: `next_batch_device()` stages the batch through a reusable pinned host buffer
-and issues an asynchronous host->device copy on the current stream.
+Added for the GPU path: `Data.from_arrays(...)` builds the same object from in-memory arrays (kept in
+pinned host memory, so the trainer's prefetching feeder can copy host->device asynchronously without a
+staging pass), and batches whose sorted row numbers are contiguous are returned as zero-copy views.
 """
 import json
 import logging
@@ -56,8 +57,35 @@ class Data:
         self.log_epochs = log_epochs
 
         contents = hdf5.File(data_fname)
-        self.datapoints = contents['datapoints']
-        self.labels = contents['labels'] if self.has_labels else None
+        self._setup(contents['datapoints'], contents['labels'] if self.has_labels else None, shuffle_first)
+
+    @classmethod
+    def from_arrays(cls, datapoints, labels=None, shuffle_first=False, batch_size=1, log_epochs=True, name='Data',
+                    pin=True):
+        """Same contract as the file-backed constructor, over arrays already in memory. With `pin` the
+        datapoints are moved once into page-locked host memory (needs a CUDA runtime; skipped without)."""
+        self = cls.__new__(cls)
+        self.name = name
+        self.logger = logging.getLogger(name)
+        self.has_labels = labels is not None
+        self.batch_size = int(batch_size)
+        self.log_epochs = log_epochs
+        datapoints = np.ascontiguousarray(datapoints, dtype=np.float32)
+        self._pinned_store = None
+        if pin:
+            try:
+                import torch
+                if torch.cuda.is_available():
+                    self._pinned_store = torch.from_numpy(datapoints).pin_memory()
+                    datapoints = self._pinned_store.numpy()
+            except Exception:       # pinning is an optimisation only
+                self._pinned_store = None
+        self._setup(datapoints, None if labels is None else np.asarray(labels, dtype=np.float32), shuffle_first)
+        return self
+
+    def _setup(self, datapoints, labels, shuffle_first):
+        self.datapoints = datapoints
+        self.labels = labels
         self.num_datapoints, self.datapoint_size = self.datapoints.shape
         if self.batch_size > self.num_datapoints:
             raise AssertionError('batch_size %d exceeds the %d datapoints' % (self.batch_size, self.num_datapoints))
@@ -65,6 +93,13 @@ class Data:
         self._cursor = _EpochCursor(self.num_datapoints, self.batch_size, shuffle_first)
         self._pinned = None
         self.logger.debug(self)
+
+    @staticmethod
+    def _take(arr, rows):
+        # sorted row numbers (data.py:92-93) that happen to be contiguous need no gather
+        if len(rows) and int(rows[-1]) - int(rows[0]) + 1 == len(rows):
+            return arr[int(rows[0]):int(rows[-1]) + 1]
+        return arr[rows]
 
     # attributes the reference exposes
     @property
@@ -87,8 +122,8 @@ class Data:
         if wrapped and self.log_epochs:
             self.logger.info('Epoch: %d', self._cursor.epoch)
         if self.has_labels:
-            return self.datapoints[rows], self.labels[rows]
-        return self.datapoints[rows]
+            return self._take(self.datapoints, rows), self._take(self.labels, rows)
+        return self._take(self.datapoints, rows)
 
     def next_batch_device(self, device='cuda'):
         """Same batch as next_batch(), delivered as a CUDA tensor via pinned staging (datapoints only)."""

@@ -235,7 +235,7 @@ class GPLVM(layer.Layer):
     def loss_and_grad(self):
         """(loss, dX [N,Q], d/d(opt_alpha, opt_gamma, opt_noise) [3]) — K3-K6 in one call."""
         scal, dX, info = self._evaluate(want_grad=True)
-        return scal[0], dX, scal[3:6]
+        return scal[0].clone(), dX.clone(), scal[3:6].clone()     # the plan's buffers are reused by the next call
 
     def _xstar(self, x=None):
         if x is None:

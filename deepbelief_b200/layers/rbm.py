@@ -26,6 +26,72 @@ from .layer import to_device, to_numpy
 from ..parallel import dist_info as _dist_info, all_reduce_sum_
 
 
+class BatchFeeder:
+    """Host batches -> device, one batch ahead of the compute stream.
+
+    `next()` hands out the device copy of the current batch and immediately starts the host->device
+    copy of the following one on a side stream (double-buffered device and pinned staging buffers), so
+    the copy of batch i+1 overlaps the CD chain of batch i. Exactly `count` batches are drawn from
+    `data.next_batch()` — the reference's loop consumes one per iteration (rbm.py:695) and no more.
+    Batches that already live in pinned memory (Data.from_arrays) skip the staging pass."""
+
+    def __init__(self, data, device, count):
+        self.data, self.device, self.left = data, device, int(count)
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.dev = [None, None]
+        self.stage = [None, None]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.slot = 0
+        self.h2d_bytes = 0
+        self._pending = False
+        self._issue(first=True)
+
+    def _host_batch(self):
+        batch = self.data.next_batch()
+        if isinstance(batch, tuple):       # (datapoints, labels): the trainers use the datapoints only
+            batch = batch[0]
+        return batch
+
+    def _issue(self, first=False):
+        if self.left <= 0:
+            self._pending = False
+            return
+        self.left -= 1
+        s = self.slot
+        host = self._host_batch()
+        src = host if isinstance(host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(host, dtype=np.float32))
+        if src.is_cuda:
+            self.dev[s] = src.to(dtype=torch.float32)
+            self.ready[s].record(torch.cuda.current_stream())
+            self._pending = True
+            return
+        if self.dev[s] is None or self.dev[s].shape != src.shape:
+            self.dev[s] = torch.empty(src.shape, dtype=torch.float32, device=self.device)
+        main = torch.cuda.current_stream()
+        self.copy_stream.wait_stream(main)           # the previous user of dev[s] (iteration i-1) is enqueued on `main`
+        if not src.is_pinned():
+            if self.stage[s] is None or self.stage[s].shape != src.shape:
+                self.stage[s] = torch.empty(src.shape, dtype=torch.float32).pin_memory()
+            else:
+                self.ready[s].synchronize()            # the last copy out of this staging buffer has finished
+            self.stage[s].copy_(src)
+            src = self.stage[s]
+        with torch.cuda.stream(self.copy_stream):
+            self.dev[s].copy_(src, non_blocking=True)
+            self.ready[s].record(self.copy_stream)
+        self.h2d_bytes += src.numel() * 4
+        self._pending = True
+
+    def next(self):
+        assert self._pending, 'BatchFeeder exhausted'
+        s = self.slot
+        torch.cuda.current_stream().wait_event(self.ready[s])
+        out = self.dev[s]
+        self.slot ^= 1
+        self._issue()
+        return out
+
+
 class RBM(layer.Layer):
     """Binary-binary RBM. Args as the reference: num_v, num_h, W_std=0.1, lr=0.1, temperature=None
     (Concrete units when set), bottom=None, plotters (accepted, may be None), session (ignored), name.
@@ -373,6 +439,11 @@ class RBM(layer.Layer):
         ops.cd_gradients(self.layer_kind, v0, vk, self._params, self.num_v, self.num_h, inv_n, grad)
         return grad, vk, hk
 
+    def launches_per_cd_step(self, k):
+        """Kernels of this library launched by one cd_step on the tensor-core path: batch conversion,
+        2k+1 chain GEMMs, the dW GEMM and the bias-gradient reduction (csrc/cd_chain.cu)."""
+        return 1 + (2 * k + 1) + 1 + 1
+
     def apply_gradient(self, optimizer, grad, opt_state, lr=None):
         """All-reduce (data parallel) + optimizer step on the packed parameters."""
         all_reduce_sum_(grad)
@@ -386,10 +457,12 @@ class RBM(layer.Layer):
 
     def train(self, optimizer, training_data, test_data, num_gibbs_steps=1, pcd=True, lr_interval=None,
               lr_drop=None, test_mean_fname=None, test_std_fname=None, max_iterations=1000, eval_interval=0,
-              ckpt_interval=0, ckpt_dir=None):
+              ckpt_interval=0, ckpt_dir=None, *, step_callback=None):
         """CD-k / PCD-k training loop (rbm.py:595-711). One iteration = next batch -> (lower layers
         re-sampled, rbm.py:621-623) -> chain -> gradient -> optimizer. Under torch.distributed every
-        rank feeds its own row shard and the packed gradient is summed over NCCL."""
+        rank feeds its own row shard and the packed gradient is summed over NCCL.
+        Extension: step_callback(iteration, grad) is called after every update with the packed
+        (all-reduced) gradient still on the device — a monitoring hook; the reference has none."""
         rank, world = _dist_info()
         opt_state = self.new_optimizer_state(optimizer)
         n_local = training_data.batch_shape()[0]
@@ -400,7 +473,8 @@ class RBM(layer.Layer):
         persistent = None
         if pcd:
             # the first batch only initialises the persistent chain and is discarded (rbm.py:631-641)
-            first = to_device(training_data.next_batch(), self.device)
+            first = training_data.next_batch()
+            first = to_device(first[0] if isinstance(first, tuple) else first, self.device)
             v_first = self.bottom.upprop(first) if self.bottom else first
             persistent = self._up_sample(v_first, True)[1].clone()
 
@@ -412,11 +486,15 @@ class RBM(layer.Layer):
             self._eval_step(test_data, test_mean_fname, test_std_fname)
 
         lr_now = optimizer.learning_rate
+        feeder = BatchFeeder(training_data, self.device, max(0, max_iter - start_iter))
+        self.last_feeder = feeder
         for self.iter in range(start_iter, max_iter):
-            batch = to_device(training_data.next_batch(), self.device)
+            batch = feeder.next()
             v0 = self.bottom.upprop(batch) if self.bottom else batch
             self.cd_step(v0, num_gibbs_steps, persistent, grad=grad, n_global=n_global)
             self.apply_gradient(optimizer, grad, opt_state, lr_now)
+            if step_callback is not None:
+                step_callback(self.iter, grad)
             if lr_interval and lr_drop and self.iter % lr_interval == 0:
                 self.lr *= lr_drop                         # rbm.py:672-673, 703-704: only layer.lr changes
             if eval_interval and self.iter % eval_interval == 0:
