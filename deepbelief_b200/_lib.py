@@ -83,6 +83,7 @@ SIGNATURES = {
     'db_softplus': (c_int, [c_void_p, c_void_p, c_float_p, c_int, c_float_p]),
     'db_mse': (c_int, [c_void_p, c_void_p, c_float_p, c_float_p, c_int, c_int, c_float_p]),
     'db_cross_entropy': (c_int, [c_void_p, c_void_p, c_float_p, c_float_p, c_int, c_int, c_int, c_float_p]),
+    'db_host_gather_rows': (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_void_p, c_int]),
 }
 
 _lock = threading.Lock()

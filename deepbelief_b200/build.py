@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(HERE, 'libdeepbelief_b200.so')
 STAMP = os.path.join(HERE, 'csrc', '.build_stamp')
 
-SOURCES = ['api.cu', 'layer_simt.cu', 'gemm_tc.cu', 'cd_chain.cu', 'gp.cu']
+SOURCES = ['api.cu', 'host_io.cu', 'layer_simt.cu', 'gemm_tc.cu', 'cd_chain.cu', 'gp.cu']
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',
@@ -72,7 +72,7 @@ def build(force=False, verbose=False):
         failed = failed or p.returncode != 0
     if failed:
         raise RuntimeError('nvcc failed; see output above')
-    link = [nvcc, '-shared', '-o', LIB_PATH] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart']
+    link = [nvcc, '-shared', '-o', LIB_PATH] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart', '-lpthread']
     subprocess.check_call(link)
     with open(STAMP, 'w') as f:
         f.write(_source_hash())

@@ -45,9 +45,19 @@ inline WeightCacheView weight_cache_view(void* cache, int V, int H) {
   return v;
 }
 
+// K chunk of the dW GEMM: at most 4096 columns (= 512 accumulation steps over hi+lo) per TMEM
+// accumulator, at most 8 chunks; partial products are summed in fp32 by dw_reduce_kernel.
+constexpr int kDwChunk = 4096;
+constexpr int kDwMaxSplits = 8;
+inline int dw_splits(int ldT) {
+  int s = (ldT + kDwChunk - 1) / kDwChunk;
+  return s < 1 ? 1 : (s > kDwMaxSplits ? kDwMaxSplits : s);
+}
+
 struct ChainWorkspace {
   __half *v0b, *vb, *hb, *vt, *pt_hi, *pt_lo;
-  int NP;
+  float* dw_part;      // [splits, V*H] partial dW products (splits > 1 only)
+  int NP, splits;
   size_t bytes;
 };
 inline ChainWorkspace chain_workspace(void* ws, int N, int V, int H) {
@@ -61,6 +71,9 @@ inline ChainWorkspace chain_workspace(void* ws, int N, int V, int H) {
   w.vt = reinterpret_cast<__half*>(p); p += align256((size_t)V * 2 * w.NP * 2);
   w.pt_hi = reinterpret_cast<__half*>(p); p += align256((size_t)H * 2 * w.NP * 2);
   w.pt_lo = reinterpret_cast<__half*>(p); p += align256((size_t)H * 2 * w.NP * 2);
+  w.splits = dw_splits(2 * w.NP);
+  w.dw_part = reinterpret_cast<float*>(p);
+  if (w.splits > 1) p += align256((size_t)w.splits * V * H * sizeof(float));
   w.bytes = (size_t)(p - p0);
   return w;
 }
@@ -162,6 +175,18 @@ __global__ void tc_bias_grads_kernel(const __half* __restrict__ vt, const __half
     }
     s = warp_sum(shi) + warp_sum(slo);
     if (lane == 0) gc[hrow] = -inv_n * (1.0f / kProbScale) * s;
+  }
+}
+
+// gW = sum over the K-chunk partials (fixed order: deterministic)
+__global__ void dw_reduce_kernel(const float4* __restrict__ part, size_t n4, int splits, float4* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 a = __ldcs(part + i);
+    for (int s = 1; s < splits; ++s) {
+      const float4 b = __ldcs(part + (size_t)s * n4 + i);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    out[i] = a;
   }
 }
 
@@ -285,9 +310,17 @@ extern "C" int db_cd_tc_step(db_handle_t h, db_stream_t stream, const db_cd_tc_d
     p.Ma = H; p.Nb = V; p.K = ldT;
     p.a_hi = ws.pt_hi; p.a_lo = ws.pt_lo; p.lda = ldT; p.b = ws.vt; p.ldb = ldT;
     p.acc_scale = -d->inv_global_n / kProbScale; p.act = 0; p.sample = 0;
-    p.out32 = gW; p.ld32 = H;
+    p.ld32 = H;
+    const bool split = ws.splits > 1 && ((size_t)V * H) % 4 == 0;
+    if (split) { p.out32 = ws.dw_part; p.k_splits = ws.splits; p.split_stride = (size_t)V * H; }
+    else p.out32 = gW;
     rc = tc_gemm_launch(p, h->num_sms, st);
     if (rc) return set_err(h, DB_ERR_CUDA, "cd_tc dW launch failed (%d)", rc);
+    if (split) {
+      const size_t n4 = (size_t)V * H / 4;
+      dw_reduce_kernel<<<ew_grid(n4, h->num_sms), 256, 0, st>>>(reinterpret_cast<const float4*>(ws.dw_part), n4, ws.splits,
+                                                                reinterpret_cast<float4*>(gW));
+    }
   }
   tc_bias_grads_kernel<<<(V + H + 7) / 8, 256, 0, st>>>(ws.vt, ws.pt_hi, ws.pt_lo, V, H, ldT, d->inv_global_n, gb, gc);
   if (vk_out) half_to_float_kernel<<<ew_grid(NV, h->num_sms), 256, 0, st>>>(ws.vb, NV, vk_out);

@@ -84,6 +84,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   const int tiles_n = (p.Nb + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  // work item w = (k-split ks, tile t): all tiles of one K chunk run before the next chunk starts
+  const int k_splits = p.k_splits > 1 ? p.k_splits : 1;
+  const int kb_per_split = (num_kb + k_splits - 1) / k_splits;
+  const int num_work = num_tiles * k_splits;
 
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&tm_a_hi);
@@ -109,10 +113,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       const uint32_t tx_bytes = (two_pass ? 2 * A_TILE_BYTES : A_TILE_BYTES) + B_TILE_BYTES;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int ks = w / num_tiles, t = w - ks * num_tiles;
         const TileCoord tc = tile_coord(t, tiles_m, tiles_n);
         const int m0 = tc.m_blk * BLOCK_M, n0 = tc.n_blk * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb_end = min(num_kb, (ks + 1) * kb_per_split);
+        for (int kb = ks * kb_per_split; kb < kb_end; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
           ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
@@ -129,11 +135,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       constexpr uint32_t idesc = ptx::umma_idesc(/*F16*/ 0, BLOCK_M, BLOCK_N);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int ks = w / num_tiles;
+        const int kb_begin = ks * kb_per_split, kb_end = min(num_kb, (ks + 1) * kb_per_split);
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);          // TMA bytes have landed
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
@@ -143,7 +151,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // advance inside the swizzle row
-            ptx::mma_f16_ss(tmem_d, d_ahi + koff, d_b + koff, idesc, (kb | k) != 0 ? 1u : 0u);
+            ptx::mma_f16_ss(tmem_d, d_ahi + koff, d_b + koff, idesc, (kb != kb_begin || k != 0) ? 1u : 0u);
             if (two_pass) ptx::mma_f16_ss(tmem_d, d_alo + koff, d_b + koff, idesc, 1u);
           }
           ptx::mma_commit(&empty_bar[stage]);               // frees the smem slot when the MMAs retire
@@ -158,7 +166,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const int quarter = warp & 3;                   // TMEM lane quarter this warp may read
     int acc = 0; uint32_t acc_phase = 0;
     const float inv_pT = p.pT_scale;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      const int ks = w / num_tiles, t = w - ks * num_tiles;
+      float* const out32 = p.out32 ? p.out32 + (size_t)ks * p.split_stride : nullptr;
       const TileCoord tc = tile_coord(t, tiles_m, tiles_n);
       const int m = tc.m_blk * BLOCK_M + quarter * 32 + lane;
       const bool m_ok = m < p.Ma;
@@ -209,10 +219,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         }
 
         // ---- [Nb, Ma] outputs: for fixed j the 32 lanes write 32 consecutive units ----
-        if (p.out32 != nullptr && m_ok) {
+        if (out32 != nullptr && m_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (nb0 + j < p.Nb) p.out32[(size_t)(nb0 + j) * p.ld32 + m] = val[j];
+            if (nb0 + j < p.Nb) out32[(size_t)(nb0 + j) * p.ld32 + m] = val[j];
         }
         if (p.out_s16 != nullptr && m_ok) {
 #pragma unroll
@@ -330,6 +340,12 @@ int tc_gemm_launch(const TcGemmParams& p, int num_sms, cudaStream_t stream) {
   if ((reinterpret_cast<uintptr_t>(p.a_hi) | reinterpret_cast<uintptr_t>(p.b) |
        reinterpret_cast<uintptr_t>(p.a_lo)) & 15) return -1000;
   if (p.sample && p.U == nullptr && (p.rng.row_offset & 3u)) return -1000;
+  if (p.k_splits > 1) {   // partial products are only meaningful for the plain linear fp32 output
+    const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+    if (p.act || p.sample || p.bias || p.out_s16 || p.out_sT16 || p.out_pT_hi || !p.out32 || p.k_splits > num_kb) return -1000;
+    const int per = (num_kb + p.k_splits - 1) / p.k_splits;
+    if ((p.k_splits - 1) * per >= num_kb) return -1000;     // an empty chunk would publish an unwritten accumulator
+  }
   if (p.out_sT16 && ((p.ldsT % 8) || (reinterpret_cast<uintptr_t>(p.out_sT16) & 15))) return -1000;
   if (p.out_pT_hi && ((p.ldpT % 8) || (reinterpret_cast<uintptr_t>(p.out_pT_hi) & 15) ||
                       (reinterpret_cast<uintptr_t>(p.out_pT_lo) & 15))) return -1000;
@@ -346,7 +362,7 @@ int tc_gemm_launch(const TcGemmParams& p, int num_sms, cudaStream_t stream) {
   });
   if (attr_err != cudaSuccess) return (int)attr_err;
 
-  const int tiles = ((p.Ma + BLOCK_M - 1) / BLOCK_M) * ((p.Nb + BLOCK_N - 1) / BLOCK_N);
+  const int tiles = ((p.Ma + BLOCK_M - 1) / BLOCK_M) * ((p.Nb + BLOCK_N - 1) / BLOCK_N) * (p.k_splits > 1 ? p.k_splits : 1);
   const int grid = tiles < num_sms ? tiles : num_sms;
   tc_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_a_hi, tm_a_lo, tm_b, p);
   return (int)cudaGetLastError();

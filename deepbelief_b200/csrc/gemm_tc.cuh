@@ -23,6 +23,11 @@ struct TcGemmParams {
   const float* U; int ldu;    // injected uniforms [Nb, Ma], nullptr -> Philox
   RngArgs rng;
   float* out32; int ld32;             // [Nb, Ma] fp32 value after act (probabilities / linear result)
+  // split-K (out32 only): the K axis is cut into k_splits contiguous chunks, chunk s writes its partial
+  // product to out32 + s * split_stride; the caller sums the partials in fp32 (round-to-nearest). The
+  // tensor core adds into its fp32 accumulator with truncation, a bias that grows with the number of
+  // accumulation steps — chunking bounds it (measured: 1.2e-4 relative at K = 32768 unsplit).
+  int k_splits; size_t split_stride;
   __half* out_s16; int lds16;         // [Nb, Ma] fp16 sample (sample==1) or value
   // "T" outputs [Ma, 2*Nb_pad] hold the two ends of the CD chain INTERLEAVED in blocks of 64 columns:
   // column(nb, phase) = (nb / 64) * 128 + phase * 64 + nb % 64   (phase 0 = data end, 1 = model end),

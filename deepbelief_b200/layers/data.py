@@ -125,16 +125,29 @@ class Data:
             return self._take(self.datapoints, rows), self._take(self.labels, rows)
         return self._take(self.datapoints, rows)
 
-    def next_batch_device(self, device='cuda'):
-        """Same batch as next_batch(), delivered as a CUDA tensor via pinned staging (datapoints only)."""
-        import torch
+    def next_batch_into(self, out):
+        """The datapoints of next_batch() without the intermediate copy: a zero-copy view when the sorted
+        rows are contiguous, otherwise gathered by the native multi-threaded row gather
+        (db_host_gather_rows) into `out` (a [batch_size, datapoint_size] float32 array, normally the
+        feeder's pinned staging buffer). Returns the array that holds the batch."""
         rows, wrapped = self._cursor.advance()
         if wrapped and self.log_epochs:
             self.logger.info('Epoch: %d', self._cursor.epoch)
-        if self._pinned is None:
-            self._pinned = torch.empty((self.batch_size, self.datapoint_size), dtype=torch.float32).pin_memory()
-        np.take(self.datapoints, rows, axis=0, out=self._pinned.numpy())
-        return self._pinned.to(device, non_blocking=True)
+        if len(rows) and int(rows[-1]) - int(rows[0]) + 1 == len(rows):
+            return self.datapoints[int(rows[0]):int(rows[-1]) + 1]
+        src = self.datapoints
+        if src.dtype != np.float32 or not src.flags['C_CONTIGUOUS'] or not out.flags['C_CONTIGUOUS']:
+            np.take(src, rows, axis=0, out=out)
+            return out
+        import ctypes
+        from .. import _lib
+        rows64 = np.ascontiguousarray(rows, dtype=np.int64)
+        rc = _lib.lib().db_host_gather_rows(ctypes.c_void_p(src.ctypes.data), src.shape[1] * 4,
+                                            ctypes.c_void_p(rows64.ctypes.data), len(rows64), src.shape[0],
+                                            ctypes.c_void_p(out.ctypes.data), 0)
+        if rc != 0:
+            raise RuntimeError('db_host_gather_rows failed (%d)' % rc)
+        return out
 
     def __str__(self):
         def stats(arr, tag):

@@ -26,70 +26,100 @@ from .layer import to_device, to_numpy
 from ..parallel import dist_info as _dist_info, all_reduce_sum_
 
 
+# page-locked staging and device batch buffers are kept across train() calls: cudaHostAlloc of a
+# 256 MB buffer costs ~100 ms, far more than a CD step
+_BUFFER_POOL = {}
+
+
+def _pooled_buffers(device, shape):
+    key = (str(device), tuple(shape))
+    bufs = _BUFFER_POOL.get(key)
+    if bufs is None:
+        if len(_BUFFER_POOL) >= 4:                 # a handful of batch shapes at most; do not hoard pinned memory
+            _BUFFER_POOL.clear()
+        bufs = _BUFFER_POOL[key] = {
+            'stage': [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(2)],
+            'dev': [torch.empty(shape, dtype=torch.float32, device=device) for _ in range(2)]}
+    return bufs
+
+
 class BatchFeeder:
     """Host batches -> device, one batch ahead of the compute stream.
 
-    `next()` hands out the device copy of the current batch and immediately starts the host->device
-    copy of the following one on a side stream (double-buffered device and pinned staging buffers), so
-    the copy of batch i+1 overlaps the CD chain of batch i. Exactly `count` batches are drawn from
-    `data.next_batch()` — the reference's loop consumes one per iteration (rbm.py:695) and no more.
-    Batches that already live in pinned memory (Data.from_arrays) skip the staging pass."""
+    `next()` hands out the device copy of the current batch; `prefetch()` — called by the trainer right
+    after it has enqueued the step's kernels — assembles the following host batch (native threaded
+    gather into pinned staging, or a zero-copy view of pinned storage) and starts its host->device
+    copy on a side stream, so both overlap the CD chain of the current batch. Device and staging
+    buffers are double-buffered. Exactly `count` batches are drawn from the data source — the
+    reference's loop consumes one per iteration (rbm.py:695) and no more."""
 
     def __init__(self, data, device, count):
         self.data, self.device, self.left = data, device, int(count)
         self.copy_stream = torch.cuda.Stream(device=device)
+        # pooled device buffers may still be read by work a previous trainer enqueued on the compute stream
+        self.copy_stream.wait_stream(torch.cuda.current_stream())
         self.dev = [None, None]
         self.stage = [None, None]
-        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]     # H2D of slot s has landed
+        self.released = [None, None]                               # compute no longer reads slot s
         self.slot = 0
         self.h2d_bytes = 0
         self._pending = False
-        self._issue(first=True)
+        self.prefetch()
 
-    def _host_batch(self):
-        batch = self.data.next_batch()
-        if isinstance(batch, tuple):       # (datapoints, labels): the trainers use the datapoints only
-            batch = batch[0]
-        return batch
+    def _staging(self, s, shape):
+        if self.stage[s] is None or tuple(self.stage[s].shape) != tuple(shape):
+            self.stage[s] = _pooled_buffers(self.device, shape)['stage'][s]
+            torch.cuda.current_stream().synchronize()   # a previous feeder may still be copying out of it
+        else:
+            self.ready[s].synchronize()            # the last copy out of this staging buffer has finished
+        return self.stage[s]
 
-    def _issue(self, first=False):
-        if self.left <= 0:
-            self._pending = False
+    def prefetch(self):
+        if self._pending or self.left <= 0:
             return
         self.left -= 1
         s = self.slot
-        host = self._host_batch()
+        if hasattr(self.data, 'next_batch_into'):
+            shape = self.data.batch_shape()
+            host = self.data.next_batch_into(self._staging(s, shape).numpy())
+        else:
+            host = self.data.next_batch()
+            if isinstance(host, tuple):            # (datapoints, labels): the trainers use the datapoints only
+                host = host[0]
         src = host if isinstance(host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(host, dtype=np.float32))
+        self._pending = True
         if src.is_cuda:
             self.dev[s] = src.to(dtype=torch.float32)
             self.ready[s].record(torch.cuda.current_stream())
-            self._pending = True
             return
         if self.dev[s] is None or self.dev[s].shape != src.shape:
-            self.dev[s] = torch.empty(src.shape, dtype=torch.float32, device=self.device)
-        main = torch.cuda.current_stream()
-        self.copy_stream.wait_stream(main)           # the previous user of dev[s] (iteration i-1) is enqueued on `main`
+            self.dev[s] = _pooled_buffers(self.device, src.shape)['dev'][s]
         if not src.is_pinned():
-            if self.stage[s] is None or self.stage[s].shape != src.shape:
-                self.stage[s] = torch.empty(src.shape, dtype=torch.float32).pin_memory()
-            else:
-                self.ready[s].synchronize()            # the last copy out of this staging buffer has finished
-            self.stage[s].copy_(src)
-            src = self.stage[s]
+            stage = self._staging(s, src.shape)
+            stage.copy_(src)
+            src = stage
+        if self.released[s] is not None:
+            self.copy_stream.wait_event(self.released[s])     # the step that read dev[s] has finished
         with torch.cuda.stream(self.copy_stream):
             self.dev[s].copy_(src, non_blocking=True)
             self.ready[s].record(self.copy_stream)
         self.h2d_bytes += src.numel() * 4
-        self._pending = True
 
     def next(self):
+        if not self._pending:
+            self.prefetch()
         assert self._pending, 'BatchFeeder exhausted'
         s = self.slot
-        torch.cuda.current_stream().wait_event(self.ready[s])
-        out = self.dev[s]
+        main = torch.cuda.current_stream()
+        # everything enqueued so far (the previous step, which read the OTHER slot) precedes this event
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.released[s ^ 1] = ev
+        main.wait_event(self.ready[s])
+        self._pending = False
         self.slot ^= 1
-        self._issue()
-        return out
+        return self.dev[s]
 
 
 class RBM(layer.Layer):
@@ -493,6 +523,7 @@ class RBM(layer.Layer):
             v0 = self.bottom.upprop(batch) if self.bottom else batch
             self.cd_step(v0, num_gibbs_steps, persistent, grad=grad, n_global=n_global)
             self.apply_gradient(optimizer, grad, opt_state, lr_now)
+            feeder.prefetch()              # host gather + H2D of the next batch overlap this step's kernels
             if step_callback is not None:
                 step_callback(self.iter, grad)
             if lr_interval and lr_drop and self.iter % lr_interval == 0:

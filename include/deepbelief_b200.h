@@ -212,6 +212,13 @@ int db_mse(db_handle_t h, db_stream_t stream, const float* a, const float* b, in
 int db_cross_entropy(db_handle_t h, db_stream_t stream, const float* probs, const float* targets, int N, int D,
                      int reduce_mean, float* out);
 
+/* ---- host-side data loader helper (no device work) --------------------------------------------- */
+/* dst[i, :] = src[rows[i], :] for i < n_rows — the batch gather of Data.next_batch (data.py:92-94:
+ * `datapoints[sorted_rows]`), multi-threaded, written straight into a (pinned) staging buffer.
+ * rows are validated against n_src_rows; threads <= 0 picks min(16, hardware threads). */
+int db_host_gather_rows(const void* src, size_t row_bytes, const int64_t* rows, size_t n_rows,
+                        size_t n_src_rows, void* dst, int threads);
+
 #ifdef __cplusplus
 }
 #endif

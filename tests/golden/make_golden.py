@@ -86,7 +86,7 @@ def rbm_goldens(out):
                 layer = make_layer(kind, V, H, W, b, c, opt_sigma)
                 v = (v_real if gv else v_bin).astype(dt)
                 h = (h_real if gh else h_bin).astype(dt)
-                vk = (v_real[::-1] if gv else vk_bin).astype(dt)
+                vk = (0.7 * v_real[::-1] + 0.05 if gv else vk_bin).astype(dt)
                 pre = '%s/%s/%s/' % (tag, kind, dname)
                 hp = layer.h_probs(v)
                 vp = layer.v_probs(h)
@@ -125,7 +125,7 @@ def rbm_goldens(out):
             if tag == 'toy':
                 set_dtype('float64')
                 v = (v_real if gv else v_bin)
-                vk = (v_real[::-1] if gv else vk_bin)
+                vk = (0.7 * v_real[::-1] + 0.05 if gv else vk_bin)
                 theta = [W.copy(), b.copy(), c.copy()] + ([opt_sigma.copy()] if gh else [])
 
                 def f(parts):

@@ -234,12 +234,19 @@ def test_full_size_n5000_properties():
     d = torch.randn(N, Q, device='cuda', generator=gen)
     d = d / d.norm()
 
+    hv = [float(v) for v in hyp.cpu()]
+
     def loss64(Xm):
-        Km = ops.gram_rbf(Xm.float().contiguous(), None, hyp, add_noise=True).double()
+        # K rebuilt in fp64 from the same effective hyper-parameters (torch fp64 is the checker only): an fp32 K
+        # carries ~3e-8 relative rounding per entry, which a central difference of a 1e7-sized loss amplifies
+        xx = Xm.double() / hv[1]
+        sq = (xx * xx).sum(1)
+        Km = hv[0] * torch.exp(-0.5 * (sq[:, None] + sq[None, :] - 2 * xx @ xx.t()).clamp_min(0))
+        Km = Km + hv[2] * torch.eye(N, device='cuda', dtype=torch.float64)
         Lm = torch.linalg.cholesky(Km)
         Sm = torch.linalg.solve_triangular(Lm, Y.double(), upper=False)
         return 0.5 * ((Sm ** 2).sum() + D * 2 * torch.log(torch.diagonal(Lm)).sum())
-    t = 1e-2
-    fd = float((loss64(X + t * d) - loss64(X - t * d)) / (2 * t))
+    t = 1e-3
+    fd = float((loss64(X.double() + t * d.double()) - loss64(X.double() - t * d.double())) / (2 * t))
     an = float((dX.double() * d.double()).sum())
     assert abs(fd - an) / (abs(fd) + 1e-30) < 5e-3

