@@ -25,6 +25,7 @@ import deepbelief.config as cfg  # noqa: E402
 from deepbelief import dist, preprocessing  # noqa: E402
 from deepbelief.layers import rbm as ref_rbm, bgrbm as ref_bgrbm, gbrbm as ref_gbrbm, ggrbm as ref_ggrbm  # noqa: E402
 from deepbelief.layers import gplvm as ref_gplvm  # noqa: E402
+from deepbelief.layers import gprbm as ref_gprbm  # noqa: E402
 
 sys.path.insert(0, os.path.join(HERE, '..', '..'))
 from deepbelief_b200 import hdf5  # noqa: E402  (only the HDF5 reader; h5py is unavailable)
@@ -256,6 +257,99 @@ def gp_goldens(out):
         out['horses/%s/X0' % dname] = np.asarray(g.X)
 
 
+def gpdbn_goldens(out):
+    """GPDBN stack (gpdbn_horses/train.py:49-94 in miniature): two Concrete RBMs + the GPRBM top layer, built and
+    evaluated by the reference's own gprbm.py / bgrbm.py / rbm.py / gplvm.py / dist.py. Parameters and every random
+    draw are injected (initial W through tf.truncated_normal, top b/c through tf.zeros, see the shim); the
+    gradient TF autodiff would give is pinned as directional finite differences (fp64) of that loss."""
+    rs = np.random.RandomState(2024)
+    N, V0, Ha, Hb, D, Q, T = 24, 30, 16, 12, 6, 2, 0.1
+    Vd = rs.binomial(1, 0.4, size=(N, V0)).astype(np.float64)
+    P = {'W0': rs.normal(size=(V0, Ha)) * 0.3, 'b0': rs.normal(size=V0) * 0.2, 'c0': rs.normal(size=Ha) * 0.2,
+         'W1': rs.normal(size=(Ha, Hb)) * 0.3, 'b1': rs.normal(size=Ha) * 0.2, 'c1': rs.normal(size=Hb) * 0.2,
+         'Wt': rs.normal(size=(Hb, D)) * 0.3, 'bt': rs.normal(size=Hb) * 0.2, 'ct': rs.normal(size=D) * 0.2,
+         'X': rs.normal(size=(N, Q))}
+    draws = {'up0': rs.uniform(size=(N, Ha)), 'up1': rs.uniform(size=(N, Hb)),
+             'eps1': rs.normal(size=(N, D)).astype(np.float32).astype(np.float64),
+             'eps2': rs.normal(size=(N, D)).astype(np.float32).astype(np.float64),
+             'down_top': rs.uniform(size=(N, Hb)), 'down1': rs.uniform(size=(N, Ha)), 'down0': rs.uniform(size=(N, V0))}
+    cases = {'fixed': dict(noise_variance=0.05, fixed_noise_variance=True, alpha=False, gamma=False),
+             'trainable': dict(noise_variance=0.3, fixed_noise_variance=False, alpha=1.4, gamma=0.9)}
+    for kk, vv in P.items():
+        out['gpdbn/P/' + kk] = vv
+    for kk, vv in draws.items():
+        out['gpdbn/draws/' + kk] = vv
+    out['gpdbn/V'] = Vd
+    out['gpdbn/T'] = np.float64(T)
+
+    def build(params, kw, dname, hyp=None):
+        set_dtype(dname)
+        dt = np.dtype(dname)
+        sess = tf.Session()
+        l0 = make_layer('rbm', V0, Ha, params['W0'], params['b0'], params['c0'], None, temperature=T, name='l0')
+        l1 = make_layer('rbm', Ha, Hb, params['W1'], params['b1'], params['c1'], None, temperature=T, bottom=l0, name='l1')
+        kern = ref_gplvm.SEKernel(alpha=kw['alpha'], gamma=kw['gamma'], session=sess)
+        if hyp is not None:           # perturbed optimisation variables (finite differences)
+            if kw['alpha'] is not False:
+                kern.opt_alpha = np.asarray(hyp[0], dtype=dt); kern.alpha = tf.nn.softplus(kern.opt_alpha)
+            if kw['gamma'] is not False:
+                kern.opt_gamma = np.asarray(hyp[1], dtype=dt); kern.gamma = tf.nn.softplus(kern.opt_gamma)
+        # the constructor itself evaluates K, L, pred_var and H1 = upprop(V) (gprbm.py:108-140): inject first
+        shim.TRUNC_QUEUE[:] = [params['Wt']]
+        shim.ZEROS_INJECT.clear()
+        shim.ZEROS_INJECT[(Hb, 1)] = [params['bt']]
+        shim.ZEROS_INJECT[(1, D)] = [params['ct']]
+        shim.RANDOM_QUEUE[:] = [draws['up0'], draws['up1'], draws['eps1']]
+        nv = kw['noise_variance']
+        if hyp is not None and not kw['fixed_noise_variance']:
+            nv = float(np.log1p(np.exp(hyp[2])))          # noise passed through its own inverse_softplus/softplus pair
+        g = ref_gprbm.GPRBM(num_v=Hb, num_h=D, Q=Q, N=N, eval_flag=False, X0=params['X'].astype(dt), V=Vd.astype(dt),
+                            kern=kern, noise_variance=nv, fixed_noise_variance=kw['fixed_noise_variance'],
+                            temperature=T, bottom=l1, session=sess, name='top')
+        if 'oah' in params:
+            raise RuntimeError('opt_alpha_h is created inside the constructor; perturb it through alpha_h_hook')
+        assert not shim.TRUNC_QUEUE and not shim.RANDOM_QUEUE
+        shim.ZEROS_INJECT.clear()
+        shim.RANDOM_QUEUE[:] = [draws['eps2'], draws['down_top'], draws['down1'], draws['down0']]
+        g.build_model()
+        assert not shim.RANDOM_QUEUE
+        return g
+
+    isp = lambda v: np.log(np.exp(v) - 1.0)  # noqa: E731
+    for cname, kw in cases.items():
+        for dname in ('float32', 'float64'):
+            g = build(P, kw, dname)
+            pre = 'gpdbn/%s/%s/' % (cname, dname)
+            out[pre + 'loss'] = np.asarray(g.loss)
+            out[pre + 'pred_var'] = np.asarray(g.pred_var)
+            out[pre + 'sigma_h'] = np.asarray(g.sigma_h)
+            out[pre + 'H1'] = np.asarray(g.H1)
+            out[pre + 'H2'] = np.asarray(g.H2)
+            out[pre + 'log_det'] = np.asarray(g.log_det)
+            out[pre + 'gp_loss'] = np.asarray(g.build_gp_loss(summary=False))
+        # directional finite differences of the reference loss (fp64): one random direction per parameter block
+        hyp0 = np.array([isp(kw['alpha']) if kw['alpha'] is not False else 0.0,
+                         isp(kw['gamma']) if kw['gamma'] is not False else 0.0, isp(kw['noise_variance'])])
+        out['gpdbn/%s/hyp_opt' % cname] = hyp0
+        eps = 1e-4     # the ~1e3-sized loss carries ~1e-10 evaluation noise: 1e-6 steps are noise-limited at 1e-4
+        drs = np.random.RandomState(7)
+        for key in ('W0', 'b0', 'c0', 'W1', 'b1', 'c1', 'Wt', 'bt', 'ct', 'X'):
+            d = drs.normal(size=P[key].shape)
+            d /= np.linalg.norm(d)
+            Pp, Pm = dict(P), dict(P)
+            Pp[key] = P[key] + eps * d
+            Pm[key] = P[key] - eps * d
+            fd = (float(build(Pp, kw, 'float64', hyp0).loss) - float(build(Pm, kw, 'float64', hyp0).loss)) / (2 * eps)
+            out['gpdbn/%s/dir/%s' % (cname, key)] = d
+            out['gpdbn/%s/fd/%s' % (cname, key)] = np.float64(fd)
+        if cname == 'trainable':
+            for j, key in enumerate(('opt_alpha', 'opt_gamma', 'opt_noise')):
+                hp, hm = hyp0.copy(), hyp0.copy()
+                hp[j] += eps; hm[j] -= eps
+                fd = (float(build(P, kw, 'float64', hp).loss) - float(build(P, kw, 'float64', hm).loss)) / (2 * eps)
+                out['gpdbn/%s/fd/%s' % (cname, key)] = np.float64(fd)
+
+
 def misc_goldens(out):
     rs = np.random.RandomState(99)
     set_dtype('float64')
@@ -273,7 +367,8 @@ def misc_goldens(out):
 
 
 def main():
-    for fn, name in ((rbm_goldens, 'rbm_golden.npz'), (gp_goldens, 'gp_golden.npz'), (misc_goldens, 'misc_golden.npz')):
+    for fn, name in ((rbm_goldens, 'rbm_golden.npz'), (gp_goldens, 'gp_golden.npz'), (misc_goldens, 'misc_golden.npz'),
+                     (gpdbn_goldens, 'gpdbn_golden.npz')):
         out = {}
         fn(out)
         path = os.path.join(HERE, name)

@@ -19,6 +19,8 @@ import numpy as np
 import scipy.linalg
 
 RANDOM_QUEUE = []          # arrays consumed by random_uniform / random_normal, in call order
+TRUNC_QUEUE = []           # arrays consumed by truncated_normal (initial W, rbm.py:59-62), in call order
+ZEROS_INJECT = {}          # shape -> list of arrays handed out by tf.zeros(shape) (initial b / c, rbm.py:64-72)
 _RNG = np.random.RandomState(0)
 
 
@@ -37,6 +39,9 @@ def _arr(x, dtype=None):
 class _Var(np.ndarray):
     """ndarray carrying the TF variable name (layer.py:13-15 filters on it)."""
     name = ''
+
+    def assign(self, value, name=None):        # returns the "op"; nothing is executed eagerly
+        return value
 
 
 def _make_var(value, name):
@@ -110,6 +115,10 @@ def random_normal(shape, mean=0.0, stddev=1.0, dtype='float32', seed=None, name=
 
 def truncated_normal(shape, mean=0.0, stddev=1.0, dtype='float32', seed=None, name=None):
     shape = tuple(int(s) for s in shape)
+    if TRUNC_QUEUE:            # injected initial weights (used as they are: parity runs choose W freely)
+        a = np.asarray(TRUNC_QUEUE.pop(0))
+        assert a.shape == shape, 'injected W has shape %s, op wants %s' % (a.shape, shape)
+        return a.astype(_dt(dtype))
     x = _RNG.normal(size=shape)
     bad = np.abs(x) > 2.0
     while bad.any():
@@ -119,7 +128,11 @@ def truncated_normal(shape, mean=0.0, stddev=1.0, dtype='float32', seed=None, na
 
 
 def zeros(shape, dtype='float32', name=None):
-    return np.zeros(tuple(int(s) for s in np.atleast_1d(shape)), dtype=_dt(dtype))
+    shape = tuple(int(s) for s in np.atleast_1d(shape))
+    pending = ZEROS_INJECT.get(shape)
+    if pending:
+        return np.asarray(pending.pop(0)).reshape(shape).astype(_dt(dtype))
+    return np.zeros(shape, dtype=_dt(dtype))
 
 
 def ones(shape, dtype='float32', name=None):
