@@ -83,6 +83,23 @@ SIGNATURES = {
     'db_softplus': (c_int, [c_void_p, c_void_p, c_float_p, c_int, c_float_p]),
     'db_mse': (c_int, [c_void_p, c_void_p, c_float_p, c_float_p, c_int, c_int, c_float_p]),
     'db_cross_entropy': (c_int, [c_void_p, c_void_p, c_float_p, c_float_p, c_int, c_int, c_int, c_float_p]),
+    'db_gpdbn_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'db_gpdbn_factor': (c_int, [c_void_p, c_void_p, c_float_p, c_int, c_int, c_int, c_float_p, c_int, c_float, c_float,
+                                c_void_p, c_float_p, c_float_p, c_void_p]),
+    'db_gpdbn_apply': (c_int, [c_void_p, c_void_p, c_float_p, c_int, c_int, c_int, c_void_p, c_float_p, c_float_p]),
+    'db_gpdbn_backward_h': (c_int, [c_void_p, c_void_p, c_float_p, c_int, c_int, c_int, c_void_p, c_float_p]),
+    'db_gpdbn_backward_x': (c_int, [c_void_p, c_void_p, c_float_p, c_float_p, c_int, c_int, c_int, c_float_p, c_int,
+                                    c_float, c_void_p, c_float_p, c_float_p]),
+    'db_gpdbn_top_forward_up': (c_int, [c_void_p, c_void_p] + [c_float_p] * 5 + [c_int, c_int] + [c_float_p] * 3),
+    'db_gpdbn_top_forward_mid': (c_int, [c_void_p, c_void_p] + [c_float_p] * 5 + [c_int, c_int] + [c_float_p] * 2),
+    'db_gpdbn_top_backward1': (c_int, [c_void_p, c_void_p] + [c_float_p] * 6 + [c_int, c_int] + [c_float_p] * 4),
+    'db_gpdbn_top_backward2': (c_int, [c_void_p, c_void_p] + [c_float_p] * 9 + [c_int, c_int] + [c_float_p] * 6),
+    'db_gemm': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float_p, c_int, c_float_p,
+                        c_int, c_float, c_float_p, c_int]),
+    'db_concrete_backward': (c_int, [c_void_p, c_void_p, c_float_p, c_float_p, c_float_p, c_int, c_int, c_float,
+                                     c_float_p]),
+    'db_cross_entropy_grad': (c_int, [c_void_p, c_void_p, c_float_p, c_float_p, c_int, c_int, c_float, c_float_p]),
+    'db_colsum': (c_int, [c_void_p, c_void_p, c_float_p, c_int, c_int, c_float, c_float, c_float_p]),
     'db_host_gather_rows': (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_void_p, c_int]),
 }
 

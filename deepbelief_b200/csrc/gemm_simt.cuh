@@ -1,0 +1,78 @@
+// General fp32 SIMT GEMM  C[M,N] = alpha * op(A) * op(B) + beta * C  (row-major, leading dimensions in
+// elements). Used for the backward products of the GPDBN stack (dW = A^T dZ, dA = dZ W^T: what TF autodiff
+// derives from tf.matmul, rbm.py:129,144) and the K^-1 products of the GP block. Built on the functor-loader
+// tile core of simt_gemm.cuh.
+#pragma once
+#include "context.h"
+#include "simt_gemm.cuh"
+
+namespace db {
+
+template <bool TRANS>
+struct GemmLoadA {   // a(m,k) of op(A): A is [M,K] (TRANS=0) or [K,M] (TRANS=1)
+  static constexpr bool k_contig = !TRANS;
+  const float* A; int lda; int M, K;
+  __device__ __forceinline__ float operator()(int m, int k) const {
+    if (m >= M || k >= K) return 0.0f;
+    return TRANS ? __ldg(A + (size_t)k * lda + m) : __ldg(A + (size_t)m * lda + k);
+  }
+};
+template <bool TRANS>
+struct GemmLoadB {   // b(k,n) of op(B): B is [K,N] (TRANS=0) or [N,K] (TRANS=1)
+  static constexpr bool k_contig = TRANS;
+  const float* B; int ldb; int K, N;
+  __device__ __forceinline__ float operator()(int k, int n) const {
+    if (k >= K || n >= N) return 0.0f;
+    return TRANS ? __ldg(B + (size_t)n * ldb + k) : __ldg(B + (size_t)k * ldb + n);
+  }
+};
+
+template <class T, bool TA, bool TB>
+__global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                                       float* __restrict__ C, int ldc, int M, int N, int K, float alpha,
+                                                       float beta) {
+  __shared__ typename T::Smem sm;
+  const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
+  GemmLoadA<TA> a{A, lda, M, K};
+  GemmLoadB<TB> b{B, ldb, K, N};
+  float acc[T::TM][T::TN];
+  simt_gemm_tile<T>(sm, a, b, m0, n0, 0, K, acc);
+#pragma unroll
+  for (int i = 0; i < T::TM; ++i) {
+    const int m = simt_row<T>(m0, i);
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < T::TN; ++j) {
+      const int n = simt_col<T>(n0, j);
+      if (n >= N) continue;
+      float* c = C + (size_t)m * ldc + n;
+      *c = beta != 0.0f ? fmaf(beta, *c, alpha * acc[i][j]) : alpha * acc[i][j];
+    }
+  }
+}
+
+template <class T, bool TA, bool TB>
+inline void launch_gemm_f32(cudaStream_t st, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N,
+                            int K, float alpha, float beta) {
+  dim3 grid((N + T::BN - 1) / T::BN, (M + T::BM - 1) / T::BM);
+  gemm_f32_kernel<T, TA, TB><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, alpha, beta);
+}
+
+// large tiles only when both output dimensions can fill them and there are enough tiles for 148 SMs
+inline int run_gemm_f32(db_handle_t h, cudaStream_t st, int transA, int transB, int M, int N, int K, float alpha,
+                        const float* A, int lda, const float* B, int ldb, float beta, float* C, int ldc) {
+  const bool large = M >= 512 && N >= 512 && ((size_t)M * N) / (128 * 128) >= (size_t)h->num_sms;
+#define DB_GEMM_CASE(TA, TB)                                                                              \
+  do {                                                                                                     \
+    if (large) launch_gemm_f32<TileLarge, TA, TB>(st, A, lda, B, ldb, C, ldc, M, N, K, alpha, beta);       \
+    else launch_gemm_f32<TileSmall, TA, TB>(st, A, lda, B, ldb, C, ldc, M, N, K, alpha, beta);             \
+  } while (0)
+  if (!transA && !transB) DB_GEMM_CASE(false, false);
+  else if (transA && !transB) DB_GEMM_CASE(true, false);
+  else if (!transA && transB) DB_GEMM_CASE(false, true);
+  else DB_GEMM_CASE(true, true);
+#undef DB_GEMM_CASE
+  return check_launch(h, "gemm_f32");
+}
+
+}  // namespace db

@@ -14,6 +14,7 @@
 // Algorithmic work: N^3 + 3 N^2 D FLOP (SURVEY.md §8 d).
 #include "context.h"
 #include "simt_gemm.cuh"
+#include "gemm_simt.cuh"
 
 namespace db {
 namespace {
@@ -424,31 +425,13 @@ struct LoadA_B {       // b(k,n) = Avec[n, k]
   __device__ __forceinline__ float operator()(int k, int n) const { return (n < N && k < D) ? __ldg(A + (size_t)n * ld + k) : 0.0f; }
 };
 
-__global__ void __launch_bounds__(256) gp_grad_kernel(const float* __restrict__ Li, int ldi, const float* __restrict__ Av, int lda,
-                                                      const float* __restrict__ X, int N, int Q, int D,
-                                                      const float* __restrict__ hyp, float* __restrict__ dXacc, GpAccum* accum) {
-  using T = TileLarge;
-  if (blockIdx.x > blockIdx.y) return;
-  __shared__ typename T::Smem sm;
-  __shared__ float rowacc[T::BM][MAXQ];
-  __shared__ float colacc[T::BN][MAXQ];
-  __shared__ float red[3][8];
-  const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
-  const bool diag_tile = blockIdx.x == blockIdx.y;
-  for (int t = threadIdx.x; t < T::BM * MAXQ; t += 256) { (&rowacc[0][0])[t] = 0.0f; (&colacc[0][0])[t] = 0.0f; }
-
-  float gacc[T::TM][T::TN];   // G tile = (D/2) Linv^T Linv - (1/2) A A^T, one accumulator for both products
-  {
-    LoadLinvT_A a{Li, ldi, N, 0.5f * (float)D};
-    LoadLinvT_B b{Li, ldi, N};
-    simt_gemm_tile<T>(sm, a, b, m0, n0, m0 /* Linv[k,i] = 0 for k < i and i >= m0 */, N, gacc);
-  }
-  __syncthreads();
-  {
-    LoadA_A a{Av, lda, N, D};
-    LoadA_B b{Av, lda, N, D};
-    simt_gemm_tile<T, LoadA_A, LoadA_B, false>(sm, a, b, m0, n0, 0, D, gacc);
-  }
+// Contract one lower tile (I >= J) of a SYMMETRIC matrix G with K_f on the fly:
+//   dXacc_i += -(2/gamma^2) sum_j G_ij Kf_ij (x_i - x_j),  trG, sum G o Kf, sum G o Kf o r^2  
+template <class T>
+__device__ __forceinline__ void gp_contract_tile(float (&gacc)[T::TM][T::TN], int m0, int n0, bool diag_tile,
+                                                 const float* __restrict__ X, int N, int Q, const float* __restrict__ hyp,
+                                                 float* __restrict__ dXacc, GpAccum* accum, float (*rowacc)[MAXQ],
+                                                 float (*colacc)[MAXQ], float (*red)[8]) {
   const float alpha = __ldg(hyp), inv_g2 = 1.0f / (__ldg(hyp + 1) * __ldg(hyp + 1));
   float trg = 0.0f, sw = 0.0f, swr = 0.0f;
 #pragma unroll
@@ -489,6 +472,34 @@ __global__ void __launch_bounds__(256) gp_grad_kernel(const float* __restrict__ 
     for (int w = 0; w < 8; ++w) { a += red[0][w]; b += red[1][w]; c += red[2][w]; }
     atomicAdd(&accum->trG, a); atomicAdd(&accum->sumW, b); atomicAdd(&accum->sumWr2, c);
   }
+}
+
+__global__ void __launch_bounds__(256) gp_grad_kernel(const float* __restrict__ Li, int ldi, const float* __restrict__ Av, int lda,
+                                                      const float* __restrict__ X, int N, int Q, int D,
+                                                      const float* __restrict__ hyp, float* __restrict__ dXacc, GpAccum* accum) {
+  using T = TileLarge;
+  if (blockIdx.x > blockIdx.y) return;
+  __shared__ typename T::Smem sm;
+  __shared__ float rowacc[T::BM][MAXQ];
+  __shared__ float colacc[T::BN][MAXQ];
+  __shared__ float red[3][8];
+  const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
+  const bool diag_tile = blockIdx.x == blockIdx.y;
+  for (int t = threadIdx.x; t < T::BM * MAXQ; t += 256) { (&rowacc[0][0])[t] = 0.0f; (&colacc[0][0])[t] = 0.0f; }
+
+  float gacc[T::TM][T::TN];   // G tile = (D/2) Linv^T Linv - (1/2) A A^T, one accumulator for both products
+  {
+    LoadLinvT_A a{Li, ldi, N, 0.5f * (float)D};
+    LoadLinvT_B b{Li, ldi, N};
+    simt_gemm_tile<T>(sm, a, b, m0, n0, m0 /* Linv[k,i] = 0 for k < i and i >= m0 */, N, gacc);
+  }
+  __syncthreads();
+  {
+    LoadA_A a{Av, lda, N, D};
+    LoadA_B b{Av, lda, N, D};
+    simt_gemm_tile<T, LoadA_A, LoadA_B, false>(sm, a, b, m0, n0, 0, D, gacc);
+  }
+  gp_contract_tile<T>(gacc, m0, n0, diag_tile, X, N, Q, hyp, dXacc, accum, rowacc, colacc, red);
 }
 
 // scalars + prior term of dX
@@ -624,6 +635,195 @@ GplvmWorkspace gplvm_workspace(void* ws, int N, int Q, int D) {
   return w;
 }
 
+
+// ---- GPDBN top layer (gprbm.py), training mode x_ph = X ------------------------------------------------
+// With K_Xx = K_f = K - s I (s = noise variance) the reference's quantities collapse to (after GP14):
+//   pred_var = s - s^2 diag(K^-1)        (gprbm.py:208-218)
+//   Hm       = H2 - s K^-1 H2            (gprbm.py:220-226)
+//   gp_loss  = 0.5 (sum H2 o K^-1 H2 + D logdet K) + |X|^2      (gprbm.py:234-245)
+// so the N-right-hand-side triangular solve disappears; K^-1 is formed explicitly once per step.
+
+// Kinv = Linv^T Linv, both triangles written (lower tile pairs computed, mirrored)
+__global__ void __launch_bounds__(256) kinv_kernel(const float* __restrict__ Li, int ldi, int N, float* __restrict__ Kinv) {
+  using T = TileLarge;
+  if (blockIdx.x > blockIdx.y) return;
+  __shared__ typename T::Smem sm;
+  const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
+  LoadLinvT_A a{Li, ldi, N, 1.0f};
+  LoadLinvT_B b{Li, ldi, N};
+  float acc[T::TM][T::TN];
+  simt_gemm_tile<T>(sm, a, b, m0, n0, m0, N, acc);
+#pragma unroll
+  for (int i = 0; i < T::TM; ++i) {
+    const int m = simt_row<T>(m0, i);
+    if (m >= N) continue;
+#pragma unroll
+    for (int jj = 0; jj < T::TN; ++jj) {
+      const int n = simt_col<T>(n0, jj);
+      if (n >= N) continue;
+      Kinv[(size_t)m * N + n] = acc[i][jj];
+      Kinv[(size_t)n * N + m] = acc[i][jj];
+    }
+  }
+}
+
+__global__ void gpdbn_pred_var_kernel(const float* __restrict__ Kinv, int N, const float* __restrict__ hyp, float* __restrict__ pv,
+                                      int* __restrict__ info) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float s = __ldg(hyp + 2);
+  const float v = s - s * s * __ldg(Kinv + (size_t)i * N + i);
+  pv[i] = v;
+  if (!(v >= 0.0f)) atomicCAS(info + 1, 0, i + 1);          // tf.assert_non_negative(pred_var), gprbm.py:215
+}
+
+// Hm = H2 - s B ; ssq += sum H2 o B
+__global__ void gpdbn_apply_kernel(const float* __restrict__ H2, const float* __restrict__ B, size_t n, const float* __restrict__ hyp,
+                                   float* __restrict__ Hm, GpAccum* acc) {
+  const float s = __ldg(hyp + 2);
+  float local = 0.0f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float h = __ldg(H2 + i), b = __ldg(B + i);
+    Hm[i] = fmaf(-s, b, h);
+    local = fmaf(h, b, local);
+  }
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&acc->ssq, local);
+}
+__global__ void gpdbn_scalars_kernel(const GpAccum* __restrict__ acc, const float* __restrict__ hyp, int D, float* __restrict__ out) {
+  out[0] = 0.5f * (acc->ssq + (float)D * acc->logdet) + acc->xsq;      // gprbm.py:242
+  out[1] = acc->logdet; out[2] = acc->ssq; out[3] = acc->xsq;
+  out[4] = hyp[0]; out[5] = hyp[1]; out[6] = hyp[2]; out[7] = 0.0f;
+}
+// g_H2 = g_Hm - s P + B ; pad[0] += sum g_Hm o B
+__global__ void gpdbn_backward_h_kernel(const float* __restrict__ gHm, const float* __restrict__ P, const float* __restrict__ B,
+                                        size_t n, const float* __restrict__ hyp, float* __restrict__ gH2, GpAccum* acc) {
+  const float s = __ldg(hyp + 2);
+  float local = 0.0f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float g = __ldg(gHm + i), b = __ldg(B + i);
+    gH2[i] = fmaf(-s, __ldg(P + i), g) + b;
+    local = fmaf(g, b, local);
+  }
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&acc->pad[0], local);
+}
+// pad[1] = sum_i g_pv_i (1 - 2 s Kinv_ii)
+__global__ void gpdbn_gpv_scalar_kernel(const float* __restrict__ gpv, const float* __restrict__ Kinv, int N,
+                                        const float* __restrict__ hyp, GpAccum* acc) {
+  const float s = __ldg(hyp + 2);
+  float local = 0.0f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x)
+    local += __ldg(gpv + i) * (1.0f - 2.0f * s * __ldg(Kinv + (size_t)i * N + i));
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&acc->pad[1], local);
+}
+
+// G = s^2 Kinv diag(g_pv) Kinv + 0.5 (E B^T + B E^T) + (D/2) Kinv, E = s P - 0.5 B   (symmetric part of dLoss/dK)
+struct LoadKinvScaledA {   // a(m,k) = s^2 g_k Kinv[m,k]
+  static constexpr bool k_contig = true;
+  const float* Kinv; const float* gpv; int N; float s2;
+  __device__ __forceinline__ float operator()(int m, int k) const {
+    return (m < N && k < N) ? s2 * __ldg(gpv + k) * __ldg(Kinv + (size_t)m * N + k) : 0.0f;
+  }
+};
+struct LoadKinvB {         // b(k,n) = Kinv[n,k]
+  static constexpr bool k_contig = true;
+  const float* Kinv; int N;
+  __device__ __forceinline__ float operator()(int k, int n) const { return (n < N && k < N) ? __ldg(Kinv + (size_t)n * N + k) : 0.0f; }
+};
+struct LoadEB_A {          // a(m,k) = k < D ? 0.5 E[m,k] : 0.5 B[m,k-D]
+  static constexpr bool k_contig = true;
+  const float* P; const float* B; int N, D; float s;
+  __device__ __forceinline__ float operator()(int m, int k) const {
+    if (m >= N || k >= 2 * D) return 0.0f;
+    if (k < D) return 0.5f * (s * __ldg(P + (size_t)m * D + k) - 0.5f * __ldg(B + (size_t)m * D + k));
+    return 0.5f * __ldg(B + (size_t)m * D + (k - D));
+  }
+};
+struct LoadEB_B {          // b(k,n) = k < D ? B[n,k] : E[n,k-D]
+  static constexpr bool k_contig = true;
+  const float* P; const float* B; int N, D; float s;
+  __device__ __forceinline__ float operator()(int k, int n) const {
+    if (n >= N || k >= 2 * D) return 0.0f;
+    if (k < D) return __ldg(B + (size_t)n * D + k);
+    return s * __ldg(P + (size_t)n * D + (k - D)) - 0.5f * __ldg(B + (size_t)n * D + (k - D));
+  }
+};
+__global__ void __launch_bounds__(256) gpdbn_grad_kernel(const float* __restrict__ Kinv, const float* __restrict__ gpv,
+                                                         const float* __restrict__ P, const float* __restrict__ B,
+                                                         const float* __restrict__ X, int N, int Q, int D,
+                                                         const float* __restrict__ hyp, float* __restrict__ dXacc, GpAccum* accum) {
+  using T = TileLarge;
+  if (blockIdx.x > blockIdx.y) return;
+  __shared__ typename T::Smem sm;
+  __shared__ float rowacc[T::BM][MAXQ];
+  __shared__ float colacc[T::BN][MAXQ];
+  __shared__ float red[3][8];
+  const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
+  const bool diag_tile = blockIdx.x == blockIdx.y;
+  for (int t = threadIdx.x; t < T::BM * MAXQ; t += 256) { (&rowacc[0][0])[t] = 0.0f; (&colacc[0][0])[t] = 0.0f; }
+  const float s = __ldg(hyp + 2);
+  float gacc[T::TM][T::TN];
+  {
+    LoadKinvScaledA a{Kinv, gpv, N, s * s};
+    LoadKinvB b{Kinv, N};
+    simt_gemm_tile<T>(sm, a, b, m0, n0, 0, N, gacc);
+  }
+  __syncthreads();
+  {
+    LoadEB_A a{P, B, N, D, s};
+    LoadEB_B b{P, B, N, D, s};
+    simt_gemm_tile<T, LoadEB_A, LoadEB_B, false>(sm, a, b, m0, n0, 0, 2 * D, gacc);
+  }
+  const float half_d = 0.5f * (float)D;
+#pragma unroll
+  for (int i = 0; i < T::TM; ++i) {
+    const int m = simt_row<T>(m0, i);
+#pragma unroll
+    for (int jj = 0; jj < T::TN; ++jj) {
+      const int n = simt_col<T>(n0, jj);
+      if (m < N && n < N) gacc[i][jj] = fmaf(half_d, __ldg(Kinv + (size_t)m * N + n), gacc[i][jj]);
+    }
+  }
+  gp_contract_tile<T>(gacc, m0, n0, diag_tile, X, N, Q, hyp, dXacc, accum, rowacc, colacc, red);
+}
+__global__ void gpdbn_finalize_kernel(const GpAccum* __restrict__ acc, const float* __restrict__ hyp, const float* __restrict__ opt,
+                                      int flags, int N, int Q, float x_prior_w, const float* __restrict__ X,
+                                      const float* __restrict__ dXacc, float* __restrict__ dX, float* __restrict__ dhyp) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i = tid; i < N * Q; i += gridDim.x * blockDim.x) dX[i] = dXacc[i] + 2.0f * x_prior_w * __ldg(X + i);
+  if (tid == 0) {
+    const float alpha = hyp[0], gamma = hyp[1];
+    dhyp[0] = (flags & 1) ? (acc->sumW / alpha) * sigmoidf_(opt[0]) : 0.0f;
+    dhyp[1] = (flags & 2) ? (acc->sumWr2 / (gamma * gamma * gamma)) * sigmoidf_(opt[1]) : 0.0f;
+    // noise: trace of dLoss/dK plus the explicit dependence of Hm and pred_var on s
+    dhyp[2] = (flags & 4) ? (acc->trG - acc->pad[0] + acc->pad[1]) * sigmoidf_(opt[2]) : 0.0f;
+  }
+}
+
+struct GpdbnWorkspace {
+  float *K, *Li, *Kinv, *B, *P, *dXacc, *hyp;
+  GpAccum* acc;
+  size_t bytes;
+};
+GpdbnWorkspace gpdbn_workspace(void* ws, int N, int Q, int D) {
+  GpdbnWorkspace w;
+  uint8_t* p = static_cast<uint8_t*>(ws);
+  uint8_t* p0 = p;
+  const size_t nn = align256(sizeof(float) * (size_t)N * N), nd = align256(sizeof(float) * (size_t)N * D);
+  w.K = reinterpret_cast<float*>(p); p += nn;
+  w.Li = reinterpret_cast<float*>(p); p += nn;
+  w.Kinv = reinterpret_cast<float*>(p); p += nn;      // doubles as the scratch of the triangular inversion
+  w.B = reinterpret_cast<float*>(p); p += nd;
+  w.P = reinterpret_cast<float*>(p); p += nd;
+  w.dXacc = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)N * Q);
+  w.hyp = reinterpret_cast<float*>(p); p += 256;
+  w.acc = reinterpret_cast<GpAccum*>(p); p += 256;
+  w.bytes = (size_t)(p - p0);
+  return w;
+}
+
 }  // namespace
 }  // namespace db
 
@@ -720,4 +920,79 @@ extern "C" int db_gp_predict(db_handle_t h, db_stream_t stream, const float* X, 
     pred_mean_kernel<<<grid, 256, 0, st>>>(workspace, S, N, M, D, y_mean, mean);
   }
   return check_launch(h, "gp_predict");
+}
+
+// ---- GPDBN top layer -------------------------------------------------------------------------------------
+extern "C" size_t db_gpdbn_workspace_bytes(int N, int Q, int D) {
+  if (N <= 0 || Q <= 0 || D <= 0) return 0;
+  return gpdbn_workspace(nullptr, N, Q, D).bytes;
+}
+
+extern "C" int db_gpdbn_factor(db_handle_t h, db_stream_t stream, const float* X, int N, int Q, int D, const float* hyp_opt,
+                               int flags, float fixed_noise, float jitter, void* workspace, float* pred_var, float* L_out,
+                               int* info) {
+  DB_REQUIRE(h, X && hyp_opt && workspace && pred_var && info, "null operand");
+  DB_REQUIRE(h, N > 1 && Q > 0 && Q <= MAXQ && D > 0, "bad shape (Q <= 8)");
+  cudaStream_t st = (cudaStream_t)stream;
+  GpdbnWorkspace w = gpdbn_workspace(workspace, N, Q, D);
+  int rc;
+  effective_hyp_kernel<<<1, 1, 0, st>>>(hyp_opt, flags, fixed_noise, jitter, w.hyp);
+  cudaMemsetAsync(w.acc, 0, sizeof(GpAccum), st);
+  cudaMemsetAsync(info, 0, 2 * sizeof(int), st);
+  if ((rc = run_gram(h, st, X, nullptr, N, N, Q, w.hyp, 1, w.K, N))) return rc;
+  {  // run_potrf clears info[0] itself
+    if ((rc = run_potrf(h, st, w.K, N, N, info))) return rc;
+  }
+  if (L_out) cudaMemcpyAsync(L_out, w.K, sizeof(float) * (size_t)N * N, cudaMemcpyDeviceToDevice, st);
+  logdet_xsq_kernel<<<1, 1024, 0, st>>>(w.K, N, N, X, N * Q, w.acc);
+  if ((rc = run_trinv(h, st, w.K, N, N, w.Li, w.Kinv))) return rc;
+  const int tiles = (N + TileLarge::BM - 1) / TileLarge::BM;
+  kinv_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(w.Li, N, N, w.Kinv);
+  gpdbn_pred_var_kernel<<<(N + 255) / 256, 256, 0, st>>>(w.Kinv, N, w.hyp, pred_var, info);
+  return check_launch(h, "gpdbn_factor");
+}
+
+extern "C" int db_gpdbn_apply(db_handle_t h, db_stream_t stream, const float* H2, int N, int Q, int D, void* workspace,
+                              float* Hm, float* scalars) {
+  DB_REQUIRE(h, H2 && workspace && Hm && scalars && N > 1 && D > 0, "null operand or bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  GpdbnWorkspace w = gpdbn_workspace(workspace, N, Q, D);
+  int rc;
+  cudaMemsetAsync(&w.acc->ssq, 0, sizeof(float), st);
+  if ((rc = run_gemm_f32(h, st, 0, 0, N, D, N, 1.0f, w.Kinv, N, H2, D, 0.0f, w.B, D))) return rc;
+  const size_t n = (size_t)N * D;
+  gpdbn_apply_kernel<<<(int)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256), 256, 0, st>>>(H2, w.B, n, w.hyp, Hm, w.acc);
+  gpdbn_scalars_kernel<<<1, 1, 0, st>>>(w.acc, w.hyp, D, scalars);
+  return check_launch(h, "gpdbn_apply");
+}
+
+extern "C" int db_gpdbn_backward_h(db_handle_t h, db_stream_t stream, const float* g_Hm, int N, int Q, int D, void* workspace,
+                                   float* g_H2) {
+  DB_REQUIRE(h, g_Hm && workspace && g_H2 && N > 1 && D > 0, "null operand or bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  GpdbnWorkspace w = gpdbn_workspace(workspace, N, Q, D);
+  int rc;
+  cudaMemsetAsync(&w.acc->pad[0], 0, 2 * sizeof(float), st);
+  if ((rc = run_gemm_f32(h, st, 0, 0, N, D, N, 1.0f, w.Kinv, N, g_Hm, D, 0.0f, w.P, D))) return rc;
+  const size_t n = (size_t)N * D;
+  gpdbn_backward_h_kernel<<<(int)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256), 256, 0, st>>>(g_Hm, w.P, w.B, n, w.hyp, g_H2,
+                                                                                                   w.acc);
+  return check_launch(h, "gpdbn_backward_h");
+}
+
+extern "C" int db_gpdbn_backward_x(db_handle_t h, db_stream_t stream, const float* X, const float* g_pv, int N, int Q, int D,
+                                   const float* hyp_opt, int flags, float x_prior_weight, void* workspace, float* dX,
+                                   float* dhyp) {
+  DB_REQUIRE(h, X && g_pv && hyp_opt && workspace && dX && dhyp, "null operand");
+  DB_REQUIRE(h, N > 1 && Q > 0 && Q <= MAXQ && D > 0, "bad shape (Q <= 8)");
+  cudaStream_t st = (cudaStream_t)stream;
+  GpdbnWorkspace w = gpdbn_workspace(workspace, N, Q, D);
+  cudaMemsetAsync(w.dXacc, 0, sizeof(float) * (size_t)N * Q, st);
+  cudaMemsetAsync(&w.acc->trG, 0, 3 * sizeof(float), st);      // trG, sumW, sumWr2
+  gpdbn_gpv_scalar_kernel<<<(N + 255) / 256 > 64 ? 64 : (N + 255) / 256, 256, 0, st>>>(g_pv, w.Kinv, N, w.hyp, w.acc);
+  const int tiles = (N + TileLarge::BM - 1) / TileLarge::BM;
+  gpdbn_grad_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(w.Kinv, g_pv, w.P, w.B, X, N, Q, D, w.hyp, w.dXacc, w.acc);
+  gpdbn_finalize_kernel<<<(N * Q + 255) / 256, 256, 0, st>>>(w.acc, w.hyp, hyp_opt, flags, N, Q, x_prior_weight, X, w.dXacc, dX,
+                                                            dhyp);
+  return check_launch(h, "gpdbn_backward_x");
 }

@@ -1,0 +1,255 @@
+// Backward pass of the GPDBN stack (gprbm.py:247-256 loss, minimised by TF autodiff in gprbm.py:386-396):
+// the general fp32 GEMM entry, the Concrete-unit and cross-entropy derivatives, and the fused elementwise
+// stages of the GPRBM top layer. The GP block itself (K, L, K^-1, pred_var, Hm, dX) lives in gp.cu.
+//
+// Top-layer algebra (alpha = alpha_h[d], r = sqrt(pred_var[n]), sigma_h = alpha r — gprbm.py:114-115):
+//   H1 = sigma_h (x + eps1) + c           x = a W          (bgrbm.py:79-82, 107-110)
+//   H2 = (H1 - mean_n H1) / alpha                           (gprbm.py:146-147)
+//   H  = Hm alpha + mean_n H1 + sigma_h eps2                (gprbm.py:225-231)
+//   y  = H / sigma_h                                         (bgrbm.py:126)
+#include "context.h"
+#include "gemm_simt.cuh"
+
+namespace db {
+namespace {
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.0f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+  return t;
+}
+
+// dz = g * d concrete/dp * dp/dz, with a = concrete(p, u, T) saved by the forward pass (rbm.py:243-275):
+//   da/dp = a (1-a) / T * (1/(p+e0) + 1/(1-p+e0)),  dp/dz = p (1-p)
+__global__ void concrete_backward_kernel(const float* __restrict__ g, const float* __restrict__ p, const float* __restrict__ a,
+                                         size_t n, float inv_temp, float* __restrict__ dz) {
+  const float e0 = 1.0e-6f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float pv = __ldg(p + i), av = __ldg(a + i);
+    dz[i] = __ldg(g + i) * av * (1.0f - av) * inv_temp * (1.0f / (pv + e0) + 1.0f / (1.0f - pv + e0)) * pv * (1.0f - pv);
+  }
+}
+
+// d/dprobs of dist.cross_entropy (dist.py:24-35): clip to [1e-6, 1-1e-6] (gradient passes inside the interval only),
+// logits = log(pc/(1-pc)), sigmoid CE  ->  -t/pc + (1-t)/(1-pc)
+__global__ void cross_entropy_grad_kernel(const float* __restrict__ probs, const float* __restrict__ t, size_t n, float scale,
+                                          float* __restrict__ out) {
+  const float e0 = 1.0e-6f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float p = __ldg(probs + i), tv = __ldg(t + i);
+    const float pc = fminf(fmaxf(p, e0), 1.0f - e0);
+    const bool inside = p >= e0 && p <= 1.0f - e0;
+    out[i] = inside ? scale * (-tv / pc + (1.0f - tv) / (1.0f - pc)) : 0.0f;
+  }
+}
+
+// out[c] = beta * out[c] + scale * sum_n A[n,c] : one CTA per 32 columns, 8 row lanes
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A, int M, int N, float scale, float beta,
+                                                     float* __restrict__ out) {
+  __shared__ float part[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), ry = threadIdx.x >> 5;
+  float s = 0.0f;
+  if (c < N) for (int r = ry; r < M; r += 8) s += __ldg(A + (size_t)r * N + c);
+  part[ry][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (ry == 0 && c < N) {
+    float t = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x & 31];
+    out[c] = (beta != 0.0f ? beta * out[c] : 0.0f) + scale * t;
+  }
+}
+
+// ---- top layer, forward --------------------------------------------------------------------------------
+// one CTA per hidden unit d: H1[:,d], its mean, H2[:,d]
+__global__ void __launch_bounds__(256) top_up_kernel(const float* __restrict__ x, const float* __restrict__ pv,
+                                                     const float* __restrict__ alpha_h, const float* __restrict__ c,
+                                                     const float* __restrict__ eps1, int N, int D, float* __restrict__ H1,
+                                                     float* __restrict__ H1_mean, float* __restrict__ H2) {
+  __shared__ float red[8];
+  const int d = blockIdx.x;
+  const float al = __ldg(alpha_h + d), cd = __ldg(c + d);
+  float s = 0.0f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const size_t i = (size_t)n * D + d;
+    const float h = al * sqrtf(__ldg(pv + n)) * (__ldg(x + i) + __ldg(eps1 + i)) + cd;
+    H1[i] = h;
+    s += h;
+  }
+  const float mean = block_sum(s, red) / (float)N;
+  if (threadIdx.x == 0) H1_mean[d] = mean;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const size_t i = (size_t)n * D + d;
+    H2[i] = (H1[i] - mean) / al;
+  }
+}
+// H = Hm alpha + mean + alpha r eps2 ; y = H / (alpha r)
+__global__ void top_mid_kernel(const float* __restrict__ Hm, const float* __restrict__ pv, const float* __restrict__ alpha_h,
+                               const float* __restrict__ H1_mean, const float* __restrict__ eps2, int N, int D,
+                               float* __restrict__ H, float* __restrict__ y) {
+  const size_t total = (size_t)N * D;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / D), d = (int)(i % D);
+    const float al = __ldg(alpha_h + d), sg = al * sqrtf(__ldg(pv + n));
+    const float h = fmaf(__ldg(Hm + i), al, __ldg(H1_mean + d)) + sg * __ldg(eps2 + i);
+    if (H) H[i] = h;
+    y[i] = h / sg;
+  }
+}
+
+// ---- top layer, backward -------------------------------------------------------------------------------
+// from g_y: g_Hm = g_H alpha, gsig = -g_y y / sigma + g_H eps2, ga[d] = sum_n g_H Hm, gmean[d] = sum_n g_H   (g_H = g_y / sigma)
+__global__ void __launch_bounds__(256) top_back1_kernel(const float* __restrict__ g_y, const float* __restrict__ y,
+                                                        const float* __restrict__ Hm, const float* __restrict__ pv,
+                                                        const float* __restrict__ alpha_h, const float* __restrict__ eps2, int N,
+                                                        int D, float* __restrict__ g_Hm, float* __restrict__ gsig,
+                                                        float* __restrict__ ga, float* __restrict__ gmean) {
+  __shared__ float red[8];
+  const int d = blockIdx.x;
+  const float al = __ldg(alpha_h + d);
+  float sa = 0.0f, sm = 0.0f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const size_t i = (size_t)n * D + d;
+    const float sg = al * sqrtf(__ldg(pv + n));
+    const float gy = __ldg(g_y + i), gH = gy / sg;
+    g_Hm[i] = gH * al;
+    gsig[i] = -gy * __ldg(y + i) / sg + gH * __ldg(eps2 + i);
+    sa = fmaf(gH, __ldg(Hm + i), sa);
+    sm += gH;
+  }
+  sa = block_sum(sa, red);
+  sm = block_sum(sm, red);
+  if (threadIdx.x == 0) { ga[d] = sa; gmean[d] = sm; }
+}
+// from g_H2: g_H1 (centred), g_x = g_H1 sigma, gsig += g_H1 (x + eps1), g_c[d], g_alpha[d] total
+__global__ void __launch_bounds__(256) top_back2_kernel(const float* __restrict__ g_H2, const float* __restrict__ H2,
+                                                        const float* __restrict__ x, const float* __restrict__ eps1,
+                                                        const float* __restrict__ pv, const float* __restrict__ alpha_h,
+                                                        const float* __restrict__ ga_in, const float* __restrict__ gmean_in, int N,
+                                                        int D, float* __restrict__ g_x, float* __restrict__ gsig,
+                                                        float* __restrict__ g_c, float* __restrict__ g_alpha) {
+  __shared__ float red[8];
+  const int d = blockIdx.x;
+  const float al = __ldg(alpha_h + d);
+  float s1 = 0.0f, s2 = 0.0f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const size_t i = (size_t)n * D + d;
+    const float g = __ldg(g_H2 + i);
+    s1 += g / al;
+    s2 = fmaf(g, __ldg(H2 + i), s2);
+  }
+  s1 = block_sum(s1, red);                       // sum_n g_H2 / alpha
+  s2 = block_sum(s2, red);                       // sum_n g_H2 o H2
+  const float gmean_total = __ldg(gmean_in + d) - s1;
+  float sc = 0.0f, sal = 0.0f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const size_t i = (size_t)n * D + d;
+    const float r = sqrtf(__ldg(pv + n));
+    const float gH1 = __ldg(g_H2 + i) / al + gmean_total / (float)N;
+    g_x[i] = gH1 * al * r;
+    const float gs = gsig[i] + gH1 * (__ldg(x + i) + __ldg(eps1 + i));
+    gsig[i] = gs;
+    sc += gH1;
+    sal = fmaf(gs, r, sal);
+  }
+  sc = block_sum(sc, red);
+  sal = block_sum(sal, red);
+  if (threadIdx.x == 0) {
+    g_c[d] = sc;
+    g_alpha[d] = __ldg(ga_in + d) - s2 / al + sal;
+  }
+}
+// g_pv[n] = (sum_d gsig[n,d] alpha_d) / (2 r_n) ; g_opt_alpha_h[d] = g_alpha[d] sigmoid(opt_alpha_h[d])  (one warp per row)
+__global__ void top_back3_kernel(const float* __restrict__ gsig, const float* __restrict__ pv, const float* __restrict__ alpha_h,
+                                 const float* __restrict__ g_alpha, const float* __restrict__ opt_alpha_h, int N, int D,
+                                 float* __restrict__ g_pv, float* __restrict__ g_opt_alpha_h) {
+  const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x & 31;
+  if (blockIdx.x == 0)
+    for (int d = threadIdx.x; d < D; d += blockDim.x) g_opt_alpha_h[d] = __ldg(g_alpha + d) * sigmoidf_(__ldg(opt_alpha_h + d));
+  if (row >= N) return;
+  float s = 0.0f;
+  for (int d = lane; d < D; d += 32) s = fmaf(__ldg(gsig + (size_t)row * D + d), __ldg(alpha_h + d), s);
+  s = warp_sum(s);
+  if (lane == 0) g_pv[row] = s / (2.0f * sqrtf(__ldg(pv + row)));
+}
+
+inline int ew_blocks(size_t n, int num_sms) {
+  size_t blocks = (n + 255) / 256, cap = (size_t)num_sms * 8;
+  return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+}  // namespace
+}  // namespace db
+
+using namespace db;
+
+extern "C" int db_gemm(db_handle_t h, db_stream_t stream, int transA, int transB, int M, int N, int K, float alpha,
+                       const float* A, int lda, const float* B, int ldb, float beta, float* C, int ldc) {
+  DB_REQUIRE(h, A && B && C && M > 0 && N > 0 && K > 0, "null operand or empty shape");
+  DB_REQUIRE(h, lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N, "leading dimension too small");
+  return run_gemm_f32(h, (cudaStream_t)stream, transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+}
+
+extern "C" int db_concrete_backward(db_handle_t h, db_stream_t stream, const float* g, const float* p, const float* a, int M,
+                                    int N, float temperature, float* dz) {
+  DB_REQUIRE(h, g && p && a && dz && M > 0 && N > 0 && temperature > 0.0f, "null operand, empty shape or temperature <= 0");
+  const size_t n = (size_t)M * N;
+  concrete_backward_kernel<<<ew_blocks(n, h->num_sms), 256, 0, (cudaStream_t)stream>>>(g, p, a, n, 1.0f / temperature, dz);
+  return check_launch(h, "concrete_backward");
+}
+
+extern "C" int db_cross_entropy_grad(db_handle_t h, db_stream_t stream, const float* probs, const float* targets, int M, int N,
+                                     float scale, float* out) {
+  DB_REQUIRE(h, probs && targets && out && M > 0 && N > 0, "null operand or empty shape");
+  const size_t n = (size_t)M * N;
+  cross_entropy_grad_kernel<<<ew_blocks(n, h->num_sms), 256, 0, (cudaStream_t)stream>>>(probs, targets, n, scale, out);
+  return check_launch(h, "cross_entropy_grad");
+}
+
+extern "C" int db_colsum(db_handle_t h, db_stream_t stream, const float* A, int M, int N, float scale, float beta, float* out) {
+  DB_REQUIRE(h, A && out && M > 0 && N > 0, "null operand or empty shape");
+  colsum_kernel<<<(N + 31) / 32, 256, 0, (cudaStream_t)stream>>>(A, M, N, scale, beta, out);
+  return check_launch(h, "colsum");
+}
+
+extern "C" int db_gpdbn_top_forward_up(db_handle_t h, db_stream_t stream, const float* x, const float* pred_var,
+                                       const float* alpha_h, const float* c, const float* eps1, int N, int D, float* H1,
+                                       float* H1_mean, float* H2) {
+  DB_REQUIRE(h, x && pred_var && alpha_h && c && eps1 && H1 && H1_mean && H2 && N > 0 && D > 0, "null operand or empty shape");
+  top_up_kernel<<<D, 256, 0, (cudaStream_t)stream>>>(x, pred_var, alpha_h, c, eps1, N, D, H1, H1_mean, H2);
+  return check_launch(h, "gpdbn_top_forward_up");
+}
+
+extern "C" int db_gpdbn_top_forward_mid(db_handle_t h, db_stream_t stream, const float* Hm, const float* pred_var,
+                                        const float* alpha_h, const float* H1_mean, const float* eps2, int N, int D, float* H,
+                                        float* y) {
+  DB_REQUIRE(h, Hm && pred_var && alpha_h && H1_mean && eps2 && y && N > 0 && D > 0, "null operand or empty shape");
+  top_mid_kernel<<<ew_blocks((size_t)N * D, h->num_sms), 256, 0, (cudaStream_t)stream>>>(Hm, pred_var, alpha_h, H1_mean, eps2, N,
+                                                                                          D, H, y);
+  return check_launch(h, "gpdbn_top_forward_mid");
+}
+
+extern "C" int db_gpdbn_top_backward1(db_handle_t h, db_stream_t stream, const float* g_y, const float* y, const float* Hm,
+                                      const float* pred_var, const float* alpha_h, const float* eps2, int N, int D, float* g_Hm,
+                                      float* gsig, float* ga, float* gmean) {
+  DB_REQUIRE(h, g_y && y && Hm && pred_var && alpha_h && eps2 && g_Hm && gsig && ga && gmean && N > 0 && D > 0, "null operand");
+  top_back1_kernel<<<D, 256, 0, (cudaStream_t)stream>>>(g_y, y, Hm, pred_var, alpha_h, eps2, N, D, g_Hm, gsig, ga, gmean);
+  return check_launch(h, "gpdbn_top_backward1");
+}
+
+extern "C" int db_gpdbn_top_backward2(db_handle_t h, db_stream_t stream, const float* g_H2, const float* H2, const float* x,
+                                      const float* eps1, const float* pred_var, const float* alpha_h, const float* opt_alpha_h,
+                                      const float* ga, const float* gmean, int N, int D, float* g_x, float* gsig, float* g_c,
+                                      float* g_alpha_scratch, float* g_opt_alpha_h, float* g_pv) {
+  DB_REQUIRE(h, g_H2 && H2 && x && eps1 && pred_var && alpha_h && opt_alpha_h && ga && gmean && g_x && gsig && g_c &&
+                    g_alpha_scratch && g_opt_alpha_h && g_pv && N > 0 && D > 0, "null operand");
+  cudaStream_t st = (cudaStream_t)stream;
+  top_back2_kernel<<<D, 256, 0, st>>>(g_H2, H2, x, eps1, pred_var, alpha_h, ga, gmean, N, D, g_x, gsig, g_c, g_alpha_scratch);
+  top_back3_kernel<<<(N + 7) / 8, 256, 0, st>>>(gsig, pred_var, alpha_h, g_alpha_scratch, opt_alpha_h, N, D, g_pv, g_opt_alpha_h);
+  return check_launch(h, "gpdbn_top_backward2");
+}

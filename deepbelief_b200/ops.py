@@ -252,3 +252,143 @@ def gp_predict(X, Lmat, S, y_mean, xstar, hyp, want_mean=True, want_var=True):
                                L.ptr(info))
     L.check(rc, 'db_gp_predict')
     return mean, var, info
+
+
+# ---- backward building blocks / GPDBN ------------------------------------------------------------------
+def gemm(A, B, trans_a=False, trans_b=False, alpha=1.0, beta=0.0, out=None):
+    """out = alpha * op(A) @ op(B) + beta * out (fp32, db_gemm)."""
+    A = _f32(A)
+    B = _f32(B)
+    M, K = (A.shape[1], A.shape[0]) if trans_a else (A.shape[0], A.shape[1])
+    K2, N = (B.shape[1], B.shape[0]) if trans_b else (B.shape[0], B.shape[1])
+    assert K == K2, 'inner dimensions differ: %s vs %s' % (tuple(A.shape), tuple(B.shape))
+    if out is None:
+        assert beta == 0.0
+        out = torch.empty((M, N), device=A.device, dtype=torch.float32)
+    assert out.is_contiguous() and tuple(out.shape) == (M, N)
+    rc = L.lib().db_gemm(L.handle(), L.stream(), 1 if trans_a else 0, 1 if trans_b else 0, M, N, K, float(alpha),
+                         L.fptr(A), A.shape[1], L.fptr(B), B.shape[1], float(beta), L.fptr(out), N)
+    L.check(rc, 'db_gemm')
+    return out
+
+
+def concrete_backward(g, p, a, temperature):
+    g, p, a = _f32(g), _f32(p), _f32(a)
+    out = torch.empty_like(p)
+    L.check(L.lib().db_concrete_backward(L.handle(), L.stream(), L.fptr(g), L.fptr(p), L.fptr(a), p.shape[0], p.shape[1],
+                                         float(temperature), L.fptr(out)), 'db_concrete_backward')
+    return out
+
+
+def cross_entropy_grad(probs, targets, scale=1.0):
+    probs, targets = _f32(probs), _f32(targets)
+    out = torch.empty_like(probs)
+    L.check(L.lib().db_cross_entropy_grad(L.handle(), L.stream(), L.fptr(probs), L.fptr(targets), probs.shape[0],
+                                          probs.shape[1], float(scale), L.fptr(out)), 'db_cross_entropy_grad')
+    return out
+
+
+def colsum(A, out=None, scale=1.0, beta=0.0):
+    A = _f32(A)
+    if out is None:
+        out = torch.empty(A.shape[1], device=A.device, dtype=torch.float32)
+    L.check(L.lib().db_colsum(L.handle(), L.stream(), L.fptr(A), A.shape[0], A.shape[1], float(scale), float(beta),
+                              L.fptr(out)), 'db_colsum')
+    return out
+
+
+def randn(rows, cols, rng, device='cuda'):
+    """Standard normals [rows, cols] from the layer's Philox stream (Box-Muller, csrc/common.cuh)."""
+    zeros = torch.zeros((rows, cols), device=device, dtype=torch.float32)
+    ones = torch.ones(cols, device=device, dtype=torch.float32)
+    return sample(zeros, L.SAMPLE_GAUSSIAN, noise_scale=ones, rng=rng)
+
+
+class GpdbnPlan:
+    """Workspace owner of the GPDBN GP block at a fixed (N, Q, D): K, L, K^-1, B = K^-1 H2, P = K^-1 g_Hm."""
+
+    def __init__(self, N, Q, D, device='cuda'):
+        self.N, self.Q, self.D = N, Q, D
+        self.workspace = torch.empty(int(L.lib().db_gpdbn_workspace_bytes(N, Q, D)), dtype=torch.uint8, device=device)
+        self.pred_var = torch.zeros(N, dtype=torch.float32, device=device)
+        self.scalars = torch.zeros(8, dtype=torch.float32, device=device)
+        self.info = torch.zeros(2, dtype=torch.int32, device=device)
+        self.dX = torch.zeros((N, Q), dtype=torch.float32, device=device)
+        self.dhyp = torch.zeros(3, dtype=torch.float32, device=device)
+
+    def factor(self, X, hyp_opt, flags, fixed_noise, jitter, L_out=None):
+        rc = L.lib().db_gpdbn_factor(L.handle(), L.stream(), L.fptr(X), self.N, self.Q, self.D, L.fptr(hyp_opt), int(flags),
+                                     float(fixed_noise), float(jitter), L.ptr(self.workspace), L.fptr(self.pred_var),
+                                     L.fptr(L_out), L.ptr(self.info))
+        L.check(rc, 'db_gpdbn_factor')
+        return self.pred_var
+
+    def apply(self, H2, Hm=None):
+        if Hm is None:
+            Hm = torch.empty_like(H2)
+        rc = L.lib().db_gpdbn_apply(L.handle(), L.stream(), L.fptr(H2), self.N, self.Q, self.D, L.ptr(self.workspace),
+                                    L.fptr(Hm), L.fptr(self.scalars))
+        L.check(rc, 'db_gpdbn_apply')
+        return Hm, self.scalars
+
+    def backward_h(self, g_Hm):
+        g_H2 = torch.empty_like(g_Hm)
+        rc = L.lib().db_gpdbn_backward_h(L.handle(), L.stream(), L.fptr(g_Hm), self.N, self.Q, self.D,
+                                         L.ptr(self.workspace), L.fptr(g_H2))
+        L.check(rc, 'db_gpdbn_backward_h')
+        return g_H2
+
+    def backward_x(self, X, g_pv, hyp_opt, flags, x_prior_weight=1.0):
+        rc = L.lib().db_gpdbn_backward_x(L.handle(), L.stream(), L.fptr(X), L.fptr(g_pv), self.N, self.Q, self.D,
+                                         L.fptr(hyp_opt), int(flags), float(x_prior_weight), L.ptr(self.workspace),
+                                         L.fptr(self.dX), L.fptr(self.dhyp))
+        L.check(rc, 'db_gpdbn_backward_x')
+        return self.dX, self.dhyp
+
+
+def gpdbn_top_forward_up(x, pred_var, alpha_h, c, eps1):
+    N, D = x.shape
+    H1 = torch.empty_like(x)
+    H2 = torch.empty_like(x)
+    mean = torch.empty(D, device=x.device, dtype=torch.float32)
+    rc = L.lib().db_gpdbn_top_forward_up(L.handle(), L.stream(), L.fptr(x), L.fptr(pred_var), L.fptr(alpha_h), L.fptr(c),
+                                         L.fptr(eps1), N, D, L.fptr(H1), L.fptr(mean), L.fptr(H2))
+    L.check(rc, 'db_gpdbn_top_forward_up')
+    return H1, mean, H2
+
+
+def gpdbn_top_forward_mid(Hm, pred_var, alpha_h, H1_mean, eps2, want_H=False):
+    N, D = Hm.shape
+    H = torch.empty_like(Hm) if want_H else None
+    y = torch.empty_like(Hm)
+    rc = L.lib().db_gpdbn_top_forward_mid(L.handle(), L.stream(), L.fptr(Hm), L.fptr(pred_var), L.fptr(alpha_h),
+                                          L.fptr(H1_mean), L.fptr(eps2), N, D, L.fptr(H), L.fptr(y))
+    L.check(rc, 'db_gpdbn_top_forward_mid')
+    return H, y
+
+
+def gpdbn_top_backward1(g_y, y, Hm, pred_var, alpha_h, eps2):
+    N, D = g_y.shape
+    g_Hm = torch.empty_like(g_y)
+    gsig = torch.empty_like(g_y)
+    ga = torch.empty(D, device=g_y.device, dtype=torch.float32)
+    gmean = torch.empty(D, device=g_y.device, dtype=torch.float32)
+    rc = L.lib().db_gpdbn_top_backward1(L.handle(), L.stream(), L.fptr(g_y), L.fptr(y), L.fptr(Hm), L.fptr(pred_var),
+                                        L.fptr(alpha_h), L.fptr(eps2), N, D, L.fptr(g_Hm), L.fptr(gsig), L.fptr(ga),
+                                        L.fptr(gmean))
+    L.check(rc, 'db_gpdbn_top_backward1')
+    return g_Hm, gsig, ga, gmean
+
+
+def gpdbn_top_backward2(g_H2, H2, x, eps1, pred_var, alpha_h, opt_alpha_h, ga, gmean, gsig, g_c, g_opt_alpha_h):
+    """Returns (g_x [N,D], g_pv [N]); writes g_c [D] and g_opt_alpha_h [D] in place (views of the packed gradient)."""
+    N, D = g_H2.shape
+    g_x = torch.empty_like(g_H2)
+    g_pv = torch.empty(N, device=g_H2.device, dtype=torch.float32)
+    scratch = torch.empty(D, device=g_H2.device, dtype=torch.float32)
+    rc = L.lib().db_gpdbn_top_backward2(L.handle(), L.stream(), L.fptr(g_H2), L.fptr(H2), L.fptr(x), L.fptr(eps1),
+                                        L.fptr(pred_var), L.fptr(alpha_h), L.fptr(opt_alpha_h), L.fptr(ga), L.fptr(gmean),
+                                        N, D, L.fptr(g_x), L.fptr(gsig), L.fptr(g_c), L.fptr(scratch),
+                                        L.fptr(g_opt_alpha_h), L.fptr(g_pv))
+    L.check(rc, 'db_gpdbn_top_backward2')
+    return g_x, g_pv

@@ -212,6 +212,64 @@ int db_mse(db_handle_t h, db_stream_t stream, const float* a, const float* b, in
 int db_cross_entropy(db_handle_t h, db_stream_t stream, const float* probs, const float* targets, int N, int D,
                      int reduce_mean, float* out);
 
+/* ---- GPDBN top layer (gprbm.py) in training mode (x_ph = X, gprbm.py:106) ---------------------------
+ * One optimisation step of GPRBM.optimize (gprbm.py:375-438) evaluates loss = CE(downprop(sample_mean), V)
+ * + gp_loss (gprbm.py:247-256) and the gradient TF autodiff derives for every trainable. The calls below
+ * are its GP block and top-layer stages; the RBM stack around them uses db_layer_forward / db_gemm /
+ * db_concrete_backward. All share one workspace (db_gpdbn_workspace_bytes). */
+size_t db_gpdbn_workspace_bytes(int N, int Q, int D);
+/* K = K_f(X) + noise I, L = chol K, K^-1, logdet (gprbm.py:108-112, 193-206);
+ * pred_var[i] = noise - noise^2 K^-1_ii  (= gprbm.py:208-218 at x_ph = X).
+ * info (device int[2]): [0] failing Cholesky pivot, [1] first negative pred_var (assert_non_negative), 1-based.
+ * L_out (optional [N,N]) receives the factor for later db_gp_predict calls. */
+int db_gpdbn_factor(db_handle_t h, db_stream_t stream, const float* X, int N, int Q, int D, const float* hyp_opt,
+                    int flags, float fixed_noise, float jitter, void* workspace, float* pred_var, float* L_out,
+                    int* info);
+/* Hm = (L^-1 K_Xx)^T (L^-1 H2) = H2 - noise K^-1 H2 (gprbm.py:220-224); scalars (device, 8 floats):
+ * [gp_loss = 0.5(sum H2 o K^-1 H2 + D logdet) + |X|^2 (gprbm.py:234-245), logdet, sum H2 o K^-1 H2, |X|^2,
+ *  alpha, gamma, noise, 0]. */
+int db_gpdbn_apply(db_handle_t h, db_stream_t stream, const float* H2, int N, int Q, int D, void* workspace,
+                   float* Hm, float* scalars);
+/* g_H2 = dLoss/dH2 given g_Hm = dLoss/dHm (includes the gp_loss term K^-1 H2). */
+int db_gpdbn_backward_h(db_handle_t h, db_stream_t stream, const float* g_Hm, int N, int Q, int D, void* workspace,
+                        float* g_H2);
+/* dX [N,Q] and dhyp[3] = d/d(opt_alpha, opt_gamma, opt_noise) given g_pv = dLoss/dpred_var [N]; must follow
+ * db_gpdbn_backward_h of the same step. x_prior_weight: the |X|^2 term of gprbm.py:242 (1.0). */
+int db_gpdbn_backward_x(db_handle_t h, db_stream_t stream, const float* X, const float* g_pv, int N, int Q, int D,
+                        const float* hyp_opt, int flags, float x_prior_weight, void* workspace, float* dX,
+                        float* dhyp);
+/* H1 = sigma_h (x + eps1) + c, sigma_h = alpha_h sqrt(pred_var) (bgrbm.py:79-82,107-110; gprbm.py:114-115);
+ * H1_mean [D]; H2 = (H1 - H1_mean) / alpha_h (gprbm.py:146-147). x = a W [N,D], eps1 standard normals. */
+int db_gpdbn_top_forward_up(db_handle_t h, db_stream_t stream, const float* x, const float* pred_var,
+                            const float* alpha_h, const float* c, const float* eps1, int N, int D, float* H1,
+                            float* H1_mean, float* H2);
+/* H = Hm alpha_h + H1_mean + sigma_h eps2 (gprbm.py:225-231); y = H / sigma_h (bgrbm.py:126). H may be NULL. */
+int db_gpdbn_top_forward_mid(db_handle_t h, db_stream_t stream, const float* Hm, const float* pred_var,
+                             const float* alpha_h, const float* H1_mean, const float* eps2, int N, int D, float* H,
+                             float* y);
+/* backward of the two stages above: (1) from g_y to g_Hm and partial sums, (2) from g_H2 to g_x, g_c,
+ * g_opt_alpha_h and g_pv. gsig [N,D], ga/gmean/g_alpha_scratch [D] are scratch carried between the calls. */
+int db_gpdbn_top_backward1(db_handle_t h, db_stream_t stream, const float* g_y, const float* y, const float* Hm,
+                           const float* pred_var, const float* alpha_h, const float* eps2, int N, int D, float* g_Hm,
+                           float* gsig, float* ga, float* gmean);
+int db_gpdbn_top_backward2(db_handle_t h, db_stream_t stream, const float* g_H2, const float* H2, const float* x,
+                           const float* eps1, const float* pred_var, const float* alpha_h, const float* opt_alpha_h,
+                           const float* ga, const float* gmean, int N, int D, float* g_x, float* gsig, float* g_c,
+                           float* g_alpha_scratch, float* g_opt_alpha_h, float* g_pv);
+
+/* ---- backward building blocks (what TF autodiff derives from tf.matmul / the Concrete units / dist.py) -- */
+/* C[M,N] = alpha * op(A) op(B) + beta * C, fp32 row-major; op = transpose when the flag is set. */
+int db_gemm(db_handle_t h, db_stream_t stream, int transA, int transB, int M, int N, int K, float alpha,
+            const float* A, int lda, const float* B, int ldb, float beta, float* C, int ldc);
+/* dz = g * d concrete(p,u,T)/dp * p(1-p) with a = the saved Concrete sample (rbm.py:243-275). */
+int db_concrete_backward(db_handle_t h, db_stream_t stream, const float* g, const float* p, const float* a, int M,
+                         int N, float temperature, float* dz);
+/* out = scale * d cross_entropy / d probs (dist.py:24-35; zero where probs was clipped). */
+int db_cross_entropy_grad(db_handle_t h, db_stream_t stream, const float* probs, const float* targets, int M, int N,
+                          float scale, float* out);
+/* out[c] = beta * out[c] + scale * sum_rows A[:,c]  (bias gradients). */
+int db_colsum(db_handle_t h, db_stream_t stream, const float* A, int M, int N, float scale, float beta, float* out);
+
 /* ---- host-side data loader helper (no device work) --------------------------------------------- */
 /* dst[i, :] = src[rows[i], :] for i < n_rows — the batch gather of Data.next_batch (data.py:92-94:
  * `datapoints[sorted_rows]`), multi-threaded, written straight into a (pinned) staging buffer.

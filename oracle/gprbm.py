@@ -140,9 +140,13 @@ class GPDBNOracle:
     def loss(self, draws):
         return float(self.forward(draws)['loss'])
 
-    def grads(self, draws):
+    def grads(self, draws, clip_mask=None):
         """Gradient of `loss` wrt every trainable: returns (state, dict) with keys lower[l].{W,b,c},
-        top.{W,b,c,opt_alpha_h}, X, opt_alpha, opt_gamma, opt_noise."""
+        top.{W,b,c,opt_alpha_h}, X, opt_alpha, opt_gamma, opt_noise.
+        clip_mask (optional bool [N,V]): which elements of V_sample count as strictly inside the clip interval of
+        dist.py:25-26. The mask is a step function of V_sample at 1e-6 / 1 - 1e-6, where fp32 resolves only ~16
+        values per 1e-6: a parity run passes the mask its fp32 evaluation produced (a tie band, like |p - u| for
+        Bernoulli samples) and checks separately that the two masks differ in few elements."""
         st = self.forward(draws)
         dt, T, N, D = self.dt, self.T, self.N, self.D
         X = self.gp['X']
@@ -152,7 +156,9 @@ class GPDBNOracle:
                          for l in self.lower]}
         # cross entropy wrt the clipped sample; clip passes gradient only strictly inside (tf.clip_by_value)
         pc, Vs = st['pc'], st['V_sample']
-        g = (-self.V / pc + (1.0 - self.V) / (1.0 - pc)) * ((Vs >= e0) & (Vs <= 1 - e0))
+        inside = ((Vs >= e0) & (Vs <= 1 - e0)) if clip_mask is None else np.asarray(clip_mask, dtype=bool)
+        st['clip_mask'] = (Vs >= e0) & (Vs <= 1 - e0)
+        g = (-self.V / pc + (1.0 - self.V) / (1.0 - pc)) * inside
         # ---- down pass, lowest layer first ----
         downs = st['downs']
         for i in range(len(self.lower) - 1, -1, -1):

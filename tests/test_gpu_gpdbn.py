@@ -1,0 +1,233 @@
+"""GPDBN stack (two Concrete RBMs + GPRBM top layer) on the GPU against the reference-pinned oracle
+(oracle/gprbm.py, goldens from the reference's own gprbm.py): loss pieces and every gradient array with the same
+injected draws; a short Adam run against the oracle's Adam; the BASELINE config-4 size through properties."""
+import numpy as np
+import pytest
+
+from conftest import Golden, has_cuda
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not has_cuda(), reason='needs a CUDA device')]
+
+import torch  # noqa: E402
+
+from oracle import gprbm as ogprbm, rbm as orbm  # noqa: E402
+from test_oracle_gpdbn import CASES, get_draws, make_oracle  # noqa: E402
+
+GRAD_NORMREL = 2e-4      # fp32 kernels vs fp64 oracle through Concrete units at T = 0.1 (steep sigmoids)
+
+
+@pytest.fixture(scope='module')
+def gpdbn_golden():
+    return Golden('gpdbn_golden.npz')
+
+
+def _np(t):
+    return t.detach().cpu().numpy().astype(np.float64)
+
+
+def _normrel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / (np.max(np.abs(np.asarray(b))) + 1e-300))
+
+
+def build_stack(g, cname):
+    from deepbelief_b200.layers.rbm import RBM
+    from deepbelief_b200.layers.gprbm import GPRBM
+    from deepbelief_b200.layers.gplvm import SEKernel
+    P = {k: g['gpdbn/P/' + k] for k in ('W0', 'b0', 'c0', 'W1', 'b1', 'c1', 'Wt', 'bt', 'ct', 'X')}
+    T = float(g['gpdbn/T'])
+    V = g['gpdbn/V']
+    N, V0 = V.shape
+    Ha, Hb, D = P['W0'].shape[1], P['W1'].shape[1], P['Wt'].shape[1]
+    l0 = RBM(V0, Ha, temperature=T, name='l0', seed=1)
+    l0.set_weights(P['W0'], P['b0'], P['c0'])
+    l1 = RBM(Ha, Hb, temperature=T, bottom=l0, name='l1', seed=2)
+    l1.set_weights(P['W1'], P['b1'], P['c1'])
+    if cname == 'fixed':
+        kern = SEKernel(alpha=False, gamma=False)
+        top = GPRBM(Hb, D, 2, N, False, X0=P['X'], V=V, kern=kern, noise_variance=0.05, fixed_noise_variance=True,
+                    temperature=T, bottom=l1, name='top', seed=3)
+    else:
+        kern = SEKernel(alpha=1.4, gamma=0.9)
+        top = GPRBM(Hb, D, 2, N, False, X0=P['X'], V=V, kern=kern, noise_variance=0.3, fixed_noise_variance=False,
+                    temperature=T, bottom=l1, name='top', seed=3)
+    top.set_weights(P['Wt'], P['bt'], P['ct'])
+    return top, (l0, l1)
+
+
+@pytest.mark.parametrize('cname', list(CASES))
+def test_loss_and_gradients_vs_oracle(gpdbn_golden, cname):
+    g = gpdbn_golden
+    top, (l0, l1) = build_stack(g, cname)
+    draws = get_draws(g)
+    loss, pieces = top.loss_and_grads(draws=draws)
+    st, og = make_oracle(g, cname).grads(draws)
+    np.testing.assert_allclose(_np(pieces['pred_var']), st['pv'], rtol=2e-4)
+    np.testing.assert_allclose(float(pieces['log_det']), st['logdet'], rtol=1e-4)
+    assert _normrel(_np(pieces['H1']), st['H1']) < 1e-4
+    assert _normrel(_np(pieces['Hm']), st['Hm']) < 1e-4
+    assert _normrel(_np(pieces['V_sample']), st['V_sample']) < 1e-3      # Concrete at T = 0.1 amplifies by ~1/T
+    np.testing.assert_allclose(float(pieces['gp_loss']), st['gp_loss'], rtol=1e-4)
+    # the cross entropy of saturated Concrete samples clips at 1 - 1e-6, where fp32 resolves 1 - p to ~6 %: the
+    # reference's own fp32 run (config.float_type) differs from its fp64 run by this much (SURVEY.md §7.3 rule)
+    ref64, ref32 = float(g['gpdbn/%s/float64/loss' % cname]), float(g['gpdbn/%s/float32/loss' % cname])
+    budget = max(2e-4, 2.0 * abs(ref32 - ref64) / abs(ref64))
+    np.testing.assert_allclose(float(loss), st['loss'], rtol=budget)
+    np.testing.assert_allclose(float(loss), ref64, rtol=budget)   # the reference itself
+    G = top._grads
+    for li, lay in enumerate((l0, l1)):
+        gW, gb, gc = top._views(lay, G['lower'][li])
+        assert _normrel(_np(gW), og['lower'][li]['W']) < GRAD_NORMREL, 'W%d' % li
+        assert _normrel(_np(gb), og['lower'][li]['b']) < GRAD_NORMREL, 'b%d' % li
+        assert _normrel(_np(gc), og['lower'][li]['c']) < GRAD_NORMREL, 'c%d' % li
+    gW, gb, gc = top._views(top, G['top'])
+    assert _normrel(_np(gW), og['top']['W']) < GRAD_NORMREL
+    assert _normrel(_np(gb), og['top']['b']) < GRAD_NORMREL
+    assert _normrel(_np(gc), og['top']['c']) < GRAD_NORMREL
+    n = top.num_v * top.num_h + top.num_v + top.num_h
+    assert _normrel(_np(G['top'][n:]), og['top']['opt_alpha_h']) < GRAD_NORMREL
+    assert _normrel(_np(G['X']).reshape(og['X'].shape), og['X']) < GRAD_NORMREL
+    want_h = np.array([float(og['opt_alpha']), float(og['opt_gamma']), float(og['opt_noise'])])
+    if cname == 'trainable':
+        np.testing.assert_allclose(_np(G['hyp']), want_h, rtol=5e-4)
+    else:
+        assert np.all(_np(G['hyp']) == 0)
+    # and against the directional finite differences of the REFERENCE's loss
+    flat = {'W0': top._views(l0, G['lower'][0])[0], 'c1': top._views(l1, G['lower'][1])[2], 'Wt': gW,
+            'X': G['X'].view(top.N, top.Q)}
+    for key, arr in flat.items():
+        d = g['gpdbn/%s/dir/%s' % (cname, key)]
+        fd = float(g['gpdbn/%s/fd/%s' % (cname, key)])
+        assert abs(float(np.sum(_np(arr) * d)) - fd) <= 5e-4 * max(abs(fd), 1.0), key
+
+
+def test_optimize_follows_oracle_adam(gpdbn_golden):
+    """3 Adam iterations with injected draws reproduce the oracle's parameters (same draws every iteration)."""
+    from deepbelief_b200 import compat as tf, ops
+    g = gpdbn_golden
+    top, (l0, l1) = build_stack(g, 'trainable')
+    draws = get_draws(g)
+    opt = tf.train.AdamOptimizer(learning_rate=1e-3)
+    opt.reset()
+    states = {}
+    o = make_oracle(g, 'trainable')
+    adams = {}
+
+    def ostep(key, theta, grad):
+        if key not in adams:
+            adams[key] = orbm.Adam(1e-3)
+        return adams[key].step(theta, grad)
+    for it in range(3):
+        top.loss_and_grads(draws=draws)
+        desc = opt.descriptor()
+        for params, grad, lay in top._trainable_buffers(False):
+            st = states.setdefault(params.data_ptr(), torch.zeros(2 * params.numel(), device='cuda'))
+            ops.optimizer_step(desc, params, grad, st)
+            if lay is not None:
+                lay._weights_version += 1
+        top._touch()
+        _, og = o.grads(draws)
+        for li in range(2):
+            for k in ('W', 'b', 'c'):
+                o.lower[li][k] = ostep(('l', li, k), o.lower[li][k], og['lower'][li][k])
+        for k in ('W', 'b', 'c', 'opt_alpha_h'):
+            o.top[k] = ostep(('t', k), o.top[k], og['top'][k])
+        o.gp['X'] = ostep('X', o.gp['X'], og['X'])
+        for k in ('opt_alpha', 'opt_gamma', 'opt_noise'):
+            o.gp[k] = ostep(k, np.float64(o.gp[k]), np.float64(og[k]))
+    # Adam's first steps are ~ lr * sign(g): compare with an absolute budget of a fraction of the total movement
+    np.testing.assert_allclose(_np(top.X), o.gp['X'], atol=3e-4)
+    np.testing.assert_allclose(_np(l0.W), o.lower[0]['W'], atol=3e-4)
+    np.testing.assert_allclose(_np(top.W), o.top['W'], atol=3e-4)
+    np.testing.assert_allclose(_np(top._hyp), [o.gp['opt_alpha'], o.gp['opt_gamma'], o.gp['opt_noise']], atol=3e-4)
+
+
+def test_optimize_api_and_checkpoint(gpdbn_golden, tmp_path):
+    """GPRBM.optimize with Philox draws: loss falls on average, fixed-X phase leaves X untouched, save/restore."""
+    from deepbelief_b200 import compat as tf
+    g = gpdbn_golden
+    top, _ = build_stack(g, 'fixed')
+    X0 = top.X.clone()
+    l_start = np.mean([float(top.loss_and_grads(want_grads=False)[0]) for _ in range(8)])
+    top.optimize(tf.train.AdamOptimizer(learning_rate=5e-3), num_iterations=10, fixed_X_num_iterations=10)
+    assert torch.equal(top.X, X0)
+    top.optimize(tf.train.AdamOptimizer(learning_rate=5e-3), num_iterations=60, ckpt_interval=60, ckpt_dir=str(tmp_path))
+    assert not torch.equal(top.X, X0)
+    l_end = np.mean([float(top.loss_and_grads(want_grads=False)[0]) for _ in range(8)])
+    assert np.isfinite(l_end) and l_end < l_start
+    other, _ = build_stack(g, 'fixed')
+    other.restore(str(tmp_path / 'top-60'))
+    assert torch.equal(other._params, top._params) and torch.equal(other.X, top.X)
+    # eval-mode style generation from the snapshots
+    img = top.downprop_latent(np.zeros(2, dtype=np.float32), num_samples_to_average=16)
+    assert img.shape == (top.datapoint_len(),) and np.all(np.isfinite(img))
+    assert top.predict_variance(np.zeros((3, 2))).shape == (3, 1)
+
+
+def _config4_stack(N, seed=0):
+    from deepbelief_b200.layers.rbm import RBM
+    from deepbelief_b200.layers.gprbm import GPRBM
+    from deepbelief_b200.layers.gplvm import SEKernel
+    rs = np.random.RandomState(seed)
+    V0, Ha, Hb, D, T = 784, 200, 100, 50, 0.1
+    V = (rs.rand(N, V0) < 0.13).astype(np.float32)
+    X0 = rs.normal(size=(N, 2)).astype(np.float32)
+    np.random.seed(1)
+    l0 = RBM(V0, Ha, W_std=0.05, temperature=T, name='c4l0', seed=11)
+    l1 = RBM(Ha, Hb, W_std=0.05, temperature=T, bottom=l0, name='c4l1', seed=12)
+    top = GPRBM(Hb, D, 2, N, False, X0=X0, V=V, kern=SEKernel(alpha=False, gamma=False), noise_variance=0.01,
+                fixed_noise_variance=True, W_std=0.05, temperature=T, bottom=l1, name='c4top', seed=13)
+    gen = torch.Generator(device='cuda').manual_seed(5)
+    U = lambda r, c: torch.rand(r, c, device='cuda', generator=gen).clamp_(1e-4, 1 - 1e-4)  # noqa: E731
+    draws = {'up': [U(N, Ha), U(N, Hb)], 'eps1': torch.randn(N, D, device='cuda', generator=gen),
+             'eps2': torch.randn(N, D, device='cuda', generator=gen), 'down_top': U(N, Hb), 'down': [U(N, Ha), U(N, V0)]}
+    return top, (l0, l1), V, draws
+
+
+def test_config4_size_properties():
+    """BASELINE config 4 size: synthetic binary 5000x784 (Bernoulli 0.13), stack 784->200->100->GPRBM(50), Q=2, T=0.1,
+    noise 0.01 fixed: pred_var in (0, noise], finite loss and gradients, loss = CE + gp_loss, Philox run works."""
+    N = 5000
+    top, _, V, draws = _config4_stack(N)
+    loss, pieces = top.loss_and_grads(draws=draws)
+    pv = _np(pieces['pred_var'])
+    assert np.all(pv > 0) and np.all(pv <= 0.01 * (1 + 1e-5))
+    assert np.isfinite(float(loss))
+    np.testing.assert_allclose(float(loss), float(pieces['ce']) + float(pieces['gp_loss']), rtol=1e-6)
+    G = top._grads
+    for t in [G['top'], G['X'], G['hyp']] + G['lower']:
+        assert bool(torch.isfinite(t).all())
+    assert float(G['X'].abs().max()) > 0 and float(G['lower'][0].abs().max()) > 0
+    loss2, _ = top.loss_and_grads()              # Philox draws
+    assert np.isfinite(float(loss2))
+
+
+def test_config4_layer_sizes_vs_oracle():
+    """The config-4 layer sizes (784->200->100->50, T=0.1, noise 0.01 fixed: cond(K) ~ 1e4) at N=1200, where the fp64
+    oracle takes seconds: every gradient array against the oracle."""
+    N = 1200
+    top, (l0, l1), V, draws = _config4_stack(N, seed=3)
+    loss, pieces = top.loss_and_grads(draws=draws)
+    cpu = lambda t: t.detach().cpu().numpy().astype(np.float64)  # noqa: E731
+    lower = [dict(W=cpu(l.W), b=cpu(l.b).ravel(), c=cpu(l.c).ravel()) for l in (l0, l1)]
+    topd = dict(W=cpu(top.W), b=cpu(top.b).ravel(), c=cpu(top.c).ravel(), opt_alpha_h=cpu(top.opt_alpha_h).ravel())
+    gp = dict(X=cpu(top.X), opt_alpha=0.0, opt_gamma=0.0, opt_noise=0.0, trainable=(False, False, False), fixed_noise=0.01)
+    o = ogprbm.GPDBNOracle(lower, topd, gp, V, 0.1)
+    nd = {k: ([cpu(a) for a in v] if isinstance(v, list) else cpu(v)) for k, v in draws.items()}
+    vs = pieces['V_sample']
+    mask = ((vs >= 1.0e-6) & (vs <= torch.tensor(1.0, device='cuda') - 1.0e-6)).cpu().numpy()   # the kernel's fp32 mask
+    st, og = o.grads(nd, clip_mask=mask)
+    assert np.mean(mask != st['clip_mask']) < 2e-3        # tie band of the clip step (see oracle.grads)
+    budget = 2e-3            # sigma^2 = 0.01 without jitter: the fp32 K^-1 carries ~cond(K) * eps
+    np.testing.assert_allclose(_np(pieces['pred_var']), st['pv'], rtol=5e-3)
+    np.testing.assert_allclose(float(pieces['gp_loss']), st['gp_loss'], rtol=1e-4)
+    np.testing.assert_allclose(float(loss), st['loss'], rtol=1e-3)
+    G = top._grads
+    for li, lay in enumerate((l0, l1)):
+        gW, gb, gc = top._views(lay, G['lower'][li])
+        assert _normrel(_np(gW), og['lower'][li]['W']) < budget
+        assert _normrel(_np(gb), og['lower'][li]['b']) < budget
+        assert _normrel(_np(gc), og['lower'][li]['c']) < budget
+    gW, gb, gc = top._views(top, G['top'])
+    assert _normrel(_np(gW), og['top']['W']) < budget
+    assert _normrel(_np(gc), og['top']['c']) < budget
+    assert _normrel(_np(G['X']).reshape(og['X'].shape), og['X']) < budget
