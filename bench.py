@@ -288,6 +288,36 @@ def run_b200(args):
     gp_info = int(gplan.info.item())
     gp_flop = float(GP_N) ** 3 + 3.0 * GP_N * GP_N * GP_D
 
+    # ---- GPDBN (BASELINE configs[3]): synthetic binary 5000x784, stack 784->200->100->GPRBM(50), Q=2, T=0.1 ----
+    gpdbn = None
+    if world == 1:
+        del gplan, gX, gY
+        torch.cuda.empty_cache()
+        from deepbelief_b200.layers.gprbm import GPRBM
+        from deepbelief_b200.layers.gplvm import SEKernel
+        rs = np.random.RandomState(0)
+        Vd = (rs.rand(GP_N, GP_D) < 0.13).astype(np.float32)
+        X0 = rs.normal(size=(GP_N, GP_Q)).astype(np.float32)
+        l0 = RBM(GP_D, 200, W_std=0.05, temperature=0.1, name='gpdbn_l0', seed=11, device=dev)
+        l1 = RBM(200, 100, W_std=0.05, temperature=0.1, bottom=l0, name='gpdbn_l1', seed=12, device=dev)
+        top = GPRBM(100, 50, GP_Q, GP_N, False, X0=X0, V=Vd, kern=SEKernel(alpha=False, gamma=False, device=dev),
+                    noise_variance=0.01, fixed_noise_variance=True, W_std=0.05, temperature=0.1, bottom=l1,
+                    name='gpdbn_top', seed=13, device=dev)
+        adam = compat.AdamOptimizer(learning_rate=1e-3)
+        top.optimize(adam, num_iterations=2)
+        torch.cuda.synchronize()
+        n_it = 5
+        t_a = time.perf_counter()
+        e0.record()
+        top.optimize(adam, num_iterations=n_it)
+        e1.record()
+        torch.cuda.synchronize()
+        t_b = time.perf_counter()
+        windows.append((t_a, t_b))
+        gpdbn = {'metric': 'GPDBN train iterations/s (loss + full-stack gradient + Adam)', 'value': n_it * 1e3 / e0.elapsed_time(e1),
+                 'unit': 'iterations/s', 'ms_per_iteration': e0.elapsed_time(e1) / n_it, 'N': GP_N,
+                 'stack': '784-200-100-GPRBM(50), Q=2, T=0.1, noise 0.01 fixed', 'data': 'synthetic Bernoulli(0.13)'}
+
     clocks = None
     if sampler is not None:
         time.sleep(0.15)
@@ -330,6 +360,7 @@ def run_b200(args):
             'gplvm': {'metric': 'GPLVM LML+grad evals/s at N=5000', 'value': world * 1e3 / gp_ms, 'unit': 'evals/s',
                       'ms_per_eval': gp_ms, 'N': GP_N, 'D': GP_D, 'Q': GP_Q, 'info': gp_info, 'scaling': 'replicas only',
                       'algorithmic_tflops': gp_flop / (gp_ms * 1e-3) / 1e12},
+            'gpdbn': gpdbn,
         }
         print(json.dumps(line))
     if world > 1:

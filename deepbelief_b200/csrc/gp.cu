@@ -94,109 +94,125 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, 
 }
 
 // ---- K4: Cholesky ---------------------------------------------------------------------------------
-// factorise the nb x nb block held in shared memory (row-major, pitch NB+1); returns failing column+1 or 0
-__device__ int potrf_block_smem(float (*D)[NB + 1], int nb) {
+// Two-level right-looking factorisation. Column blocks are NB = 64 wide; OB = 512 columns form an outer
+// block. Per column block ONE launch (potrf_colblock_kernel) factorises the 64x64 diagonal block and solves the
+// panel below it; a narrow SYRK then updates only the remaining columns of the outer block (K = 64), and once
+// per outer block a wide SYRK (K = 512) updates the rest of the matrix — so the strictly sequential part is
+// ~80 short launches and the bulk of the N^3/3 flops runs as deep-K GEMM tiles.
+constexpr int OB = 512;
+constexpr int LT_PITCH = 68;   // floats; rows 16-byte aligned for float4 broadcast reads
+
+// s = v[c] - sum_{k<c} v[k] * Lrow[k]   (v in registers, Lrow = row c of the factor in shared memory)
+template <int C>
+__device__ __forceinline__ float potrf_dot(const float (&v)[NB], const float* __restrict__ Lrow) {
+  float s0 = v[C], s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+  for (int k = 0; k + 3 < C; k += 4) {
+    const float4 l = *reinterpret_cast<const float4*>(Lrow + k);
+    s0 = fmaf(-v[k], l.x, s0); s1 = fmaf(-v[k + 1], l.y, s1); s2 = fmaf(-v[k + 2], l.z, s2); s3 = fmaf(-v[k + 3], l.w, s3);
+  }
+#pragma unroll
+  for (int k = (C / 4) * 4; k < C; ++k) s1 = fmaf(-v[k], Lrow[k], s1);
+  return (s0 + s1) + (s2 + s3);
+}
+
+template <int C>
+struct PotrfCols {
+  // columns 0..C-1 already done; thread r owns matrix row r of the diagonal block in v[]
+  static __device__ __forceinline__ void factor(float (&v)[NB], float (*Lt)[LT_PITCH], float* dinv, int* fail, int r) {
+    PotrfCols<C - 1>::factor(v, Lt, dinv, fail, r);
+    constexpr int c = C - 1;
+    float s = 0.0f;
+    if (r >= c) s = potrf_dot<c>(v, Lt[c]);
+    if (r == c) {
+      if (!(s > 0.0f) && *fail == 0) *fail = c + 1;
+      const float d = sqrtf(s);
+      Lt[c][c] = d;
+      dinv[c] = 1.0f / d;
+      v[c] = d;
+    }
+    __syncthreads();
+    if (r > c) { v[c] = s * dinv[c]; Lt[r][c] = v[c]; }
+    __syncthreads();
+  }
+  // forward substitution of one panel row against the finished factor: x L^T = v
+  static __device__ __forceinline__ void solve(float (&v)[NB], float (*Lt)[LT_PITCH], const float* dinv) {
+    PotrfCols<C - 1>::solve(v, Lt, dinv);
+    constexpr int c = C - 1;
+    v[c] = potrf_dot<c>(v, Lt[c]) * dinv[c];
+  }
+};
+template <>
+struct PotrfCols<0> {
+  static __device__ __forceinline__ void factor(float (&)[NB], float (*)[LT_PITCH], float*, int*, int) {}
+  static __device__ __forceinline__ void solve(float (&)[NB], float (*)[LT_PITCH], const float*) {}
+};
+
+// grid.x = number of 64-row blocks from row j down; block 0 is the diagonal block. 64 threads, one matrix row each.
+// Every CTA factorises the diagonal block itself (identical arithmetic, ~7 us) instead of waiting for another launch.
+__global__ void __launch_bounds__(NB) potrf_colblock_kernel(float* __restrict__ A, int lda, int N, int j, int* __restrict__ info) {
+  __shared__ __align__(16) float Lt[NB][LT_PITCH];
+  __shared__ float dinv[NB];
   __shared__ int s_fail;
-  if (threadIdx.x == 0) s_fail = 0;
-  __syncthreads();
-  for (int c = 0; c < nb; ++c) {
-    if (threadIdx.x == 0) {
-      const float d = D[c][c];
-      if (!(d > 0.0f) && s_fail == 0) s_fail = c + 1;
-      D[c][c] = sqrtf(d);
-    }
-    __syncthreads();
-    const float inv = 1.0f / D[c][c];
-    for (int r = c + 1 + threadIdx.x; r < nb; r += blockDim.x) D[r][c] *= inv;
-    __syncthreads();
-    // trailing update of the lower triangle: D[r][cc] -= D[r][c] * D[cc][c], c < cc <= r
-    const int rem = nb - c - 1;
-    for (int t = threadIdx.x; t < rem * rem; t += blockDim.x) {
-      const int r = c + 1 + t / rem, cc = c + 1 + t % rem;
-      if (cc <= r) D[r][cc] = fmaf(-D[r][c], D[cc][c], D[r][cc]);
-    }
-    __syncthreads();
+  const int r = threadIdx.x;
+  const int nb = min(NB, N - j);
+  float v[NB];
+  {
+    const float* src = A + (size_t)(j + r) * lda + j;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) v[k] = (r < nb && k <= r) ? src[k] : (k == r ? 1.0f : 0.0f);   // identity padding
   }
-  return s_fail;
+  if (r == 0) s_fail = 0;
+  __syncthreads();
+  PotrfCols<NB>::factor(v, Lt, dinv, &s_fail, r);
+  if (blockIdx.x == 0) {
+    if (r < nb) {
+      float* dst = A + (size_t)(j + r) * lda + j;
+#pragma unroll
+      for (int k = 0; k < NB; ++k) if (k <= r) dst[k] = v[k];
+    }
+    if (r == 0 && s_fail && s_fail <= nb) atomicCAS(info, 0, j + s_fail);
+    return;
+  }
+  const int row = j + blockIdx.x * NB + r;
+  if (row >= N) return;
+  float* src = A + (size_t)row * lda + j;
+#pragma unroll
+  for (int k = 0; k < NB; ++k) v[k] = k < nb ? src[k] : 0.0f;
+  PotrfCols<NB>::solve(v, Lt, dinv);
+#pragma unroll
+  for (int k = 0; k < NB; ++k) if (k < nb) src[k] = v[k];
 }
 
-// Panel step j, kernel 1: factorise the diagonal block (one CTA).
-__global__ void __launch_bounds__(256) potrf_diag_kernel(float* __restrict__ A, int lda, int N, int j, int* __restrict__ info) {
-  __shared__ float D[NB][NB + 1];
-  const int nb = min(NB, N - j);
-  for (int t = threadIdx.x; t < NB * NB; t += 256) {
-    const int r = t / NB, c = t % NB;
-    D[r][c] = (r < nb && c <= r) ? A[(size_t)(j + r) * lda + j + c] : 0.0f;
-  }
-  __syncthreads();
-  const int fail = potrf_block_smem(D, nb);
-  for (int t = threadIdx.x; t < NB * NB; t += 256) {
-    const int r = t / NB, c = t % NB;
-    if (r < nb && c <= r) A[(size_t)(j + r) * lda + j + c] = D[r][c];
-  }
-  if (threadIdx.x == 0 && fail) atomicCAS(info, 0, j + fail);
-}
-// Panel step j, kernel 2: CTA b solves its 64 rows of the panel against the factorised block (X L^T = R).
-__global__ void __launch_bounds__(256) potrf_panel_kernel(float* __restrict__ A, int lda, int N, int j) {
-  __shared__ float D[NB][NB + 1];
-  __shared__ float R[NB][NB + 1];
-  const int nb = min(NB, N - j);
-  const int r0 = j + NB + blockIdx.x * NB;
-  const int nr = min(NB, N - r0);
-  for (int t = threadIdx.x; t < NB * NB; t += 256) {
-    const int r = t / NB, c = t % NB;
-    D[r][c] = (r < nb && c <= r) ? A[(size_t)(j + r) * lda + j + c] : 0.0f;
-    R[r][c] = (r < nr && c < nb) ? A[(size_t)(r0 + r) * lda + j + c] : 0.0f;
-  }
-  __syncthreads();
-  for (int c = 0; c < nb; ++c) {
-    const float inv = 1.0f / D[c][c];
-    for (int r = threadIdx.x; r < nr; r += 256) R[r][c] *= inv;
-    __syncthreads();
-    const int rem = nb - c - 1;
-    for (int t = threadIdx.x; t < nr * rem; t += 256) {
-      const int r = t / rem, cc = c + 1 + t % rem;
-      R[r][cc] = fmaf(-R[r][c], D[cc][c], R[r][cc]);
-    }
-    __syncthreads();
-  }
-  for (int t = threadIdx.x; t < NB * NB; t += 256) {
-    const int r = t / NB, c = t % NB;
-    if (r < nr && c < nb) A[(size_t)(r0 + r) * lda + j + c] = R[r][c];
-  }
-}
-
-// trailing update: C = A[j2:, j2:] (lower) -= P P^T with P = A[j2:, j:j+NB], j2 = j + NB
-struct LoadPanelA {
+// C[i, jc] -= sum_{k in [k0,k1)} A[i,k] A[jc,k]  for i in [i0,N), jc in [j0,j1), jc <= i   (lower part only)
+struct LoadSyrkA {
   static constexpr bool k_contig = true;
-  const float* P; int lda; int rows;
-  __device__ __forceinline__ float operator()(int m, int k) const { return m < rows ? __ldg(P + (size_t)m * lda + k) : 0.0f; }
+  const float* P; int lda; int rows, kk;
+  __device__ __forceinline__ float operator()(int m, int k) const { return (m < rows && k < kk) ? __ldg(P + (size_t)m * lda + k) : 0.0f; }
 };
-struct LoadPanelB {
+struct LoadSyrkB {
   static constexpr bool k_contig = true;
-  const float* P; int lda; int rows;
-  __device__ __forceinline__ float operator()(int k, int n) const { return n < rows ? __ldg(P + (size_t)n * lda + k) : 0.0f; }
+  const float* P; int lda; int rows, kk;
+  __device__ __forceinline__ float operator()(int k, int n) const { return (n < rows && k < kk) ? __ldg(P + (size_t)n * lda + k) : 0.0f; }
 };
-__global__ void __launch_bounds__(256) syrk_update_kernel(float* __restrict__ A, int lda, int N, int j) {
+__global__ void __launch_bounds__(256) syrk_block_kernel(float* __restrict__ A, int lda, int N, int i0, int j0, int j1, int k0,
+                                                         int k1) {
   using T = TileLarge;
-  if (blockIdx.x > blockIdx.y) return;          // lower tile pairs only
-  __shared__ typename T::Smem sm;
-  const int j2 = j + NB;
-  const int rows = N - j2;
   const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
-  const float* P = A + (size_t)j2 * lda + j;
-  LoadPanelA a{P, lda, rows};
-  LoadPanelB b{P, lda, rows};
+  if (j0 + n0 > i0 + m0 + T::BM - 1) return;            // tile entirely above the diagonal
+  __shared__ typename T::Smem sm;
+  LoadSyrkA a{A + (size_t)i0 * lda + k0, lda, N - i0, k1 - k0};
+  LoadSyrkB b{A + (size_t)j0 * lda + k0, lda, j1 - j0, k1 - k0};
   float acc[T::TM][T::TN];
-  simt_gemm_tile<T>(sm, a, b, m0, n0, 0, NB, acc);
+  simt_gemm_tile<T>(sm, a, b, m0, n0, 0, k1 - k0, acc);
 #pragma unroll
   for (int i = 0; i < T::TM; ++i) {
-    const int m = simt_row<T>(m0, i);
-    if (m >= rows) continue;
+    const int row = i0 + simt_row<T>(m0, i);
+    if (row >= N) continue;
 #pragma unroll
     for (int jj = 0; jj < T::TN; ++jj) {
-      const int n = simt_col<T>(n0, jj);
-      if (n <= m) A[(size_t)(j2 + m) * lda + j2 + n] -= acc[i][jj];
+      const int col = j0 + simt_col<T>(n0, jj);
+      if (col < j1 && col <= row) A[(size_t)row * lda + col] -= acc[i][jj];
     }
   }
 }
@@ -571,13 +587,19 @@ int run_gram(db_handle_t h, cudaStream_t st, const float* X, const float* Y, int
 
 int run_potrf(db_handle_t h, cudaStream_t st, float* A, int lda, int N, int* info) {
   cudaMemsetAsync(info, 0, sizeof(int), st);
-  for (int j = 0; j < N; j += NB) {
-    const int below = N - j - NB;
-    potrf_diag_kernel<<<1, 256, 0, st>>>(A, lda, N, j, info);
-    if (below > 0) {
-      potrf_panel_kernel<<<(below + NB - 1) / NB, 256, 0, st>>>(A, lda, N, j);
-      const int tiles = (below + TileLarge::BM - 1) / TileLarge::BM;
-      syrk_update_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(A, lda, N, j);
+  for (int b0 = 0; b0 < N; b0 += OB) {
+    const int b1 = b0 + OB < N ? b0 + OB : N;
+    for (int j = b0; j < b1; j += NB) {
+      potrf_colblock_kernel<<<(N - j + NB - 1) / NB, NB, 0, st>>>(A, lda, N, j, info);
+      const int j2 = j + NB;
+      if (j2 < b1) {     // narrow update: remaining columns of this outer block, all rows below
+        dim3 grid((b1 - j2 + TileLarge::BN - 1) / TileLarge::BN, (N - j2 + TileLarge::BM - 1) / TileLarge::BM);
+        syrk_block_kernel<<<grid, 256, 0, st>>>(A, lda, N, j2, j2, b1, j, j2);
+      }
+    }
+    if (b1 < N) {        // wide update of everything right of the outer block, K = b1 - b0
+      const int t = (N - b1 + TileLarge::BM - 1) / TileLarge::BM;
+      syrk_block_kernel<<<dim3(t, t), 256, 0, st>>>(A, lda, N, b1, b1, N, b0, b1);
     }
   }
   return check_launch(h, "potrf_lower");

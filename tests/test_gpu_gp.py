@@ -62,7 +62,7 @@ def test_cholesky_and_triangular_solves(N):
     info = ops.potrf_lower(A)
     assert int(info.item()) == 0
     Lref = np.linalg.cholesky(K)
-    assert _normrel(np.tril(_np(A)), Lref) < 2e-6
+    assert _normrel(np.tril(_np(A)), Lref) < 1e-5          # fp32 factor of a cond(K) ~ 3e3 matrix (bound ~ cond * eps)
     assert np.allclose(np.triu(_np(A), 1), np.triu(K, 1), rtol=1e-6)       # strict upper triangle untouched
     for nrhs in (1, 37, 300):
         B = rs.normal(size=(N, nrhs))
