@@ -102,86 +102,93 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, 
 constexpr int OB = 512;
 constexpr int LT_PITCH = 68;   // floats; rows 16-byte aligned for float4 broadcast reads
 
-// s = v[c] - sum_{k<c} v[k] * Lrow[k]   (v in registers, Lrow = row c of the factor in shared memory)
-template <int C>
-__device__ __forceinline__ float potrf_dot(const float (&v)[NB], const float* __restrict__ Lrow) {
-  float s0 = v[C], s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+// Shared-memory layout of a 64x64 block: S[c][r] holds element (row r, column c), so "my row's element c" is
+// lane-contiguous (thread r reads S[c][r]) and "row c2's element c" (S[c][c2]) is a broadcast; 8 consecutive
+// columns of one row of L^T, S[k][c0..c0+7], are two aligned float4.
+// Left-looking in chunks of 8 columns: the rank-c0 update of a chunk is a k-loop of 8 FMAs per 3 shared loads,
+// only the 8x8 triangular part of each chunk is unrolled (small code: the whole factorisation stays in the
+// instruction cache, unlike a fully unrolled 64-column version).
+
+// acc[i] = Own[c0+i][r] - sum_{k<c0} Own[k][r] * S[k][c0+i]     (Own == S for the diagonal block)
+__device__ __forceinline__ void chunk_update(float (&acc)[8], const float (*Own)[LT_PITCH], const float (*S)[LT_PITCH], int c0,
+                                             int r) {
 #pragma unroll
-  for (int k = 0; k + 3 < C; k += 4) {
-    const float4 l = *reinterpret_cast<const float4*>(Lrow + k);
-    s0 = fmaf(-v[k], l.x, s0); s1 = fmaf(-v[k + 1], l.y, s1); s2 = fmaf(-v[k + 2], l.z, s2); s3 = fmaf(-v[k + 3], l.w, s3);
+  for (int i = 0; i < 8; ++i) acc[i] = Own[c0 + i][r];
+#pragma unroll 4
+  for (int k = 0; k < c0; ++k) {
+    const float x = Own[k][r];
+    const float4 l0 = *reinterpret_cast<const float4*>(&S[k][c0]);
+    const float4 l1 = *reinterpret_cast<const float4*>(&S[k][c0 + 4]);
+    acc[0] = fmaf(-x, l0.x, acc[0]); acc[1] = fmaf(-x, l0.y, acc[1]); acc[2] = fmaf(-x, l0.z, acc[2]); acc[3] = fmaf(-x, l0.w, acc[3]);
+    acc[4] = fmaf(-x, l1.x, acc[4]); acc[5] = fmaf(-x, l1.y, acc[5]); acc[6] = fmaf(-x, l1.z, acc[6]); acc[7] = fmaf(-x, l1.w, acc[7]);
   }
-#pragma unroll
-  for (int k = (C / 4) * 4; k < C; ++k) s1 = fmaf(-v[k], Lrow[k], s1);
-  return (s0 + s1) + (s2 + s3);
 }
 
-template <int C>
-struct PotrfCols {
-  // columns 0..C-1 already done; thread r owns matrix row r of the diagonal block in v[]
-  static __device__ __forceinline__ void factor(float (&v)[NB], float (*Lt)[LT_PITCH], float* dinv, int* fail, int r) {
-    PotrfCols<C - 1>::factor(v, Lt, dinv, fail, r);
-    constexpr int c = C - 1;
-    float s = 0.0f;
-    if (r >= c) s = potrf_dot<c>(v, Lt[c]);
-    if (r == c) {
-      if (!(s > 0.0f) && *fail == 0) *fail = c + 1;
-      const float d = sqrtf(s);
-      Lt[c][c] = d;
-      dinv[c] = 1.0f / d;
-      v[c] = d;
-    }
-    __syncthreads();
-    if (r > c) { v[c] = s * dinv[c]; Lt[r][c] = v[c]; }
-    __syncthreads();
-  }
-  // forward substitution of one panel row against the finished factor: x L^T = v
-  static __device__ __forceinline__ void solve(float (&v)[NB], float (*Lt)[LT_PITCH], const float* dinv) {
-    PotrfCols<C - 1>::solve(v, Lt, dinv);
-    constexpr int c = C - 1;
-    v[c] = potrf_dot<c>(v, Lt[c]) * dinv[c];
-  }
-};
-template <>
-struct PotrfCols<0> {
-  static __device__ __forceinline__ void factor(float (&)[NB], float (*)[LT_PITCH], float*, int*, int) {}
-  static __device__ __forceinline__ void solve(float (&)[NB], float (*)[LT_PITCH], const float*) {}
-};
-
 // grid.x = number of 64-row blocks from row j down; block 0 is the diagonal block. 64 threads, one matrix row each.
-// Every CTA factorises the diagonal block itself (identical arithmetic, ~7 us) instead of waiting for another launch.
+// Every CTA factorises the diagonal block itself (identical arithmetic) instead of waiting for another launch.
 __global__ void __launch_bounds__(NB) potrf_colblock_kernel(float* __restrict__ A, int lda, int N, int j, int* __restrict__ info) {
-  __shared__ __align__(16) float Lt[NB][LT_PITCH];
+  __shared__ __align__(16) float S[NB][LT_PITCH];   // diagonal block: A on entry, L on exit (lower part)
+  __shared__ __align__(16) float P[NB][LT_PITCH];   // this CTA's panel rows (blockIdx.x > 0)
   __shared__ float dinv[NB];
   __shared__ int s_fail;
   const int r = threadIdx.x;
   const int nb = min(NB, N - j);
-  float v[NB];
   {
     const float* src = A + (size_t)(j + r) * lda + j;
-#pragma unroll
-    for (int k = 0; k < NB; ++k) v[k] = (r < nb && k <= r) ? src[k] : (k == r ? 1.0f : 0.0f);   // identity padding
+    for (int k = 0; k < NB; ++k) S[k][r] = (r < nb && k <= r) ? __ldg(src + k) : (k == r ? 1.0f : 0.0f);   // identity padding
+  }
+  const int prow = j + blockIdx.x * NB + r;
+  if (blockIdx.x > 0) {
+    const float* src = A + (size_t)prow * lda + j;
+    for (int k = 0; k < NB; ++k) P[k][r] = (prow < N && k < nb) ? __ldg(src + k) : 0.0f;
   }
   if (r == 0) s_fail = 0;
   __syncthreads();
-  PotrfCols<NB>::factor(v, Lt, dinv, &s_fail, r);
+  for (int c0 = 0; c0 < NB; c0 += 8) {
+    float acc[8];
+    chunk_update(acc, S, S, c0, r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i;
+      float s = acc[i];
+#pragma unroll
+      for (int m = 0; m < i; ++m) s = fmaf(-acc[m], S[c0 + m][c], s);    // acc[m] already holds L[r][c0+m]
+      if (r == c) {
+        if (!(s > 0.0f) && s_fail == 0) s_fail = c + 1;
+        const float d = sqrtf(s);
+        S[c][c] = d;
+        dinv[c] = 1.0f / d;
+      }
+      __syncthreads();
+      if (r > c) { acc[i] = s * dinv[c]; S[c][r] = acc[i]; }
+      __syncthreads();
+    }
+  }
   if (blockIdx.x == 0) {
     if (r < nb) {
       float* dst = A + (size_t)(j + r) * lda + j;
-#pragma unroll
-      for (int k = 0; k < NB; ++k) if (k <= r) dst[k] = v[k];
+      for (int k = 0; k <= r; ++k) dst[k] = S[k][r];
     }
     if (r == 0 && s_fail && s_fail <= nb) atomicCAS(info, 0, j + s_fail);
     return;
   }
-  const int row = j + blockIdx.x * NB + r;
-  if (row >= N) return;
-  float* src = A + (size_t)row * lda + j;
+  // panel rows: x L^T = a by forward substitution, same chunking, no synchronisation needed
+  for (int c0 = 0; c0 < NB; c0 += 8) {
+    float acc[8];
+    chunk_update(acc, P, S, c0, r);
 #pragma unroll
-  for (int k = 0; k < NB; ++k) v[k] = k < nb ? src[k] : 0.0f;
-  PotrfCols<NB>::solve(v, Lt, dinv);
+    for (int i = 0; i < 8; ++i) {
+      float s = acc[i];
 #pragma unroll
-  for (int k = 0; k < NB; ++k) if (k < nb) src[k] = v[k];
+      for (int m = 0; m < i; ++m) s = fmaf(-acc[m], S[c0 + m][c0 + i], s);
+      acc[i] = s * dinv[c0 + i];
+      P[c0 + i][r] = acc[i];
+    }
+  }
+  if (prow < N) {
+    float* dst = A + (size_t)prow * lda + j;
+    for (int k = 0; k < nb; ++k) dst[k] = P[k][r];
+  }
 }
 
 // C[i, jc] -= sum_{k in [k0,k1)} A[i,k] A[jc,k]  for i in [i0,N), jc in [j0,j1), jc <= i   (lower part only)
@@ -371,7 +378,9 @@ __global__ void __launch_bounds__(256) trmm_kernel(const float* __restrict__ Li,
                                                    int nrhs, float* __restrict__ out, int ldo, float* __restrict__ ssq) {
   __shared__ typename T::Smem sm;
   __shared__ float red[8];
-  const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
+  // the k range grows with the row block (TRANS=0): launch the long tiles first so they do not form the tail
+  const int by = TRANS ? blockIdx.y : gridDim.y - 1 - blockIdx.y;
+  const int m0 = by * T::BM, n0 = blockIdx.x * T::BN;
   LoadLinvA<TRANS> a{Li, ldi, N};
   LoadMatB b{B, ldb, N, nrhs};
   float acc[T::TM][T::TN];
