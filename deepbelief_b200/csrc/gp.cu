@@ -327,10 +327,9 @@ struct LoadMatB {     // element (k,n) of a row-major sub-matrix
   const float* P; int ld; int rows, cols;
   __device__ __forceinline__ float operator()(int k, int n) const { return (k < rows && n < cols) ? __ldg(P + (size_t)k * ld + n) : 0.0f; }
 };
-template <int STEP>
+template <int STEP, class T>
 __global__ void __launch_bounds__(256) trinv_level_kernel(const float* __restrict__ L, int ldl, int N, int s, float* __restrict__ Li,
                                                           int ldi, float* __restrict__ Tmp, int ldt) {
-  using T = TileSmall;
   __shared__ typename T::Smem sm;
   const int p = blockIdx.z;
   const int c0 = 2 * p * s, r0 = c0 + s;
@@ -459,6 +458,63 @@ __device__ __forceinline__ void gp_contract_tile(float (&gacc)[T::TM][T::TN], in
                                                  float (*colacc)[MAXQ], float (*red)[8]) {
   const float alpha = __ldg(hyp), inv_g2 = 1.0f / (__ldg(hyp + 1) * __ldg(hyp + 1));
   float trg = 0.0f, sw = 0.0f, swr = 0.0f;
+  if (Q <= 2) {
+    // fast path (every example uses Q = 2): per-thread row / column partial sums in registers, reduced with
+    // shuffles over the 16 threads that share a row, shared-memory atomics only once per warp and column
+    constexpr int QF = 2;
+    float racc[T::TM][QF], cacc[T::TN][QF];
+#pragma unroll
+    for (int i = 0; i < T::TM; ++i) { racc[i][0] = racc[i][1] = 0.0f; }
+#pragma unroll
+    for (int jj = 0; jj < T::TN; ++jj) { cacc[jj][0] = cacc[jj][1] = 0.0f; }
+    float xn[T::TN][QF];
+#pragma unroll
+    for (int jj = 0; jj < T::TN; ++jj) {
+      const int n = simt_col<T>(n0, jj);
+      xn[jj][0] = n < N ? __ldg(X + (size_t)n * Q) : 0.0f;
+      xn[jj][1] = (n < N && Q > 1) ? __ldg(X + (size_t)n * Q + 1) : 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < T::TM; ++i) {
+      const int m = simt_row<T>(m0, i);
+      const float xm0 = m < N ? __ldg(X + (size_t)m * Q) : 0.0f;
+      const float xm1 = (m < N && Q > 1) ? __ldg(X + (size_t)m * Q + 1) : 0.0f;
+#pragma unroll
+      for (int jj = 0; jj < T::TN; ++jj) {
+        const int n = simt_col<T>(n0, jj);
+        if (m >= N || n >= N || (diag_tile && n > m)) continue;
+        const float g = gacc[i][jj];
+        if (m == n) { trg += g; sw += g * alpha; continue; }
+        const float d0 = xm0 - xn[jj][0], d1 = xm1 - xn[jj][1];
+        const float r2 = fmaf(d0, d0, d1 * d1);
+        const float w = g * alpha * __expf(-0.5f * r2 * inv_g2);
+        sw += 2.0f * w; swr += 2.0f * w * r2;
+        racc[i][0] = fmaf(w, d0, racc[i][0]); racc[i][1] = fmaf(w, d1, racc[i][1]);
+        cacc[jj][0] = fmaf(-w, d0, cacc[jj][0]); cacc[jj][1] = fmaf(-w, d1, cacc[jj][1]);
+      }
+    }
+    const int tx = threadIdx.x % (T::BN / T::TN), lane = threadIdx.x & 31;
+    static_assert(T::BN / T::TN == 16, "row reduction assumes 16 threads per tile row");
+#pragma unroll
+    for (int i = 0; i < T::TM; ++i) {
+#pragma unroll
+      for (int q = 0; q < QF; ++q) {
+        float v = racc[i][q];
+        v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8);
+        if (tx == 0 && q < Q) rowacc[simt_row<T>(0, i)][q] = v;        // rows are owned by one 16-thread group
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < T::TN; ++jj) {
+#pragma unroll
+      for (int q = 0; q < QF; ++q) {
+        float v = cacc[jj][q];
+        v += __shfl_xor_sync(0xffffffffu, v, 16);                       // the two tile rows held by this warp
+        if (lane < 16 && q < Q) atomicAdd(&colacc[simt_col<T>(0, jj)][q], v);
+      }
+    }
+  } else {
 #pragma unroll
   for (int i = 0; i < T::TM; ++i) {
     const int m = simt_row<T>(m0, i);
@@ -480,6 +536,7 @@ __device__ __forceinline__ void gp_contract_tile(float (&gacc)[T::TM][T::TN], in
         atomicAdd(&colacc[n - n0][q], -w * df[q]);
       }
     }
+  }
   }
   __syncthreads();
   // dX_i = -(2/gamma^2) sum_j W_ij (x_i - x_j); each unordered pair was visited once -> both rows updated
@@ -620,9 +677,15 @@ int run_trinv(db_handle_t h, cudaStream_t st, const float* L, int ldl, int N, fl
   trinv_diag_kernel<<<nblk, 64, 0, st>>>(L, ldl, N, Li, N);
   for (int s = NB; s < N; s *= 2) {
     const int pairs = (N + 2 * s - 1) / (2 * s);
-    dim3 grid((s + TileSmall::BN - 1) / TileSmall::BN, (s + TileSmall::BM - 1) / TileSmall::BM, pairs);
-    trinv_level_kernel<0><<<grid, 256, 0, st>>>(L, ldl, N, s, Li, N, Tmp, N);
-    trinv_level_kernel<1><<<grid, 256, 0, st>>>(L, ldl, N, s, Li, N, Tmp, N);
+    if (false && s >= 1024) {  // measured: the large tile gives too few CTAs at these level sizes (slower)
+      dim3 grid((s + TileLarge::BN - 1) / TileLarge::BN, (s + TileLarge::BM - 1) / TileLarge::BM, pairs);
+      trinv_level_kernel<0, TileLarge><<<grid, 256, 0, st>>>(L, ldl, N, s, Li, N, Tmp, N);
+      trinv_level_kernel<1, TileLarge><<<grid, 256, 0, st>>>(L, ldl, N, s, Li, N, Tmp, N);
+    } else {
+      dim3 grid((s + TileSmall::BN - 1) / TileSmall::BN, (s + TileSmall::BM - 1) / TileSmall::BM, pairs);
+      trinv_level_kernel<0, TileSmall><<<grid, 256, 0, st>>>(L, ldl, N, s, Li, N, Tmp, N);
+      trinv_level_kernel<1, TileSmall><<<grid, 256, 0, st>>>(L, ldl, N, s, Li, N, Tmp, N);
+    }
   }
   return check_launch(h, "trinv_lower");
 }

@@ -217,18 +217,31 @@ def test_config4_layer_sizes_vs_oracle():
     mask = ((vs >= 1.0e-6) & (vs <= torch.tensor(1.0, device='cuda') - 1.0e-6)).cpu().numpy()   # the kernel's fp32 mask
     st, og = o.grads(nd, clip_mask=mask)
     assert np.mean(mask != st['clip_mask']) < 2e-3        # tie band of the clip step (see oracle.grads)
-    budget = 2e-3            # sigma^2 = 0.01 without jitter: the fp32 K^-1 carries ~cond(K) * eps
-    # pred_var = s - s^2 K^-1_ii cancels ~60x at s = 0.01 (values ~1.6e-4): absolute budget 3e-4 * s
-    np.testing.assert_allclose(_np(pieces['pred_var']), st['pv'], rtol=5e-3, atol=3e-6)
+    # sigma^2 = 0.01 without jitter: cond(K) ~ 1e5 at N = 1200, so fp32 carries ~cond * eps. The budget per array is
+    # max(2e-3, 2 x the error of the reference's own formulas evaluated in fp32) — SURVEY.md §7.3 rule
+    o32 = ogprbm.GPDBNOracle(lower, topd, gp, V, 0.1, dtype=np.float32)
+    try:
+        _, og32 = o32.grads(nd, clip_mask=mask)
+    except FloatingPointError:          # the fp32 reference formula may trip its own assert_non_negative here
+        og32 = None
+
+    def budget(got64, key_path):
+        if og32 is None:
+            return 5e-3
+        ref32 = og32
+        for k in key_path:
+            ref32 = ref32[k]
+        return max(2e-3, 2.0 * _normrel(np.asarray(ref32, dtype=np.float64), got64))
+    np.testing.assert_allclose(_np(pieces['pred_var']), st['pv'], rtol=5e-3, atol=3e-6)   # s - s^2 K^-1_ii cancels ~60x
     np.testing.assert_allclose(float(pieces['gp_loss']), st['gp_loss'], rtol=1e-4)
     np.testing.assert_allclose(float(loss), st['loss'], rtol=1e-3)
     G = top._grads
     for li, lay in enumerate((l0, l1)):
         gW, gb, gc = top._views(lay, G['lower'][li])
-        assert _normrel(_np(gW), og['lower'][li]['W']) < budget
-        assert _normrel(_np(gb), og['lower'][li]['b']) < budget
-        assert _normrel(_np(gc), og['lower'][li]['c']) < budget
+        assert _normrel(_np(gW), og['lower'][li]['W']) < budget(og['lower'][li]['W'], ('lower', li, 'W'))
+        assert _normrel(_np(gb), og['lower'][li]['b']) < budget(og['lower'][li]['b'], ('lower', li, 'b'))
+        assert _normrel(_np(gc), og['lower'][li]['c']) < budget(og['lower'][li]['c'], ('lower', li, 'c'))
     gW, gb, gc = top._views(top, G['top'])
-    assert _normrel(_np(gW), og['top']['W']) < budget
-    assert _normrel(_np(gc), og['top']['c']) < budget
-    assert _normrel(_np(G['X']).reshape(og['X'].shape), og['X']) < budget
+    assert _normrel(_np(gW), og['top']['W']) < budget(og['top']['W'], ('top', 'W'))
+    assert _normrel(_np(gc), og['top']['c']) < budget(og['top']['c'], ('top', 'c'))
+    assert _normrel(_np(G['X']).reshape(og['X'].shape), og['X']) < budget(og['X'], ('X',))
