@@ -133,14 +133,50 @@ __global__ void __launch_bounds__(NB) potrf_colblock_kernel(float* __restrict__ 
   __shared__ int s_fail;
   const int r = threadIdx.x;
   const int nb = min(NB, N - j);
+  // one matrix row per thread; loads are issued 16 at a time so their latencies overlap
+  const int prow = j + blockIdx.x * NB + r;
   {
     const float* src = A + (size_t)(j + r) * lda + j;
-    for (int k = 0; k < NB; ++k) S[k][r] = (r < nb && k <= r) ? __ldg(src + k) : (k == r ? 1.0f : 0.0f);   // identity padding
+    const bool vec = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && nb == NB;   // j is a multiple of 64
+#pragma unroll 1
+    for (int kb = 0; kb < NB; kb += 16) {
+      float t[16];
+      if (vec) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 q = (kb + 4 * u <= r) ? __ldg(reinterpret_cast<const float4*>(src + kb) + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+          t[4 * u] = q.x; t[4 * u + 1] = q.y; t[4 * u + 2] = q.z; t[4 * u + 3] = q.w;
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) t[u] = (r < nb && kb + u <= r) ? __ldg(src + kb + u) : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int k = kb + u;
+        S[k][r] = (r < nb && k <= r) ? t[u] : (k == r ? 1.0f : 0.0f);   // identity padding
+      }
+    }
   }
-  const int prow = j + blockIdx.x * NB + r;
   if (blockIdx.x > 0) {
     const float* src = A + (size_t)prow * lda + j;
-    for (int k = 0; k < NB; ++k) P[k][r] = (prow < N && k < nb) ? __ldg(src + k) : 0.0f;
+    const bool vec = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && nb == NB && prow < N;
+#pragma unroll 1
+    for (int kb = 0; kb < NB; kb += 16) {
+      float t[16];
+      if (vec) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(src + kb) + u);
+          t[4 * u] = q.x; t[4 * u + 1] = q.y; t[4 * u + 2] = q.z; t[4 * u + 3] = q.w;
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) t[u] = (prow < N && kb + u < nb) ? __ldg(src + kb + u) : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) P[kb + u][r] = t[u];
+    }
   }
   if (r == 0) s_fail = 0;
   __syncthreads();
@@ -187,7 +223,13 @@ __global__ void __launch_bounds__(NB) potrf_colblock_kernel(float* __restrict__ 
   }
   if (prow < N) {
     float* dst = A + (size_t)prow * lda + j;
-    for (int k = 0; k < nb; ++k) dst[k] = P[k][r];
+    if (((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && nb == NB) {
+#pragma unroll 4
+      for (int k = 0; k < NB; k += 4)
+        *reinterpret_cast<float4*>(dst + k) = make_float4(P[k][r], P[k + 1][r], P[k + 2][r], P[k + 3][r]);
+    } else {
+      for (int k = 0; k < nb; ++k) dst[k] = P[k][r];
+    }
   }
 }
 
