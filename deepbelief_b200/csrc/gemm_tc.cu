@@ -57,6 +57,18 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int tiles_m, int tiles_n)
   return c;
 }
 
+// work item -> (k-split, tile, column offset and width inside the tile)
+struct WorkItem { int ks, tile, n_off, bn; };
+__device__ __forceinline__ WorkItem decode_work(int w, int num_tiles, int num_full, int k_splits) {
+  WorkItem wi;
+  if (k_splits > 1) { wi.ks = w / num_tiles; wi.tile = w - wi.ks * num_tiles; wi.n_off = 0; wi.bn = BLOCK_N; return wi; }
+  wi.ks = 0;
+  if (w < num_full) { wi.tile = w; wi.n_off = 0; wi.bn = BLOCK_N; return wi; }
+  const int h = w - num_full;
+  wi.tile = num_full + (h >> 1); wi.n_off = (h & 1) * (BLOCK_N / 2); wi.bn = BLOCK_N / 2;
+  return wi;
+}
+
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -64,7 +76,8 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
-               const __grid_constant__ CUtensorMap tm_b, const TcGemmParams p) {
+               const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_b_half,
+               const TcGemmParams p) {
 #if defined(DB_SM100)
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms need 1024-byte aligned tiles
@@ -87,12 +100,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   // work item w = (k-split ks, tile t): all tiles of one K chunk run before the next chunk starts
   const int k_splits = p.k_splits > 1 ? p.k_splits : 1;
   const int kb_per_split = (num_kb + k_splits - 1) / k_splits;
-  const int num_work = num_tiles * k_splits;
+  // Tail balancing: when the last wave would occupy at most half of the CTAs, its tiles are cut into two
+  // 128-column halves (UMMA N = 128), so the wave costs about half a tile time instead of a full one.
+  const int tail_tiles = (k_splits == 1 && p.split_tail) ? num_tiles % (int)gridDim.x : 0;
+  const int num_full = num_tiles - tail_tiles;
+  const int num_work = k_splits > 1 ? num_tiles * k_splits : num_full + 2 * tail_tiles;
 
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&tm_a_hi);
     if (two_pass) ptx::tma_prefetch_desc(&tm_a_lo);
     ptx::tma_prefetch_desc(&tm_b);
+    if (tail_tiles) ptx::tma_prefetch_desc(&tm_b_half);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
@@ -112,11 +130,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const uint32_t tx_bytes = (two_pass ? 2 * A_TILE_BYTES : A_TILE_BYTES) + B_TILE_BYTES;
+      const uint32_t a_bytes = two_pass ? 2 * A_TILE_BYTES : A_TILE_BYTES;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-        const int ks = w / num_tiles, t = w - ks * num_tiles;
-        const TileCoord tc = tile_coord(t, tiles_m, tiles_n);
-        const int m0 = tc.m_blk * BLOCK_M, n0 = tc.n_blk * BLOCK_N;
+        const WorkItem wi = decode_work(w, num_tiles, num_full, k_splits);
+        const int ks = wi.ks;
+        const TileCoord tc = tile_coord(wi.tile, tiles_m, tiles_n);
+        const int m0 = tc.m_blk * BLOCK_M, n0 = tc.n_blk * BLOCK_N + wi.n_off;
+        const uint32_t tx_bytes = a_bytes + (uint32_t)wi.bn * BLOCK_K * 2;
         const int kb_end = min(num_kb, (ks + 1) * kb_per_split);
         for (int kb = ks * kb_per_split; kb < kb_end; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -124,7 +144,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
           ptx::tma_load_2d(st, &tm_a_hi, &full_bar[stage], kb * BLOCK_K, m0);
           if (two_pass) ptx::tma_load_2d(st + A_TILE_BYTES, &tm_a_lo, &full_bar[stage], kb * BLOCK_K, m0);
-          ptx::tma_load_2d(st + 2 * A_TILE_BYTES, &tm_b, &full_bar[stage], kb * BLOCK_K, n0);
+          ptx::tma_load_2d(st + 2 * A_TILE_BYTES, wi.bn == BLOCK_N ? &tm_b : &tm_b_half, &full_bar[stage], kb * BLOCK_K, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -132,11 +152,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc(/*F16*/ 0, BLOCK_M, BLOCK_N);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-        const int ks = w / num_tiles;
+        const WorkItem wi = decode_work(w, num_tiles, num_full, k_splits);
+        const int ks = wi.ks;
+        const uint32_t idesc = ptx::umma_idesc(/*F16*/ 0, BLOCK_M, (uint32_t)wi.bn);
         const int kb_begin = ks * kb_per_split, kb_end = min(num_kb, (ks + 1) * kb_per_split);
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
         ptx::tc_fence_after();
@@ -167,12 +188,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     int acc = 0; uint32_t acc_phase = 0;
     const float inv_pT = p.pT_scale;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-      const int ks = w / num_tiles, t = w - ks * num_tiles;
+      const WorkItem wi = decode_work(w, num_tiles, num_full, k_splits);
+      const int ks = wi.ks;
       float* const out32 = p.out32 ? p.out32 + (size_t)ks * p.split_stride : nullptr;
-      const TileCoord tc = tile_coord(t, tiles_m, tiles_n);
+      const TileCoord tc = tile_coord(wi.tile, tiles_m, tiles_n);
       const int m = tc.m_blk * BLOCK_M + quarter * 32 + lane;
       const bool m_ok = m < p.Ma;
-      const int n_tile0 = tc.n_blk * BLOCK_N;
+      const int n_tile0 = tc.n_blk * BLOCK_N + wi.n_off;
+      const int n_chunks = wi.bn / 32;
       const float bias_m = (p.bias != nullptr && m_ok) ? __ldg(p.bias + m) : 0.0f;
       const float acc_scale = p.acc_scale_dev ? p.acc_scale * __ldg(p.acc_scale_dev) : p.acc_scale;
 
@@ -181,7 +204,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 
 #pragma unroll 1
-      for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+      for (int chunk = 0; chunk < n_chunks; ++chunk) {
         const int nb0 = n_tile0 + chunk * 32;
         if (nb0 >= p.Nb) break;                     // warp-uniform
         uint32_t r[32];
@@ -350,10 +373,11 @@ int tc_gemm_launch(const TcGemmParams& p, int num_sms, cudaStream_t stream) {
   if (p.out_pT_hi && ((p.ldpT % 8) || (reinterpret_cast<uintptr_t>(p.out_pT_hi) & 15) ||
                       (reinterpret_cast<uintptr_t>(p.out_pT_lo) & 15))) return -1000;
 
-  CUtensorMap tm_a_hi, tm_a_lo, tm_b;
+  CUtensorMap tm_a_hi, tm_a_lo, tm_b, tm_b_half;
   if (!make_tmap_f16(&tm_a_hi, p.a_hi, p.Ma, p.K, p.lda, BLOCK_M)) return -1001;
   if (!make_tmap_f16(&tm_a_lo, p.a_lo ? p.a_lo : p.a_hi, p.Ma, p.K, p.lda, BLOCK_M)) return -1001;
   if (!make_tmap_f16(&tm_b, p.b, p.Nb, p.K, p.ldb, BLOCK_N)) return -1001;
+  if (!make_tmap_f16(&tm_b_half, p.b, p.Nb, p.K, p.ldb, BLOCK_N / 2)) return -1001;
 
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -362,9 +386,13 @@ int tc_gemm_launch(const TcGemmParams& p, int num_sms, cudaStream_t stream) {
   });
   if (attr_err != cudaSuccess) return (int)attr_err;
 
-  const int tiles = ((p.Ma + BLOCK_M - 1) / BLOCK_M) * ((p.Nb + BLOCK_N - 1) / BLOCK_N) * (p.k_splits > 1 ? p.k_splits : 1);
+  const int base_tiles = ((p.Ma + BLOCK_M - 1) / BLOCK_M) * ((p.Nb + BLOCK_N - 1) / BLOCK_N);
+  const int tiles = base_tiles * (p.k_splits > 1 ? p.k_splits : 1);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  tc_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_a_hi, tm_a_lo, tm_b, p);
+  TcGemmParams q = p;
+  const int rem = base_tiles % grid;
+  q.split_tail = (p.k_splits <= 1 && base_tiles > grid && rem > 0 && 2 * rem <= grid) ? 1 : 0;
+  tc_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_a_hi, tm_a_lo, tm_b, tm_b_half, q);
   return (int)cudaGetLastError();
 }
 
