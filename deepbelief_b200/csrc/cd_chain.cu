@@ -179,11 +179,12 @@ __global__ void tc_bias_grads_kernel(const __half* __restrict__ vt, const __half
 }
 
 // gW = sum over the K-chunk partials (fixed order: deterministic)
-__global__ void dw_reduce_kernel(const float4* __restrict__ part, size_t n4, int splits, float4* __restrict__ out) {
+__global__ void dw_reduce_kernel(const float4* __restrict__ part, size_t n4, size_t stride4, int splits,
+                                 float4* __restrict__ out) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 a = __ldcs(part + i);
     for (int s = 1; s < splits; ++s) {
-      const float4 b = __ldcs(part + (size_t)s * n4 + i);
+      const float4 b = __ldcs(part + (size_t)s * stride4 + i);
       a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
     out[i] = a;
@@ -201,6 +202,31 @@ inline int ew_grid(size_t n, int num_sms) {
 }
 
 inline bool tc_shape_ok(int N, int V, int H) { return N >= 8 && (N % 8 == 0) && (V % 8 == 0) && (H % 8 == 0) && V >= 8 && H >= 8; }
+
+
+// dW[v,h] = -(1/N) (v0^T p0 - vk^T pk) for rows v in [v_begin, v_begin + v_count): one GEMM over the interleaved
+// K = 2*NP axis (K-chunked, see dw_splits)
+int launch_dw(db_handle_t h, cudaStream_t st, const db_cd_tc_desc_t* d, const ChainWorkspace& ws, float* gW, int v_begin,
+              int v_count) {
+  const int V = d->V, H = d->H;
+  const int ldT = 2 * ws.NP;
+  TcGemmParams p{};
+  p.Ma = H; p.Nb = v_count; p.K = ldT;
+  p.a_hi = ws.pt_hi; p.a_lo = ws.pt_lo; p.lda = ldT; p.b = ws.vt + (size_t)v_begin * ldT; p.ldb = ldT;
+  p.acc_scale = -d->inv_global_n / kProbScale; p.act = 0; p.sample = 0;
+  p.ld32 = H;
+  const bool split = ws.splits > 1 && ((size_t)V * H) % 4 == 0 && ((size_t)v_begin * H) % 4 == 0 && ((size_t)v_count * H) % 4 == 0;
+  if (split) { p.out32 = ws.dw_part + (size_t)v_begin * H; p.k_splits = ws.splits; p.split_stride = (size_t)V * H; }
+  else p.out32 = gW + (size_t)v_begin * H;
+  int rc = tc_gemm_launch(p, tc_ctas(h), st);
+  if (rc) return set_err(h, DB_ERR_CUDA, "cd_tc dW launch failed (%d)", rc);
+  if (split) {
+    const size_t n4 = (size_t)v_count * H / 4, stride4 = (size_t)V * H / 4;
+    dw_reduce_kernel<<<ew_grid(n4, h->num_sms), 256, 0, st>>>(reinterpret_cast<const float4*>(ws.dw_part + (size_t)v_begin * H), n4,
+                                                              stride4, ws.splits, reinterpret_cast<float4*>(gW + (size_t)v_begin * H));
+  }
+  return DB_OK;
+}
 
 }  // namespace
 }  // namespace db
@@ -282,7 +308,7 @@ extern "C" int db_cd_tc_step(db_handle_t h, db_stream_t stream, const db_cd_tc_d
       p.out_pT_hi = ws.pt_hi; p.out_pT_lo = ws.pt_lo; p.ldpT = ldT; p.pT_phase = phase;
       p.pT_scale = phase == 0 ? kProbScale : -kProbScale;
     }
-    return tc_gemm_launch(p, h->num_sms, st);
+    return tc_gemm_launch(p, tc_ctas(h), st);
   };
   auto down = [&](bool last, const float* U, uint64_t draw_i) -> int {
     TcGemmParams p{};
@@ -292,7 +318,7 @@ extern "C" int db_cd_tc_step(db_handle_t h, db_stream_t stream, const db_cd_tc_d
     p.sample = 1; p.U = U; p.ldu = V; set_draw(p, draw_i);
     p.out_s16 = ws.vb; p.lds16 = V;
     if (last) { p.out_sT16 = ws.vt; p.ldsT = ldT; p.sT_phase = 1; }
-    return tc_gemm_launch(p, h->num_sms, st);
+    return tc_gemm_launch(p, tc_ctas(h), st);
   };
 
   int rc = up(ws.v0b, 0, !d->pcd, injected, 0, p0_out);
@@ -305,25 +331,24 @@ extern "C" int db_cd_tc_step(db_handle_t h, db_stream_t stream, const db_cd_tc_d
     rc = up(ws.vb, s == k ? 1 : -1, true, Uh, (uint64_t)(2 * s), s == k ? pk_out : nullptr);
     if (rc) return set_err(h, DB_ERR_CUDA, "cd_tc up launch failed (%d)", rc);
   }
-  {  // dW[v,h] = -(1/N) (v0^T p0 - vk^T pk): one GEMM over the interleaved K = 2*NP axis
-    TcGemmParams p{};
-    p.Ma = H; p.Nb = V; p.K = ldT;
-    p.a_hi = ws.pt_hi; p.a_lo = ws.pt_lo; p.lda = ldT; p.b = ws.vt; p.ldb = ldT;
-    p.acc_scale = -d->inv_global_n / kProbScale; p.act = 0; p.sample = 0;
-    p.ld32 = H;
-    const bool split = ws.splits > 1 && ((size_t)V * H) % 4 == 0;
-    if (split) { p.out32 = ws.dw_part; p.k_splits = ws.splits; p.split_stride = (size_t)V * H; }
-    else p.out32 = gW;
-    rc = tc_gemm_launch(p, h->num_sms, st);
-    if (rc) return set_err(h, DB_ERR_CUDA, "cd_tc dW launch failed (%d)", rc);
-    if (split) {
-      const size_t n4 = (size_t)V * H / 4;
-      dw_reduce_kernel<<<ew_grid(n4, h->num_sms), 256, 0, st>>>(reinterpret_cast<const float4*>(ws.dw_part), n4, ws.splits,
-                                                                reinterpret_cast<float4*>(gW));
-    }
+  if (!d->defer_dw) {
+    rc = launch_dw(h, st, d, ws, gW, 0, V);
+    if (rc) return rc;
   }
   tc_bias_grads_kernel<<<(V + H + 7) / 8, 256, 0, st>>>(ws.vt, ws.pt_hi, ws.pt_lo, V, H, ldT, d->inv_global_n, gb, gc);
   if (vk_out) half_to_float_kernel<<<ew_grid(NV, h->num_sms), 256, 0, st>>>(ws.vb, NV, vk_out);
   if (hk_out) half_to_float_kernel<<<ew_grid(NH, h->num_sms), 256, 0, st>>>(hstate, NH, hk_out);
   return check_launch(h, "cd_tc_step");
+}
+
+extern "C" int db_cd_tc_dw(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, void* workspace, float* grad,
+                           int v_begin, int v_count) {
+  DB_REQUIRE(h, d && workspace && grad, "null operand");
+  DB_REQUIRE(h, v_begin >= 0 && v_count > 0 && v_begin + v_count <= d->V, "row range outside [0, V)");
+  if (h->cc_major < 10) return set_err(h, DB_ERR_UNSUPPORTED, "tcgen05 path needs sm_100a (device is sm_%d%d)", h->cc_major, h->cc_minor);
+  if (!tc_shape_ok(d->N, d->V, d->H)) return set_err(h, DB_ERR_UNSUPPORTED, "tensor path needs N, V, H multiples of 8");
+  ChainWorkspace ws = chain_workspace(workspace, d->N, d->V, d->H);
+  int rc = launch_dw(h, (cudaStream_t)stream, d, ws, grad, v_begin, v_count);
+  if (rc) return rc;
+  return check_launch(h, "cd_tc_dw");
 }

@@ -214,7 +214,7 @@ __global__ void softplus_vec_kernel(const float* __restrict__ x, int n, float* _
 // optimizer
 // ------------------------------------------------------------------------------------------------
 __global__ void optimizer_kernel(db_opt_t o, float lr_t, float* __restrict__ p, const float* __restrict__ g,
-                                 float* __restrict__ st, size_t n) {
+                                 float* __restrict__ st, float* __restrict__ st2, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float th = p[i];
     float gi = __ldg(g + i) + o.weight_decay * th;
@@ -226,8 +226,8 @@ __global__ void optimizer_kernel(db_opt_t o, float lr_t, float* __restrict__ p, 
       th -= o.lr * a;
     } else {
       float m = o.beta1 * st[i] + (1.0f - o.beta1) * gi;
-      float v = o.beta2 * st[n + i] + (1.0f - o.beta2) * gi * gi;
-      st[i] = m; st[n + i] = v;
+      float v = o.beta2 * st2[i] + (1.0f - o.beta2) * gi * gi;
+      st[i] = m; st2[i] = v;
       th -= lr_t * m / (sqrtf(v) + o.eps);
     }
     p[i] = th;
@@ -386,11 +386,10 @@ extern "C" int db_cd_gradients(db_handle_t h, db_stream_t stream, int layer_kind
   return check_launch(h, "cd_gradients");
 }
 
-extern "C" int db_optimizer_step(db_handle_t h, db_stream_t stream, const db_opt_t* opt, float* params, const float* grad,
-                                 float* state, size_t n) {
-  DB_REQUIRE(h, opt && params && grad && n > 0, "null operand");
+extern "C" int db_optimizer_step_range(db_handle_t h, db_stream_t stream, const db_opt_t* opt, float* params, const float* grad,
+                                       float* state, size_t n_total, size_t begin, size_t count) {
+  DB_REQUIRE(h, opt && params && grad && n_total > 0 && count > 0 && begin + count <= n_total, "null operand or bad range");
   DB_REQUIRE(h, opt->kind == DB_OPT_SGD || state, "optimizer state required");
-  DB_REQUIRE(h, opt->kind >= DB_OPT_SGD && opt->kind <= DB_OPT_ADAM, "bad optimizer kind");
   float lr_t = opt->lr;
   if (opt->kind == DB_OPT_ADAM) {
     DB_REQUIRE(h, opt->step >= 1, "Adam needs step >= 1");
@@ -398,8 +397,15 @@ extern "C" int db_optimizer_step(db_handle_t h, db_stream_t stream, const db_opt
     const double b1t = pow((double)opt->beta1, opt->step), b2t = pow((double)opt->beta2, opt->step);
     lr_t = (float)((double)opt->lr * sqrt(1.0 - b2t) / (1.0 - b1t));
   }
-  optimizer_kernel<<<ew_grid(n, h->num_sms), 256, 0, (cudaStream_t)stream>>>(*opt, lr_t, params, grad, state, n);
+  float* m = state ? state + begin : nullptr;
+  float* v = (state && opt->kind == DB_OPT_ADAM) ? state + n_total + begin : nullptr;
+  optimizer_kernel<<<ew_grid(count, h->num_sms), 256, 0, (cudaStream_t)stream>>>(*opt, lr_t, params + begin, grad + begin, m, v, count);
   return check_launch(h, "optimizer_step");
+}
+
+extern "C" int db_optimizer_step(db_handle_t h, db_stream_t stream, const db_opt_t* opt, float* params, const float* grad,
+                                 float* state, size_t n) {
+  return db_optimizer_step_range(h, stream, opt, params, grad, state, n, 0, n);
 }
 
 extern "C" int db_mse(db_handle_t h, db_stream_t stream, const float* a, const float* b, int N, int D, float* out) {

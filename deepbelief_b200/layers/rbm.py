@@ -434,15 +434,7 @@ class RBM(layer.Layer):
         if grad is None:
             grad = torch.empty_like(self._params)
         if self._tc_eligible(n) and not force_simt and persistent is None:
-            plan = self._tc_plan
-            if plan is None or (plan.N, plan.k, plan.n_global) != (n, k, n_global or n):
-                plan = self._tc_plan = ops.CdTcPlan(n, self.num_v, self.num_h, k, pcd=False, n_global=n_global or n,
-                                                    device=self.device)
-                plan.n_global = n_global or n
-                plan.version = -1
-            if plan.version != self._weights_version:
-                plan.refresh_weights(self._params)
-                plan.version = self._weights_version
+            plan = self._tc_plan_for(n, k, n_global or n)
             plan.step(v0, self._params, grad, injected=injected, rng=self.rng)
             return grad, None, None
         # general path: one fused launch per half Gibbs step
@@ -473,6 +465,61 @@ class RBM(layer.Layer):
         """Kernels of this library launched by one cd_step on the tensor-core path: batch conversion,
         2k+1 chain GEMMs, the dW GEMM and the bias-gradient reduction (csrc/cd_chain.cu)."""
         return 1 + (2 * k + 1) + 1 + 1
+
+    # SMs left to the NCCL kernels while a dW chunk is computed next to an in-flight all-reduce (the persistent
+    # tcgen05 GEMM otherwise occupies every SM and the collective could not start until it has finished)
+    COMM_SMS = 16
+    # Measured on 8 B200 at config 5 (scripts/scale_probe.py): 4 chunked all-reduces cost 0.68 ms against 0.40 ms for
+    # one 134 MB call and the dW GEMM loses the reserved SMs, so the pipelined step (4.85-5.00 ms) is SLOWER than
+    # the plain one (4.77 ms). The plain path is therefore the default; DW_CHUNKS > 1 enables the pipeline.
+    DW_CHUNKS = 1
+
+    def cd_update(self, v_0_batch, k, optimizer, opt_state, grad, n_global=None, lr=None, persistent=None):
+        """One full CD-k update: chain, gradient, (data-parallel) sum over ranks, optimizer step.
+        With several ranks on the tensor-core path the dW GEMM is issued in DW_CHUNKS row chunks and the NCCL
+        all-reduce of chunk c runs while chunk c+1 is computed; the optimizer then consumes the chunks as they
+        arrive. Results are identical to cd_step + apply_gradient (same kernels, same reduction order)."""
+        import torch.distributed as td
+        _, world = _dist_info()
+        v0 = to_device(v_0_batch, self.device)
+        n = v0.shape[0]
+        chunk_rows = (self.num_v // max(self.DW_CHUNKS, 1)) // 256 * 256
+        if world == 1 or self.DW_CHUNKS <= 1 or persistent is not None or not self._tc_eligible(n) or chunk_rows < 256:
+            self.cd_step(v0, k, persistent, grad=grad, n_global=n_global)
+            self.apply_gradient(optimizer, grad, opt_state, lr)
+            return
+        plan = self._tc_plan_for(n, k, n_global or n)
+        plan.step(v0, self._params, grad, rng=self.rng, defer_dw=True)
+        H, total = self.num_h, self._params.numel()
+        bounds = [(c * chunk_rows, chunk_rows) for c in range(self.DW_CHUNKS - 1)]
+        bounds.append(((self.DW_CHUNKS - 1) * chunk_rows, self.num_v - (self.DW_CHUNKS - 1) * chunk_rows))
+        works = []
+        ops.set_sm_limit(max(1, plan.num_sms - self.COMM_SMS))
+        try:
+            for c, (vb, vc) in enumerate(bounds):
+                plan.dw(grad, vb, vc)
+                lo = vb * H
+                hi = total if c == len(bounds) - 1 else (vb + vc) * H      # the last chunk carries db | dc as well
+                works.append((lo, hi, td.all_reduce(grad[lo:hi], op=td.ReduceOp.SUM, async_op=True)))
+        finally:
+            ops.set_sm_limit(0)
+        desc = optimizer.descriptor(lr)
+        for lo, hi, work in works:
+            work.wait()
+            ops.optimizer_step_range(desc, self._params, grad, opt_state, lo, hi - lo)
+        self._weights_version += 1
+
+    def _tc_plan_for(self, n, k, n_global):
+        plan = self._tc_plan
+        if plan is None or (plan.N, plan.k, plan.n_global) != (n, k, n_global):
+            plan = self._tc_plan = ops.CdTcPlan(n, self.num_v, self.num_h, k, pcd=False, n_global=n_global, device=self.device)
+            plan.n_global = n_global
+            plan.version = -1
+            plan.num_sms = int(L.lib().db_num_sms(L.handle()))
+        if plan.version != self._weights_version:
+            plan.refresh_weights(self._params)
+            plan.version = self._weights_version
+        return plan
 
     def apply_gradient(self, optimizer, grad, opt_state, lr=None):
         """All-reduce (data parallel) + optimizer step on the packed parameters."""
@@ -521,8 +568,8 @@ class RBM(layer.Layer):
         for self.iter in range(start_iter, max_iter):
             batch = feeder.next()
             v0 = self.bottom.upprop(batch) if self.bottom else batch
-            self.cd_step(v0, num_gibbs_steps, persistent, grad=grad, n_global=n_global)
-            self.apply_gradient(optimizer, grad, opt_state, lr_now)
+            self.cd_update(v0, num_gibbs_steps, optimizer, opt_state, grad, n_global=n_global, lr=lr_now,
+                           persistent=persistent)
             feeder.prefetch()              # host gather + H2D of the next batch overlap this step's kernels
             if step_callback is not None:
                 step_callback(self.iter, grad)

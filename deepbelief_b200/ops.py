@@ -123,6 +123,17 @@ def optimizer_step(opt, params, grad, state):
     L.check(rc, 'db_optimizer_step')
 
 
+def optimizer_step_range(opt, params, grad, state, begin, count):
+    """The same update on elements [begin, begin + count) only (chunk-pipelined data-parallel step)."""
+    rc = L.lib().db_optimizer_step_range(L.handle(), L.stream(), ctypes.byref(opt), L.fptr(params), L.fptr(grad),
+                                         L.fptr(state), params.numel(), int(begin), int(count))
+    L.check(rc, 'db_optimizer_step_range')
+
+
+def set_sm_limit(max_ctas):
+    L.check(L.lib().db_set_sm_limit(L.handle(), int(max_ctas)), 'db_set_sm_limit')
+
+
 def softplus(x):
     x = _f32(x)
     out = torch.empty_like(x)
@@ -167,13 +178,23 @@ class CdTcPlan:
         rc = L.lib().db_cd_tc_refresh_weights(L.handle(), L.stream(), L.fptr(params), self.V, self.H, L.ptr(self.cache))
         L.check(rc, 'db_cd_tc_refresh_weights')
 
-    def step(self, v0, params, grad, injected=None, rng=None, vk_out=None, hk_out=None, p0_out=None, pk_out=None):
+    def step(self, v0, params, grad, injected=None, rng=None, vk_out=None, hk_out=None, p0_out=None, pk_out=None,
+             defer_dw=False):
+        """defer_dw: leave dW to later dw() calls (row chunks); the bias gradients are still written."""
+        self.desc.defer_dw = 1 if defer_dw else 0
         r = rng.next(2 * self.k + 1) if (rng is not None and injected is None) else None
         rc = L.lib().db_cd_tc_step(
             L.handle(), L.stream(), ctypes.byref(self.desc), L.fptr(v0), L.fptr(params), L.ptr(self.cache),
             L.ptr(self.pcd_state), L.fptr(injected), ctypes.byref(r) if r is not None else None,
             L.ptr(self.workspace), L.fptr(grad), L.fptr(vk_out), L.fptr(hk_out), L.fptr(p0_out), L.fptr(pk_out))
         L.check(rc, 'db_cd_tc_step')
+        return grad
+
+    def dw(self, grad, v_begin, v_count):
+        """dW rows [v_begin, v_begin + v_count) of the packed gradient from the chain ends of the last step()."""
+        rc = L.lib().db_cd_tc_dw(L.handle(), L.stream(), ctypes.byref(self.desc), L.ptr(self.workspace), L.fptr(grad),
+                                 int(v_begin), int(v_count))
+        L.check(rc, 'db_cd_tc_dw')
         return grad
 
 

@@ -141,6 +141,8 @@ typedef struct {
   int k;              /* Gibbs steps >= 1 */
   int pcd;            /* 1: chain starts from (and updates) the persistent hidden state */
   float inv_global_n; /* 1 / (batch rows over all ranks) */
+  int defer_dw;       /* 1: db_cd_tc_step leaves dW to later db_cd_tc_dw calls (row chunks, so a data-parallel
+                         caller can all-reduce chunk c while chunk c+1 is still being computed) */
 } db_cd_tc_desc_t;
 
 size_t db_cd_tc_workspace_bytes(const db_cd_tc_desc_t* d);
@@ -156,6 +158,18 @@ int db_cd_tc_step(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, c
                   const float* params, const void* weight_cache, void* pcd_state,
                   const float* injected, const db_rng_t* rng, void* workspace, float* grad,
                   float* vk_out, float* hk_out, float* p0_out, float* pk_out);
+
+/* dW rows [v_begin, v_begin + v_count) of the packed gradient, from the chain ends left in `workspace` by a
+ * db_cd_tc_step call made with defer_dw = 1. */
+int db_cd_tc_dw(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, void* workspace, float* grad,
+                int v_begin, int v_count);
+/* Upper bound on the CTAs the persistent tensor-core kernels launch (0 = one per SM). A caller that overlaps
+ * its own collective kernels (NCCL) with db_cd_tc_dw leaves them a few SMs this way. */
+int db_set_sm_limit(db_handle_t h, int max_ctas);
+/* db_optimizer_step restricted to elements [begin, begin + count) of a packed buffer of n_total elements
+ * (state layout unchanged: m | v, each n_total long). */
+int db_optimizer_step_range(db_handle_t h, db_stream_t stream, const db_opt_t* opt, float* params, const float* grad,
+                            float* state, size_t n_total, size_t begin, size_t count);
 
 /* ---- GP path (gplvm.py / gprbm.py) ----------------------------------------------------------- */
 /* hyp (device, 3 floats + workspace use): effective kernel variance alpha, length-scale gamma, noise
