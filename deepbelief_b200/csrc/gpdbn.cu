@@ -34,6 +34,14 @@ __global__ void concrete_backward_kernel(const float* __restrict__ g, const floa
   }
 }
 
+// dz = g * p (1 - p): backward of tf.sigmoid when the probabilities themselves are propagated (sample=False)
+__global__ void sigmoid_backward_kernel(const float* __restrict__ g, const float* __restrict__ p, size_t n, float* __restrict__ dz) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float pv = __ldg(p + i);
+    dz[i] = __ldg(g + i) * pv * (1.0f - pv);
+  }
+}
+
 // d/dprobs of dist.cross_entropy (dist.py:24-35): clip to [1e-6, 1-1e-6] (gradient passes inside the interval only),
 // logits = log(pc/(1-pc)), sigmoid CE  ->  -t/pc + (1-t)/(1-pc)
 __global__ void cross_entropy_grad_kernel(const float* __restrict__ probs, const float* __restrict__ t, size_t n, float scale,
@@ -201,6 +209,13 @@ extern "C" int db_concrete_backward(db_handle_t h, db_stream_t stream, const flo
   const size_t n = (size_t)M * N;
   concrete_backward_kernel<<<ew_blocks(n, h->num_sms), 256, 0, (cudaStream_t)stream>>>(g, p, a, n, 1.0f / temperature, dz);
   return check_launch(h, "concrete_backward");
+}
+
+extern "C" int db_sigmoid_backward(db_handle_t h, db_stream_t stream, const float* g, const float* p, int M, int N, float* dz) {
+  DB_REQUIRE(h, g && p && dz && M > 0 && N > 0, "null operand or empty shape");
+  const size_t n = (size_t)M * N;
+  sigmoid_backward_kernel<<<ew_blocks(n, h->num_sms), 256, 0, (cudaStream_t)stream>>>(g, p, n, dz);
+  return check_launch(h, "sigmoid_backward");
 }
 
 extern "C" int db_cross_entropy_grad(db_handle_t h, db_stream_t stream, const float* probs, const float* targets, int M, int N,

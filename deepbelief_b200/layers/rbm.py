@@ -581,9 +581,113 @@ class RBM(layer.Layer):
                 self.checkpoint_iter += ckpt_interval      # rbm.py:676, 709-711
                 self.save(self.iter, ckpt_dir)
 
+    # ---- fine-tuning through propagate() --------------------------------------------------------------------------------
+    def _stack_bottom_first(self):
+        return list(reversed(self.layers))
+
+    def propagate_with_tape(self, v_batch, k=1, sample=True, draws=None):
+        """propagate() (rbm.py:327-349) that also records, per sampling op, (direction, layer, input, probabilities,
+        output, mode) for the backward pass. draws: optional injected uniforms, one per sampling op in order."""
+        assert k > 0, 'k must be > 0'
+        stack = self._stack_bottom_first()
+        for lay in stack:
+            if lay.layer_kind != L.LAYER_RBM:
+                raise NotImplementedError('backprop supports stacks of binary RBM layers (as the reference examples use)')
+        tape, di = [], 0
+        a = to_device(v_batch, self.device)
+
+        def one(lay, x, up):
+            nonlocal di
+            if lay.temperature is not None:
+                kind, mode = L.SAMPLE_CONCRETE, 'concrete'              # rbm.py:177-185: whatever `sample` says
+            elif sample:
+                kind, mode = L.SAMPLE_BERNOULLI, 'bernoulli'
+            else:
+                kind, mode = L.SAMPLE_NONE, 'prob'
+            d = None
+            if kind != L.SAMPLE_NONE and draws is not None:
+                d = to_device(draws[di], self.device)
+                di += 1
+            fn = lay._up if up else lay._down
+            p, s = fn(x, L.ACT_SIGMOID, kind, None, d, want_act=True)
+            out = p if mode == 'prob' else s
+            tape.append(('up' if up else 'down', lay, x, p, out, mode))
+            return out
+        for _ in range(k):
+            for lay in stack:
+                a = one(lay, a, True)
+            for lay in reversed(stack):
+                a = one(lay, a, False)
+        return a, tape
+
+    def backprop_gradients(self, v_batch, k=1, sample=True, draws=None):
+        """loss = dist.cross_entropy(propagate(v, k, sample), v) (rbm.py:739-748) and its gradient wrt (W | b | c) of every
+        layer of the stack, bottom first — what optimizer.minimize(training_loss) differentiates (rbm.py:755-758)."""
+        v = to_device(v_batch, self.device)
+        out, tape = self.propagate_with_tape(v, k, sample, draws)
+        loss = dist.cross_entropy(out, v)
+        stack = self._stack_bottom_first()
+        grads = {id(lay): torch.zeros_like(lay._params) for lay in stack}
+        g = ops.cross_entropy_grad(out, v, scale=1.0 / v.shape[0])
+        for direction, lay, a_in, p, o, mode in reversed(tape):
+            if mode == 'bernoulli':
+                break                                                   # tf.cast(tf.greater(p, u)) carries no gradient
+            dz = ops.concrete_backward(g, p, o, lay.temperature) if mode == 'concrete' else ops.sigmoid_backward(g, p)
+            vh = lay.num_v * lay.num_h
+            gl = grads[id(lay)]
+            gW = gl[:vh].view(lay.num_v, lay.num_h)
+            if direction == 'up':
+                ops.gemm(a_in, dz, trans_a=True, beta=1.0, out=gW)
+                ops.colsum(dz, out=gl[vh + lay.num_v:vh + lay.num_v + lay.num_h], beta=1.0)
+                g = ops.gemm(dz, lay.W, trans_b=True)
+            else:
+                ops.gemm(dz, a_in, trans_a=True, beta=1.0, out=gW)
+                ops.colsum(dz, out=gl[vh:vh + lay.num_v], beta=1.0)
+                g = ops.gemm(dz, lay.W)
+        return loss, [grads[id(lay)] for lay in stack], out
+
     def backprop(self, training_data, test_data, training_sampling=True, training_num_propagation_cycles=5,
                  test_num_propagation_cycles=5, learning_rate=0.1, max_iterations=1000, ignore_ckpt_iter=False,
                  eval_interval=0, ckpt_interval=0, ckpt_dir=None):
-        """Cross-entropy fine-tuning through propagate() (rbm.py:713-789) — a 'next' row of the scope
-        table; not part of the accelerated hot path yet."""
-        raise NotImplementedError('RBM.backprop is outside the round-1 hot-path scope (SURVEY.md §8 f4)')
+        """Cross-entropy fine-tuning of the whole stack through propagate() with plain gradient descent
+        (rbm.py:713-789): per iteration one forward/backward sweep of fused GEMM+sample launches, db_gemm and
+        db_concrete_backward / db_sigmoid_backward, then db_optimizer_step per layer."""
+        from .. import compat
+        if not training_sampling:
+            training_num_propagation_cycles = 1                        # rbm.py:735-736
+        stack = self._stack_bottom_first()
+        opt = compat.GradientDescentOptimizer(learning_rate=learning_rate)
+        start_iter = 1 if ignore_ckpt_iter else self.checkpoint_iter
+        max_iter = max_iterations + 1
+
+        def evaluate():
+            tb = test_data.next_batch()
+            tb = to_device(tb[0] if isinstance(tb, tuple) else tb, self.device)
+            v1 = self.propagate(tb, k=test_num_propagation_cycles, sample=True)
+            test_loss = float(dist.cross_entropy(v1, tb))
+            self.logger.info('Iteration: %d, Test loss: %f', self.iter, test_loss)
+            self.loss_x_vals.append(self.iter)
+            self.loss_y_vals.append(test_loss)
+            if self.loss_plotter:
+                self.loss_plotter.set_data(self.loss_x_vals, self.loss_y_vals, 'loss_' + self.name)
+            if self.distr_plotter:
+                self.distr_plotter.set_data((to_numpy(tb.mean(dim=0, keepdim=True)), to_numpy(v1.mean(dim=0, keepdim=True))),
+                                            'distr_' + self.name + '_' + str(self.iter))
+        if eval_interval:
+            self.loss_x_vals, self.loss_y_vals = [], []
+            self.iter = start_iter - 1
+            evaluate()
+        feeder = BatchFeeder(training_data, self.device, max(0, max_iter - start_iter))
+        for self.iter in range(start_iter, max_iter):
+            batch = feeder.next()
+            _, grads, _ = self.backprop_gradients(batch, training_num_propagation_cycles, training_sampling)
+            feeder.prefetch()
+            desc = opt.descriptor()
+            for lay, gl in zip(stack, grads):
+                ops.optimizer_step(desc, lay._params, gl, None)
+                lay._weights_version += 1
+            if eval_interval and self.iter % eval_interval == 0:
+                evaluate()
+            if ckpt_dir and ckpt_interval and self.iter % ckpt_interval == 0:
+                self.checkpoint_iter += ckpt_interval
+                self.save_all(self.iter, ckpt_dir)

@@ -301,6 +301,14 @@ def concrete_backward(g, p, a, temperature):
     return out
 
 
+def sigmoid_backward(g, p):
+    g, p = _f32(g), _f32(p)
+    out = torch.empty_like(p)
+    L.check(L.lib().db_sigmoid_backward(L.handle(), L.stream(), L.fptr(g), L.fptr(p), p.shape[0], p.shape[1], L.fptr(out)),
+            'db_sigmoid_backward')
+    return out
+
+
 def cross_entropy_grad(probs, targets, scale=1.0):
     probs, targets = _f32(probs), _f32(targets)
     out = torch.empty_like(probs)

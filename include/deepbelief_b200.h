@@ -278,6 +278,8 @@ int db_gemm(db_handle_t h, db_stream_t stream, int transA, int transB, int M, in
 /* dz = g * d concrete(p,u,T)/dp * p(1-p) with a = the saved Concrete sample (rbm.py:243-275). */
 int db_concrete_backward(db_handle_t h, db_stream_t stream, const float* g, const float* p, const float* a, int M,
                          int N, float temperature, float* dz);
+/* dz = g * p (1 - p): derivative of tf.sigmoid (rbm.py:160,174) where probabilities are propagated (sample=False). */
+int db_sigmoid_backward(db_handle_t h, db_stream_t stream, const float* g, const float* p, int M, int N, float* dz);
 /* out = scale * d cross_entropy / d probs (dist.py:24-35; zero where probs was clipped). */
 int db_cross_entropy_grad(db_handle_t h, db_stream_t stream, const float* probs, const float* targets, int M, int N,
                           float scale, float* out);

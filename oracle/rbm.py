@@ -210,3 +210,72 @@ class Adam:
         self.v = self.b2 * self.v + (1 - self.b2) * g * g
         lr_t = self.lr * np.sqrt(1 - self.b2 ** self.t) / (1 - self.b1 ** self.t)
         return theta - lr_t * self.m / (np.sqrt(self.v) + self.eps)
+
+
+# ---- fine-tuning through propagate(): RBM.backprop (rbm.py:713-789) -------------------------------------------
+def _concrete(p, u, temperature, dtype):
+    e0 = dtype(EPS0)
+    pre = np.log(p + e0) - np.log(1.0 - p + e0) + np.log(u + e0) - np.log(1.0 - u + e0)
+    return sigmoid(dtype(1.0 / temperature) * pre)
+
+
+def propagate_loss_and_grads(layers, v, k, draws, sample=True, dtype=np.float64):
+    """loss = dist.cross_entropy(propagate(v, k, sample), v) (rbm.py:739-748, dist.py:24-35 reduce_mean=True) for a
+    stack of binary RBMs given bottom-first as dicts {W, b, c, temperature}, and its gradient wrt every W, b, c
+    (what optimizer.minimize(training_loss) differentiates, rbm.py:755-758).
+    draws: one uniform array per sampling op in execution order (per cycle: upprop bottom->top, downprop top->bottom).
+    Units with a temperature are Concrete (rbm.py:177-185: chosen whenever temperature is set, whatever `sample`
+    says); without one they are Bernoulli samples (no gradient) or, with sample=False, probabilities."""
+    L = [{key: (np.asarray(val, dtype=dtype) if key in ('W', 'b', 'c') else val) for key, val in lay.items()} for lay in layers]
+    v = np.asarray(v, dtype=dtype)
+    tape, di, a = [], 0, v
+    for _ in range(k):
+        for li, lay in enumerate(L):                              # upprop (rbm.py:277-300)
+            p = sigmoid(a @ lay['W'] + lay['c'].reshape(1, -1))
+            T = lay.get('temperature')
+            if T is not None:
+                out, mode = _concrete(p, np.asarray(draws[di], dtype=dtype), T, dtype), 'concrete'; di += 1
+            elif sample:
+                out, mode = (p > np.asarray(draws[di], dtype=dtype)).astype(dtype), 'bernoulli'; di += 1
+            else:
+                out, mode = p, 'prob'
+            tape.append(('up', li, a, p, out, mode))
+            a = out
+        for li in range(len(L) - 1, -1, -1):                      # downprop (rbm.py:302-325)
+            lay = L[li]
+            p = sigmoid(a @ lay['W'].T + lay['b'].reshape(1, -1))
+            T = lay.get('temperature')
+            if T is not None:
+                out, mode = _concrete(p, np.asarray(draws[di], dtype=dtype), T, dtype), 'concrete'; di += 1
+            elif sample:
+                out, mode = (p > np.asarray(draws[di], dtype=dtype)).astype(dtype), 'bernoulli'; di += 1
+            else:
+                out, mode = p, 'prob'
+            tape.append(('down', li, a, p, out, mode))
+            a = out
+    e0 = dtype(EPS0)
+    pc = np.clip(a, e0, 1 - e0)
+    logits = np.log(pc / (1 - pc))
+    ce = np.maximum(logits, 0) - logits * v + np.log1p(np.exp(-np.abs(logits)))
+    N = v.shape[0]
+    loss = np.mean(np.sum(ce, axis=1))
+    grads = [dict(W=np.zeros_like(l['W']), b=np.zeros_like(l['b']), c=np.zeros_like(l['c'])) for l in L]
+    g = (-v / pc + (1 - v) / (1 - pc)) * ((a >= e0) & (a <= 1 - e0)) / N
+    for direction, li, a_in, p, out, mode in reversed(tape):
+        lay = L[li]
+        if mode == 'bernoulli':
+            break                                                   # tf.cast(tf.greater(...)) carries no gradient
+        if mode == 'concrete':
+            T = dtype(lay['temperature'])
+            dz = g * out * (1 - out) / T * (1 / (p + e0) + 1 / (1 - p + e0)) * p * (1 - p)
+        else:
+            dz = g * p * (1 - p)
+        if direction == 'up':
+            grads[li]['W'] += a_in.T @ dz
+            grads[li]['c'] += dz.sum(axis=0).reshape(grads[li]['c'].shape)
+            g = dz @ lay['W'].T
+        else:
+            grads[li]['W'] += dz.T @ a_in
+            grads[li]['b'] += dz.sum(axis=0).reshape(grads[li]['b'].shape)
+            g = dz @ lay['W']
+    return float(loss), grads, a

@@ -170,6 +170,44 @@ def rbm_goldens(out):
         out['stack/' + kk] = vv
 
 
+def backprop_goldens(out):
+    """RBM.backprop's training loss (rbm.py:739-748): cross entropy of propagate(v, k) against v on a two-layer stack,
+    by the reference's own rbm.py / dist.py; its gradient as directional finite differences (fp64)."""
+    set_dtype('float64')
+    rs = np.random.RandomState(314)
+    V, H1, H2, N, k = 14, 9, 6, 11, 2
+    P = {'W1': rs.normal(size=(V, H1)) * 0.4, 'b1': rs.normal(size=V) * 0.1, 'c1': rs.normal(size=H1) * 0.1,
+         'W2': rs.normal(size=(H1, H2)) * 0.4, 'b2': rs.normal(size=H1) * 0.1, 'c2': rs.normal(size=H2) * 0.1}
+    v = rs.binomial(1, 0.5, size=(N, V)).astype(np.float64)
+    draws = []
+    for _ in range(k):
+        draws += [rs.uniform(size=(N, H1)), rs.uniform(size=(N, H2)), rs.uniform(size=(N, H1)), rs.uniform(size=(N, V))]
+    for kk, vv in P.items():
+        out['backprop/P/' + kk] = vv
+    out['backprop/v'], out['backprop/k'] = v, np.int64(k)
+    for i, d in enumerate(draws):
+        out['backprop/draw%d' % i] = d
+
+    def loss_at(params, T, sample):
+        l1 = make_layer('rbm', V, H1, params['W1'], params['b1'], params['c1'], None, temperature=T, name='b1')
+        l2 = make_layer('rbm', H1, H2, params['W2'], params['b2'], params['c2'], None, temperature=T, bottom=l1, name='b2')
+        shim.RANDOM_QUEUE[:] = [d for d in draws] if (T is not None or sample) else []
+        v1 = l2.propagate(v, k=k if (T is not None or sample) else 1, sample=sample)
+        shim.RANDOM_QUEUE[:] = []
+        return float(dist.cross_entropy(v1, v)), v1
+    for cname, (T, sample) in {'concrete': (0.25, True), 'prob': (None, False)}.items():
+        loss, v1 = loss_at(P, T, sample)
+        out['backprop/%s/loss' % cname], out['backprop/%s/v1' % cname] = np.float64(loss), v1
+        drs = np.random.RandomState(8)
+        eps = 1e-5
+        for key in P:
+            d = drs.normal(size=P[key].shape); d /= np.linalg.norm(d)
+            Pp, Pm = dict(P), dict(P)
+            Pp[key] = P[key] + eps * d; Pm[key] = P[key] - eps * d
+            out['backprop/%s/dir/%s' % (cname, key)] = d
+            out['backprop/%s/fd/%s' % (cname, key)] = np.float64((loss_at(Pp, T, sample)[0] - loss_at(Pm, T, sample)[0]) / (2 * eps))
+
+
 def gp_goldens(out):
     rs = np.random.RandomState(4321)
     # SEKernel (tests/test_gplvm.py shapes + a 2-D case)
@@ -368,7 +406,7 @@ def misc_goldens(out):
 
 def main():
     for fn, name in ((rbm_goldens, 'rbm_golden.npz'), (gp_goldens, 'gp_golden.npz'), (misc_goldens, 'misc_golden.npz'),
-                     (gpdbn_goldens, 'gpdbn_golden.npz')):
+                     (gpdbn_goldens, 'gpdbn_golden.npz'), (backprop_goldens, 'backprop_golden.npz')):
         out = {}
         fn(out)
         path = os.path.join(HERE, name)

@@ -401,3 +401,51 @@ def test_full_size_config5_properties():
     # the dW GEMM runs K = 2N = 32768 deep; the tensor core's fp32 accumulate truncates, so the K axis is cut
     # into <= 4096-column chunks summed in fp32 (csrc/cd_chain.cu): 1.2e-4 unsplit, bound here 3e-5
     assert _normrel(gW, gb[:, None] * sig(c.astype(np.float32).astype(np.float64))[None, :]) < 3e-5
+
+
+@pytest.mark.parametrize('cname', ['concrete', 'prob'])
+def test_backprop_gradients_vs_oracle(cname):
+    """RBM.backprop's loss and gradient (rbm.py:739-758) on a two-layer stack against the reference-pinned oracle."""
+    from conftest import Golden
+    from deepbelief_b200.layers.rbm import RBM
+    g = Golden('backprop_golden.npz')
+    T, sample = {'concrete': (0.25, True), 'prob': (None, False)}[cname]
+    P = {k: g['backprop/P/' + k] for k in ('W1', 'b1', 'c1', 'W2', 'b2', 'c2')}
+    v = g['backprop/v']
+    V, H1 = P['W1'].shape
+    H2 = P['W2'].shape[1]
+    k = int(g['backprop/k']) if (T is not None or sample) else 1
+    draws = [g['backprop/draw%d' % i] for i in range(4 * int(g['backprop/k']))]
+    l1 = RBM(V, H1, temperature=T, name='bp1')
+    l1.set_weights(P['W1'], P['b1'], P['c1'])
+    l2 = RBM(H1, H2, temperature=T, bottom=l1, name='bp2')
+    l2.set_weights(P['W2'], P['b2'], P['c2'])
+    loss, grads, v1 = l2.backprop_gradients(v, k=k, sample=sample, draws=draws if T is not None else None)
+    layers = [dict(W=P['W1'], b=P['b1'], c=P['c1'], temperature=T), dict(W=P['W2'], b=P['b2'], c=P['c2'], temperature=T)]
+    oloss, ograds, ov1 = orbm.propagate_loss_and_grads(layers, v, k, draws, sample=sample)
+    # saturated Concrete samples are clipped at 1 - 1e-6, where fp32 resolves 1 - p to ~6 %: the budget is the error of
+    # the reference formulas evaluated in fp32 (SURVEY.md §7.3 rule)
+    oloss32 = orbm.propagate_loss_and_grads(layers, v, k, draws, sample=sample, dtype=np.float32)[0]
+    budget = max(1e-5, 2.0 * abs(oloss32 - oloss) / abs(oloss))
+    np.testing.assert_allclose(float(loss), oloss, rtol=budget)
+    np.testing.assert_allclose(float(loss), float(g['backprop/%s/loss' % cname]), rtol=budget)      # the reference itself
+    assert _normrel(_np(v1), ov1) < 1e-4
+    for gl, og, (nv, nh) in zip(grads, ograds, ((V, H1), (H1, H2))):
+        got = _np(gl)
+        assert _normrel(got[:nv * nh].reshape(nv, nh), og['W']) < GRAD_NORMREL
+        assert _normrel(got[nv * nh:nv * nh + nv], og['b']) < GRAD_NORMREL
+        assert _normrel(got[nv * nh + nv:], og['c']) < GRAD_NORMREL
+
+
+def test_backprop_loop_reduces_reconstruction_loss(horses):
+    """RBM.backprop on horses (probabilities propagated, SGD): the test cross entropy falls."""
+    import os
+    from conftest import DATASETS
+    from deepbelief_b200.layers.data import Data
+    from deepbelief_b200.layers.rbm import RBM
+    np.random.seed(0)
+    lay = RBM(1024, 64, W_std=0.01, name='bp-horses', seed=3)
+    path = os.path.join(DATASETS, 'weizmann_horses_training_328x1024_binary.h5')
+    lay.backprop(Data(path, batch_size=328, log_epochs=False), Data(path, batch_size=328, log_epochs=False),
+                 training_sampling=False, learning_rate=0.05, max_iterations=60, eval_interval=30)
+    assert len(lay.loss_y_vals) == 3 and lay.loss_y_vals[-1] < lay.loss_y_vals[0]
