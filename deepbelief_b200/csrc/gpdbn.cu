@@ -268,3 +268,127 @@ extern "C" int db_gpdbn_top_backward2(db_handle_t h, db_stream_t stream, const f
   top_back3_kernel<<<(N + 7) / 8, 256, 0, st>>>(gsig, pred_var, alpha_h, g_alpha_scratch, opt_alpha_h, N, D, g_pv, g_opt_alpha_h);
   return check_launch(h, "gpdbn_top_backward2");
 }
+
+// ---- test-time latent search (gplvm.py:470-541) ---------------------------------------------------------
+// One CTA per restart r: pm[r,:] -> min/max normalisation (gplvm.py:293-296), cross entropy against the test
+// point (dist.py:24-35, mean over the single row) scaled by 1/Dim, plus log_var_scaling * log(pred_var[r]);
+// writes loss[r], the normalised and the [0,1]-clipped prediction, and d loss / d pm[r,:] and d loss / d pred_var[r].
+namespace db { namespace {
+__global__ void __launch_bounds__(256) testgen_rowloss_kernel(const float* __restrict__ pm, const float* __restrict__ target,
+                                                             const float* __restrict__ pv, int R, int D, float log_var_scaling,
+                                                             float* __restrict__ loss, float* __restrict__ pm_norm,
+                                                             float* __restrict__ pm_clip, float* __restrict__ g_pm,
+                                                             float* __restrict__ g_pv) {
+  __shared__ float s_val[8]; __shared__ int s_idx[8];
+  __shared__ float s_mn, s_mx; __shared__ int s_imn, s_imx;
+  __shared__ float red[8];
+  const int r = blockIdx.x;
+  const float* row = pm + (size_t)r * D;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // min / max with the first index attaining them (tf.reduce_min/max route the gradient there)
+  float mn = INFINITY, mx = -INFINITY; int imn = 0x7fffffff, imx = 0x7fffffff;
+  for (int d = threadIdx.x; d < D; d += 256) {
+    const float v = __ldg(row + d);
+    if (v < mn) { mn = v; imn = d; }
+    if (v > mx) { mx = v; imx = d; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const float omn = __shfl_xor_sync(0xffffffffu, mn, o); const int oi = __shfl_xor_sync(0xffffffffu, imn, o);
+    if (omn < mn || (omn == mn && oi < imn)) { mn = omn; imn = oi; }
+    const float omx = __shfl_xor_sync(0xffffffffu, mx, o); const int oj = __shfl_xor_sync(0xffffffffu, imx, o);
+    if (omx > mx || (omx == mx && oj < imx)) { mx = omx; imx = oj; }
+  }
+  if (lane == 0) { s_val[warp] = mn; s_idx[warp] = imn; }
+  __syncthreads();
+  if (threadIdx.x == 0) { float b = s_val[0]; int bi = s_idx[0]; for (int w = 1; w < 8; ++w) if (s_val[w] < b || (s_val[w] == b && s_idx[w] < bi)) { b = s_val[w]; bi = s_idx[w]; } s_mn = b; s_imn = bi; }
+  __syncthreads();
+  if (lane == 0) { s_val[warp] = mx; s_idx[warp] = imx; }
+  __syncthreads();
+  if (threadIdx.x == 0) { float b = s_val[0]; int bi = s_idx[0]; for (int w = 1; w < 8; ++w) if (s_val[w] > b || (s_val[w] == b && s_idx[w] < bi)) { b = s_val[w]; bi = s_idx[w]; } s_mx = b; s_imx = bi; }
+  __syncthreads();
+  mn = s_mn; mx = s_mx;
+  const float rng = mx - mn, inv_rng = 1.0f / rng, inv_dim = 1.0f / (float)D;
+  const float e0 = 1.0e-6f;
+  float ce = 0.0f, sum_g = 0.0f, sum_gp = 0.0f;     // sum_d g_n, sum_d g_n * pn   (g_n = d loss / d pm_norm)
+  for (int d = threadIdx.x; d < D; d += 256) {
+    const float v = __ldg(row + d), t = __ldg(target + d);
+    const float pn = (v - mn) * inv_rng;
+    const float pc = fminf(fmaxf(pn, e0), 1.0f - e0);
+    const float x = logf(pc / (1.0f - pc));
+    ce += fmaxf(x, 0.0f) - x * t + log1pf(__expf(-fabsf(x)));
+    const bool inside = pn >= e0 && pn <= 1.0f - e0;
+    const float gn = inside ? inv_dim * (-t / pc + (1.0f - t) / (1.0f - pc)) : 0.0f;
+    if (pm_norm) pm_norm[(size_t)r * D + d] = pn;
+    if (pm_clip) pm_clip[(size_t)r * D + d] = fminf(fmaxf(v, 0.0f), 1.0f);
+    g_pm[(size_t)r * D + d] = gn * inv_rng;
+    sum_g += gn; sum_gp = fmaf(gn, pn, sum_gp);
+  }
+  auto bsum = [&](float v) { v = warp_sum(v); __syncthreads(); if (lane == 0) red[warp] = v; __syncthreads(); float t = 0.f; for (int w = 0; w < 8; ++w) t += red[w]; return t; };
+  ce = bsum(ce); sum_g = bsum(sum_g); sum_gp = bsum(sum_gp);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // pn = (v - mn) / (mx - mn): d/dmn = (pn - 1)/rng, d/dmx = -pn/rng, routed to the arg-min / arg-max entries
+    g_pm[(size_t)r * D + s_imn] += (sum_gp - sum_g) * inv_rng;
+    g_pm[(size_t)r * D + s_imx] += -sum_gp * inv_rng;
+    const float v = __ldg(pv + r);
+    loss[r] = ce * inv_dim + log_var_scaling * logf(v);
+    g_pv[r] = log_var_scaling / v;
+  }
+}
+// pred_var[r] = alpha - sum_i Kxs[i,r] Cv[i,r] ; flags negative entries
+__global__ void testgen_pred_var_kernel(const float* __restrict__ Kxs, const float* __restrict__ Cv, int N, int R,
+                                        const float* __restrict__ hyp, float* __restrict__ pv, int* __restrict__ info) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  float s = 0.0f;
+  for (int i = 0; i < N; ++i) s = fmaf(__ldg(Kxs + (size_t)i * R + r), __ldg(Cv + (size_t)i * R + r), s);
+  const float v = __ldg(hyp) - s;
+  pv[r] = v;
+  if (v < 0.0f && info) atomicCAS(info, 0, r + 1);
+}
+// g_x[r,q] = -(1/gamma^2) sum_i (gK[i,r] - 2 g_pv[r] Cv[i,r]) Kxs[i,r] (x[r,q] - X[i,q])      (one warp per restart)
+__global__ void testgen_grad_x_kernel(const float* __restrict__ gK, const float* __restrict__ Cv, const float* __restrict__ Kxs,
+                                      const float* __restrict__ g_pv, const float* __restrict__ X, const float* __restrict__ x,
+                                      int N, int R, int Q, const float* __restrict__ hyp, float* __restrict__ g_x) {
+  const int r = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const float inv_g2 = 1.0f / (__ldg(hyp + 1) * __ldg(hyp + 1)), gp = __ldg(g_pv + r);
+  for (int q = 0; q < Q; ++q) {
+    const float xq = __ldg(x + (size_t)r * Q + q);
+    float s = 0.0f;
+    for (int i = lane; i < N; i += 32) {
+      const size_t idx = (size_t)i * R + r;
+      const float w = (__ldg(gK + idx) - 2.0f * gp * __ldg(Cv + idx)) * __ldg(Kxs + idx);
+      s = fmaf(w, xq - __ldg(X + (size_t)i * Q + q), s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) g_x[(size_t)r * Q + q] = -inv_g2 * s;
+  }
+}
+}}  // namespace db::<anon>
+
+extern "C" int db_testgen_rowloss(db_handle_t h, db_stream_t stream, const float* pm, const float* target, const float* pred_var,
+                                  int R, int D, float log_var_scaling, float* loss, float* pm_norm, float* pm_clip, float* g_pm,
+                                  float* g_pv) {
+  DB_REQUIRE(h, pm && target && pred_var && loss && g_pm && g_pv && R > 0 && D > 1, "null operand or bad shape");
+  db::testgen_rowloss_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(pm, target, pred_var, R, D, log_var_scaling, loss, pm_norm, pm_clip,
+                                                                   g_pm, g_pv);
+  return check_launch(h, "testgen_rowloss");
+}
+
+extern "C" int db_testgen_pred_var(db_handle_t h, db_stream_t stream, const float* Kxs, const float* Cv, int N, int R,
+                                   const float* hyp, float* pred_var, int* info) {
+  DB_REQUIRE(h, Kxs && Cv && hyp && pred_var && N > 0 && R > 0, "null operand or bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (info) cudaMemsetAsync(info, 0, sizeof(int), st);
+  db::testgen_pred_var_kernel<<<(R + 127) / 128, 128, 0, st>>>(Kxs, Cv, N, R, hyp, pred_var, info);
+  return check_launch(h, "testgen_pred_var");
+}
+
+extern "C" int db_testgen_grad_x(db_handle_t h, db_stream_t stream, const float* gK, const float* Cv, const float* Kxs,
+                                 const float* g_pv, const float* X, const float* x, int N, int R, int Q, const float* hyp,
+                                 float* g_x) {
+  DB_REQUIRE(h, gK && Cv && Kxs && g_pv && X && x && hyp && g_x && N > 0 && R > 0 && Q > 0, "null operand or bad shape");
+  db::testgen_grad_x_kernel<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(gK, Cv, Kxs, g_pv, X, x, N, R, Q, hyp, g_x);
+  return check_launch(h, "testgen_grad_x");
+}

@@ -369,7 +369,56 @@ class GPLVM(layer.Layer):
         if pivot:
             raise RuntimeError('Cholesky decomposition was not successful: pivot %d is not positive' % pivot)
 
+    def _latent_search_cache(self):
+        """K^-1 and A = K^-1 Y for the current (frozen) parameters — the reference re-runs tf.cholesky inside every
+        one of its ~num_points * num_runs * num_iterations session.run calls."""
+        Lf, S = self._factor()
+        eye = torch.eye(self.N, device=self.device, dtype=torch.float32)
+        Kinv = ops.trsm_lower(Lf, ops.trsm_lower(Lf, eye), trans=True)
+        A = ops.trsm_lower(Lf, S.clone(), trans=True)
+        return Kinv, A
+
+    def latent_search_loss(self, x, test_point, log_var_scaling=0.1, cache=None, want_outputs=False):
+        """(loss [R], d loss / d x [R,Q], ...) of gplvm.py:478-483 at restarts x [R,Q] for one test point."""
+        Kinv, A = cache or self._latent_search_cache()
+        return ops.testgen_eval(self.X, Kinv, A, self.Y_mean, self._effective_hyp(), to_device(x, self.device),
+                                to_device(test_point, self.device).reshape(-1), log_var_scaling, want_outputs)
+
     def test_generalisation(self, test_data, output_table_path, optimizer, log_var_scaling=0.1, num_iterations=1000,
                             num_runs=1):
-        """Latent-point search for test images (gplvm.py:470-541) — scope row f2."""
-        raise NotImplementedError('GPLVM.test_generalisation is outside the round-1 hot-path scope (SURVEY.md §8 f2)')
+        """Latent-point search for test images (gplvm.py:470-541). For every test point, `num_runs` restarts (all
+        training latents when num_runs == N, else random training latents) are optimised for `num_iterations` steps
+        on loss = CE(normalised(pred_mean(x)), test_point) / Dim + log_var_scaling * log(pred_var(x)); the best run is
+        kept. The restarts of one test point are advanced TOGETHER as a batch [R,Q] with K^-1 and K^-1 Y cached —
+        the arithmetic per restart is the reference's; optimizer slots start fresh per test point (the reference
+        keeps one set of slots across runs, which only matters for stateful optimizers)."""
+        test_data = np.asarray(test_data, dtype=np.float32)
+        assert num_runs <= self.N
+        cache = self._latent_search_cache()
+        rs = np.random.RandomState(0)                              # tf.random_uniform(seed=0) [TF stream not reproduced]
+        table = []
+        for test_point_index in range(test_data.shape[0]):
+            test_point = test_data[test_point_index:test_point_index + 1]
+            if num_runs == self.N:
+                idx = np.arange(self.N)
+            else:
+                idx = rs.randint(0, max(self.N - 1, 1), size=num_runs)        # maxval = N - 1, exclusive (gplvm.py:497-499)
+            x = self.X[torch.as_tensor(idx, device=self.device)].clone().contiguous()
+            optimizer.reset()
+            state = torch.zeros(max(optimizer.state_multiple(), 1) * x.numel(), dtype=torch.float32, device=self.device)
+            for _ in range(num_iterations):
+                _, g_x, _, _, _ = self.latent_search_loss(x, test_point, log_var_scaling, cache)
+                ops.optimizer_step(optimizer.descriptor(), x.view(-1), g_x.view(-1), state)
+            loss, _, info, pm_norm, pm_clip = self.latent_search_loss(x, test_point, log_var_scaling, cache, want_outputs=True)
+            bad = int(info.item())
+            if bad:
+                raise RuntimeError('assert_non_negative(pred_var) failed for restart %d' % (bad - 1))
+            dist_np = to_numpy(loss)
+            best = int(np.argmin(dist_np))                          # first minimum = the reference's strict '<' sweep
+            for run in range(len(idx)):
+                self.logger.info('Test point: {}, Run: {}, Distance: {}'.format(test_point_index, run, dist_np[run]))
+            table.append((test_point_index, float(dist_np[best]), to_numpy(x[best:best + 1]), test_point,
+                          to_numpy(pm_norm[best:best + 1]), to_numpy(pm_clip[best:best + 1])))
+        with open(output_table_path, 'wb') as f:
+            pickle.dump(table, f)
+        return table

@@ -421,3 +421,35 @@ def gpdbn_top_backward2(g_H2, H2, x, eps1, pred_var, alpha_h, opt_alpha_h, ga, g
                                         L.fptr(g_opt_alpha_h), L.fptr(g_pv))
     L.check(rc, 'db_gpdbn_top_backward2')
     return g_x, g_pv
+
+
+# ---- test-time latent search (GPLVM.test_generalisation) -----------------------------------------------------
+def testgen_eval(X, Kinv, A, y_mean, hyp, x, target, log_var_scaling, want_outputs=False):
+    """Loss [R] and d loss / d x [R,Q] of the batched latent search (gplvm.py:478-483) at restarts x [R,Q].
+    Kinv [N,N] and A = K^-1 Y [N,D] are cached by the caller (the reference refactorises K on every step)."""
+    N, Q = X.shape
+    R = x.shape[0]
+    D = A.shape[1]
+    dev = X.device
+    Kxs = gram_rbf(X, x, hyp)                                                   # [N,R]
+    pm = (y_mean.reshape(1, D).expand(R, D).contiguous() if y_mean is not None
+          else torch.zeros((R, D), device=dev, dtype=torch.float32))
+    gemm(Kxs, A, trans_a=True, beta=1.0, out=pm)                                # K_Xx^T K^-1 Y + Y_mean
+    Cv = gemm(Kinv, Kxs)                                                        # K^-1 K_Xx
+    pv = torch.empty(R, device=dev, dtype=torch.float32)
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    L.check(L.lib().db_testgen_pred_var(L.handle(), L.stream(), L.fptr(Kxs), L.fptr(Cv), N, R, L.fptr(hyp), L.fptr(pv),
+                                        L.ptr(info)), 'db_testgen_pred_var')
+    loss = torch.empty(R, device=dev, dtype=torch.float32)
+    g_pm = torch.empty((R, D), device=dev, dtype=torch.float32)
+    g_pv = torch.empty(R, device=dev, dtype=torch.float32)
+    pm_norm = torch.empty((R, D), device=dev, dtype=torch.float32) if want_outputs else None
+    pm_clip = torch.empty((R, D), device=dev, dtype=torch.float32) if want_outputs else None
+    L.check(L.lib().db_testgen_rowloss(L.handle(), L.stream(), L.fptr(pm), L.fptr(target), L.fptr(pv), R, D,
+                                       float(log_var_scaling), L.fptr(loss), L.fptr(pm_norm), L.fptr(pm_clip), L.fptr(g_pm),
+                                       L.fptr(g_pv)), 'db_testgen_rowloss')
+    gK = gemm(A, g_pm, trans_b=True)                                            # [N,R]
+    g_x = torch.empty((R, Q), device=dev, dtype=torch.float32)
+    L.check(L.lib().db_testgen_grad_x(L.handle(), L.stream(), L.fptr(gK), L.fptr(Cv), L.fptr(Kxs), L.fptr(g_pv), L.fptr(X),
+                                      L.fptr(x), N, R, Q, L.fptr(hyp), L.fptr(g_x)), 'db_testgen_grad_x')
+    return loss, g_x, info, pm_norm, pm_clip

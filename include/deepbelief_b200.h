@@ -271,6 +271,21 @@ int db_gpdbn_top_backward2(db_handle_t h, db_stream_t stream, const float* g_H2,
                            const float* ga, const float* gmean, int N, int D, float* g_x, float* gsig, float* g_c,
                            float* g_alpha_scratch, float* g_opt_alpha_h, float* g_pv);
 
+/* ---- test-time latent search (GPLVM.test_generalisation, gplvm.py:470-541), batched over R restarts ---------
+ * loss[r] = CE(normalised(pm[r,:]), target) / D + log_var_scaling * log(pred_var[r]) with
+ * normalised(v) = (v - min v) / (max v - min v) (gplvm.py:293-296), CE as dist.py:24-35; also d loss / d pm and
+ * d loss / d pred_var. pm_norm / pm_clip (clip to [0,1], gplvm.py:480) may be NULL. */
+int db_testgen_rowloss(db_handle_t h, db_stream_t stream, const float* pm, const float* target, const float* pred_var,
+                       int R, int D, float log_var_scaling, float* loss, float* pm_norm, float* pm_clip, float* g_pm,
+                       float* g_pv);
+/* pred_var[r] = alpha - sum_i Kxs[i,r] (K^-1 Kxs)[i,r] (gplvm.py:278-288); info: first negative entry (1-based). */
+int db_testgen_pred_var(db_handle_t h, db_stream_t stream, const float* Kxs, const float* Cv, int N, int R,
+                        const float* hyp, float* pred_var, int* info);
+/* g_x[r,:] = sum_i (gK[i,r] - 2 g_pv[r] Cv[i,r]) dKxs[i,r]/dx_r — the chain through the RBF kernel (gplvm.py:61-86). */
+int db_testgen_grad_x(db_handle_t h, db_stream_t stream, const float* gK, const float* Cv, const float* Kxs,
+                      const float* g_pv, const float* X, const float* x, int N, int R, int Q, const float* hyp,
+                      float* g_x);
+
 /* ---- backward building blocks (what TF autodiff derives from tf.matmul / the Concrete units / dist.py) -- */
 /* C[M,N] = alpha * op(A) op(B) + beta * C, fp32 row-major; op = transpose when the flag is set. */
 int db_gemm(db_handle_t h, db_stream_t stream, int transA, int transB, int M, int N, int K, float alpha,

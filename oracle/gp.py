@@ -142,3 +142,20 @@ class GPLVMOracle:
             mean = mean + np.asarray(y_mean, dtype=self.dtype).reshape(1, -1)
         var = se_kernel(xstar, None, self.alpha, self.gamma, diag=True) - np.sum(np.square(sys1), axis=0)
         return mean, var
+
+
+def testgen_loss(model, x, target, log_var_scaling=0.1, y_mean=None):
+    """Per-restart loss of GPLVM.test_generalisation (gplvm.py:478-483) at test latents x [R,Q], each row treated as
+    its own M=1 problem: CE(normalised(pred_mean), target) / Dim + log_var_scaling * log(pred_var)."""
+    x = np.asarray(x, dtype=model.dtype)
+    target = np.asarray(target, dtype=model.dtype).reshape(1, -1)
+    out = np.zeros(x.shape[0], dtype=model.dtype)
+    e0 = model.dtype(10e-7)
+    for r in range(x.shape[0]):
+        mean, var = model.predict(x[r:r + 1], y_mean)
+        pn = (mean - mean.min()) / (mean.max() - mean.min())                     # gplvm.py:293-296
+        pc = np.clip(pn, e0, 1 - e0)
+        lg = np.log(pc / (1 - pc))
+        ce = np.sum(np.maximum(lg, 0) - lg * target + np.log1p(np.exp(-np.abs(lg))))   # dist.py:24-35, one row
+        out[r] = ce / target.shape[1] + log_var_scaling * np.log(var[0])
+    return out

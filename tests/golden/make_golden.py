@@ -282,6 +282,23 @@ def gp_goldens(out):
             (loss_at(X0, oa, og + eps, on) - loss_at(X0, oa, og - eps, on)) / (2 * eps),
             (loss_at(X0, oa, og, on + eps) - loss_at(X0, oa, og, on - eps)) / (2 * eps)])
         out['gplvm/%s/opt' % cname] = np.array([oa, og, on])
+    # test-time latent search loss (gplvm.py:478-483) at single test latents, by the reference's own graph pieces
+    set_dtype('float64')
+    tp = rs.binomial(1, 0.5, size=(1, D)).astype(np.float64)
+    out['testgen/target'] = tp
+    kw = cases['trainable']
+    losses, norms, clips = [], [], []
+    for m in range(M):
+        sess = tf.Session()
+        kern = ref_gplvm.SEKernel(alpha=kw['alpha'], gamma=kw['gamma'], session=sess)
+        g = ref_gplvm.GPLVM(Yd, Q, kern=kern, noise_variance=kw['noise_variance'],
+                            fixed_noise_variance=kw['fixed_noise_variance'], x_test_var=xs[m:m + 1], session=sess)
+        g.build_model()
+        pmn = g.build_pred_mean_normalized(g.pred_mean)
+        loss = 1 / D * dist.cross_entropy(pmn, tp) + 0.1 * tf.log(g.pred_var)
+        losses.append(np.asarray(loss).reshape(-1)[0]); norms.append(np.asarray(pmn)[0])
+        clips.append(np.asarray(tf.clip_by_value(g.pred_mean, 0.0, 1.0))[0])
+    out['testgen/loss'], out['testgen/pm_norm'], out['testgen/pm_clip'] = np.array(losses), np.array(norms), np.array(clips)
     # GPLVM at construction on the bundled horses data (anchor (3) of SURVEY.md §8c), reference code, fp64 + fp32
     horses = hdf5.File(os.path.join(HERE, 'datasets', 'weizmann_horses_training_328x1024_binary.h5'))['datapoints']
     for dname in ('float32', 'float64'):

@@ -250,3 +250,37 @@ def test_full_size_n5000_properties():
     fd = float((loss64(X.double() + t * d.double()) - loss64(X.double() - t * d.double())) / (2 * t))
     an = float((dX.double() * d.double()).sum())
     assert abs(fd - an) / (abs(fd) + 1e-30) < 5e-3
+
+
+def test_latent_search_loss_and_gradient(gp_golden):
+    """GPLVM.test_generalisation's per-restart loss (gplvm.py:478-483) against the reference's own evaluation (golden),
+    its gradient wrt the test latents against central differences of the fp64 oracle, and the driver loop."""
+    import pickle
+    from deepbelief_b200 import compat as tf
+    g = gp_golden
+    lay, orc, pre = _gplvm_pair(g, 'trainable')
+    xs, target = g['gplvm/xstar'], g['testgen/target']
+    loss, g_x, info, pm_norm, pm_clip = lay.latent_search_loss(xs, target, 0.1, want_outputs=True)
+    assert int(info.item()) == 0
+    # the normalised prediction contains an exact 1 (its arg-max), clipped to 1 - 1e-6: fp32 resolves that to 1 - 1.013e-6,
+    # which moves log(p/(1-p)) by 0.0132 for that one element (the reference's fp32 run does the same)
+    np.testing.assert_allclose(_np(loss), g['testgen/loss'], rtol=1e-4, atol=0.015 / lay.D)
+    assert _normrel(_np(pm_norm), g['testgen/pm_norm']) < 1e-4
+    assert _normrel(_np(pm_clip), g['testgen/pm_clip']) < 1e-4
+    y_mean = g[pre + 'Y_mean']
+    eps = 1e-5
+    fd = np.zeros_like(xs)
+    for q in range(xs.shape[1]):
+        d = np.zeros_like(xs); d[:, q] = eps
+        fd[:, q] = (ogp.testgen_loss(orc, xs + d, target, 0.1, y_mean) - ogp.testgen_loss(orc, xs - d, target, 0.1, y_mean)) / (2 * eps)
+    assert _normrel(_np(g_x), fd) < 2e-4
+    # the search itself: SGD from every training latent, best restart kept; the distance can only improve on the start
+    start = _np(lay.latent_search_loss(_np(lay.X), target, 0.1)[0]).min()
+    import tempfile, os
+    path = os.path.join(tempfile.mkdtemp(), 'table.pkl')
+    table = lay.test_generalisation(np.vstack([target, 1 - target]), path, tf.train.GradientDescentOptimizer(learning_rate=0.01),
+                                    log_var_scaling=0.1, num_iterations=25, num_runs=lay.N)
+    assert len(table) == 2 and table[0][0] == 0 and table[0][2].shape == (1, lay.Q) and table[0][4].shape == (1, lay.D)
+    assert table[0][1] <= start + 1e-6
+    with open(path, 'rb') as f:
+        assert len(pickle.load(f)) == 2

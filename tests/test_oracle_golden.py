@@ -205,3 +205,13 @@ def test_survey_anchors_on_horses(horses, gp_golden):
     dX, da, dg, dn = gp.grad()
     np.testing.assert_allclose(np.linalg.norm(dX), 891.6048745762016, rtol=1e-5)
     np.testing.assert_allclose([da, dg, dn], [4347.456017283226, -9954.42826462195, 92050.97401113895], rtol=1e-5)
+
+
+def test_latent_search_loss_matches_reference(gp_golden):
+    """oracle.gp.testgen_loss against the loss the reference's own graph pieces produce (gplvm.py:478-483)."""
+    g = gp_golden
+    pre = 'gplvm/trainable/float64/'
+    oa, og_, on = g['gplvm/trainable/opt']
+    m = ogp.GPLVMOracle(g[pre + 'Y_centered'], g[pre + 'X0'], opt_alpha=oa, opt_gamma=og_, opt_noise=on)
+    got = ogp.testgen_loss(m, g['gplvm/xstar'], g['testgen/target'], 0.1, y_mean=g[pre + 'Y_mean'])
+    np.testing.assert_allclose(got, g['testgen/loss'], rtol=1e-12)
