@@ -351,6 +351,11 @@ def run_b200(args):
                'sample': 'CD-10 + Adam on %d rows of the 4096x8192 workload, 2 timed steps after 1 warm-up '
                          '(oracle port, numpy fp32, BLAS threads)' % n_rows}
 
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'r01_tc_gemm_traffic.json')
+    if os.path.exists(tpath):                      # dram bytes per launch of the dominant kernel, from the committed ncu capture
+        with open(tpath) as f:
+            traffic = json.load(f).get('traffic_bytes_per_launch_mean')
     if rank == 0:
         achieved = cd_flops(n_local) / (chain_ms * 1e-3) / 1e12
         peak = peaks['tensor_sustained']
@@ -365,7 +370,8 @@ def run_b200(args):
                     'num_gibbs_steps=10, pcd=False)', 'monitor_last': monitor[-1] if monitor else None},
             'gpu_launches': launches_per_step * K,
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                         'frac': achieved / peak, 'traffic': None,
+                         'frac': achieved / peak, 'traffic': traffic,
+                         'traffic_unit': 'bytes per tc_gemm_kernel launch (ncu dram read+write, profiles/r01_tc_gemm_traffic.json)',
                          'kernel': 'tc_gemm_kernel (22 launches per step: 21 chain GEMMs + dW)',
                          'peak_source': 'MEASURED_PEAKS.json bf16 sustained (%s); fp16 runs at the bf16 rate'
                                         % peaks['source'],
