@@ -101,6 +101,10 @@ SIGNATURES = {
     'db_testgen_rowloss': (c_int, [c_void_p, c_void_p, c_float_p, c_float_p, c_float_p, c_int, c_int, c_float] + [c_float_p] * 5),
     'db_testgen_pred_var': (c_int, [c_void_p, c_void_p, c_float_p, c_float_p, c_int, c_int, c_float_p, c_float_p, c_void_p]),
     'db_testgen_grad_x': (c_int, [c_void_p, c_void_p] + [c_float_p] * 6 + [c_int, c_int, c_int, c_float_p, c_float_p]),
+    'db_testgen_meanloss': (c_int, [c_void_p, c_void_p, c_float_p, c_float_p, c_float_p, c_int, c_int, c_int, c_float,
+                                    c_float_p, c_float_p, c_float_p]),
+    'db_testgen_reduce_samples': (c_int, [c_void_p, c_void_p, c_float_p, c_float_p, c_float_p, c_float_p, c_int, c_int,
+                                          c_int, c_float, c_float_p, c_float_p]),
     'db_gemm': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float_p, c_int, c_float_p,
                         c_int, c_float, c_float_p, c_int]),
     'db_concrete_backward': (c_int, [c_void_p, c_void_p, c_float_p, c_float_p, c_float_p, c_int, c_int, c_float,

@@ -392,3 +392,82 @@ extern "C" int db_testgen_grad_x(db_handle_t h, db_stream_t stream, const float*
   db::testgen_grad_x_kernel<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(gK, Cv, Kxs, g_pv, X, x, N, R, Q, hyp, g_x);
   return check_launch(h, "testgen_grad_x");
 }
+
+// ---- GPRBM.test_generalisation (gprbm.py:468-562): batched over R restarts x S samples ----------------------
+namespace db { namespace {
+// per restart r: m = mean over its S down-propagated samples, loss[r] = CE(m, target)/Dim + lvs * log(pv[r])
+// (gprbm.py:497-499), g_Vs[(r,s),:] = d loss[r] / d sample, model_point[r,:] = m
+__global__ void __launch_bounds__(256) testgen_meanloss_kernel(const float* __restrict__ Vs, const float* __restrict__ target,
+                                                              const float* __restrict__ pv, int R, int S, int Dim,
+                                                              float log_var_scaling, float* __restrict__ loss,
+                                                              float* __restrict__ model_point, float* __restrict__ g_Vs) {
+  __shared__ float red[8];
+  const int r = blockIdx.x;
+  const float e0 = 1.0e-6f, inv_dim = 1.0f / (float)Dim, inv_s = 1.0f / (float)S;
+  float ce = 0.0f;
+  for (int d = threadIdx.x; d < Dim; d += 256) {
+    float m = 0.0f;
+    for (int s = 0; s < S; ++s) m += __ldg(Vs + ((size_t)r * S + s) * Dim + d);
+    m *= inv_s;
+    const float t = __ldg(target + d);
+    const float pc = fminf(fmaxf(m, e0), 1.0f - e0);
+    const float x = logf(pc / (1.0f - pc));
+    ce += fmaxf(x, 0.0f) - x * t + log1pf(__expf(-fabsf(x)));
+    const bool inside = m >= e0 && m <= 1.0f - e0;
+    const float g = inside ? inv_dim * inv_s * (-t / pc + (1.0f - t) / (1.0f - pc)) : 0.0f;
+    if (model_point) model_point[(size_t)r * Dim + d] = m;
+    for (int s = 0; s < S; ++s) g_Vs[((size_t)r * S + s) * Dim + d] = g;
+  }
+  ce = warp_sum(ce);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ce;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    loss[r] = t * inv_dim + log_var_scaling * logf(__ldg(pv + r));
+  }
+}
+// per restart r: g_Hm[r,d] = sum_s gHm_rows[(r,s),d] ; g_pv[r] = sum_{s,d} gsig_rows[(r,s),d] alpha_h[d] / (2 sqrt(pv[r])) + lvs / pv[r]
+__global__ void __launch_bounds__(256) testgen_reduce_samples_kernel(const float* __restrict__ gHm_rows, const float* __restrict__ gsig_rows,
+                                                                    const float* __restrict__ alpha_h, const float* __restrict__ pv,
+                                                                    int R, int S, int D, float log_var_scaling,
+                                                                    float* __restrict__ g_Hm, float* __restrict__ g_pv) {
+  __shared__ float red[8];
+  const int r = blockIdx.x;
+  float acc = 0.0f;
+  for (int d = threadIdx.x; d < D; d += 256) {
+    float sh = 0.0f, ss = 0.0f;
+    for (int s = 0; s < S; ++s) {
+      const size_t i = ((size_t)r * S + s) * D + d;
+      sh += __ldg(gHm_rows + i); ss += __ldg(gsig_rows + i);
+    }
+    g_Hm[(size_t)r * D + d] = sh;
+    acc = fmaf(ss, __ldg(alpha_h + d), acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    const float v = __ldg(pv + r);
+    g_pv[r] = t / (2.0f * sqrtf(v)) + log_var_scaling / v;
+  }
+}
+}}  // namespace db::<anon>
+
+extern "C" int db_testgen_meanloss(db_handle_t h, db_stream_t stream, const float* Vs, const float* target, const float* pred_var,
+                                   int R, int S, int Dim, float log_var_scaling, float* loss, float* model_point, float* g_Vs) {
+  DB_REQUIRE(h, Vs && target && pred_var && loss && g_Vs && R > 0 && S > 0 && Dim > 0, "null operand or bad shape");
+  db::testgen_meanloss_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(Vs, target, pred_var, R, S, Dim, log_var_scaling, loss, model_point, g_Vs);
+  return check_launch(h, "testgen_meanloss");
+}
+
+extern "C" int db_testgen_reduce_samples(db_handle_t h, db_stream_t stream, const float* gHm_rows, const float* gsig_rows,
+                                         const float* alpha_h, const float* pred_var, int R, int S, int D, float log_var_scaling,
+                                         float* g_Hm, float* g_pv) {
+  DB_REQUIRE(h, gHm_rows && gsig_rows && alpha_h && pred_var && g_Hm && g_pv && R > 0 && S > 0 && D > 0, "null operand or bad shape");
+  db::testgen_reduce_samples_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(gHm_rows, gsig_rows, alpha_h, pred_var, R, S, D,
+                                                                         log_var_scaling, g_Hm, g_pv);
+  return check_launch(h, "testgen_reduce_samples");
+}

@@ -12,8 +12,8 @@ forward / backward sweep over hand-written CUDA kernels (C ABI, include/deepbeli
                 db_colsum, db_cross_entropy / _grad;
   * update    : db_optimizer_step per parameter buffer (same Adam step t for all, as one TF minimize op).
 Randomness: per-layer Philox streams, or injected draws (`draws=`) for the parity tests.
-Not built yet: eval-mode graphs beyond `downprop_latent` / `predict_variance` (test_generalisation,
-test_held_out_data, interp_test: scope row f2 of SURVEY.md §8).
+Eval-mode graphs: `downprop_latent`, `predict_variance` and `test_generalisation` (batched latent search with cached
+K^-1) are built; `test_held_out_data` and `interp_test` are not (scope row f2 of SURVEY.md §8).
 """
 import os
 
@@ -453,9 +453,101 @@ class GPRBM(bgrbm.BGRBM):
                 self.kern.save(i, ckpt_dir)
         self._check_info()
 
+    # ---- test-time latent search (gprbm.py:468-562) ------------------------------------------------------------------
+    def _latent_search_cache(self):
+        """K^-1 and B = K^-1 H2 for the frozen model (H2 / H1_mean are the snapshots of gprbm.py:149-153)."""
+        self._factor(need_L=True)
+        eye = torch.eye(self.N, device=self.device, dtype=torch.float32)
+        Kinv = ops.trsm_lower(self._Lfac, ops.trsm_lower(self._Lfac, eye), trans=True)
+        return Kinv, ops.gemm(Kinv, self.H2_var)
+
+    def latent_search_loss(self, x, test_point, log_var_scaling=0.1, num_samples=1, cache=None, draws=None,
+                           want_outputs=False):
+        """loss [R] and d loss / d x [R,Q] of gprbm.py:490-499 at restarts x [R,Q], each with `num_samples` Gaussian
+        samples of the top hidden layer pushed down the Concrete stack (rows ordered r * S + s).
+        draws (optional injected randomness): {'eps' [R*S,D], 'down_top' [R*S,Vt], 'down': [per lower layer, top first]}."""
+        if self.temperature is None:
+            raise NotImplementedError('the latent search differentiates through Concrete units (temperature)')
+        Kinv, B = cache or self._latent_search_cache()
+        dev, D, S = self.device, self.D, int(num_samples)
+        x = to_device(x, dev)
+        R = x.shape[0]
+        dr = draws or {}
+        inj = lambda v: None if v is None else to_device(v, dev)  # noqa: E731
+        hyp = ops.gp_effective_hyp(self._hyp, self.flags, self.fixed_noise, self.noise_jitter or 0.0)
+        alpha_h = self.alpha_h.reshape(-1)
+        target = to_device(test_point, dev).reshape(-1)
+        Kxs = ops.gram_rbf(self.X, x, hyp)                                   # [N,R]
+        Hm = ops.gemm(Kxs, B, trans_a=True)                                  # (L^-1 K_Xx)^T (L^-1 H2)
+        Cv = ops.gemm(Kinv, Kxs)
+        pv, info = ops.testgen_pred_var(Kxs, Cv, hyp)
+        rows = torch.arange(R, device=dev).repeat_interleave(S)
+        Hm_rows, pv_rows = Hm[rows].contiguous(), pv[rows].contiguous()
+        eps = inj(dr.get('eps'))
+        if eps is None:
+            eps = ops.randn(R * S, D, self.rng, dev)
+        _, y = ops.gpdbn_top_forward_mid(Hm_rows, pv_rows, alpha_h, self.H1_mean_var, eps)
+        q, d = ops.layer_forward(y, self.W, self.b, True, L.ACT_SIGMOID, L.SAMPLE_CONCRETE, self.temperature,
+                                 injected=inj(dr.get('down_top')), rng=self.rng)
+        tape = [(self, q, d)]
+        for i, lay in enumerate(self.layers[1:]):                              # top-most lower layer first
+            if lay.temperature is None:
+                raise NotImplementedError('the latent search differentiates through Concrete units (temperature)')
+            q, d = lay._down(d, lay.visible_act, L.SAMPLE_CONCRETE, None, inj(dr['down'][i]) if 'down' in dr else None)
+            tape.append((lay, q, d))
+        loss, model_point, g = ops.testgen_meanloss(d, target, pv, R, S, log_var_scaling, want_outputs)
+        for lay, q, d_out in reversed(tape):
+            g = ops.gemm(ops.concrete_backward(g, q, d_out, lay.temperature), lay.W)
+        gHm_rows, gsig_rows, _, _ = ops.gpdbn_top_backward1(g, y, Hm_rows, pv_rows, alpha_h, eps)
+        g_Hm, g_pv = ops.testgen_reduce_samples(gHm_rows, gsig_rows, alpha_h, pv, R, S, log_var_scaling)
+        g_x = ops.testgen_grad_x(ops.gemm(B, g_Hm, trans_b=True), Cv, Kxs, g_pv, self.X, x, hyp)
+        return loss, g_x, info, model_point, pv
+
+    def test_generalisation(self, test_data, output_table_path, optimizer, num_iterations=1000, log_var_scaling=0.1,
+                            method='all_training', num_runs=1, num_samples_to_average=1):
+        """gprbm.py:468-562. The restarts of one test point advance together as a batch [R,Q] with K^-1 and K^-1 H2
+        cached (the reference runs them one after the other and refactorises K on every step); optimizer slots start
+        fresh per test point."""
+        import pickle
+        test_data = np.asarray(test_data, dtype=np.float32)
+        assert num_runs <= self.N
+        if self.eval_flag is False:
+            self._snapshot_hidden()                       # H2 / H1_mean from a fresh upprop, as _eval_step does before plots
+        cache = self._latent_search_cache()
+        rs = np.random.RandomState(0)
+        table = []
+        for test_point_index in range(test_data.shape[0]):
+            test_point = test_data[test_point_index:test_point_index + 1]
+            if method == 'all_training':
+                assert num_runs == self.N
+                x = self.X.clone().contiguous()
+            elif method == 'random_normal':
+                x = to_device(rs.normal(size=(num_runs, self.Q)), self.device)
+            elif method == 'random_training':
+                idx = rs.randint(0, max(self.N - 1, 1), size=num_runs)        # maxval N-1 exclusive (gprbm.py:516-521)
+                x = self.X[torch.as_tensor(idx, device=self.device)].clone().contiguous()
+            else:
+                raise AssertionError('unknown method %r' % method)
+            optimizer.reset()
+            state = torch.zeros(max(optimizer.state_multiple(), 1) * x.numel(), dtype=torch.float32, device=self.device)
+            for _ in range(num_iterations):
+                _, g_x, _, _, _ = self.latent_search_loss(x, test_point, log_var_scaling, num_samples_to_average, cache)
+                ops.optimizer_step(optimizer.descriptor(), x.view(-1), g_x.view(-1), state)
+            loss, _, info, model_point, pv = self.latent_search_loss(x, test_point, log_var_scaling, num_samples_to_average,
+                                                                    cache, want_outputs=True)
+            bad = int(info.item())
+            if bad:
+                raise RuntimeError('assert_non_negative(pred_var) failed for restart %d' % (bad - 1))
+            dist_np = to_numpy(loss)
+            best = int(np.argmin(dist_np))
+            for run in range(x.shape[0]):
+                self.logger.info('Test point: {}, Run: {}, Distance: {}'.format(test_point_index, run, dist_np[run]))
+            table.append((test_point_index, float(dist_np[best]), to_numpy(x[best:best + 1]), test_point,
+                          to_numpy(model_point[best]), float(pv[best])))
+        with open(output_table_path, 'wb') as f:
+            pickle.dump(table, f)
+        return table
+
     def test_held_out_data(self, test_data, output_x_fname, optimizer, num_iterations=1000):
         raise NotImplementedError('GPRBM.test_held_out_data is outside the round-1 scope (SURVEY.md §8 f2)')
 
-    def test_generalisation(self, test_data, output_table_path, optimizer, log_var_scaling=0.1, num_iterations=1000,
-                            method='all_training', num_runs=1, num_samples_to_average=100):
-        raise NotImplementedError('GPRBM.test_generalisation is outside the round-1 scope (SURVEY.md §8 f2)')

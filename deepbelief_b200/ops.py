@@ -436,10 +436,7 @@ def testgen_eval(X, Kinv, A, y_mean, hyp, x, target, log_var_scaling, want_outpu
           else torch.zeros((R, D), device=dev, dtype=torch.float32))
     gemm(Kxs, A, trans_a=True, beta=1.0, out=pm)                                # K_Xx^T K^-1 Y + Y_mean
     Cv = gemm(Kinv, Kxs)                                                        # K^-1 K_Xx
-    pv = torch.empty(R, device=dev, dtype=torch.float32)
-    info = torch.zeros(1, dtype=torch.int32, device=dev)
-    L.check(L.lib().db_testgen_pred_var(L.handle(), L.stream(), L.fptr(Kxs), L.fptr(Cv), N, R, L.fptr(hyp), L.fptr(pv),
-                                        L.ptr(info)), 'db_testgen_pred_var')
+    pv, info = testgen_pred_var(Kxs, Cv, hyp)
     loss = torch.empty(R, device=dev, dtype=torch.float32)
     g_pm = torch.empty((R, D), device=dev, dtype=torch.float32)
     g_pv = torch.empty(R, device=dev, dtype=torch.float32)
@@ -449,7 +446,43 @@ def testgen_eval(X, Kinv, A, y_mean, hyp, x, target, log_var_scaling, want_outpu
                                        float(log_var_scaling), L.fptr(loss), L.fptr(pm_norm), L.fptr(pm_clip), L.fptr(g_pm),
                                        L.fptr(g_pv)), 'db_testgen_rowloss')
     gK = gemm(A, g_pm, trans_b=True)                                            # [N,R]
-    g_x = torch.empty((R, Q), device=dev, dtype=torch.float32)
+    g_x = testgen_grad_x(gK, Cv, Kxs, g_pv, X, x, hyp)
+    return loss, g_x, info, pm_norm, pm_clip
+
+
+def testgen_pred_var(Kxs, Cv, hyp):
+    N, R = Kxs.shape
+    pv = torch.empty(R, device=Kxs.device, dtype=torch.float32)
+    info = torch.zeros(1, dtype=torch.int32, device=Kxs.device)
+    L.check(L.lib().db_testgen_pred_var(L.handle(), L.stream(), L.fptr(Kxs), L.fptr(Cv), N, R, L.fptr(hyp), L.fptr(pv),
+                                        L.ptr(info)), 'db_testgen_pred_var')
+    return pv, info
+
+
+def testgen_grad_x(gK, Cv, Kxs, g_pv, X, x, hyp):
+    N, R = Kxs.shape
+    Q = X.shape[1]
+    g_x = torch.empty((R, Q), device=X.device, dtype=torch.float32)
     L.check(L.lib().db_testgen_grad_x(L.handle(), L.stream(), L.fptr(gK), L.fptr(Cv), L.fptr(Kxs), L.fptr(g_pv), L.fptr(X),
                                       L.fptr(x), N, R, Q, L.fptr(hyp), L.fptr(g_x)), 'db_testgen_grad_x')
-    return loss, g_x, info, pm_norm, pm_clip
+    return g_x
+
+
+def testgen_meanloss(Vs, target, pv, R, S, log_var_scaling, want_model_point=False):
+    Dim = Vs.shape[1]
+    loss = torch.empty(R, device=Vs.device, dtype=torch.float32)
+    mp = torch.empty((R, Dim), device=Vs.device, dtype=torch.float32) if want_model_point else None
+    g = torch.empty_like(Vs)
+    L.check(L.lib().db_testgen_meanloss(L.handle(), L.stream(), L.fptr(Vs), L.fptr(target), L.fptr(pv), R, S, Dim,
+                                        float(log_var_scaling), L.fptr(loss), L.fptr(mp), L.fptr(g)), 'db_testgen_meanloss')
+    return loss, mp, g
+
+
+def testgen_reduce_samples(gHm_rows, gsig_rows, alpha_h, pv, R, S, log_var_scaling):
+    D = gHm_rows.shape[1]
+    g_Hm = torch.empty((R, D), device=pv.device, dtype=torch.float32)
+    g_pv = torch.empty(R, device=pv.device, dtype=torch.float32)
+    L.check(L.lib().db_testgen_reduce_samples(L.handle(), L.stream(), L.fptr(gHm_rows), L.fptr(gsig_rows), L.fptr(alpha_h),
+                                              L.fptr(pv), R, S, D, float(log_var_scaling), L.fptr(g_Hm), L.fptr(g_pv)),
+            'db_testgen_reduce_samples')
+    return g_Hm, g_pv

@@ -286,6 +286,17 @@ int db_testgen_grad_x(db_handle_t h, db_stream_t stream, const float* gK, const 
                       const float* g_pv, const float* X, const float* x, int N, int R, int Q, const float* hyp,
                       float* g_x);
 
+/* GPRBM.test_generalisation (gprbm.py:468-562), R restarts x S samples per restart (rows ordered r*S + s):
+ * loss[r] = CE(mean_s Vs[(r,s),:], target) / Dim + log_var_scaling * log(pred_var[r]) (gprbm.py:497-499);
+ * model_point [R,Dim] = the sample mean (may be NULL); g_Vs = d loss / d Vs. */
+int db_testgen_meanloss(db_handle_t h, db_stream_t stream, const float* Vs, const float* target, const float* pred_var,
+                        int R, int S, int Dim, float log_var_scaling, float* loss, float* model_point, float* g_Vs);
+/* sums the per-row outputs of db_gpdbn_top_backward1 over the S samples of each restart:
+ * g_Hm [R,D]; g_pv[r] = sum_{s,d} gsig alpha_h / (2 sqrt(pred_var[r])) + log_var_scaling / pred_var[r]. */
+int db_testgen_reduce_samples(db_handle_t h, db_stream_t stream, const float* gHm_rows, const float* gsig_rows,
+                              const float* alpha_h, const float* pred_var, int R, int S, int D, float log_var_scaling,
+                              float* g_Hm, float* g_pv);
+
 /* ---- backward building blocks (what TF autodiff derives from tf.matmul / the Concrete units / dist.py) -- */
 /* C[M,N] = alpha * op(A) op(B) + beta * C, fp32 row-major; op = transpose when the flag is set. */
 int db_gemm(db_handle_t h, db_stream_t stream, int transA, int transB, int M, int N, int K, float alpha,

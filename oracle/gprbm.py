@@ -244,3 +244,45 @@ class GPDBNOracle:
             g_a = dz @ self.lower[l]['W'].T
         out['top'] = gt
         return st, out
+
+
+def latent_search_loss(oracle, H2, H1_mean, x, target, log_var_scaling, num_samples, draws):
+    """Per-restart loss of GPRBM.test_generalisation (gprbm.py:490-499) at test latents x [R,Q], each row its own
+    M=1 problem as in the reference: build_sample_mean(H2_var, H1_mean_var, num_samples) (gprbm.py:220-232) with
+    sigma_h = alpha_h * sqrt(pred_var(x)) (gprbm.py:114-115), downprop through the Concrete stack, cross entropy of
+    the sample MEAN against the test point / Dim + log_var_scaling * log(pred_var).
+    draws: {'eps' [R*S,D], 'down_top' [R*S,Vt], 'down': [per lower layer, top-most first]}, rows ordered r*S + s."""
+    o, dt, T = oracle, oracle.dt, oracle.T
+    alpha, gamma, noise = o.hyp()
+    X = o.gp['X']
+    x = np.asarray(x, dtype=dt)
+    R, S, D = x.shape[0], int(num_samples), o.D
+    H2 = np.asarray(H2, dtype=dt)
+    H1_mean = np.asarray(H1_mean, dtype=dt).reshape(1, D)
+    target = np.asarray(target, dtype=dt).reshape(1, -1)
+    K = se_kernel(X, None, alpha, gamma) + noise * np.eye(o.N, dtype=dt)
+    L = np.linalg.cholesky(K)
+    alpha_h = softplus(o.top['opt_alpha_h']).reshape(1, D)
+    sys2 = scipy.linalg.solve_triangular(L, H2, lower=True)
+    out = np.zeros(R, dtype=dt)
+    e0 = dt(EPS0)
+    for r in range(R):
+        KXx = se_kernel(X, x[r:r + 1], alpha, gamma)
+        sys1 = scipy.linalg.solve_triangular(L, KXx, lower=True)
+        pv = se_kernel(x[r:r + 1], None, alpha, gamma, diag=True) - np.sum(np.square(sys1), axis=0)     # [1]
+        sigma_h = alpha_h * np.sqrt(pv)[:, None]                                                      # [1,D]
+        H = (sys1.T @ sys2) * alpha_h + H1_mean                                                       # [1,D]
+        rows = slice(r * S, (r + 1) * S)
+        H = H + sigma_h * np.asarray(draws['eps'], dtype=dt)[rows]                                    # [S,D]
+        y = H / sigma_h
+        q = sigmoid((o.top['W'] @ y.T + o.top['b'].reshape(-1, 1)).T)
+        d = concrete(q, np.asarray(draws['down_top'], dtype=dt)[rows], T)
+        for i, lay in enumerate(reversed(o.lower)):
+            q = sigmoid((lay['W'] @ d.T + lay['b'].reshape(-1, 1)).T)
+            d = concrete(q, np.asarray(draws['down'][i], dtype=dt)[rows], T)
+        m = np.mean(d, axis=0, keepdims=True)
+        pc = np.clip(m, e0, 1 - e0)
+        lg = np.log(pc / (1 - pc))
+        ce = np.sum(np.maximum(lg, 0) - lg * target + np.log1p(np.exp(-np.abs(lg))))
+        out[r] = ce / target.shape[1] + log_var_scaling * np.log(pv[0])
+    return out

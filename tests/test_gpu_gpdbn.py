@@ -245,3 +245,49 @@ def test_config4_layer_sizes_vs_oracle():
     assert _normrel(_np(gW), og['top']['W']) < budget(og['top']['W'], ('top', 'W'))
     assert _normrel(_np(gc), og['top']['c']) < budget(og['top']['c'], ('top', 'c'))
     assert _normrel(_np(G['X']).reshape(og['X'].shape), og['X']) < budget(og['X'], ('X',))
+
+
+def test_latent_search_loss_and_gradient_vs_oracle(gpdbn_golden, tmp_path):
+    """GPRBM.test_generalisation (gprbm.py:468-562): per-restart loss against the oracle's line-by-line restatement of
+    gprbm.py:490-499 with the same injected draws, the x-gradient against central differences of that oracle, and the
+    batched driver loop (table format, distance no worse than the best start)."""
+    from deepbelief_b200 import compat as tf
+    g = gpdbn_golden
+    top, (l0, l1) = build_stack(g, 'trainable')
+    o = make_oracle(g, 'trainable')
+    rs = np.random.RandomState(11)
+    N, D, Q = top.N, top.D, top.Q
+    H2 = rs.normal(size=(N, D)).astype(np.float32)
+    H1_mean = rs.normal(size=D).astype(np.float32) * 0.3
+    top.H2_var.copy_(torch.as_tensor(H2).cuda())
+    top.H1_mean_var.copy_(torch.as_tensor(H1_mean).cuda())
+    R, S = 5, 3
+    x = rs.normal(size=(R, Q)).astype(np.float32)
+    Vt, Va, V0 = top.num_v, l1.num_v, l0.num_v
+    draws = {'eps': rs.normal(size=(R * S, D)).astype(np.float32),
+             'down_top': rs.uniform(0.05, 0.95, size=(R * S, Vt)).astype(np.float32),
+             'down': [rs.uniform(0.05, 0.95, size=(R * S, Va)).astype(np.float32),
+                      rs.uniform(0.05, 0.95, size=(R * S, V0)).astype(np.float32)]}
+    target = g['gpdbn/V'][:1].astype(np.float32)
+    loss, g_x, info, mp, pv = top.latent_search_loss(x, target, 0.1, S, draws=draws, want_outputs=True)
+    assert int(info.item()) == 0
+    want = ogprbm.latent_search_loss(o, H2, H1_mean, x, target, 0.1, S, draws)
+    np.testing.assert_allclose(_np(loss), want, rtol=2e-4, atol=0.015 / V0)
+    eps = 1e-4
+    fd = np.zeros((R, Q))
+    for q in range(Q):
+        d = np.zeros((R, Q)); d[:, q] = eps
+        fd[:, q] = (ogprbm.latent_search_loss(o, H2, H1_mean, x + d, target, 0.1, S, draws) -
+                    ogprbm.latent_search_loss(o, H2, H1_mean, x - d, target, 0.1, S, draws)) / (2 * eps)
+    # entries of the sample mean that sit at the 1e-6 clip of dist.cross_entropy switch their gradient on/off (tie band,
+    # see oracle.grads): most components agree to ~1e-4, a restart with such an element to ~1e-2
+    err = np.abs(_np(g_x) - fd) / np.max(np.abs(fd))
+    assert np.max(err) < 1e-2 and np.median(err) < 3e-4
+    # driver: the snapshots are refreshed from a fresh upprop, all training latents are tried (method 'all_training')
+    table = top.test_generalisation(g['gpdbn/V'][:2], str(tmp_path / 't.pkl'), tf.train.GradientDescentOptimizer(learning_rate=0.01),
+                                    num_iterations=10, log_var_scaling=0.1, method='all_training', num_runs=N,
+                                    num_samples_to_average=4)
+    assert len(table) == 2 and table[0][2].shape == (1, Q) and table[0][4].shape == (V0,) and np.isfinite(table[0][1])
+    t2 = top.test_generalisation(g['gpdbn/V'][:1], str(tmp_path / 't2.pkl'), tf.train.GradientDescentOptimizer(learning_rate=0.01),
+                                 num_iterations=3, method='random_training', num_runs=6, num_samples_to_average=2)
+    assert len(t2) == 1
