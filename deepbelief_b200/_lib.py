@@ -87,6 +87,9 @@ SIGNATURES = {
     'db_softplus': (c_int, [c_void_p, c_void_p, c_float_p, c_int, c_float_p]),
     'db_mse': (c_int, [c_void_p, c_void_p, c_float_p, c_float_p, c_int, c_int, c_float_p]),
     'db_cross_entropy': (c_int, [c_void_p, c_void_p, c_float_p, c_float_p, c_int, c_int, c_int, c_float_p]),
+    'db_tf32_split_lo': (c_int, [c_void_p, c_void_p, c_float_p, c_int, c_int, c_int, c_float_p]),
+    'db_gemm_tf32x3_nt': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float_p, c_float_p, c_int, c_float_p,
+                                  c_float_p, c_int, c_float, c_float_p, c_int, c_int]),
     'db_gpdbn_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'db_gpdbn_factor': (c_int, [c_void_p, c_void_p, c_float_p, c_int, c_int, c_int, c_float_p, c_int, c_float, c_float,
                                 c_void_p, c_float_p, c_float_p, c_void_p]),

@@ -1,0 +1,328 @@
+// 3xTF32 tensor-core GEMM for the GP chain (gplvm.py:212 tf.cholesky trailing updates, :235 / :248 triangular
+// solves expressed through L^-1, and the K^-1 / A A^T products of the analytic gradient):
+//
+//   C[M, N] = alpha * X[M, K] * Y[N, K]^T + beta * C        fp32 in / fp32 out, both operands K-major (row-major)
+//
+// Every operand is used as x = hi + lo with hi = tf32(x) (the tensor core reads the top 19 bits of the fp32 word
+// in shared memory: no conversion pass) and lo = x - hi precomputed once per operand (db_tf32_split_lo); the three
+// products hi*hi + lo*hi + hi*lo accumulate into one TMEM tile, which restores fp32-level accuracy (~2^-21).
+// The tensor core adds into the fp32 accumulator with truncation, so K is cut into chunks of <= 1024 columns; the
+// partial tiles are summed by the epilogue in fp32 (same CTA, sequential: deterministic).
+//
+// Same persistent, warp-specialised structure as gemm_tc.cu: warp 0 TMA producer (4 tensor maps, 128B swizzle,
+// 2-stage ring of 96 KB), warp 1 tcgen05.mma kind::tf32 128x256x8, warp 2 TMEM allocator, warps 4-7 epilogue.
+// Output orientation: TMEM lanes = rows of Y (= columns of C), so a warp writes 32 consecutive floats of a row of C.
+#include "context.h"
+#include "ptx.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <mutex>
+#include <cstdlib>
+
+namespace db {
+namespace {
+
+constexpr int BM = 128;       // rows of Y per tile (TMEM lanes)   -> columns of C
+constexpr int BN = 256;       // rows of X per tile (TMEM columns) -> rows of C
+constexpr int BK = 16;        // fp32 elements = one 64-byte swizzle row (smaller stages -> 4 in flight in 192 KB)
+constexpr int UK = 8;         // tf32 MMA K
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 4;    // 16 KB
+constexpr int B_BYTES = BN * BK * 4;    // 32 KB
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // hi + lo of both operands: 96 KB
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = ACC_STAGES * BN;
+constexpr int THREADS = 256;
+constexpr int K_CHUNK = 512;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+
+struct Tf32Params {
+  int M, N, K;            // C is [M, N]; X [M, K], Y [N, K]
+  float alpha, beta;
+  float* C; int ldc;
+  int lower_only;         // 1: only elements with col <= row are produced (tiles above the diagonal are skipped)
+  int k_chunks;
+  int passes;             // 3 (debug: DB_TF32_PASSES=1 issues only the hi*hi product)
+};
+
+// K-major operand tile written by TMA with SWIZZLE_64B: rows are 64 B apart, 8-row groups 512 B apart
+__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)1u << 16;
+  d |= (uint64_t)(512u >> 4) << 32;
+  d |= (uint64_t)1u << 46;
+  d |= (uint64_t)4u << 61;                            // layout type SWIZZLE_64B
+  return d;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tm_y_hi, const __grid_constant__ CUtensorMap tm_y_lo,
+                   const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo, const Tf32Params p) {
+#if defined(DB_SM100)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = tfull_bar + ACC_STAGES;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tempty_bar + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (p.N + BM - 1) / BM;     // along columns of C
+  const int tiles_n = (p.M + BN - 1) / BN;     // along rows of C
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (p.K + BK - 1) / BK;
+  const int kb_per_chunk = (num_kb + p.k_chunks - 1) / p.k_chunks;
+
+  if (warp == 0 && lane == 0) {
+    ptx::tma_prefetch_desc(&tm_y_hi); ptx::tma_prefetch_desc(&tm_y_lo);
+    ptx::tma_prefetch_desc(&tm_x_hi); ptx::tma_prefetch_desc(&tm_x_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < ACC_STAGES; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 128); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) { ptx::tmem_alloc(tmem_base_smem, TMEM_COLS); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  // tile t -> (column block of C, row block of C); row-block-major so consecutive CTAs share the X rows in L2
+  auto tile_m0 = [&](int t) { return (t % tiles_m) * BM; };
+  auto tile_n0 = [&](int t) { return (t / tiles_m) * BN; };
+  auto skipped = [&](int t) { return p.lower_only && tile_m0(t) > tile_n0(t) + BN - 1; };   // min col > max row
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        if (skipped(t)) continue;
+        const int m0 = tile_m0(t), n0 = tile_n0(t);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          ptx::tma_load_2d(st, &tm_y_hi, &full_bar[stage], kb * BK, m0);
+          ptx::tma_load_2d(st + A_BYTES, &tm_y_lo, &full_bar[stage], kb * BK, m0);
+          ptx::tma_load_2d(st + 2 * A_BYTES, &tm_x_hi, &full_bar[stage], kb * BK, n0);
+          ptx::tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tm_x_lo, &full_bar[stage], kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc(/*TF32*/ 2, BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        if (skipped(t)) continue;
+        for (int ck = 0; ck < p.k_chunks; ++ck) {
+          const int kb_begin = ck * kb_per_chunk, kb_end = min(num_kb, (ck + 1) * kb_per_chunk);
+          if (kb_begin >= kb_end) break;
+          ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+          for (int kb = kb_begin; kb < kb_end; ++kb) {
+            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::tc_fence_after();
+            const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
+            const uint64_t d_yhi = umma_desc_k_sw64(sa), d_ylo = umma_desc_k_sw64(sa + A_BYTES);
+            const uint64_t d_xhi = umma_desc_k_sw64(sa + 2 * A_BYTES), d_xlo = umma_desc_k_sw64(sa + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k) {
+              const uint64_t koff = (uint64_t)((k * UK * 4) >> 4);
+              ptx::mma_tf32_ss(tmem_d, d_yhi + koff, d_xhi + koff, idesc, (kb != kb_begin || k != 0) ? 1u : 0u);
+              if (p.passes == 3) {
+                ptx::mma_tf32_ss(tmem_d, d_ylo + koff, d_xhi + koff, idesc, 1u);
+                ptx::mma_tf32_ss(tmem_d, d_yhi + koff, d_xlo + koff, idesc, 1u);
+              }
+            }
+            ptx::mma_commit(&empty_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          ptx::mma_commit(&tfull_bar[acc]);
+          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int quarter = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      if (skipped(t)) continue;
+      const int col = tile_m0(t) + quarter * 32 + lane;       // column of C handled by this thread
+      const int row0 = tile_n0(t);
+      const bool col_ok = col < p.N;
+      for (int ck = 0; ck < p.k_chunks; ++ck) {
+        if (ck * kb_per_chunk >= num_kb) break;
+        ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+        const float prev = ck == 0 ? p.beta : 1.0f;             // later chunks add to what the first one wrote
+#pragma unroll 1
+        for (int chunk = 0; chunk < BN / 32; ++chunk) {
+          const int r0 = row0 + chunk * 32;
+          if (r0 >= p.M) break;
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(taddr0 + (uint32_t)(chunk * 32), r);
+          ptx::tmem_ld_wait();
+          if (col_ok) {
+            // all loads of the read-modify-write are issued before the first store (the compiler cannot prove the
+            // 32 row addresses distinct, and a load-after-store chain would serialise 32 memory latencies)
+            float oldv[32];
+            if (prev != 0.0f) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int row = r0 + j;
+                oldv[j] = (row < p.M && (!p.lower_only || col <= row)) ? __ldcg(p.C + (size_t)row * p.ldc + col) : 0.0f;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int row = r0 + j;
+              if (row < p.M && (!p.lower_only || col <= row)) {
+                const float v = p.alpha * __uint_as_float(r[j]);
+                p.C[(size_t)row * p.ldc + col] = prev != 0.0f ? fmaf(prev, oldv[j], v) : v;
+              }
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&tempty_bar[acc]);
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, TMEM_COLS); }
+#endif
+}
+
+__global__ void tf32_split_lo_kernel(const float* __restrict__ x, size_t rows, size_t cols, size_t ld, float* __restrict__ lo) {
+  const size_t total = rows * cols;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / cols, c = i - r * cols;
+    const float v = __ldg(x + r * ld + c);
+    lo[r * ld + c] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  }
+}
+
+// [R, C] row-major (ld_in) -> [C, R] row-major (ld_out), optionally also the tf32 remainder of the transposed copy
+__global__ void __launch_bounds__(256) transpose_f32_kernel(const float* __restrict__ in, int R, int C, int ld_in,
+                                                            float* __restrict__ out, int ld_out) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + 8 * i, c = c0 + tx;
+    tile[ty + 8 * i][tx] = (r < R && c < C) ? __ldg(in + (size_t)r * ld_in + c) : 0.0f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, r = r0 + tx;
+    if (c < C && r < R) out[(size_t)c * ld_out + r] = tile[tx][ty + 8 * i];
+  }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  });
+  return fn;
+}
+
+bool make_tmap_f32(CUtensorMap* tm, const void* base, int rows, int cols, int ld, int box_rows) {
+  auto enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+bool tf32_gemm_supported(int M, int N, int K, const float* X, const float* X_lo, int ldx, const float* Y, const float* Y_lo, int ldy) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(X_lo) | reinterpret_cast<uintptr_t>(Y) |
+                      reinterpret_cast<uintptr_t>(Y_lo);
+  return M > 0 && N > 0 && K > 0 && (a & 15) == 0 && (ldx % 4 == 0) && (ldy % 4 == 0) && ldx >= K && ldy >= K;
+}
+
+// C[M,N] = alpha X Y^T + beta C; returns 0, or a negative code when the shape cannot use TMA (caller falls back to SIMT)
+int tf32_gemm_launch(db_handle_t h, cudaStream_t st, int M, int N, int K, float alpha, const float* X, const float* X_lo, int ldx,
+                     const float* Y, const float* Y_lo, int ldy, float beta, float* C, int ldc, int lower_only) {
+  if (!tf32_gemm_supported(M, N, K, X, X_lo, ldx, Y, Y_lo, ldy)) return -1000;
+  CUtensorMap tyh, tyl, txh, txl;
+  if (!make_tmap_f32(&tyh, Y, N, K, ldy, BM) || !make_tmap_f32(&tyl, Y_lo, N, K, ldy, BM) ||
+      !make_tmap_f32(&txh, X, M, K, ldx, BN) || !make_tmap_f32(&txl, X_lo, M, K, ldx, BN)) return -1001;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(tf32x3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+  });
+  if (attr_err != cudaSuccess) return (int)attr_err;
+  Tf32Params p;
+  p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.C = C; p.ldc = ldc; p.lower_only = lower_only;
+  const int num_kb = (K + BK - 1) / BK;
+  int kchunk = K_CHUNK;
+  { const char* e = getenv("DB_TF32_KCHUNK"); if (e) kchunk = atoi(e) > 0 ? atoi(e) : K_CHUNK; }
+  int chunks = (K + kchunk - 1) / kchunk;
+  if (chunks < 1) chunks = 1;
+  while (chunks > 1 && (chunks - 1) * ((num_kb + chunks - 1) / chunks) >= num_kb) --chunks;   // no empty chunk
+  p.k_chunks = chunks;
+  { const char* e = getenv("DB_TF32_PASSES"); p.passes = (e && e[0] == '1') ? 1 : 3; }
+  const int tiles = ((N + BM - 1) / BM) * ((M + BN - 1) / BN);
+  const int ctas = tc_ctas(h);
+  const int grid = tiles < ctas ? tiles : ctas;
+  tf32x3_gemm_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tyh, tyl, txh, txl, p);
+  return (int)cudaGetLastError();
+}
+
+void tf32_split_lo(db_handle_t h, cudaStream_t st, const float* x, size_t rows, size_t cols, size_t ld, float* lo) {
+  const size_t total = rows * cols;
+  size_t blocks = (total + 255) / 256, cap = (size_t)h->num_sms * 8;
+  tf32_split_lo_kernel<<<(int)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks)), 256, 0, st>>>(x, rows, cols, ld, lo);
+}
+
+void transpose_f32(cudaStream_t st, const float* in, int R, int C, int ld_in, float* out, int ld_out) {
+  dim3 grid((C + 31) / 32, (R + 31) / 32);
+  transpose_f32_kernel<<<grid, 256, 0, st>>>(in, R, C, ld_in, out, ld_out);
+}
+
+}  // namespace db
+
+using namespace db;
+
+extern "C" int db_tf32_split_lo(db_handle_t h, db_stream_t stream, const float* x, int rows, int cols, int ld, float* lo) {
+  DB_REQUIRE(h, x && lo && rows > 0 && cols > 0 && ld >= cols, "null operand or bad shape");
+  tf32_split_lo(h, (cudaStream_t)stream, x, rows, cols, ld, lo);
+  return check_launch(h, "tf32_split_lo");
+}
+
+extern "C" int db_gemm_tf32x3_nt(db_handle_t h, db_stream_t stream, int M, int N, int K, float alpha, const float* X,
+                                 const float* X_lo, int ldx, const float* Y, const float* Y_lo, int ldy, float beta, float* C,
+                                 int ldc, int lower_only) {
+  DB_REQUIRE(h, X && X_lo && Y && Y_lo && C && M > 0 && N > 0 && K > 0 && ldc >= N, "null operand or bad shape");
+  if (h->cc_major < 10) return set_err(h, DB_ERR_UNSUPPORTED, "tcgen05 path needs sm_100a (device is sm_%d%d)", h->cc_major, h->cc_minor);
+  const int rc = tf32_gemm_launch(h, (cudaStream_t)stream, M, N, K, alpha, X, X_lo, ldx, Y, Y_lo, ldy, beta, C, ldc, lower_only);
+  if (rc == -1000) return set_err(h, DB_ERR_UNSUPPORTED, "3xTF32 GEMM needs 16-byte aligned operands and leading dimensions that are multiples of 4");
+  if (rc) return set_err(h, DB_ERR_CUDA, "tf32x3 GEMM launch failed (%d)", rc);
+  return DB_OK;
+}

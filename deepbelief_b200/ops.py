@@ -486,3 +486,31 @@ def testgen_reduce_samples(gHm_rows, gsig_rows, alpha_h, pv, R, S, log_var_scali
                                               L.fptr(pv), R, S, D, float(log_var_scaling), L.fptr(g_Hm), L.fptr(g_pv)),
             'db_testgen_reduce_samples')
     return g_Hm, g_pv
+
+
+# ---- 3xTF32 tensor-core GEMM -------------------------------------------------------------------------------------
+def tf32_split_lo(x):
+    """x - tf32(x): the remainder operand of the 3xTF32 GEMM (same shape)."""
+    x = _f32(x)
+    lo = torch.empty_like(x)
+    L.check(L.lib().db_tf32_split_lo(L.handle(), L.stream(), L.fptr(x), x.shape[0], x.shape[1], x.shape[1], L.fptr(lo)),
+            'db_tf32_split_lo')
+    return lo
+
+
+def gemm_tf32x3_nt(X, Y, alpha=1.0, beta=0.0, out=None, lower_only=False, X_lo=None, Y_lo=None):
+    """out[M,N] = alpha * X[M,K] @ Y[N,K]^T + beta * out on the tensor cores with fp32-level accuracy."""
+    X, Y = _f32(X), _f32(Y)
+    M, K = X.shape
+    N = Y.shape[0]
+    assert Y.shape[1] == K
+    X_lo = tf32_split_lo(X) if X_lo is None else X_lo
+    Y_lo = (X_lo if Y is X else tf32_split_lo(Y)) if Y_lo is None else Y_lo
+    if out is None:
+        assert beta == 0.0
+        out = torch.zeros((M, N), device=X.device, dtype=torch.float32) if lower_only else \
+            torch.empty((M, N), device=X.device, dtype=torch.float32)
+    rc = L.lib().db_gemm_tf32x3_nt(L.handle(), L.stream(), M, N, K, float(alpha), L.fptr(X), L.fptr(X_lo), K, L.fptr(Y),
+                                   L.fptr(Y_lo), K, float(beta), L.fptr(out), N, 1 if lower_only else 0)
+    L.check(rc, 'db_gemm_tf32x3_nt')
+    return out

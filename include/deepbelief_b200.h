@@ -226,6 +226,18 @@ int db_mse(db_handle_t h, db_stream_t stream, const float* a, const float* b, in
 int db_cross_entropy(db_handle_t h, db_stream_t stream, const float* probs, const float* targets, int N, int D,
                      int reduce_mean, float* out);
 
+/* ---- 3xTF32 tensor-core GEMM (tcgen05 kind::tf32) for the GP chain ------------------------------------------
+ * C[M,N] = alpha * X[M,K] Y[N,K]^T + beta * C, fp32, both operands row-major (K contiguous). X_lo / Y_lo are the
+ * tf32 remainders x - tf32(x) of the operands (same shape and leading dimension), produced by db_tf32_split_lo.
+ * Three MMA passes (hi*hi + lo*hi + hi*lo) keep fp32-level accuracy; K is accumulated in chunks of 1024 columns.
+ * lower_only = 1 writes only elements with column <= row. Needs 16-byte aligned pointers and ldx, ldy % 4 == 0
+ * (else DB_ERR_UNSUPPORTED). Replaces the dense products inside tf.cholesky / tf.matrix_triangular_solve and their
+ * autodiff (gplvm.py:212, 235, 425-428). */
+int db_tf32_split_lo(db_handle_t h, db_stream_t stream, const float* x, int rows, int cols, int ld, float* lo);
+int db_gemm_tf32x3_nt(db_handle_t h, db_stream_t stream, int M, int N, int K, float alpha, const float* X,
+                      const float* X_lo, int ldx, const float* Y, const float* Y_lo, int ldy, float beta, float* C,
+                      int ldc, int lower_only);
+
 /* ---- GPDBN top layer (gprbm.py) in training mode (x_ph = X, gprbm.py:106) ---------------------------
  * One optimisation step of GPRBM.optimize (gprbm.py:375-438) evaluates loss = CE(downprop(sample_mean), V)
  * + gp_loss (gprbm.py:247-256) and the gradient TF autodiff derives for every trainable. The calls below
