@@ -6,11 +6,12 @@
 // Every operand is used as x = hi + lo with hi = tf32(x) (the tensor core reads the top 19 bits of the fp32 word
 // in shared memory: no conversion pass) and lo = x - hi precomputed once per operand (db_tf32_split_lo); the three
 // products hi*hi + lo*hi + hi*lo accumulate into one TMEM tile, which restores fp32-level accuracy (~2^-21).
-// The tensor core adds into the fp32 accumulator with truncation, so K is cut into chunks of <= 1024 columns; the
-// partial tiles are summed by the epilogue in fp32 (same CTA, sequential: deterministic).
+// The tensor core adds into the fp32 accumulator with truncation, so K is cut into chunks of 128 columns; the
+// partial tiles are summed by the epilogue threads in registers, in fp32 round-to-nearest (deterministic).
 //
 // Same persistent, warp-specialised structure as gemm_tc.cu: warp 0 TMA producer (4 tensor maps, 128B swizzle,
-// 2-stage ring of 96 KB), warp 1 tcgen05.mma kind::tf32 128x256x8, warp 2 TMEM allocator, warps 4-7 epilogue.
+// 64B swizzle, 6-stage ring of 32 KB), warp 1 tcgen05.mma kind::tf32 128x128x8, warp 2 TMEM allocator (4 accumulator
+// stages), warps 4-7 epilogue.
 // Output orientation: TMEM lanes = rows of Y (= columns of C), so a warp writes 32 consecutive floats of a row of C.
 #include "context.h"
 #include "ptx.cuh"
@@ -23,17 +24,17 @@ namespace db {
 namespace {
 
 constexpr int BM = 128;       // rows of Y per tile (TMEM lanes)   -> columns of C
-constexpr int BN = 256;       // rows of X per tile (TMEM columns) -> rows of C
-constexpr int BK = 16;        // fp32 elements = one 64-byte swizzle row (smaller stages -> 4 in flight in 192 KB)
+constexpr int BN = 128;       // rows of X per tile (TMEM columns) -> rows of C (128 partial sums per epilogue thread)
+constexpr int BK = 16;        // fp32 elements = one 64-byte swizzle row
 constexpr int UK = 8;         // tf32 MMA K
-constexpr int STAGES = 4;
+constexpr int STAGES = 6;         // 6 x 32 KB in flight
 constexpr int A_BYTES = BM * BK * 4;    // 16 KB
 constexpr int B_BYTES = BN * BK * 4;    // 32 KB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // hi + lo of both operands: 96 KB
-constexpr int ACC_STAGES = 2;
+constexpr int ACC_STAGES = 4;
 constexpr int TMEM_COLS = ACC_STAGES * BN;
 constexpr int THREADS = 256;
-constexpr int K_CHUNK = 512;
+constexpr int K_CHUNK = 128;      // 16 MMA k-steps x 3 products = 48 truncating accumulator adds per chunk
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
 
 struct Tf32Params {
@@ -41,7 +42,8 @@ struct Tf32Params {
   float alpha, beta;
   float* C; int ldc;
   int lower_only;         // 1: only elements with col <= row are produced (tiles above the diagonal are skipped)
-  int k_chunks;
+  int kb_chunk;           // k-blocks (of BK columns) accumulated in TMEM before the partial tile is added to C
+  int tri_k;              // 1: X[i,k] = 0 for k < i and Y[j,k] = 0 for k < j (transposed triangular factors): k starts at max(i0, j0)
   int passes;             // 3 (debug: DB_TF32_PASSES=1 issues only the hi*hi product)
 };
 
@@ -74,7 +76,7 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tm_y_hi, const __grid_con
   const int tiles_n = (p.M + BN - 1) / BN;     // along rows of C
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (p.K + BK - 1) / BK;
-  const int kb_per_chunk = (num_kb + p.k_chunks - 1) / p.k_chunks;
+  const int kb_per_chunk = p.kb_chunk;
 
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&tm_y_hi); ptx::tma_prefetch_desc(&tm_y_lo);
@@ -95,6 +97,7 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tm_y_hi, const __grid_con
   auto tile_m0 = [&](int t) { return (t % tiles_m) * BM; };
   auto tile_n0 = [&](int t) { return (t / tiles_m) * BN; };
   auto skipped = [&](int t) { return p.lower_only && tile_m0(t) > tile_n0(t) + BN - 1; };   // min col > max row
+  auto tile_kb0 = [&](int t) { return p.tri_k ? max(tile_m0(t), tile_n0(t)) / BK : 0; };
 
   if (warp == 0) {
     if (lane == 0) {
@@ -102,7 +105,7 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tm_y_hi, const __grid_con
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         if (skipped(t)) continue;
         const int m0 = tile_m0(t), n0 = tile_n0(t);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = tile_kb0(t); kb < num_kb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
           ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
@@ -121,9 +124,8 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tm_y_hi, const __grid_con
       int acc = 0; uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         if (skipped(t)) continue;
-        for (int ck = 0; ck < p.k_chunks; ++ck) {
-          const int kb_begin = ck * kb_per_chunk, kb_end = min(num_kb, (ck + 1) * kb_per_chunk);
-          if (kb_begin >= kb_end) break;
+        for (int kb_begin = tile_kb0(t); kb_begin < num_kb; kb_begin += kb_per_chunk) {
+          const int kb_end = min(num_kb, kb_begin + kb_per_chunk);
           ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
           ptx::tc_fence_after();
           const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
@@ -151,6 +153,8 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tm_y_hi, const __grid_con
       }
     }
   } else if (warp >= 4) {
+    // Epilogue: the K-chunk partial tiles are summed in REGISTERS in fp32 round-to-nearest (thread = one column of C,
+    // 128 rows), so the truncating tensor-core accumulator never sees more than K_CHUNK columns; one write at the end.
     const int quarter = warp & 3;
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -158,43 +162,47 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tm_y_hi, const __grid_con
       const int col = tile_m0(t) + quarter * 32 + lane;       // column of C handled by this thread
       const int row0 = tile_n0(t);
       const bool col_ok = col < p.N;
-      for (int ck = 0; ck < p.k_chunks; ++ck) {
-        if (ck * kb_per_chunk >= num_kb) break;
+      float sum[BN];
+#pragma unroll
+      for (int j = 0; j < BN; ++j) sum[j] = 0.0f;
+      for (int kb_begin = tile_kb0(t); kb_begin < num_kb; kb_begin += kb_per_chunk) {
         ptx::mbar_wait(&tfull_bar[acc], acc_phase);
         ptx::tc_fence_after();
         const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-        const float prev = ck == 0 ? p.beta : 1.0f;             // later chunks add to what the first one wrote
-#pragma unroll 1
+#pragma unroll
         for (int chunk = 0; chunk < BN / 32; ++chunk) {
-          const int r0 = row0 + chunk * 32;
-          if (r0 >= p.M) break;
           uint32_t r[32];
           ptx::tmem_ld_32x32(taddr0 + (uint32_t)(chunk * 32), r);
           ptx::tmem_ld_wait();
-          if (col_ok) {
-            // all loads of the read-modify-write are issued before the first store (the compiler cannot prove the
-            // 32 row addresses distinct, and a load-after-store chain would serialise 32 memory latencies)
-            float oldv[32];
-            if (prev != 0.0f) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int row = r0 + j;
-                oldv[j] = (row < p.M && (!p.lower_only || col <= row)) ? __ldcg(p.C + (size_t)row * p.ldc + col) : 0.0f;
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int row = r0 + j;
-              if (row < p.M && (!p.lower_only || col <= row)) {
-                const float v = p.alpha * __uint_as_float(r[j]);
-                p.C[(size_t)row * p.ldc + col] = prev != 0.0f ? fmaf(prev, oldv[j], v) : v;
-              }
-            }
-          }
+          for (int j = 0; j < 32; ++j) sum[chunk * 32 + j] += __uint_as_float(r[j]);
         }
         ptx::tc_fence_before();
         ptx::mbar_arrive(&tempty_bar[acc]);
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+      if (col_ok) {
+#pragma unroll
+        for (int g = 0; g < BN / 32; ++g) {
+          // all loads of a read-modify-write group are issued before its first store (the 32 row addresses cannot be
+          // proven distinct by the compiler; a load-after-store chain would serialise 32 memory latencies)
+          float oldv[32];
+          if (p.beta != 0.0f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int row = row0 + g * 32 + j;
+              oldv[j] = (row < p.M && (!p.lower_only || col <= row)) ? __ldcg(p.C + (size_t)row * p.ldc + col) : 0.0f;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int row = row0 + g * 32 + j;
+            if (row < p.M && (!p.lower_only || col <= row)) {
+              const float v = p.alpha * sum[g * 32 + j];
+              p.C[(size_t)row * p.ldc + col] = p.beta != 0.0f ? fmaf(p.beta, oldv[j], v) : v;
+            }
+          }
+        }
       }
     }
   }
@@ -267,7 +275,7 @@ bool tf32_gemm_supported(int M, int N, int K, const float* X, const float* X_lo,
 
 // C[M,N] = alpha X Y^T + beta C; returns 0, or a negative code when the shape cannot use TMA (caller falls back to SIMT)
 int tf32_gemm_launch(db_handle_t h, cudaStream_t st, int M, int N, int K, float alpha, const float* X, const float* X_lo, int ldx,
-                     const float* Y, const float* Y_lo, int ldy, float beta, float* C, int ldc, int lower_only) {
+                     const float* Y, const float* Y_lo, int ldy, float beta, float* C, int ldc, int lower_only, int tri_k) {
   if (!tf32_gemm_supported(M, N, K, X, X_lo, ldx, Y, Y_lo, ldy)) return -1000;
   CUtensorMap tyh, tyl, txh, txl;
   if (!make_tmap_f32(&tyh, Y, N, K, ldy, BM) || !make_tmap_f32(&tyl, Y_lo, N, K, ldy, BM) ||
@@ -280,13 +288,10 @@ int tf32_gemm_launch(db_handle_t h, cudaStream_t st, int M, int N, int K, float 
   if (attr_err != cudaSuccess) return (int)attr_err;
   Tf32Params p;
   p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.C = C; p.ldc = ldc; p.lower_only = lower_only;
-  const int num_kb = (K + BK - 1) / BK;
   int kchunk = K_CHUNK;
   { const char* e = getenv("DB_TF32_KCHUNK"); if (e) kchunk = atoi(e) > 0 ? atoi(e) : K_CHUNK; }
-  int chunks = (K + kchunk - 1) / kchunk;
-  if (chunks < 1) chunks = 1;
-  while (chunks > 1 && (chunks - 1) * ((num_kb + chunks - 1) / chunks) >= num_kb) --chunks;   // no empty chunk
-  p.k_chunks = chunks;
+  p.kb_chunk = kchunk / BK < 1 ? 1 : kchunk / BK;
+  p.tri_k = tri_k;
   { const char* e = getenv("DB_TF32_PASSES"); p.passes = (e && e[0] == '1') ? 1 : 3; }
   const int tiles = ((N + BM - 1) / BM) * ((M + BN - 1) / BN);
   const int ctas = tc_ctas(h);
@@ -321,7 +326,7 @@ extern "C" int db_gemm_tf32x3_nt(db_handle_t h, db_stream_t stream, int M, int N
                                  int ldc, int lower_only) {
   DB_REQUIRE(h, X && X_lo && Y && Y_lo && C && M > 0 && N > 0 && K > 0 && ldc >= N, "null operand or bad shape");
   if (h->cc_major < 10) return set_err(h, DB_ERR_UNSUPPORTED, "tcgen05 path needs sm_100a (device is sm_%d%d)", h->cc_major, h->cc_minor);
-  const int rc = tf32_gemm_launch(h, (cudaStream_t)stream, M, N, K, alpha, X, X_lo, ldx, Y, Y_lo, ldy, beta, C, ldc, lower_only);
+  const int rc = tf32_gemm_launch(h, (cudaStream_t)stream, M, N, K, alpha, X, X_lo, ldx, Y, Y_lo, ldy, beta, C, ldc, lower_only, 0);
   if (rc == -1000) return set_err(h, DB_ERR_UNSUPPORTED, "3xTF32 GEMM needs 16-byte aligned operands and leading dimensions that are multiples of 4");
   if (rc) return set_err(h, DB_ERR_CUDA, "tf32x3 GEMM launch failed (%d)", rc);
   return DB_OK;

@@ -15,6 +15,7 @@
 #include "context.h"
 #include "simt_gemm.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tf32.cuh"
 
 namespace db {
 namespace {
@@ -693,7 +694,9 @@ int run_gram(db_handle_t h, cudaStream_t st, const float* X, const float* Y, int
   return check_launch(h, "gram_rbf");
 }
 
-int run_potrf(db_handle_t h, cudaStream_t st, float* A, int lda, int N, int* info) {
+// lo_buf (optional, same shape / leading dimension as A): scratch for the tf32 remainders of the panels; when given
+// and the operands are TMA-addressable, the wide K = 512 trailing updates run on the tensor cores (3xTF32).
+int run_potrf(db_handle_t h, cudaStream_t st, float* A, int lda, int N, int* info, float* lo_buf = nullptr) {
   cudaMemsetAsync(info, 0, sizeof(int), st);
   for (int b0 = 0; b0 < N; b0 += OB) {
     const int b1 = b0 + OB < N ? b0 + OB : N;
@@ -706,8 +709,23 @@ int run_potrf(db_handle_t h, cudaStream_t st, float* A, int lda, int N, int* inf
       }
     }
     if (b1 < N) {        // wide update of everything right of the outer block, K = b1 - b0
-      const int t = (N - b1 + TileLarge::BM - 1) / TileLarge::BM;
-      syrk_block_kernel<<<dim3(t, t), 256, 0, st>>>(A, lda, N, b1, b1, N, b0, b1);
+      const int rows = N - b1;
+      const float* P = A + (size_t)b1 * lda + b0;
+      bool done = false;
+      if (lo_buf != nullptr && h->cc_major >= 10 && rows >= 512) {
+        float* Plo = lo_buf + (size_t)b1 * lda + b0;
+        if (tf32_gemm_supported(rows, rows, b1 - b0, P, Plo, lda, P, Plo, lda)) {
+          tf32_split_lo(h, st, P, rows, b1 - b0, lda, Plo);
+          const int rc = tf32_gemm_launch(h, st, rows, rows, b1 - b0, -1.0f, P, Plo, lda, P, Plo, lda, 1.0f,
+                                          A + (size_t)b1 * lda + b1, lda, /*lower_only=*/1, /*tri_k=*/0);
+          if (rc != 0 && rc != -1000) return set_err(h, DB_ERR_CUDA, "tf32 trailing update failed (%d)", rc);
+          done = rc == 0;
+        }
+      }
+      if (!done) {
+        const int t = (rows + TileLarge::BM - 1) / TileLarge::BM;
+        syrk_block_kernel<<<dim3(t, t), 256, 0, st>>>(A, lda, N, b1, b1, N, b0, b1);
+      }
     }
   }
   return check_launch(h, "potrf_lower");
@@ -750,7 +768,7 @@ int run_trmm(db_handle_t h, cudaStream_t st, const float* Li, int N, const float
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 struct GplvmWorkspace {
-  float *K, *Li, *Tmp, *S, *Av, *dXacc, *hyp;
+  float *K, *Li, *Tmp, *S, *Av, *B1, *B2, *B3, *dXacc, *hyp;
   GpAccum* acc;
   size_t bytes;
 };
@@ -764,6 +782,9 @@ GplvmWorkspace gplvm_workspace(void* ws, int N, int Q, int D) {
   w.Tmp = reinterpret_cast<float*>(p); p += nn;
   w.S = reinterpret_cast<float*>(p); p += nd;
   w.Av = reinterpret_cast<float*>(p); p += nd;
+  w.B1 = reinterpret_cast<float*>(p); p += nd;     // tensor-core path: Y^T, its tf32 remainder, A^T
+  w.B2 = reinterpret_cast<float*>(p); p += nd;
+  w.B3 = reinterpret_cast<float*>(p); p += nd;
   w.dXacc = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)N * Q);
   w.hyp = reinterpret_cast<float*>(p); p += 256;
   w.acc = reinterpret_cast<GpAccum*>(p); p += 256;
@@ -771,6 +792,84 @@ GplvmWorkspace gplvm_workspace(void* ws, int N, int Q, int D) {
   return w;
 }
 
+inline bool gp_use_tensor_path(db_handle_t h, int N, int D) {
+  return h->cc_major >= 10 && N >= 512 && (N % 4) == 0 && (D % 4) == 0 && D >= 32;
+}
+
+
+
+// ---- tensor-core form of the LML + gradient evaluation (N >= 512, N % 4 == 0, D % 4 == 0) ---------------------------
+// K^-1 = Linv^T Linv as ONE 3xTF32 GEMM over the transposed factor (K range clipped to the non-zero part), A = K^-1 Y,
+// -0.5 A A^T, then a streaming contraction of G = (D/2) K^-1 - 0.5 A A^T with K_f. |L^-1 Y|^2 = sum Y o A.
+__global__ void __launch_bounds__(256) mirror_lower_kernel(float* __restrict__ A, int N) {
+  __shared__ float tile[32][33];
+  if (blockIdx.x > blockIdx.y) return;                       // tile (by, bx) of the lower triangle -> (bx, by)
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + 8 * i, c = c0 + tx;
+    tile[ty + 8 * i][tx] = (r < N && c < N) ? A[(size_t)r * N + c] : 0.0f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, r = r0 + tx;           // writes element (c, r) = (r, c)^T
+    if (c < N && r < N && c < r) A[(size_t)c * N + r] = tile[tx][ty + 8 * i];
+  }
+}
+// tr G = 0.5 (D |Linv|_F^2 - |A|_F^2) from two fp32 round-to-nearest reductions (scratch[0], scratch[1]) replaces the
+// trace summed from the tensor-core tiles: sums of squares are monotone, so the truncating accumulator biases them
+// one way (~3e-6), and tr G cancels ~50x. The diagonal also enters sum G o Kf (Kf_ii = alpha).
+__global__ void gp_fix_trace_kernel(GpAccum* acc, const float* __restrict__ scratch, const float* __restrict__ hyp, int D) {
+  const float tr = 0.5f * ((float)D * scratch[0] - scratch[1]);
+  acc->sumW += hyp[0] * (tr - acc->trG);
+  acc->trG = tr;
+}
+// Kinv[i,i] = sum_k LinvT[i,k]^2 in fp32 round-to-nearest (one warp per row): the tensor-core value of this monotone
+// sum is biased low by the truncating accumulator, and A = K^-1 Y inherits a diagonal bias one-to-one.
+__global__ void kinv_diag_kernel(const float* __restrict__ LinvT, int N, float* __restrict__ Kinv) {
+  const int i = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
+  if (i >= N) return;
+  const float* row = LinvT + (size_t)i * N;
+  float s = 0.0f;
+  for (int k = i + lane; k < N; k += 32) { const float v = __ldg(row + k); s = fmaf(v, v, s); }
+  s = warp_sum(s);
+  if (lane == 0) Kinv[(size_t)i * N + i] = s;
+}
+__global__ void dot_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n, float* __restrict__ out) {
+  float s = 0.0f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    s = fmaf(__ldg(a + i), __ldg(b + i), s);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+// G tile = (D/2) Kinv + AA (AA = -0.5 A A^T, lower part valid) read from memory, contracted with K_f
+__global__ void __launch_bounds__(256) gp_contract_mem_kernel(const float* __restrict__ Kinv, const float* __restrict__ AA, int N, int Q,
+                                                              int D, const float* __restrict__ X, const float* __restrict__ hyp,
+                                                              float* __restrict__ dXacc, GpAccum* accum) {
+  using T = TileLarge;
+  if (blockIdx.x > blockIdx.y) return;
+  __shared__ float rowacc[T::BM][MAXQ];
+  __shared__ float colacc[T::BN][MAXQ];
+  __shared__ float red[3][8];
+  const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
+  const bool diag_tile = blockIdx.x == blockIdx.y;
+  for (int t = threadIdx.x; t < T::BM * MAXQ; t += 256) { (&rowacc[0][0])[t] = 0.0f; (&colacc[0][0])[t] = 0.0f; }
+  const float half_d = 0.5f * (float)D;
+  float gacc[T::TM][T::TN];
+#pragma unroll
+  for (int i = 0; i < T::TM; ++i) {
+    const int m = simt_row<T>(m0, i);
+#pragma unroll
+    for (int jj = 0; jj < T::TN; ++jj) {
+      const int n = simt_col<T>(n0, jj);
+      gacc[i][jj] = (m < N && n < N && n <= m) ? fmaf(half_d, __ldg(Kinv + (size_t)m * N + n), __ldg(AA + (size_t)m * N + n)) : 0.0f;
+    }
+  }
+  __syncthreads();
+  gp_contract_tile<T>(gacc, m0, n0, diag_tile, X, N, Q, hyp, dXacc, accum, rowacc, colacc, red);
+}
 
 // ---- GPDBN top layer (gprbm.py), training mode x_ph = X ------------------------------------------------
 // With K_Xx = K_f = K - s I (s = noise variance) the reference's quantities collapse to (after GP14):
@@ -1023,16 +1122,48 @@ extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float*
   effective_hyp_kernel<<<1, 1, 0, st>>>(hyp_opt, flags, fixed_noise, jitter, w.hyp);
   cudaMemsetAsync(w.acc, 0, sizeof(GpAccum), st);
   if ((rc = run_gram(h, st, X, nullptr, N, N, Q, w.hyp, 1, w.K, N))) return rc;
-  if ((rc = run_potrf(h, st, w.K, N, N, info))) return rc;
+  const bool tc = gp_use_tensor_path(h, N, D);
+  if ((rc = run_potrf(h, st, w.K, N, N, info, tc ? w.Li : nullptr))) return rc;
   if (L_out) cudaMemcpyAsync(L_out, w.K, sizeof(float) * (size_t)N * N, cudaMemcpyDeviceToDevice, st);
   logdet_xsq_kernel<<<1, 1024, 0, st>>>(w.K, N, N, X, N * Q, w.acc);
   if ((rc = run_trinv(h, st, w.K, N, N, w.Li, w.Tmp))) return rc;
+  if (tc) {
+    const size_t nn = (size_t)N * N, nd = (size_t)N * D;
+    const int tiles32 = (N + 31) / 32;
+    float* frob = reinterpret_cast<float*>(w.acc) + 16;                          // two scratch floats behind the accumulators
+    cudaMemsetAsync(frob, 0, 2 * sizeof(float), st);
+    transpose_f32(st, w.Li, N, N, N, w.Tmp, N);                                  // Tmp = Linv^T (upper triangular)
+    dot_sum_kernel<<<h->num_sms * 4, 256, 0, st>>>(w.Li, w.Li, nn, frob);         // |Linv|_F^2 = tr K^-1
+    tf32_split_lo(h, st, w.Tmp, N, N, N, w.K);                                   // K buffer = its tf32 remainder
+    int trc = tf32_gemm_launch(h, st, N, N, N, 1.0f, w.Tmp, w.K, N, w.Tmp, w.K, N, 0.0f, w.Li, N, 1, 1);   // Li = K^-1 (lower)
+    if (trc) return set_err(h, DB_ERR_CUDA, "tf32 K^-1 product failed (%d)", trc);
+    mirror_lower_kernel<<<dim3(tiles32, tiles32), 256, 0, st>>>(w.Li, N);
+    kinv_diag_kernel<<<(N + 7) / 8, 256, 0, st>>>(w.Tmp, N, w.Li);
+    tf32_split_lo(h, st, w.Li, N, N, N, w.Tmp);                                  // Tmp = remainder of K^-1
+    transpose_f32(st, Y, N, D, D, w.B1, N);                                      // B1 = Y^T [D,N]
+    tf32_split_lo(h, st, w.B1, D, N, N, w.B2);
+    trc = tf32_gemm_launch(h, st, D, N, N, 1.0f, w.B1, w.B2, N, w.Li, w.Tmp, N, 0.0f, w.B3, N, 0, 0);        // B3 = (K^-1 Y)^T
+    if (trc) return set_err(h, DB_ERR_CUDA, "tf32 K^-1 Y product failed (%d)", trc);
+    transpose_f32(st, w.B3, D, N, N, w.Av, D);                                   // Av = A = K^-1 Y [N,D]
+    dot_sum_kernel<<<h->num_sms * 4, 256, 0, st>>>(Y, w.Av, nd, &w.acc->ssq);    // |L^-1 Y|^2 = sum Y o A
+    if (want_grad) {
+      tf32_split_lo(h, st, w.Av, N, D, D, w.S);                                  // S buffer = remainder of A
+      trc = tf32_gemm_launch(h, st, N, N, D, -0.5f, w.Av, w.S, D, w.Av, w.S, D, 0.0f, w.K, N, 1, 0);         // K buffer = -0.5 A A^T (lower)
+      if (trc) return set_err(h, DB_ERR_CUDA, "tf32 A A^T product failed (%d)", trc);
+      cudaMemsetAsync(w.dXacc, 0, sizeof(float) * (size_t)N * Q, st);
+      const int tiles = (N + TileLarge::BM - 1) / TileLarge::BM;
+      gp_contract_mem_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(w.Li, w.K, N, Q, D, X, w.hyp, w.dXacc, w.acc);
+      dot_sum_kernel<<<h->num_sms * 4, 256, 0, st>>>(w.Av, w.Av, nd, frob + 1);   // |A|_F^2
+      gp_fix_trace_kernel<<<1, 1, 0, st>>>(w.acc, frob, w.hyp, D);
+    }
+  } else {
   if ((rc = run_trmm<0>(h, st, w.Li, N, Y, D, D, w.S, D, &w.acc->ssq))) return rc;
   if (want_grad) {
     if ((rc = run_trmm<1>(h, st, w.Li, N, w.S, D, D, w.Av, D, nullptr))) return rc;
     cudaMemsetAsync(w.dXacc, 0, sizeof(float) * (size_t)N * Q, st);
     const int tiles = (N + TileLarge::BM - 1) / TileLarge::BM;
     gp_grad_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(w.Li, N, w.Av, D, X, N, Q, D, w.hyp, w.dXacc, w.acc);
+  }
   }
   gp_finalize_kernel<<<(N * Q + 255) / 256, 256, 0, st>>>(w.acc, w.hyp, hyp_opt, flags, N, Q, D, x_prior_weight, include_const,
                                                        want_grad, X, w.dXacc, dX, out_scalars);

@@ -225,7 +225,7 @@ def test_full_size_n5000_properties():
     assert torch.equal(K, K.t())                                              # symmetric, exact
     Lt = torch.tril(Lf).double()
     resid = (Lt @ Lt.t() - K.double()).abs().max() / K.double().abs().max()   # torch fp64 only as the checker
-    assert float(resid) < 2e-6
+    assert float(resid) < 5e-6            # fp32 factor; the wide trailing updates run as 3xTF32 tensor-core GEMMs
     S = ops.trsm_lower(Lf, Y.clone())
     assert float((Lt @ S.double() - Y.double()).abs().max()) < 5e-4
     np.testing.assert_allclose(float(scal[2]), float((S.double() ** 2).sum()), rtol=1e-5)
@@ -284,3 +284,28 @@ def test_latent_search_loss_and_gradient(gp_golden):
     assert table[0][1] <= start + 1e-6
     with open(path, 'rb') as f:
         assert len(pickle.load(f)) == 2
+
+
+@pytest.mark.parametrize('N,D', [(1024, 64), (1540, 128)])
+def test_tensor_core_gp_path_vs_oracle(N, D):
+    """N >= 512 with N, D multiples of 4 takes the 3xTF32 tcgen05 path (Cholesky trailing updates, K^-1, K^-1 Y,
+    A A^T): loss, log-determinant and every gradient against the fp64 oracle."""
+    from deepbelief_b200 import ops
+    rs = np.random.RandomState(N)
+    X = rs.normal(size=(N, 2)) * 1.5
+    Y = rs.normal(size=(N, D))
+    Y -= Y.mean(axis=0, keepdims=True)
+    oa, og_, on = np.log(np.expm1(1.3)), np.log(np.expm1(0.8)), np.log(np.expm1(0.7))
+    orc = ogp.GPLVMOracle(Y, X, opt_alpha=oa, opt_gamma=og_, opt_noise=on)
+    plan = ops.GplvmPlan(N, 2, D)
+    Lf = torch.zeros(N, N, device='cuda')
+    scal, dX, info = plan.evaluate(_cu(X), _cu(Y), _cu([oa, og_, on]), 7, jitter=1e-6, L_out=Lf)
+    assert int(info.item()) == 0
+    loss, logdet, ssq, Lref, _ = orc.loss()
+    w_dX, w_da, w_dg, w_dn = orc.grad()
+    np.testing.assert_allclose(float(scal[0]), float(loss), rtol=LOSS_RTOL)
+    np.testing.assert_allclose(float(scal[1]), float(logdet), rtol=LOSS_RTOL)
+    np.testing.assert_allclose(float(scal[2]), float(ssq), rtol=LOSS_RTOL)
+    assert _normrel(np.tril(_np(Lf)), Lref) < 1e-5
+    assert _normrel(_np(dX), w_dX) < GRAD_NORMREL
+    np.testing.assert_allclose(_np(scal[3:6]), [w_da, w_dg, w_dn], rtol=3e-4)
