@@ -6,12 +6,13 @@
 // Every operand is used as x = hi + lo with hi = tf32(x) (the tensor core reads the top 19 bits of the fp32 word
 // in shared memory: no conversion pass) and lo = x - hi precomputed once per operand (db_tf32_split_lo); the three
 // products hi*hi + lo*hi + hi*lo accumulate into one TMEM tile, which restores fp32-level accuracy (~2^-21).
-// The tensor core adds into the fp32 accumulator with truncation, so K is cut into chunks of 128 columns; the
-// partial tiles are summed by the epilogue threads in registers, in fp32 round-to-nearest (deterministic).
+// The tensor core adds into the fp32 accumulator with truncation, so K is cut into chunks of 128 columns for the
+// hi*hi product (its own accumulator; the corrections use a second one); the partial tiles are summed by the
+// epilogue threads in registers, in fp32 round-to-nearest (deterministic).
 //
 // Same persistent, warp-specialised structure as gemm_tc.cu: warp 0 TMA producer (4 tensor maps, 128B swizzle,
-// 64B swizzle, 6-stage ring of 32 KB), warp 1 tcgen05.mma kind::tf32 128x128x8, warp 2 TMEM allocator (4 accumulator
-// stages), warps 4-7 epilogue.
+// 64B swizzle, 6-stage ring of 32 KB), warp 1 tcgen05.mma kind::tf32 128x128x8, warp 2 TMEM allocator (2 main + 2
+// correction accumulator stages), warps 4-7 epilogue.
 // Output orientation: TMEM lanes = rows of Y (= columns of C), so a warp writes 32 consecutive floats of a row of C.
 #include "context.h"
 #include "ptx.cuh"
@@ -31,10 +32,17 @@ constexpr int STAGES = 6;         // 6 x 32 KB in flight
 constexpr int A_BYTES = BM * BK * 4;    // 16 KB
 constexpr int B_BYTES = BN * BK * 4;    // 32 KB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // hi + lo of both operands: 96 KB
-constexpr int ACC_STAGES = 4;
-constexpr int TMEM_COLS = ACC_STAGES * BN;
+constexpr int ACC_STAGES = 2;     // main accumulators (hi*hi), flushed every K_CHUNK columns
+constexpr int CORR_STAGES = 2;    // correction accumulators (lo*hi + hi*lo), flushed once per tile
+constexpr int TMEM_COLS = (ACC_STAGES + CORR_STAGES) * BN;
 constexpr int THREADS = 256;
-constexpr int K_CHUNK = 128;      // 16 MMA k-steps x 3 products = 48 truncating accumulator adds per chunk
+// The tensor core adds into its fp32 accumulator with truncation toward zero: every add shrinks the partial sum by
+// ~half an ulp, a systematic relative bias of ~T * 2^-24 after T adds (measured: 2.4e-6 at T = 48). The hi*hi products
+// therefore get their own accumulator, flushed every 128 columns (T = 16); the two correction products are 2^-11
+// smaller, so their accumulator can run over the whole K range of a tile. Measured on tr G of the N=1500 GPLVM test (a
+// 89x cancelling difference, scripts/diag_trace.py): chunk 32 / 64 / 128 / 512 / 2048 -> 2.5e-4 / 1.8e-4 / 1.3e-4 /
+// 4.4e-4 / 8.4e-4 relative (one shared accumulator at 128: 5.0e-4).
+constexpr int K_CHUNK = 128;
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
 
 struct Tf32Params {
@@ -69,7 +77,9 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tm_y_hi, const __grid_con
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = tfull_bar + ACC_STAGES;
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tempty_bar + ACC_STAGES);
+  uint64_t* cfull_bar = tempty_bar + ACC_STAGES;
+  uint64_t* cempty_bar = cfull_bar + CORR_STAGES;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(cempty_bar + CORR_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (p.N + BM - 1) / BM;     // along columns of C
@@ -85,6 +95,7 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tm_y_hi, const __grid_con
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < ACC_STAGES; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 128); }
+    for (int a = 0; a < CORR_STAGES; ++a) { ptx::mbar_init(&cfull_bar[a], 1); ptx::mbar_init(&cempty_bar[a], 128); }
     ptx::fence_barrier_init();
   }
   if (warp == 2) { ptx::tmem_alloc(tmem_base_smem, TMEM_COLS); ptx::tmem_relinquish(); }
@@ -122,9 +133,14 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tm_y_hi, const __grid_con
       constexpr uint32_t idesc = ptx::umma_idesc(/*TF32*/ 2, BM, BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      int cacc = 0; uint32_t cacc_phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         if (skipped(t)) continue;
-        for (int kb_begin = tile_kb0(t); kb_begin < num_kb; kb_begin += kb_per_chunk) {
+        const int kb_first = tile_kb0(t);
+        if (kb_first >= num_kb) continue;
+        const uint32_t tmem_c = tmem_base + (uint32_t)((ACC_STAGES + cacc) * BN);
+        if (p.passes == 3) { ptx::mbar_wait(&cempty_bar[cacc], cacc_phase ^ 1); ptx::tc_fence_after(); }
+        for (int kb_begin = kb_first; kb_begin < num_kb; kb_begin += kb_per_chunk) {
           const int kb_end = min(num_kb, kb_begin + kb_per_chunk);
           ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
           ptx::tc_fence_after();
@@ -140,8 +156,8 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tm_y_hi, const __grid_con
               const uint64_t koff = (uint64_t)((k * UK * 4) >> 4);
               ptx::mma_tf32_ss(tmem_d, d_yhi + koff, d_xhi + koff, idesc, (kb != kb_begin || k != 0) ? 1u : 0u);
               if (p.passes == 3) {
-                ptx::mma_tf32_ss(tmem_d, d_ylo + koff, d_xhi + koff, idesc, 1u);
-                ptx::mma_tf32_ss(tmem_d, d_yhi + koff, d_xlo + koff, idesc, 1u);
+                ptx::mma_tf32_ss(tmem_c, d_ylo + koff, d_xhi + koff, idesc, (kb != kb_first || k != 0) ? 1u : 0u);
+                ptx::mma_tf32_ss(tmem_c, d_yhi + koff, d_xlo + koff, idesc, 1u);
               }
             }
             ptx::mma_commit(&empty_bar[stage]);
@@ -150,6 +166,10 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tm_y_hi, const __grid_con
           ptx::mma_commit(&tfull_bar[acc]);
           if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
+        if (p.passes == 3) {
+          ptx::mma_commit(&cfull_bar[cacc]);
+          if (++cacc == CORR_STAGES) { cacc = 0; cacc_phase ^= 1; }
+        }
       }
     }
   } else if (warp >= 4) {
@@ -157,6 +177,7 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tm_y_hi, const __grid_con
     // 128 rows), so the truncating tensor-core accumulator never sees more than K_CHUNK columns; one write at the end.
     const int quarter = warp & 3;
     int acc = 0; uint32_t acc_phase = 0;
+    int cacc = 0; uint32_t cacc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       if (skipped(t)) continue;
       const int col = tile_m0(t) + quarter * 32 + lane;       // column of C handled by this thread
@@ -165,7 +186,8 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tm_y_hi, const __grid_con
       float sum[BN];
 #pragma unroll
       for (int j = 0; j < BN; ++j) sum[j] = 0.0f;
-      for (int kb_begin = tile_kb0(t); kb_begin < num_kb; kb_begin += kb_per_chunk) {
+      const int kb_first = tile_kb0(t);
+      for (int kb_begin = kb_first; kb_begin < num_kb; kb_begin += kb_per_chunk) {
         ptx::mbar_wait(&tfull_bar[acc], acc_phase);
         ptx::tc_fence_after();
         const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
@@ -180,6 +202,22 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tm_y_hi, const __grid_con
         ptx::tc_fence_before();
         ptx::mbar_arrive(&tempty_bar[acc]);
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+      if (p.passes == 3 && kb_first < num_kb) {
+        ptx::mbar_wait(&cfull_bar[cacc], cacc_phase);
+        ptx::tc_fence_after();
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((ACC_STAGES + cacc) * BN);
+#pragma unroll
+        for (int chunk = 0; chunk < BN / 32; ++chunk) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(taddr0 + (uint32_t)(chunk * 32), r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[chunk * 32 + j] += __uint_as_float(r[j]);
+        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&cempty_bar[cacc]);
+        if (++cacc == CORR_STAGES) { cacc = 0; cacc_phase ^= 1; }
       }
       if (col_ok) {
 #pragma unroll

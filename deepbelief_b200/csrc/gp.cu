@@ -16,6 +16,8 @@
 #include "simt_gemm.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tf32.cuh"
+#include <cstdlib>
+#include <mutex>
 
 namespace db {
 namespace {
@@ -231,6 +233,268 @@ __global__ void __launch_bounds__(NB) potrf_colblock_kernel(float* __restrict__ 
     } else {
       for (int k = 0; k < nb; ++k) dst[k] = P[k][r];
     }
+  }
+}
+
+// ---- one launch per column block: fused look-ahead update + factorisation + panel solve + narrow update ----------
+// Launch for column block j of the outer block [b0, b1), jprev = j - 64 (or -1 when j == b0):
+//   strip CTAs  (blockIdx.x <  strips): 64-row strip s of the rows from j down (s = 0 is the diagonal block). Each one
+//     applies panel jprev (rank-64) to its own block of column block j and (redundantly) to the diagonal block,
+//     factorises the diagonal block (redundantly: identical arithmetic in every CTA, no inter-CTA dependency) and
+//     solves its strip; the solve of column chunk c runs on two other warps as soon as chunk c of L is final.
+//   update CTAs (blockIdx.x >= strips): one 64x64 tile each of the columns [j + 64, b1): tile -= panel jprev product,
+//     i.e. the right-looking narrow update of the PREVIOUS panel rides along in the same launch, off the critical path.
+// Column block cb has therefore received panel p < cb - 64 from the launch of step p + 64 and panel cb - 64 in its
+// own launch. 256 threads; shared blocks are stored transposed, T[k][r] = element (row r, column k).
+constexpr int STEP_THREADS = 256;
+constexpr int STEP_SMEM = 4 * NB * LT_PITCH * (int)sizeof(float);
+
+// 64x64 block at (row0, col0) -> T[k][r]; rows >= rows_valid / columns >= cols_valid read as zero
+__device__ __forceinline__ void load_block_T(float (*T)[LT_PITCH], const float* __restrict__ A, int lda, int row0, int col0,
+                                             int rows_valid, int cols_valid, bool vec) {
+  const int r = threadIdx.x & 63, q = threadIdx.x >> 6;
+  const float* src = A + (size_t)(row0 + r) * lda + col0;
+  float4 v[4];
+  if (vec && cols_valid == NB) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      v[i] = r < rows_valid ? __ldcg(reinterpret_cast<const float4*>(src) + q + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = 4 * (q + 4 * i);
+      v[i].x = (r < rows_valid && c + 0 < cols_valid) ? __ldcg(src + c + 0) : 0.0f;
+      v[i].y = (r < rows_valid && c + 1 < cols_valid) ? __ldcg(src + c + 1) : 0.0f;
+      v[i].z = (r < rows_valid && c + 2 < cols_valid) ? __ldcg(src + c + 2) : 0.0f;
+      v[i].w = (r < rows_valid && c + 3 < cols_valid) ? __ldcg(src + c + 3) : 0.0f;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = 4 * (q + 4 * i);
+    T[c][r] = v[i].x; T[c + 1][r] = v[i].y; T[c + 2][r] = v[i].z; T[c + 3][r] = v[i].w;
+  }
+}
+
+// acc[i][jj] = sum_k Rows[k][4 tr + i] * Cols[k][4 tc + jj]
+__device__ __forceinline__ void block_product(float (&acc)[4][4], const float (*Rows)[LT_PITCH], const float (*Cols)[LT_PITCH],
+                                              int tr, int tc) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) acc[i][jj] = 0.0f;
+#pragma unroll 8
+  for (int k = 0; k < NB; ++k) {
+    const float4 a = *reinterpret_cast<const float4*>(&Rows[k][4 * tr]);
+    const float4 b = *reinterpret_cast<const float4*>(&Cols[k][4 * tc]);
+    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fmaf(av[i], bv[jj], acc[i][jj]);
+  }
+}
+
+// Cholesky of the 8x8 diagonal sub-block at c0 entirely in registers (every calling thread redundantly):
+// l[i][m] (m <= i) and inv[i] = 1 / l[i][i]. rsqrt + one Newton step: no shared-memory round trip per column.
+__device__ __forceinline__ void factor8(const float (*blk)[8], float (&l)[8][8], float (&inv)[8], int c0, int& fail) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 lo = *reinterpret_cast<const float4*>(&blk[i][0]);
+    const float4 hi = *reinterpret_cast<const float4*>(&blk[i][4]);
+    l[i][0] = lo.x; l[i][1] = lo.y; l[i][2] = lo.z; l[i][3] = lo.w;
+    l[i][4] = hi.x; l[i][5] = hi.y; l[i][6] = hi.z; l[i][7] = hi.w;
+  }
+#pragma unroll
+  for (int jc = 0; jc < 8; ++jc) {
+    float s = l[jc][jc];
+#pragma unroll
+    for (int m = 0; m < jc; ++m) s = fmaf(-l[jc][m], l[jc][m], s);
+    if (!(s > 0.0f) && fail == 0) fail = c0 + jc + 1;
+    float y = rsqrtf(s);
+    y = y * fmaf(-0.5f * s * y, y, 1.5f);
+    inv[jc] = y;
+    l[jc][jc] = s * y;
+#pragma unroll
+    for (int i = jc + 1; i < 8; ++i) {
+      float t = l[i][jc];
+#pragma unroll
+      for (int m = 0; m < jc; ++m) t = fmaf(-l[i][m], l[jc][m], t);
+      l[i][jc] = t * y;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(STEP_THREADS) potrf_step_kernel(float* __restrict__ A, int lda, int N, int j, int jprev, int b1,
+                                                                  int strips, int* __restrict__ info) {
+  extern __shared__ __align__(16) float step_smem[];
+  float (*S)[LT_PITCH] = reinterpret_cast<float (*)[LT_PITCH]>(step_smem);                        // diagonal block
+  float (*P)[LT_PITCH] = reinterpret_cast<float (*)[LT_PITCH]>(step_smem + NB * LT_PITCH);        // own block
+  float (*Dp)[LT_PITCH] = reinterpret_cast<float (*)[LT_PITCH]>(step_smem + 2 * NB * LT_PITCH);   // previous panel, diagonal rows
+  float (*Op)[LT_PITCH] = reinterpret_cast<float (*)[LT_PITCH]>(step_smem + 3 * NB * LT_PITCH);   // previous panel, own rows
+  __shared__ float dinv[NB];
+  __shared__ __align__(16) float dblk[2][8][8];   // updated 8x8 diagonal sub-block, double-buffered by chunk parity
+  __shared__ int s_fail;
+  __shared__ volatile int s_progress;
+  const int t = threadIdx.x;
+  const bool vec = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  const int tc = t & 15, tr = t >> 4;
+
+  if ((int)blockIdx.x >= strips) {
+    // ---------------- update CTA: tile (row strip, column block cb) of [j + 64, b1) -= panel jprev ----------------
+    const int ncb = (b1 - (j + NB) + NB - 1) / NB;
+    const int u = blockIdx.x - strips;
+    const int cb = j + NB + (u % ncb) * NB;
+    const int row0 = j + NB + (u / ncb) * NB;
+    if (row0 < cb || row0 >= N) return;
+    load_block_T(Op, A, lda, row0, jprev, N - row0, NB, vec);
+    load_block_T(Dp, A, lda, cb, jprev, N - cb, NB, vec);
+    __syncthreads();
+    float acc[4][4];
+    block_product(acc, Op, Dp, tr, tc);
+    const int ncols = min(NB, b1 - cb);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = row0 + 4 * tr + i;
+      if (row >= N) continue;
+      float* dst = A + (size_t)row * lda + cb + 4 * tc;
+      if (vec && ncols == NB && row0 > cb) {
+        float4 x = *reinterpret_cast<float4*>(dst);
+        x.x -= acc[i][0]; x.y -= acc[i][1]; x.z -= acc[i][2]; x.w -= acc[i][3];
+        *reinterpret_cast<float4*>(dst) = x;
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int col = cb + 4 * tc + jj;
+          if (4 * tc + jj < ncols && col <= row) dst[jj] -= acc[i][jj];
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------- strip CTA ----------------
+  const int strip = blockIdx.x;
+  const int nb = min(NB, N - j);
+  const int row0 = j + strip * NB;
+  load_block_T(S, A, lda, j, j, nb, nb, vec);
+  if (strip > 0) load_block_T(P, A, lda, row0, j, N - row0, nb, vec);
+  if (jprev >= 0) {
+    load_block_T(Dp, A, lda, j, jprev, nb, NB, vec);
+    if (strip > 0) load_block_T(Op, A, lda, row0, jprev, N - row0, NB, vec);
+  }
+  if (t == 0) { s_fail = 0; s_progress = 0; }
+  __syncthreads();
+  if (jprev >= 0) {
+    float acc[4][4];
+    block_product(acc, Dp, Dp, tr, tc);
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      float4* d = reinterpret_cast<float4*>(&S[4 * tc + jj][4 * tr]);
+      float4 x = *d;
+      x.x -= acc[0][jj]; x.y -= acc[1][jj]; x.z -= acc[2][jj]; x.w -= acc[3][jj];
+      *d = x;
+    }
+    if (strip > 0) {
+      block_product(acc, Op, Dp, tr, tc);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        float4* d = reinterpret_cast<float4*>(&P[4 * tc + jj][4 * tr]);
+        float4 x = *d;
+        x.x -= acc[0][jj]; x.y -= acc[1][jj]; x.z -= acc[2][jj]; x.w -= acc[3][jj];
+        *d = x;
+      }
+    }
+    __syncthreads();
+  }
+  if (nb < NB) {   // identity padding of the ragged last block
+    for (int e = t; e < NB * NB; e += STEP_THREADS) {
+      const int k = e >> 6, r = e & 63;
+      if (r >= nb || k >= nb) S[k][r] = (k == r) ? 1.0f : 0.0f;
+    }
+    __syncthreads();
+  }
+
+  if (t < NB) {
+    // ---- factorisation of the diagonal block: thread r owns row r; left-looking in chunks of 8 columns ----
+    const int r = t;
+    int fail = 0;
+    for (int c0 = 0; c0 < NB; c0 += 8) {
+      float acc[8];
+      chunk_update(acc, S, S, c0, r);
+      const int par = (c0 >> 3) & 1;
+      if (r >= c0 && r < c0 + 8) {     // rows of the 8x8 diagonal sub-block publish their updated values
+        *reinterpret_cast<float4*>(&dblk[par][r - c0][0]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(&dblk[par][r - c0][4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
+      asm volatile("bar.sync 1, 64;" ::: "memory");
+      float l[8][8], inv[8];
+      factor8(dblk[par], l, inv, c0, fail);
+      float x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float s = acc[i];
+#pragma unroll
+        for (int m = 0; m < i; ++m) s = fmaf(-x[m], l[i][m], s);
+        x[i] = s * inv[i];
+        S[c0 + i][r] = (c0 + i <= r) ? x[i] : 0.0f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (r == c0 + i) dinv[r] = inv[i];
+      asm volatile("bar.sync 1, 64;" ::: "memory");     // chunk c0 of L is final
+      if (r == 0) { __threadfence_block(); s_progress = c0 / 8 + 1; }
+    }
+    if (r == 0 && fail) s_fail = fail;
+  } else if (t < 2 * NB && strip > 0) {
+    // ---- panel rows: x L^T = a by forward substitution, chunk c as soon as chunk c of L is final ----
+    const int r = t - NB;
+    for (int c0 = 0; c0 < NB; c0 += 8) {
+      while (s_progress < c0 / 8) { }
+      __threadfence_block();
+      float acc[8];
+      chunk_update(acc, P, S, c0, r);
+      while (s_progress < c0 / 8 + 1) { }
+      __threadfence_block();
+      float l[8][8];
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const float4 lo = *reinterpret_cast<const float4*>(&S[c0 + m][c0]);
+        const float4 hi = *reinterpret_cast<const float4*>(&S[c0 + m][c0 + 4]);
+        l[0][m] = lo.x; l[1][m] = lo.y; l[2][m] = lo.z; l[3][m] = lo.w;
+        l[4][m] = hi.x; l[5][m] = hi.y; l[6][m] = hi.z; l[7][m] = hi.w;
+      }
+      float x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float s = acc[i];
+#pragma unroll
+        for (int m = 0; m < i; ++m) s = fmaf(-x[m], l[i][m], s);
+        x[i] = s * dinv[c0 + i];
+        P[c0 + i][r] = x[i];
+      }
+    }
+  }
+  __syncthreads();
+  // ---- write back: the diagonal CTA stores L_jj (lower part), the others their solved strip ----
+  {
+    const int r = t & 63, q = t >> 6;
+    float (*Src)[LT_PITCH] = strip == 0 ? S : P;
+    const int row = row0 + r;
+    if (row < N) {
+      float* dst = A + (size_t)row * lda + j;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = 4 * (q + 4 * i);
+        if (strip > 0 && vec && nb == NB) {
+          *reinterpret_cast<float4*>(dst + c) = make_float4(Src[c][r], Src[c + 1][r], Src[c + 2][r], Src[c + 3][r]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (c + e < nb && (strip > 0 || c + e <= r)) dst[c + e] = Src[c + e][r];
+        }
+      }
+    }
+    if (strip == 0 && t == 0 && s_fail && s_fail <= nb) atomicCAS(info, 0, j + s_fail);
   }
 }
 
@@ -698,15 +962,29 @@ int run_gram(db_handle_t h, cudaStream_t st, const float* X, const float* Y, int
 // and the operands are TMA-addressable, the wide K = 512 trailing updates run on the tensor cores (3xTF32).
 int run_potrf(db_handle_t h, cudaStream_t st, float* A, int lda, int N, int* info, float* lo_buf = nullptr) {
   cudaMemsetAsync(info, 0, sizeof(int), st);
+  static const bool legacy = [] { const char* e = getenv("DB_POTRF_LEGACY"); return e && e[0] == '1'; }();
+  static std::once_flag smem_once;
+  std::call_once(smem_once, [] { cudaFuncSetAttribute(potrf_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEP_SMEM); });
   for (int b0 = 0; b0 < N; b0 += OB) {
     const int b1 = b0 + OB < N ? b0 + OB : N;
     for (int j = b0; j < b1; j += NB) {
-      potrf_colblock_kernel<<<(N - j + NB - 1) / NB, NB, 0, st>>>(A, lda, N, j, info);
-      const int j2 = j + NB;
-      if (j2 < b1) {     // narrow update: remaining columns of this outer block, all rows below
-        dim3 grid((b1 - j2 + TileLarge::BN - 1) / TileLarge::BN, (N - j2 + TileLarge::BM - 1) / TileLarge::BM);
-        syrk_block_kernel<<<grid, 256, 0, st>>>(A, lda, N, j2, j2, b1, j, j2);
+      if (legacy) {
+        potrf_colblock_kernel<<<(N - j + NB - 1) / NB, NB, 0, st>>>(A, lda, N, j, info);
+        const int j2 = j + NB;
+        if (j2 < b1) {     // narrow update: remaining columns of this outer block, all rows below
+          dim3 grid((b1 - j2 + TileLarge::BN - 1) / TileLarge::BN, (N - j2 + TileLarge::BM - 1) / TileLarge::BM);
+          syrk_block_kernel<<<grid, 256, 0, st>>>(A, lda, N, j2, j2, b1, j, j2);
+        }
+        continue;
       }
+      const int strips = (N - j + NB - 1) / NB;
+      const int jprev = j > b0 ? j - NB : -1;
+      int updates = 0;
+      if (jprev >= 0 && j + NB < b1) {
+        const int ncb = (b1 - (j + NB) + NB - 1) / NB;
+        updates = ncb * ((N - (j + NB) + NB - 1) / NB);
+      }
+      potrf_step_kernel<<<strips + updates, STEP_THREADS, STEP_SMEM, st>>>(A, lda, N, j, jprev, b1, strips, info);
     }
     if (b1 < N) {        // wide update of everything right of the outer block, K = b1 - b0
       const int rows = N - b1;
@@ -793,6 +1071,8 @@ GplvmWorkspace gplvm_workspace(void* ws, int N, int Q, int D) {
 }
 
 inline bool gp_use_tensor_path(db_handle_t h, int N, int D) {
+  static const bool simt_only = [] { const char* e = getenv("DB_GP_SIMT"); return e && e[0] == '1'; }();   // diagnostics
+  if (simt_only) return false;
   return h->cc_major >= 10 && N >= 512 && (N % 4) == 0 && (D % 4) == 0 && D >= 32;
 }
 

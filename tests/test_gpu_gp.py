@@ -52,7 +52,7 @@ def test_se_kernel_reference_unit_tests_and_goldens(gp_golden):
     assert float(fixed.alpha) == 1.0 and float(fixed.gamma) == 1.0       # gplvm.py:31-32,41-42
 
 
-@pytest.mark.parametrize('N', [5, 64, 130, 700])
+@pytest.mark.parametrize('N', [5, 64, 130, 700, 1101])
 def test_cholesky_and_triangular_solves(N):
     from deepbelief_b200 import ops
     rs = np.random.RandomState(N)
