@@ -43,16 +43,24 @@ constexpr int THREADS = 256;
 // 89x cancelling difference, scripts/diag_trace.py): chunk 32 / 64 / 128 / 512 / 2048 -> 2.5e-4 / 1.8e-4 / 1.3e-4 /
 // 4.4e-4 / 8.4e-4 relative (one shared accumulator at 128: 5.0e-4).
 constexpr int K_CHUNK = 128;
+// Each truncating add loses on average ~0.7 ulp-halves of the running sum; the epilogue multiplies every hi*hi chunk by
+// 1 + kShrinkPerAdd * adds to remove the expected shrink. Calibrated on random data (scripts/check_tf32.py: max error vs
+// fp64 at K = 4096 is 7.9e-7 / 4.9e-7 / 3.8e-7 / 6.0e-7 for 0 / 2e-8 / 4e-8 / 6e-8; scripts/diag_trace.py: tr G error
+// 2.6e-4 / 1.5e-4 / 1.5e-4 / 2.6e-5).
+constexpr float kShrinkPerAdd = 5e-8f;
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
 
 struct Tf32Params {
   int M, N, K;            // C is [M, N]; X [M, K], Y [N, K]
   float alpha, beta;
   float* C; int ldc;
+  float* C_lo;            // optional: tf32 remainder of the written values (same layout), so C can be the next operand
   int lower_only;         // 1: only elements with col <= row are produced (tiles above the diagonal are skipped)
   int kb_chunk;           // k-blocks (of BK columns) accumulated in TMEM before the partial tile is added to C
   int tri_k;              // 1: X[i,k] = 0 for k < i and Y[j,k] = 0 for k < j (transposed triangular factors): k starts at max(i0, j0)
+                          // 2: only X is upper triangular (X[i,k] = 0 for k < i): k starts at the first row of the tile
   int passes;             // 3 (debug: DB_TF32_PASSES=1 issues only the hi*hi product)
+  float debias;           // 1 + expected relative shrink of one K chunk of the truncating hi*hi accumulator
 };
 
 // K-major operand tile written by TMA with SWIZZLE_64B: rows are 64 B apart, 8-row groups 512 B apart
@@ -108,7 +116,7 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tm_y_hi, const __grid_con
   auto tile_m0 = [&](int t) { return (t % tiles_m) * BM; };
   auto tile_n0 = [&](int t) { return (t / tiles_m) * BN; };
   auto skipped = [&](int t) { return p.lower_only && tile_m0(t) > tile_n0(t) + BN - 1; };   // min col > max row
-  auto tile_kb0 = [&](int t) { return p.tri_k ? max(tile_m0(t), tile_n0(t)) / BK : 0; };
+  auto tile_kb0 = [&](int t) { return p.tri_k == 1 ? max(tile_m0(t), tile_n0(t)) / BK : (p.tri_k == 2 ? tile_n0(t) / BK : 0); };
 
   if (warp == 0) {
     if (lane == 0) {
@@ -197,7 +205,7 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tm_y_hi, const __grid_con
           ptx::tmem_ld_32x32(taddr0 + (uint32_t)(chunk * 32), r);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sum[chunk * 32 + j] += __uint_as_float(r[j]);
+          for (int j = 0; j < 32; ++j) sum[chunk * 32 + j] = fmaf(__uint_as_float(r[j]), p.debias, sum[chunk * 32 + j]);
         }
         ptx::tc_fence_before();
         ptx::mbar_arrive(&tempty_bar[acc]);
@@ -236,8 +244,10 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tm_y_hi, const __grid_con
           for (int j = 0; j < 32; ++j) {
             const int row = row0 + g * 32 + j;
             if (row < p.M && (!p.lower_only || col <= row)) {
-              const float v = p.alpha * sum[g * 32 + j];
-              p.C[(size_t)row * p.ldc + col] = p.beta != 0.0f ? fmaf(p.beta, oldv[j], v) : v;
+              float v = p.alpha * sum[g * 32 + j];
+              if (p.beta != 0.0f) v = fmaf(p.beta, oldv[j], v);
+              p.C[(size_t)row * p.ldc + col] = v;
+              if (p.C_lo != nullptr) p.C_lo[(size_t)row * p.ldc + col] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
             }
           }
         }
@@ -313,7 +323,7 @@ bool tf32_gemm_supported(int M, int N, int K, const float* X, const float* X_lo,
 
 // C[M,N] = alpha X Y^T + beta C; returns 0, or a negative code when the shape cannot use TMA (caller falls back to SIMT)
 int tf32_gemm_launch(db_handle_t h, cudaStream_t st, int M, int N, int K, float alpha, const float* X, const float* X_lo, int ldx,
-                     const float* Y, const float* Y_lo, int ldy, float beta, float* C, int ldc, int lower_only, int tri_k) {
+                     const float* Y, const float* Y_lo, int ldy, float beta, float* C, int ldc, int lower_only, int tri_k, float* C_lo) {
   if (!tf32_gemm_supported(M, N, K, X, X_lo, ldx, Y, Y_lo, ldy)) return -1000;
   CUtensorMap tyh, tyl, txh, txl;
   if (!make_tmap_f32(&tyh, Y, N, K, ldy, BM) || !make_tmap_f32(&tyl, Y_lo, N, K, ldy, BM) ||
@@ -325,12 +335,19 @@ int tf32_gemm_launch(db_handle_t h, cudaStream_t st, int M, int N, int K, float 
   });
   if (attr_err != cudaSuccess) return (int)attr_err;
   Tf32Params p;
-  p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.C = C; p.ldc = ldc; p.lower_only = lower_only;
+  p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.C = C; p.ldc = ldc; p.C_lo = C_lo; p.lower_only = lower_only;
   int kchunk = K_CHUNK;
   { const char* e = getenv("DB_TF32_KCHUNK"); if (e) kchunk = atoi(e) > 0 ? atoi(e) : K_CHUNK; }
   p.kb_chunk = kchunk / BK < 1 ? 1 : kchunk / BK;
   p.tri_k = tri_k;
   { const char* e = getenv("DB_TF32_PASSES"); p.passes = (e && e[0] == '1') ? 1 : 3; }
+  {
+    // every accumulator add truncates toward zero: expected relative loss per add ~ kShrinkPerAdd of the running sum
+    float per_add = kShrinkPerAdd;
+    const char* e = getenv("DB_TF32_DEBIAS"); if (e) per_add = (float)atof(e);
+    const int adds = p.kb_chunk * (BK / UK);
+    p.debias = 1.0f + per_add * (float)adds;
+  }
   const int tiles = ((N + BM - 1) / BM) * ((M + BN - 1) / BN);
   const int ctas = tc_ctas(h);
   const int grid = tiles < ctas ? tiles : ctas;
@@ -364,7 +381,7 @@ extern "C" int db_gemm_tf32x3_nt(db_handle_t h, db_stream_t stream, int M, int N
                                  int ldc, int lower_only) {
   DB_REQUIRE(h, X && X_lo && Y && Y_lo && C && M > 0 && N > 0 && K > 0 && ldc >= N, "null operand or bad shape");
   if (h->cc_major < 10) return set_err(h, DB_ERR_UNSUPPORTED, "tcgen05 path needs sm_100a (device is sm_%d%d)", h->cc_major, h->cc_minor);
-  const int rc = tf32_gemm_launch(h, (cudaStream_t)stream, M, N, K, alpha, X, X_lo, ldx, Y, Y_lo, ldy, beta, C, ldc, lower_only, 0);
+  const int rc = tf32_gemm_launch(h, (cudaStream_t)stream, M, N, K, alpha, X, X_lo, ldx, Y, Y_lo, ldy, beta, C, ldc, lower_only, 0, nullptr);
   if (rc == -1000) return set_err(h, DB_ERR_UNSUPPORTED, "3xTF32 GEMM needs 16-byte aligned operands and leading dimensions that are multiples of 4");
   if (rc) return set_err(h, DB_ERR_CUDA, "tf32x3 GEMM launch failed (%d)", rc);
   return DB_OK;

@@ -990,10 +990,11 @@ int run_potrf(db_handle_t h, cudaStream_t st, float* A, int lda, int N, int* inf
       const int rows = N - b1;
       const float* P = A + (size_t)b1 * lda + b0;
       bool done = false;
-      if (lo_buf != nullptr && h->cc_major >= 10 && rows >= 512) {
+      if (lo_buf != nullptr && h->cc_major >= 10) {
+        // the remainders are kept for every panel: the tensor-core triangular inverse reads them again (run_trinv_tc)
         float* Plo = lo_buf + (size_t)b1 * lda + b0;
-        if (tf32_gemm_supported(rows, rows, b1 - b0, P, Plo, lda, P, Plo, lda)) {
-          tf32_split_lo(h, st, P, rows, b1 - b0, lda, Plo);
+        tf32_split_lo(h, st, P, rows, b1 - b0, lda, Plo);
+        if (rows >= 512 && tf32_gemm_supported(rows, rows, b1 - b0, P, Plo, lda, P, Plo, lda)) {
           const int rc = tf32_gemm_launch(h, st, rows, rows, b1 - b0, -1.0f, P, Plo, lda, P, Plo, lda, 1.0f,
                                           A + (size_t)b1 * lda + b1, lda, /*lower_only=*/1, /*tri_k=*/0);
           if (rc != 0 && rc != -1000) return set_err(h, DB_ERR_CUDA, "tf32 trailing update failed (%d)", rc);
@@ -1028,6 +1029,77 @@ int run_trinv(db_handle_t h, cudaStream_t st, const float* L, int ldl, int N, fl
   return check_launch(h, "trinv_lower");
 }
 
+// ---- tensor-core triangular inverse (N >= 512, N % 4 == 0) ---------------------------------------------------------
+// Produces U = Linv^T (upper triangular, what the K^-1 = U U^T product reads) and its tf32 remainder, block row by block
+// row of Linv with 512-wide blocks B_j (P_j = 512 j rows precede block j):
+//   Linv_jj           : SIMT recursive doubling inside every diagonal block (levels 64, 128, 256), written to Li
+//   WT  = U[:P_j,:P_j] L[B_j,:P_j]^T               (3xTF32 GEMM; X upper triangular -> K loop clipped per tile)
+//   U[:P_j, B_j] = -WT Linv_jj^T                    (3xTF32 GEMM, remainder written by the epilogue)
+// L and the remainders of its panels (left behind by run_potrf in lo_buf) are the only inputs; the diagonal blocks of the
+// L buffer are overwritten with the remainders of Linv_jj (L_jj is dead once Linv_jj exists).
+// grid (16, 16, nblk): 32x32 tiles of diagonal block z
+__global__ void __launch_bounds__(256) trinv_diag_finish_kernel(const float* __restrict__ Li, int N, float* __restrict__ LiLo,
+                                                                float* __restrict__ U, float* __restrict__ Ulo) {
+  __shared__ float tile[32][33];
+  const int b0 = blockIdx.z * OB;
+  const int nb = min(OB, N - b0);
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  if (r0 >= nb || c0 >= nb) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + 8 * i, c = c0 + tx;
+    float v = 0.0f;
+    if (r < nb && c < nb) {
+      const size_t idx = (size_t)(b0 + r) * N + b0 + c;
+      v = c <= r ? Li[idx] : 0.0f;
+      LiLo[idx] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    }
+    tile[ty + 8 * i][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, r = r0 + tx;           // element (c, r) of U_jj = element (r, c) of Linv_jj
+    if (c < nb && r < nb) {
+      const float v = tile[tx][ty + 8 * i];
+      const size_t idx = (size_t)(b0 + c) * N + b0 + r;
+      U[idx] = v;
+      Ulo[idx] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    }
+  }
+}
+
+int run_trinv_tc(db_handle_t h, cudaStream_t st, float* L, const float* Llo, int N, float* Li, float* U, float* Ulo, float* WT,
+                 float* WTlo) {
+  const int nblk = (N + OB - 1) / OB;
+  cudaMemsetAsync(U, 0, sizeof(float) * (size_t)N * N, st);
+  cudaMemsetAsync(Ulo, 0, sizeof(float) * (size_t)N * N, st);
+  for (int j = 0; j < nblk; ++j) {      // the upper part of the diagonal blocks of Li is read by the GEMMs: zero it
+    const int b0 = j * OB, nb = std::min(OB, N - b0);
+    cudaMemset2DAsync(Li + (size_t)b0 * N + b0, sizeof(float) * (size_t)N, 0, sizeof(float) * (size_t)nb, nb, st);
+  }
+  trinv_diag_kernel<<<(N + NB - 1) / NB, 64, 0, st>>>(L, N, N, Li, N);
+  for (int s = NB; s < OB && s < N; s *= 2) {
+    const int pairs = (N + 2 * s - 1) / (2 * s);
+    dim3 grid((s + TileSmall::BN - 1) / TileSmall::BN, (s + TileSmall::BM - 1) / TileSmall::BM, pairs);
+    // scratch T of the SIMT levels: the lower part of U's diagonal blocks (overwritten by trinv_diag_finish_kernel)
+    trinv_level_kernel<0, TileSmall><<<grid, 256, 0, st>>>(L, N, N, s, Li, N, U, N);
+    trinv_level_kernel<1, TileSmall><<<grid, 256, 0, st>>>(L, N, N, s, Li, N, U, N);
+  }
+  trinv_diag_finish_kernel<<<dim3(OB / 32, OB / 32, nblk), 256, 0, st>>>(Li, N, L, U, Ulo);
+  for (int j = 1; j < nblk; ++j) {
+    const int P = j * OB, nb = std::min(OB, N - P);
+    int rc = tf32_gemm_launch(h, st, P, nb, P, 1.0f, U, Ulo, N, L + (size_t)P * N, Llo + (size_t)P * N, N, 0.0f, WT, OB,
+                              /*lower_only=*/0, /*tri_k=*/2, WTlo);
+    if (rc) return set_err(h, DB_ERR_CUDA, "tf32 triangular inverse (block row product) failed (%d)", rc);
+    rc = tf32_gemm_launch(h, st, P, nb, nb, -1.0f, WT, WTlo, OB, Li + (size_t)P * N + P, L + (size_t)P * N + P, N, 0.0f,
+                          U + P, N, 0, 0, Ulo + P);
+    if (rc) return set_err(h, DB_ERR_CUDA, "tf32 triangular inverse (block column) failed (%d)", rc);
+  }
+  return check_launch(h, "trinv_tc");
+}
+
 template <int TRANS>
 int run_trmm(db_handle_t h, cudaStream_t st, const float* Li, int N, const float* B, int ldb, int nrhs, float* out, int ldo,
              float* ssq) {
@@ -1046,7 +1118,7 @@ int run_trmm(db_handle_t h, cudaStream_t st, const float* Li, int N, const float
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 struct GplvmWorkspace {
-  float *K, *Li, *Tmp, *S, *Av, *B1, *B2, *B3, *dXacc, *hyp;
+  float *K, *Li, *Tmp, *S, *Av, *B1, *B2, *B3, *dXacc, *hyp, *Ulo, *WT, *WTlo;
   GpAccum* acc;
   size_t bytes;
 };
@@ -1066,6 +1138,9 @@ GplvmWorkspace gplvm_workspace(void* ws, int N, int Q, int D) {
   w.dXacc = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)N * Q);
   w.hyp = reinterpret_cast<float*>(p); p += 256;
   w.acc = reinterpret_cast<GpAccum*>(p); p += 256;
+  w.Ulo = reinterpret_cast<float*>(p); p += nn;       // tensor-core path: tf32 remainder of Linv^T
+  w.WT = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)N * OB);     // block-row products of run_trinv_tc
+  w.WTlo = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)N * OB);
   w.bytes = (size_t)(p - p0);
   return w;
 }
@@ -1406,16 +1481,16 @@ extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float*
   if ((rc = run_potrf(h, st, w.K, N, N, info, tc ? w.Li : nullptr))) return rc;
   if (L_out) cudaMemcpyAsync(L_out, w.K, sizeof(float) * (size_t)N * N, cudaMemcpyDeviceToDevice, st);
   logdet_xsq_kernel<<<1, 1024, 0, st>>>(w.K, N, N, X, N * Q, w.acc);
-  if ((rc = run_trinv(h, st, w.K, N, N, w.Li, w.Tmp))) return rc;
+  if (!tc && (rc = run_trinv(h, st, w.K, N, N, w.Li, w.Tmp))) return rc;
   if (tc) {
     const size_t nn = (size_t)N * N, nd = (size_t)N * D;
     const int tiles32 = (N + 31) / 32;
     float* frob = reinterpret_cast<float*>(w.acc) + 16;                          // two scratch floats behind the accumulators
     cudaMemsetAsync(frob, 0, 2 * sizeof(float), st);
-    transpose_f32(st, w.Li, N, N, N, w.Tmp, N);                                  // Tmp = Linv^T (upper triangular)
-    dot_sum_kernel<<<h->num_sms * 4, 256, 0, st>>>(w.Li, w.Li, nn, frob);         // |Linv|_F^2 = tr K^-1
-    tf32_split_lo(h, st, w.Tmp, N, N, N, w.K);                                   // K buffer = its tf32 remainder
-    int trc = tf32_gemm_launch(h, st, N, N, N, 1.0f, w.Tmp, w.K, N, w.Tmp, w.K, N, 0.0f, w.Li, N, 1, 1);   // Li = K^-1 (lower)
+    // Tmp = Linv^T (upper triangular), Ulo = its tf32 remainder
+    if ((rc = run_trinv_tc(h, st, w.K, w.Li, N, w.Li, w.Tmp, w.Ulo, w.WT, w.WTlo))) return rc;
+    dot_sum_kernel<<<h->num_sms * 4, 256, 0, st>>>(w.Tmp, w.Tmp, nn, frob);       // |Linv|_F^2 = tr K^-1
+    int trc = tf32_gemm_launch(h, st, N, N, N, 1.0f, w.Tmp, w.Ulo, N, w.Tmp, w.Ulo, N, 0.0f, w.Li, N, 1, 1);   // Li = K^-1 (lower)
     if (trc) return set_err(h, DB_ERR_CUDA, "tf32 K^-1 product failed (%d)", trc);
     mirror_lower_kernel<<<dim3(tiles32, tiles32), 256, 0, st>>>(w.Li, N);
     kinv_diag_kernel<<<(N + 7) / 8, 256, 0, st>>>(w.Tmp, N, w.Li);
