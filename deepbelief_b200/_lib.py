@@ -132,7 +132,7 @@ def lib():
     global _lib
     with _lock:
         if _lib is None:
-            path = _build.LIB_PATH
+            path = os.environ.get('DEEPBELIEF_B200_LIB') or _build.LIB_PATH     # override: instrumented debug builds
             if not os.path.exists(path):
                 path = _build.build()
             try:

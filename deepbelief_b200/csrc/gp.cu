@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, 
 // per outer block a wide SYRK (K = 512) updates the rest of the matrix — so the strictly sequential part is
 // ~80 short launches and the bulk of the N^3/3 flops runs as deep-K GEMM tiles.
 constexpr int OB = 512;
-constexpr int LT_PITCH = 68;   // floats; rows 16-byte aligned for float4 broadcast reads
+constexpr int LT_PITCH = 72;   // floats; rows 16-byte aligned for float4 reads, and (8 t + g) mod 32 is a bijection for the
+                               // mma.sync fragment reads (t = lane & 3, g = lane >> 2): conflict-free
 
 // Shared-memory layout of a 64x64 block: S[c][r] holds element (row r, column c), so "my row's element c" is
 // lane-contiguous (thread r reads S[c][r]) and "row c2's element c" (S[c][c2]) is a broadcast; 8 consecutive
@@ -237,61 +238,141 @@ __global__ void __launch_bounds__(NB) potrf_colblock_kernel(float* __restrict__ 
 }
 
 // ---- one launch per column block: fused look-ahead update + factorisation + panel solve + narrow update ----------
-// Launch for column block j of the outer block [b0, b1), jprev = j - 64 (or -1 when j == b0):
+// Launch for column block j of the outer block [b0, b1), jprev = j - 64 (or -1 when j == b0). Every CTA owns its SM
+// (STEP_SMEM below); 256 threads.
 //   strip CTAs  (blockIdx.x <  strips): 64-row strip s of the rows from j down (s = 0 is the diagonal block). Each one
-//     applies panel jprev (rank-64) to its own block of column block j and (redundantly) to the diagonal block,
-//     factorises the diagonal block (redundantly: identical arithmetic in every CTA, no inter-CTA dependency) and
-//     solves its strip; the solve of column chunk c runs on two other warps as soon as chunk c of L is final.
-//   update CTAs (blockIdx.x >= strips): one 64x64 tile each of the columns [j + 64, b1): tile -= panel jprev product,
-//     i.e. the right-looking narrow update of the PREVIOUS panel rides along in the same launch, off the critical path.
+//     applies panel jprev (rank-64) to its own block of column block j and (redundantly) to the diagonal block - one
+//     128 x 64 x 64 product on the tensor cores (mma.sync, 3xTF32) -, factorises the diagonal block (redundantly:
+//     identical arithmetic in every CTA, no inter-CTA dependency; warps 0-1, 8x8 sub-blocks in registers) and solves its
+//     strip (warps 2-3, chunk c as soon as chunk c of L is final).
+//   update CTAs (blockIdx.x >= strips, at most one per remaining SM): loop over the 128 x 64 tiles of the columns
+//     [j + 64, b1): tile -= panel jprev product, i.e. the right-looking narrow update of the PREVIOUS panel rides along
+//     in the same launch, off the critical path (next tile's operands in flight during the product).
 // Column block cb has therefore received panel p < cb - 64 from the launch of step p + 64 and panel cb - 64 in its
-// own launch. 256 threads; shared blocks are stored transposed, T[k][r] = element (row r, column k).
+// own launch. S and P (factorisation operands) are stored transposed, T[k][r] = element (row r, column k); the blocks
+// of the previous panel (tensor-core operands only) row-major.
+// Measured per step at N = 5000 (clock64 in strip CTA 1, build with -DDB_POTRF_TIMING and run with DB_POTRF_DEBUG=1):
+// load 6.5k, update 4.9k, factorisation 13.3k cycles; 16 us per step.
 constexpr int STEP_THREADS = 256;
-constexpr int STEP_SMEM = 4 * NB * LT_PITCH * (int)sizeof(float);
+// Requested dynamic shared memory: more than half an SM, so every CTA of a step launch owns its SM. The strip CTAs are
+// the critical path; measured with two update CTAs sharing their SM, their load and product phases ran 3x slower.
+constexpr int STEP_SMEM = 200 * 1024;
+constexpr int BLK_FLOATS = NB * LT_PITCH;
 
-// 64x64 block at (row0, col0) -> T[k][r]; rows >= rows_valid / columns >= cols_valid read as zero
-__device__ __forceinline__ void load_block_T(float (*T)[LT_PITCH], const float* __restrict__ A, int lda, int row0, int col0,
-                                             int rows_valid, int cols_valid, bool vec) {
-  const int r = threadIdx.x & 63, q = threadIdx.x >> 6;
+// 64x64 block at (row0, col0): global -> registers (PER float4 per thread of a GROUP-thread group), then registers ->
+// T[k][r]. Split in two so a CTA can issue the loads of all its blocks before the first shared store.
+// Rows >= rows_valid / columns >= cols_valid read as zero.
+template <int GROUP>
+struct BlockRegs { float4 v[1024 / GROUP]; };
+template <int GROUP>
+__device__ __forceinline__ void block_load(BlockRegs<GROUP>& b, int tid, const float* __restrict__ A, int lda, int row0, int col0,
+                                           int rows_valid, int cols_valid, bool vec) {
+  constexpr int PER = 1024 / GROUP, QS = GROUP / 64;
+  const int r = tid & 63, q = tid >> 6;
   const float* src = A + (size_t)(row0 + r) * lda + col0;
-  float4 v[4];
   if (vec && cols_valid == NB) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      v[i] = r < rows_valid ? __ldcg(reinterpret_cast<const float4*>(src) + q + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < PER; ++i)
+      b.v[i] = r < rows_valid ? __ldcg(reinterpret_cast<const float4*>(src) + q + QS * i) : make_float4(0.f, 0.f, 0.f, 0.f);
   } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int c = 4 * (q + 4 * i);
-      v[i].x = (r < rows_valid && c + 0 < cols_valid) ? __ldcg(src + c + 0) : 0.0f;
-      v[i].y = (r < rows_valid && c + 1 < cols_valid) ? __ldcg(src + c + 1) : 0.0f;
-      v[i].z = (r < rows_valid && c + 2 < cols_valid) ? __ldcg(src + c + 2) : 0.0f;
-      v[i].w = (r < rows_valid && c + 3 < cols_valid) ? __ldcg(src + c + 3) : 0.0f;
+    for (int i = 0; i < PER; ++i) {
+      const int c = 4 * (q + QS * i);
+      b.v[i].x = (r < rows_valid && c + 0 < cols_valid) ? __ldcg(src + c + 0) : 0.0f;
+      b.v[i].y = (r < rows_valid && c + 1 < cols_valid) ? __ldcg(src + c + 1) : 0.0f;
+      b.v[i].z = (r < rows_valid && c + 2 < cols_valid) ? __ldcg(src + c + 2) : 0.0f;
+      b.v[i].w = (r < rows_valid && c + 3 < cols_valid) ? __ldcg(src + c + 3) : 0.0f;
     }
   }
+}
+template <int GROUP>
+__device__ __forceinline__ void block_store_T(float (*T)[LT_PITCH], int tid, const BlockRegs<GROUP>& b) {
+  constexpr int PER = 1024 / GROUP, QS = GROUP / 64;
+  const int r = tid & 63, q = tid >> 6;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int c = 4 * (q + 4 * i);
-    T[c][r] = v[i].x; T[c + 1][r] = v[i].y; T[c + 2][r] = v[i].z; T[c + 3][r] = v[i].w;
+  for (int i = 0; i < PER; ++i) {
+    const int c = 4 * (q + QS * i);
+    T[c][r] = b.v[i].x; T[c + 1][r] = b.v[i].y; T[c + 2][r] = b.v[i].z; T[c + 3][r] = b.v[i].w;
   }
 }
 
-// acc[i][jj] = sum_k Rows[k][4 tr + i] * Cols[k][4 tc + jj]
-__device__ __forceinline__ void block_product(float (&acc)[4][4], const float (*Rows)[LT_PITCH], const float (*Cols)[LT_PITCH],
-                                              int tr, int tc) {
+// Operands that only feed the tensor-core products stay row-major, R[row][k] with pitch RM_PITCH (conflict-free
+// fragment reads: (4 g + t) mod 32 is a bijection), and are loaded coalesced: 16 threads read one 256-byte row. A
+// warp-wide float4 load that touches 32 different rows (the transposed loader above) costs ~66 cycles of L1 replays.
+constexpr int RM_PITCH = 68;
+struct BlockRegsRM { float4 v[4]; };
+__device__ __forceinline__ void block_load_rm(BlockRegsRM& b, int tid, const float* __restrict__ A, int lda, int row0, int col0,
+                                              int rows_valid, bool vec) {
+  const int c4 = tid & 15, rr = tid >> 4;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 4; ++i) {
+    const int r = rr + 16 * i;
+    const float* src = A + (size_t)(row0 + r) * lda + col0 + 4 * c4;
+    if (r < rows_valid) {
+      if (vec) b.v[i] = __ldcg(reinterpret_cast<const float4*>(src));
+      else b.v[i] = make_float4(__ldcg(src), __ldcg(src + 1), __ldcg(src + 2), __ldcg(src + 3));
+    } else {
+      b.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+__device__ __forceinline__ void block_store_rm(float* R, int tid, const BlockRegsRM& b) {
+  const int c4 = tid & 15, rr = tid >> 4;
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) acc[i][jj] = 0.0f;
-#pragma unroll 8
-  for (int k = 0; k < NB; ++k) {
-    const float4 a = *reinterpret_cast<const float4*>(&Rows[k][4 * tr]);
-    const float4 b = *reinterpret_cast<const float4*>(&Cols[k][4 * tc]);
-    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(R + (rr + 16 * i) * RM_PITCH + 4 * c4) = b.v[i];
+}
+
+// 128 x 64 product on the tensor cores (mma.sync m16n8k8, 3xTF32: hi*hi + lo*hi + hi*lo, fp32 accumulate), 8 warps:
+//   D[m][n] = sum_k R[m][k] * C[n][k],  R = [R0 (rows 0..63); R1 (rows 64..127)], operand blocks row-major (RM_PITCH).
+// Warp w owns rows 16 w .. 16 w + 15 (w < 4: R0, else R1) and all 64 columns: acc[nt] is the m16n8 fragment of column
+// tile nt (c0: (g, 2t), c1: (g, 2t+1), c2: (g+8, 2t), c3: (g+8, 2t+1); g = lane >> 2, t = lane & 3).
+// Measured on the critical path of the Cholesky step: the same product with fp32 FMAs (8x8 register tiles, 4 warps)
+// took 14.5k cycles per step.
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_block_product(float (&acc)[8][4], const float* Rows, int m0, const float* C, int lane) {
+  const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+  for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fmaf(av[i], bv[jj], acc[i][jj]);
+    for (int e = 0; e < 4; ++e) acc[nt][e] = 0.0f;
+  const float* ra = Rows + (m0 + g) * RM_PITCH + t;
+  const float* rb = C + g * RM_PITCH + t;
+#pragma unroll 2
+  for (int k0 = 0; k0 < NB; k0 += 8) {
+    uint32_t ahi[4], alo[4];
+    split_tf32(ra[k0], ahi[0], alo[0]);
+    split_tf32(ra[8 * RM_PITCH + k0], ahi[1], alo[1]);
+    split_tf32(ra[k0 + 4], ahi[2], alo[2]);
+    split_tf32(ra[8 * RM_PITCH + k0 + 4], ahi[3], alo[3]);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      uint32_t bhi[2], blo[2];
+      split_tf32(rb[8 * nt * RM_PITCH + k0], bhi[0], blo[0]);
+      split_tf32(rb[8 * nt * RM_PITCH + k0 + 4], bhi[1], blo[1]);
+      mma_tf32(acc[nt], alo, bhi);
+      mma_tf32(acc[nt], ahi, blo);
+      mma_tf32(acc[nt], ahi, bhi);
+    }
+  }
+}
+// T[col][row] -= acc for the fragment rows m0 + g (+8) and columns 8 nt + 2t (+1)
+__device__ __forceinline__ void mma_subtract_T(float (*T)[LT_PITCH], const float (&acc)[8][4], int m0, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int c = 8 * nt + 2 * t;
+    T[c][m0 + g] -= acc[nt][0];
+    T[c + 1][m0 + g] -= acc[nt][1];
+    T[c][m0 + g + 8] -= acc[nt][2];
+    T[c + 1][m0 + g + 8] -= acc[nt][3];
   }
 }
 
@@ -325,50 +406,106 @@ __device__ __forceinline__ void factor8(const float (*blk)[8], float (&l)[8][8],
   }
 }
 
+#ifdef DB_POTRF_TIMING
+#define STEP_MARK(slot, cond) do { if (dbg != nullptr && blockIdx.x == 1 && (cond)) dbg[slot] = clock64(); } while (0)
+#else
+#define STEP_MARK(slot, cond) do { } while (0)
+#endif
 __global__ void __launch_bounds__(STEP_THREADS) potrf_step_kernel(float* __restrict__ A, int lda, int N, int j, int jprev, int b1,
-                                                                  int strips, int* __restrict__ info) {
+                                                                  int strips, int* __restrict__ info, long long* __restrict__ dbg) {
   extern __shared__ __align__(16) float step_smem[];
   float (*S)[LT_PITCH] = reinterpret_cast<float (*)[LT_PITCH]>(step_smem);                        // diagonal block
   float (*P)[LT_PITCH] = reinterpret_cast<float (*)[LT_PITCH]>(step_smem + NB * LT_PITCH);        // own block
-  float (*Dp)[LT_PITCH] = reinterpret_cast<float (*)[LT_PITCH]>(step_smem + 2 * NB * LT_PITCH);   // previous panel, diagonal rows
-  float (*Op)[LT_PITCH] = reinterpret_cast<float (*)[LT_PITCH]>(step_smem + 3 * NB * LT_PITCH);   // previous panel, own rows
   __shared__ float dinv[NB];
   __shared__ __align__(16) float dblk[2][8][8];   // updated 8x8 diagonal sub-block, double-buffered by chunk parity
   __shared__ int s_fail;
   __shared__ volatile int s_progress;
   const int t = threadIdx.x;
   const bool vec = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
-  const int tc = t & 15, tr = t >> 4;
+  // Programmatic dependent launch: the next step's CTAs may be scheduled as soon as every CTA of this launch has
+  // started; they block here until the previous launch has completed and its writes are visible.
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  STEP_MARK(0, t == 0);
 
   if ((int)blockIdx.x >= strips) {
-    // ---------------- update CTA: tile (row strip, column block cb) of [j + 64, b1) -= panel jprev ----------------
+    // ---------------- update CTA: loops over the (128 rows x 64 columns) tiles of the columns [j + 64, b1);
+    // tile -= (128 rows of panel jprev) (rows cb.. of panel jprev)^T, next tile's operands in flight meanwhile ----------------
+    float* O0 = step_smem;
+    float* O1 = step_smem + BLK_FLOATS;
+    float* Dq = step_smem + 2 * BLK_FLOATS;
+    const int warp = t >> 5, lane = t & 31;
     const int ncb = (b1 - (j + NB) + NB - 1) / NB;
-    const int u = blockIdx.x - strips;
-    const int cb = j + NB + (u % ncb) * NB;
-    const int row0 = j + NB + (u / ncb) * NB;
-    if (row0 < cb || row0 >= N) return;
-    load_block_T(Op, A, lda, row0, jprev, N - row0, NB, vec);
-    load_block_T(Dp, A, lda, cb, jprev, N - cb, NB, vec);
-    __syncthreads();
-    float acc[4][4];
-    block_product(acc, Op, Dp, tr, tc);
-    const int ncols = min(NB, b1 - cb);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int row = row0 + 4 * tr + i;
-      if (row >= N) continue;
-      float* dst = A + (size_t)row * lda + cb + 4 * tc;
-      if (vec && ncols == NB && row0 > cb) {
-        float4 x = *reinterpret_cast<float4*>(dst);
-        x.x -= acc[i][0]; x.y -= acc[i][1]; x.z -= acc[i][2]; x.w -= acc[i][3];
-        *reinterpret_cast<float4*>(dst) = x;
-      } else {
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int col = cb + 4 * tc + jj;
-          if (4 * tc + jj < ncols && col <= row) dst[jj] -= acc[i][jj];
-        }
+    const int stride = (int)gridDim.x - strips;
+    // tile index -> (column block cb, first row); column block cb has ceil((N - cb) / 128) tiles starting at row cb
+    auto locate = [&](int tile, int& cb, int& row0) -> bool {
+      int rem = tile;
+      cb = j + NB;
+      for (int cbi = 0; cbi < ncb; ++cbi, cb += NB) {
+        const int nt = (N - cb + 2 * NB - 1) / (2 * NB);
+        if (rem < nt) { row0 = cb + rem * 2 * NB; return true; }
+        rem -= nt;
       }
+      return false;
+    };
+    int tile = (int)blockIdx.x - strips;
+    int cb, row0;
+    bool have = locate(tile, cb, row0);
+    BlockRegsRM r0, r1, rd;
+    if (have) {
+      block_load_rm(r0, t, A, lda, row0, jprev, N - row0, vec);
+      block_load_rm(r1, t, A, lda, row0 + NB, jprev, N - row0 - NB, vec);
+      block_load_rm(rd, t, A, lda, cb, jprev, N - cb, vec);
+    }
+    while (have) {
+      __syncthreads();                                      // the previous tile's fragment reads are done
+      block_store_rm(O0, t, r0);
+      block_store_rm(O1, t, r1);
+      block_store_rm(Dq, t, rd);
+      __syncthreads();
+      const int cur_cb = cb, cur_row0 = row0;
+      tile += stride;
+      have = locate(tile, cb, row0);                        // CTA-uniform
+      if (have) {
+        block_load_rm(r0, t, A, lda, row0, jprev, N - row0, vec);
+        block_load_rm(r1, t, A, lda, row0 + NB, jprev, N - row0 - NB, vec);
+        block_load_rm(rd, t, A, lda, cb, jprev, N - cb, vec);
+      }
+      const int m0 = 16 * (warp & 3);
+      const int ncols = min(NB, b1 - cur_cb);
+      const int g = lane >> 2, tq = lane & 3;
+      // the tile's current values: every load is issued before the product and long before the first store (a
+      // load -> subtract -> store chain per element would serialise 16 L2 round trips)
+      float2 cur[2][8];
+      const int rbase = cur_row0 + (warp < 4 ? 0 : NB) + m0 + g;
+      const bool fast = vec && ncols == NB && cur_cb + NB - 1 <= rbase && rbase + 8 < N;     // both rows inside, below the diagonal
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const int row = rbase + 8 * hh, c = 8 * nt + 2 * tq;
+          const float* src = A + (size_t)row * lda + cur_cb + c;
+          if (fast) cur[hh][nt] = __ldcg(reinterpret_cast<const float2*>(src));
+          else {
+            cur[hh][nt].x = (row < N && c < ncols && cur_cb + c <= row) ? __ldcg(src) : 0.0f;
+            cur[hh][nt].y = (row < N && c + 1 < ncols && cur_cb + c + 1 <= row) ? __ldcg(src + 1) : 0.0f;
+          }
+        }
+      float acc[8][4];
+      mma_block_product(acc, warp < 4 ? O0 : O1, m0, Dq, lane);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const int row = rbase + 8 * hh, c = 8 * nt + 2 * tq;
+          float* dst = A + (size_t)row * lda + cur_cb + c;
+          const float vx = cur[hh][nt].x - acc[nt][2 * hh], vy = cur[hh][nt].y - acc[nt][2 * hh + 1];
+          if (fast) *reinterpret_cast<float2*>(dst) = make_float2(vx, vy);
+          else {
+            if (row < N && c < ncols && cur_cb + c <= row) dst[0] = vx;
+            if (row < N && c + 1 < ncols && cur_cb + c + 1 <= row) dst[1] = vy;
+          }
+        }
     }
     return;
   }
@@ -377,32 +514,35 @@ __global__ void __launch_bounds__(STEP_THREADS) potrf_step_kernel(float* __restr
   const int strip = blockIdx.x;
   const int nb = min(NB, N - j);
   const int row0 = j + strip * NB;
-  load_block_T(S, A, lda, j, j, nb, nb, vec);
-  if (strip > 0) load_block_T(P, A, lda, row0, j, N - row0, nb, vec);
-  if (jprev >= 0) {
-    load_block_T(Dp, A, lda, j, jprev, nb, NB, vec);
-    if (strip > 0) load_block_T(Op, A, lda, row0, jprev, N - row0, NB, vec);
+  float* Dp = step_smem + 2 * BLK_FLOATS;      // previous panel, diagonal rows (row-major, tensor-core operand)
+  float* Op = step_smem + 3 * BLK_FLOATS;      // previous panel, own rows
+  {
+    BlockRegs<256> rs, rp;
+    BlockRegsRM rdp, rop;
+    block_load<256>(rs, t, A, lda, j, j, nb, nb, vec);
+    if (strip > 0) block_load<256>(rp, t, A, lda, row0, j, N - row0, nb, vec);
+    if (jprev >= 0) {
+      block_load_rm(rdp, t, A, lda, j, jprev, nb, vec);
+      if (strip > 0) block_load_rm(rop, t, A, lda, row0, jprev, N - row0, vec);
+    }
+    block_store_T<256>(S, t, rs);
+    if (strip > 0) block_store_T<256>(P, t, rp);
+    if (jprev >= 0) {
+      block_store_rm(Dp, t, rdp);
+      if (strip > 0) block_store_rm(Op, t, rop);
+    }
   }
   if (t == 0) { s_fail = 0; s_progress = 0; }
   __syncthreads();
+  STEP_MARK(1, t == 0);
   if (jprev >= 0) {
-    float acc[4][4];
-    block_product(acc, Dp, Dp, tr, tc);
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      float4* d = reinterpret_cast<float4*>(&S[4 * tc + jj][4 * tr]);
-      float4 x = *d;
-      x.x -= acc[0][jj]; x.y -= acc[1][jj]; x.z -= acc[2][jj]; x.w -= acc[3][jj];
-      *d = x;
-    }
-    if (strip > 0) {
-      block_product(acc, Op, Dp, tr, tc);
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        float4* d = reinterpret_cast<float4*>(&P[4 * tc + jj][4 * tr]);
-        float4 x = *d;
-        x.x -= acc[0][jj]; x.y -= acc[1][jj]; x.z -= acc[2][jj]; x.w -= acc[3][jj];
-        *d = x;
+    {     // S -= Dp Dp^T (warps 0-3) and P -= Op Dp^T (warps 4-7) on the tensor cores
+      const int warp = t >> 5, lane = t & 31;
+      const int m0 = 16 * (warp & 3);
+      if (warp < 4 || strip > 0) {
+        float acc[8][4];
+        mma_block_product(acc, warp < 4 ? Dp : Op, m0, Dp, lane);
+        mma_subtract_T(warp < 4 ? S : P, acc, m0, lane);
       }
     }
     __syncthreads();
@@ -415,6 +555,7 @@ __global__ void __launch_bounds__(STEP_THREADS) potrf_step_kernel(float* __restr
     __syncthreads();
   }
 
+  STEP_MARK(2, t == 0);
   if (t < NB) {
     // ---- factorisation of the diagonal block: thread r owns row r; left-looking in chunks of 8 columns ----
     const int r = t;
@@ -445,6 +586,7 @@ __global__ void __launch_bounds__(STEP_THREADS) potrf_step_kernel(float* __restr
       if (r == 0) { __threadfence_block(); s_progress = c0 / 8 + 1; }
     }
     if (r == 0 && fail) s_fail = fail;
+    STEP_MARK(3, t == 0);
   } else if (t < 2 * NB && strip > 0) {
     // ---- panel rows: x L^T = a by forward substitution, chunk c as soon as chunk c of L is final ----
     const int r = t - NB;
@@ -474,6 +616,7 @@ __global__ void __launch_bounds__(STEP_THREADS) potrf_step_kernel(float* __restr
       }
     }
   }
+  STEP_MARK(4, t == NB);
   __syncthreads();
   // ---- write back: the diagonal CTA stores L_jj (lower part), the others their solved strip ----
   {
@@ -496,6 +639,10 @@ __global__ void __launch_bounds__(STEP_THREADS) potrf_step_kernel(float* __restr
     }
     if (strip == 0 && t == 0 && s_fail && s_fail <= nb) atomicCAS(info, 0, j + s_fail);
   }
+  STEP_MARK(5, t == 0);
+#ifdef DB_POTRF_TIMING
+  if (dbg != nullptr && blockIdx.x == 1 && t == 0) { unsigned long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); dbg[6] = (long long)g; }
+#endif
 }
 
 // C[i, jc] -= sum_{k in [k0,k1)} A[i,k] A[jc,k]  for i in [i0,N), jc in [j0,j1), jc <= i   (lower part only)
@@ -963,11 +1110,13 @@ int run_gram(db_handle_t h, cudaStream_t st, const float* X, const float* Y, int
 int run_potrf(db_handle_t h, cudaStream_t st, float* A, int lda, int N, int* info, float* lo_buf = nullptr) {
   cudaMemsetAsync(info, 0, sizeof(int), st);
   static const bool legacy = [] { const char* e = getenv("DB_POTRF_LEGACY"); return e && e[0] == '1'; }();
+  static const bool pdl = [] { const char* e = getenv("DB_POTRF_PDL"); return !(e && e[0] == '0'); }();
   static std::once_flag smem_once;
   std::call_once(smem_once, [] { cudaFuncSetAttribute(potrf_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEP_SMEM); });
   for (int b0 = 0; b0 < N; b0 += OB) {
     const int b1 = b0 + OB < N ? b0 + OB : N;
-    for (int j = b0; j < b1; j += NB) {
+    static const bool skip_steps = [] { const char* e = getenv("DB_POTRF_SKIP_STEPS"); return e && e[0] == '1'; }();   // timing diagnostics only
+    for (int j = b0; j < b1 && !skip_steps; j += NB) {
       if (legacy) {
         potrf_colblock_kernel<<<(N - j + NB - 1) / NB, NB, 0, st>>>(A, lda, N, j, info);
         const int j2 = j + NB;
@@ -979,14 +1128,49 @@ int run_potrf(db_handle_t h, cudaStream_t st, float* A, int lda, int N, int* inf
       }
       const int strips = (N - j + NB - 1) / NB;
       const int jprev = j > b0 ? j - NB : -1;
-      int updates = 0;
+      int updates = 0;                 // update CTAs: each loops over 128x64 tiles of the columns [j + 64, b1)
       if (jprev >= 0 && j + NB < b1) {
-        const int ncb = (b1 - (j + NB) + NB - 1) / NB;
-        updates = ncb * ((N - (j + NB) + NB - 1) / NB);
+        int tiles = 0;
+        for (int cb = j + NB; cb < b1; cb += NB) tiles += (N - cb + 2 * NB - 1) / (2 * NB);
+        const int free_sms = h->num_sms - strips;
+        updates = tiles;
+        const int cap = free_sms > 8 ? free_sms : 8;
+        if (updates > cap) updates = cap;
       }
-      potrf_step_kernel<<<strips + updates, STEP_THREADS, STEP_SMEM, st>>>(A, lda, N, j, jprev, b1, strips, info);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(strips + updates); cfg.blockDim = dim3(STEP_THREADS); cfg.dynamicSmemBytes = STEP_SMEM; cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = (pdl && strips + updates <= 2 * h->num_sms) ? 1 : 0;   // measured: slower on larger grids
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      long long* dbg = nullptr;
+#ifdef DB_POTRF_TIMING
+      static long long* dbg_buf = nullptr;
+      static int dbg_step = 0;
+      if (getenv("DB_POTRF_DEBUG")) {
+        if (!dbg_buf) { cudaMalloc(&dbg_buf, 8 * 128 * sizeof(long long)); }
+        if (j == 0) {
+          if (dbg_step > 0) {   // dump the previous factorisation
+            static long long hbuf[8 * 128];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(hbuf, dbg_buf, sizeof(hbuf), cudaMemcpyDeviceToHost);
+            for (int i = 0; i < dbg_step && i < 128; ++i) {
+              const long long* d = hbuf + 8 * i;
+              fprintf(stderr, "step %3d: load %6lld upd %6lld factor %6lld solve-end %6lld total %6lld clk | since prev end %7.2f us\n", i,
+                      d[1] - d[0], d[2] - d[1], d[3] - d[2], d[4] - d[2], d[5] - d[0], i ? (d[6] - hbuf[8 * (i - 1) + 6]) * 1e-3 : 0.0);
+            }
+          }
+          dbg_step = 0;
+          cudaMemsetAsync(dbg_buf, 0, 8 * 128 * sizeof(long long), st);
+        }
+        if (dbg_step < 128) dbg = dbg_buf + 8 * dbg_step;
+        ++dbg_step;
+      }
+#endif
+      cudaLaunchKernelEx(&cfg, potrf_step_kernel, A, lda, N, j, jprev, b1, strips, info, dbg);
     }
-    if (b1 < N) {        // wide update of everything right of the outer block, K = b1 - b0
+    static const bool skip_wide = [] { const char* e = getenv("DB_POTRF_SKIP_WIDE"); return e && e[0] == '1'; }();   // timing diagnostics only
+    if (b1 < N && !skip_wide) {        // wide update of everything right of the outer block, K = b1 - b0
       const int rows = N - b1;
       const float* P = A + (size_t)b1 * lda + b0;
       bool done = false;
