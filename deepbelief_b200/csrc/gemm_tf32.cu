@@ -112,19 +112,33 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tm_y_hi, const __grid_con
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
 
-  // tile t -> (column block of C, row block of C); row-block-major so consecutive CTAs share the X rows in L2
-  auto tile_m0 = [&](int t) { return (t % tiles_m) * BM; };
-  auto tile_n0 = [&](int t) { return (t / tiles_m) * BN; };
-  auto skipped = [&](int t) { return p.lower_only && tile_m0(t) > tile_n0(t) + BN - 1; };   // min col > max row
-  auto tile_kb0 = [&](int t) { return p.tri_k == 1 ? max(tile_m0(t), tile_n0(t)) / BK : (p.tri_k == 2 ? tile_n0(t) / BK : 0); };
+  // tile t -> (column block of C, row block of C); row-block-major so consecutive CTAs share the X rows in L2.
+  // lower_only on a square tile grid enumerates the T (T + 1) / 2 lower tiles only (row block i, column block <= i, i
+  // ascending): the CTAs get equal tile counts, and with tri_k the long-K tiles (small i) are dealt first. Measured on
+  // the K = 512 trailing update with the rectangular enumeration + skipping: SMs active 51 % of the kernel.
+  const bool tri_enum = p.lower_only && tiles_m == tiles_n;
+  const int total_tiles = tri_enum ? tiles_n * (tiles_n + 1) / 2 : num_tiles;
+  auto tile_coords = [&](int t, int& m0, int& n0) {
+    if (tri_enum) {
+      int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+      while (i * (i + 1) / 2 > t) --i;
+      while ((i + 1) * (i + 2) / 2 <= t) ++i;
+      n0 = i * BN; m0 = (t - i * (i + 1) / 2) * BM;
+    } else {
+      m0 = (t % tiles_m) * BM; n0 = (t / tiles_m) * BN;
+    }
+  };
+  auto skipped_at = [&](int m0, int n0) { return p.lower_only && m0 > n0 + BN - 1; };   // min col > max row
+  auto kb0_at = [&](int m0, int n0) { return p.tri_k == 1 ? max(m0, n0) / BK : (p.tri_k == 2 ? n0 / BK : 0); };
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        if (skipped(t)) continue;
-        const int m0 = tile_m0(t), n0 = tile_n0(t);
-        for (int kb = tile_kb0(t); kb < num_kb; ++kb) {
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int m0, n0;
+        tile_coords(t, m0, n0);
+        if (skipped_at(m0, n0)) continue;
+        for (int kb = kb0_at(m0, n0); kb < num_kb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
           ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
@@ -142,9 +156,11 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tm_y_hi, const __grid_con
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       int cacc = 0; uint32_t cacc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        if (skipped(t)) continue;
-        const int kb_first = tile_kb0(t);
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int m0, n0;
+        tile_coords(t, m0, n0);
+        if (skipped_at(m0, n0)) continue;
+        const int kb_first = kb0_at(m0, n0);
         if (kb_first >= num_kb) continue;
         const uint32_t tmem_c = tmem_base + (uint32_t)((ACC_STAGES + cacc) * BN);
         if (p.passes == 3) { ptx::mbar_wait(&cempty_bar[cacc], cacc_phase ^ 1); ptx::tc_fence_after(); }
@@ -186,15 +202,17 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tm_y_hi, const __grid_con
     const int quarter = warp & 3;
     int acc = 0; uint32_t acc_phase = 0;
     int cacc = 0; uint32_t cacc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      if (skipped(t)) continue;
-      const int col = tile_m0(t) + quarter * 32 + lane;       // column of C handled by this thread
-      const int row0 = tile_n0(t);
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int m0, n0;
+      tile_coords(t, m0, n0);
+      if (skipped_at(m0, n0)) continue;
+      const int col = m0 + quarter * 32 + lane;                // column of C handled by this thread
+      const int row0 = n0;
       const bool col_ok = col < p.N;
       float sum[BN];
 #pragma unroll
       for (int j = 0; j < BN; ++j) sum[j] = 0.0f;
-      const int kb_first = tile_kb0(t);
+      const int kb_first = kb0_at(m0, n0);
       for (int kb_begin = kb_first; kb_begin < num_kb; kb_begin += kb_per_chunk) {
         ptx::mbar_wait(&tfull_bar[acc], acc_phase);
         ptx::tc_fence_after();
@@ -227,28 +245,28 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tm_y_hi, const __grid_con
         ptx::mbar_arrive(&cempty_bar[cacc]);
         if (++cacc == CORR_STAGES) { cacc = 0; cacc_phase ^= 1; }
       }
-      if (col_ok) {
+      // rows [jlo, jhi) of this thread's column are written: inside C, and at or below the diagonal when lower_only.
+      // One pointer walks down the column; all loads of a read-modify-write group are issued before its first store.
+      const int jlo = p.lower_only ? max(0, col - row0) : 0;
+      const int jhi = col_ok ? min(BN, p.M - row0) : 0;
+      const unsigned span = jhi > jlo ? (unsigned)(jhi - jlo) : 0u;
+      float* cp = p.C + (size_t)row0 * p.ldc + col;
+      float* lp = p.C_lo ? p.C_lo + (size_t)row0 * p.ldc + col : nullptr;
 #pragma unroll
-        for (int g = 0; g < BN / 32; ++g) {
-          // all loads of a read-modify-write group are issued before its first store (the 32 row addresses cannot be
-          // proven distinct by the compiler; a load-after-store chain would serialise 32 memory latencies)
-          float oldv[32];
-          if (p.beta != 0.0f) {
+      for (int g = 0; g < BN / 16; ++g) {
+        float oldv[16];
+        if (p.beta != 0.0f) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int row = row0 + g * 32 + j;
-              oldv[j] = (row < p.M && (!p.lower_only || col <= row)) ? __ldcg(p.C + (size_t)row * p.ldc + col) : 0.0f;
-            }
-          }
+          for (int j = 0; j < 16; ++j)
+            oldv[j] = (unsigned)(g * 16 + j - jlo) < span ? __ldcg(cp + (size_t)(g * 16 + j) * p.ldc) : 0.0f;
+        }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int row = row0 + g * 32 + j;
-            if (row < p.M && (!p.lower_only || col <= row)) {
-              float v = p.alpha * sum[g * 32 + j];
-              if (p.beta != 0.0f) v = fmaf(p.beta, oldv[j], v);
-              p.C[(size_t)row * p.ldc + col] = v;
-              if (p.C_lo != nullptr) p.C_lo[(size_t)row * p.ldc + col] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-            }
+        for (int j = 0; j < 16; ++j) {
+          if ((unsigned)(g * 16 + j - jlo) < span) {
+            float v = p.alpha * sum[g * 16 + j];
+            if (p.beta != 0.0f) v = fmaf(p.beta, oldv[j], v);
+            cp[(size_t)(g * 16 + j) * p.ldc] = v;
+            if (lp != nullptr) lp[(size_t)(g * 16 + j) * p.ldc] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
           }
         }
       }
@@ -348,7 +366,8 @@ int tf32_gemm_launch(db_handle_t h, cudaStream_t st, int M, int N, int K, float 
     const int adds = p.kb_chunk * (BK / UK);
     p.debias = 1.0f + per_add * (float)adds;
   }
-  const int tiles = ((N + BM - 1) / BM) * ((M + BN - 1) / BN);
+  const int tm = (N + BM - 1) / BM, tn = (M + BN - 1) / BN;
+  const int tiles = (lower_only && tm == tn) ? tn * (tn + 1) / 2 : tm * tn;
   const int ctas = tc_ctas(h);
   const int grid = tiles < ctas ? tiles : ctas;
   tf32x3_gemm_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tyh, tyl, txh, txl, p);

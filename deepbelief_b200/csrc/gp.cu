@@ -1340,8 +1340,9 @@ inline bool gp_use_tensor_path(db_handle_t h, int N, int D) {
 // ---- tensor-core form of the LML + gradient evaluation (N >= 512, N % 4 == 0, D % 4 == 0) ---------------------------
 // K^-1 = Linv^T Linv as ONE 3xTF32 GEMM over the transposed factor (K range clipped to the non-zero part), A = K^-1 Y,
 // -0.5 A A^T, then a streaming contraction of G = (D/2) K^-1 - 0.5 A A^T with K_f. |L^-1 Y|^2 = sum Y o A.
-__global__ void __launch_bounds__(256) mirror_lower_kernel(float* __restrict__ A, int N) {
+__global__ void __launch_bounds__(256) mirror_lower_kernel(float* __restrict__ A, float* __restrict__ A2, int N) {
   __shared__ float tile[32][33];
+  __shared__ float tile2[32][33];
   if (blockIdx.x > blockIdx.y) return;                       // tile (by, bx) of the lower triangle -> (bx, by)
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -1349,12 +1350,16 @@ __global__ void __launch_bounds__(256) mirror_lower_kernel(float* __restrict__ A
   for (int i = 0; i < 4; ++i) {
     const int r = r0 + ty + 8 * i, c = c0 + tx;
     tile[ty + 8 * i][tx] = (r < N && c < N) ? A[(size_t)r * N + c] : 0.0f;
+    if (A2) tile2[ty + 8 * i][tx] = (r < N && c < N) ? A2[(size_t)r * N + c] : 0.0f;
   }
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int c = c0 + ty + 8 * i, r = r0 + tx;           // writes element (c, r) = (r, c)^T
-    if (c < N && r < N && c < r) A[(size_t)c * N + r] = tile[tx][ty + 8 * i];
+    if (c < N && r < N && c < r) {
+      A[(size_t)c * N + r] = tile[tx][ty + 8 * i];
+      if (A2) A2[(size_t)c * N + r] = tile2[tx][ty + 8 * i];
+    }
   }
 }
 // tr G = 0.5 (D |Linv|_F^2 - |A|_F^2) from two fp32 round-to-nearest reductions (scratch[0], scratch[1]) replaces the
@@ -1367,19 +1372,34 @@ __global__ void gp_fix_trace_kernel(GpAccum* acc, const float* __restrict__ scra
 }
 // Kinv[i,i] = sum_k LinvT[i,k]^2 in fp32 round-to-nearest (one warp per row): the tensor-core value of this monotone
 // sum is biased low by the truncating accumulator, and A = K^-1 Y inherits a diagonal bias one-to-one.
-__global__ void kinv_diag_kernel(const float* __restrict__ LinvT, int N, float* __restrict__ Kinv) {
+__global__ void kinv_diag_kernel(const float* __restrict__ LinvT, int N, float* __restrict__ Kinv, float* __restrict__ Kinv_lo) {
   const int i = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
   if (i >= N) return;
   const float* row = LinvT + (size_t)i * N;
   float s = 0.0f;
   for (int k = i + lane; k < N; k += 32) { const float v = __ldg(row + k); s = fmaf(v, v, s); }
   s = warp_sum(s);
-  if (lane == 0) Kinv[(size_t)i * N + i] = s;
+  if (lane == 0) {
+    Kinv[(size_t)i * N + i] = s;
+    if (Kinv_lo) Kinv_lo[(size_t)i * N + i] = s - __uint_as_float(__float_as_uint(s) & 0xffffe000u);
+  }
 }
-__global__ void dot_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) dot_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n,
+                                                      float* __restrict__ out) {
   float s = 0.0f;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    s = fmaf(__ldg(a + i), __ldg(b + i), s);
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+  if ((n & 3) == 0 && (((uintptr_t)a | (uintptr_t)b) & 15) == 0) {
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    for (size_t i = tid; i < n / 4; i += nthr) {
+      const float4 x = __ldg(a4 + i), y = __ldg(b4 + i);
+      s0 = fmaf(x.x, y.x, s0); s1 = fmaf(x.y, y.y, s1); s2 = fmaf(x.z, y.z, s2); s3 = fmaf(x.w, y.w, s3);
+    }
+    s = (s0 + s1) + (s2 + s3);
+  } else {
+    for (size_t i = tid; i < n; i += nthr) s = fmaf(__ldg(a + i), __ldg(b + i), s);
+  }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
 }
@@ -1673,26 +1693,26 @@ extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float*
     cudaMemsetAsync(frob, 0, 2 * sizeof(float), st);
     // Tmp = Linv^T (upper triangular), Ulo = its tf32 remainder
     if ((rc = run_trinv_tc(h, st, w.K, w.Li, N, w.Li, w.Tmp, w.Ulo, w.WT, w.WTlo))) return rc;
-    dot_sum_kernel<<<h->num_sms * 4, 256, 0, st>>>(w.Tmp, w.Tmp, nn, frob);       // |Linv|_F^2 = tr K^-1
-    int trc = tf32_gemm_launch(h, st, N, N, N, 1.0f, w.Tmp, w.Ulo, N, w.Tmp, w.Ulo, N, 0.0f, w.Li, N, 1, 1);   // Li = K^-1 (lower)
+    dot_sum_kernel<<<h->num_sms * 8, 256, 0, st>>>(w.Tmp, w.Tmp, nn, frob);       // |Linv|_F^2 = tr K^-1
+    // Li = K^-1 (lower), K buffer (L is dead) = its tf32 remainder, written by the same epilogue
+    int trc = tf32_gemm_launch(h, st, N, N, N, 1.0f, w.Tmp, w.Ulo, N, w.Tmp, w.Ulo, N, 0.0f, w.Li, N, 1, 1, w.K);
     if (trc) return set_err(h, DB_ERR_CUDA, "tf32 K^-1 product failed (%d)", trc);
-    mirror_lower_kernel<<<dim3(tiles32, tiles32), 256, 0, st>>>(w.Li, N);
-    kinv_diag_kernel<<<(N + 7) / 8, 256, 0, st>>>(w.Tmp, N, w.Li);
-    tf32_split_lo(h, st, w.Li, N, N, N, w.Tmp);                                  // Tmp = remainder of K^-1
+    mirror_lower_kernel<<<dim3(tiles32, tiles32), 256, 0, st>>>(w.Li, w.K, N);
+    kinv_diag_kernel<<<(N + 7) / 8, 256, 0, st>>>(w.Tmp, N, w.Li, w.K);
     transpose_f32(st, Y, N, D, D, w.B1, N);                                      // B1 = Y^T [D,N]
     tf32_split_lo(h, st, w.B1, D, N, N, w.B2);
-    trc = tf32_gemm_launch(h, st, D, N, N, 1.0f, w.B1, w.B2, N, w.Li, w.Tmp, N, 0.0f, w.B3, N, 0, 0);        // B3 = (K^-1 Y)^T
+    trc = tf32_gemm_launch(h, st, D, N, N, 1.0f, w.B1, w.B2, N, w.Li, w.K, N, 0.0f, w.B3, N, 0, 0);          // B3 = (K^-1 Y)^T
     if (trc) return set_err(h, DB_ERR_CUDA, "tf32 K^-1 Y product failed (%d)", trc);
     transpose_f32(st, w.B3, D, N, N, w.Av, D);                                   // Av = A = K^-1 Y [N,D]
-    dot_sum_kernel<<<h->num_sms * 4, 256, 0, st>>>(Y, w.Av, nd, &w.acc->ssq);    // |L^-1 Y|^2 = sum Y o A
+    dot_sum_kernel<<<h->num_sms * 8, 256, 0, st>>>(Y, w.Av, nd, &w.acc->ssq);    // |L^-1 Y|^2 = sum Y o A
     if (want_grad) {
       tf32_split_lo(h, st, w.Av, N, D, D, w.S);                                  // S buffer = remainder of A
-      trc = tf32_gemm_launch(h, st, N, N, D, -0.5f, w.Av, w.S, D, w.Av, w.S, D, 0.0f, w.K, N, 1, 0);         // K buffer = -0.5 A A^T (lower)
+      trc = tf32_gemm_launch(h, st, N, N, D, -0.5f, w.Av, w.S, D, w.Av, w.S, D, 0.0f, w.Tmp, N, 1, 0);       // Tmp = -0.5 A A^T (lower)
       if (trc) return set_err(h, DB_ERR_CUDA, "tf32 A A^T product failed (%d)", trc);
       cudaMemsetAsync(w.dXacc, 0, sizeof(float) * (size_t)N * Q, st);
       const int tiles = (N + TileLarge::BM - 1) / TileLarge::BM;
-      gp_contract_mem_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(w.Li, w.K, N, Q, D, X, w.hyp, w.dXacc, w.acc);
-      dot_sum_kernel<<<h->num_sms * 4, 256, 0, st>>>(w.Av, w.Av, nd, frob + 1);   // |A|_F^2
+      gp_contract_mem_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(w.Li, w.Tmp, N, Q, D, X, w.hyp, w.dXacc, w.acc);
+      dot_sum_kernel<<<h->num_sms * 8, 256, 0, st>>>(w.Av, w.Av, nd, frob + 1);   // |A|_F^2
       gp_fix_trace_kernel<<<1, 1, 0, st>>>(w.acc, frob, w.hyp, D);
     }
   } else {
