@@ -1329,6 +1329,10 @@ GplvmWorkspace gplvm_workspace(void* ws, int N, int Q, int D) {
   return w;
 }
 
+inline bool gpdbn_tensor_factor() {     // DB_GPDBN_SIMT=1: keep the GPDBN factorisation on the fp32 SIMT kernels (A/B timing, diagnostics)
+  static const bool simt = [] { const char* e = getenv("DB_GPDBN_SIMT"); return e && e[0] == '1'; }();
+  return !simt;
+}
 inline bool gp_use_tensor_path(db_handle_t h, int N, int D) {
   static const bool simt_only = [] { const char* e = getenv("DB_GP_SIMT"); return e && e[0] == '1'; }();   // diagnostics
   if (simt_only) return false;
@@ -1597,7 +1601,7 @@ __global__ void gpdbn_finalize_kernel(const GpAccum* __restrict__ acc, const flo
 }
 
 struct GpdbnWorkspace {
-  float *K, *Li, *Kinv, *B, *P, *dXacc, *hyp;
+  float *K, *Li, *Kinv, *B, *P, *dXacc, *hyp, *U, *Ulo, *WT, *WTlo;
   GpAccum* acc;
   size_t bytes;
 };
@@ -1614,6 +1618,11 @@ GpdbnWorkspace gpdbn_workspace(void* ws, int N, int Q, int D) {
   w.dXacc = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)N * Q);
   w.hyp = reinterpret_cast<float*>(p); p += 256;
   w.acc = reinterpret_cast<GpAccum*>(p); p += 256;
+  // tensor-core factorisation (N >= 512, N % 4 == 0): Linv^T, its tf32 remainder and the block-row products
+  w.U = reinterpret_cast<float*>(p); p += nn;
+  w.Ulo = reinterpret_cast<float*>(p); p += nn;
+  w.WT = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)N * OB);
+  w.WTlo = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)N * OB);
   w.bytes = (size_t)(p - p0);
   return w;
 }
@@ -1766,14 +1775,23 @@ extern "C" int db_gpdbn_factor(db_handle_t h, db_stream_t stream, const float* X
   cudaMemsetAsync(w.acc, 0, sizeof(GpAccum), st);
   cudaMemsetAsync(info, 0, 2 * sizeof(int), st);
   if ((rc = run_gram(h, st, X, nullptr, N, N, Q, w.hyp, 1, w.K, N))) return rc;
-  {  // run_potrf clears info[0] itself
-    if ((rc = run_potrf(h, st, w.K, N, N, info))) return rc;
-  }
+  const bool tc = gp_use_tensor_path(h, N, 32) && gpdbn_tensor_factor();
+  if ((rc = run_potrf(h, st, w.K, N, N, info, tc ? w.Li : nullptr))) return rc;      // clears info[0] itself
   if (L_out) cudaMemcpyAsync(L_out, w.K, sizeof(float) * (size_t)N * N, cudaMemcpyDeviceToDevice, st);
   logdet_xsq_kernel<<<1, 1024, 0, st>>>(w.K, N, N, X, N * Q, w.acc);
-  if ((rc = run_trinv(h, st, w.K, N, N, w.Li, w.Kinv))) return rc;
-  const int tiles = (N + TileLarge::BM - 1) / TileLarge::BM;
-  kinv_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(w.Li, N, N, w.Kinv);
+  if (tc) {
+    // Linv^T and K^-1 = Linv^T Linv on the tensor cores (3xTF32), diagonal of K^-1 in exact fp32 (it carries pred_var)
+    if ((rc = run_trinv_tc(h, st, w.K, w.Li, N, w.Li, w.U, w.Ulo, w.WT, w.WTlo))) return rc;
+    const int trc = tf32_gemm_launch(h, st, N, N, N, 1.0f, w.U, w.Ulo, N, w.U, w.Ulo, N, 0.0f, w.Kinv, N, 1, 1);
+    if (trc) return set_err(h, DB_ERR_CUDA, "tf32 K^-1 product failed (%d)", trc);
+    const int tiles32 = (N + 31) / 32;
+    mirror_lower_kernel<<<dim3(tiles32, tiles32), 256, 0, st>>>(w.Kinv, nullptr, N);
+    kinv_diag_kernel<<<(N + 7) / 8, 256, 0, st>>>(w.U, N, w.Kinv, nullptr);
+  } else {
+    if ((rc = run_trinv(h, st, w.K, N, N, w.Li, w.Kinv))) return rc;
+    const int tiles = (N + TileLarge::BM - 1) / TileLarge::BM;
+    kinv_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(w.Li, N, N, w.Kinv);
+  }
   gpdbn_pred_var_kernel<<<(N + 255) / 256, 256, 0, st>>>(w.Kinv, N, w.hyp, pred_var, info);
   return check_launch(h, "gpdbn_factor");
 }
