@@ -1586,6 +1586,61 @@ __global__ void __launch_bounds__(256) gpdbn_grad_kernel(const float* __restrict
   }
   gp_contract_tile<T>(gacc, m0, n0, diag_tile, X, N, Q, hyp, dXacc, accum, rowacc, colacc, red);
 }
+// Tensor-core form of the same gradient: Xs = s^2 K^-1 diag(g_pv) (and its tf32 remainder) is materialised, G1 = Xs K^-1
+// runs as one 3xTF32 GEMM (lower part), and the contraction kernel reads the G1 tile from memory instead of forming it.
+__global__ void __launch_bounds__(256) kinv_scale_cols_kernel(const float4* __restrict__ Kinv, const float* __restrict__ gpv, int N,
+                                                              const float* __restrict__ hyp, float4* __restrict__ Xs,
+                                                              float4* __restrict__ Xs_lo) {
+  const float s2 = __ldg(hyp + 2) * __ldg(hyp + 2);
+  const size_t n4 = (size_t)N * N / 4, row4 = (size_t)N / 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % row4) * 4;
+    const float4 k = __ldg(Kinv + i);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gpv + c));
+    float4 v = make_float4(s2 * g.x * k.x, s2 * g.y * k.y, s2 * g.z * k.z, s2 * g.w * k.w);
+    Xs[i] = v;
+    Xs_lo[i] = make_float4(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u), v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u),
+                           v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u), v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+  }
+}
+__global__ void __launch_bounds__(256) gpdbn_grad_mem_kernel(const float* __restrict__ G1, const float* __restrict__ Kinv,
+                                                             const float* __restrict__ P, const float* __restrict__ B,
+                                                             const float* __restrict__ X, int N, int Q, int D,
+                                                             const float* __restrict__ hyp, float* __restrict__ dXacc, GpAccum* accum) {
+  using T = TileLarge;
+  if (blockIdx.x > blockIdx.y) return;
+  __shared__ typename T::Smem sm;
+  __shared__ float rowacc[T::BM][MAXQ];
+  __shared__ float colacc[T::BN][MAXQ];
+  __shared__ float red[3][8];
+  const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
+  const bool diag_tile = blockIdx.x == blockIdx.y;
+  for (int t = threadIdx.x; t < T::BM * MAXQ; t += 256) { (&rowacc[0][0])[t] = 0.0f; (&colacc[0][0])[t] = 0.0f; }
+  const float s = __ldg(hyp + 2);
+  const float half_d = 0.5f * (float)D;
+  float gacc[T::TM][T::TN];
+#pragma unroll
+  for (int i = 0; i < T::TM; ++i) {
+    const int m = simt_row<T>(m0, i);
+#pragma unroll
+    for (int jj = 0; jj < T::TN; ++jj) {
+      const int n = simt_col<T>(n0, jj);
+      float v = 0.0f;
+      if (m < N && n < N) {
+        const size_t lo_idx = n <= m ? (size_t)m * N + n : (size_t)n * N + m;      // G1 is symmetric, lower part stored
+        v = fmaf(half_d, __ldg(Kinv + (size_t)m * N + n), __ldg(G1 + lo_idx));
+      }
+      gacc[i][jj] = v;
+    }
+  }
+  __syncthreads();
+  {
+    LoadEB_A a{P, B, N, D, s};
+    LoadEB_B b{P, B, N, D, s};
+    simt_gemm_tile<T, LoadEB_A, LoadEB_B, false>(sm, a, b, m0, n0, 0, 2 * D, gacc);
+  }
+  gp_contract_tile<T>(gacc, m0, n0, diag_tile, X, N, Q, hyp, dXacc, accum, rowacc, colacc, red);
+}
 __global__ void gpdbn_finalize_kernel(const GpAccum* __restrict__ acc, const float* __restrict__ hyp, const float* __restrict__ opt,
                                       int flags, int N, int Q, float x_prior_w, const float* __restrict__ X,
                                       const float* __restrict__ dXacc, float* __restrict__ dX, float* __restrict__ dhyp) {
@@ -1782,11 +1837,12 @@ extern "C" int db_gpdbn_factor(db_handle_t h, db_stream_t stream, const float* X
   if (tc) {
     // Linv^T and K^-1 = Linv^T Linv on the tensor cores (3xTF32), diagonal of K^-1 in exact fp32 (it carries pred_var)
     if ((rc = run_trinv_tc(h, st, w.K, w.Li, N, w.Li, w.U, w.Ulo, w.WT, w.WTlo))) return rc;
-    const int trc = tf32_gemm_launch(h, st, N, N, N, 1.0f, w.U, w.Ulo, N, w.U, w.Ulo, N, 0.0f, w.Kinv, N, 1, 1);
+    // the K buffer (L is dead) keeps the tf32 remainder of K^-1 for the backward GEMM (db_gpdbn_backward_x)
+    const int trc = tf32_gemm_launch(h, st, N, N, N, 1.0f, w.U, w.Ulo, N, w.U, w.Ulo, N, 0.0f, w.Kinv, N, 1, 1, w.K);
     if (trc) return set_err(h, DB_ERR_CUDA, "tf32 K^-1 product failed (%d)", trc);
     const int tiles32 = (N + 31) / 32;
-    mirror_lower_kernel<<<dim3(tiles32, tiles32), 256, 0, st>>>(w.Kinv, nullptr, N);
-    kinv_diag_kernel<<<(N + 7) / 8, 256, 0, st>>>(w.U, N, w.Kinv, nullptr);
+    mirror_lower_kernel<<<dim3(tiles32, tiles32), 256, 0, st>>>(w.Kinv, w.K, N);
+    kinv_diag_kernel<<<(N + 7) / 8, 256, 0, st>>>(w.U, N, w.Kinv, w.K);
   } else {
     if ((rc = run_trinv(h, st, w.K, N, N, w.Li, w.Kinv))) return rc;
     const int tiles = (N + TileLarge::BM - 1) / TileLarge::BM;
@@ -1835,7 +1891,19 @@ extern "C" int db_gpdbn_backward_x(db_handle_t h, db_stream_t stream, const floa
   cudaMemsetAsync(&w.acc->trG, 0, 3 * sizeof(float), st);      // trG, sumW, sumWr2
   gpdbn_gpv_scalar_kernel<<<(N + 255) / 256 > 64 ? 64 : (N + 255) / 256, 256, 0, st>>>(g_pv, w.Kinv, N, w.hyp, w.acc);
   const int tiles = (N + TileLarge::BM - 1) / TileLarge::BM;
-  gpdbn_grad_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(w.Kinv, g_pv, w.P, w.B, X, N, Q, D, w.hyp, w.dXacc, w.acc);
+  bool done = false;
+  if (gp_use_tensor_path(h, N, 32) && gpdbn_tensor_factor() && (reinterpret_cast<uintptr_t>(g_pv) & 15) == 0) {
+    // same decision as db_gpdbn_factor: the K buffer holds the remainder of K^-1
+    kinv_scale_cols_kernel<<<h->num_sms * 8, 256, 0, st>>>(reinterpret_cast<const float4*>(w.Kinv), g_pv, N, w.hyp,
+                                                          reinterpret_cast<float4*>(w.Li), reinterpret_cast<float4*>(w.U));
+    const int trc = tf32_gemm_launch(h, st, N, N, N, 1.0f, w.Li, w.U, N, w.Kinv, w.K, N, 0.0f, w.Ulo, N, 1, 0);
+    if (trc != 0 && trc != -1000) return set_err(h, DB_ERR_CUDA, "tf32 gradient product failed (%d)", trc);
+    if (trc == 0) {
+      gpdbn_grad_mem_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(w.Ulo, w.Kinv, w.P, w.B, X, N, Q, D, w.hyp, w.dXacc, w.acc);
+      done = true;
+    }
+  }
+  if (!done) gpdbn_grad_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(w.Kinv, g_pv, w.P, w.B, X, N, Q, D, w.hyp, w.dXacc, w.acc);
   gpdbn_finalize_kernel<<<(N * Q + 255) / 256, 256, 0, st>>>(w.acc, w.hyp, hyp_opt, flags, N, Q, x_prior_weight, X, w.dXacc, dX,
                                                             dhyp);
   return check_launch(h, "gpdbn_backward_x");
