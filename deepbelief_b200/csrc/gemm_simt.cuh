@@ -27,16 +27,21 @@ struct GemmLoadB {   // b(k,n) of op(B): B is [K,N] (TRANS=0) or [N,K] (TRANS=1)
   }
 };
 
+// gridDim.z > 1: split-K. Slice z covers k in [z * k_per, (z + 1) * k_per) and adds alpha * partial into C with atomics;
+// the caller has already replaced C by beta * C (gemm_scale_c_kernel). The order of the fp32 additions is then not fixed.
 template <class T, bool TA, bool TB>
 __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                                                        float* __restrict__ C, int ldc, int M, int N, int K, float alpha,
-                                                       float beta) {
+                                                       float beta, int k_per) {
   __shared__ typename T::Smem sm;
   const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
   GemmLoadA<TA> a{A, lda, M, K};
   GemmLoadB<TB> b{B, ldb, K, N};
   float acc[T::TM][T::TN];
-  simt_gemm_tile<T>(sm, a, b, m0, n0, 0, K, acc);
+  const bool split = gridDim.z > 1;
+  const int k_begin = split ? blockIdx.z * k_per : 0;
+  const int k_end = split ? min(K, k_begin + k_per) : K;
+  simt_gemm_tile<T>(sm, a, b, m0, n0, k_begin, k_end, acc);
 #pragma unroll
   for (int i = 0; i < T::TM; ++i) {
     const int m = simt_row<T>(m0, i);
@@ -46,16 +51,44 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
       const int n = simt_col<T>(n0, j);
       if (n >= N) continue;
       float* c = C + (size_t)m * ldc + n;
-      *c = beta != 0.0f ? fmaf(beta, *c, alpha * acc[i][j]) : alpha * acc[i][j];
+      if (split) atomicAdd(c, alpha * acc[i][j]);
+      else *c = beta != 0.0f ? fmaf(beta, *c, alpha * acc[i][j]) : alpha * acc[i][j];
     }
+  }
+}
+static __global__ void gemm_scale_c_kernel(float* __restrict__ C, int ldc, int M, int N, float beta) {
+  const size_t total = (size_t)M * N;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    float* c = C + (i / N) * (size_t)ldc + (i % N);
+    *c = beta != 0.0f ? beta * *c : 0.0f;
   }
 }
 
 template <class T, bool TA, bool TB>
-inline void launch_gemm_f32(cudaStream_t st, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N,
-                            int K, float alpha, float beta) {
+inline void launch_gemm_f32(cudaStream_t st, int num_sms, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M,
+                            int N, int K, float alpha, float beta) {
   dim3 grid((N + T::BN - 1) / T::BN, (M + T::BM - 1) / T::BM);
-  gemm_f32_kernel<T, TA, TB><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, alpha, beta);
+  // few output tiles and a long K (dW = X^T dZ over the batch, K^-1 H2 at N = 5000): split K so that every SM has work
+  const int tiles = (int)(grid.x * grid.y);
+  int splits = 1;
+  if (2 * tiles <= num_sms && K >= 1024) {
+    splits = (2 * num_sms + tiles - 1) / tiles;
+    const int max_splits = K / 256;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+  }
+  int k_per = K;
+  if (splits > 1) {
+    k_per = ((K + splits - 1) / splits + T::BK - 1) / T::BK * T::BK;
+    splits = (K + k_per - 1) / k_per;
+  }
+  if (splits > 1) {
+    const size_t total = (size_t)M * N;
+    const int blocks = (int)((total + 255) / 256 < (size_t)num_sms * 8 ? (total + 255) / 256 : (size_t)num_sms * 8);
+    gemm_scale_c_kernel<<<blocks, 256, 0, st>>>(C, ldc, M, N, beta);
+    grid.z = splits;
+  }
+  gemm_f32_kernel<T, TA, TB><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, alpha, beta, k_per);
 }
 
 // large tiles only when both output dimensions can fill them and there are enough tiles for 148 SMs
@@ -64,8 +97,8 @@ inline int run_gemm_f32(db_handle_t h, cudaStream_t st, int transA, int transB, 
   const bool large = M >= 512 && N >= 512 && ((size_t)M * N) / (128 * 128) >= (size_t)h->num_sms;
 #define DB_GEMM_CASE(TA, TB)                                                                              \
   do {                                                                                                     \
-    if (large) launch_gemm_f32<TileLarge, TA, TB>(st, A, lda, B, ldb, C, ldc, M, N, K, alpha, beta);       \
-    else launch_gemm_f32<TileSmall, TA, TB>(st, A, lda, B, ldb, C, ldc, M, N, K, alpha, beta);             \
+    if (large) launch_gemm_f32<TileLarge, TA, TB>(st, h->num_sms, A, lda, B, ldb, C, ldc, M, N, K, alpha, beta);       \
+    else launch_gemm_f32<TileSmall, TA, TB>(st, h->num_sms, A, lda, B, ldb, C, ldc, M, N, K, alpha, beta);             \
   } while (0)
   if (!transA && !transB) DB_GEMM_CASE(false, false);
   else if (transA && !transB) DB_GEMM_CASE(true, false);
