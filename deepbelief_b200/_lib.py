@@ -114,6 +114,8 @@ SIGNATURES = {
                                      c_float_p]),
     'db_sigmoid_backward': (c_int, [c_void_p, c_void_p, c_float_p, c_float_p, c_int, c_int, c_float_p]),
     'db_cross_entropy_grad': (c_int, [c_void_p, c_void_p, c_float_p, c_float_p, c_int, c_int, c_float, c_float_p]),
+    'db_sbm_expand': (c_int, [c_void_p, c_void_p, c_float_p, c_int, c_int, c_int, c_float_p]),
+    'db_sbm_gather': (c_int, [c_void_p, c_void_p, c_float_p, c_int, c_int, c_int, c_float_p]),
     'db_colsum': (c_int, [c_void_p, c_void_p, c_float_p, c_int, c_int, c_float, c_float, c_float_p]),
     'db_host_gather_rows': (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_void_p, c_int]),
 }

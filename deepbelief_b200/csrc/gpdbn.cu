@@ -226,6 +226,71 @@ extern "C" int db_cross_entropy_grad(db_handle_t h, db_stream_t stream, const fl
   return check_launch(h, "cross_entropy_grad");
 }
 
+// ---- SBM_Lower (sbm_lower.py:59-117): four overlapping patches of the side x side image share one weight matrix ----
+// Patch p reads the P x P window at (row offset, column offset) = (0,0), (0,pad), (pad,pad), (pad,0) with
+// P = side/2 + overlap/2, pad = P - overlap (sbm_lower.py:63-67) and feeds hidden units [p H4, (p+1) H4). The layer
+// is an RBM whose dense weight W_eff[V, 4 H4] holds the shared matrix scattered four times and zeros elsewhere, so the
+// CD kernels run unchanged; the gradient of the shared matrix is the sum of the four scattered blocks.
+namespace db { namespace {
+__device__ __forceinline__ void sbm_offsets(int p, int pad, int& roff, int& coff) {
+  roff = (p >= 2) ? pad : 0;
+  coff = (p == 1 || p == 2) ? pad : 0;
+}
+__global__ void sbm_expand_kernel(const float* __restrict__ Ws, int side, int P, int pad, int H4, float* __restrict__ Weff) {
+  const int H = 4 * H4;
+  const size_t total = (size_t)side * side * H;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i / H), col = (int)(i % H), p = col / H4, jj = col % H4;
+    int roff, coff;
+    sbm_offsets(p, pad, roff, coff);
+    const int r = v / side - roff, c = v % side - coff;
+    Weff[i] = (r >= 0 && r < P && c >= 0 && c < P) ? __ldg(Ws + (size_t)(r * P + c) * H4 + jj) : 0.0f;
+  }
+}
+__global__ void sbm_gather_kernel(const float* __restrict__ gWeff, int side, int P, int pad, int H4, float* __restrict__ gWs) {
+  const int H = 4 * H4;
+  const size_t total = (size_t)P * P * H4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int pix = (int)(i / H4), jj = (int)(i % H4), r = pix / P, c = pix % P;
+    float s = 0.0f;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      int roff, coff;
+      sbm_offsets(p, pad, roff, coff);
+      s += __ldg(gWeff + (size_t)((r + roff) * side + c + coff) * H + p * H4 + jj);
+    }
+    gWs[i] = s;
+  }
+}
+inline bool sbm_shape_ok(int side, int overlap, int num_h) {
+  return side > 0 && num_h > 0 && overlap >= 0 && side % 2 == 0 && overlap % 2 == 0 && num_h % 4 == 0 && overlap <= side;
+}
+} }  // namespace db::(anonymous)
+
+extern "C" int db_sbm_expand(db_handle_t h, db_stream_t stream, const float* W_shared, int side, int side_overlap, int num_h,
+                             float* W_eff) {
+  DB_REQUIRE(h, W_shared && W_eff, "null operand");
+  DB_REQUIRE(h, sbm_shape_ok(side, side_overlap, num_h), "side and side_overlap must be even, num_h a multiple of 4");   // sbm_lower.py:24-26
+  const int P = side / 2 + side_overlap / 2;
+  const size_t total = (size_t)side * side * num_h;
+  const size_t blocks = (total + 255) / 256, cap = (size_t)h->num_sms * 8;
+  sbm_expand_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, (cudaStream_t)stream>>>(W_shared, side, P, P - side_overlap,
+                                                                                        num_h / 4, W_eff);
+  return check_launch(h, "sbm_expand");
+}
+
+extern "C" int db_sbm_gather(db_handle_t h, db_stream_t stream, const float* gW_eff, int side, int side_overlap, int num_h,
+                             float* gW_shared) {
+  DB_REQUIRE(h, gW_eff && gW_shared, "null operand");
+  DB_REQUIRE(h, sbm_shape_ok(side, side_overlap, num_h), "side and side_overlap must be even, num_h a multiple of 4");
+  const int P = side / 2 + side_overlap / 2;
+  const size_t total = (size_t)P * P * (num_h / 4);
+  const size_t blocks = (total + 255) / 256, cap = (size_t)h->num_sms * 8;
+  sbm_gather_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, (cudaStream_t)stream>>>(gW_eff, side, P, P - side_overlap,
+                                                                                        num_h / 4, gW_shared);
+  return check_launch(h, "sbm_gather");
+}
+
 extern "C" int db_colsum(db_handle_t h, db_stream_t stream, const float* A, int M, int N, float scale, float beta, float* out) {
   DB_REQUIRE(h, A && out && M > 0 && N > 0, "null operand or empty shape");
   colsum_kernel<<<(N + 31) / 32, 256, 0, (cudaStream_t)stream>>>(A, M, N, scale, beta, out);

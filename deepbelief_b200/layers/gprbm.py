@@ -289,7 +289,7 @@ class GPRBM(bgrbm.BGRBM):
             dz = ops.concrete_backward(g, q, d_out, lay.temperature)          # [N, V_l]
             ops.gemm(dz, d_in, trans_a=True, out=gW)                          # dW = dz^T d_in
             ops.colsum(dz, out=gb)
-            g = ops.gemm(dz, lay.W)                                           # [N, H_l]
+            g = ops.gemm(dz, lay.Wk)                                          # [N, H_l]
         gWt, gbt, gct = self._views(self, G['top'])
         g_oah = G['top'][self.num_v * self.num_h + self.num_v + self.num_h:]
         y, q, d_out = downs[0]
@@ -318,7 +318,7 @@ class GPRBM(bgrbm.BGRBM):
             ops.gemm(a_in, dz, trans_a=True, beta=1.0, out=gW)
             ops.colsum(dz, out=gc)
             if l > 0:
-                g_a = ops.gemm(dz, lay.W, trans_b=True)
+                g_a = ops.gemm(dz, lay.Wk, trans_b=True)
         return G
 
     # ---- generation ---------------------------------------------------------------------------------------------------
@@ -402,7 +402,7 @@ class GPRBM(bgrbm.BGRBM):
     def _trainable_buffers(self, fixed_X):
         lower = self._lower()
         G = self._ensure_grads(lower)
-        bufs = [(lay._params, g, lay) for lay, g in zip(lower, G['lower'])]
+        bufs = [lay._trainable_pair(g) + (lay,) for lay, g in zip(lower, G['lower'])]
         bufs.append((self._params, G['top'], self))
         if not fixed_X:
             bufs.append((self._x_params, G['X'], None))
@@ -427,7 +427,7 @@ class GPRBM(bgrbm.BGRBM):
                                               device=self.device)
                 ops.optimizer_step(desc, params, grad, states[key])
                 if lay is not None:
-                    lay._weights_version += 1
+                    lay._after_update()
             self._touch()
 
         i = 0
@@ -497,7 +497,7 @@ class GPRBM(bgrbm.BGRBM):
             tape.append((lay, q, d))
         loss, model_point, g = ops.testgen_meanloss(d, target, pv, R, S, log_var_scaling, want_outputs)
         for lay, q, d_out in reversed(tape):
-            g = ops.gemm(ops.concrete_backward(g, q, d_out, lay.temperature), lay.W)
+            g = ops.gemm(ops.concrete_backward(g, q, d_out, lay.temperature), lay.Wk)
         gHm_rows, gsig_rows, _, _ = ops.gpdbn_top_backward1(g, y, Hm_rows, pv_rows, alpha_h, eps)
         g_Hm, g_pv = ops.testgen_reduce_samples(gHm_rows, gsig_rows, alpha_h, pv, R, S, log_var_scaling)
         g_x = ops.testgen_grad_x(ops.gemm(B, g_Hm, trans_b=True), Cv, Kxs, g_pv, self.X, x, hyp)

@@ -151,6 +151,9 @@ class RBM(layer.Layer):
         self.W = self._params[:vh].view(num_v, num_h)
         self.b = self._params[vh:vh + num_v].view(num_v, 1)
         self.c = self._params[vh + num_v:vh + num_v + num_h].view(1, num_h)
+        # operands the kernels read; a layer with tied weights (SBM_Lower) exposes its shared parameters as W / b / c
+        # and keeps the dense expansion here
+        self.Wk, self.bk, self.ck = self.W, self.b, self.c
         # truncated normal, +-2 sigma redraw (rbm.py:59-62) — host RNG, parity runs inject W
         w0 = np.random.normal(size=(num_v, num_h))
         bad = np.abs(w0) > 2.0
@@ -221,12 +224,12 @@ class RBM(layer.Layer):
 
     # ---- net inputs and probabilities ----------------------------------------------------------------------------
     def _up(self, v_batch, act, sample_kind=L.SAMPLE_NONE, noise=None, draw=None, want_act=True):
-        return ops.layer_forward(to_device(v_batch, self.device), self.W, self.c, False, act, sample_kind,
+        return ops.layer_forward(to_device(v_batch, self.device), self.Wk, self.ck, False, act, sample_kind,
                                  self.temperature, col_scale=self._h_scale(), noise_scale=noise, injected=draw,
                                  rng=self.rng, want_act=want_act)
 
     def _down(self, h_batch, act, sample_kind=L.SAMPLE_NONE, noise=None, draw=None, want_act=True):
-        return ops.layer_forward(to_device(h_batch, self.device), self.W, self.b, True, act, sample_kind,
+        return ops.layer_forward(to_device(h_batch, self.device), self.Wk, self.bk, True, act, sample_kind,
                                  self.temperature, a_div=self._v_div(), noise_scale=noise, injected=draw,
                                  rng=self.rng, want_act=want_act)
 
@@ -319,7 +322,7 @@ class RBM(layer.Layer):
     # ---- energies ------------------------------------------------------------------------------------------------------
     def free_energy(self, v_batch):
         """F(v) = -(v b + sum_j softplus((vW + c)_j)) -> [N, 1] (rbm.py:378-396)."""
-        return ops.free_energy(self.layer_kind, to_device(v_batch, self.device), self.W, self.b, self.c,
+        return ops.free_energy(self.layer_kind, to_device(v_batch, self.device), self.Wk, self.bk, self.ck,
                                self._sigma_vector())
 
     def _sigma_vector(self):
@@ -521,16 +524,26 @@ class RBM(layer.Layer):
             plan.version = self._weights_version
         return plan
 
+    # ---- what the optimizer sees: the packed kernel parameters themselves, unless a subclass ties weights ----
+    def _trainable_pair(self, grad):
+        """(trainable parameter buffer, its gradient) for the packed kernel-layout gradient `grad`."""
+        return self._params, grad
+
+    def _after_update(self):
+        self._weights_version += 1
+
     def apply_gradient(self, optimizer, grad, opt_state, lr=None):
         """All-reduce (data parallel) + optimizer step on the packed parameters."""
         all_reduce_sum_(grad)
-        ops.optimizer_step(optimizer.descriptor(lr), self._params, grad, opt_state)
-        self._weights_version += 1
+        params, g = self._trainable_pair(grad)
+        ops.optimizer_step(optimizer.descriptor(lr), params, g, opt_state)
+        self._after_update()
 
     def new_optimizer_state(self, optimizer):
         optimizer.reset()                                    # fresh slots per train() (rbm.py:107-117, 670)
         mult = optimizer.state_multiple()
-        return torch.zeros(max(mult, 1) * self._params.numel(), dtype=torch.float32, device=self.device)
+        n = self._trainable_pair(self._params)[0].numel()
+        return torch.zeros(max(mult, 1) * n, dtype=torch.float32, device=self.device)
 
     def train(self, optimizer, training_data, test_data, num_gibbs_steps=1, pcd=True, lr_interval=None,
               lr_drop=None, test_mean_fname=None, test_std_fname=None, max_iterations=1000, eval_interval=0,
@@ -639,11 +652,11 @@ class RBM(layer.Layer):
             if direction == 'up':
                 ops.gemm(a_in, dz, trans_a=True, beta=1.0, out=gW)
                 ops.colsum(dz, out=gl[vh + lay.num_v:vh + lay.num_v + lay.num_h], beta=1.0)
-                g = ops.gemm(dz, lay.W, trans_b=True)
+                g = ops.gemm(dz, lay.Wk, trans_b=True)
             else:
                 ops.gemm(dz, a_in, trans_a=True, beta=1.0, out=gW)
                 ops.colsum(dz, out=gl[vh:vh + lay.num_v], beta=1.0)
-                g = ops.gemm(dz, lay.W)
+                g = ops.gemm(dz, lay.Wk)
         return loss, [grads[id(lay)] for lay in stack], out
 
     def backprop(self, training_data, test_data, training_sampling=True, training_num_propagation_cycles=5,
@@ -684,8 +697,9 @@ class RBM(layer.Layer):
             feeder.prefetch()
             desc = opt.descriptor()
             for lay, gl in zip(stack, grads):
-                ops.optimizer_step(desc, lay._params, gl, None)
-                lay._weights_version += 1
+                params, g = lay._trainable_pair(gl)
+                ops.optimizer_step(desc, params, g, None)
+                lay._after_update()
             if eval_interval and self.iter % eval_interval == 0:
                 evaluate()
             if ckpt_dir and ckpt_interval and self.iter % ckpt_interval == 0:

@@ -317,6 +317,20 @@ def cross_entropy_grad(probs, targets, scale=1.0):
     return out
 
 
+def sbm_expand(W_shared, side, side_overlap, num_h, out):
+    """Dense [side*side, num_h] equivalent of the patch-shared SBM_Lower weights (sbm_lower.py:59-117)."""
+    L.check(L.lib().db_sbm_expand(L.handle(), L.stream(), L.fptr(_f32(W_shared)), int(side), int(side_overlap), int(num_h),
+                                  L.fptr(out)), 'db_sbm_expand')
+    return out
+
+
+def sbm_gather(gW_eff, side, side_overlap, num_h, out):
+    """Gradient of the shared SBM_Lower matrix from the gradient of its dense equivalent."""
+    L.check(L.lib().db_sbm_gather(L.handle(), L.stream(), L.fptr(_f32(gW_eff)), int(side), int(side_overlap), int(num_h),
+                                  L.fptr(out)), 'db_sbm_gather')
+    return out
+
+
 def colsum(A, out=None, scale=1.0, beta=0.0):
     A = _f32(A)
     if out is None:

@@ -322,6 +322,16 @@ int db_sigmoid_backward(db_handle_t h, db_stream_t stream, const float* g, const
 int db_cross_entropy_grad(db_handle_t h, db_stream_t stream, const float* probs, const float* targets, int M, int N,
                           float scale, float* out);
 /* out[c] = beta * out[c] + scale * sum_rows A[:,c]  (bias gradients). */
+/* SBM_Lower (reference deepbelief/layers/sbm_lower.py:59-117): one weight matrix W_shared [P*P, num_h/4] shared by the
+ * four overlapping P x P patches of the side x side image, P = side/2 + side_overlap/2. db_sbm_expand writes the dense
+ * equivalent W_eff [side*side, num_h] (the tf.slice / tf.pad / tf.concat plumbing of h_net_input and v_net_input as one
+ * scatter), so every RBM entry point runs unchanged on it; db_sbm_gather sums the four scattered blocks of a dense
+ * gradient into the gradient of the shared matrix (what TF autodiff derives for the shared variable). */
+int db_sbm_expand(db_handle_t h, db_stream_t stream, const float* W_shared, int side, int side_overlap, int num_h,
+                  float* W_eff);
+int db_sbm_gather(db_handle_t h, db_stream_t stream, const float* gW_eff, int side, int side_overlap, int num_h,
+                  float* gW_shared);
+
 int db_colsum(db_handle_t h, db_stream_t stream, const float* A, int M, int N, float scale, float beta, float* out);
 
 /* ---- host-side data loader helper (no device work) --------------------------------------------- */

@@ -26,6 +26,7 @@ from deepbelief import dist, preprocessing  # noqa: E402
 from deepbelief.layers import rbm as ref_rbm, bgrbm as ref_bgrbm, gbrbm as ref_gbrbm, ggrbm as ref_ggrbm  # noqa: E402
 from deepbelief.layers import gplvm as ref_gplvm  # noqa: E402
 from deepbelief.layers import gprbm as ref_gprbm  # noqa: E402
+from deepbelief.layers import sbm_lower as ref_sbm  # noqa: E402
 
 sys.path.insert(0, os.path.join(HERE, '..', '..'))
 from deepbelief_b200 import hdf5  # noqa: E402  (only the HDF5 reader; h5py is unavailable)
@@ -405,6 +406,56 @@ def gpdbn_goldens(out):
                 out['gpdbn/%s/fd/%s' % (cname, key)] = np.float64(fd)
 
 
+def sbm_goldens(out):
+    """SBM_Lower (sbm_lower.py:59-117): net inputs, probabilities, free energy, cd_loss of the reference class with injected
+    shared weights, and the gradient of cd_loss with respect to the shared W and b as central differences (fp64)."""
+    rs = np.random.RandomState(77)
+    for tag, (side, ov, H, N) in {'s8': (8, 2, 12, 9), 's12': (12, 4, 8, 7)}.items():
+        P = side // 2 + ov // 2
+        W = rs.normal(size=(P * P, H // 4)) * 0.3
+        b = rs.normal(size=side * side) * 0.2
+        v0 = rs.binomial(1, 0.5, size=(N, side * side)).astype(np.float64)
+        vk = rs.binomial(1, 0.5, size=(N, side * side)).astype(np.float64)
+        h = rs.binomial(1, 0.5, size=(N, H)).astype(np.float64)
+        pre = 'sbm/%s/' % tag
+        out[pre + 'dims'] = np.array([side, ov, H, N])
+        out[pre + 'W'], out[pre + 'b'], out[pre + 'v0'], out[pre + 'vk'], out[pre + 'h'] = W, b, v0, vk, h
+        for dname in ('float64', 'float32'):
+            set_dtype(dname)
+            dt = np.dtype(dname)
+
+            def build(Wm, bm, dt=dt):
+                lay = ref_sbm.SBM_Lower(side=side, side_overlap=ov, num_h=H, session=tf.Session(), name='S' + tag + str(dt))
+                lay.W = Wm.astype(dt)
+                lay.b = bm.astype(dt).reshape(-1, 1)
+                lay._b_transpose = np.transpose(lay.b)          # sbm_lower.py:57 (evaluated at construction)
+                return lay
+            lay = build(W, b)
+            q = pre + dname + '/'
+            out[q + 'h_net'] = lay.h_net_input(v0.astype(dt))
+            out[q + 'v_net'] = lay.v_net_input(h.astype(dt))
+            out[q + 'h_probs'] = lay.h_probs(v0.astype(dt))
+            out[q + 'v_probs'] = lay.v_probs(h.astype(dt))
+            out[q + 'free_energy'] = lay.free_energy(v0.astype(dt))
+            out[q + 'cd_loss'] = lay.cd_loss(v0.astype(dt), vk.astype(dt))
+        set_dtype('float64')
+
+        def loss_at(Wm, bm):
+            return float(build(Wm, bm, np.dtype('float64')).cd_loss(v0, vk))
+        eps = 1e-6
+        gW = np.zeros_like(W)
+        for i in range(W.shape[0]):
+            for j in range(W.shape[1]):
+                d = np.zeros_like(W); d[i, j] = eps
+                gW[i, j] = (loss_at(W + d, b) - loss_at(W - d, b)) / (2 * eps)
+        gb = np.zeros_like(b)
+        for i in range(b.size):
+            d = np.zeros_like(b); d[i] = eps
+            gb[i] = (loss_at(W, b + d) - loss_at(W, b - d)) / (2 * eps)
+        out[pre + 'fd_gW'], out[pre + 'fd_gb'] = gW, gb
+    set_dtype('float32')
+
+
 def misc_goldens(out):
     rs = np.random.RandomState(99)
     set_dtype('float64')
@@ -422,8 +473,11 @@ def misc_goldens(out):
 
 
 def main():
+    only = sys.argv[1:]
     for fn, name in ((rbm_goldens, 'rbm_golden.npz'), (gp_goldens, 'gp_golden.npz'), (misc_goldens, 'misc_golden.npz'),
-                     (gpdbn_goldens, 'gpdbn_golden.npz'), (backprop_goldens, 'backprop_golden.npz')):
+                     (gpdbn_goldens, 'gpdbn_golden.npz'), (backprop_goldens, 'backprop_golden.npz'), (sbm_goldens, 'sbm_golden.npz')):
+        if only and name not in only:
+            continue
         out = {}
         fn(out)
         path = os.path.join(HERE, name)

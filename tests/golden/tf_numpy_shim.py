@@ -267,6 +267,14 @@ def install():
     tf.tile = lambda a, m, name=None: np.tile(a, m)
     tf.concat = lambda v, axis, name=None: np.concatenate(v, axis=axis)
     tf.clip_by_value = lambda a, lo, hi, name=None: np.clip(a, lo, hi)
+
+    def _slice(a, begin, size, name=None):          # size -1 = to the end of that axis
+        a = np.asarray(a)
+        idx = tuple(slice(int(b), None if int(sz) == -1 else int(b) + int(sz)) for b, sz in zip(begin, size))
+        return a[idx]
+    tf.slice = _slice
+    tf.pad = lambda a, paddings, mode='CONSTANT', name=None: np.pad(a, np.asarray(paddings), mode='constant')
+    tf.split = lambda a, n, axis=0, name=None: np.split(a, n, axis=axis)
     tf.reduce_min = lambda a, axis=None, name=None: np.min(a, axis=axis)
     tf.reduce_max = lambda a, axis=None, name=None: np.max(a, axis=axis)
     tf.assert_type = lambda a, t, name=None: None
