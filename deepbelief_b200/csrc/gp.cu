@@ -16,6 +16,7 @@
 #include "simt_gemm.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tf32.cuh"
+#include "ptx.cuh"
 #include <cstdlib>
 #include <mutex>
 
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(NB) potrf_colblock_kernel(float* __restrict__ 
 // (STEP_SMEM below); 256 threads.
 //   strip CTAs  (blockIdx.x <  strips): 64-row strip s of the rows from j down (s = 0 is the diagonal block). Each one
 //     applies panel jprev (rank-64) to its own block of column block j and (redundantly) to the diagonal block - one
-//     128 x 64 x 64 product on the tensor cores (mma.sync, 3xTF32) -, factorises the diagonal block (redundantly:
+//     128 x 64 x 64 product on the tensor cores (tcgen05.mma, 3xTF32, accumulator in TMEM) -, factorises the diagonal block (redundantly:
 //     identical arithmetic in every CTA, no inter-CTA dependency; warps 0-1, 8x8 sub-blocks in registers) and solves its
 //     strip (warps 2-3, chunk c as soon as chunk c of L is final).
 //   update CTAs (blockIdx.x >= strips, at most one per remaining SM): loop over the 128 x 64 tiles of the columns
@@ -252,12 +253,11 @@ __global__ void __launch_bounds__(NB) potrf_colblock_kernel(float* __restrict__ 
 // own launch. S and P (factorisation operands) are stored transposed, T[k][r] = element (row r, column k); the blocks
 // of the previous panel (tensor-core operands only) row-major.
 // Measured per step at N = 5000 (clock64 in strip CTA 1, build with -DDB_POTRF_TIMING and run with DB_POTRF_DEBUG=1):
-// load 6.5k, update 4.9k, factorisation 13.3k cycles; 16 us per step.
+// load 7.5k, update 2.5k (4.9k with mma.sync, 14.5k with fp32 FMAs), factorisation 15.5k cycles; 16 us per step.
 constexpr int STEP_THREADS = 256;
 // Requested dynamic shared memory: more than half an SM, so every CTA of a step launch owns its SM. The strip CTAs are
 // the critical path; measured with two update CTAs sharing their SM, their load and product phases ran 3x slower.
 constexpr int STEP_SMEM = 200 * 1024;
-constexpr int BLK_FLOATS = NB * LT_PITCH;
 
 // 64x64 block at (row0, col0): global -> registers (PER float4 per thread of a GROUP-thread group), then registers ->
 // T[k][r]. Split in two so a CTA can issue the loads of all its blocks before the first shared store.
@@ -296,10 +296,12 @@ __device__ __forceinline__ void block_store_T(float (*T)[LT_PITCH], int tid, con
   }
 }
 
-// Operands that only feed the tensor-core products stay row-major, R[row][k] with pitch RM_PITCH (conflict-free
-// fragment reads: (4 g + t) mod 32 is a bijection), and are loaded coalesced: 16 threads read one 256-byte row. A
-// warp-wide float4 load that touches 32 different rows (the transposed loader above) costs ~66 cycles of L1 replays.
-constexpr int RM_PITCH = 68;
+// Operands that only feed the tensor-core products are loaded coalesced (16 threads read one 256-byte row; a warp-wide
+// float4 load that touches 32 different rows, as the transposed loader above does, costs ~66 cycles of L1 replays) and
+// stored as 64-byte-swizzled K-major tiles, the layout TMA SWIZZLE_64B would produce and gemm_tf32.cu feeds to
+// tcgen05.mma: k-block kb (16 floats) of an R-row operand is a [R][64 B] tile at kb * R * 64 bytes, and 16-byte chunk c of
+// row r sits at chunk position c ^ ((r >> 1) & 3). Every value is stored twice: x itself (the tensor core reads its top 19
+// bits = tf32(x)) and the remainder x - tf32(x).
 struct BlockRegsRM { float4 v[4]; };
 __device__ __forceinline__ void block_load_rm(BlockRegsRM& b, int tid, const float* __restrict__ A, int lda, int row0, int col0,
                                               int rows_valid, bool vec) {
@@ -316,64 +318,48 @@ __device__ __forceinline__ void block_load_rm(BlockRegsRM& b, int tid, const flo
     }
   }
 }
-__device__ __forceinline__ void block_store_rm(float* R, int tid, const BlockRegsRM& b) {
+__device__ __forceinline__ float tf32_rem(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+// rows [row_off, row_off + 64) of an R-row operand
+__device__ __forceinline__ void block_store_sw(uint8_t* hi, uint8_t* lo, int R, int row_off, int tid, const BlockRegsRM& b) {
   const int c4 = tid & 15, rr = tid >> 4;
+  const int kb = c4 >> 2, chunk = c4 & 3;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(R + (rr + 16 * i) * RM_PITCH + 4 * c4) = b.v[i];
+  for (int i = 0; i < 4; ++i) {
+    const int r = row_off + rr + 16 * i;
+    const int off = kb * R * 64 + r * 64 + ((chunk ^ ((r >> 1) & 3)) << 4);
+    const float4 v = b.v[i];
+    *reinterpret_cast<float4*>(hi + off) = v;
+    *reinterpret_cast<float4*>(lo + off) = make_float4(tf32_rem(v.x), tf32_rem(v.y), tf32_rem(v.z), tf32_rem(v.w));
+  }
 }
-
-// 128 x 64 product on the tensor cores (mma.sync m16n8k8, 3xTF32: hi*hi + lo*hi + hi*lo, fp32 accumulate), 8 warps:
-//   D[m][n] = sum_k R[m][k] * C[n][k],  R = [R0 (rows 0..63); R1 (rows 64..127)], operand blocks row-major (RM_PITCH).
-// Warp w owns rows 16 w .. 16 w + 15 (w < 4: R0, else R1) and all 64 columns: acc[nt] is the m16n8 fragment of column
-// tile nt (c0: (g, 2t), c1: (g, 2t+1), c2: (g+8, 2t), c3: (g+8, 2t+1); g = lane >> 2, t = lane & 3).
-// Measured on the critical path of the Cholesky step: the same product with fp32 FMAs (8x8 register tiles, 4 warps)
-// took 14.5k cycles per step.
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+// K-major operand tile with SWIZZLE_64B: rows 64 B apart, 8-row groups 512 B apart (same descriptor as gemm_tf32.cu)
+__device__ __forceinline__ uint64_t step_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)1u << 16;
+  d |= (uint64_t)(512u >> 4) << 32;
+  d |= (uint64_t)1u << 46;
+  d |= (uint64_t)4u << 61;
+  return d;
 }
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(x) & 0xffffe000u;
-  lo = __float_as_uint(x - __uint_as_float(hi));
-}
-__device__ __forceinline__ void mma_block_product(float (&acc)[8][4], const float* Rows, int m0, const float* C, int lane) {
-  const int g = lane >> 2, t = lane & 3;
+// D[128, 64] (TMEM: lane = row, column = column) = A[128, 64] B[64, 64]^T, 3xTF32 (lo*hi + hi*lo + hi*hi), issued by ONE
+// thread: 4 k-blocks x 2 k-steps x 3 tcgen05.mma (M = 128, N = 64, K = 8); the commit arrives on `bar`.
+__device__ __forceinline__ void step_issue_product(uint32_t tmem_d, const uint8_t* a_hi, const uint8_t* a_lo, const uint8_t* b_hi,
+                                                   const uint8_t* b_lo, int b_rows, uint64_t* bar) {
+  constexpr uint32_t idesc = ptx::umma_idesc(/*TF32*/ 2, 128, 64);
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt)
+  for (int kb = 0; kb < 4; ++kb) {
+    const uint64_t dah = step_desc_sw64(ptx::smem_u32(a_hi + kb * 128 * 64)), dal = step_desc_sw64(ptx::smem_u32(a_lo + kb * 128 * 64));
+    const uint64_t dbh = step_desc_sw64(ptx::smem_u32(b_hi + kb * b_rows * 64)), dbl = step_desc_sw64(ptx::smem_u32(b_lo + kb * b_rows * 64));
 #pragma unroll
-    for (int e = 0; e < 4; ++e) acc[nt][e] = 0.0f;
-  const float* ra = Rows + (m0 + g) * RM_PITCH + t;
-  const float* rb = C + g * RM_PITCH + t;
-#pragma unroll 2
-  for (int k0 = 0; k0 < NB; k0 += 8) {
-    uint32_t ahi[4], alo[4];
-    split_tf32(ra[k0], ahi[0], alo[0]);
-    split_tf32(ra[8 * RM_PITCH + k0], ahi[1], alo[1]);
-    split_tf32(ra[k0 + 4], ahi[2], alo[2]);
-    split_tf32(ra[8 * RM_PITCH + k0 + 4], ahi[3], alo[3]);
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      uint32_t bhi[2], blo[2];
-      split_tf32(rb[8 * nt * RM_PITCH + k0], bhi[0], blo[0]);
-      split_tf32(rb[8 * nt * RM_PITCH + k0 + 4], bhi[1], blo[1]);
-      mma_tf32(acc[nt], alo, bhi);
-      mma_tf32(acc[nt], ahi, blo);
-      mma_tf32(acc[nt], ahi, bhi);
+    for (int k = 0; k < 2; ++k) {
+      const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);
+      ptx::mma_tf32_ss(tmem_d, dal + koff, dbh + koff, idesc, (kb | k) ? 1u : 0u);
+      ptx::mma_tf32_ss(tmem_d, dah + koff, dbl + koff, idesc, 1u);
+      ptx::mma_tf32_ss(tmem_d, dah + koff, dbh + koff, idesc, 1u);
     }
   }
-}
-// T[col][row] -= acc for the fragment rows m0 + g (+8) and columns 8 nt + 2t (+1)
-__device__ __forceinline__ void mma_subtract_T(float (*T)[LT_PITCH], const float (&acc)[8][4], int m0, int lane) {
-  const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    const int c = 8 * nt + 2 * t;
-    T[c][m0 + g] -= acc[nt][0];
-    T[c + 1][m0 + g] -= acc[nt][1];
-    T[c][m0 + g + 8] -= acc[nt][2];
-    T[c + 1][m0 + g + 8] -= acc[nt][3];
-  }
+  ptx::mma_commit(bar);
 }
 
 // Cholesky of the 8x8 diagonal sub-block at c0 entirely in registers (every calling thread redundantly):
@@ -413,28 +399,42 @@ __device__ __forceinline__ void factor8(const float (*blk)[8], float (&l)[8][8],
 #endif
 __global__ void __launch_bounds__(STEP_THREADS) potrf_step_kernel(float* __restrict__ A, int lda, int N, int j, int jprev, int b1,
                                                                   int strips, int* __restrict__ info, long long* __restrict__ dbg) {
-  extern __shared__ __align__(16) float step_smem[];
+#if defined(DB_SM100)
+  extern __shared__ __align__(16) uint8_t step_smem_raw[];
+  // 1 KB aligned: the swizzle pattern of the operand tiles is a function of the shared-memory address bits
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(step_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_hi = smem;                       // [4 k-blocks][128 rows][64 B]: rows 0-63 diagonal / first strip, 64-127 own / second strip
+  uint8_t* a_lo = smem + 32 * 1024;
+  uint8_t* b_hi = smem + 64 * 1024;           // [4][64][64 B] (update CTAs; the strip CTAs reuse rows 0-63 of a_*)
+  uint8_t* b_lo = smem + 80 * 1024;
+  float* step_smem = reinterpret_cast<float*>(smem + 96 * 1024);
   float (*S)[LT_PITCH] = reinterpret_cast<float (*)[LT_PITCH]>(step_smem);                        // diagonal block
   float (*P)[LT_PITCH] = reinterpret_cast<float (*)[LT_PITCH]>(step_smem + NB * LT_PITCH);        // own block
+  float* stage = step_smem;                   // update CTAs: [128][STAGE_PITCH] product tile for the coalesced read-modify-write
   __shared__ float dinv[NB];
   __shared__ __align__(16) float dblk[2][8][8];   // updated 8x8 diagonal sub-block, double-buffered by chunk parity
   __shared__ int s_fail;
   __shared__ volatile int s_progress;
+  __shared__ __align__(8) uint64_t mma_bar;
+  __shared__ uint32_t tmem_slot;
   const int t = threadIdx.x;
+  const int warp = t >> 5, lane = t & 31;
   const bool vec = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  const bool use_tc = jprev >= 0;             // launch-uniform: products with the previous panel exist
+  if (use_tc) {
+    if (warp == 0) { ptx::tmem_alloc(&tmem_slot, 64); ptx::tmem_relinquish(); }
+    if (t == 0) { ptx::mbar_init(&mma_bar, 1); ptx::fence_barrier_init(); }
+  }
   // Programmatic dependent launch: the next step's CTAs may be scheduled as soon as every CTA of this launch has
   // started; they block here until the previous launch has completed and its writes are visible.
   asm volatile("griddepcontrol.launch_dependents;");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   STEP_MARK(0, t == 0);
+  uint32_t mma_phase = 0;
 
   if ((int)blockIdx.x >= strips) {
     // ---------------- update CTA: loops over the (128 rows x 64 columns) tiles of the columns [j + 64, b1);
     // tile -= (128 rows of panel jprev) (rows cb.. of panel jprev)^T, next tile's operands in flight meanwhile ----------------
-    float* O0 = step_smem;
-    float* O1 = step_smem + BLK_FLOATS;
-    float* Dq = step_smem + 2 * BLK_FLOATS;
-    const int warp = t >> 5, lane = t & 31;
     const int ncb = (b1 - (j + NB) + NB - 1) / NB;
     const int stride = (int)gridDim.x - strips;
     // tile index -> (column block cb, first row); column block cb has ceil((N - cb) / 128) tiles starting at row cb
@@ -457,56 +457,81 @@ __global__ void __launch_bounds__(STEP_THREADS) potrf_step_kernel(float* __restr
       block_load_rm(r1, t, A, lda, row0 + NB, jprev, N - row0 - NB, vec);
       block_load_rm(rd, t, A, lda, cb, jprev, N - cb, vec);
     }
+    ptx::tc_fence_before();
+    __syncthreads();                                        // TMEM address and barrier are visible
+    ptx::tc_fence_after();
+    const uint32_t tmem_d = tmem_slot;
+    constexpr int STAGE_PITCH = 68;
     while (have) {
-      __syncthreads();                                      // the previous tile's fragment reads are done
-      block_store_rm(O0, t, r0);
-      block_store_rm(O1, t, r1);
-      block_store_rm(Dq, t, rd);
+      block_store_sw(a_hi, a_lo, 128, 0, t, r0);
+      block_store_sw(a_hi, a_lo, 128, NB, t, r1);
+      block_store_sw(b_hi, b_lo, NB, 0, t, rd);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
       __syncthreads();
+      if (t == 0) {
+        ptx::tc_fence_after();
+        step_issue_product(tmem_d, a_hi, a_lo, b_hi, b_lo, NB, &mma_bar);
+      }
       const int cur_cb = cb, cur_row0 = row0;
       tile += stride;
       have = locate(tile, cb, row0);                        // CTA-uniform
-      if (have) {
+      if (have) {                                           // next tile's operands in flight during the product
         block_load_rm(r0, t, A, lda, row0, jprev, N - row0, vec);
         block_load_rm(r1, t, A, lda, row0 + NB, jprev, N - row0 - NB, vec);
         block_load_rm(rd, t, A, lda, cb, jprev, N - cb, vec);
       }
-      const int m0 = 16 * (warp & 3);
+      // the tile's current values, coalesced: 16 threads per row
+      const int c4 = t & 15, rr = t >> 4;
       const int ncols = min(NB, b1 - cur_cb);
-      const int g = lane >> 2, tq = lane & 3;
-      // the tile's current values: every load is issued before the product and long before the first store (a
-      // load -> subtract -> store chain per element would serialise 16 L2 round trips)
-      float2 cur[2][8];
-      const int rbase = cur_row0 + (warp < 4 ? 0 : NB) + m0 + g;
-      const bool fast = vec && ncols == NB && cur_cb + NB - 1 <= rbase && rbase + 8 < N;     // both rows inside, below the diagonal
+      float4 cur[8];
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh)
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          const int row = rbase + 8 * hh, c = 8 * nt + 2 * tq;
-          const float* src = A + (size_t)row * lda + cur_cb + c;
-          if (fast) cur[hh][nt] = __ldcg(reinterpret_cast<const float2*>(src));
-          else {
-            cur[hh][nt].x = (row < N && c < ncols && cur_cb + c <= row) ? __ldcg(src) : 0.0f;
-            cur[hh][nt].y = (row < N && c + 1 < ncols && cur_cb + c + 1 <= row) ? __ldcg(src + 1) : 0.0f;
-          }
+      for (int i = 0; i < 8; ++i) {
+        const int row = cur_row0 + rr + 16 * i;
+        const float* src = A + (size_t)row * lda + cur_cb + 4 * c4;
+        if (row < N && vec && ncols == NB) cur[i] = __ldcg(reinterpret_cast<const float4*>(src));
+        else {
+          cur[i].x = (row < N && 4 * c4 + 0 < ncols) ? __ldcg(src + 0) : 0.0f;
+          cur[i].y = (row < N && 4 * c4 + 1 < ncols) ? __ldcg(src + 1) : 0.0f;
+          cur[i].z = (row < N && 4 * c4 + 2 < ncols) ? __ldcg(src + 2) : 0.0f;
+          cur[i].w = (row < N && 4 * c4 + 3 < ncols) ? __ldcg(src + 3) : 0.0f;
         }
-      float acc[8][4];
-      mma_block_product(acc, warp < 4 ? O0 : O1, m0, Dq, lane);
+      }
+      ptx::mbar_wait(&mma_bar, mma_phase);
+      mma_phase ^= 1;
+      ptx::tc_fence_after();
+      {   // TMEM -> registers -> row-major staging tile: warp w reads lanes 32 (w & 3).., columns 32 (w >> 2)..
+        uint32_t r[32];
+        const int lrow = 32 * (warp & 3) + lane, col0 = 32 * (warp >> 2);
+        ptx::tmem_ld_32x32(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0, r);
+        ptx::tmem_ld_wait();
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh)
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(stage + lrow * STAGE_PITCH + col0 + 4 * q) =
+              make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+      }
+      ptx::tc_fence_before();
+      __syncthreads();
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          const int row = rbase + 8 * hh, c = 8 * nt + 2 * tq;
-          float* dst = A + (size_t)row * lda + cur_cb + c;
-          const float vx = cur[hh][nt].x - acc[nt][2 * hh], vy = cur[hh][nt].y - acc[nt][2 * hh + 1];
-          if (fast) *reinterpret_cast<float2*>(dst) = make_float2(vx, vy);
-          else {
-            if (row < N && c < ncols && cur_cb + c <= row) dst[0] = vx;
-            if (row < N && c + 1 < ncols && cur_cb + c + 1 <= row) dst[1] = vy;
-          }
+      for (int i = 0; i < 8; ++i) {
+        const int lrow = rr + 16 * i, row = cur_row0 + lrow;
+        if (row >= N) continue;
+        const float4 d = *reinterpret_cast<const float4*>(stage + lrow * STAGE_PITCH + 4 * c4);
+        float* dst = A + (size_t)row * lda + cur_cb + 4 * c4;
+        const int col = cur_cb + 4 * c4;
+        if (vec && ncols == NB && col + 3 <= row) {
+          *reinterpret_cast<float4*>(dst) = make_float4(cur[i].x - d.x, cur[i].y - d.y, cur[i].z - d.z, cur[i].w - d.w);
+        } else {
+          if (4 * c4 + 0 < ncols && col + 0 <= row) dst[0] = cur[i].x - d.x;
+          if (4 * c4 + 1 < ncols && col + 1 <= row) dst[1] = cur[i].y - d.y;
+          if (4 * c4 + 2 < ncols && col + 2 <= row) dst[2] = cur[i].z - d.z;
+          if (4 * c4 + 3 < ncols && col + 3 <= row) dst[3] = cur[i].w - d.w;
         }
+      }
+      __syncthreads();                                      // staging tile and operand tiles are free again
     }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_d, 64); }
     return;
   }
 
@@ -514,38 +539,48 @@ __global__ void __launch_bounds__(STEP_THREADS) potrf_step_kernel(float* __restr
   const int strip = blockIdx.x;
   const int nb = min(NB, N - j);
   const int row0 = j + strip * NB;
-  float* Dp = step_smem + 2 * BLK_FLOATS;      // previous panel, diagonal rows (row-major, tensor-core operand)
-  float* Op = step_smem + 3 * BLK_FLOATS;      // previous panel, own rows
   {
     BlockRegs<256> rs, rp;
     BlockRegsRM rdp, rop;
     block_load<256>(rs, t, A, lda, j, j, nb, nb, vec);
     if (strip > 0) block_load<256>(rp, t, A, lda, row0, j, N - row0, nb, vec);
-    if (jprev >= 0) {
+    if (use_tc) {
       block_load_rm(rdp, t, A, lda, j, jprev, nb, vec);
-      if (strip > 0) block_load_rm(rop, t, A, lda, row0, jprev, N - row0, vec);
+      block_load_rm(rop, t, A, lda, row0, jprev, strip > 0 ? N - row0 : 0, vec);
     }
     block_store_T<256>(S, t, rs);
     if (strip > 0) block_store_T<256>(P, t, rp);
-    if (jprev >= 0) {
-      block_store_rm(Dp, t, rdp);
-      if (strip > 0) block_store_rm(Op, t, rop);
+    if (use_tc) {
+      block_store_sw(a_hi, a_lo, 128, 0, t, rdp);           // rows 0-63: previous panel, diagonal rows (also the B operand)
+      block_store_sw(a_hi, a_lo, 128, NB, t, rop);          // rows 64-127: previous panel, own rows (zeros for strip 0)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
   }
   if (t == 0) { s_fail = 0; s_progress = 0; }
+  ptx::tc_fence_before();
   __syncthreads();
+  ptx::tc_fence_after();
   STEP_MARK(1, t == 0);
-  if (jprev >= 0) {
-    {     // S -= Dp Dp^T (warps 0-3) and P -= Op Dp^T (warps 4-7) on the tensor cores
-      const int warp = t >> 5, lane = t & 31;
-      const int m0 = 16 * (warp & 3);
-      if (warp < 4 || strip > 0) {
-        float acc[8][4];
-        mma_block_product(acc, warp < 4 ? Dp : Op, m0, Dp, lane);
-        mma_subtract_T(warp < 4 ? S : P, acc, m0, lane);
-      }
+  if (use_tc) {
+    // [S; P] -= [Dp; Op] Dp^T : one 128 x 64 x 64 product on the tensor cores (tcgen05, 3xTF32), accumulator in TMEM
+    const uint32_t tmem_d = tmem_slot;
+    if (t == 0) step_issue_product(tmem_d, a_hi, a_lo, a_hi, a_lo, 128, &mma_bar);
+    ptx::mbar_wait(&mma_bar, mma_phase);
+    mma_phase ^= 1;
+    ptx::tc_fence_after();
+    if ((warp & 3) < 2 || strip > 0) {                      // lanes 0-63 -> S, lanes 64-127 -> P
+      uint32_t r[32];
+      const int lrow = 32 * (warp & 3) + lane, col0 = 32 * (warp >> 2);
+      ptx::tmem_ld_32x32(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0, r);
+      ptx::tmem_ld_wait();
+      float (*T)[LT_PITCH] = lrow < NB ? S : P;
+      const int rloc = lrow & (NB - 1);
+#pragma unroll
+      for (int q = 0; q < 32; ++q) T[col0 + q][rloc] -= __uint_as_float(r[q]);
     }
+    ptx::tc_fence_before();
     __syncthreads();
+    if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_d, 64); }
   }
   if (nb < NB) {   // identity padding of the ragged last block
     for (int e = t; e < NB * NB; e += STEP_THREADS) {
@@ -591,11 +626,11 @@ __global__ void __launch_bounds__(STEP_THREADS) potrf_step_kernel(float* __restr
     // ---- panel rows: x L^T = a by forward substitution, chunk c as soon as chunk c of L is final ----
     const int r = t - NB;
     for (int c0 = 0; c0 < NB; c0 += 8) {
-      while (s_progress < c0 / 8) { }
+      while (s_progress < c0 / 8) __nanosleep(64);
       __threadfence_block();
       float acc[8];
       chunk_update(acc, P, S, c0, r);
-      while (s_progress < c0 / 8 + 1) { }
+      while (s_progress < c0 / 8 + 1) __nanosleep(64);    // polling without a pause steals shared-memory issue slots from the factorising warps
       __threadfence_block();
       float l[8][8];
 #pragma unroll
@@ -643,6 +678,7 @@ __global__ void __launch_bounds__(STEP_THREADS) potrf_step_kernel(float* __restr
 #ifdef DB_POTRF_TIMING
   if (dbg != nullptr && blockIdx.x == 1 && t == 0) { unsigned long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); dbg[6] = (long long)g; }
 #endif
+#endif  // DB_SM100
 }
 
 // C[i, jc] -= sum_{k in [k0,k1)} A[i,k] A[jc,k]  for i in [i0,N), jc in [j0,j1), jc <= i   (lower part only)
