@@ -385,7 +385,13 @@ def run_b200(args):
             'clocks': clocks,
             'gplvm': {'metric': 'GPLVM LML+grad evals/s at N=5000', 'value': world * 1e3 / gp_ms, 'unit': 'evals/s',
                       'ms_per_eval': gp_ms, 'N': GP_N, 'D': GP_D, 'Q': GP_Q, 'info': gp_info, 'scaling': 'replicas only',
-                      'algorithmic_tflops': gp_flop / (gp_ms * 1e-3) / 1e12},
+                      'algorithmic_tflops': gp_flop / (gp_ms * 1e-3) / 1e12,
+                      # N^3 + 3 N^2 D algorithmic FLOP against the fp32 FFMA peak that bounds the reference's
+                      # formulation (148 SMs x 128 FMA x 2 x max SM clock); the N^3-class stages run as 3xTF32 tcgen05 GEMMs
+                      'roofline': {'bound': 'fp32-ffma', 'achieved': gp_flop / (gp_ms * 1e-3) / 1e12,
+                                   'peak': 148 * 128 * 2 * 1.965e9 / 1e12, 'unit': 'TFLOP/s',
+                                   'frac': gp_flop / (gp_ms * 1e-3) / (148 * 128 * 2 * 1.965e9),
+                                   'note': 'latency-bound Cholesky critical path: 79 column-block steps of 16 us (DESIGN.md K4)'}},
             'gpdbn': gpdbn,
         }
         print(json.dumps(line))
