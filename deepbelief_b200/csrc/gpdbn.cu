@@ -55,21 +55,29 @@ __global__ void cross_entropy_grad_kernel(const float* __restrict__ probs, const
   }
 }
 
-// out[c] = beta * out[c] + scale * sum_n A[n,c] : one CTA per 32 columns, 8 row lanes
+// out[c] = beta * out[c] + scale * sum_n A[n,c] : one CTA per 32 columns (x) and row slice (y), 8 row lanes.
+// gridDim.y > 1 (tall matrices with few columns, e.g. the bias gradients over a batch of 5000): the slices add their
+// partial sums with atomics into out, which colsum_scale_kernel has already replaced by beta * out.
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A, int M, int N, float scale, float beta,
-                                                     float* __restrict__ out) {
+                                                     float* __restrict__ out, int rows_per_slice) {
   __shared__ float part[8][33];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31), ry = threadIdx.x >> 5;
+  const int r_begin = blockIdx.y * rows_per_slice, r_end = min(M, r_begin + rows_per_slice);
   float s = 0.0f;
-  if (c < N) for (int r = ry; r < M; r += 8) s += __ldg(A + (size_t)r * N + c);
+  if (c < N) for (int r = r_begin + ry; r < r_end; r += 8) s += __ldg(A + (size_t)r * N + c);
   part[ry][threadIdx.x & 31] = s;
   __syncthreads();
   if (ry == 0 && c < N) {
     float t = 0.0f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x & 31];
-    out[c] = (beta != 0.0f ? beta * out[c] : 0.0f) + scale * t;
+    if (gridDim.y > 1) atomicAdd(out + c, scale * t);
+    else out[c] = (beta != 0.0f ? beta * out[c] : 0.0f) + scale * t;
   }
+}
+__global__ void colsum_scale_kernel(float* __restrict__ out, int N, float beta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < N) out[c] = beta != 0.0f ? beta * out[c] : 0.0f;
 }
 
 // ---- top layer, forward --------------------------------------------------------------------------------
@@ -293,7 +301,16 @@ extern "C" int db_sbm_gather(db_handle_t h, db_stream_t stream, const float* gW_
 
 extern "C" int db_colsum(db_handle_t h, db_stream_t stream, const float* A, int M, int N, float scale, float beta, float* out) {
   DB_REQUIRE(h, A && out && M > 0 && N > 0, "null operand or empty shape");
-  colsum_kernel<<<(N + 31) / 32, 256, 0, (cudaStream_t)stream>>>(A, M, N, scale, beta, out);
+  const int col_tiles = (N + 31) / 32;
+  int slices = 1;
+  if (M >= 2048 && col_tiles < h->num_sms) {
+    slices = (2 * h->num_sms + col_tiles - 1) / col_tiles;
+    if (slices > M / 256) slices = M / 256;
+    if (slices < 1) slices = 1;
+  }
+  const int rows_per_slice = (M + slices - 1) / slices;
+  if (slices > 1) colsum_scale_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(out, N, beta);
+  colsum_kernel<<<dim3(col_tiles, slices), 256, 0, (cudaStream_t)stream>>>(A, M, N, scale, beta, out, rows_per_slice);
   return check_launch(h, "colsum");
 }
 

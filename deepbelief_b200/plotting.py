@@ -41,9 +41,25 @@ class ImageGridPlotter(_Recorder):
         self._dump(fig_name, images=images)
 
 
+def _latent_grid(xlim, ylim, delta, yflipud=False):
+    """The evaluation grid of the reference's latent-space plotters (plotting.py:174-184): every (x, y) with
+    x in xlim, y in ylim on a `delta` lattice, x fastest; the sample plotter walks y from the top."""
+    x = np.arange(xlim[0], xlim[1] + delta, delta)
+    y = np.arange(ylim[0], ylim[1] + delta, delta)
+    xx, yy = np.meshgrid(x, y)
+    xx = xx.ravel()[:, None]
+    yy = (np.flipud(yy.ravel()) if yflipud else yy.ravel())[:, None]
+    return np.hstack([xx, yy]).astype(np.float32)
+
+
 class LatentPointPlotter(_Recorder):
-    def __init__(self, grid=None, output_dir=None, **kw):
-        super().__init__(output_dir, **kw)
+    """Constructor arguments as the reference (plotting.py:189-199): xlim, ylim, delta build the grid on which the layers
+    evaluate the predictive variance; a ready-made `grid` may be passed instead."""
+
+    def __init__(self, xlim=None, ylim=None, delta=None, grid=None, output_dir=None, **kw):
+        super().__init__(output_dir, xlim=xlim, ylim=ylim, delta=delta, **kw)
+        if grid is None and xlim is not None and ylim is not None and delta:
+            grid = _latent_grid(xlim, ylim, delta)
         self.grid = grid
 
     def plot(self, X, log_var, fig_name, labels=None):
@@ -51,8 +67,13 @@ class LatentPointPlotter(_Recorder):
 
 
 class LatentSamplePlotter(_Recorder):
-    def __init__(self, grid=None, num_samples_to_average=100, output_dir=None, **kw):
-        super().__init__(output_dir, **kw)
+    """plotting.py:462-483: grid on a `delta` lattice (default 0.5), y descending."""
+
+    def __init__(self, image_shape=None, xlim=None, ylim=None, delta=0.5, grid=None, num_samples_to_average=100,
+                 output_dir=None, **kw):
+        super().__init__(output_dir, image_shape=image_shape, xlim=xlim, ylim=ylim, delta=delta, **kw)
+        if grid is None and xlim is not None and ylim is not None and delta:
+            grid = _latent_grid(xlim, ylim, delta, yflipud=True)
         self.grid = grid
         self.num_samples_to_average = num_samples_to_average
 
