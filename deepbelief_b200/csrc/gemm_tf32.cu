@@ -11,7 +11,7 @@
 // epilogue threads in registers, in fp32 round-to-nearest (deterministic).
 //
 // Same persistent, warp-specialised structure as gemm_tc.cu: warp 0 TMA producer (4 tensor maps, 128B swizzle,
-// 64B swizzle, 6-stage ring of 32 KB), warp 1 tcgen05.mma kind::tf32 128x128x8, warp 2 TMEM allocator (2 main + 2
+// 128B swizzle, 3-stage ring of 64 KB), warp 1 tcgen05.mma kind::tf32 128x128x8, warp 2 TMEM allocator (2 main + 2
 // correction accumulator stages), warps 4-7 epilogue.
 // Output orientation: TMEM lanes = rows of Y (= columns of C), so a warp writes 32 consecutive floats of a row of C.
 #include "context.h"
@@ -26,12 +26,13 @@ namespace {
 
 constexpr int BM = 128;       // rows of Y per tile (TMEM lanes)   -> columns of C
 constexpr int BN = 128;       // rows of X per tile (TMEM columns) -> rows of C (128 partial sums per epilogue thread)
-constexpr int BK = 16;        // fp32 elements = one 64-byte swizzle row
+constexpr int BK = 32;        // fp32 elements = one 128-byte swizzle row
 constexpr int UK = 8;         // tf32 MMA K
-constexpr int STAGES = 6;         // 6 x 32 KB in flight
+constexpr int STAGES = 3;         // 3 x 64 KB in flight; 12 MMAs (768 cycles) per barrier round trip (BK = 16 / 6 stages
+                                  // kept the tensor pipe only 48-50 % busy: the single issuing thread was handshake-bound)
 constexpr int A_BYTES = BM * BK * 4;    // 16 KB
-constexpr int B_BYTES = BN * BK * 4;    // 32 KB
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // hi + lo of both operands: 96 KB
+constexpr int B_BYTES = BN * BK * 4;    // 16 KB
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // hi + lo of both operands: 64 KB
 constexpr int ACC_STAGES = 2;     // main accumulators (hi*hi), flushed every K_CHUNK columns
 constexpr int CORR_STAGES = 2;    // correction accumulators (lo*hi + hi*lo), flushed once per tile
 constexpr int TMEM_COLS = (ACC_STAGES + CORR_STAGES) * BN;
@@ -63,16 +64,8 @@ struct Tf32Params {
   float debias;           // 1 + expected relative shrink of one K chunk of the truncating hi*hi accumulator
 };
 
-// K-major operand tile written by TMA with SWIZZLE_64B: rows are 64 B apart, 8-row groups 512 B apart
-__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
-  d |= (uint64_t)1u << 16;
-  d |= (uint64_t)(512u >> 4) << 32;
-  d |= (uint64_t)1u << 46;
-  d |= (uint64_t)4u << 61;                            // layout type SWIZZLE_64B
-  return d;
-}
+// K-major operand tile written by TMA with SWIZZLE_128B: rows are 128 B apart, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) { return ptx::umma_desc_k_sw128(smem_addr); }
 
 __global__ void __launch_bounds__(THREADS, 1)
 tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tm_y_hi, const __grid_constant__ CUtensorMap tm_y_lo,
@@ -327,7 +320,7 @@ bool make_tmap_f32(CUtensorMap* tm, const void* base, int rows, int cols, int ld
   cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
