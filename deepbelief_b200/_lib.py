@@ -108,6 +108,9 @@ SIGNATURES = {
                                     c_float_p, c_float_p, c_float_p]),
     'db_testgen_reduce_samples': (c_int, [c_void_p, c_void_p, c_float_p, c_float_p, c_float_p, c_float_p, c_int, c_int,
                                           c_int, c_float, c_float_p, c_float_p]),
+    'db_heldout_mse': (c_int, [c_void_p, c_void_p, c_float_p, c_float_p, c_int, c_int, c_int, c_float_p, c_float_p]),
+    'db_interp_objective': (c_int, [c_void_p, c_void_p, c_float_p, c_float_p, c_float_p, c_float_p, c_int, c_int, c_float,
+                                    c_float_p, c_float_p, c_float_p]),
     'db_gemm': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float_p, c_int, c_float_p,
                         c_int, c_float, c_float_p, c_int]),
     'db_concrete_backward': (c_int, [c_void_p, c_void_p, c_float_p, c_float_p, c_float_p, c_int, c_int, c_float,

@@ -538,6 +538,89 @@ __global__ void __launch_bounds__(256) testgen_reduce_samples_kernel(const float
 }
 }}  // namespace db::<anon>
 
+// ---- GPRBM.test_held_out_data (gprbm.py:440-466) and GPRBM.interp_test (gprbm.py:614-689) ---------------------
+namespace db { namespace {
+// loss[r] = mean_m sum_d (T[m,d] - Vs[r,d])^2 — dist.mse (dist.py:5-21) with the [M,Dim] test set as `predictions` and the
+// single down-propagated row of restart r broadcast as `targets`; g_Vs[r,:] = d loss[r] / d Vs[r,:]
+__global__ void __launch_bounds__(256) heldout_mse_kernel(const float* __restrict__ Vs, const float* __restrict__ T, int R, int M,
+                                                         int Dim, float* __restrict__ loss, float* __restrict__ g_Vs) {
+  __shared__ float red[8];
+  const int r = blockIdx.x;
+  const float inv_m = 1.0f / (float)M;
+  float acc = 0.0f;
+  for (int d = threadIdx.x; d < Dim; d += 256) {
+    const float v = __ldg(Vs + (size_t)r * Dim + d);
+    float sq = 0.0f, gs = 0.0f;
+    for (int m = 0; m < M; ++m) {
+      const float diff = __ldg(T + (size_t)m * Dim + d) - v;
+      sq = fmaf(diff, diff, sq);
+      gs += diff;
+    }
+    acc += sq;
+    g_Vs[(size_t)r * Dim + d] = -2.0f * gs * inv_m;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    loss[r] = t * inv_m;
+  }
+}
+// objective = mean over the P+1 segments start -> Xi[0] -> ... -> Xi[P-1] -> end of |segment|^2 + lambda * mean_p log pv[p]
+// (gprbm.py:651-660); g_x [P,Q] = gradient of the segment term, g_pv [P] = lambda / (P pv[p]). One block (P is tens of points).
+__global__ void __launch_bounds__(256) interp_objective_kernel(const float* __restrict__ Xi, const float* __restrict__ xs,
+                                                              const float* __restrict__ xe, const float* __restrict__ pv, int P, int Q,
+                                                              float lambda, float* __restrict__ objective, float* __restrict__ g_x,
+                                                              float* __restrict__ g_pv) {
+  __shared__ float red[8];
+  const float inv_seg = 1.0f / (float)(P + 1), inv_p = 1.0f / (float)P;
+  float acc = 0.0f;
+  for (int i = threadIdx.x; i < (P + 1) * Q; i += 256) {           // segment s = i / Q runs from point s-1 to point s
+    const int s = i / Q, q = i - s * Q;
+    const float a = s == 0 ? __ldg(xs + q) : __ldg(Xi + (size_t)(s - 1) * Q + q);
+    const float b = s == P ? __ldg(xe + q) : __ldg(Xi + (size_t)s * Q + q);
+    acc = fmaf(b - a, b - a, acc);
+  }
+  acc *= inv_seg;
+  for (int p = threadIdx.x; p < P; p += 256) {
+    const float v = __ldg(pv + p);
+    acc = fmaf(lambda * inv_p, logf(v), acc);
+    g_pv[p] = lambda * inv_p / v;
+  }
+  for (int i = threadIdx.x; i < P * Q; i += 256) {
+    const int p = i / Q, q = i - p * Q;
+    const float x = __ldg(Xi + i);
+    const float prev = p == 0 ? __ldg(xs + q) : __ldg(Xi + i - Q);
+    const float next = p == P - 1 ? __ldg(xe + q) : __ldg(Xi + i + Q);
+    g_x[i] = 2.0f * inv_seg * (2.0f * x - prev - next);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    *objective = t;
+  }
+}
+}}  // namespace db::<anon>
+
+extern "C" int db_heldout_mse(db_handle_t h, db_stream_t stream, const float* Vs, const float* T, int R, int M, int Dim,
+                              float* loss, float* g_Vs) {
+  DB_REQUIRE(h, Vs && T && loss && g_Vs && R > 0 && M > 0 && Dim > 0, "null operand or bad shape");
+  db::heldout_mse_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(Vs, T, R, M, Dim, loss, g_Vs);
+  return check_launch(h, "heldout_mse");
+}
+
+extern "C" int db_interp_objective(db_handle_t h, db_stream_t stream, const float* Xi, const float* x_start, const float* x_end,
+                                   const float* pred_var, int P, int Q, float lambda, float* objective, float* g_x, float* g_pv) {
+  DB_REQUIRE(h, Xi && x_start && x_end && pred_var && objective && g_x && g_pv && P > 0 && Q > 0, "null operand or bad shape");
+  db::interp_objective_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(Xi, x_start, x_end, pred_var, P, Q, lambda, objective, g_x, g_pv);
+  return check_launch(h, "interp_objective");
+}
+
 extern "C" int db_testgen_meanloss(db_handle_t h, db_stream_t stream, const float* Vs, const float* target, const float* pred_var,
                                    int R, int S, int Dim, float log_var_scaling, float* loss, float* model_point, float* g_Vs) {
   DB_REQUIRE(h, Vs && target && pred_var && loss && g_Vs && R > 0 && S > 0 && Dim > 0, "null operand or bad shape");

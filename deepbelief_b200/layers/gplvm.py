@@ -8,7 +8,9 @@ gradient, replacing TF autodiff of gplvm.py:425-428) and db_gp_predict.
 Eager semantics: attributes the reference builds as graph tensors (`K`, `L`, `loss`, `pred_mean`,
 `pred_var`, …) are `compat.Lazy` values here — re-evaluated whenever a `Session.run` (or `.eval()`)
 asks for them, exactly as a TF graph node would be.
-Not supported: ARD length-scales (gplvm.py:24-28) — no example or test of the reference uses them.
+ARD length-scales (gplvm.py:24-28, gamma [1,Q]): K depends on x only through x / gamma, so the layers hand the CUDA
+chain the latents in kernel coordinates (X / gamma, scalar gamma slot fixed at 1) and chain the gradients back:
+dL/dX = dL/dXs / gamma, dL/dgamma_q = -sum_n dL/dXs[n,q] X[n,q] / gamma_q^2.
 """
 import pickle
 
@@ -31,21 +33,32 @@ class SEKernel(layer.Stateful):
     optimisation variables, or the constant 1.0 when passed as False (gplvm.py:18-49)."""
 
     def __init__(self, alpha=1.0, gamma=1.0, ARD=False, Q=None, session=None, name='SEKernel', device='cuda'):
-        if ARD and gamma is not False:
-            raise NotImplementedError('ARD length-scales are not supported by the CUDA GP path')
         self.Q = Q
         self.device = device
-        self.flags = (0 if alpha is False else _FLAG_ALPHA) | (0 if gamma is False else _FLAG_GAMMA)
+        self.ard = bool(ARD) and gamma is not False
+        self.flags = (0 if alpha is False else _FLAG_ALPHA) | (0 if (gamma is False or self.ard) else _FLAG_GAMMA)
         # [opt_alpha, opt_gamma, (noise slot, owned by the GP layer)]
         self._hyp = torch.zeros(3, dtype=torch.float32, device=device)
         self._hyp[0] = _inv_softplus(alpha) if alpha is not False else 0.0
-        self._hyp[1] = _inv_softplus(gamma) if gamma is not False else 0.0
+        self._opt_gamma_vec = None
+        if self.ard:
+            assert Q is not None, 'ARD needs the latent dimensionality Q'
+            if type(gamma) == np.ndarray:
+                assert gamma.shape == (1, Q)                                       # gplvm.py:26-27
+            g = (gamma * np.ones((1, Q))).astype(np.float64)
+            self._opt_gamma_vec = torch.as_tensor(preprocessing.inverse_softplus(g).reshape(-1).astype(np.float32)).to(device)
+        else:
+            self._hyp[1] = _inv_softplus(gamma) if gamma is not False else 0.0
         super().__init__(params={'alpha': lambda: self.alpha, 'gamma': lambda: self.gamma}, session=session, name=name)
 
-    def bind(self, storage):
-        """Move the optimisation variables into `storage` (a 3-float view of the GP layer's packed parameters)."""
+    def bind(self, storage, ard_storage=None):
+        """Move the optimisation variables into `storage` (a 3-float view of the GP layer's packed parameters; the ARD
+        length-scales into `ard_storage` [Q])."""
         storage[:2].copy_(self._hyp[:2])
         self._hyp = storage
+        if self.ard and ard_storage is not None:
+            ard_storage.copy_(self._opt_gamma_vec)
+            self._opt_gamma_vec = ard_storage
 
     @property
     def opt_alpha(self):
@@ -53,7 +66,24 @@ class SEKernel(layer.Stateful):
 
     @property
     def opt_gamma(self):
-        return self._hyp[1]
+        return self._opt_gamma_vec.view(1, -1) if self.ard else self._hyp[1]
+
+    def gamma_vec(self):
+        """ARD length-scales [Q] (softplus of the optimisation variables)."""
+        return ops.softplus(self._opt_gamma_vec)
+
+    def scale(self, x):
+        """x in kernel coordinates: x / gamma per latent dimension with ARD (gplvm.py:67), x itself otherwise (the scalar
+        gamma is applied inside the CUDA kernels)."""
+        if not self.ard or x is None:
+            return x
+        return (x / self.gamma_vec().view(1, -1)).contiguous()
+
+    def chain_scale(self, dXs, X):
+        """(dL/dX, dL/dopt_gamma [Q]) from the gradient with respect to the scaled latents."""
+        gam = self.gamma_vec().view(1, -1)
+        d_gamma = -(dXs * X).sum(dim=0) / (gam.view(-1) ** 2)
+        return dXs / gam, d_gamma * torch.sigmoid(self._opt_gamma_vec)
 
     def effective(self, noise_flags=0, fixed_noise=0.0, jitter=0.0):
         """Device tensor [alpha, gamma, noise] after the softplus / constant rules."""
@@ -65,18 +95,20 @@ class SEKernel(layer.Stateful):
 
     @property
     def gamma(self):
-        return self.effective()[1]
+        return self.gamma_vec().view(1, -1) if self.ard else self.effective()[1]
 
     def state_tensors(self):
+        if self.ard:
+            return {'hyp': self._hyp, 'opt_gamma_ard': self._opt_gamma_vec}
         return {'hyp': self._hyp}
 
     def K(self, x, y=None, diag=False):
         """gplvm.py:84-86. diag=True with y=None is exactly alpha (gplvm.py:64-66)."""
-        x = to_device(x, self.device)
+        x = self.scale(to_device(x, self.device))
         hyp = self.effective()
         if diag and y is None:
             return hyp[0].expand(x.shape[0]).contiguous()
-        full = ops.gram_rbf(x, to_device(y, self.device) if y is not None else None, hyp, add_noise=False)
+        full = ops.gram_rbf(x, self.scale(to_device(y, self.device)) if y is not None else None, hyp, add_noise=False)
         if diag:
             return torch.diagonal(full).contiguous()
         return full
@@ -115,9 +147,10 @@ class GPLVM(layer.Layer):
         assert self.X0.shape[1] == self.Q
         self.N, self.D = self.X0.shape[0], self.Y_np.shape[1]
 
-        # packed trainables [X | opt_alpha, opt_gamma, opt_noise]
+        # packed trainables [X | opt_alpha, opt_gamma, opt_noise | ARD opt_gamma [Q]]
         nq = self.N * self.Q
-        self._params = torch.zeros(nq + 3, dtype=torch.float32, device=device)
+        n_ard = self.Q if (kern is not None and getattr(kern, 'ard', False)) else 0
+        self._params = torch.zeros(nq + 3 + n_ard, dtype=torch.float32, device=device)
         self.X = self._params[:nq].view(self.N, self.Q)
         self.X.copy_(to_device(self.X0, device))
         self._hyp = self._params[nq:nq + 3]
@@ -131,7 +164,7 @@ class GPLVM(layer.Layer):
             self._hyp[2] = _inv_softplus(noise_variance)               # gplvm.py:145-152
 
         self.kern = kern or SEKernel(session=session, Q=self.Q, device=device)
-        self.kern.bind(self._hyp)
+        self.kern.bind(self._hyp, self._params[nq + 3:] if n_ard else None)
 
         if x_test_var is not None:
             self.x_test = x_test_var
@@ -191,7 +224,7 @@ class GPLVM(layer.Layer):
 
     # ---- model ---------------------------------------------------------------------------------------------------
     def _evaluate(self, want_grad=False, need_factor=False):
-        scal, dX, info = self._plan.evaluate(self.X, self.Y, self._hyp, self.flags, fixed_noise=self.fixed_noise,
+        scal, dX, info = self._plan.evaluate(self.kern.scale(self.X), self.Y, self._hyp, self.flags, fixed_noise=self.fixed_noise,
                                              jitter=self.noise_jitter or 0.0, x_prior_weight=0.0, include_const=True,
                                              want_grad=want_grad, L_out=self._L if need_factor else None)
         return scal, dX, info
@@ -218,7 +251,7 @@ class GPLVM(layer.Layer):
 
     def build_K(self):
         """K_f(X) + (noise [+ jitter]) I (gplvm.py:218-224)."""
-        return ops.gram_rbf(self.X, None, self._effective_hyp(), add_noise=True)
+        return ops.gram_rbf(self.kern.scale(self.X), None, self._effective_hyp(), add_noise=True)
 
     def build_log_det(self):
         """2 sum log L_ii (gplvm.py:226-228)."""
@@ -235,24 +268,29 @@ class GPLVM(layer.Layer):
     def loss_and_grad(self):
         """(loss, dX [N,Q], d/d(opt_alpha, opt_gamma, opt_noise) [3]) — K3-K6 in one call."""
         scal, dX, info = self._evaluate(want_grad=True)
+        if self.kern.ard:                                          # (loss, dX, d/d(opt_alpha, opt_gamma [Q], opt_noise))
+            dX, d_gam = self.kern.chain_scale(dX, self.X)
+            return scal[0].clone(), dX, torch.cat([scal[3:4], d_gam, scal[5:6]])
         return scal[0].clone(), dX.clone(), scal[3:6].clone()     # the plan's buffers are reused by the next call
 
     def _xstar(self, x=None):
         if x is None:
             x = self.x_ph.value
         assert x is not None, 'no test latent points: feed x_ph or pass x_test_var'
-        return to_device(np.array(to_numpy(x), ndmin=2) if not isinstance(x, torch.Tensor) else x, self.device)
+        return self.kern.scale(to_device(np.array(to_numpy(x), ndmin=2) if not isinstance(x, torch.Tensor) else x, self.device))
 
     def build_pred_mean(self, x=None):
         """(L^-1 K_Xx)^T (L^-1 Y) + Y_mean (gplvm.py:246-254)."""
         Lf, S = self._factor()
-        mean, _, _ = ops.gp_predict(self.X, Lf, S, self.Y_mean, self._xstar(x), self._effective_hyp(), want_var=False)
+        mean, _, _ = ops.gp_predict(self.kern.scale(self.X), Lf, S, self.Y_mean, self._xstar(x), self._effective_hyp(),
+                                    want_var=False)
         return mean
 
     def build_pred_var(self, x=None):
         """alpha - colsum((L^-1 K_Xx)^2); noise not added back; asserts >= 0 (gplvm.py:278-288)."""
         Lf, S = self._factor()
-        _, var, info = ops.gp_predict(self.X, Lf, None, None, self._xstar(x), self._effective_hyp(), want_mean=False)
+        _, var, info = ops.gp_predict(self.kern.scale(self.X), Lf, None, None, self._xstar(x), self._effective_hyp(),
+                                      want_mean=False)
         bad = int(info.item())
         if bad:
             raise RuntimeError('assert_non_negative(pred_var) failed at test point %d' % (bad - 1))
@@ -349,7 +387,10 @@ class GPLVM(layer.Layer):
         try:
             for i in range(1, num_iterations + 1):
                 scal, dX, info = self._evaluate(want_grad=True)
-                grad[:nq].copy_(dX.view(-1))
+                if self.kern.ard:
+                    dX, d_gam = self.kern.chain_scale(dX, self.X)
+                    grad[nq + 3:].copy_(d_gam)
+                grad[:nq].copy_(dX.reshape(-1))
                 grad[nq:nq + 3].copy_(scal[3:6])
                 ops.optimizer_step(optimizer.descriptor(), self._params, grad, state)
                 self._version += 1
@@ -381,8 +422,12 @@ class GPLVM(layer.Layer):
     def latent_search_loss(self, x, test_point, log_var_scaling=0.1, cache=None, want_outputs=False):
         """(loss [R], d loss / d x [R,Q], ...) of gplvm.py:478-483 at restarts x [R,Q] for one test point."""
         Kinv, A = cache or self._latent_search_cache()
-        return ops.testgen_eval(self.X, Kinv, A, self.Y_mean, self._effective_hyp(), to_device(x, self.device),
-                                to_device(test_point, self.device).reshape(-1), log_var_scaling, want_outputs)
+        out = ops.testgen_eval(self.kern.scale(self.X), Kinv, A, self.Y_mean, self._effective_hyp(),
+                               self.kern.scale(to_device(x, self.device)), to_device(test_point, self.device).reshape(-1),
+                               log_var_scaling, want_outputs)
+        if self.kern.ard:                                          # d/dx = d/d(x / gamma) / gamma
+            out = (out[0], out[1] / self.kern.gamma_vec().view(1, -1)) + tuple(out[2:])
+        return out
 
     def test_generalisation(self, test_data, output_table_path, optimizer, log_var_scaling=0.1, num_iterations=1000,
                             num_runs=1):

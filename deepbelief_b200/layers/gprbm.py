@@ -62,6 +62,9 @@ class GPRBM(bgrbm.BGRBM):
             self.noise_jitter, self._noise_flag = noise_jitter, _FLAG_NOISE
             self._hyp[2] = float(preprocessing.inverse_softplus(np.float64(noise_variance)))   # gprbm.py:68-73
         self.kern = kern or gplvm.SEKernel(session=session, Q=self.Q, device=device)
+        if getattr(self.kern, 'ard', False):
+            raise NotImplementedError('GPRBM takes a scalar length-scale (the GPDBN examples fix gamma, gpdbn_horses/flags.py:35-36); '
+                                      'ARD kernels are supported by GPLVM')
         self.kern.bind(self._hyp)
         self._plan = ops.GpdbnPlan(self.N, self.Q, self.D, device=device)
         self._Lfac = None
@@ -461,11 +464,10 @@ class GPRBM(bgrbm.BGRBM):
         Kinv = ops.trsm_lower(self._Lfac, ops.trsm_lower(self._Lfac, eye), trans=True)
         return Kinv, ops.gemm(Kinv, self.H2_var)
 
-    def latent_search_loss(self, x, test_point, log_var_scaling=0.1, num_samples=1, cache=None, draws=None,
-                           want_outputs=False):
-        """loss [R] and d loss / d x [R,Q] of gprbm.py:490-499 at restarts x [R,Q], each with `num_samples` Gaussian
-        samples of the top hidden layer pushed down the Concrete stack (rows ordered r * S + s).
-        draws (optional injected randomness): {'eps' [R*S,D], 'down_top' [R*S,Vt], 'down': [per lower layer, top first]}."""
+    def _latent_forward(self, x, num_samples, cache=None, draws=None):
+        """Frozen-model forward at test latents x [R,Q], S samples each (rows r * S + s): K_Xx, predictive variance,
+        sample mean (gprbm.py:208-232 with sigma_h = alpha_h sqrt(pred_var), gprbm.py:114-115) and downprop through the
+        Concrete stack. Returns the tape the x-gradient needs."""
         if self.temperature is None:
             raise NotImplementedError('the latent search differentiates through Concrete units (temperature)')
         Kinv, B = cache or self._latent_search_cache()
@@ -476,7 +478,6 @@ class GPRBM(bgrbm.BGRBM):
         inj = lambda v: None if v is None else to_device(v, dev)  # noqa: E731
         hyp = ops.gp_effective_hyp(self._hyp, self.flags, self.fixed_noise, self.noise_jitter or 0.0)
         alpha_h = self.alpha_h.reshape(-1)
-        target = to_device(test_point, dev).reshape(-1)
         Kxs = ops.gram_rbf(self.X, x, hyp)                                   # [N,R]
         Hm = ops.gemm(Kxs, B, trans_a=True)                                  # (L^-1 K_Xx)^T (L^-1 H2)
         Cv = ops.gemm(Kinv, Kxs)
@@ -495,13 +496,34 @@ class GPRBM(bgrbm.BGRBM):
                 raise NotImplementedError('the latent search differentiates through Concrete units (temperature)')
             q, d = lay._down(d, lay.visible_act, L.SAMPLE_CONCRETE, None, inj(dr['down'][i]) if 'down' in dr else None)
             tape.append((lay, q, d))
-        loss, model_point, g = ops.testgen_meanloss(d, target, pv, R, S, log_var_scaling, want_outputs)
-        for lay, q, d_out in reversed(tape):
+        return dict(x=x, R=R, S=S, B=B, hyp=hyp, alpha_h=alpha_h, Kxs=Kxs, Cv=Cv, pv=pv, info=info, Hm_rows=Hm_rows,
+                    pv_rows=pv_rows, eps=eps, y=y, tape=tape, out=d)
+
+    def _latent_backward(self, fw, g, log_var_scaling):
+        """d loss / d x [R,Q] from g = d loss / d (down-propagated rows); adds log_var_scaling / pred_var to d / d pred_var."""
+        for lay, q, d_out in reversed(fw['tape']):
             g = ops.gemm(ops.concrete_backward(g, q, d_out, lay.temperature), lay.Wk)
-        gHm_rows, gsig_rows, _, _ = ops.gpdbn_top_backward1(g, y, Hm_rows, pv_rows, alpha_h, eps)
-        g_Hm, g_pv = ops.testgen_reduce_samples(gHm_rows, gsig_rows, alpha_h, pv, R, S, log_var_scaling)
-        g_x = ops.testgen_grad_x(ops.gemm(B, g_Hm, trans_b=True), Cv, Kxs, g_pv, self.X, x, hyp)
-        return loss, g_x, info, model_point, pv
+        gHm_rows, gsig_rows, _, _ = ops.gpdbn_top_backward1(g, fw['y'], fw['Hm_rows'], fw['pv_rows'], fw['alpha_h'], fw['eps'])
+        g_Hm, g_pv = ops.testgen_reduce_samples(gHm_rows, gsig_rows, fw['alpha_h'], fw['pv'], fw['R'], fw['S'], log_var_scaling)
+        return ops.testgen_grad_x(ops.gemm(fw['B'], g_Hm, trans_b=True), fw['Cv'], fw['Kxs'], g_pv, self.X, fw['x'], fw['hyp'])
+
+    def latent_search_loss(self, x, test_point, log_var_scaling=0.1, num_samples=1, cache=None, draws=None,
+                           want_outputs=False):
+        """loss [R] and d loss / d x [R,Q] of gprbm.py:490-499 at restarts x [R,Q], each with `num_samples` Gaussian
+        samples of the top hidden layer pushed down the Concrete stack (rows ordered r * S + s).
+        draws (optional injected randomness): {'eps' [R*S,D], 'down_top' [R*S,Vt], 'down': [per lower layer, top first]}."""
+        fw = self._latent_forward(x, num_samples, cache, draws)
+        target = to_device(test_point, self.device).reshape(-1)
+        loss, model_point, g = ops.testgen_meanloss(fw['out'], target, fw['pv'], fw['R'], fw['S'], log_var_scaling, want_outputs)
+        g_x = self._latent_backward(fw, g, log_var_scaling)
+        return loss, g_x, fw['info'], model_point, fw['pv']
+
+    def held_out_loss(self, x, test_data, cache=None, draws=None):
+        """The objective of test_held_out_data (gprbm.py:447-453) at x [R,Q] (the reference's x_test is one row): the mean
+        over the test rows of the squared distance to ONE down-propagated sample per row of x, and its x-gradient."""
+        fw = self._latent_forward(x, 1, cache, draws)
+        loss, g = ops.heldout_mse(fw['out'], to_device(test_data, self.device))
+        return loss, self._latent_backward(fw, g, 0.0), fw['info']
 
     def test_generalisation(self, test_data, output_table_path, optimizer, num_iterations=1000, log_var_scaling=0.1,
                             method='all_training', num_runs=1, num_samples_to_average=1):
@@ -549,5 +571,89 @@ class GPRBM(bgrbm.BGRBM):
         return table
 
     def test_held_out_data(self, test_data, output_x_fname, optimizer, num_iterations=1000):
-        raise NotImplementedError('GPRBM.test_held_out_data is outside the round-1 scope (SURVEY.md §8 f2)')
+        """gprbm.py:440-466: minimise dist.mse(test_data, downprop(sample_mean(x_test))) over the single test latent
+        x_test [1,Q] (a fresh draw of the hidden noise and of the Concrete units every iteration, as session.run would
+        give) and np.save the result. x_test starts from the constructor's x_test_var when one was passed, else from a
+        standard-normal draw (the initializer gpdbn_horses/test_generalisation.py:36 uses)."""
+        test_data = np.asarray(test_data, dtype=np.float32)
+        assert test_data.ndim == 2 and test_data.shape[1] == self.datapoint_len()
+        if self.eval_flag is False:
+            self._snapshot_hidden()
+        cache = self._latent_search_cache()
+        x0 = self.x_test
+        if x0 is None:
+            x = ops.randn(1, self.Q, self.rng, self.device)
+        else:
+            x0 = x0.value if isinstance(x0, compat.Variable) else x0
+            x = to_device(np.array(to_numpy(x0), dtype=np.float32, ndmin=2), self.device).clone().contiguous()
+        assert x.shape == (1, self.Q)
+        T = to_device(test_data, self.device)
+        optimizer.reset()
+        state = torch.zeros(max(optimizer.state_multiple(), 1) * x.numel(), dtype=torch.float32, device=self.device)
+        for _ in range(num_iterations):
+            _, g_x, _ = self.held_out_loss(x, T, cache)
+            ops.optimizer_step(optimizer.descriptor(), x.view(-1), g_x.view(-1), state)
+        x_np = to_numpy(x)
+        if isinstance(self.x_test, compat.Variable):
+            self.x_test.assign(x_np)                      # the reference optimises the variable in place
+        np.save(output_x_fname, x_np)
+        return x_np
 
+    # ---- geodesic interpolation (gprbm.py:564-689) ---------------------------------------------------------------
+    def create_observed_prediction_with_variance(self, tf_input, num_samples, cache=None, draws=None):
+        """gprbm.py:564-612: for every latent point of tf_input [P,Q] the mean over `num_samples` down-propagated samples
+        drawn with sigma_h = alpha_h sqrt(pred_var_p), and the predictive variances [P]."""
+        fw = self._latent_forward(tf_input, num_samples, cache, draws)
+        bad = int(fw['info'].item())
+        if bad:
+            raise RuntimeError('assert_non_negative(pred_var) failed at interpolation point %d' % (bad - 1))
+        images = fw['out'].view(fw['R'], fw['S'], -1).mean(dim=1)          # tf.reduce_mean over the samples of a point
+        return images, fw['pv']
+
+    def interp_objective(self, Xi, x_start, x_end, interp_lambda, cache=None):
+        """Objective of interp_test (gprbm.py:651-660) at the path Xi [P,Q] and its gradient with respect to Xi."""
+        Kinv, _ = cache or self._latent_search_cache()
+        Xi = to_device(Xi, self.device)
+        hyp = ops.gp_effective_hyp(self._hyp, self.flags, self.fixed_noise, self.noise_jitter or 0.0)
+        Kxs = ops.gram_rbf(self.X, Xi, hyp)
+        Cv = ops.gemm(Kinv, Kxs)
+        pv, info = ops.testgen_pred_var(Kxs, Cv, hyp)
+        obj, g_seg, g_pv = ops.interp_objective(Xi, to_device(x_start, self.device).reshape(-1),
+                                                to_device(x_end, self.device).reshape(-1), pv, interp_lambda)
+        g_x = ops.testgen_grad_x(torch.zeros_like(Kxs), Cv, Kxs, g_pv, self.X, Xi, hyp)
+        return obj, g_x + g_seg, info
+
+    def interp_test(self, starting_point_index, end_point_index, num_points=20, interp_lambda=0.1, learning_rate=0.01,
+                    num_iterations=500, num_sample_to_average=100):
+        """gprbm.py:614-689: a path of num_points + 2 latents between two training latents, first the straight line, then
+        optimised with Adam(learning_rate) towards short segments through low predictive variance. Returns
+        (linear_points, geodesic_points): the mean down-propagated images along both paths [num_points + 2, V]."""
+        if self.eval_flag is False:
+            self._snapshot_hidden()
+        cache = self._latent_search_cache()
+        X = to_numpy(self.X)
+        x_s = np.reshape(X[starting_point_index], (1, self.Q))
+        x_e = np.reshape(X[end_point_index], (1, self.Q))
+        a = np.linspace(0.0, 1.0, num_points + 2)[:, np.newaxis]             # 0, interior points, 1 (gprbm.py:627-634)
+        xx = (x_s + np.dot(a, x_e - x_s)).astype(np.float32)
+        Xi = to_device(xx, self.device).clone().contiguous()
+        obs_init, _ = self.create_observed_prediction_with_variance(Xi, num_sample_to_average, cache)
+        optimizer = compat.train.AdamOptimizer(learning_rate=learning_rate)
+        optimizer.reset()
+        state = torch.zeros(max(optimizer.state_multiple(), 1) * Xi.numel(), dtype=torch.float32, device=self.device)
+        refresh_iter = int(np.ceil(num_iterations / 10))
+        cost = float('nan')
+        for i in range(num_iterations):
+            obj, g_x, info = self.interp_objective(Xi, x_s, x_e, interp_lambda, cache)
+            ops.optimizer_step(optimizer.descriptor(), Xi.view(-1), g_x.view(-1), state)
+            if (i % refresh_iter) == 0:
+                bad = int(info.item())
+                if bad:
+                    raise RuntimeError('assert_non_negative(pred_var) failed at interpolation point %d' % (bad - 1))
+                cost = float(obj.item())
+                print('  opt iter {:5}: {}'.format(i, cost))
+        if num_iterations:
+            print('Final iter {:5}: {}'.format(num_iterations - 1, float(obj.item())))
+        self.interp_latents = to_numpy(Xi)
+        geodesic, _ = self.create_observed_prediction_with_variance(Xi, num_sample_to_average, cache)
+        return to_numpy(obs_init), to_numpy(geodesic)

@@ -539,6 +539,29 @@ def testgen_reduce_samples(gHm_rows, gsig_rows, alpha_h, pv, R, S, log_var_scali
     return g_Hm, g_pv
 
 
+def heldout_mse(Vs, T):
+    """loss [R] = mean_m sum_d (T[m,d] - Vs[r,d])^2 and d loss / d Vs (GPRBM.test_held_out_data, gprbm.py:453)."""
+    Vs, T = _f32(Vs), _f32(T)
+    R, Dim = Vs.shape
+    loss = torch.empty(R, device=Vs.device, dtype=torch.float32)
+    g = torch.empty_like(Vs)
+    L.check(L.lib().db_heldout_mse(L.handle(), L.stream(), L.fptr(Vs), L.fptr(T), R, T.shape[0], Dim, L.fptr(loss), L.fptr(g)),
+            'db_heldout_mse')
+    return loss, g
+
+
+def interp_objective(Xi, x_start, x_end, pv, interp_lambda):
+    """(objective [1], g_x of the segment term [P,Q], g_pv [P]) of GPRBM.interp_test (gprbm.py:651-660)."""
+    Xi = _f32(Xi)
+    P, Q = Xi.shape
+    obj = torch.empty(1, device=Xi.device, dtype=torch.float32)
+    g_x = torch.empty_like(Xi)
+    g_pv = torch.empty(P, device=Xi.device, dtype=torch.float32)
+    L.check(L.lib().db_interp_objective(L.handle(), L.stream(), L.fptr(Xi), L.fptr(_f32(x_start)), L.fptr(_f32(x_end)), L.fptr(pv),
+                                        P, Q, float(interp_lambda), L.fptr(obj), L.fptr(g_x), L.fptr(g_pv)), 'db_interp_objective')
+    return obj, g_x, g_pv
+
+
 # ---- 3xTF32 tensor-core GEMM -------------------------------------------------------------------------------------
 def tf32_split_lo(x):
     """x - tf32(x): the remainder operand of the 3xTF32 GEMM (same shape)."""

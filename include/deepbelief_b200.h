@@ -309,6 +309,16 @@ int db_testgen_reduce_samples(db_handle_t h, db_stream_t stream, const float* gH
                               const float* alpha_h, const float* pred_var, int R, int S, int D, float log_var_scaling,
                               float* g_Hm, float* g_pv);
 
+/* GPRBM.test_held_out_data (gprbm.py:440-466): loss[r] = mean_m sum_d (T[m,d] - Vs[r,d])^2 — dist.mse (dist.py:5-21)
+ * of the [M,Dim] test set against the one down-propagated row of restart r; g_Vs [R,Dim] = d loss / d Vs. */
+int db_heldout_mse(db_handle_t h, db_stream_t stream, const float* Vs, const float* T, int R, int M, int Dim,
+                   float* loss, float* g_Vs);
+/* GPRBM.interp_test (gprbm.py:651-660): objective = mean over the P+1 segments x_start -> Xi[0] -> ... -> Xi[P-1] -> x_end
+ * of |segment|^2 + lambda * mean_p log pred_var[p]; g_x [P,Q] = gradient of the segment term with respect to Xi,
+ * g_pv [P] = lambda / (P pred_var[p]) (chained through db_testgen_grad_x by the caller). */
+int db_interp_objective(db_handle_t h, db_stream_t stream, const float* Xi, const float* x_start, const float* x_end,
+                        const float* pred_var, int P, int Q, float lambda, float* objective, float* g_x, float* g_pv);
+
 /* ---- backward building blocks (what TF autodiff derives from tf.matmul / the Concrete units / dist.py) -- */
 /* C[M,N] = alpha * op(A) op(B) + beta * C, fp32 row-major; op = transpose when the flag is set. */
 int db_gemm(db_handle_t h, db_stream_t stream, int transA, int transB, int M, int N, int K, float alpha,

@@ -68,7 +68,10 @@ class GPLVMOracle:
         self.Q = self.X.shape[1]
         one = inverse_softplus(np.float64(1.0))
         self.opt_alpha = dtype(one if opt_alpha is None else opt_alpha)
-        self.opt_gamma = dtype(one if opt_gamma is None else opt_gamma)
+        if opt_gamma is not None and np.ndim(opt_gamma) > 0:          # ARD: one length-scale per latent dimension (gplvm.py:24-28)
+            self.opt_gamma = np.asarray(opt_gamma, dtype=dtype).reshape(1, self.Q)
+        else:
+            self.opt_gamma = dtype(one if opt_gamma is None else opt_gamma)
         self.opt_noise = dtype(one if opt_noise is None else opt_noise)
         self.fixed_noise = dtype(fixed_noise)
         self.jitter = dtype(jitter)
@@ -117,16 +120,23 @@ class GPLVMOracle:
         A = Kinv @ self.Y
         G = 0.5 * (self.D * Kinv - A @ A.T)
         Wm = G * Kf
-        g2 = self.gamma * self.gamma
+        g2 = self.gamma * self.gamma                                # scalar, or [1,Q] with ARD (broadcasts over the columns of X)
         dX = -2.0 * (np.sum(Wm, axis=1, keepdims=True) * self.X - Wm @ self.X) / g2
         dX = dX + 2.0 * x_prior_weight * self.X
-        diff2 = sq_dist(self.X, None, 1.0)                          # unscaled |xi-xj|^2
         d_alpha = np.sum(Wm) / self.alpha
-        d_gamma = np.sum(Wm * diff2) / (self.gamma ** 3)
+        if np.ndim(self.opt_gamma) > 0:                             # ARD: d/dgamma_q = sum_ij Wm_ij (x_iq - x_jq)^2 / gamma_q^3
+            d_gamma = np.array([np.sum(Wm * sq_dist(self.X[:, q:q + 1], None, 1.0)) for q in range(self.Q)]).reshape(1, self.Q)
+            d_gamma = d_gamma / (self.gamma ** 3)
+        else:
+            diff2 = sq_dist(self.X, None, 1.0)                      # unscaled |xi-xj|^2
+            d_gamma = np.sum(Wm * diff2) / (self.gamma ** 3)
         d_noise = np.trace(G)
         out = [dX.astype(self.dtype)]
         out.append(self.dtype(d_alpha * sigmoid(np.asarray(self.opt_alpha))) if self.trainable[0] else self.dtype(0))
-        out.append(self.dtype(d_gamma * sigmoid(np.asarray(self.opt_gamma))) if self.trainable[1] else self.dtype(0))
+        if np.ndim(self.opt_gamma) > 0:
+            out.append((d_gamma * sigmoid(self.opt_gamma)).reshape(-1).astype(self.dtype))
+        else:
+            out.append(self.dtype(d_gamma * sigmoid(np.asarray(self.opt_gamma))) if self.trainable[1] else self.dtype(0))
         out.append(self.dtype(d_noise * sigmoid(np.asarray(self.opt_noise))) if self.trainable[2] else self.dtype(0))
         return tuple(out)
 

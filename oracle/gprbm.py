@@ -286,3 +286,100 @@ def latent_search_loss(oracle, H2, H1_mean, x, target, log_var_scaling, num_samp
         ce = np.sum(np.maximum(lg, 0) - lg * target + np.log1p(np.exp(-np.abs(lg))))
         out[r] = ce / target.shape[1] + log_var_scaling * np.log(pv[0])
     return out
+
+
+def _latent_down(o, L, sys2, H1_mean, alpha_h, x_r, rows, draws):
+    """One test latent x_r [1,Q]: pred_var (gprbm.py:208-218), sigma_h = alpha_h sqrt(pred_var) (gprbm.py:114-115),
+    build_sample_mean with the noise rows `rows` of draws['eps'] (gprbm.py:220-232) and downprop through the Concrete
+    stack (rbm.py:302-325). Returns (down-propagated rows [S,V0], pred_var [1])."""
+    dt, T = o.dt, o.T
+    alpha, gamma, _ = o.hyp()
+    X = o.gp['X']
+    KXx = se_kernel(X, x_r, alpha, gamma)
+    sys1 = scipy.linalg.solve_triangular(L, KXx, lower=True)
+    pv = se_kernel(x_r, None, alpha, gamma, diag=True) - np.sum(np.square(sys1), axis=0)
+    sigma_h = alpha_h * np.sqrt(pv)[:, None]
+    H = (sys1.T @ sys2) * alpha_h + H1_mean
+    H = H + sigma_h * np.asarray(draws['eps'], dtype=dt)[rows]
+    y = H / sigma_h
+    q = sigmoid((o.top['W'] @ y.T + o.top['b'].reshape(-1, 1)).T)
+    d = concrete(q, np.asarray(draws['down_top'], dtype=dt)[rows], T)
+    for i, lay in enumerate(reversed(o.lower)):
+        q = sigmoid((lay['W'] @ d.T + lay['b'].reshape(-1, 1)).T)
+        d = concrete(q, np.asarray(draws['down'][i], dtype=dt)[rows], T)
+    return d, pv
+
+
+def _frozen_gp(o, H2, H1_mean):
+    dt = o.dt
+    alpha, gamma, noise = o.hyp()
+    X = o.gp['X']
+    K = se_kernel(X, None, alpha, gamma) + noise * np.eye(o.N, dtype=dt)
+    L = np.linalg.cholesky(K)
+    alpha_h = softplus(o.top['opt_alpha_h']).reshape(1, o.D)
+    sys2 = scipy.linalg.solve_triangular(L, np.asarray(H2, dtype=dt), lower=True)
+    return L, sys2, np.asarray(H1_mean, dtype=dt).reshape(1, o.D), alpha_h
+
+
+def held_out_loss(oracle, H2, H1_mean, x, test_data, draws):
+    """The objective of GPRBM.test_held_out_data (gprbm.py:440-466): dist.mse(test_data, downprop(sample_mean(x_test)))
+    with the [M,V] test set as `predictions` and the ONE down-propagated row (num_samples None, x_test [1,Q]) broadcast
+    as `targets` (dist.py:5-21): mean over the M test rows of sum_v (t_mv - d_v)^2. x may hold R independent rows;
+    row r uses row r of every draw. Returns [R]."""
+    o, dt = oracle, oracle.dt
+    L, sys2, H1m, alpha_h = _frozen_gp(o, H2, H1_mean)
+    x = np.asarray(x, dtype=dt)
+    Tt = np.asarray(test_data, dtype=dt)
+    out = np.zeros(x.shape[0], dtype=dt)
+    for r in range(x.shape[0]):
+        d, _ = _latent_down(o, L, sys2, H1m, alpha_h, x[r:r + 1], slice(r, r + 1), draws)
+        out[r] = np.mean(np.sum(np.square(Tt - d), axis=1))
+    return out
+
+
+def interp_path(x_start, x_end, num_points):
+    """The initial (linear) interpolation latents of GPRBM.interp_test (gprbm.py:623-637): num_points interior points
+    plus both end points, [num_points + 2, Q]."""
+    x_s = np.reshape(x_start, (1, -1))
+    x_e = np.reshape(x_end, (1, -1))
+    a = np.linspace(0.0, 1.0, num_points + 2)[1:-1, np.newaxis]
+    a = np.insert(a, 0, 0)
+    a = np.append(a, 1.0)
+    a = np.reshape(a, (num_points + 2, 1))
+    return x_s + np.dot(a, x_e - x_s)
+
+
+def interp_objective(oracle, Xi, x_start, x_end, interp_lambda):
+    """gprbm.py:651-660: mean_i |segment_i|^2 over the P+1 segments start -> Xi[0] -> ... -> Xi[-1] -> end, plus
+    lambda * mean(log pred_var(Xi)) with pred_var as build_pred_var_interp (gprbm.py:569-579). Returns (objective,
+    pred_var [P])."""
+    o, dt = oracle, oracle.dt
+    alpha, gamma, noise = o.hyp()
+    X = o.gp['X']
+    Xi = np.asarray(Xi, dtype=dt)
+    x_s = np.asarray(x_start, dtype=dt).reshape(1, -1)
+    x_e = np.asarray(x_end, dtype=dt).reshape(1, -1)
+    K = se_kernel(X, None, alpha, gamma) + noise * np.eye(o.N, dtype=dt)
+    L = np.linalg.cholesky(K)
+    KXx = se_kernel(X, Xi, alpha, gamma)
+    sys1 = scipy.linalg.solve_triangular(L, KXx, lower=True)
+    pv = se_kernel(Xi, None, alpha, gamma, diag=True) - np.sum(np.square(sys1), axis=0)
+    seg = np.concatenate([Xi[0:1] - x_s, Xi[1:] - Xi[:-1], x_e - Xi[-1:]], axis=0)
+    dist_term = np.mean(np.sum(np.square(seg), axis=1))
+    return dist_term + dt(interp_lambda) * np.mean(np.log(pv)), pv
+
+
+def interp_images(oracle, H2, H1_mean, Xi, num_samples, draws):
+    """create_observed_prediction_with_variance (gprbm.py:564-612): per interpolation point, sigma_h = alpha_h *
+    sqrt(pred_var_i), `num_samples` noise rows (rows i*S + s of the draws), downprop, mean over the samples.
+    Returns (images [P,V0], pred_var [P])."""
+    o, dt = oracle, oracle.dt
+    L, sys2, H1m, alpha_h = _frozen_gp(o, H2, H1_mean)
+    Xi = np.asarray(Xi, dtype=dt)
+    S = int(num_samples)
+    imgs, pvs = [], []
+    for i in range(Xi.shape[0]):
+        d, pv = _latent_down(o, L, sys2, H1m, alpha_h, Xi[i:i + 1], slice(i * S, (i + 1) * S), draws)
+        imgs.append(np.mean(d, axis=0, keepdims=True))
+        pvs.append(pv[0])
+    return np.concatenate(imgs, axis=0), np.asarray(pvs, dtype=dt)

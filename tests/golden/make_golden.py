@@ -406,6 +406,147 @@ def gpdbn_goldens(out):
                 out['gpdbn/%s/fd/%s' % (cname, key)] = np.float64(fd)
 
 
+def latent_goldens(out):
+    """GPRBM.test_held_out_data (gprbm.py:440-466) and the graph pieces of GPRBM.interp_test (gprbm.py:564-660) in
+    EVAL mode (eval_flag True, x_ph = x_test), executed from the reference's own gprbm.py on the stack and parameters of
+    gpdbn_golden.npz ('trainable' case). The optimizer loops themselves need TF autodiff and are not run; the objective
+    values at given latents are what is pinned (their x-gradients are checked by finite differences in the tests)."""
+    G = {k.replace('__', '/'): v for k, v in np.load(os.path.join(HERE, 'gpdbn_golden.npz')).items()}
+    P = {k: G['gpdbn/P/' + k] for k in ('W0', 'b0', 'c0', 'W1', 'b1', 'c1', 'Wt', 'bt', 'ct', 'X')}
+    Vd, T = G['gpdbn/V'], float(G['gpdbn/T'])
+    N, V0 = Vd.shape
+    Ha, Hb, D, Q = P['W0'].shape[1], P['W1'].shape[1], P['Wt'].shape[1], P['X'].shape[1]
+    rs = np.random.RandomState(4242)
+    H2 = rs.normal(size=(N, D))
+    H1_mean = rs.normal(size=(1, D)) * 0.3
+    out['latent/H2'], out['latent/H1_mean'] = H2, H1_mean
+
+    def build(x_test, dname):
+        set_dtype(dname)
+        dt = np.dtype(dname)
+        sess = tf.Session()
+        l0 = make_layer('rbm', V0, Ha, P['W0'], P['b0'], P['c0'], None, temperature=T, name='l0')
+        l1 = make_layer('rbm', Ha, Hb, P['W1'], P['b1'], P['c1'], None, temperature=T, bottom=l0, name='l1')
+        kern = ref_gplvm.SEKernel(alpha=1.4, gamma=0.9, session=sess)
+        shim.TRUNC_QUEUE[:] = [P['Wt']]
+        shim.ZEROS_INJECT.clear()
+        shim.ZEROS_INJECT[(Hb, 1)] = [P['bt']]
+        shim.ZEROS_INJECT[(1, D)] = [P['ct']]
+        shim.RANDOM_QUEUE[:] = []
+        g = ref_gprbm.GPRBM(num_v=Hb, num_h=D, Q=Q, N=N, eval_flag=True, X0=P['X'].astype(dt), kern=kern,
+                            noise_variance=0.3, fixed_noise_variance=False, temperature=T, bottom=l1,
+                            x_test_var=np.asarray(x_test, dtype=dt), session=sess, name='top')
+        assert not shim.TRUNC_QUEUE
+        shim.ZEROS_INJECT.clear()
+        g.H2_var = H2.astype(dt)                   # what restore() / update_H2_var leave in the snapshots
+        g.H1_mean_var = H1_mean.astype(dt)
+        return g
+
+    # ---- test_held_out_data: mse(test_data, downprop(build_sample_mean(H2_var, H1_mean_var))) ----
+    R, M = 3, 5
+    xs = rs.normal(size=(R, Q))
+    test_data = rs.binomial(1, 0.4, size=(M, V0)).astype(np.float64)
+    hd = {'eps': rs.normal(size=(R, D)).astype(np.float32).astype(np.float64),
+          'down_top': rs.uniform(0.05, 0.95, size=(R, Hb)), 'down1': rs.uniform(0.05, 0.95, size=(R, Ha)),
+          'down0': rs.uniform(0.05, 0.95, size=(R, V0))}
+    out['heldout/x'], out['heldout/test_data'] = xs, test_data
+    for k, v in hd.items():
+        out['heldout/draws/' + k] = v
+    for dname in ('float32', 'float64'):
+        vals = []
+        for r in range(R):
+            g = build(xs[r:r + 1], dname)
+            shim.RANDOM_QUEUE[:] = [hd['eps'][r:r + 1], hd['down_top'][r:r + 1], hd['down1'][r:r + 1], hd['down0'][r:r + 1]]
+            pm = g.build_sample_mean(g.H2_var, g.H1_mean_var)
+            dm = g.downprop(pm)
+            assert not shim.RANDOM_QUEUE
+            vals.append(float(dist.mse(test_data.astype(dname), dm)))
+        out['heldout/%s/mse' % dname] = np.array(vals)
+
+    # ---- interp_test pieces: create_observed_prediction_with_variance at given interpolation latents ----
+    Pn, S = 4, 3
+    Xi = rs.normal(size=(Pn + 2, Q)) * 0.8
+    idr = {'eps': rs.normal(size=((Pn + 2) * S, D)).astype(np.float32).astype(np.float64),
+           'down_top': rs.uniform(0.05, 0.95, size=((Pn + 2) * S, Hb)),
+           'down1': rs.uniform(0.05, 0.95, size=((Pn + 2) * S, Ha)),
+           'down0': rs.uniform(0.05, 0.95, size=((Pn + 2) * S, V0))}
+    out['interp/Xi'] = Xi
+    out['interp/S'] = np.int64(S)
+    for k, v in idr.items():
+        out['interp/draws/' + k] = v
+    for dname in ('float32', 'float64'):
+        g = build(xs[:1], dname)
+        q = []
+        for i in range(Pn + 2):
+            rows = slice(i * S, (i + 1) * S)
+            # build_sample_mean_interp draws a [1,D] normal first and discards it when num_samples is given (gprbm.py:587-589)
+            q += [np.zeros((1, D)), idr['eps'][rows], idr['down_top'][rows], idr['down1'][rows], idr['down0'][rows]]
+        shim.RANDOM_QUEUE[:] = q
+        imgs, var = g.create_observed_prediction_with_variance(tf_input=Xi.astype(dname), num_samples=S)
+        assert not shim.RANDOM_QUEUE
+        out['interp/%s/images' % dname] = np.asarray(imgs)
+        out['interp/%s/pred_var' % dname] = np.asarray(var)
+
+
+def ard_goldens(out):
+    """SEKernel(ARD=True) (gplvm.py:24-28: one length-scale per latent dimension, gamma [1,Q]) and a GPLVM on it, run
+    from the reference source; gradients as central differences (fp64) of the reference loss with respect to X and
+    to each optimisation variable (opt_alpha, opt_gamma[q], opt_noise)."""
+    rs = np.random.RandomState(777)
+    N, D, Q, M = 26, 9, 3, 5
+    Yd = rs.normal(size=(N, D))
+    xs = rs.normal(size=(M, Q))
+    X0 = rs.normal(size=(N, Q))
+    gam = np.array([[0.6, 1.1, 1.9]])
+    alpha, noise = 1.3, 0.4
+    isp = lambda v: np.log(np.exp(v) - 1.0)  # noqa: E731
+    out['ard/Y'], out['ard/xstar'], out['ard/X0'], out['ard/gamma'] = Yd, xs, X0, gam
+    out['ard/alpha'], out['ard/noise'] = np.float64(alpha), np.float64(noise)
+
+    def build(dname, X, oa, og, on):
+        set_dtype(dname)
+        dt = np.dtype(dname)
+        sess = tf.Session()
+        kern = ref_gplvm.SEKernel(alpha=alpha, gamma=1.0, ARD=True, Q=Q, session=sess)     # gamma -> ones [1,Q]
+        assert np.asarray(kern.gamma).shape == (1, Q)
+        kern.opt_alpha = np.asarray(oa, dtype=dt); kern.alpha = tf.nn.softplus(kern.opt_alpha)
+        kern.opt_gamma = np.asarray(og, dtype=dt).reshape(1, Q); kern.gamma = tf.nn.softplus(kern.opt_gamma)
+        g = ref_gplvm.GPLVM(Yd.astype(dt), Q, X0=X.astype(dt), kern=kern, noise_variance=noise, x_test_var=xs.astype(dt),
+                            session=sess)
+        g.opt_noise_variance = np.asarray(on, dtype=dt); g.noise_variance = tf.nn.softplus(g.opt_noise_variance)
+        g.build_model()
+        return g, kern
+
+    oa, og, on = isp(alpha), isp(gam), isp(noise)
+    out['ard/opt'] = np.concatenate([[oa], og.reshape(-1), [on]])
+    for dname in ('float32', 'float64'):
+        g, kern = build(dname, X0, oa, og, on)
+        pre = 'ard/%s/' % dname
+        dt = np.dtype(dname)
+        out[pre + 'K_X'] = kern.K(X0.astype(dt))
+        out[pre + 'K_Xx'] = kern.K(X0.astype(dt), xs.astype(dt))
+        out[pre + 'K'], out[pre + 'L'] = g.K, g.L
+        out[pre + 'loss'], out[pre + 'log_det'] = np.asarray(g.loss), np.asarray(g.log_det)
+        out[pre + 'pred_mean'], out[pre + 'pred_var'] = g.pred_mean, g.pred_var
+    eps = 1e-6
+    f = lambda X, a, gm, n: float(build('float64', X, a, gm, n)[0].loss)  # noqa: E731
+    gX = np.zeros_like(X0)
+    for i in range(N):
+        for qd in range(Q):
+            Xp, Xm = X0.copy(), X0.copy()
+            Xp[i, qd] += eps; Xm[i, qd] -= eps
+            gX[i, qd] = (f(Xp, oa, og, on) - f(Xm, oa, og, on)) / (2 * eps)
+    out['ard/fd_dX'] = gX
+    dg = np.zeros(Q)
+    for qd in range(Q):
+        gp, gm = og.copy(), og.copy()
+        gp[0, qd] += eps; gm[0, qd] -= eps
+        dg[qd] = (f(X0, oa, gp, on) - f(X0, oa, gm, on)) / (2 * eps)
+    out['ard/fd_dopt_gamma'] = dg
+    out['ard/fd_dopt_alpha'] = np.float64((f(X0, oa + eps, og, on) - f(X0, oa - eps, og, on)) / (2 * eps))
+    out['ard/fd_dopt_noise'] = np.float64((f(X0, oa, og, on + eps) - f(X0, oa, og, on - eps)) / (2 * eps))
+
+
 def sbm_goldens(out):
     """SBM_Lower (sbm_lower.py:59-117): net inputs, probabilities, free energy, cd_loss of the reference class with injected
     shared weights, and the gradient of cd_loss with respect to the shared W and b as central differences (fp64)."""
@@ -475,7 +616,8 @@ def misc_goldens(out):
 def main():
     only = sys.argv[1:]
     for fn, name in ((rbm_goldens, 'rbm_golden.npz'), (gp_goldens, 'gp_golden.npz'), (misc_goldens, 'misc_golden.npz'),
-                     (gpdbn_goldens, 'gpdbn_golden.npz'), (backprop_goldens, 'backprop_golden.npz'), (sbm_goldens, 'sbm_golden.npz')):
+                     (gpdbn_goldens, 'gpdbn_golden.npz'), (backprop_goldens, 'backprop_golden.npz'), (sbm_goldens, 'sbm_golden.npz'),
+                     (latent_goldens, 'latent_golden.npz'), (ard_goldens, 'ard_golden.npz')):
         if only and name not in only:
             continue
         out = {}

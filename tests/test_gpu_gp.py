@@ -309,3 +309,56 @@ def test_tensor_core_gp_path_vs_oracle(N, D):
     assert _normrel(np.tril(_np(Lf)), Lref) < 1e-5
     assert _normrel(_np(dX), w_dX) < GRAD_NORMREL
     np.testing.assert_allclose(_np(scal[3:6]), [w_da, w_dg, w_dn], rtol=3e-4)
+
+
+def test_ard_kernel_and_gplvm_vs_reference(tmp_path):
+    """SEKernel(ARD=True) (gplvm.py:24-28, one length-scale per latent dimension): K, loss, prediction against the
+    values the reference's own gplvm.py produces (tests/golden/ard_golden.npz); gradients with respect to X and every
+    optimisation variable against central differences of the reference loss; optimize() moves all of them; checkpoint
+    round trip of the vector length-scales."""
+    from conftest import Golden
+    from deepbelief_b200 import compat as tf
+    from deepbelief_b200.layers.gplvm import GPLVM, SEKernel
+    g = Golden('ard_golden.npz')
+    Q = g['ard/X0'].shape[1]
+    kern = SEKernel(alpha=float(g['ard/alpha']), gamma=g['ard/gamma'], ARD=True, Q=Q)
+    np.testing.assert_allclose(_np(kern.gamma), g['ard/gamma'], rtol=1e-6)
+    X0, xs = g['ard/X0'], g['ard/xstar']
+    np.testing.assert_allclose(_np(kern.K(X0)), g['ard/float64/K_X'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(_np(kern.K(X0, xs)), g['ard/float64/K_Xx'], rtol=1e-5, atol=1e-6)
+    lay = GPLVM(g['ard/Y'].astype(np.float32), Q, X0=X0, kern=kern, noise_variance=float(g['ard/noise']), name='gplvm_ard')
+    lay.build_model()
+    np.testing.assert_allclose(_np(lay.K.eval()), g['ard/float64/K'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(float(lay.loss.eval()), g['ard/float64/loss'], rtol=LOSS_RTOL)
+    np.testing.assert_allclose(float(lay.log_det.eval()), g['ard/float64/log_det'], rtol=LOSS_RTOL)
+    assert _normrel(_np(lay.build_pred_mean(xs)), g['ard/float64/pred_mean']) < 1e-4
+    np.testing.assert_allclose(_np(lay.build_pred_var(xs)), g['ard/float64/pred_var'], rtol=1e-3, atol=1e-6)
+    loss, dX, dopt = lay.loss_and_grad()
+    dopt = _np(dopt)
+    assert dopt.shape == (Q + 2,)
+    assert _normrel(_np(dX), g['ard/fd_dX']) < GRAD_NORMREL
+    np.testing.assert_allclose(dopt[0], g['ard/fd_dopt_alpha'], rtol=1e-4)
+    np.testing.assert_allclose(dopt[1:1 + Q], g['ard/fd_dopt_gamma'], rtol=1e-4, atol=1e-4 * np.max(np.abs(g['ard/fd_dopt_gamma'])))
+    np.testing.assert_allclose(dopt[1 + Q], g['ard/fd_dopt_noise'], rtol=1e-4)
+    # latent search (gplvm.py:478-483) in the unscaled coordinates: loss and x-gradient against the fp64 oracle
+    opt = g['ard/opt']
+    y_mean = g['ard/Y'].mean(axis=0, keepdims=True)
+    orc = ogp.GPLVMOracle(g['ard/Y'] - y_mean, X0, opt_alpha=opt[0], opt_gamma=opt[1:1 + Q], opt_noise=opt[1 + Q])
+    target = (np.random.RandomState(3).uniform(size=(1, lay.D)) > 0.5).astype(np.float64)
+    x = xs[:3]
+    ls, g_x, _, _, _ = lay.latent_search_loss(x, target, 0.1)
+    np.testing.assert_allclose(_np(ls), ogp.testgen_loss(orc, x, target, 0.1, y_mean), rtol=1e-4, atol=0.015 / lay.D)
+    fd = np.zeros_like(x)
+    for q in range(Q):
+        d = np.zeros_like(x); d[:, q] = 1e-6
+        fd[:, q] = (ogp.testgen_loss(orc, x + d, target, 0.1, y_mean) - ogp.testgen_loss(orc, x - d, target, 0.1, y_mean)) / 2e-6
+    assert _normrel(_np(g_x), fd) < 1e-3
+    # optimisation touches X, alpha, every length-scale and the noise, and lowers the loss
+    before = (float(lay.loss.eval()), _np(kern.gamma).copy(), _np(lay.X).copy())
+    lay.optimize(tf.train.AdamOptimizer(learning_rate=0.01), num_iterations=30)
+    assert float(lay.loss.eval()) < before[0]
+    assert np.all(np.abs(_np(kern.gamma) - before[1]) > 1e-4) and np.max(np.abs(_np(lay.X) - before[2])) > 1e-3
+    ck = kern.save(1, str(tmp_path))
+    k2 = SEKernel(alpha=1.0, gamma=1.0, ARD=True, Q=Q)
+    k2.restore(ck)
+    np.testing.assert_allclose(_np(k2.gamma), _np(kern.gamma), rtol=0, atol=0)

@@ -291,3 +291,85 @@ def test_latent_search_loss_and_gradient_vs_oracle(gpdbn_golden, tmp_path):
     t2 = top.test_generalisation(g['gpdbn/V'][:1], str(tmp_path / 't2.pkl'), tf.train.GradientDescentOptimizer(learning_rate=0.01),
                                  num_iterations=3, method='random_training', num_runs=6, num_samples_to_average=2)
     assert len(t2) == 1
+
+
+def _latent_draws(lg, pre):
+    f = lambda a: np.asarray(a, dtype=np.float32)  # noqa: E731
+    return {'eps': f(lg[pre + 'draws/eps']), 'down_top': f(lg[pre + 'draws/down_top']),
+            'down': [f(lg[pre + 'draws/down1']), f(lg[pre + 'draws/down0'])]}
+
+
+def test_held_out_data_vs_reference_and_oracle(gpdbn_golden, tmp_path):
+    """GPRBM.test_held_out_data (gprbm.py:440-466): the objective at given x against the value the reference's own
+    graph pieces produce (tests/golden/latent_golden.npz) and against the oracle, its x-gradient against central
+    differences of the oracle, and the driver loop (saved x, loss not worse than at the start on fixed draws)."""
+    from deepbelief_b200 import compat as tf
+    from conftest import Golden
+    g, lg = gpdbn_golden, Golden('latent_golden.npz')
+    top, _ = build_stack(g, 'trainable')
+    o = make_oracle(g, 'trainable')
+    H2, H1_mean = lg['latent/H2'], lg['latent/H1_mean']
+    top.H2_var.copy_(torch.as_tensor(H2, dtype=torch.float32).cuda())
+    top.H1_mean_var.copy_(torch.as_tensor(H1_mean, dtype=torch.float32).cuda().reshape(top.H1_mean_var.shape))
+    x, T = lg['heldout/x'].astype(np.float32), lg['heldout/test_data'].astype(np.float32)
+    draws = _latent_draws(lg, 'heldout/')
+    loss, g_x, info = top.held_out_loss(x, T, draws=draws)
+    assert int(info.item()) == 0
+    np.testing.assert_allclose(_np(loss), lg['heldout/float64/mse'], rtol=1e-4)          # the reference's own value
+    x64 = x.astype(np.float64)
+    np.testing.assert_allclose(_np(loss), ogprbm.held_out_loss(o, H2, H1_mean, x64, T, draws), rtol=1e-4)
+    eps = 1e-4
+    fd = np.zeros_like(x64)
+    for q in range(x.shape[1]):
+        d = np.zeros_like(x64); d[:, q] = eps
+        fd[:, q] = (ogprbm.held_out_loss(o, H2, H1_mean, x64 + d, T, draws) -
+                    ogprbm.held_out_loss(o, H2, H1_mean, x64 - d, T, draws)) / (2 * eps)
+    assert _normrel(_np(g_x), fd) < 1e-3
+    # driver: eval-mode call pattern (x_test_var from the constructor), SGD on fresh draws, result saved with np.save
+    top.eval_flag = True
+    top.x_test = tf.get_variable(name='x_test', initializer=x[:1])
+    out = str(tmp_path / 'x_held_out.npy')
+    x_opt = top.test_held_out_data(T, out, tf.train.AdamOptimizer(learning_rate=0.05), num_iterations=60)
+    assert x_opt.shape == (1, top.Q) and np.array_equal(np.load(out), x_opt)
+    l0 = np.mean([float(top.held_out_loss(x[:1], T)[0][0]) for _ in range(40)])
+    l1 = np.mean([float(top.held_out_loss(x_opt, T)[0][0]) for _ in range(40)])
+    assert np.isfinite(l1) and l1 < l0 + 0.05 * abs(l0)
+
+
+def test_interp_test_vs_reference_and_oracle(gpdbn_golden):
+    """GPRBM.interp_test (gprbm.py:564-689): images and predictive variances along a path against
+    create_observed_prediction_with_variance run from the reference source, the path objective and its gradient against
+    the oracle, and the driver (objective decreases from the straight line; output shapes)."""
+    from conftest import Golden
+    g, lg = gpdbn_golden, Golden('latent_golden.npz')
+    top, _ = build_stack(g, 'trainable')
+    o = make_oracle(g, 'trainable')
+    H2, H1_mean = lg['latent/H2'], lg['latent/H1_mean']
+    top.H2_var.copy_(torch.as_tensor(H2, dtype=torch.float32).cuda())
+    top.H1_mean_var.copy_(torch.as_tensor(H1_mean, dtype=torch.float32).cuda().reshape(top.H1_mean_var.shape))
+    Xi, S = lg['interp/Xi'], int(lg['interp/S'])
+    imgs, pv = top.create_observed_prediction_with_variance(Xi.astype(np.float32), S, draws=_latent_draws(lg, 'interp/'))
+    np.testing.assert_allclose(_np(pv), lg['interp/float64/pred_var'], rtol=2e-4)
+    assert _normrel(_np(imgs), lg['interp/float64/images']) < 1e-4
+    lam = 0.1
+    obj, g_x, info = top.interp_objective(Xi[1:-1].astype(np.float32), Xi[0].astype(np.float32), Xi[-1].astype(np.float32), lam)
+    want, _ = ogprbm.interp_objective(o, Xi[1:-1], Xi[0], Xi[-1], lam)
+    assert int(info.item()) == 0
+    np.testing.assert_allclose(float(obj), want, rtol=1e-4)
+    eps = 1e-5
+    fd = np.zeros_like(Xi[1:-1])
+    for i in range(fd.shape[0]):
+        for q in range(fd.shape[1]):
+            d = np.zeros_like(fd); d[i, q] = eps
+            fd[i, q] = (ogprbm.interp_objective(o, Xi[1:-1] + d, Xi[0], Xi[-1], lam)[0] -
+                        ogprbm.interp_objective(o, Xi[1:-1] - d, Xi[0], Xi[-1], lam)[0]) / (2 * eps)
+    assert _normrel(_np(g_x), fd) < 1e-3
+    # driver: the same path start as the reference builds, objective not worse after Adam
+    path0 = ogprbm.interp_path(_np(top.X)[0], _np(top.X)[5], 4).astype(np.float32)
+    start = float(top.interp_objective(path0, path0[0], path0[-1], lam)[0])
+    lin, geo = top.interp_test(0, 5, num_points=4, interp_lambda=lam, learning_rate=0.01, num_iterations=50,
+                               num_sample_to_average=8)
+    V0 = top.datapoint_len()
+    assert lin.shape == (6, V0) and geo.shape == (6, V0) and np.isfinite(geo).all()
+    end = float(top.interp_objective(top.interp_latents, path0[0], path0[-1], lam)[0])
+    assert end <= start + 1e-6

@@ -215,3 +215,30 @@ def test_latent_search_loss_matches_reference(gp_golden):
     m = ogp.GPLVMOracle(g[pre + 'Y_centered'], g[pre + 'X0'], opt_alpha=oa, opt_gamma=og_, opt_noise=on)
     got = ogp.testgen_loss(m, g['gplvm/xstar'], g['testgen/target'], 0.1, y_mean=g[pre + 'Y_mean'])
     np.testing.assert_allclose(got, g['testgen/loss'], rtol=1e-12)
+
+
+def test_ard_kernel_and_gplvm_match_reference():
+    """SEKernel(ARD=True) (gplvm.py:24-28) through the oracle against the reference's own gplvm.py: K, L, loss,
+    prediction, and the closed-form gradient against central differences of the reference loss."""
+    from conftest import Golden
+    g = Golden("ard_golden.npz")
+    opt = g['ard/opt']
+    Q = g['ard/X0'].shape[1]
+    m = ogp.GPLVMOracle(g['ard/Y'] - g['ard/Y'].mean(axis=0, keepdims=True), g['ard/X0'], opt_alpha=opt[0],
+                        opt_gamma=opt[1:1 + Q], opt_noise=opt[1 + Q])
+    np.testing.assert_allclose(m.gamma, g['ard/gamma'], rtol=1e-12)
+    np.testing.assert_allclose(ogp.se_kernel(m.X, None, m.alpha, m.gamma), g['ard/float64/K_X'], rtol=1e-12)
+    np.testing.assert_allclose(ogp.se_kernel(m.X, g['ard/xstar'], m.alpha, m.gamma), g['ard/float64/K_Xx'], rtol=1e-12)
+    np.testing.assert_allclose(m.K(), g['ard/float64/K'], rtol=1e-12)
+    loss, logdet, _, L, _ = m.loss()
+    np.testing.assert_allclose(L, g['ard/float64/L'], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(loss, g['ard/float64/loss'], rtol=1e-12)
+    np.testing.assert_allclose(logdet, g['ard/float64/log_det'], rtol=1e-12)
+    mean, var = m.predict(g['ard/xstar'], y_mean=g['ard/Y'].mean(axis=0, keepdims=True))
+    np.testing.assert_allclose(mean, g['ard/float64/pred_mean'], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(var, g['ard/float64/pred_var'], rtol=1e-9)
+    dX, da, dg, dn = m.grad()
+    assert np.max(np.abs(dX - g['ard/fd_dX'])) / np.max(np.abs(g['ard/fd_dX'])) < 1e-6
+    np.testing.assert_allclose(dg, g['ard/fd_dopt_gamma'], rtol=1e-6)
+    np.testing.assert_allclose(da, g['ard/fd_dopt_alpha'], rtol=1e-6)
+    np.testing.assert_allclose(dn, g['ard/fd_dopt_noise'], rtol=1e-6)

@@ -87,3 +87,43 @@ def test_gradient_opt_alpha_h_by_own_finite_difference(gpdbn_golden):
     fd = (lp - lm) / (2 * eps)
     an = float(np.sum(grads['top']['opt_alpha_h'] * d))
     assert abs(an - fd) <= 1e-5 * max(abs(fd), 1.0)
+
+
+@pytest.fixture(scope='module')
+def latent_golden():
+    return Golden('latent_golden.npz')
+
+
+def latent_draws(lg, pre):
+    return {'eps': lg[pre + 'draws/eps'], 'down_top': lg[pre + 'draws/down_top'],
+            'down': [lg[pre + 'draws/down1'], lg[pre + 'draws/down0']]}
+
+
+def test_held_out_loss_matches_reference(gpdbn_golden, latent_golden):
+    """oracle.held_out_loss against the mse the reference's own build_sample_mean / downprop / dist.mse produce in eval
+    mode (gprbm.py:440-453), fp64 and fp32."""
+    g, lg = gpdbn_golden, latent_golden
+    for dname, rtol in (('float64', 1e-11), ('float32', 2e-4)):
+        o = make_oracle(g, 'trainable', dtype=np.dtype(dname).type)
+        got = ogprbm.held_out_loss(o, lg['latent/H2'], lg['latent/H1_mean'], lg['heldout/x'], lg['heldout/test_data'],
+                                   latent_draws(lg, 'heldout/'))
+        np.testing.assert_allclose(got, lg['heldout/%s/mse' % dname], rtol=rtol)
+
+
+def test_interp_pieces_match_reference(gpdbn_golden, latent_golden):
+    """oracle.interp_images / interp_objective against create_observed_prediction_with_variance run from the reference
+    source (gprbm.py:564-612)."""
+    g, lg = gpdbn_golden, latent_golden
+    o = make_oracle(g, 'trainable')
+    Xi, S = lg['interp/Xi'], int(lg['interp/S'])
+    imgs, pv = ogprbm.interp_images(o, lg['latent/H2'], lg['latent/H1_mean'], Xi, S, latent_draws(lg, 'interp/'))
+    np.testing.assert_allclose(pv, lg['interp/float64/pred_var'], rtol=1e-10)
+    np.testing.assert_allclose(imgs, lg['interp/float64/images'], rtol=1e-9, atol=1e-13)
+    obj, pv2 = ogprbm.interp_objective(o, Xi[1:-1], Xi[0], Xi[-1], 0.1)
+    np.testing.assert_allclose(pv2, lg['interp/float64/pred_var'][1:-1], rtol=1e-10)
+    seg = np.diff(Xi, axis=0)
+    want = np.mean(np.sum(seg ** 2, axis=1)) + 0.1 * np.mean(np.log(lg['interp/float64/pred_var'][1:-1]))
+    np.testing.assert_allclose(obj, want, rtol=1e-10)
+    # the linear initial path of gprbm.py:623-637
+    path = ogprbm.interp_path(Xi[0], Xi[-1], 3)
+    np.testing.assert_allclose(path, Xi[0] + np.linspace(0, 1, 5)[:, None] * (Xi[-1] - Xi[0]), rtol=1e-14)
