@@ -23,12 +23,12 @@ c_size_t = ctypes.c_size_t
 
 class db_rng_t(ctypes.Structure):
     _fields_ = [('seed', ctypes.c_uint64), ('draw', ctypes.c_uint64),
-                ('row_offset', ctypes.c_uint32), ('reserved', ctypes.c_uint32)]
+                ('row_offset', ctypes.c_uint32), ('reserved', ctypes.c_uint32), ('clock', ctypes.c_void_p)]
 
 
 class db_opt_t(ctypes.Structure):
     _fields_ = [('kind', c_int), ('lr', c_float), ('momentum', c_float), ('beta1', c_float),
-                ('beta2', c_float), ('eps', c_float), ('weight_decay', c_float), ('step', c_int)]
+                ('beta2', c_float), ('eps', c_float), ('weight_decay', c_float), ('step', c_int), ('clock', ctypes.c_void_p)]
 
 
 class db_cd_tc_desc_t(ctypes.Structure):
@@ -61,6 +61,7 @@ SIGNATURES = {
     'db_cd_param_count': (c_size_t, [c_int, c_int, c_int]),
     'db_cd_gradients': (c_int, [c_void_p, c_void_p, c_int, c_float_p, c_float_p, c_int, c_int, c_int, c_float_p,
                                 c_float, c_float_p, c_float_p]),
+    'db_clock_advance': (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_uint64, ctypes.c_uint64]),
     'db_optimizer_step': (c_int, [c_void_p, c_void_p, ctypes.POINTER(db_opt_t), c_float_p, c_float_p, c_float_p,
                                   c_size_t]),
     'db_cd_tc_workspace_bytes': (c_size_t, [ctypes.POINTER(db_cd_tc_desc_t)]),
@@ -202,5 +203,6 @@ def check(rc, what):
     return rc
 
 
-def make_rng(seed, draw, row_offset=0):
-    return db_rng_t(int(seed) & 0xFFFFFFFFFFFFFFFF, int(draw) & 0xFFFFFFFFFFFFFFFF, int(row_offset), 0)
+def make_rng(seed, draw, row_offset=0, clock=None):
+    """clock: device address of a 2 x uint64 clock (db_clock_advance) or None."""
+    return db_rng_t(int(seed) & 0xFFFFFFFFFFFFFFFF, int(draw) & 0xFFFFFFFFFFFFFFFF, int(row_offset), 0, clock)

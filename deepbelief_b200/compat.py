@@ -133,6 +133,8 @@ class Optimizer:
         o.eps = getattr(self, 'epsilon', 1e-8)
         o.weight_decay = self.weight_decay
         o.step = self.step_count
+        clock = getattr(self, 'clock', None)            # device clock while the step is captured into a CUDA graph
+        o.clock = clock.data_ptr() if clock is not None else None
         return o
 
 

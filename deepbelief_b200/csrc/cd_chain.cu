@@ -278,6 +278,7 @@ extern "C" int db_cd_tc_step(db_handle_t h, db_stream_t stream, const db_cd_tc_d
   float* gW = grad; float* gb = grad + (size_t)V * H; float* gc = gb + V;
   __half* hstate = d->pcd ? static_cast<__half*>(pcd_state) : ws.hb;
 
+  if (rng && rng->clock) return set_err(h, DB_ERR_UNSUPPORTED, "the tensor-core chain takes its draw ids by value (no device clock)");
   RngArgs r; to_rng(rng, r);
   const uint64_t draw0 = rng ? rng->draw : 0;
   auto set_draw = [&](TcGemmParams& p, uint64_t i) {

@@ -77,7 +77,17 @@ struct RngArgs {
   uint32_t seed_lo, seed_hi;   // key
   uint32_t draw_lo, draw_hi;   // c2, c3: one draw id per sampling call
   uint32_t row_offset;         // global index of local row 0 (row-sharded batches)
+  const unsigned long long* clock;  // optional device clock: draw id += clock[0] (db_rng_t.clock), resolved by rng_resolved
 };
+
+// the draw id a kernel launched with a device clock uses (SIMT kernels call this once per thread)
+__device__ __forceinline__ RngArgs rng_resolved(RngArgs r) {
+  if (r.clock) {
+    const unsigned long long d = (((unsigned long long)r.draw_hi << 32) | r.draw_lo) + __ldg(r.clock);
+    r.draw_lo = (uint32_t)d; r.draw_hi = (uint32_t)(d >> 32); r.clock = nullptr;
+  }
+  return r;
+}
 
 // uniform for element (global_row, col)
 __device__ __forceinline__ float philox_uniform_at(const RngArgs& r, uint32_t grow, uint32_t col) {

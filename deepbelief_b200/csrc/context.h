@@ -39,8 +39,10 @@ inline void to_rng(const db_rng_t* r, RngArgs& o) {
     o.seed_lo = (uint32_t)r->seed; o.seed_hi = (uint32_t)(r->seed >> 32);
     o.draw_lo = (uint32_t)r->draw; o.draw_hi = (uint32_t)(r->draw >> 32);
     o.row_offset = r->row_offset;
+    o.clock = (const unsigned long long*)r->clock;
   } else {
     o.seed_lo = o.seed_hi = o.draw_lo = o.draw_hi = o.row_offset = 0;
+    o.clock = nullptr;
   }
 }
 

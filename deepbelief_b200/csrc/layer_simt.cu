@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(256) layer_forward_kernel(const LayerFwdParams
   BLoadW<TRANS> b{p.W, p.ldw, p.K, p.N};
   float acc[T::TM][T::TN];
   simt_gemm_tile<T>(sm, a, b, m0, n0, 0, p.K, acc);
+  const RngArgs rng = rng_resolved(p.rng);
 #pragma unroll
   for (int i = 0; i < T::TM; ++i) {
     const int m = simt_row<T>(m0, i);
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(256) layer_forward_kernel(const LayerFwdParams
         float ns = 0.0f;
         if (p.noise_scale_mode == DB_BCAST_ROW) ns = __ldg(p.noise_scale + n);
         else if (p.noise_scale_mode == DB_BCAST_FULL) ns = __ldg(p.noise_scale + idx);
-        p.out_sample[idx] = draw_sample(p.sample_kind, val, p.inv_temp, ns, p.injected, p.rng, m, n, idx);
+        p.out_sample[idx] = draw_sample(p.sample_kind, val, p.inv_temp, ns, p.injected, rng, m, n, idx);
       }
     }
   }
@@ -92,7 +93,8 @@ __global__ void __launch_bounds__(256) layer_forward_kernel(const LayerFwdParams
 
 __global__ void sample_kernel(const float* __restrict__ P, int M, int N, int kind, float inv_temp,
                               const float* __restrict__ noise_scale, int ns_mode, const float* __restrict__ injected,
-                              RngArgs rng, float* __restrict__ out) {
+                              RngArgs rng_in, float* __restrict__ out) {
+  const RngArgs rng = rng_resolved(rng_in);
   const size_t total = (size_t)M * N;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int m = (int)(idx / N), n = (int)(idx % N);
@@ -215,6 +217,15 @@ __global__ void softplus_vec_kernel(const float* __restrict__ x, int n, float* _
 // ------------------------------------------------------------------------------------------------
 __global__ void optimizer_kernel(db_opt_t o, float lr_t, float* __restrict__ p, const float* __restrict__ g,
                                  float* __restrict__ st, float* __restrict__ st2, size_t n) {
+  if (o.clock && o.kind == DB_OPT_ADAM) {      // step number from the device clock (graph replay): bias correction here
+    __shared__ float lr_sh;
+    if (threadIdx.x == 0) {
+      const double t = (double)o.step + (double)__ldg((const unsigned long long*)o.clock + 1);
+      lr_sh = (float)((double)o.lr * sqrt(1.0 - pow((double)o.beta2, t)) / (1.0 - pow((double)o.beta1, t)));
+    }
+    __syncthreads();
+    lr_t = lr_sh;
+  }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float th = p[i];
     float gi = __ldg(g + i) + o.weight_decay * th;
@@ -384,6 +395,17 @@ extern "C" int db_cd_gradients(db_handle_t h, db_stream_t stream, int layer_kind
   }
   if (gh) cd_gaussian_hidden_grads_kernel<<<(H + 255) / 256, 256, 0, st>>>(H, c, opt_sigma, gc, gsig);
   return check_launch(h, "cd_gradients");
+}
+
+__global__ void clock_advance_kernel(unsigned long long* clock, unsigned long long draws, unsigned long long steps) {
+  clock[0] += draws;
+  clock[1] += steps;
+}
+
+extern "C" int db_clock_advance(db_handle_t h, db_stream_t stream, uint64_t* clock, uint64_t draws, uint64_t steps) {
+  DB_REQUIRE(h, clock, "null clock");
+  clock_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)clock, draws, steps);
+  return check_launch(h, "clock_advance");
 }
 
 extern "C" int db_optimizer_step_range(db_handle_t h, db_stream_t stream, const db_opt_t* opt, float* params, const float* grad,

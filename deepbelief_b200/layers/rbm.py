@@ -12,6 +12,7 @@ tensors [N, units] and run hand-written CUDA through the C ABI:
 Randomness: a counter-based Philox stream per layer (`seed`), or injected draws via the keyword-only
 `draw=` arguments (parity tests).
 """
+import os
 import pickle
 
 import numpy as np
@@ -120,6 +121,76 @@ class BatchFeeder:
         self._pending = False
         self.slot ^= 1
         return self.dev[s]
+
+
+class CdGraphStep:
+    """One whole training iteration of the general (SIMT) path — lower layers re-sampled, CD-k chain, gradient,
+    optimizer — captured ONCE into a CUDA graph and replayed per batch. The reference-sized configurations
+    (328 x 1024 x 500, CD-1) are launch-bound: ~10 kernels of a few microseconds each behind a Python call chain.
+    Draw ids and the Adam step number cannot be baked into a graph, so the captured kernels add a device clock
+    (db_rng_t.clock / db_opt_t.clock) that the last node of the graph advances: replay j uses exactly the draw ids
+    and step number the j-th eager iteration would, and the results are bit-identical to the eager loop."""
+
+    def __init__(self, lay, batch_shape, k, optimizer, opt_state, grad, n_global, lr, persistent):
+        self.lay, self.k, self.optimizer = lay, k, optimizer
+        dev = lay.device
+        self.batch = torch.empty(tuple(batch_shape), dtype=torch.float32, device=dev)
+        self.rngs = [l.rng for l in lay.layers]                      # this layer first, then the stack below it
+        self.clocks = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in self.rngs]
+
+        def iteration():
+            v0 = lay.bottom.upprop(self.batch) if lay.bottom else self.batch
+            lay.cd_step(v0, k, persistent, grad=grad, n_global=n_global, force_simt=True)
+            lay.apply_gradient(optimizer, grad, opt_state, lr)
+
+        # one eager iteration on a snapshot: loads every kernel, counts the draws each layer consumes, changes nothing
+        snap = (lay._trainable_pair(lay._params)[0].clone(), lay._params.clone(), opt_state.clone(),
+                None if persistent is None else persistent.clone(), [r.draw for r in self.rngs], optimizer.step_count,
+                lay._weights_version)
+        self.batch.zero_()
+        iteration()
+        self.draws = [r.draw - d0 for r, d0 in zip(self.rngs, snap[4])]
+
+        def restore():
+            lay._trainable_pair(lay._params)[0].copy_(snap[0])
+            lay._params.copy_(snap[1])
+            opt_state.copy_(snap[2])
+            if persistent is not None:
+                persistent.copy_(snap[3])
+            for r, d0 in zip(self.rngs, snap[4]):
+                r.draw = d0
+            optimizer.step_count = snap[5]
+        restore()
+        torch.cuda.current_stream().synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        try:
+            for r, c in zip(self.rngs, self.clocks):
+                r.clock = c
+            optimizer.clock = self.clocks[0]
+            with torch.cuda.graph(self.graph):
+                iteration()
+                for c, n in zip(self.clocks, self.draws):
+                    ops.clock_advance(c, n, 1)
+        finally:
+            for r in self.rngs:
+                r.clock = None
+            optimizer.clock = None
+        restore()                                                    # capture executed nothing; host counters rewound
+        self.base_draw, self.base_step = list(snap[4]), snap[5]       # what clock == 0 stands for
+        self.synced = (list(snap[4]), snap[5])                       # host counters the device clocks currently match
+
+    def run(self, batch):
+        now = ([r.draw for r in self.rngs], self.optimizer.step_count)
+        if now != self.synced:                                       # eager sampling in between (evaluation steps): re-base
+            for c, d, b in zip(self.clocks, now[0], self.base_draw):
+                c.copy_(torch.tensor([d - b, now[1] - self.base_step], dtype=torch.int64))
+        self.batch.copy_(batch, non_blocking=True)
+        self.graph.replay()
+        for r, n in zip(self.rngs, self.draws):
+            r.draw += n
+        self.optimizer.step_count += 1
+        self.lay._weights_version += 1
+        self.synced = ([r.draw for r in self.rngs], self.optimizer.step_count)
 
 
 class RBM(layer.Layer):
@@ -469,6 +540,11 @@ class RBM(layer.Layer):
         2k+1 chain GEMMs, the dW GEMM and the bias-gradient reduction (csrc/cd_chain.cu)."""
         return 1 + (2 * k + 1) + 1 + 1
 
+    # train(): iterations of the general path whose per-layer work (rows x V x H) is below this are launch-bound and run
+    # as one captured CUDA graph (CdGraphStep) once the loop is at least GRAPH_MIN_ITERATIONS long
+    GRAPH_MAX_WORK = 1 << 31
+    GRAPH_MIN_ITERATIONS = 8
+
     # SMs left to the NCCL kernels while a dW chunk is computed next to an in-flight all-reduce (the persistent
     # tcgen05 GEMM otherwise occupies every SM and the collective could not start until it has finished)
     COMM_SMS = 16
@@ -578,11 +654,27 @@ class RBM(layer.Layer):
         lr_now = optimizer.learning_rate
         feeder = BatchFeeder(training_data, self.device, max(0, max_iter - start_iter))
         self.last_feeder = feeder
+        graph_step = None
+        width = self.layers[-1].num_v
+        use_graph = (world == 1 and max_iter - start_iter >= self.GRAPH_MIN_ITERATIONS and
+                     os.environ.get('DEEPBELIEF_B200_GRAPH', '1') != '0' and
+                     (pcd or not self._tc_eligible(n_local)) and
+                     n_local * max(l.num_v * l.num_h for l in self.layers) <= self.GRAPH_MAX_WORK)
         for self.iter in range(start_iter, max_iter):
             batch = feeder.next()
-            v0 = self.bottom.upprop(batch) if self.bottom else batch
-            self.cd_update(v0, num_gibbs_steps, optimizer, opt_state, grad, n_global=n_global, lr=lr_now,
-                           persistent=persistent)
+            if use_graph and graph_step is None:
+                try:
+                    graph_step = CdGraphStep(self, (n_local, width), num_gibbs_steps, optimizer, opt_state, grad, n_global,
+                                             lr_now, persistent)
+                except RuntimeError as e:                       # capture not possible here: plain launches
+                    self.logger.warning('CUDA-graph capture of the training iteration failed (%s); eager launches', e)
+                    use_graph = False
+            if graph_step is not None:
+                graph_step.run(batch)
+            else:
+                v0 = self.bottom.upprop(batch) if self.bottom else batch
+                self.cd_update(v0, num_gibbs_steps, optimizer, opt_state, grad, n_global=n_global, lr=lr_now,
+                               persistent=persistent)
             feeder.prefetch()              # host gather + H2D of the next batch overlap this step's kernels
             if step_callback is not None:
                 step_callback(self.iter, grad)

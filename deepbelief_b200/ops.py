@@ -36,9 +36,10 @@ class Rng:
         self.seed = int(seed)
         self.draw = 0
         self.row_offset = int(row_offset)
+        self.clock = None          # device clock tensor (int64 [2]) while a training iteration is captured into a CUDA graph
 
     def next(self, count=1):
-        r = L.make_rng(self.seed, self.draw, self.row_offset)
+        r = L.make_rng(self.seed, self.draw, self.row_offset, self.clock.data_ptr() if self.clock is not None else None)
         self.draw += count
         return r
 
@@ -116,6 +117,12 @@ def cd_gradients(layer_kind, v0, vk, params, V, H, inv_global_n=None, grad=None)
                                  L.fptr(ws), L.fptr(grad))
     L.check(rc, 'db_cd_gradients')
     return grad
+
+
+def clock_advance(clock, draws, steps):
+    """clock[0] += draws, clock[1] += steps on the stream (the last node of a captured training iteration)."""
+    assert clock.dtype == torch.int64 and clock.numel() == 2 and clock.is_cuda
+    L.check(L.lib().db_clock_advance(L.handle(), L.stream(), clock.data_ptr(), int(draws), int(steps)), 'db_clock_advance')
 
 
 def optimizer_step(opt, params, grad, state):

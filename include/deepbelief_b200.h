@@ -67,6 +67,8 @@ typedef struct {
   uint64_t draw;
   uint32_t row_offset;
   uint32_t reserved;
+  const uint64_t* clock; /* optional device clock (db_clock_advance): the draw id used is draw + clock[0], read by the
+                            kernel — a captured CUDA graph replays with fresh draws. NULL = draw as given */
 } db_rng_t;
 
 typedef struct {
@@ -76,6 +78,7 @@ typedef struct {
   float beta1, beta2, eps; /* DB_OPT_ADAM */
   float weight_decay;  /* g += weight_decay * theta (builder-defined extension) */
   int step;            /* 1-based step number t (Adam bias correction) */
+  const uint64_t* clock; /* optional device clock: the step number used is step + clock[1] (graph replay). NULL = step */
 } db_opt_t;
 
 /* ---- context ------------------------------------------------------------------------------- */
@@ -126,6 +129,11 @@ size_t db_cd_param_count(int layer_kind, int V, int H);
 int db_cd_gradients(db_handle_t h, db_stream_t stream, int layer_kind,
                     const float* v0, const float* vk, int N, int V, int H,
                     const float* params, float inv_global_n, float* workspace, float* grad);
+
+/* Device clock for CUDA-graph replay of a training iteration: clock is 2 uint64 in device memory, [0] = draw ids
+ * consumed so far, [1] = optimizer steps taken so far (both relative to the values baked into the captured launches).
+ * db_clock_advance adds (draws, steps) on the stream — captured as the last node of the iteration. */
+int db_clock_advance(db_handle_t h, db_stream_t stream, uint64_t* clock, uint64_t draws, uint64_t steps);
 
 /* One optimizer step over n packed elements; state: Momentum n floats, Adam 2n floats (m | v). */
 int db_optimizer_step(db_handle_t h, db_stream_t stream, const db_opt_t* opt, float* params,

@@ -449,3 +449,60 @@ def test_backprop_loop_reduces_reconstruction_loss(horses):
     lay.backprop(Data(path, batch_size=328, log_epochs=False), Data(path, batch_size=328, log_epochs=False),
                  training_sampling=False, learning_rate=0.05, max_iterations=60, eval_interval=30)
     assert len(lay.loss_y_vals) == 3 and lay.loss_y_vals[-1] < lay.loss_y_vals[0]
+
+
+@pytest.mark.parametrize('case', ['rbm_adam_eval', 'gbrbm_momentum_pcd', 'stack_concrete'])
+def test_training_iteration_as_cuda_graph_is_bit_identical(horses, monkeypatch, case):
+    """RBM.train on the general path replays one captured CUDA graph per iteration (CdGraphStep: draw ids and the Adam
+    step number come from a device clock): the parameters after the loop must be bit-identical to the eager loop —
+    Adam with evaluation steps in between (which consume draws eagerly), Momentum + weight decay with PCD on a
+    Gaussian-visible layer, and a Concrete layer trained on top of a re-sampled bottom layer."""
+    from deepbelief_b200 import compat as tf
+    from deepbelief_b200.layers.data import Data
+    from deepbelief_b200.layers.rbm import RBM, CdGraphStep
+    from deepbelief_b200.layers.gbrbm import GBRBM
+    rs = np.random.RandomState(5)
+    X = horses[:300].astype(np.float32)
+    test = horses[300:328].astype(np.float32)
+
+    def run(graph):
+        monkeypatch.setenv('DEEPBELIEF_B200_GRAPH', '1' if graph else '0')
+        np.random.seed(0)                           # Data reshuffles with the global numpy stream on every epoch wrap
+        rs2 = np.random.RandomState(11)
+        kw = {}
+        if case == 'rbm_adam_eval':
+            lay = RBM(1024, 100, name='g0', seed=3)
+            lay.set_weights((rs2.normal(size=(1024, 100)) * 0.01).astype(np.float32), np.zeros(1024), np.zeros(100))
+            opt, data = tf.train.AdamOptimizer(learning_rate=1e-3), X
+            kw = dict(num_gibbs_steps=2, pcd=False, eval_interval=5)
+        elif case == 'gbrbm_momentum_pcd':
+            lay = GBRBM(1024, 60, name='g1', seed=4)
+            lay.set_weights((rs2.normal(size=(1024, 60)) * 0.001).astype(np.float32), np.zeros(1024), np.zeros(60))
+            opt = tf.train.MomentumOptimizer(learning_rate=1e-3, momentum=0.9, weight_decay=1e-4)
+            data = ((X - X.mean(0)) / (X.std(0) + 1e-3)).astype(np.float32)
+            kw = dict(num_gibbs_steps=1, pcd=True)
+        else:
+            bottom = RBM(1024, 64, temperature=0.1, name='g2b', seed=5)
+            bottom.set_weights((rs2.normal(size=(1024, 64)) * 0.05).astype(np.float32), np.zeros(1024), np.zeros(64))
+            lay = RBM(64, 32, temperature=0.1, bottom=bottom, name='g2', seed=6)
+            lay.set_weights((rs2.normal(size=(64, 32)) * 0.05).astype(np.float32), np.zeros(64), np.zeros(32))
+            opt, data = tf.train.AdamOptimizer(learning_rate=1e-3), X
+            kw = dict(num_gibbs_steps=3, pcd=False)
+        created = []
+        orig = CdGraphStep.__init__
+
+        def spy(self, *a, **k):
+            created.append(1)
+            orig(self, *a, **k)
+        monkeypatch.setattr(CdGraphStep, '__init__', spy)
+        lay.train(opt, Data.from_arrays(data, batch_size=100, log_epochs=False), Data.from_arrays(test, batch_size=14, log_epochs=False),
+                  max_iterations=17, **kw)
+        monkeypatch.setattr(CdGraphStep, '__init__', orig)
+        assert bool(created) == graph
+        return _np(lay._params), lay.rng.draw, opt.step_count
+
+    p_graph, d_graph, s_graph = run(True)
+    p_eager, d_eager, s_eager = run(False)
+    assert (d_graph, s_graph) == (d_eager, s_eager)
+    assert np.array_equal(p_graph, p_eager)
+    assert np.isfinite(p_graph).all() and np.abs(p_graph).max() > 0
