@@ -61,6 +61,8 @@ SIGNATURES = {
     'db_cd_param_count': (c_size_t, [c_int, c_int, c_int]),
     'db_cd_gradients': (c_int, [c_void_p, c_void_p, c_int, c_float_p, c_float_p, c_int, c_int, c_int, c_float_p,
                                 c_float, c_float_p, c_float_p]),
+    'db_cd_gradients_hidden': (c_int, [c_void_p, c_void_p, c_int, c_float_p, c_float_p, c_float_p, c_float_p, c_int, c_int,
+                                       c_int, c_float_p, c_float, c_float_p]),
     'db_clock_advance': (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_uint64, ctypes.c_uint64]),
     'db_optimizer_step': (c_int, [c_void_p, c_void_p, ctypes.POINTER(db_opt_t), c_float_p, c_float_p, c_float_p,
                                   c_size_t]),

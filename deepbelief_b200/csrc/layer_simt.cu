@@ -56,39 +56,48 @@ __device__ __forceinline__ float draw_sample(int kind, float val, float inv_temp
   return val;
 }
 
+// epilogue of one output element: scale, bias, activation, sample
+__device__ __forceinline__ void layer_epilogue(const LayerFwdParams& p, const RngArgs& rng, int m, int n, float x) {
+  if (m >= p.M || n >= p.N) return;
+  const size_t idx = (size_t)m * p.N + n;
+  if (p.col_scale_mode == DB_BCAST_ROW) x *= __ldg(p.col_scale + n);
+  else if (p.col_scale_mode == DB_BCAST_FULL) x *= __ldg(p.col_scale + idx);
+  if (p.bias) x += __ldg(p.bias + n);
+  const float val = p.act == DB_ACT_SIGMOID ? sigmoidf_(x) : x;
+  if (p.out_act) p.out_act[idx] = val;
+  if (p.out_sample) {
+    float ns = 0.0f;
+    if (p.noise_scale_mode == DB_BCAST_ROW) ns = __ldg(p.noise_scale + n);
+    else if (p.noise_scale_mode == DB_BCAST_FULL) ns = __ldg(p.noise_scale + idx);
+    p.out_sample[idx] = draw_sample(p.sample_kind, val, p.inv_temp, ns, p.injected, rng, m, n, idx);
+  }
+}
+
+// grid (N tiles, M tiles, splits); splits > 1: launched as clusters (1,1,splits) that split K (simt_gemm.cuh)
 template <bool TRANS>
-__global__ void __launch_bounds__(256) layer_forward_kernel(const LayerFwdParams p) {
+__global__ void __launch_bounds__(256) layer_forward_kernel(const LayerFwdParams p, int splits) {
   using T = TileSmall;
   __shared__ typename T::Smem sm;
+  __shared__ __align__(16) float red[T::BM * T::BN];
   const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
   ALoadLayer a{p.A, p.lda, p.a_div, p.a_div_mode, p.M, p.K};
   BLoadW<TRANS> b{p.W, p.ldw, p.K, p.N};
   float acc[T::TM][T::TN];
-  simt_gemm_tile<T>(sm, a, b, m0, n0, 0, p.K, acc);
   const RngArgs rng = rng_resolved(p.rng);
+  if (splits == 1) {
+    simt_gemm_tile<T>(sm, a, b, m0, n0, 0, p.K, acc);
 #pragma unroll
-  for (int i = 0; i < T::TM; ++i) {
-    const int m = simt_row<T>(m0, i);
-    if (m >= p.M) continue;
+    for (int i = 0; i < T::TM; ++i) {
+      const int m = simt_row<T>(m0, i);
 #pragma unroll
-    for (int j = 0; j < T::TN; ++j) {
-      const int n = simt_col<T>(n0, j);
-      if (n >= p.N) continue;
-      const size_t idx = (size_t)m * p.N + n;
-      float x = acc[i][j];
-      if (p.col_scale_mode == DB_BCAST_ROW) x *= __ldg(p.col_scale + n);
-      else if (p.col_scale_mode == DB_BCAST_FULL) x *= __ldg(p.col_scale + idx);
-      if (p.bias) x += __ldg(p.bias + n);
-      const float val = p.act == DB_ACT_SIGMOID ? sigmoidf_(x) : x;
-      if (p.out_act) p.out_act[idx] = val;
-      if (p.out_sample) {
-        float ns = 0.0f;
-        if (p.noise_scale_mode == DB_BCAST_ROW) ns = __ldg(p.noise_scale + n);
-        else if (p.noise_scale_mode == DB_BCAST_FULL) ns = __ldg(p.noise_scale + idx);
-        p.out_sample[idx] = draw_sample(p.sample_kind, val, p.inv_temp, ns, p.injected, rng, m, n, idx);
-      }
+      for (int j = 0; j < T::TN; ++j) layer_epilogue(p, rng, m, simt_col<T>(n0, j), acc[i][j]);
     }
+    return;
   }
+  int k_begin, k_end;
+  simt_split_range<T>(p.K, splits, (int)cooperative_groups::this_cluster().block_rank(), k_begin, k_end);
+  simt_gemm_tile<T>(sm, a, b, m0, n0, k_begin, k_end, acc);
+  simt_cluster_reduce<T>(red, acc, splits, [&](int r, int c, float x) { layer_epilogue(p, rng, m0 + r, n0 + c, x); });
 }
 
 __global__ void sample_kernel(const float* __restrict__ P, int M, int N, int kind, float inv_temp,
@@ -162,36 +171,57 @@ struct BLoadQ {
   }
 };
 __global__ void __launch_bounds__(256) cd_dw_kernel(const float* v0, const float* vk, const float* q0, const float* qk,
-                                                    int N, int V, int H, float scale, float* __restrict__ dW) {
+                                                    int N, int V, int H, float scale, float* __restrict__ dW, int splits) {
   using T = TileSmall;
   __shared__ typename T::Smem sm;
+  __shared__ __align__(16) float red[T::BM * T::BN];
   const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
   ALoadVT a{v0, vk, N, V};
   BLoadQ b{q0, qk, N, H};
   float acc[T::TM][T::TN];
-  simt_gemm_tile<T>(sm, a, b, m0, n0, 0, 2 * N, acc);
+  if (splits == 1) {
+    simt_gemm_tile<T>(sm, a, b, m0, n0, 0, 2 * N, acc);
 #pragma unroll
-  for (int i = 0; i < T::TM; ++i) {
-    const int m = simt_row<T>(m0, i);
-    if (m >= V) continue;
+    for (int i = 0; i < T::TM; ++i) {
+      const int m = simt_row<T>(m0, i);
+      if (m >= V) continue;
 #pragma unroll
-    for (int j = 0; j < T::TN; ++j) {
-      const int n = simt_col<T>(n0, j);
-      if (n < H) dW[(size_t)m * H + n] = scale * acc[i][j];
+      for (int j = 0; j < T::TN; ++j) {
+        const int n = simt_col<T>(n0, j);
+        if (n < H) dW[(size_t)m * H + n] = scale * acc[i][j];
+      }
     }
+    return;
   }
+  int k_begin, k_end;
+  simt_split_range<T>(2 * N, splits, (int)cooperative_groups::this_cluster().block_rank(), k_begin, k_end);
+  simt_gemm_tile<T>(sm, a, b, m0, n0, k_begin, k_end, acc);
+  simt_cluster_reduce<T>(red, acc, splits, [&](int r, int c, float x) {
+    if (m0 + r < V && n0 + c < H) dW[(size_t)(m0 + r) * H + n0 + c] = scale * x;
+  });
 }
 
-// out[c] += scale * sum_{n in chunk} (a[n,c] - b[n,c]);  out must be zeroed first
-__global__ void colsum_diff_kernel(const float* __restrict__ a, const float* __restrict__ b, int N, int C, float scale,
-                                   float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// out[c] += scale * sum_{n in chunk} (a[n,c] - b[n,c]);  out must be zeroed first. 256 threads = 32 columns x 8 row
+// lanes (rows n = lane, lane + 8, ...), lanes summed in order through shared memory; grid (ceil(C/32), row chunks) —
+// with one row chunk the result is deterministic (a single atomicAdd onto 0 per column)
+__global__ void __launch_bounds__(256) colsum_diff_kernel(const float* __restrict__ a, const float* __restrict__ b, int N,
+                                                          int C, float scale, float* __restrict__ out) {
+  __shared__ float part[8][33];
+  const int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   const int rows_per = (N + gridDim.y - 1) / gridDim.y;
   const int r0 = blockIdx.y * rows_per, r1 = min(N, r0 + rows_per);
   float s = 0.0f;
-  for (int n = r0; n < r1; ++n) s += __ldg(a + (size_t)n * C + c) - __ldg(b + (size_t)n * C + c);
-  atomicAdd(out + c, scale * s);
+  if (c < C)
+    for (int n = r0 + lane; n < r1; n += 8) s += __ldg(a + (size_t)n * C + c) - __ldg(b + (size_t)n * C + c);
+  part[lane][cl] = s;
+  __syncthreads();
+  if (lane == 0 && c < C) {
+    float t = part[0][cl];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) t += part[q][cl];
+    atomicAdd(out + c, scale * t);
+  }
 }
 
 // Gaussian-hidden bias / sigma gradients from d[j] = inv_n * sum_n (x0 - xk)[n,j]  (held in gc on entry)
@@ -282,8 +312,10 @@ inline int ew_grid(size_t n, int num_sms) {
 
 int launch_layer_forward(db_handle_t h, cudaStream_t st, const LayerFwdParams& p, int transW) {
   dim3 grid((p.N + TileSmall::BN - 1) / TileSmall::BN, (p.M + TileSmall::BM - 1) / TileSmall::BM);
-  if (transW) layer_forward_kernel<true><<<grid, 256, 0, st>>>(p);
-  else layer_forward_kernel<false><<<grid, 256, 0, st>>>(p);
+  const int splits = simt_splits((long)grid.x * grid.y, p.K, h->num_sms);
+  grid.z = splits;
+  if (transW) simt_launch_split(layer_forward_kernel<true>, grid, 256, st, p, splits);
+  else simt_launch_split(layer_forward_kernel<false>, grid, 256, st, p, splits);
   return check_launch(h, "layer_forward");
 }
 
@@ -353,48 +385,71 @@ extern "C" size_t db_cd_param_count(int layer_kind, int V, int H) {
   return n;
 }
 
-extern "C" int db_cd_gradients(db_handle_t h, db_stream_t stream, int layer_kind, const float* v0, const float* vk, int N,
-                               int V, int H, const float* params, float inv_global_n, float* workspace, float* grad) {
-  DB_REQUIRE(h, v0 && vk && params && workspace && grad && N > 0 && V > 0 && H > 0, "null operand or empty shape");
-  cudaStream_t st = (cudaStream_t)stream;
+// hp0 / hpk: hidden probabilities sigmoid(v W + c) at the two ends of the chain when the caller already has them
+// (Bernoulli-hidden layers: they are what the chain sampled h_0 and h_k from), else recomputed here
+static int cd_gradients_impl(db_handle_t h, cudaStream_t st, int layer_kind, const float* v0, const float* vk,
+                             const float* hp0, const float* hpk, int N, int V, int H, const float* params,
+                             float inv_global_n, float* workspace, float* grad) {
   const float* W = params;
   const float* c = params + (size_t)V * H + V;
   const float* opt_sigma = c + H;
   float* gW = grad; float* gb = grad + (size_t)V * H; float* gc = gb + V; float* gsig = gc + H;
-  float* q0 = workspace; float* qk = workspace + (size_t)N * H;
   const bool gh = gaussian_hidden(layer_kind);
+  const float* q0 = hp0; const float* qk = hpk;
   float* sigma = nullptr;
   if (gh) {
     // effective sigma_h = softplus(opt_sigma_h) (bgrbm.py:51), staged in the gsig slot until the end
     sigma = gsig;
     softplus_vec_kernel<<<(H + 255) / 256, 256, 0, st>>>(opt_sigma, H, sigma);
   }
-  for (int side = 0; side < 2; ++side) {
-    LayerFwdParams p{};
-    p.A = side ? vk : v0; p.lda = V; p.W = W; p.ldw = H; p.M = N; p.N = H; p.K = V; p.act = DB_ACT_LINEAR;
-    p.out_act = side ? qk : q0;
-    int rc = launch_layer_forward(h, st, p, 0);
-    if (rc) return rc;
-  }
-  // bias sums first (Gaussian hiddens need x0 - xk, i.e. before c/sigma is added; the shift cancels anyway)
+  const int row_chunks = N >= 8192 ? 8 : 1;
   cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)(V + H), st);
-  {
-    dim3 g((V + 255) / 256, N >= 4096 ? 32 : (N >= 512 ? 8 : 1));
-    colsum_diff_kernel<<<g, 256, 0, st>>>(v0, vk, N, V, -inv_global_n, gb);
+  colsum_diff_kernel<<<dim3((V + 31) / 32, row_chunks), 256, 0, st>>>(v0, vk, N, V, -inv_global_n, gb);
+  if (!hp0) {
+    float* w0 = workspace; float* wk = workspace + (size_t)N * H;
+    for (int side = 0; side < 2; ++side) {
+      LayerFwdParams p{};
+      p.A = side ? vk : v0; p.lda = V; p.W = W; p.ldw = H; p.M = N; p.N = H; p.K = V;
+      if (gh) { p.act = DB_ACT_LINEAR; }                       // x = v W; c / sigma is added below
+      else { p.act = DB_ACT_SIGMOID; p.bias = c; }             // q = sigmoid(v W + c) in the GEMM epilogue
+      p.out_act = side ? wk : w0;
+      int rc = launch_layer_forward(h, st, p, 0);
+      if (rc) return rc;
+    }
+    q0 = w0; qk = wk;
+    if (gh) {
+      // bias sums need x0 - xk, i.e. before c / sigma is added (the shift cancels in the difference anyway)
+      colsum_diff_kernel<<<dim3((H + 31) / 32, row_chunks), 256, 0, st>>>(q0, qk, N, H, -inv_global_n, gc);
+      const size_t nh = (size_t)N * H;
+      cd_hidden_term_kernel<<<ew_grid(nh, h->num_sms), 256, 0, st>>>(1, w0, N, H, c, sigma);
+      cd_hidden_term_kernel<<<ew_grid(nh, h->num_sms), 256, 0, st>>>(1, wk, N, H, c, sigma);
+    }
   }
-  const size_t nh = (size_t)N * H;
-  cd_hidden_term_kernel<<<ew_grid(nh, h->num_sms), 256, 0, st>>>(gh ? 1 : 0, q0, N, H, c, sigma);
-  cd_hidden_term_kernel<<<ew_grid(nh, h->num_sms), 256, 0, st>>>(gh ? 1 : 0, qk, N, H, c, sigma);
-  {
-    dim3 g((H + 255) / 256, N >= 4096 ? 32 : (N >= 512 ? 8 : 1));
-    colsum_diff_kernel<<<g, 256, 0, st>>>(q0, qk, N, H, -inv_global_n, gc);
-  }
+  if (!gh) colsum_diff_kernel<<<dim3((H + 31) / 32, row_chunks), 256, 0, st>>>(q0, qk, N, H, -inv_global_n, gc);
   {
     dim3 g((H + TileSmall::BN - 1) / TileSmall::BN, (V + TileSmall::BM - 1) / TileSmall::BM);
-    cd_dw_kernel<<<g, 256, 0, st>>>(v0, vk, q0, qk, N, V, H, -inv_global_n, gW);
+    const int splits = simt_splits((long)g.x * g.y, 2 * N, h->num_sms);
+    g.z = splits;
+    simt_launch_split(cd_dw_kernel, g, 256, st, v0, vk, q0, qk, N, V, H, -inv_global_n, gW, splits);
   }
   if (gh) cd_gaussian_hidden_grads_kernel<<<(H + 255) / 256, 256, 0, st>>>(H, c, opt_sigma, gc, gsig);
   return check_launch(h, "cd_gradients");
+}
+
+extern "C" int db_cd_gradients(db_handle_t h, db_stream_t stream, int layer_kind, const float* v0, const float* vk, int N,
+                               int V, int H, const float* params, float inv_global_n, float* workspace, float* grad) {
+  DB_REQUIRE(h, v0 && vk && params && workspace && grad && N > 0 && V > 0 && H > 0, "null operand or empty shape");
+  return cd_gradients_impl(h, (cudaStream_t)stream, layer_kind, v0, vk, nullptr, nullptr, N, V, H, params, inv_global_n,
+                           workspace, grad);
+}
+
+extern "C" int db_cd_gradients_hidden(db_handle_t h, db_stream_t stream, int layer_kind, const float* v0, const float* vk,
+                                      const float* hp0, const float* hpk, int N, int V, int H, const float* params,
+                                      float inv_global_n, float* grad) {
+  DB_REQUIRE(h, v0 && vk && hp0 && hpk && params && grad && N > 0 && V > 0 && H > 0, "null operand or empty shape");
+  DB_REQUIRE(h, !gaussian_hidden(layer_kind), "Gaussian-hidden layers recompute their hidden term (db_cd_gradients)");
+  return cd_gradients_impl(h, (cudaStream_t)stream, layer_kind, v0, vk, hp0, hpk, N, V, H, params, inv_global_n, nullptr,
+                           grad);
 }
 
 __global__ void clock_advance_kernel(unsigned long long* clock, unsigned long long draws, unsigned long long steps) {

@@ -6,6 +6,8 @@
 // callers can fuse prologues (bgrbm.py:126 h/sigma_h), transposed or triangular views, and on-the-fly
 // operands (e.g. the RBF Gram entries) without materialising them.
 #pragma once
+#include <cooperative_groups.h>
+#include <utility>
 #include "common.cuh"
 
 namespace db {
@@ -118,6 +120,73 @@ template <class T>
 __device__ __forceinline__ int simt_col(int n0, int j) {
   const int tx = threadIdx.x % (T::BN / T::TN);
   return n0 + (j / 4) * (T::BN / (T::TN / 4)) + tx * 4 + (j % 4);
+}
+
+// ---- cluster split-K ---------------------------------------------------------------------------------------
+// The reference-sized layers (328 x 1024 x 500) give a 64 x 64 tile grid of ~50 CTAs for 148 SMs, each CTA walking
+// the whole K serially: 4 % of the thread slots, 4-6 TFLOP/s. Such launches run as thread-block clusters (1,1,S):
+// the S CTAs of a cluster share one output tile and split K; every CTA parks its micro-tile in its own shared memory,
+// and after a cluster barrier CTA r sums rows [r BM/S, (r+1) BM/S) of the S partial tiles through distributed shared
+// memory — in rank order, so the result does not depend on scheduling — and runs the epilogue on them.
+
+// S in {1,2,4,8}: enough CTAs for two per SM, at least 64 columns of K each
+inline int simt_splits(long tiles, int K, int num_sms) {
+  int s = 1;
+  while (s < 8 && tiles * s < 2L * num_sms && K / (2 * s) >= 64) s *= 2;
+  return s;
+}
+// this CTA's K range [k_begin, k_end) of a K split S ways (multiples of BK)
+template <class T>
+__device__ __forceinline__ void simt_split_range(int K, int splits, int rank, int& k_begin, int& k_end) {
+  const int chunk = ((K + splits - 1) / splits + T::BK - 1) / T::BK * T::BK;
+  k_begin = min(K, rank * chunk);
+  k_end = min(K, k_begin + chunk);
+}
+// red: BM*BN floats of shared memory (16-byte aligned); epi(m_local, n_local, value) is called once per tile element by
+// exactly one thread of the cluster
+template <class T, class Epi>
+__device__ __forceinline__ void simt_cluster_reduce(float* red, const float (&acc)[T::TM][T::TN], int splits, Epi&& epi) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x;
+  const int tx = tid % (T::BN / T::TN), ty = tid / (T::BN / T::TN);
+#pragma unroll
+  for (int i = 0; i < T::TM; ++i) {
+    const int row = (i / 4) * (T::BM / (T::TM / 4)) + ty * 4 + (i % 4);
+#pragma unroll
+    for (int g = 0; g < T::TN / 4; ++g) {
+      const int col = g * (T::BN / (T::TN / 4)) + tx * 4;
+      *reinterpret_cast<float4*>(red + row * T::BN + col) =
+          make_float4(acc[i][4 * g], acc[i][4 * g + 1], acc[i][4 * g + 2], acc[i][4 * g + 3]);
+    }
+  }
+  cluster.sync();
+  const int rank = (int)cluster.block_rank();
+  const int rows_per = T::BM / splits;
+  const float* src[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) src[q] = q < splits ? cluster.map_shared_rank(red, q) : red;
+  for (int idx = tid; idx < rows_per * T::BN; idx += T::THREADS) {
+    const int row = rank * rows_per + idx / T::BN, col = idx % T::BN;
+    float s = src[0][row * T::BN + col];
+#pragma unroll
+    for (int q = 1; q < 8; ++q)
+      if (q < splits) s += src[q][row * T::BN + col];
+    epi(row, col, s);
+  }
+  cluster.sync();     // nobody leaves while its tile is still being read
+}
+
+// launch `kernel` on `grid` (z = splits) as clusters of (1,1,splits); splits == 1 is a plain launch
+template <class... KArgs, class... Args>
+inline cudaError_t simt_launch_split(void (*kernel)(KArgs...), dim3 grid, int threads, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = grid.z;
+  cfg.attrs = at; cfg.numAttrs = grid.z > 1 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 using TileSmall = SimtTile<64, 64, 16, 4, 4>;     // small layers / ragged shapes: more CTAs

@@ -521,7 +521,9 @@ class RBM(layer.Layer):
             d = injected[off:off + count].view(n, -1)
             off += count
             return d
-        h0 = self._up_sample(v0, True, take(n * self.num_h))[1]
+        # Bernoulli-hidden layers: the probabilities h_0 and h_k are sampled from are the hidden terms of the gradient
+        reuse = self.hidden_act == L.ACT_SIGMOID
+        p0, h0 = self._up_sample(v0, True, take(n * self.num_h), want_probs=reuse)
         h = h0 if persistent is None else persistent
         draws = None
         if injected is not None:
@@ -529,10 +531,11 @@ class RBM(layer.Layer):
             for _ in range(k):
                 dv = take(n * self.num_v) if self._visible_sampling(True)[0] != L.SAMPLE_NONE else None
                 draws.append((dv, take(n * self.num_h)))
-        _, vk, _, hk = self.gibbs_sample(h, k, draws=draws)
+        _, vk, pk, hk = self.gibbs_sample(h, k, draws=draws)
         if persistent is not None:
             persistent.copy_(hk)
-        ops.cd_gradients(self.layer_kind, v0, vk, self._params, self.num_v, self.num_h, inv_n, grad)
+        ops.cd_gradients(self.layer_kind, v0, vk, self._params, self.num_v, self.num_h, inv_n, grad,
+                         hidden_probs=(p0, pk) if reuse else None)
         return grad, vk, hk
 
     def launches_per_cd_step(self, k):

@@ -104,13 +104,22 @@ def cd_param_count(layer_kind, V, H):
     return int(L.lib().db_cd_param_count(layer_kind, V, H))
 
 
-def cd_gradients(layer_kind, v0, vk, params, V, H, inv_global_n=None, grad=None):
-    """Packed CD gradient (W|b|c[|opt_sigma_h]) from the two ends of the chain."""
+def cd_gradients(layer_kind, v0, vk, params, V, H, inv_global_n=None, grad=None, hidden_probs=None):
+    """Packed CD gradient (W|b|c[|opt_sigma_h]) from the two ends of the chain. hidden_probs: (p0, pk), the hidden
+    probabilities at v0 and vk when the chain has them already (Bernoulli-hidden layers)."""
     v0 = _f32(v0)
     vk = _f32(vk)
     N = v0.shape[0]
     if grad is None:
         grad = torch.empty_like(params)
+    if hidden_probs is not None:
+        p0, pk = _f32(hidden_probs[0]), _f32(hidden_probs[1])
+        assert p0.shape == (N, H) and pk.shape == (N, H)
+        rc = L.lib().db_cd_gradients_hidden(L.handle(), L.stream(), layer_kind, L.fptr(v0), L.fptr(vk), L.fptr(p0),
+                                            L.fptr(pk), N, V, H, L.fptr(params),
+                                            float(inv_global_n if inv_global_n is not None else 1.0 / N), L.fptr(grad))
+        L.check(rc, 'db_cd_gradients_hidden')
+        return grad
     ws = torch.empty((2, N, H), device=v0.device, dtype=torch.float32)
     rc = L.lib().db_cd_gradients(L.handle(), L.stream(), layer_kind, L.fptr(v0), L.fptr(vk), N, V, H,
                                  L.fptr(params), float(inv_global_n if inv_global_n is not None else 1.0 / N),

@@ -130,6 +130,13 @@ int db_cd_gradients(db_handle_t h, db_stream_t stream, int layer_kind,
                     const float* v0, const float* vk, int N, int V, int H,
                     const float* params, float inv_global_n, float* workspace, float* grad);
 
+/* Same gradient when the caller already holds the hidden probabilities hp0 = sigmoid(v0 W + c) and hpk = sigmoid(vk W + c)
+ * [N,H] — on Bernoulli-hidden layers (RBM, GBRBM) they are what the chain sampled h_0 and h_k from (rbm.py:628, 368-370),
+ * so the two free-energy GEMMs of rbm.py:388-390 are not repeated. Gaussian-hidden kinds are refused. */
+int db_cd_gradients_hidden(db_handle_t h, db_stream_t stream, int layer_kind,
+                           const float* v0, const float* vk, const float* hp0, const float* hpk, int N, int V, int H,
+                           const float* params, float inv_global_n, float* grad);
+
 /* Device clock for CUDA-graph replay of a training iteration: clock is 2 uint64 in device memory, [0] = draw ids
  * consumed so far, [1] = optimizer steps taken so far (both relative to the values baked into the captured launches).
  * db_clock_advance adds (draws, steps) on the stream — captured as the last node of the iteration. */

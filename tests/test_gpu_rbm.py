@@ -506,3 +506,61 @@ def test_training_iteration_as_cuda_graph_is_bit_identical(horses, monkeypatch, 
     assert (d_graph, s_graph) == (d_eager, s_eager)
     assert np.array_equal(p_graph, p_eager)
     assert np.isfinite(p_graph).all() and np.abs(p_graph).max() > 0
+
+
+@pytest.mark.parametrize('M,N,K,trans', [(328, 500, 1024, False), (328, 1024, 500, True), (70, 130, 1000, False),
+                                         (100, 60, 1024, False), (33, 64, 257, True), (5000, 100, 200, False)])
+def test_layer_forward_cluster_split_k(M, N, K, trans):
+    """Launches with few output tiles run as thread-block clusters that split K and reduce through distributed shared
+    memory (simt_gemm.cuh): every epilogue (scale, bias, sigmoid, Bernoulli with injected uniforms, Gaussian noise,
+    a_div prologue) against a float64 evaluation, ragged edges included, and bit-identical on repetition."""
+    from deepbelief_b200 import ops, _lib as L
+    rs = np.random.RandomState(M + N + K)
+    A = rs.rand(M, K).astype(np.float32)
+    W = (rs.normal(size=(N, K) if trans else (K, N)) * 0.05).astype(np.float32)
+    bias = rs.normal(size=N).astype(np.float32) * 0.1
+    scale = (0.5 + rs.rand(1, N)).astype(np.float32)
+    div = (0.5 + rs.rand(1, K)).astype(np.float32)
+    cu = lambda a: torch.as_tensor(a).cuda()  # noqa: E731
+    x = (A.astype(np.float64) / div) @ (W.T if trans else W).astype(np.float64) * scale + bias
+    p = 1.0 / (1.0 + np.exp(-x))
+    # margin-guaranteed uniforms: |p - u| > 1e-3
+    u = rs.rand(M, N)
+    u = np.where(np.abs(p - u) < 1e-3, np.clip(p + 0.01, 0, 1), u).astype(np.float32)
+    act, s = ops.layer_forward(cu(A), cu(W), cu(bias), trans, L.ACT_SIGMOID, L.SAMPLE_BERNOULLI, a_div=cu(div),
+                               col_scale=cu(scale), injected=cu(u))
+    np.testing.assert_allclose(_np(act), p, rtol=PROB_RTOL, atol=1e-7)
+    np.testing.assert_array_equal(_np(s), (p > u).astype(np.float64))
+    act2, s2 = ops.layer_forward(cu(A), cu(W), cu(bias), trans, L.ACT_SIGMOID, L.SAMPLE_BERNOULLI, a_div=cu(div),
+                                 col_scale=cu(scale), injected=cu(u))
+    assert torch.equal(act, act2) and torch.equal(s, s2)
+    eps = rs.normal(size=(M, N)).astype(np.float32)
+    lin, g = ops.layer_forward(cu(A), cu(W), cu(bias), trans, L.ACT_LINEAR, L.SAMPLE_GAUSSIAN, a_div=cu(div),
+                               col_scale=cu(scale), noise_scale=cu(scale), injected=cu(eps))
+    assert _normrel(_np(lin), x) < 2e-6
+    assert _normrel(_np(g), x + scale * eps) < 2e-6
+
+
+@pytest.mark.parametrize('kind', ['rbm', 'gbrbm'])
+def test_cd_gradient_from_chain_probabilities_is_bit_identical(horses, kind):
+    """db_cd_gradients_hidden takes the hidden probabilities the chain sampled from instead of repeating the two
+    free-energy GEMMs (rbm.py:388-390): same bits as db_cd_gradients, and both within tolerance of the oracle."""
+    from deepbelief_b200 import ops
+    rs = np.random.RandomState(3)
+    V, H = 1024, 500
+    lay = _layer(kind, V, H, name='q' + kind)
+    W = (rs.normal(size=(V, H)) * 0.02).astype(np.float32)
+    b, c = rs.normal(size=V).astype(np.float32) * 0.1, rs.normal(size=H).astype(np.float32) * 0.1
+    lay.set_weights(W, b, c)
+    v0 = horses.astype(np.float32) if kind == 'rbm' else rs.normal(size=(328, V)).astype(np.float32)
+    vk = (rs.rand(328, V) < 0.4).astype(np.float32) if kind == 'rbm' else rs.normal(size=(328, V)).astype(np.float32)
+    p0, pk = lay.h_probs(v0), lay.h_probs(vk)
+    g_plain = lay.cd_gradient(v0, vk)
+    g_hidden = ops.cd_gradients(lay.layer_kind, torch.as_tensor(v0).cuda(), torch.as_tensor(vk).cuda(), lay._params, V, H,
+                                hidden_probs=(p0, pk))
+    assert torch.equal(g_plain, g_hidden)
+    orc = orbm.RBMOracle(W, b, c, kind=kind)
+    want = orc.cd_grad_packed(v0.astype(np.float64), vk.astype(np.float64))
+    got = _np(g_hidden)
+    for lo, hi in ((0, V * H), (V * H, V * H + V), (V * H + V, V * H + V + H)):
+        assert _normrel(got[lo:hi], want[lo:hi]) < GRAD_NORMREL
