@@ -30,6 +30,19 @@ struct ALoadLayer {
     else if (div_mode == DB_BCAST_FULL) v = v / __ldg(div + (size_t)m * lda + k);
     return v;
   }
+  __host__ __device__ bool vec_ok() const {
+    return lda % 4 == 0 && aligned16(A) && (div_mode == DB_BCAST_NONE || aligned16(div));
+  }
+  __device__ __forceinline__ float4 load4(int m, int k) const {     // k .. k+3 of row m
+    if (m >= M || k >= K) return make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k + 3 >= K) return make_float4((*this)(m, k), (*this)(m, k + 1), (*this)(m, k + 2), (*this)(m, k + 3));
+    float4 v = __ldg(reinterpret_cast<const float4*>(A + (size_t)m * lda + k));
+    if (div_mode != DB_BCAST_NONE) {
+      const float4 d = __ldg(reinterpret_cast<const float4*>(div + (div_mode == DB_BCAST_ROW ? (size_t)k : (size_t)m * lda + k)));
+      v.x = v.x / d.x; v.y = v.y / d.y; v.z = v.z / d.z; v.w = v.w / d.w;
+    }
+    return v;
+  }
 };
 template <bool TRANS>
 struct BLoadW {
@@ -38,6 +51,16 @@ struct BLoadW {
   __device__ __forceinline__ float operator()(int k, int n) const {
     if (k >= K || n >= N) return 0.0f;
     return TRANS ? __ldg(W + (size_t)n * ldw + k) : __ldg(W + (size_t)k * ldw + n);
+  }
+  __host__ __device__ bool vec_ok() const { return ldw % 4 == 0 && aligned16(W); }
+  __device__ __forceinline__ float4 load4(int k, int n) const {     // TRANS: k .. k+3 of column n; else n .. n+3 of row k
+    if (k >= K || n >= N) return make_float4(0.f, 0.f, 0.f, 0.f);
+    if (TRANS) {
+      if (k + 3 >= K) return make_float4((*this)(k, n), (*this)(k + 1, n), (*this)(k + 2, n), (*this)(k + 3, n));
+      return __ldg(reinterpret_cast<const float4*>(W + (size_t)n * ldw + k));
+    }
+    if (n + 3 >= N) return make_float4((*this)(k, n), (*this)(k, n + 1), (*this)(k, n + 2), (*this)(k, n + 3));
+    return __ldg(reinterpret_cast<const float4*>(W + (size_t)k * ldw + n));
   }
 };
 
@@ -73,30 +96,21 @@ __device__ __forceinline__ void layer_epilogue(const LayerFwdParams& p, const Rn
   }
 }
 
-// grid (N tiles, M tiles, splits); splits > 1: launched as clusters (1,1,splits) that split K (simt_gemm.cuh)
-template <bool TRANS>
+// grid (N tiles, M tiles, splits); splits > 1: launched as clusters (1,1,splits) that split K (simt_gemm.cuh).
+// VEC: float4 operand loads (alignment checked by the launcher)
+template <bool TRANS, class T, bool VEC>
 __global__ void __launch_bounds__(256) layer_forward_kernel(const LayerFwdParams p, int splits) {
-  using T = TileSmall;
   __shared__ typename T::Smem sm;
   __shared__ __align__(16) float red[T::BM * T::BN];
   const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
   ALoadLayer a{p.A, p.lda, p.a_div, p.a_div_mode, p.M, p.K};
   BLoadW<TRANS> b{p.W, p.ldw, p.K, p.N};
   float acc[T::TM][T::TN];
-  const RngArgs rng = rng_resolved(p.rng);
-  if (splits == 1) {
-    simt_gemm_tile<T>(sm, a, b, m0, n0, 0, p.K, acc);
-#pragma unroll
-    for (int i = 0; i < T::TM; ++i) {
-      const int m = simt_row<T>(m0, i);
-#pragma unroll
-      for (int j = 0; j < T::TN; ++j) layer_epilogue(p, rng, m, simt_col<T>(n0, j), acc[i][j]);
-    }
-    return;
-  }
   int k_begin, k_end;
-  simt_split_range<T>(p.K, splits, (int)cooperative_groups::this_cluster().block_rank(), k_begin, k_end);
-  simt_gemm_tile<T>(sm, a, b, m0, n0, k_begin, k_end, acc);
+  simt_split_range<T>(p.K, splits, k_begin, k_end);
+  if (VEC) simt_gemm_tile_vec<T>(sm, a, b, m0, n0, k_begin, k_end, acc);
+  else simt_gemm_tile<T>(sm, a, b, m0, n0, k_begin, k_end, acc);
+  const RngArgs rng = rng_resolved(p.rng);
   simt_cluster_reduce<T>(red, acc, splits, [&](int r, int c, float x) { layer_epilogue(p, rng, m0 + r, n0 + c, x); });
 }
 
@@ -161,6 +175,12 @@ struct ALoadVT {
     // k = 2n + phase: data and model terms alternate so the fp32 partial sums of the difference stay small
     return (k & 1) ? __ldg(vk + (size_t)(k >> 1) * V + m) : __ldg(v0 + (size_t)(k >> 1) * V + m);
   }
+  __host__ __device__ bool vec_ok() const { return V % 4 == 0 && aligned16(v0) && aligned16(vk); }
+  __device__ __forceinline__ float4 load4(int m, int k) const {     // m .. m+3 of row k
+    if (m >= V || k >= 2 * N) return make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m + 3 >= V) return make_float4((*this)(m, k), (*this)(m + 1, k), (*this)(m + 2, k), (*this)(m + 3, k));
+    return __ldg(reinterpret_cast<const float4*>(((k & 1) ? vk : v0) + (size_t)(k >> 1) * V + m));
+  }
 };
 struct BLoadQ {
   static constexpr bool k_contig = false;
@@ -169,57 +189,69 @@ struct BLoadQ {
     if (n >= H || k >= 2 * N) return 0.0f;
     return (k & 1) ? -__ldg(qk + (size_t)(k >> 1) * H + n) : __ldg(q0 + (size_t)(k >> 1) * H + n);
   }
+  __host__ __device__ bool vec_ok() const { return H % 4 == 0 && aligned16(q0) && aligned16(qk); }
+  __device__ __forceinline__ float4 load4(int k, int n) const {     // n .. n+3 of row k
+    if (n >= H || k >= 2 * N) return make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n + 3 >= H) return make_float4((*this)(k, n), (*this)(k, n + 1), (*this)(k, n + 2), (*this)(k, n + 3));
+    const float4 v = __ldg(reinterpret_cast<const float4*>(((k & 1) ? qk : q0) + (size_t)(k >> 1) * H + n));
+    return (k & 1) ? make_float4(-v.x, -v.y, -v.z, -v.w) : v;
+  }
 };
+template <class T, bool VEC>
 __global__ void __launch_bounds__(256) cd_dw_kernel(const float* v0, const float* vk, const float* q0, const float* qk,
                                                     int N, int V, int H, float scale, float* __restrict__ dW, int splits) {
-  using T = TileSmall;
   __shared__ typename T::Smem sm;
   __shared__ __align__(16) float red[T::BM * T::BN];
   const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
   ALoadVT a{v0, vk, N, V};
   BLoadQ b{q0, qk, N, H};
   float acc[T::TM][T::TN];
-  if (splits == 1) {
-    simt_gemm_tile<T>(sm, a, b, m0, n0, 0, 2 * N, acc);
-#pragma unroll
-    for (int i = 0; i < T::TM; ++i) {
-      const int m = simt_row<T>(m0, i);
-      if (m >= V) continue;
-#pragma unroll
-      for (int j = 0; j < T::TN; ++j) {
-        const int n = simt_col<T>(n0, j);
-        if (n < H) dW[(size_t)m * H + n] = scale * acc[i][j];
-      }
-    }
-    return;
-  }
   int k_begin, k_end;
-  simt_split_range<T>(2 * N, splits, (int)cooperative_groups::this_cluster().block_rank(), k_begin, k_end);
-  simt_gemm_tile<T>(sm, a, b, m0, n0, k_begin, k_end, acc);
+  simt_split_range<T>(2 * N, splits, k_begin, k_end);
+  if (VEC) simt_gemm_tile_vec<T>(sm, a, b, m0, n0, k_begin, k_end, acc);
+  else simt_gemm_tile<T>(sm, a, b, m0, n0, k_begin, k_end, acc);
   simt_cluster_reduce<T>(red, acc, splits, [&](int r, int c, float x) {
     if (m0 + r < V && n0 + c < H) dW[(size_t)(m0 + r) * H + n0 + c] = scale * x;
   });
 }
 
-// out[c] += scale * sum_{n in chunk} (a[n,c] - b[n,c]);  out must be zeroed first. 256 threads = 32 columns x 8 row
-// lanes (rows n = lane, lane + 8, ...), lanes summed in order through shared memory; grid (ceil(C/32), row chunks) —
-// with one row chunk the result is deterministic (a single atomicAdd onto 0 per column)
-__global__ void __launch_bounds__(256) colsum_diff_kernel(const float* __restrict__ a, const float* __restrict__ b, int N,
-                                                          int C, float scale, float* __restrict__ out) {
-  __shared__ float part[8][33];
-  const int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
+// Column sums of two differences in one launch: out1[c] += scale * sum_n (a1 - b1)[n,c] over C1 columns and the same for
+// (a2, b2, C2, out2); outputs must be zeroed first. The 328-row batches of the reference leave this latency-bound (bytes
+// in flight, not bandwidth), so the CTA is narrow and tall: 256 threads = 8 columns x 32 row lanes (rows lane, lane + 32,
+// ...; four independent partial sums per thread), lanes summed in order through shared memory; grid (ceil(C1/8) +
+// ceil(C2/8), row chunks) — with one row chunk the result is deterministic (one atomicAdd onto 0 per column).
+__global__ void __launch_bounds__(256) colsum_diff2_kernel(const float* __restrict__ a1, const float* __restrict__ b1, int C1,
+                                                           float* __restrict__ out1, const float* __restrict__ a2,
+                                                           const float* __restrict__ b2, int C2, float* __restrict__ out2,
+                                                           int N, float scale) {
+  __shared__ float part[32][9];
+  const int blocks1 = (C1 + 7) / 8;
+  const bool second = (int)blockIdx.x >= blocks1;
+  const float* __restrict__ a = second ? a2 : a1;
+  const float* __restrict__ b = second ? b2 : b1;
+  float* __restrict__ out = second ? out2 : out1;
+  const int C = second ? C2 : C1;
+  const int cl = threadIdx.x & 7, lane = threadIdx.x >> 3;
+  const int c = ((int)blockIdx.x - (second ? blocks1 : 0)) * 8 + cl;
   const int rows_per = (N + gridDim.y - 1) / gridDim.y;
   const int r0 = blockIdx.y * rows_per, r1 = min(N, r0 + rows_per);
-  float s = 0.0f;
-  if (c < C)
-    for (int n = r0 + lane; n < r1; n += 8) s += __ldg(a + (size_t)n * C + c) - __ldg(b + (size_t)n * C + c);
-  part[lane][cl] = s;
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+  if (c < C) {
+    int n = r0 + lane;
+    for (; n + 96 < r1; n += 128) {
+      s0 += __ldg(a + (size_t)n * C + c) - __ldg(b + (size_t)n * C + c);
+      s1 += __ldg(a + (size_t)(n + 32) * C + c) - __ldg(b + (size_t)(n + 32) * C + c);
+      s2 += __ldg(a + (size_t)(n + 64) * C + c) - __ldg(b + (size_t)(n + 64) * C + c);
+      s3 += __ldg(a + (size_t)(n + 96) * C + c) - __ldg(b + (size_t)(n + 96) * C + c);
+    }
+    for (; n < r1; n += 32) s0 += __ldg(a + (size_t)n * C + c) - __ldg(b + (size_t)n * C + c);
+  }
+  part[lane][cl] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (lane == 0 && c < C) {
     float t = part[0][cl];
 #pragma unroll
-    for (int q = 1; q < 8; ++q) t += part[q][cl];
+    for (int q = 1; q < 32; ++q) t += part[q][cl];
     atomicAdd(out + c, scale * t);
   }
 }
@@ -311,11 +343,17 @@ inline int ew_grid(size_t n, int num_sms) {
 }  // namespace
 
 int launch_layer_forward(db_handle_t h, cudaStream_t st, const LayerFwdParams& p, int transW) {
-  dim3 grid((p.N + TileSmall::BN - 1) / TileSmall::BN, (p.M + TileSmall::BM - 1) / TileSmall::BM);
+  // (128 x 64 tiles with 8 x 4 micro-tiles measured SLOWER at the reference's sizes, 328 x 1024 x 500: 31.8 vs 24.1 us per
+  // launch — fewer, fatter CTAs, and the kernel is latency- not FMA-bound)
+  using T = TileSmall;
+  dim3 grid((p.N + T::BN - 1) / T::BN, (p.M + T::BM - 1) / T::BM);
   const int splits = simt_splits((long)grid.x * grid.y, p.K, h->num_sms);
   grid.z = splits;
-  if (transW) simt_launch_split(layer_forward_kernel<true>, grid, 256, st, p, splits);
-  else simt_launch_split(layer_forward_kernel<false>, grid, 256, st, p, splits);
+  const ALoadLayer a{p.A, p.lda, p.a_div, p.a_div_mode, p.M, p.K};
+  const bool vec = a.vec_ok() && BLoadW<false>{p.W, p.ldw, p.K, p.N}.vec_ok();
+  auto kernel = transW ? (vec ? layer_forward_kernel<true, T, true> : layer_forward_kernel<true, T, false>)
+                       : (vec ? layer_forward_kernel<false, T, true> : layer_forward_kernel<false, T, false>);
+  simt_launch_split(kernel, grid, 256, st, p, splits);
   return check_launch(h, "layer_forward");
 }
 
@@ -404,7 +442,11 @@ static int cd_gradients_impl(db_handle_t h, cudaStream_t st, int layer_kind, con
   }
   const int row_chunks = N >= 8192 ? 8 : 1;
   cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)(V + H), st);
-  colsum_diff_kernel<<<dim3((V + 31) / 32, row_chunks), 256, 0, st>>>(v0, vk, N, V, -inv_global_n, gb);
+  auto colsums = [&](bool visible, bool hidden) {      // db = -inv_n sum (v0 - vk), dc = -inv_n sum (q0 - qk)
+    const int bv = visible ? (V + 7) / 8 : 0, bh = hidden ? (H + 7) / 8 : 0;
+    colsum_diff2_kernel<<<dim3(bv + bh, row_chunks), 256, 0, st>>>(v0, vk, visible ? V : 0, gb, q0, qk, hidden ? H : 0, gc, N,
+                                                                 -inv_global_n);
+  };
   if (!hp0) {
     float* w0 = workspace; float* wk = workspace + (size_t)N * H;
     for (int side = 0; side < 2; ++side) {
@@ -419,18 +461,21 @@ static int cd_gradients_impl(db_handle_t h, cudaStream_t st, int layer_kind, con
     q0 = w0; qk = wk;
     if (gh) {
       // bias sums need x0 - xk, i.e. before c / sigma is added (the shift cancels in the difference anyway)
-      colsum_diff_kernel<<<dim3((H + 31) / 32, row_chunks), 256, 0, st>>>(q0, qk, N, H, -inv_global_n, gc);
+      colsums(true, true);
       const size_t nh = (size_t)N * H;
       cd_hidden_term_kernel<<<ew_grid(nh, h->num_sms), 256, 0, st>>>(1, w0, N, H, c, sigma);
       cd_hidden_term_kernel<<<ew_grid(nh, h->num_sms), 256, 0, st>>>(1, wk, N, H, c, sigma);
     }
   }
-  if (!gh) colsum_diff_kernel<<<dim3((H + 31) / 32, row_chunks), 256, 0, st>>>(q0, qk, N, H, -inv_global_n, gc);
+  if (!gh) colsums(true, true);
   {
-    dim3 g((H + TileSmall::BN - 1) / TileSmall::BN, (V + TileSmall::BM - 1) / TileSmall::BM);
+    using T = TileSmall;
+    dim3 g((H + T::BN - 1) / T::BN, (V + T::BM - 1) / T::BM);
     const int splits = simt_splits((long)g.x * g.y, 2 * N, h->num_sms);
     g.z = splits;
-    simt_launch_split(cd_dw_kernel, g, 256, st, v0, vk, q0, qk, N, V, H, -inv_global_n, gW, splits);
+    const bool vec = ALoadVT{v0, vk, N, V}.vec_ok() && BLoadQ{q0, qk, N, H}.vec_ok();
+    simt_launch_split(vec ? cd_dw_kernel<T, true> : cd_dw_kernel<T, false>, g, 256, st, v0, vk, q0, qk, N, V, H,
+                      -inv_global_n, gW, splits);
   }
   if (gh) cd_gaussian_hidden_grads_kernel<<<(H + 255) / 256, 256, 0, st>>>(H, c, opt_sigma, gc, gsig);
   return check_launch(h, "cd_gradients");
