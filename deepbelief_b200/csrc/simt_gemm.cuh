@@ -295,6 +295,8 @@ inline cudaError_t simt_launch_split(void (*kernel)(KArgs...), dim3 grid, int th
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// small layers / ragged shapes: more CTAs. (Measured and dropped for the RBM kernels at 328 x 1024 x 500: 32-column
+// k-blocks, 23.2 vs 21.9 us per forward launch and 47 vs 32 us for dW; 128 x 64 tiles with 8 x 4 micro-tiles, 31.8 us.)
 using TileSmall = SimtTile<64, 64, 16, 4, 4>;
 using TileMid = SimtTile<128, 64, 16, 8, 4>;      // RBM layers with >= 65 rows: 32 FMAs per 3 shared-memory loads     // small layers / ragged shapes: more CTAs
 using TileLarge = SimtTile<128, 128, 8, 8, 8>;    // GP chain at N ~ 5000

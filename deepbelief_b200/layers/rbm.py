@@ -161,20 +161,29 @@ class CdGraphStep:
                 r.draw = d0
             optimizer.step_count = snap[5]
         restore()
-        torch.cuda.current_stream().synchronize()
         self.graph = torch.cuda.CUDAGraph()
+        # capture_begin / capture_end on a side stream rather than the torch.cuda.graph context manager: that one runs
+        # gc.collect() and empties the allocator cache first, 20-230 ms here against 0.1 ms per replayed iteration
+        main = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(main)
         try:
             for r, c in zip(self.rngs, self.clocks):
                 r.clock = c
             optimizer.clock = self.clocks[0]
-            with torch.cuda.graph(self.graph):
-                iteration()
-                for c, n in zip(self.clocks, self.draws):
-                    ops.clock_advance(c, n, 1)
+            with torch.cuda.stream(side):
+                self.graph.capture_begin()
+                try:
+                    iteration()
+                    for c, n in zip(self.clocks, self.draws):
+                        ops.clock_advance(c, n, 1)
+                finally:
+                    self.graph.capture_end()
         finally:
             for r in self.rngs:
                 r.clock = None
             optimizer.clock = None
+        main.wait_stream(side)
         restore()                                                    # capture executed nothing; host counters rewound
         self.base_draw, self.base_step = list(snap[4]), snap[5]       # what clock == 0 stands for
         self.synced = (list(snap[4]), snap[5])                       # host counters the device clocks currently match
@@ -494,9 +503,14 @@ class RBM(layer.Layer):
         return test_loss
 
     # ---- training ----------------------------------------------------------------------------------------------------------
+    # rows x V x H below which the general path (cluster split-K SIMT kernels replayed as one CUDA graph) beats the
+    # tensor-core chain, whose ~2k+3 launches cost ~30 us each however small the layer (scripts/probe_tc_crossover.py)
+    TC_MIN_WORK = 250_000_000
+
     def _tc_eligible(self, n_rows):
         return (self.layer_kind == L.LAYER_RBM and self.temperature is None and n_rows % 8 == 0 and
-                self.num_v % 8 == 0 and self.num_h % 8 == 0 and n_rows >= 8)
+                self.num_v % 8 == 0 and self.num_h % 8 == 0 and n_rows >= 8 and
+                n_rows * self.num_v * self.num_h >= self.TC_MIN_WORK)
 
     def cd_step(self, v_0_batch, k=1, persistent=None, *, grad=None, n_global=None, injected=None, force_simt=False):
         """Positive phase + k Gibbs steps + packed CD gradient for one (local) batch; returns
@@ -546,7 +560,7 @@ class RBM(layer.Layer):
     # train(): iterations of the general path whose per-layer work (rows x V x H) is below this are launch-bound and run
     # as one captured CUDA graph (CdGraphStep) once the loop is at least GRAPH_MIN_ITERATIONS long
     GRAPH_MAX_WORK = 1 << 31
-    GRAPH_MIN_ITERATIONS = 8
+    GRAPH_MIN_ITERATIONS = 64
 
     # SMs left to the NCCL kernels while a dW chunk is computed next to an in-flight all-reduce (the persistent
     # tcgen05 GEMM otherwise occupies every SM and the collective could not start until it has finished)

@@ -467,6 +467,7 @@ def test_training_iteration_as_cuda_graph_is_bit_identical(horses, monkeypatch, 
 
     def run(graph):
         monkeypatch.setenv('DEEPBELIEF_B200_GRAPH', '1' if graph else '0')
+        monkeypatch.setattr(RBM, 'GRAPH_MIN_ITERATIONS', 8)          # the loops here are 17 iterations long
         np.random.seed(0)                           # Data reshuffles with the global numpy stream on every epoch wrap
         rs2 = np.random.RandomState(11)
         kw = {}
