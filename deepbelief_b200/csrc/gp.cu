@@ -1074,6 +1074,36 @@ __global__ void __launch_bounds__(256) gp_grad_kernel(const float* __restrict__ 
   gp_contract_tile<T>(gacc, m0, n0, diag_tile, X, N, Q, hyp, dXacc, accum, rowacc, colacc, red);
 }
 
+// Small N (the reference's N = 328: a 3 x 3 grid of 128-row tiles, six useful CTAs walking K = N + D serially, 236 us):
+// G = (D/2) Linv^T Linv - (1/2) A A^T is formed by 64 x 64 tiles whose K ranges are split over a thread-block cluster
+// (simt_gemm.cuh) and written to memory (lower tiles); gp_contract_mem_kernel then contracts it with K_f.
+__global__ void __launch_bounds__(256) gp_g_split_kernel(const float* __restrict__ Li, int ldi, const float* __restrict__ Av, int lda,
+                                                         int N, int D, float* __restrict__ G, int splits) {
+  using T = TileSmall;
+  if (blockIdx.x > blockIdx.y) return;      // the CTAs of a cluster share (x, y): they leave together
+  __shared__ typename T::Smem sm;
+  __shared__ __align__(16) float red[T::BM * T::BN];
+  const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
+  float acc[T::TM][T::TN];
+  int kb, ke;
+  {
+    simt_split_range<T>(N - m0, splits, kb, ke);          // Linv[k,i] = 0 for k < i and i >= m0
+    LoadLinvT_A a{Li, ldi, N, 0.5f * (float)D};
+    LoadLinvT_B b{Li, ldi, N};
+    simt_gemm_tile<T>(sm, a, b, m0, n0, m0 + kb, m0 + ke, acc);
+  }
+  __syncthreads();
+  {
+    simt_split_range<T>(D, splits, kb, ke);
+    LoadA_A a{Av, lda, N, D};
+    LoadA_B b{Av, lda, N, D};
+    simt_gemm_tile<T, LoadA_A, LoadA_B, false>(sm, a, b, m0, n0, kb, ke, acc);
+  }
+  simt_cluster_reduce<T>(red, acc, splits, [&](int r, int c, float x) {
+    if (m0 + r < N && n0 + c < N) G[(size_t)(m0 + r) * N + n0 + c] = x;
+  });
+}
+
 // scalars + prior term of dX
 __global__ void gp_finalize_kernel(const GpAccum* __restrict__ acc, const float* __restrict__ hyp, const float* __restrict__ opt,
                                    int flags, int N, int Q, int D, float x_prior_w, int include_const, int want_grad,
@@ -1323,7 +1353,8 @@ int run_trinv_tc(db_handle_t h, cudaStream_t st, float* L, const float* Llo, int
 template <int TRANS>
 int run_trmm(db_handle_t h, cudaStream_t st, const float* Li, int N, const float* B, int ldb, int nrhs, float* out, int ldo,
              float* ssq) {
-  if (nrhs >= 256) {
+  // 128 x 128 tiles only when they fill the SMs (N = 328, D = 1024 is 24 of them: 62 us per product)
+  if (nrhs >= 256 && ((nrhs + 127) / 128) * ((N + 127) / 128) >= h->num_sms) {
     using T = TileLarge;
     dim3 grid((nrhs + T::BN - 1) / T::BN, (N + T::BM - 1) / T::BM);
     trmm_kernel<TRANS, T><<<grid, 256, 0, st>>>(Li, N, N, B, ldb, nrhs, out, ldo, ssq);
@@ -1443,7 +1474,8 @@ __global__ void __launch_bounds__(256) dot_sum_kernel(const float* __restrict__ 
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
 }
-// G tile = (D/2) Kinv + AA (AA = -0.5 A A^T, lower part valid) read from memory, contracted with K_f
+// G tile = (D/2) Kinv + AA (AA = -0.5 A A^T, lower part valid; Kinv == nullptr: AA is G already) read from memory,
+// contracted with K_f
 __global__ void __launch_bounds__(256) gp_contract_mem_kernel(const float* __restrict__ Kinv, const float* __restrict__ AA, int N, int Q,
                                                               int D, const float* __restrict__ X, const float* __restrict__ hyp,
                                                               float* __restrict__ dXacc, GpAccum* accum) {
@@ -1463,7 +1495,12 @@ __global__ void __launch_bounds__(256) gp_contract_mem_kernel(const float* __res
 #pragma unroll
     for (int jj = 0; jj < T::TN; ++jj) {
       const int n = simt_col<T>(n0, jj);
-      gacc[i][jj] = (m < N && n < N && n <= m) ? fmaf(half_d, __ldg(Kinv + (size_t)m * N + n), __ldg(AA + (size_t)m * N + n)) : 0.0f;
+      float g = 0.0f;
+      if (m < N && n < N && n <= m) {
+        g = __ldg(AA + (size_t)m * N + n);
+        if (Kinv != nullptr) g = fmaf(half_d, __ldg(Kinv + (size_t)m * N + n), g);
+      }
+      gacc[i][jj] = g;
     }
   }
   __syncthreads();
@@ -1821,7 +1858,15 @@ extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float*
     if ((rc = run_trmm<1>(h, st, w.Li, N, w.S, D, D, w.Av, D, nullptr))) return rc;
     cudaMemsetAsync(w.dXacc, 0, sizeof(float) * (size_t)N * Q, st);
     const int tiles = (N + TileLarge::BM - 1) / TileLarge::BM;
-    gp_grad_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(w.Li, N, w.Av, D, X, N, Q, D, w.hyp, w.dXacc, w.acc);
+    const int tiles_s = (N + TileSmall::BM - 1) / TileSmall::BM;
+    const int splits = simt_splits((long)tiles_s * (tiles_s + 1) / 2, D + N / 2, h->num_sms);
+    if (splits > 1) {      // few tiles: cluster split-K into w.Tmp (free once Linv is formed), then the contraction from memory
+      simt_launch_split(gp_g_split_kernel, dim3(tiles_s, tiles_s, splits), 256, st, (const float*)w.Li, N, (const float*)w.Av, D, N, D,
+                        w.Tmp, splits);
+      gp_contract_mem_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(nullptr, w.Tmp, N, Q, D, X, w.hyp, w.dXacc, w.acc);
+    } else {
+      gp_grad_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(w.Li, N, w.Av, D, X, N, Q, D, w.hyp, w.dXacc, w.acc);
+    }
   }
   }
   gp_finalize_kernel<<<(N * Q + 255) / 256, 256, 0, st>>>(w.acc, w.hyp, hyp_opt, flags, N, Q, D, x_prior_weight, include_const,

@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from deepbelief_b200 import ops
-N, D, Q = 5000, 784, 2
+N, D, Q = (int(sys.argv[1]) if len(sys.argv) > 1 else 5000), (int(sys.argv[2]) if len(sys.argv) > 2 else 784), 2
 X = torch.randn(N, Q, device='cuda'); Y = torch.randn(N, D, device='cuda')
 hyp_opt = torch.tensor([0.5413, 0.5413, 0.5413], device='cuda')
 plan = ops.GplvmPlan(N, Q, D)
