@@ -783,9 +783,13 @@ __global__ void __launch_bounds__(256) trsm_update_kernel(const float* __restric
 }
 
 // ---- triangular inverse ---------------------------------------------------------------------------
-// level 0: invert every 64x64 diagonal block (one CTA each; thread c solves column c of L_bb X = I)
+// level 0: invert every 64x64 diagonal block (one CTA each; thread c solves column c of L_bb X = I by forward
+// substitution). The solution lives in shared memory (a register array indexed by the row went to local memory: 44 us per
+// launch) and every thread walks the same (r, k) range — entries above the diagonal are exact zeros, so the extra terms
+// change nothing — with the dot product unrolled by eight over four accumulators.
 __global__ void __launch_bounds__(64) trinv_diag_kernel(const float* __restrict__ L, int ldl, int N, float* __restrict__ Li, int ldi) {
   __shared__ float D[NB][NB + 1];
+  __shared__ float Xs[NB][NB + 1];      // Xs[r][c] = X[r, c]
   const int i0 = blockIdx.x * NB;
   const int nb = min(NB, N - i0);
   for (int t = threadIdx.x; t < NB * NB; t += 64) {
@@ -794,15 +798,17 @@ __global__ void __launch_bounds__(64) trinv_diag_kernel(const float* __restrict_
   }
   __syncthreads();
   const int c = threadIdx.x;
-  if (c >= nb) return;
-  float x[NB];
-#pragma unroll 1
-  for (int r = c; r < nb; ++r) {
-    float s = (r == c) ? 1.0f : 0.0f;
-    for (int k = c; k < r; ++k) s = fmaf(-D[r][k], x[k], s);
-    x[r] = s / D[r][r];
+  for (int r = 0; r < NB; ++r) Xs[r][c] = 0.0f;          // rows not solved yet read as zero: the k loop needs no tail
+  for (int r = 0; r < nb; ++r) {
+    float s[4] = {(r == c) ? 1.0f : 0.0f, 0.0f, 0.0f, 0.0f};
+    for (int k = 0; k < r; k += 8) {                      // k .. k+7 <= 63; D[r][k > r] = 0 and Xs[k >= r][c] = 0
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s[u & 3] = fmaf(-D[r][k + u], Xs[k + u][c], s[u & 3]);
+    }
+    const float x = ((s[0] + s[1]) + (s[2] + s[3])) / D[r][r];
+    Xs[r][c] = x;                        // only this thread reads column c again
+    if (c <= r) Li[(size_t)(i0 + r) * ldi + i0 + c] = x;
   }
-  for (int r = c; r < nb; ++r) Li[(size_t)(i0 + r) * ldi + i0 + c] = x[r];
 }
 // level with half-size s: for pair p, rows R = [(2p+1)s, min(N,(2p+2)s)), cols C = [2ps, (2p+1)s):
 //   T = L[R, C] * Linv[C, C]          (Linv[C,C] lower triangular: k >= column)
@@ -1476,10 +1482,10 @@ __global__ void __launch_bounds__(256) dot_sum_kernel(const float* __restrict__ 
 }
 // G tile = (D/2) Kinv + AA (AA = -0.5 A A^T, lower part valid; Kinv == nullptr: AA is G already) read from memory,
 // contracted with K_f
+template <class T>
 __global__ void __launch_bounds__(256) gp_contract_mem_kernel(const float* __restrict__ Kinv, const float* __restrict__ AA, int N, int Q,
                                                               int D, const float* __restrict__ X, const float* __restrict__ hyp,
                                                               float* __restrict__ dXacc, GpAccum* accum) {
-  using T = TileLarge;
   if (blockIdx.x > blockIdx.y) return;
   __shared__ float rowacc[T::BM][MAXQ];
   __shared__ float colacc[T::BN][MAXQ];
@@ -1848,7 +1854,7 @@ extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float*
       if (trc) return set_err(h, DB_ERR_CUDA, "tf32 A A^T product failed (%d)", trc);
       cudaMemsetAsync(w.dXacc, 0, sizeof(float) * (size_t)N * Q, st);
       const int tiles = (N + TileLarge::BM - 1) / TileLarge::BM;
-      gp_contract_mem_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(w.Li, w.Tmp, N, Q, D, X, w.hyp, w.dXacc, w.acc);
+      gp_contract_mem_kernel<TileLarge><<<dim3(tiles, tiles), 256, 0, st>>>(w.Li, w.Tmp, N, Q, D, X, w.hyp, w.dXacc, w.acc);
       dot_sum_kernel<<<h->num_sms * 8, 256, 0, st>>>(w.Av, w.Av, nd, frob + 1);   // |A|_F^2
       gp_fix_trace_kernel<<<1, 1, 0, st>>>(w.acc, frob, w.hyp, D);
     }
@@ -1863,7 +1869,7 @@ extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float*
     if (splits > 1) {      // few tiles: cluster split-K into w.Tmp (free once Linv is formed), then the contraction from memory
       simt_launch_split(gp_g_split_kernel, dim3(tiles_s, tiles_s, splits), 256, st, (const float*)w.Li, N, (const float*)w.Av, D, N, D,
                         w.Tmp, splits);
-      gp_contract_mem_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(nullptr, w.Tmp, N, Q, D, X, w.hyp, w.dXacc, w.acc);
+      gp_contract_mem_kernel<TileSmall><<<dim3(tiles_s, tiles_s), 256, 0, st>>>(nullptr, w.Tmp, N, Q, D, X, w.hyp, w.dXacc, w.acc);
     } else {
       gp_grad_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(w.Li, N, w.Av, D, X, N, Q, D, w.hyp, w.dXacc, w.acc);
     }
