@@ -16,6 +16,16 @@ struct GemmLoadA {   // a(m,k) of op(A): A is [M,K] (TRANS=0) or [K,M] (TRANS=1)
     if (m >= M || k >= K) return 0.0f;
     return TRANS ? __ldg(A + (size_t)k * lda + m) : __ldg(A + (size_t)m * lda + k);
   }
+  __host__ __device__ bool vec_ok() const { return lda % 4 == 0 && aligned16(A); }
+  __device__ __forceinline__ float4 load4(int m, int k) const {     // TRANS: m .. m+3 of row k; else k .. k+3 of row m
+    if (m >= M || k >= K) return make_float4(0.f, 0.f, 0.f, 0.f);
+    if (TRANS) {
+      if (m + 3 >= M) return make_float4((*this)(m, k), (*this)(m + 1, k), (*this)(m + 2, k), (*this)(m + 3, k));
+      return __ldg(reinterpret_cast<const float4*>(A + (size_t)k * lda + m));
+    }
+    if (k + 3 >= K) return make_float4((*this)(m, k), (*this)(m, k + 1), (*this)(m, k + 2), (*this)(m, k + 3));
+    return __ldg(reinterpret_cast<const float4*>(A + (size_t)m * lda + k));
+  }
 };
 template <bool TRANS>
 struct GemmLoadB {   // b(k,n) of op(B): B is [K,N] (TRANS=0) or [N,K] (TRANS=1)
@@ -24,6 +34,16 @@ struct GemmLoadB {   // b(k,n) of op(B): B is [K,N] (TRANS=0) or [N,K] (TRANS=1)
   __device__ __forceinline__ float operator()(int k, int n) const {
     if (k >= K || n >= N) return 0.0f;
     return TRANS ? __ldg(B + (size_t)n * ldb + k) : __ldg(B + (size_t)k * ldb + n);
+  }
+  __host__ __device__ bool vec_ok() const { return ldb % 4 == 0 && aligned16(B); }
+  __device__ __forceinline__ float4 load4(int k, int n) const {     // TRANS: k .. k+3 of column n; else n .. n+3 of row k
+    if (k >= K || n >= N) return make_float4(0.f, 0.f, 0.f, 0.f);
+    if (TRANS) {
+      if (k + 3 >= K) return make_float4((*this)(k, n), (*this)(k + 1, n), (*this)(k + 2, n), (*this)(k + 3, n));
+      return __ldg(reinterpret_cast<const float4*>(B + (size_t)n * ldb + k));
+    }
+    if (n + 3 >= N) return make_float4((*this)(k, n), (*this)(k, n + 1), (*this)(k, n + 2), (*this)(k, n + 3));
+    return __ldg(reinterpret_cast<const float4*>(B + (size_t)k * ldb + n));
   }
 };
 
@@ -56,6 +76,33 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
     }
   }
 }
+// 64 x 64 tiles, K split over a thread-block cluster (1,1,splits) and reduced through distributed shared memory in rank
+// order (simt_gemm.cuh): deterministic, beta applied in the epilogue. The backward products of the horses-sized stacks have
+// one to eight output tiles and K = 100-328 — every k-block is a dependent round trip to memory, 17-34 us per launch.
+template <bool TA, bool TB, bool VEC>
+__global__ void __launch_bounds__(256) gemm_f32_cluster_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B,
+                                                               int ldb, float* __restrict__ C, int ldc, int M, int N, int K,
+                                                               float alpha, float beta, int splits) {
+  using T = TileSmall;
+  __shared__ typename T::Smem sm;
+  __shared__ __align__(16) float red[T::BM * T::BN];
+  const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
+  GemmLoadA<TA> a{A, lda, M, K};
+  GemmLoadB<TB> b{B, ldb, K, N};
+  float acc[T::TM][T::TN];
+  int kb, ke;
+  simt_split_range<T>(K, splits, kb, ke);
+  if (VEC) simt_gemm_tile_vec<T>(sm, a, b, m0, n0, kb, ke, acc);
+  else simt_gemm_tile<T>(sm, a, b, m0, n0, kb, ke, acc);
+  simt_cluster_reduce<T>(red, acc, splits, [&](int r, int c, float x) {
+    const int m = m0 + r, n = n0 + c;
+    if (m < M && n < N) {
+      float* cp = C + (size_t)m * ldc + n;
+      *cp = beta != 0.0f ? fmaf(beta, *cp, alpha * x) : alpha * x;
+    }
+  });
+}
+
 static __global__ void gemm_scale_c_kernel(float* __restrict__ C, int ldc, int M, int N, float beta) {
   const size_t total = (size_t)M * N;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -87,6 +134,13 @@ inline void launch_gemm_f32(cudaStream_t st, int num_sms, const float* A, int ld
     const int blocks = (int)((total + 255) / 256 < (size_t)num_sms * 8 ? (total + 255) / 256 : (size_t)num_sms * 8);
     gemm_scale_c_kernel<<<blocks, 256, 0, st>>>(C, ldc, M, N, beta);
     grid.z = splits;
+  } else if (T::BM == TileSmall::BM && T::BN == TileSmall::BN && T::BK == TileSmall::BK) {
+    const int cs = simt_splits(tiles, K, num_sms, 32);
+    const bool vec = GemmLoadA<TA>{A, lda, M, K}.vec_ok() && GemmLoadB<TB>{B, ldb, K, N}.vec_ok();
+    grid.z = cs;
+    simt_launch_split(vec ? gemm_f32_cluster_kernel<TA, TB, true> : gemm_f32_cluster_kernel<TA, TB, false>, grid, 256, st, A, lda, B,
+                      ldb, C, ldc, M, N, K, alpha, beta, cs);
+    return;
   }
   gemm_f32_kernel<T, TA, TB><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, alpha, beta, k_per);
 }

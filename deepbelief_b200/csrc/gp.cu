@@ -1544,6 +1544,26 @@ __global__ void __launch_bounds__(256) kinv_kernel(const float* __restrict__ Li,
   }
 }
 
+// small N: the same product on 64 x 64 lower tiles whose K range [m0, N) is split over a thread-block cluster
+__global__ void __launch_bounds__(256) kinv_split_kernel(const float* __restrict__ Li, int ldi, int N, float* __restrict__ Kinv,
+                                                         int splits) {
+  using T = TileSmall;
+  if (blockIdx.x > blockIdx.y) return;      // the CTAs of a cluster share (x, y)
+  __shared__ typename T::Smem sm;
+  __shared__ __align__(16) float red[T::BM * T::BN];
+  const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
+  LoadLinvT_A a{Li, ldi, N, 1.0f};
+  LoadLinvT_B b{Li, ldi, N};
+  float acc[T::TM][T::TN];
+  int kb, ke;
+  simt_split_range<T>(N - m0, splits, kb, ke);
+  simt_gemm_tile<T>(sm, a, b, m0, n0, m0 + kb, m0 + ke, acc);
+  simt_cluster_reduce<T>(red, acc, splits, [&](int r, int c, float x) {
+    const int m = m0 + r, n = n0 + c;
+    if (m < N && n < N) { Kinv[(size_t)m * N + n] = x; Kinv[(size_t)n * N + m] = x; }
+  });
+}
+
 __global__ void gpdbn_pred_var_kernel(const float* __restrict__ Kinv, int N, const float* __restrict__ hyp, float* __restrict__ pv,
                                       int* __restrict__ info) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1664,6 +1684,39 @@ __global__ void __launch_bounds__(256) gpdbn_grad_kernel(const float* __restrict
     }
   }
   gp_contract_tile<T>(gacc, m0, n0, diag_tile, X, N, Q, hyp, dXacc, accum, rowacc, colacc, red);
+}
+
+// small N: G = s^2 Kinv diag(g_pv) Kinv + (E B^T + B E^T)/2-type product + (D/2) Kinv formed by 64 x 64 lower tiles with a
+// cluster-split K and written to memory; gp_contract_mem_kernel<TileSmall>(nullptr, G, ...) contracts it
+__global__ void __launch_bounds__(256) gpdbn_g_split_kernel(const float* __restrict__ Kinv, const float* __restrict__ gpv,
+                                                            const float* __restrict__ P, const float* __restrict__ B, int N, int D,
+                                                            const float* __restrict__ hyp, float* __restrict__ G, int splits) {
+  using T = TileSmall;
+  if (blockIdx.x > blockIdx.y) return;
+  __shared__ typename T::Smem sm;
+  __shared__ __align__(16) float red[T::BM * T::BN];
+  const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
+  const float s = __ldg(hyp + 2);
+  float gacc[T::TM][T::TN];
+  int kb, ke;
+  {
+    simt_split_range<T>(N, splits, kb, ke);
+    LoadKinvScaledA a{Kinv, gpv, N, s * s};
+    LoadKinvB b{Kinv, N};
+    simt_gemm_tile<T>(sm, a, b, m0, n0, kb, ke, gacc);
+  }
+  __syncthreads();
+  {
+    simt_split_range<T>(2 * D, splits, kb, ke);
+    LoadEB_A a{P, B, N, D, s};
+    LoadEB_B b{P, B, N, D, s};
+    simt_gemm_tile<T, LoadEB_A, LoadEB_B, false>(sm, a, b, m0, n0, kb, ke, gacc);
+  }
+  const float half_d = 0.5f * (float)D;
+  simt_cluster_reduce<T>(red, gacc, splits, [&](int r, int c, float x) {
+    const int m = m0 + r, n = n0 + c;
+    if (m < N && n < N) G[(size_t)m * N + n] = fmaf(half_d, __ldg(Kinv + (size_t)m * N + n), x);
+  });
 }
 // Tensor-core form of the same gradient: Xs = s^2 K^-1 diag(g_pv) (and its tf32 remainder) is materialised, G1 = Xs K^-1
 // runs as one 3xTF32 GEMM (lower part), and the contraction kernel reads the G1 tile from memory instead of forming it.
@@ -1933,7 +1986,10 @@ extern "C" int db_gpdbn_factor(db_handle_t h, db_stream_t stream, const float* X
   } else {
     if ((rc = run_trinv(h, st, w.K, N, N, w.Li, w.Kinv))) return rc;
     const int tiles = (N + TileLarge::BM - 1) / TileLarge::BM;
-    kinv_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(w.Li, N, N, w.Kinv);
+    const int tiles_s = (N + TileSmall::BM - 1) / TileSmall::BM;
+    const int splits = simt_splits((long)tiles_s * (tiles_s + 1) / 2, N, h->num_sms);
+    if (splits > 1) simt_launch_split(kinv_split_kernel, dim3(tiles_s, tiles_s, splits), 256, st, (const float*)w.Li, N, N, w.Kinv, splits);
+    else kinv_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(w.Li, N, N, w.Kinv);
   }
   gpdbn_pred_var_kernel<<<(N + 255) / 256, 256, 0, st>>>(w.Kinv, N, w.hyp, pred_var, info);
   return check_launch(h, "gpdbn_factor");
@@ -1990,7 +2046,17 @@ extern "C" int db_gpdbn_backward_x(db_handle_t h, db_stream_t stream, const floa
       done = true;
     }
   }
-  if (!done) gpdbn_grad_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(w.Kinv, g_pv, w.P, w.B, X, N, Q, D, w.hyp, w.dXacc, w.acc);
+  if (!done) {
+    const int tiles_s = (N + TileSmall::BM - 1) / TileSmall::BM;
+    const int splits = simt_splits((long)tiles_s * (tiles_s + 1) / 2, N + 2 * D, h->num_sms);
+    if (splits > 1) {       // few tiles (the horses runs, N = 328): cluster split-K into w.Ulo, contraction from memory
+      simt_launch_split(gpdbn_g_split_kernel, dim3(tiles_s, tiles_s, splits), 256, st, (const float*)w.Kinv, g_pv, (const float*)w.P,
+                        (const float*)w.B, N, D, (const float*)w.hyp, w.Ulo, splits);
+      gp_contract_mem_kernel<TileSmall><<<dim3(tiles_s, tiles_s), 256, 0, st>>>(nullptr, w.Ulo, N, Q, D, X, w.hyp, w.dXacc, w.acc);
+    } else {
+      gpdbn_grad_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(w.Kinv, g_pv, w.P, w.B, X, N, Q, D, w.hyp, w.dXacc, w.acc);
+    }
+  }
   gpdbn_finalize_kernel<<<(N * Q + 255) / 256, 256, 0, st>>>(w.acc, w.hyp, hyp_opt, flags, N, Q, x_prior_weight, X, w.dXacc, dX,
                                                             dhyp);
   return check_launch(h, "gpdbn_backward_x");

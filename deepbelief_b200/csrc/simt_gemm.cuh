@@ -228,10 +228,10 @@ __device__ __forceinline__ int simt_col(int n0, int j) {
 // and after a cluster barrier CTA r sums rows [r BM/S, (r+1) BM/S) of the S partial tiles through distributed shared
 // memory — in rank order, so the result does not depend on scheduling — and runs the epilogue on them.
 
-// S in {1,2,4,8}: enough CTAs for two per SM, at least 64 columns of K each
-inline int simt_splits(long tiles, int K, int num_sms) {
+// S in {1,2,4,8}: enough CTAs for two per SM, at least min_k (64) columns of K each
+inline int simt_splits(long tiles, int K, int num_sms, int min_k = 64) {
   int s = 1;
-  while (s < 8 && tiles * s < 2L * num_sms && K / (2 * s) >= 64) s *= 2;
+  while (s < 8 && tiles * s < 2L * num_sms && K / (2 * s) >= min_k) s *= 2;
   return s;
 }
 // this CTA's K range [k_begin, k_end) of a K split S ways (multiples of BK)

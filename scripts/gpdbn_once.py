@@ -6,7 +6,7 @@ from deepbelief_b200 import compat
 from deepbelief_b200.layers.rbm import RBM
 from deepbelief_b200.layers.gprbm import GPRBM
 from deepbelief_b200.layers.gplvm import SEKernel
-N, D, Q = 5000, 784, 2
+N, D, Q = (int(sys.argv[1]) if len(sys.argv) > 1 else 5000), (int(sys.argv[2]) if len(sys.argv) > 2 else 784), 2    # `328 1024`: the gpdbn_horses sizes
 n_it = int(os.environ.get('N_IT', 1))
 dev = 'cuda:0'
 rs = np.random.RandomState(0)
