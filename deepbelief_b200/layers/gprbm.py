@@ -111,6 +111,8 @@ class GPRBM(bgrbm.BGRBM):
         pv = self._factor()
         return (self.alpha_h.reshape(1, self.D) * torch.sqrt(pv).reshape(self.N, 1)).contiguous()
 
+    INFO_INTERVAL = 32          # optimize(): iterations between reads of the factorisation status
+
     def _touch(self):
         self._version += 1
         self._weights_version += 1
@@ -152,7 +154,8 @@ class GPRBM(bgrbm.BGRBM):
                 self._Lfac = torch.zeros((self.N, self.N), dtype=torch.float32, device=self.device)
             self._plan.factor(self.X, self._hyp, self.flags, self.fixed_noise, self.noise_jitter or 0.0, L_out=self._Lfac)
             self._gp_version = self._version
-            self._check_info()
+            if not getattr(self, '_defer_info', False):
+                self._check_info()
         return self._plan.pred_var
 
     def _check_info(self):
@@ -437,11 +440,17 @@ class GPRBM(bgrbm.BGRBM):
         if eval_interval:
             self.eval_interval = eval_interval
             self._eval_step(i)
+        # The factorisation status (pivot / negative pred_var, what TF raises inside session.run) is a device-to-host read
+        # that would stall the launch queue once per iteration: inside the loop it is read every INFO_INTERVAL iterations
+        # and after the last one — a failure aborts the training a few iterations late, with the same error.
+        self._defer_info = True
         try:
             fixed = fixed_X_num_iterations or 0
             assert fixed <= num_iterations
             for i in range(1, num_iterations + 1):
                 step(fixed_X=i <= fixed)
+                if i % self.INFO_INTERVAL == 0:
+                    self._check_info()
                 if eval_interval and i % eval_interval == 0:
                     self._eval_step(i)
                 if ckpt_dir and ckpt_interval and i % ckpt_interval == 0:
@@ -454,6 +463,8 @@ class GPRBM(bgrbm.BGRBM):
             if ckpt_dir and ckpt_interval:
                 self.save_all(i, ckpt_dir)
                 self.kern.save(i, ckpt_dir)
+        finally:
+            self._defer_info = False
         self._check_info()
 
     # ---- test-time latent search (gprbm.py:468-562) ------------------------------------------------------------------
