@@ -23,6 +23,7 @@ import torch
 from .. import _lib as L
 from .. import compat, ops, preprocessing
 from . import bgrbm, gplvm
+from ..replay import ReplayedStep
 from .layer import to_device, to_numpy
 
 _FLAG_NOISE = 4
@@ -112,6 +113,7 @@ class GPRBM(bgrbm.BGRBM):
         return (self.alpha_h.reshape(1, self.D) * torch.sqrt(pv).reshape(self.N, 1)).contiguous()
 
     INFO_INTERVAL = 32          # optimize(): iterations between reads of the factorisation status
+    GRAPH_MIN_ITERATIONS = 64   # optimize(): shortest run of iterations worth a graph capture (~3 ms)
 
     def _touch(self):
         self._version += 1
@@ -447,8 +449,29 @@ class GPRBM(bgrbm.BGRBM):
         try:
             fixed = fixed_X_num_iterations or 0
             assert fixed <= num_iterations
+            # the horses-sized stacks are bound by the host (~80 launches of 5-30 us per iteration): once a mode (X fixed /
+            # free) has run eagerly it is captured and replayed as one CUDA graph (replay.ReplayedStep), bit-identical
+            use_graph = os.environ.get('DEEPBELIEF_B200_GRAPH', '1') != '0'
+            rngs = [l.rng for l in self.layers]
+            warmed, replayed = set(), {}
             for i in range(1, num_iterations + 1):
-                step(fixed_X=i <= fixed)
+                fx = i <= fixed
+                left = (fixed if fx else num_iterations) - i + 1          # iterations left in this mode
+                if use_graph and fx in warmed and fx not in replayed and left >= self.GRAPH_MIN_ITERATIONS:
+                    self._touch()                                         # the captured iteration must re-factorise
+                    try:
+                        replayed[fx] = ReplayedStep(lambda: step(fixed_X=fx), rngs, optimizer, self.device)
+                    except RuntimeError as e:
+                        self.logger.warning('CUDA-graph capture of the training iteration failed (%s); eager launches', e)
+                        use_graph = False
+                if fx in replayed:
+                    replayed[fx].run()
+                    for l in self.layers[1:]:
+                        l._weights_version += 1           # (their post-update launches are part of the graph)
+                    self._touch()
+                else:
+                    step(fixed_X=fx)
+                    warmed.add(fx)
                 if i % self.INFO_INTERVAL == 0:
                     self._check_info()
                 if eval_interval and i % eval_interval == 0:

@@ -373,3 +373,44 @@ def test_interp_test_vs_reference_and_oracle(gpdbn_golden):
     assert lin.shape == (6, V0) and geo.shape == (6, V0) and np.isfinite(geo).all()
     end = float(top.interp_objective(top.interp_latents, path0[0], path0[-1], lam)[0])
     assert end <= start + 1e-6
+
+
+@pytest.mark.parametrize('opt_name', ['adam', 'momentum'])
+def test_optimize_as_cuda_graph_matches_the_eager_loop(monkeypatch, opt_name):
+    """GPRBM.optimize replays one captured CUDA graph per iteration (replay.ReplayedStep: Philox draw ids and the optimizer
+    step number come from a device clock) once a mode has run eagerly — across the fixed-X / free-X switch and with
+    evaluation steps (which draw eagerly) in between. The host counters must end identical, and every trainable of the stack
+    must agree with the eager loop as closely as two eager runs agree with each other (the loss reductions use atomics, so
+    the eager loop itself repeats only to ~1e-6..1e-5 after 23 iterations; one wrong draw id would move parameters by
+    ~lr per iteration)."""
+    from deepbelief_b200 import compat as tf
+    from deepbelief_b200.layers.gprbm import GPRBM
+    from deepbelief_b200 import replay
+
+    def run(graph):
+        monkeypatch.setenv('DEEPBELIEF_B200_GRAPH', '1' if graph else '0')
+        monkeypatch.setattr(GPRBM, 'GRAPH_MIN_ITERATIONS', 4)
+        top, lower, _, _ = _config4_stack(192, seed=3)
+        opt = (tf.train.AdamOptimizer(learning_rate=2e-3) if opt_name == 'adam'
+               else tf.train.MomentumOptimizer(learning_rate=1e-4, momentum=0.9))
+        created = []
+        orig = replay.ReplayedStep.__init__
+
+        def spy(self, *a, **k):
+            created.append(1)
+            orig(self, *a, **k)
+        monkeypatch.setattr(replay.ReplayedStep, '__init__', spy)
+        top.optimize(opt, num_iterations=23, fixed_X_num_iterations=9, eval_interval=5)
+        monkeypatch.setattr(replay.ReplayedStep, '__init__', orig)
+        assert len(created) == (2 if graph else 0)                       # one graph per mode (X fixed / X free)
+        return [top._params.clone(), top.X.clone(), top._hyp.clone()] + [l._params.clone() for l in lower], \
+            [l.rng.draw for l in top.layers], opt.step_count
+
+    p_graph, d_graph, s_graph = run(True)
+    p_eager, d_eager, s_eager = run(False)
+    p_again, _, _ = run(False)
+    assert (d_graph, s_graph) == (d_eager, s_eager)
+    noise = max(float((a - b).abs().max()) for a, b in zip(p_eager, p_again))
+    diff = max(float((a - b).abs().max()) for a, b in zip(p_graph, p_eager))
+    assert all(bool(torch.isfinite(a).all()) for a in p_graph)
+    assert diff <= max(10.0 * noise, 1e-5), (diff, noise)
