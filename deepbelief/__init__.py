@@ -21,6 +21,7 @@ _ALIASES = {
     'deepbelief.layers.bgrbm': 'deepbelief_b200.layers.bgrbm',
     'deepbelief.layers.gbrbm': 'deepbelief_b200.layers.gbrbm',
     'deepbelief.layers.ggrbm': 'deepbelief_b200.layers.ggrbm',
+    'deepbelief.layers.bgrbmsv': 'deepbelief_b200.layers.bgrbmsv',
     'deepbelief.layers.sbm_lower': 'deepbelief_b200.layers.sbm_lower',
     'deepbelief.layers.gplvm': 'deepbelief_b200.layers.gplvm',
     'deepbelief.layers.gprbm': 'deepbelief_b200.layers.gprbm',

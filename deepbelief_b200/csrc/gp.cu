@@ -50,12 +50,16 @@ __global__ void effective_hyp_kernel(const float* __restrict__ opt, int flags, f
 // 32 x 256 tile per CTA; thread = 4 consecutive columns x 8 rows -> 16-byte coalesced stores.
 // Squared distances use the difference form (exact 0 on the diagonal; the reference's expanded form
 // gplvm.py:67-82 leaves +-2e-6 there in fp32, SURVEY.md §7 hard part 3).
+// The column latents are staged q-major ([Q][256]) so that a thread's four columns are one conflict-free 16-byte read,
+// and for Q <= 4 they are read ONCE into registers (they do not depend on the row). The first version kept them
+// column-major and re-read them per row: an 8-way bank conflict per read, 64 shared-memory wavefronts per warp and row —
+// that, not HBM, bounded the kernel (51 us for the 100 MB of N = 5000, 1.96 TB/s).
 __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, const float* __restrict__ Y, int N, int M,
                                                    int Q, const float* __restrict__ hyp, int add_noise,
                                                    float* __restrict__ out, int ldo) {
-  extern __shared__ float gsm[];
-  float* xs = gsm;                 // [32][Q]
-  float* ys = gsm + 32 * Q;        // [256][Q]
+  extern __shared__ __align__(16) float gsm[];
+  float* ys = gsm;                 // [Q][256]
+  float* xs = gsm + 256 * Q;       // [32][Q]
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 256;
   const float alpha = __ldg(hyp), inv_gamma = 1.0f / __ldg(hyp + 1), noise = __ldg(hyp + 2);
   const float* Ysrc = Y ? Y : X;
@@ -64,22 +68,43 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, 
     xs[t] = r < N ? __ldg(X + (size_t)r * Q + t % Q) * inv_gamma : 0.0f;
   }
   for (int t = threadIdx.x; t < 256 * Q; t += 256) {
-    const int r = j0 + t / Q;
-    ys[t] = r < M ? __ldg(Ysrc + (size_t)r * Q + t % Q) * inv_gamma : 0.0f;
+    const int c = t / Q, q = t % Q, r = j0 + c;
+    ys[q * 256 + c] = r < M ? __ldg(Ysrc + (size_t)r * Q + q) * inv_gamma : 0.0f;
   }
   __syncthreads();
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
   const int j = j0 + 4 * tx;
   if (j >= M) return;
-#pragma unroll 1
+  constexpr int QR = 4;            // latent dimensions held in registers
+  float4 yr[QR];
+#pragma unroll
+  for (int q = 0; q < QR; ++q)
+    yr[q] = q < Q ? *reinterpret_cast<const float4*>(ys + q * 256 + 4 * tx) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool vec_store = j + 3 < M && (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+#pragma unroll 2
   for (int rr = 0; rr < 8; ++rr) {
     const int il = ty + 4 * rr, i = i0 + il;
     if (i >= N) break;
     float d[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int q = 0; q < Q; ++q) {
-      const float xv = xs[il * Q + q];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { const float t = xv - ys[(4 * tx + e) * Q + q]; d[e] = fmaf(t, t, d[e]); }
+    for (int q = 0; q < QR; ++q) {
+      if (q < Q) {
+        const float xv = xs[il * Q + q];
+        float t;
+        t = xv - yr[q].x; d[0] = fmaf(t, t, d[0]);
+        t = xv - yr[q].y; d[1] = fmaf(t, t, d[1]);
+        t = xv - yr[q].z; d[2] = fmaf(t, t, d[2]);
+        t = xv - yr[q].w; d[3] = fmaf(t, t, d[3]);
+      }
+    }
+    for (int q = QR; q < Q; ++q) {
+      const float xv = xs[il * Q + q];
+      const float4 yv = *reinterpret_cast<const float4*>(ys + q * 256 + 4 * tx);
+      float t;
+      t = xv - yv.x; d[0] = fmaf(t, t, d[0]);
+      t = xv - yv.y; d[1] = fmaf(t, t, d[1]);
+      t = xv - yv.z; d[2] = fmaf(t, t, d[2]);
+      t = xv - yv.w; d[3] = fmaf(t, t, d[3]);
     }
     float kv[4];
 #pragma unroll
@@ -88,7 +113,7 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, 
       if (add_noise && Y == nullptr && i == j + e) kv[e] += noise;
     }
     float* o = out + (size_t)i * ldo + j;
-    if (j + 3 < M && (ldo % 4 == 0)) {
+    if (vec_store) {
       *reinterpret_cast<float4*>(o) = make_float4(kv[0], kv[1], kv[2], kv[3]);
     } else {
 #pragma unroll

@@ -565,3 +565,43 @@ def test_cd_gradient_from_chain_probabilities_is_bit_identical(horses, kind):
     got = _np(g_hidden)
     for lo, hi in ((0, V * H), (V * H, V * H + V), (V * H + V, V * H + V + H)):
         assert _normrel(got[lo:hi], want[lo:hi]) < GRAD_NORMREL
+
+
+def test_bgrbmsv_shared_sigma(horses):
+    """BGRBMSV (bgrbmsv.py): one shared sigma_h = softplus(1) at construction, forward / gradients equal to the BGRBM oracle
+    with that value in every unit, the shared scalar's gradient the sum of the per-unit gradients, and training keeps the
+    H packed entries equal; a fed sigma_h (the placeholder form) is used as given and not trained."""
+    from deepbelief_b200 import compat as tf
+    from deepbelief_b200.layers.bgrbmsv import BGRBMSV
+    from deepbelief_b200.layers.data import Data
+    rs = np.random.RandomState(9)
+    V, H, N = 1024, 40, 96
+    lay = BGRBMSV(V, H, name='sv', seed=2)
+    W = (rs.normal(size=(V, H)) * 0.01).astype(np.float32)
+    b, c = rs.normal(size=V).astype(np.float32) * 0.05, rs.normal(size=H).astype(np.float32) * 0.05
+    lay.set_weights(W, b, c)
+    sig = np.log1p(np.exp(1.0))
+    np.testing.assert_allclose(_np(lay.sigma_h), np.full((1, H), sig), rtol=1e-6)
+    assert lay.params['sigma_h']().shape == (1,)
+    orc = orbm.RBMOracle(W, b, c, kind='bgrbm', opt_sigma_h=np.full((1, H), 1.0))
+    v0 = horses[:N].astype(np.float64)
+    vk = (rs.rand(N, V) < 0.4).astype(np.float64)
+    np.testing.assert_allclose(_np(lay.h_probs(v0)), orc.h_probs(v0), rtol=PROB_RTOL, atol=1e-6)
+    want = orc.cd_grad_packed(v0, vk)
+    grad = lay.cd_gradient(v0, vk)
+    off = V * H + V + H
+    assert _normrel(_np(grad)[:off], want[:off]) < GRAD_NORMREL
+    _, shared = lay._trainable_pair(grad)
+    got_sigma = _np(shared)[off:]
+    assert np.all(got_sigma == got_sigma[0]) and abs(got_sigma[0] - want[off:].sum()) < GRAD_NORMREL * np.abs(want[off:]).sum()
+    lay.train(tf.train.AdamOptimizer(learning_rate=1e-3), Data.from_arrays(horses[:N].astype(np.float32), batch_size=N, log_epochs=False),
+              None, num_gibbs_steps=1, pcd=False, max_iterations=6)
+    os_ = _np(lay.opt_sigma_h).ravel()
+    assert np.all(os_ == os_[0]) and os_[0] != 1.0 and np.isfinite(os_[0])
+    fed = BGRBMSV(V, H, sigma_h_ph=0.7, name='svfed', seed=2)
+    fed.set_weights(W, b, c)
+    np.testing.assert_allclose(_np(fed.sigma_h), np.full((1, H), 0.7), rtol=1e-6)
+    fed.train(tf.train.GradientDescentOptimizer(learning_rate=1e-3), Data.from_arrays(horses[:N].astype(np.float32), batch_size=N, log_epochs=False),
+              None, num_gibbs_steps=1, pcd=False, max_iterations=3)
+    np.testing.assert_allclose(_np(fed.sigma_h), np.full((1, H), 0.7), rtol=1e-6)
+    assert not np.array_equal(_np(fed.W), W)
