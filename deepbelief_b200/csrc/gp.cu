@@ -47,7 +47,8 @@ __global__ void effective_hyp_kernel(const float* __restrict__ opt, int flags, f
 }
 
 // ---- K3: Gram -------------------------------------------------------------------------------------
-// 32 x 256 tile per CTA; thread = 4 consecutive columns x 8 rows -> 16-byte coalesced stores.
+// rows x 256 tile per CTA (rows = 128 for big matrices: one resident wave of CTAs, the latent staging amortised over 32
+// rows per thread; 32 for small ones: more CTAs); thread = 4 consecutive columns x rows/4 rows -> 16-byte coalesced stores.
 // Squared distances use the difference form (exact 0 on the diagonal; the reference's expanded form
 // gplvm.py:67-82 leaves +-2e-6 there in fp32, SURVEY.md §7 hard part 3).
 // The column latents are staged q-major ([Q][256]) so that a thread's four columns are one conflict-free 16-byte read,
@@ -56,14 +57,14 @@ __global__ void effective_hyp_kernel(const float* __restrict__ opt, int flags, f
 // that, not HBM, bounded the kernel (51 us for the 100 MB of N = 5000, 1.96 TB/s).
 __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, const float* __restrict__ Y, int N, int M,
                                                    int Q, const float* __restrict__ hyp, int add_noise,
-                                                   float* __restrict__ out, int ldo) {
+                                                   float* __restrict__ out, int ldo, int rows) {
   extern __shared__ __align__(16) float gsm[];
   float* ys = gsm;                 // [Q][256]
-  float* xs = gsm + 256 * Q;       // [32][Q]
-  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 256;
+  float* xs = gsm + 256 * Q;       // [rows][Q]
+  const int i0 = blockIdx.y * rows, j0 = blockIdx.x * 256;
   const float alpha = __ldg(hyp), inv_gamma = 1.0f / __ldg(hyp + 1), noise = __ldg(hyp + 2);
   const float* Ysrc = Y ? Y : X;
-  for (int t = threadIdx.x; t < 32 * Q; t += 256) {
+  for (int t = threadIdx.x; t < rows * Q; t += 256) {
     const int r = i0 + t / Q;
     xs[t] = r < N ? __ldg(X + (size_t)r * Q + t % Q) * inv_gamma : 0.0f;
   }
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, 
     yr[q] = q < Q ? *reinterpret_cast<const float4*>(ys + q * 256 + 4 * tx) : make_float4(0.f, 0.f, 0.f, 0.f);
   const bool vec_store = j + 3 < M && (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
 #pragma unroll 2
-  for (int rr = 0; rr < 8; ++rr) {
+  for (int rr = 0; rr < rows / 4; ++rr) {
     const int il = ty + 4 * rr, i = i0 + il;
     if (i >= N) break;
     float d[4] = {0.f, 0.f, 0.f, 0.f};
@@ -1197,8 +1198,9 @@ __global__ void __launch_bounds__(256) pred_mean_kernel(const float* __restrict_
 // ---- host-side building blocks -----------------------------------------------------------------------
 int run_gram(db_handle_t h, cudaStream_t st, const float* X, const float* Y, int N, int M, int Q, const float* hyp,
              int add_noise, float* out, int ldo) {
-  dim3 grid((M + 255) / 256, (N + 31) / 32);
-  gram_kernel<<<grid, 256, sizeof(float) * 288 * Q, st>>>(X, Y, N, M, Q, hyp, add_noise, out, ldo);
+  const int rows = ((long)((M + 255) / 256) * ((N + 127) / 128) >= 2L * h->num_sms) ? 128 : 32;
+  dim3 grid((M + 255) / 256, (N + rows - 1) / rows);
+  gram_kernel<<<grid, 256, sizeof(float) * (256 + rows) * Q, st>>>(X, Y, N, M, Q, hyp, add_noise, out, ldo, rows);
   return check_launch(h, "gram_rbf");
 }
 

@@ -19,4 +19,15 @@ for N, Q in ((5000, 2), (8192, 2), (5000, 8)):
     us = e0.elapsed_time(e1) / reps * 1e3
     gb = (4.0 * N * N + 4.0 * N * Q) / 1e9
     print('gram N=%d Q=%d: %.1f us, %.0f GB/s' % (N, Q, us, gb / (us * 1e-6)), flush=True)
+# write-only ceiling of this box for the same footprint: a plain fill of N^2 floats (library kernel, reference only)
+for N in (5000, 8192):
+    bufs = [torch.empty(N, N, device='cuda') for _ in range(3)]
+    for b in bufs: b.fill_(1.0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(60): bufs[i % 3].fill_(1.0)
+    e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 60 * 1e3
+    print('fill  N=%d: %.1f us, %.0f GB/s (write-only reference)' % (N, us, 4.0 * N * N / 1e9 / (us * 1e-6)), flush=True)
 print('peaks', {k: v for k, v in peaks.items() if 'hbm' in k.lower() or 'GB' in str(k)})
