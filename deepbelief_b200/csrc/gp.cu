@@ -55,10 +55,16 @@ __global__ void effective_hyp_kernel(const float* __restrict__ opt, int flags, f
 // and for Q <= 4 they are read ONCE into registers (they do not depend on the row). The first version kept them
 // column-major and re-read them per row: an 8-way bank conflict per read, 64 shared-memory wavefronts per warp and row —
 // that, not HBM, bounded the kernel (51 us for the 100 MB of N = 5000, 1.96 TB/s).
+// QT: the latent dimension as a compile-time constant (1..4; the reference's Q is 2), 0 = any Q at run time. ncu on the
+// run-time-Q version: 75 % of the issue slots busy at 39 % occupancy and only 42 of the 100 MB reaching DRAM inside the
+// kernel's duration — it was bound by instructions (predicated q loops, index arithmetic, per-element diagonal tests), not
+// by memory.
+template <int QT>
 __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, const float* __restrict__ Y, int N, int M,
-                                                   int Q, const float* __restrict__ hyp, int add_noise,
+                                                   int Q_rt, const float* __restrict__ hyp, int add_noise,
                                                    float* __restrict__ out, int ldo, int rows) {
   extern __shared__ __align__(16) float gsm[];
+  const int Q = QT > 0 ? QT : Q_rt;
   float* ys = gsm;                 // [Q][256]
   float* xs = gsm + 256 * Q;       // [rows][Q]
   const int i0 = blockIdx.y * rows, j0 = blockIdx.x * 256;
@@ -76,21 +82,23 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, 
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
   const int j = j0 + 4 * tx;
   if (j >= M) return;
-  constexpr int QR = 4;            // latent dimensions held in registers
+  constexpr int QR = QT > 0 ? QT : 4;            // latent dimensions held in registers
   float4 yr[QR];
 #pragma unroll
   for (int q = 0; q < QR; ++q)
-    yr[q] = q < Q ? *reinterpret_cast<const float4*>(ys + q * 256 + 4 * tx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    yr[q] = (QT > 0 || q < Q) ? *reinterpret_cast<const float4*>(ys + q * 256 + 4 * tx) : make_float4(0.f, 0.f, 0.f, 0.f);
   const bool vec_store = j + 3 < M && (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const bool diag = add_noise && Y == nullptr;
+  const int nr = min(rows / 4, (N - i0 - ty + 3) / 4);          // rows i0 + ty + 4 rr < N
+  float* o = out + (size_t)(i0 + ty) * ldo + j;
+  const float* xrow = xs + ty * Q;
 #pragma unroll 2
-  for (int rr = 0; rr < rows / 4; ++rr) {
-    const int il = ty + 4 * rr, i = i0 + il;
-    if (i >= N) break;
+  for (int rr = 0; rr < nr; ++rr, o += (size_t)4 * ldo, xrow += 4 * Q) {
     float d[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int q = 0; q < QR; ++q) {
-      if (q < Q) {
-        const float xv = xs[il * Q + q];
+      if (QT > 0 || q < Q) {
+        const float xv = xrow[q];
         float t;
         t = xv - yr[q].x; d[0] = fmaf(t, t, d[0]);
         t = xv - yr[q].y; d[1] = fmaf(t, t, d[1]);
@@ -98,22 +106,25 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, 
         t = xv - yr[q].w; d[3] = fmaf(t, t, d[3]);
       }
     }
-    for (int q = QR; q < Q; ++q) {
-      const float xv = xs[il * Q + q];
-      const float4 yv = *reinterpret_cast<const float4*>(ys + q * 256 + 4 * tx);
-      float t;
-      t = xv - yv.x; d[0] = fmaf(t, t, d[0]);
-      t = xv - yv.y; d[1] = fmaf(t, t, d[1]);
-      t = xv - yv.z; d[2] = fmaf(t, t, d[2]);
-      t = xv - yv.w; d[3] = fmaf(t, t, d[3]);
+    if (QT == 0) {
+      for (int q = QR; q < Q; ++q) {
+        const float xv = xrow[q];
+        const float4 yv = *reinterpret_cast<const float4*>(ys + q * 256 + 4 * tx);
+        float t;
+        t = xv - yv.x; d[0] = fmaf(t, t, d[0]);
+        t = xv - yv.y; d[1] = fmaf(t, t, d[1]);
+        t = xv - yv.z; d[2] = fmaf(t, t, d[2]);
+        t = xv - yv.w; d[3] = fmaf(t, t, d[3]);
+      }
     }
     float kv[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      kv[e] = alpha * __expf(-0.5f * d[e]);
-      if (add_noise && Y == nullptr && i == j + e) kv[e] += noise;
+    for (int e = 0; e < 4; ++e) kv[e] = alpha * __expf(-0.5f * d[e]);
+    const int dj = i0 + ty + 4 * rr - j;                          // the diagonal element of this row, if it is one of the four
+    if (diag && (unsigned)dj < 4u) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) if (dj == e) kv[e] += noise;
     }
-    float* o = out + (size_t)i * ldo + j;
     if (vec_store) {
       *reinterpret_cast<float4*>(o) = make_float4(kv[0], kv[1], kv[2], kv[3]);
     } else {
@@ -1200,7 +1211,14 @@ int run_gram(db_handle_t h, cudaStream_t st, const float* X, const float* Y, int
              int add_noise, float* out, int ldo) {
   const int rows = ((long)((M + 255) / 256) * ((N + 127) / 128) >= 2L * h->num_sms) ? 128 : 32;
   dim3 grid((M + 255) / 256, (N + rows - 1) / rows);
-  gram_kernel<<<grid, 256, sizeof(float) * (256 + rows) * Q, st>>>(X, Y, N, M, Q, hyp, add_noise, out, ldo, rows);
+  const size_t smem = sizeof(float) * (256 + rows) * Q;
+  switch (Q) {
+    case 1: gram_kernel<1><<<grid, 256, smem, st>>>(X, Y, N, M, Q, hyp, add_noise, out, ldo, rows); break;
+    case 2: gram_kernel<2><<<grid, 256, smem, st>>>(X, Y, N, M, Q, hyp, add_noise, out, ldo, rows); break;
+    case 3: gram_kernel<3><<<grid, 256, smem, st>>>(X, Y, N, M, Q, hyp, add_noise, out, ldo, rows); break;
+    case 4: gram_kernel<4><<<grid, 256, smem, st>>>(X, Y, N, M, Q, hyp, add_noise, out, ldo, rows); break;
+    default: gram_kernel<0><<<grid, 256, smem, st>>>(X, Y, N, M, Q, hyp, add_noise, out, ldo, rows); break;
+  }
   return check_launch(h, "gram_rbf");
 }
 

@@ -362,3 +362,35 @@ def test_ard_kernel_and_gplvm_vs_reference(tmp_path):
     k2 = SEKernel(alpha=1.0, gamma=1.0, ARD=True, Q=Q)
     k2.restore(ck)
     np.testing.assert_allclose(_np(k2.gamma), _np(kern.gamma), rtol=0, atol=0)
+
+
+@pytest.mark.parametrize('N,M,Q', [(328, None, 2), (70, None, 1), (1030, None, 3), (300, 45, 4), (129, 700, 5), (5000, None, 2),
+                                   (4100, 4100, 7)])
+def test_gram_kernel_every_latent_dimension(N, M, Q):
+    """K3 is compiled per latent dimension (Q = 1..4) with a run-time-Q fallback, and tiles 32 or 128 rows per CTA
+    depending on the matrix size: square (noise on the diagonal, exact alpha + noise there) and rectangular K_Xx forms
+    against float64 (gplvm.py:61-86), ragged edges included."""
+    from deepbelief_b200 import ops
+    rs = np.random.RandomState(N + Q)
+    X = rs.normal(size=(N, Q)).astype(np.float32)
+    Y = None if M is None else rs.normal(size=(M, Q)).astype(np.float32)
+    alpha, gamma, noise = 1.3, 0.8, 0.05
+    hyp = torch.tensor([alpha, gamma, noise], device='cuda')
+    got = ops.gram_rbf(torch.as_tensor(X).cuda(), None if Y is None else torch.as_tensor(Y).cuda(), hyp, add_noise=True)
+    A = X.astype(np.float64) / gamma
+    B = A if Y is None else Y.astype(np.float64) / gamma
+    d2 = ((A[:, None, :] - B[None, :, :]) ** 2).sum(-1) if N * B.shape[0] <= 2_000_000 else None
+    if d2 is None:                                     # big cases: row blocks
+        got_np = got.cpu().numpy()
+        for r0 in range(0, N, 997):
+            blk = ((A[r0:r0 + 64, None, :] - B[None, :, :]) ** 2).sum(-1)
+            want = alpha * np.exp(-0.5 * blk)
+            if Y is None:
+                want[np.arange(want.shape[0]), r0 + np.arange(want.shape[0])] += noise
+            np.testing.assert_allclose(got_np[r0:r0 + 64], want, rtol=2e-5, atol=1e-6)
+        return
+    want = alpha * np.exp(-0.5 * d2)
+    if Y is None:
+        want[np.arange(N), np.arange(N)] += noise
+        assert np.all(got.diagonal().cpu().numpy() == np.float32(np.float32(alpha) + np.float32(noise)))
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=2e-5, atol=1e-6)
