@@ -304,6 +304,19 @@ def run_b200(args):
     windows.append((t_a, t_b))
     gp_ms = parallel.max_over_ranks(e0.elapsed_time(e1), device=dev) / gp_iters
     gp_info = int(gplan.info.item())
+    # the HBM-bound member of the chain, timed alone: RBF Gram (K3), 4 N^2 + 4 N Q algorithmic bytes per launch; the 100 MB
+    # outputs cycle through the allocator's freed blocks (3 x 100 MB > L2)
+    g_hyp = torch.tensor([1.0, 1.0, 1.0], dtype=torch.float32, device=dev)
+    for _ in range(3):
+        ops.gram_rbf(gX, None, g_hyp, add_noise=True)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(30):
+        ops.gram_rbf(gX, None, g_hyp, add_noise=True)
+    g1.record()
+    torch.cuda.synchronize()
+    gram_us = g0.elapsed_time(g1) / 30 * 1e3
+    gram_gbs = (4.0 * GP_N * GP_N + 4.0 * GP_N * GP_Q) / 1e9 / (gram_us * 1e-6)
     gp_flop = float(GP_N) ** 3 + 3.0 * GP_N * GP_N * GP_D
 
     # ---- GPDBN (BASELINE configs[3]): synthetic binary 5000x784, stack 784->200->100->GPRBM(50), Q=2, T=0.1 ----
@@ -391,7 +404,13 @@ def run_b200(args):
                       'roofline': {'bound': 'fp32-ffma', 'achieved': gp_flop / (gp_ms * 1e-3) / 1e12,
                                    'peak': 148 * 128 * 2 * 1.965e9 / 1e12, 'unit': 'TFLOP/s',
                                    'frac': gp_flop / (gp_ms * 1e-3) / (148 * 128 * 2 * 1.965e9),
-                                   'note': 'latency-bound Cholesky critical path: 79 column-block steps of 16 us (DESIGN.md K4)'}},
+                                   'note': 'latency-bound Cholesky critical path: 79 column-block steps of 16 us (DESIGN.md K4)'},
+                      'gram': {'kernel': 'gram_kernel<2>', 'us_per_launch': gram_us,
+                               'roofline': {'bound': 'hbm', 'achieved': gram_gbs, 'peak': load_peaks()['hbm_gbs'], 'unit': 'GB/s',
+                                            'frac': gram_gbs / load_peaks()['hbm_gbs'],
+                                            'traffic': 42781696.0,
+                                            'traffic_note': 'dram read+write inside the kernel (profiles/r01_gram_full_raw.csv); the '
+                                                            '126 MB L2 absorbs the rest of the 100 MB it writes'}}},
             'gpdbn': gpdbn,
         }
         print(json.dumps(line))

@@ -382,7 +382,7 @@ def test_optimize_as_cuda_graph_matches_the_eager_loop(monkeypatch, opt_name):
     evaluation steps (which draw eagerly) in between. The host counters must end identical, and every trainable of the stack
     must agree with the eager loop as closely as two eager runs agree with each other (the loss reductions use atomics, so
     the eager loop itself repeats only to ~1e-6..1e-5 after 23 iterations; one wrong draw id would move parameters by
-    ~lr per iteration)."""
+    ~lr per iteration, 1e-3 and more by the end)."""
     from deepbelief_b200 import compat as tf
     from deepbelief_b200.layers.gprbm import GPRBM
     from deepbelief_b200 import replay
@@ -413,4 +413,4 @@ def test_optimize_as_cuda_graph_matches_the_eager_loop(monkeypatch, opt_name):
     noise = max(float((a - b).abs().max()) for a, b in zip(p_eager, p_again))
     diff = max(float((a - b).abs().max()) for a, b in zip(p_graph, p_eager))
     assert all(bool(torch.isfinite(a).all()) for a in p_graph)
-    assert diff <= max(10.0 * noise, 1e-5), (diff, noise)
+    assert diff <= max(10.0 * noise, 2e-4), (diff, noise)     # (measured: noise 6e-6..1.3e-5, diff 5e-6..2.1e-5)
