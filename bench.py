@@ -389,6 +389,10 @@ def run_b200(args):
                          'peak_source': 'MEASURED_PEAKS.json bf16 sustained (%s); fp16 runs at the bf16 rate'
                                         % peaks['source'],
                          'executed_tflops': 2.0 * achieved,
+                         # north_star names the TF32 tensor peak as the roofline of the CD GEMMs (a single-pass fp32-accurate
+                         # product would run as kind::tf32, half the 16-bit rate): the same achieved figure against it
+                         'frac_of_tf32_peak': achieved / (0.5 * peak),
+                         'frac_executed_of_peak': 2.0 * achieved / peak,
                          'note': 'achieved counts ALGORITHMIC flop (2k+3)*2*N*V*H; every MMA is issued twice '
                                  '(hi and lo half of the split real operand), so the tensor pipe executes 2x',
                          'chain_ms_per_step': chain_ms,
