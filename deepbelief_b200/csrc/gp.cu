@@ -55,6 +55,12 @@ __global__ void effective_hyp_kernel(const float* __restrict__ opt, int flags, f
 // and for Q <= 4 they are read ONCE into registers (they do not depend on the row). The first version kept them
 // column-major and re-read them per row: an 8-way bank conflict per read, 64 shared-memory wavefronts per warp and row —
 // that, not HBM, bounded the kernel (51 us for the 100 MB of N = 5000, 1.96 TB/s).
+// 2^x, flush-to-zero: no range fix-up around MUFU.EX2 (__expf costs 8 instructions per entry without -ftz)
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // QT: the latent dimension as a compile-time constant (1..4; the reference's Q is 2), 0 = any Q at run time. ncu on the
 // run-time-Q version: 75 % of the issue slots busy at 39 % occupancy and only 42 of the 100 MB reaching DRAM inside the
 // kernel's duration — it was bound by instructions (predicated q loops, index arithmetic, per-element diagonal tests), not
@@ -88,7 +94,9 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, 
   for (int q = 0; q < QR; ++q)
     yr[q] = (QT > 0 || q < Q) ? *reinterpret_cast<const float4*>(ys + q * 256 + 4 * tx) : make_float4(0.f, 0.f, 0.f, 0.f);
   const bool vec_store = j + 3 < M && (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  const bool diag = add_noise && Y == nullptr;
+  const bool square = Y == nullptr;
+  const float diag_value = add_noise ? alpha + noise : alpha;
+  const float lg_alpha = log2f(alpha);           // alpha exp(-d/2) = 2^(log2 alpha - d log2(e)/2): one FFMA + one EX2 per entry
   const int nr = min(rows / 4, (N - i0 - ty + 3) / 4);          // rows i0 + ty + 4 rr < N
   float* o = out + (size_t)(i0 + ty) * ldo + j;
   const float* xrow = xs + ty * Q;
@@ -119,11 +127,11 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, 
     }
     float kv[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) kv[e] = alpha * __expf(-0.5f * d[e]);
+    for (int e = 0; e < 4; ++e) kv[e] = ex2_ftz(fmaf(d[e], -0.5f * 1.4426950408889634f, lg_alpha));   // alpha exp(-d/2)
     const int dj = i0 + ty + 4 * rr - j;                          // the diagonal element of this row, if it is one of the four
-    if (diag && (unsigned)dj < 4u) {
+    if (square && (unsigned)dj < 4u) {                            // r = 0 there: exactly alpha (+ noise)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) if (dj == e) kv[e] += noise;
+      for (int e = 0; e < 4; ++e) if (dj == e) kv[e] = diag_value;
     }
     if (vec_store) {
       *reinterpret_cast<float4*>(o) = make_float4(kv[0], kv[1], kv[2], kv[3]);
