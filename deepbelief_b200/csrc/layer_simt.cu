@@ -1,7 +1,8 @@
 // SIMT (fp32 FFMA) form of the RBM-family kernels: used for small / ragged layers (the reference's
 // own test shapes are 6x5, tests/test_rbm.py:10-16), for the real-valued layer kinds (BGRBM / GBRBM /
 // GGRBM / Concrete units), and as the general form of the CD gradient. Large binary RBMs go through
-// the tcgen05 path (gemm_tc.cu / cd_chain.cu).
+// the tcgen05 path (gemm_tc.cu / cd_chain.cu). Launches with few output tiles (the reference's 328 x 1024 x 500) split K
+// over a thread-block cluster and reduce through distributed shared memory (simt_gemm.cuh).
 #include "context.h"
 #include "simt_gemm.cuh"
 
