@@ -950,6 +950,43 @@ __global__ void __launch_bounds__(256) trmm_kernel(const float* __restrict__ Li,
   }
 }
 
+// 64 x 64 tiles with the (triangular) K range of the tile split over a thread-block cluster (simt_gemm.cuh): the horses-sized
+// products (N = 328, D = 1024) are 96 tiles walking up to 328 columns each — latency-bound at 23-26 us per launch
+template <int TRANS>
+__global__ void __launch_bounds__(256) trmm_split_kernel(const float* __restrict__ Li, int ldi, int N, const float* __restrict__ B,
+                                                         int ldb, int nrhs, float* __restrict__ out, int ldo,
+                                                         float* __restrict__ ssq, int splits) {
+  using T = TileSmall;
+  __shared__ typename T::Smem sm;
+  __shared__ __align__(16) float red[T::BM * T::BN];
+  __shared__ float wsum[8];
+  const int by = TRANS ? blockIdx.y : gridDim.y - 1 - blockIdx.y;
+  const int m0 = by * T::BM, n0 = blockIdx.x * T::BN;
+  LoadLinvA<TRANS> a{Li, ldi, N};
+  LoadMatB b{B, ldb, N, nrhs};
+  float acc[T::TM][T::TN];
+  const int kb = TRANS ? m0 : 0;
+  const int ke = TRANS ? N : min(N, m0 + T::BM);
+  int sb, se;
+  simt_split_range<T>(ke - kb, splits, sb, se);
+  simt_gemm_tile<T>(sm, a, b, m0, n0, kb + sb, kb + se, acc);
+  float local = 0.0f;
+  simt_cluster_reduce<T>(red, acc, splits, [&](int r, int c, float x) {
+    const int m = m0 + r, n = n0 + c;
+    if (m < N && n < nrhs) { out[(size_t)m * ldo + n] = x; local = fmaf(x, x, local); }
+  });
+  if (ssq != nullptr) {
+    local = warp_sum(local);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.0f;
+      for (int w = 0; w < 8; ++w) t += wsum[w];
+      atomicAdd(ssq, t);
+    }
+  }
+}
+
 __global__ void logdet_xsq_kernel(const float* __restrict__ L, int ldl, int N, const float* __restrict__ X, int nx, GpAccum* acc) {
   float s = 0.0f, x2 = 0.0f;
   for (int i = threadIdx.x; i < N; i += blockDim.x) s += logf(__ldg(L + (size_t)i * ldl + i));
@@ -1420,7 +1457,13 @@ int run_trmm(db_handle_t h, cudaStream_t st, const float* Li, int N, const float
   } else {
     using T = TileSmall;
     dim3 grid((nrhs + T::BN - 1) / T::BN, (N + T::BM - 1) / T::BM);
-    trmm_kernel<TRANS, T><<<grid, 256, 0, st>>>(Li, N, N, B, ldb, nrhs, out, ldo, ssq);
+    const int splits = simt_splits((long)grid.x * grid.y, N, h->num_sms);
+    if (splits > 1) {
+      grid.z = splits;
+      simt_launch_split(trmm_split_kernel<TRANS>, grid, 256, st, Li, N, N, B, ldb, nrhs, out, ldo, ssq, splits);
+    } else {
+      trmm_kernel<TRANS, T><<<grid, 256, 0, st>>>(Li, N, N, B, ldb, nrhs, out, ldo, ssq);
+    }
   }
   return check_launch(h, "trmm");
 }
