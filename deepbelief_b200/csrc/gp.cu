@@ -902,6 +902,44 @@ __global__ void __launch_bounds__(256) trinv_level_kernel(const float* __restric
   }
 }
 
+// The same level with the K range of every tile split over a thread-block cluster (simt_gemm.cuh); the pair index is folded
+// into blockIdx.y (grid: (column tiles, row tiles * pairs, splits)). At N = 328 the three levels are six launches of 1-16
+// tiles with K = 64-256: 7-18 us each, a quarter of an LML+gradient evaluation.
+template <int STEP>
+__global__ void __launch_bounds__(256) trinv_level_split_kernel(const float* __restrict__ L, int ldl, int N, int s,
+                                                                float* __restrict__ Li, int ldi, float* __restrict__ Tmp, int ldt,
+                                                                int tiles_y, int splits) {
+  using T = TileSmall;
+  __shared__ typename T::Smem sm;
+  __shared__ __align__(16) float red[T::BM * T::BN];
+  const int p = blockIdx.y / tiles_y, by = blockIdx.y % tiles_y;
+  const int c0 = 2 * p * s, r0 = c0 + s;
+  if (r0 >= N) return;                       // uniform over the cluster (same x, y)
+  const int nr = min(s, N - r0);
+  const int m0 = by * T::BM, n0 = blockIdx.x * T::BN;
+  if (m0 >= nr || n0 >= s) return;
+  float acc[T::TM][T::TN];
+  int kb, ke;
+  if (STEP == 0) {
+    LoadMat a{L + (size_t)r0 * ldl + c0, ldl, nr, s};
+    LoadMatB b{Li + (size_t)c0 * ldi + c0, ldi, s, s};
+    simt_split_range<T>(s - n0, splits, kb, ke);                       // k >= first column of the tile
+    simt_gemm_tile<T>(sm, a, b, m0, n0, n0 + kb, n0 + ke, acc);
+  } else {
+    LoadMat a{Li + (size_t)r0 * ldi + r0, ldi, nr, nr};
+    LoadMatB b{Tmp + (size_t)r0 * ldt + c0, ldt, nr, s};
+    simt_split_range<T>(min(nr, m0 + T::BM), splits, kb, ke);          // k <= last row of the tile
+    simt_gemm_tile<T>(sm, a, b, m0, n0, kb, ke, acc);
+  }
+  simt_cluster_reduce<T>(red, acc, splits, [&](int r, int c, float x) {
+    const int m = m0 + r, n = n0 + c;
+    if (m < nr && n < s) {
+      if (STEP == 0) Tmp[(size_t)(r0 + m) * ldt + c0 + n] = x;
+      else Li[(size_t)(r0 + m) * ldi + c0 + n] = -x;
+    }
+  });
+}
+
 // ---- triangular products with Linv ------------------------------------------------------------------
 // out = Linv * B (trans=0, k <= row) or Linv^T * B (trans=1, k >= row); optional sum of squares of out
 template <int TRANS>
@@ -1368,8 +1406,16 @@ int run_trinv(db_handle_t h, cudaStream_t st, const float* L, int ldl, int N, fl
       trinv_level_kernel<1, TileLarge><<<grid, 256, 0, st>>>(L, ldl, N, s, Li, N, Tmp, N);
     } else {
       dim3 grid((s + TileSmall::BN - 1) / TileSmall::BN, (s + TileSmall::BM - 1) / TileSmall::BM, pairs);
-      trinv_level_kernel<0, TileSmall><<<grid, 256, 0, st>>>(L, ldl, N, s, Li, N, Tmp, N);
-      trinv_level_kernel<1, TileSmall><<<grid, 256, 0, st>>>(L, ldl, N, s, Li, N, Tmp, N);
+      const int splits = simt_splits((long)grid.x * grid.y * pairs, s, h->num_sms, 32);
+      if (splits > 1) {
+        const int tiles_y = (int)grid.y;
+        dim3 g2(grid.x, grid.y * pairs, splits);
+        simt_launch_split(trinv_level_split_kernel<0>, g2, 256, st, L, ldl, N, s, Li, N, Tmp, N, tiles_y, splits);
+        simt_launch_split(trinv_level_split_kernel<1>, g2, 256, st, L, ldl, N, s, Li, N, Tmp, N, tiles_y, splits);
+      } else {
+        trinv_level_kernel<0, TileSmall><<<grid, 256, 0, st>>>(L, ldl, N, s, Li, N, Tmp, N);
+        trinv_level_kernel<1, TileSmall><<<grid, 256, 0, st>>>(L, ldl, N, s, Li, N, Tmp, N);
+      }
     }
   }
   return check_launch(h, "trinv_lower");
