@@ -841,16 +841,19 @@ __global__ void __launch_bounds__(64) trinv_diag_kernel(const float* __restrict_
     const int r = t / NB, c = t % NB;
     D[r][c] = (r < nb && c <= r) ? __ldg(L + (size_t)(i0 + r) * ldl + i0 + c) : 0.0f;
   }
+  __shared__ float rdiag[NB];
   __syncthreads();
   const int c = threadIdx.x;
+  rdiag[c] = c < nb ? 1.0f / D[c][c] : 0.0f;             // the division leaves the serial chain
   for (int r = 0; r < NB; ++r) Xs[r][c] = 0.0f;          // rows not solved yet read as zero: the k loop needs no tail
+  __syncthreads();
   for (int r = 0; r < nb; ++r) {
     float s[4] = {(r == c) ? 1.0f : 0.0f, 0.0f, 0.0f, 0.0f};
     for (int k = 0; k < r; k += 8) {                      // k .. k+7 <= 63; D[r][k > r] = 0 and Xs[k >= r][c] = 0
 #pragma unroll
       for (int u = 0; u < 8; ++u) s[u & 3] = fmaf(-D[r][k + u], Xs[k + u][c], s[u & 3]);
     }
-    const float x = ((s[0] + s[1]) + (s[2] + s[3])) / D[r][r];
+    const float x = ((s[0] + s[1]) + (s[2] + s[3])) * rdiag[r];
     Xs[r][c] = x;                        // only this thread reads column c again
     if (c <= r) Li[(size_t)(i0 + r) * ldi + i0 + c] = x;
   }
