@@ -69,6 +69,12 @@ def test_alias_package_maps_reference_module_paths():
     import deepbelief.dist as d
     import deepbelief.layers.data as data
     assert d.__name__ == 'deepbelief_b200.dist' and data.Data.__module__ == 'deepbelief_b200.layers.data'
+    # every layer module of the reference (deepbelief/layers/*.py except the unfinished conv_rbm) resolves
+    import importlib
+    for name, cls in (('rbm', 'RBM'), ('bgrbm', 'BGRBM'), ('gbrbm', 'GBRBM'), ('ggrbm', 'GGRBM'), ('bgrbmsv', 'BGRBMSV'),
+                      ('sbm_lower', 'SBM_Lower'), ('gplvm', 'GPLVM'), ('gprbm', 'GPRBM')):
+        mod = importlib.import_module('deepbelief.layers.' + name)
+        assert hasattr(mod, cls) and mod.__name__ == 'deepbelief_b200.layers.' + name
 
 
 def test_philox_known_answer_and_row_sharding():
