@@ -140,9 +140,11 @@ def lib():
     global _lib
     with _lock:
         if _lib is None:
-            path = os.environ.get('DEEPBELIEF_B200_LIB') or _build.LIB_PATH     # override: instrumented debug builds
-            if not os.path.exists(path):
-                path = _build.build()
+            path = os.environ.get('DEEPBELIEF_B200_LIB')                        # override: instrumented debug builds
+            if not path:
+                # csrc/.build_stamp (untracked, written next to the .so) holds the hash of the sources the library was built
+                # from: a library older than the sources would be called with newer struct layouts, so it is rebuilt
+                path = _build.build() if _build.needs_build() else _build.LIB_PATH
             try:
                 loaded = ctypes.CDLL(path)
             except OSError as e:   # no silent fallback

@@ -184,3 +184,53 @@ summary = types.SimpleNamespace(FileWriter=_FileWriter, merge_all=lambda: None, 
                                 histogram=lambda *a, **k: None)
 float32 = np.float32
 int32 = np.int32
+
+
+# ---- running the reference's scripts unmodified --------------------------------------------------------------------
+def install_as_tensorflow():
+    """Register this module as `tensorflow` (sys.modules), so that a reference script's own first line
+    `import tensorflow as tf` (examples/dbn_horses/train.py:1, gplvm_horses/train.py:1, gpdbn_horses/train.py:1)
+    resolves to the shim without editing the script. Refuses to shadow a real TensorFlow."""
+    import sys
+    this = sys.modules[__name__]
+    have = sys.modules.get('tensorflow')
+    if have is not None and have is not this:
+        raise RuntimeError('a real `tensorflow` module is already imported; not shadowing it')
+    sys.modules['tensorflow'] = this
+    return this
+
+
+def _png_bytes(img):
+    """Minimal 8-bit greyscale PNG encoder (zlib + CRC from the standard library)."""
+    import struct
+    import zlib
+    a = np.asarray(img, dtype=np.float64)
+    assert a.ndim == 2, 'greyscale images only'
+    lo, hi = float(a.min()), float(a.max())
+    a8 = np.zeros(a.shape, np.uint8) if hi <= lo else np.round((a - lo) * (255.0 / (hi - lo))).astype(np.uint8)
+    raw = b''.join(b'\x00' + a8[r].tobytes() for r in range(a8.shape[0]))
+
+    def chunk(tag, data):
+        return struct.pack('>I', len(data)) + tag + data + struct.pack('>I', zlib.crc32(tag + data) & 0xffffffff)
+    return (b'\x89PNG\r\n\x1a\n' + chunk(b'IHDR', struct.pack('>IIBBBBB', a8.shape[1], a8.shape[0], 8, 0, 0, 0, 0)) +
+            chunk(b'IDAT', zlib.compress(raw, 6)) + chunk(b'IEND', b''))
+
+
+def install_script_environment():
+    """What `python -m deepbelief_b200.run <script>` sets up before executing a reference script verbatim: the
+    `tensorflow` alias and `scipy.misc.imsave`, which the reference's test_generalisation.py scripts call
+    (e.g. examples/gplvm_horses/test_generalisation.py:90) and which SciPy >= 1.2 no longer ships (min-max
+    scaled 8-bit greyscale PNG, as the old function wrote)."""
+    install_as_tensorflow()
+    try:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            from scipy import misc
+        if not hasattr(misc, 'imsave'):
+            def imsave(name, arr, format=None):
+                with open(name, 'wb') as f:
+                    f.write(_png_bytes(arr))
+            misc.imsave = imsave
+    except ImportError:
+        pass

@@ -20,7 +20,7 @@ class BGRBM(rbm.RBM):
 
     def __init__(self, num_v, num_h, W_std=0.001, lr=0.001, temperature=None, bottom=None, loss_plotter=None,
                  distr_plotter=None, filter_plotter=None, latent_sample_plotter=None, latent_space_explorer=None,
-                 session=None, name='BGRBM', seed=0, device='cuda'):
+                 session=None, name='BGRBM', seed=None, device='cuda'):
         super().__init__(num_v=num_v, num_h=num_h, W_std=W_std, lr=lr, temperature=temperature, bottom=bottom,
                          loss_plotter=loss_plotter, distr_plotter=distr_plotter, filter_plotter=filter_plotter,
                          latent_sample_plotter=latent_sample_plotter, latent_space_explorer=latent_space_explorer,

@@ -19,7 +19,7 @@ from .layer import to_device
 class BGRBMSV(bgrbm.BGRBM):
     def __init__(self, num_v, num_h, W_std=0.001, lr=0.001, sigma_h_ph=None, temperature=None, bottom=None,
                  loss_plotter=None, distr_plotter=None, filter_plotter=None, latent_sample_plotter=None,
-                 latent_space_explorer=None, session=None, name='BGRBMSV', seed=0, device='cuda'):
+                 latent_space_explorer=None, session=None, name='BGRBMSV', seed=None, device='cuda'):
         self._sigma_fed = sigma_h_ph is not None
         super().__init__(num_v=num_v, num_h=num_h, W_std=W_std, lr=lr, temperature=temperature, bottom=bottom,
                          loss_plotter=loss_plotter, distr_plotter=distr_plotter, filter_plotter=filter_plotter,

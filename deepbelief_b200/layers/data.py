@@ -28,6 +28,7 @@ class _EpochCursor:
         self.num_rows, self.batch_size = num_rows, batch_size
         self.start = 0        # first position of the NEXT window inside `order`
         self.epoch = 0
+        self.random = np.random    # the reference reshuffles with the GLOBAL numpy state (data.py:84-90)
         if shuffle_first:
             np.random.shuffle(self.order)
 
@@ -37,7 +38,7 @@ class _EpochCursor:
         if wrapped:           # drop the tail, start a new shuffled epoch
             self.epoch += 1
             lo, hi = 0, self.batch_size
-            np.random.shuffle(self.order)
+            self.random.shuffle(self.order)
         self.start = hi
         return np.sort(self.order[lo:hi]), wrapped
 
@@ -92,7 +93,30 @@ class Data:
 
         self._cursor = _EpochCursor(self.num_datapoints, self.batch_size, shuffle_first)
         self._pinned = None
+        self._shard = None          # (rank, world, local rows) once shard() has been called
         self.logger.debug(self)
+
+    # ---- data-parallel view (no counterpart in the reference, which is single-process) -----------------------------
+    def shard(self, rank, world, shuffle_seed=None):
+        """Row-shard every batch over `world` data-parallel ranks: the GLOBAL batch is still `batch_size` rows chosen by
+        the reference's rule (sorted rows of the permutation window, tail dropped, reshuffle per epoch), and this rank
+        keeps rows [rank * b, (rank + 1) * b) of it, b = batch_size / world — so N ranks train on exactly the batches
+        one process would see. Every rank must walk the same permutations: epoch reshuffles switch from the global
+        numpy state to a private RandomState(shuffle_seed) (RBM.train broadcasts rank 0's seed)."""
+        rank, world = int(rank), int(world)
+        assert 0 <= rank < world
+        assert self.batch_size % world == 0, 'batch_size %d is not divisible by %d ranks' % (self.batch_size, world)
+        assert not self.has_labels, 'sharding is implemented for unlabelled training data'
+        self._shard = (rank, world, self.batch_size // world)
+        if shuffle_seed is not None:
+            self._cursor.random = np.random.RandomState(int(shuffle_seed) & 0x7fffffff)
+        return self
+
+    def _local(self, rows):
+        if self._shard is None:
+            return rows
+        rank, _, b = self._shard
+        return rows[rank * b:(rank + 1) * b]
 
     @staticmethod
     def _take(arr, rows):
@@ -115,10 +139,11 @@ class Data:
         return self._cursor.order
 
     def batch_shape(self):
-        return self.batch_size, self.datapoint_size
+        return (self._shard[2] if self._shard else self.batch_size), self.datapoint_size
 
     def next_batch(self):
         rows, wrapped = self._cursor.advance()
+        rows = self._local(rows)
         if wrapped and self.log_epochs:
             self.logger.info('Epoch: %d', self._cursor.epoch)
         if self.has_labels:
@@ -131,6 +156,7 @@ class Data:
         (db_host_gather_rows) into `out` (a [batch_size, datapoint_size] float32 array, normally the
         feeder's pinned staging buffer). Returns the array that holds the batch."""
         rows, wrapped = self._cursor.advance()
+        rows = self._local(rows)
         if wrapped and self.log_epochs:
             self.logger.info('Epoch: %d', self._cursor.epoch)
         if len(rows) and int(rows[-1]) - int(rows[0]) + 1 == len(rows):

@@ -10,7 +10,7 @@ class GGRBM(gbrbm.GBRBM, bgrbm.BGRBM):
 
     def __init__(self, num_v, num_h, W_std=0.001, lr=0.001, bottom=None, loss_plotter=None, distr_plotter=None,
                  filter_plotter=None, latent_sample_plotter=None, latent_space_explorer=None, session=None,
-                 name='GGRBM', seed=0, device='cuda'):
+                 name='GGRBM', seed=None, device='cuda'):
         super().__init__(num_v=num_v, num_h=num_h, W_std=W_std, lr=lr, bottom=bottom, loss_plotter=loss_plotter,
                          distr_plotter=distr_plotter, filter_plotter=filter_plotter,
                          latent_sample_plotter=latent_sample_plotter, latent_space_explorer=latent_space_explorer,

@@ -79,6 +79,14 @@ class SEKernel(layer.Stateful):
             return x
         return (x / self.gamma_vec().view(1, -1)).contiguous()
 
+    def scale_into(self, x, out):
+        """scale(x) written into a persistent buffer (ARD): the LML+gradient plan keys its CUDA graphs on the operand
+        addresses, and a fresh temporary per iteration would never be replayed."""
+        if not self.ard:
+            return x
+        torch.div(x, self.gamma_vec().view(1, -1), out=out)
+        return out
+
     def chain_scale(self, dXs, X):
         """(dL/dX, dL/dopt_gamma [Q]) from the gradient with respect to the scaled latents."""
         gam = self.gamma_vec().view(1, -1)
@@ -224,7 +232,12 @@ class GPLVM(layer.Layer):
 
     # ---- model ---------------------------------------------------------------------------------------------------
     def _evaluate(self, want_grad=False, need_factor=False):
-        scal, dX, info = self._plan.evaluate(self.kern.scale(self.X), self.Y, self._hyp, self.flags, fixed_noise=self.fixed_noise,
+        Xs = self.X
+        if self.kern.ard:
+            if getattr(self, '_Xs', None) is None:
+                self._Xs = torch.empty_like(self.X)
+            Xs = self.kern.scale_into(self.X, self._Xs)
+        scal, dX, info = self._plan.evaluate(Xs, self.Y, self._hyp, self.flags, fixed_noise=self.fixed_noise,
                                              jitter=self.noise_jitter or 0.0, x_prior_weight=0.0, include_const=True,
                                              want_grad=want_grad, L_out=self._L if need_factor else None)
         return scal, dX, info
@@ -394,9 +407,16 @@ class GPLVM(layer.Layer):
                 grad[nq:nq + 3].copy_(scal[3:6])
                 ops.optimizer_step(optimizer.descriptor(), self._params, grad, state)
                 self._version += 1
-                if eval_interval and i % eval_interval == 0:
+                at_eval = eval_interval and i % eval_interval == 0
+                at_ckpt = ckpt_dir and ckpt_interval and i % ckpt_interval == 0
+                # the factorisation status is a device scalar: reading it stalls the launch queue, so it is read every
+                # INFO_INTERVAL iterations and before anything is logged or saved (the reference's tf.cholesky raises
+                # InvalidArgumentError at the failing iteration, gplvm.py:212)
+                if at_eval or at_ckpt or i % self.INFO_INTERVAL == 0:
+                    self._raise_if_not_pd()
+                if at_eval:
                     self._eval_step(i)
-                if ckpt_dir and ckpt_interval and i % ckpt_interval == 0:
+                if at_ckpt:
                     self.save_all(i, ckpt_dir)
                     self.kern.save(i, ckpt_dir)
         except KeyboardInterrupt:
@@ -406,6 +426,11 @@ class GPLVM(layer.Layer):
             if ckpt_dir and ckpt_interval:
                 self.save_all(i, ckpt_dir)
                 self.kern.save(i, ckpt_dir)
+        self._raise_if_not_pd()
+
+    INFO_INTERVAL = 32
+
+    def _raise_if_not_pd(self):
         pivot = int(self._plan.info.item())
         if pivot:
             raise RuntimeError('Cholesky decomposition was not successful: pivot %d is not positive' % pivot)

@@ -24,6 +24,7 @@ from .. import _lib as L
 from .. import compat, ops, preprocessing
 from . import bgrbm, gplvm
 from ..replay import ReplayedStep
+from . import layer
 from .layer import to_device, to_numpy
 
 _FLAG_NOISE = 4
@@ -33,7 +34,7 @@ class GPRBM(bgrbm.BGRBM):
     def __init__(self, num_v, num_h, Q, N, eval_flag, X0=None, V=None, Y_labels=None, kern=None, noise_variance=1.0,
                  fixed_noise_variance=False, noise_jitter=1e-6, W_std=0.001, lr=0.001, temperature=None, bottom=None,
                  x_test_var=None, loss_plotter=None, distr_plotter=None, filter_plotter=None, latent_point_plotter=None,
-                 latent_sample_plotter=None, latent_space_explorer=None, session=None, name='GPRBM', seed=0,
+                 latent_sample_plotter=None, latent_space_explorer=None, session=None, name='GPRBM', seed=None,
                  device='cuda'):
         self.Q, self.N, self.D = Q, N, num_h
         self.Y_labels = Y_labels
@@ -130,7 +131,7 @@ class GPRBM(bgrbm.BGRBM):
     def save(self, i, ckpt_dir):
         assert os.path.isdir(ckpt_dir), 'The directory does not exist: %s' % ckpt_dir
         path = os.path.join(ckpt_dir, '%s-%d' % (self.name, i))
-        torch.save({k: v.detach().cpu() for k, v in self.state_tensors().items()}, path)
+        layer.write_checkpoint({k: v.detach().cpu() for k, v in self.state_tensors().items()}, path)
         self.logger.info('State saved')
         return path
 

@@ -27,6 +27,18 @@ def to_numpy(x):
     return np.asarray(x)
 
 
+def write_checkpoint(state, path):
+    """torch.save through a temporary file + rename, from rank 0 only: under torch.distributed every rank holds the same
+    replicated state and would otherwise write the same path concurrently (non-atomic)."""
+    from ..parallel import dist_info
+    if dist_info()[0] != 0:
+        return path
+    tmp = '%s.tmp.%d' % (path, os.getpid())
+    torch.save(state, tmp)
+    os.replace(tmp, path)
+    return path
+
+
 class Stateful:
     def __init__(self, params=None, session=None, name=None):
         self.params = params if params is not None else {}
@@ -67,7 +79,7 @@ class Stateful:
     def save(self, i, ckpt_dir):
         assert os.path.isdir(ckpt_dir), 'The directory does not exist: %s' % ckpt_dir
         ckpt_file = os.path.join(ckpt_dir, '%s-%d' % (self.name, i))
-        torch.save({k: v.detach().cpu() for k, v in self.state_tensors().items()}, ckpt_file)
+        write_checkpoint({k: v.detach().cpu() for k, v in self.state_tensors().items()}, ckpt_file)
         self.logger.info('State saved')
         return ckpt_file
 

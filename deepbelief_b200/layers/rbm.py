@@ -26,6 +26,18 @@ from .layer import to_device, to_numpy
 
 from ..parallel import dist_info as _dist_info, all_reduce_sum_
 
+import itertools
+import zlib
+
+_layer_counter = itertools.count(1)
+
+
+def default_stream(name):
+    """Philox key of a layer constructed without `seed=`: crc32(name) in the high word, the construction index in the low
+    word. Two layers of one stack therefore draw from different streams (TF gives every random op its own stream,
+    rbm.py:202,230), and every rank of a data-parallel job — same script, same construction order — derives the same keys."""
+    return (zlib.crc32(str(name).encode()) << 32) | (next(_layer_counter) & 0xffffffff)
+
 
 # page-locked staging and device batch buffers are kept across train() calls: cudaHostAlloc of a
 # 256 MB buffer costs ~100 ms, far more than a CD step
@@ -205,7 +217,7 @@ class CdGraphStep:
 class RBM(layer.Layer):
     """Binary-binary RBM. Args as the reference: num_v, num_h, W_std=0.1, lr=0.1, temperature=None
     (Concrete units when set), bottom=None, plotters (accepted, may be None), session (ignored), name.
-    Extra keyword `seed` selects the Philox stream."""
+    Extra keyword `seed` selects the Philox stream (default: a stream of its own per layer, see default_stream)."""
 
     layer_kind = L.LAYER_RBM
     visible_act = L.ACT_SIGMOID
@@ -213,7 +225,7 @@ class RBM(layer.Layer):
 
     def __init__(self, num_v, num_h, W_std=0.1, lr=0.1, temperature=None, bottom=None, loss_plotter=None,
                  distr_plotter=None, filter_plotter=None, latent_sample_plotter=None, latent_space_explorer=None,
-                 session=None, name='RBM', seed=0, device='cuda'):
+                 session=None, name='RBM', seed=None, device='cuda'):
         assert isinstance(num_v, int) and num_v > 1
         assert isinstance(num_h, int) and num_h > 1
         self.num_v, self.num_h = num_v, num_h
@@ -222,7 +234,7 @@ class RBM(layer.Layer):
         self.ls_plotter = latent_sample_plotter
         self.latent_space_explorer = latent_space_explorer
         self.device = device
-        self.rng = ops.Rng(seed=seed)
+        self.rng = ops.Rng(seed=default_stream(name) if seed is None else seed)
 
         # one packed buffer [W | b | c | (opt_sigma_h)] so the optimizer / all-reduce see a single array
         n = ops.cd_param_count(self.layer_kind, num_v, num_h)
@@ -263,7 +275,7 @@ class RBM(layer.Layer):
         import os
         assert os.path.isdir(ckpt_dir), 'The directory does not exist: %s' % ckpt_dir
         path = os.path.join(ckpt_dir, '%s-%d' % (self.name, i))
-        torch.save({'params': self._params.detach().cpu(), 'ckpt_iter': self.checkpoint_iter, 'lr': self.lr}, path)
+        layer.write_checkpoint({'params': self._params.detach().cpu(), 'ckpt_iter': self.checkpoint_iter, 'lr': self.lr}, path)
         self.logger.info('State saved')
         return path
 
@@ -605,6 +617,25 @@ class RBM(layer.Layer):
             ops.optimizer_step_range(desc, self._params, grad, opt_state, lo, hi - lo)
         self._weights_version += 1
 
+    def sync_replicas(self, training_data=None):
+        """Data-parallel start-up (no counterpart in the single-process reference): every layer of the stack takes rank
+        0's parameters (the constructors draw W from each process's own numpy state, rbm.py:59-62), and a training set
+        that has not been sharded yet is row-sharded with a shuffle seed broadcast from rank 0 (Data.shard), so that the
+        ranks' batches tile the global batch a single process would have drawn."""
+        import torch.distributed as td
+        rank, world = _dist_info()
+        if world == 1:
+            return
+        for lay in self.layers:
+            td.broadcast(lay._params, 0)
+            lay._after_update()
+        if training_data is not None and hasattr(training_data, 'shard') and getattr(training_data, '_shard', None) is None:
+            seed = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int64, device=self._params.device)
+            td.broadcast(seed, 0)
+            training_data.shard(rank, world, shuffle_seed=int(seed.item()))
+            self.logger.info('training data sharded over %d ranks: %d of the %d rows of each batch on this rank',
+                             world, training_data.batch_shape()[0], training_data.batch_size)
+
     def _tc_plan_for(self, n, k, n_global):
         plan = self._tc_plan
         if plan is None or (plan.N, plan.k, plan.n_global) != (n, k, n_global):
@@ -648,9 +679,12 @@ class RBM(layer.Layer):
         (all-reduced) gradient still on the device — a monitoring hook; the reference has none."""
         rank, world = _dist_info()
         opt_state = self.new_optimizer_state(optimizer)
+        if world > 1:
+            self.sync_replicas(training_data)
         n_local = training_data.batch_shape()[0]
         n_global = n_local * world
-        self.rng.row_offset = rank * n_local            # G-invariant draws (SURVEY §8e)
+        for lay in self.layers:                          # G-invariant draws (SURVEY §8e): the lower layers re-sampled by
+            lay.rng.row_offset = rank * n_local          # bottom.upprop key their draws by the global row as well
         grad = torch.empty_like(self._params)
 
         persistent = None

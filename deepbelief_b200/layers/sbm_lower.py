@@ -15,13 +15,14 @@ import torch
 
 from .. import ops
 from . import rbm
+from . import layer
 from .layer import to_device
 
 
 class SBM_Lower(rbm.RBM):
     def __init__(self, side, side_overlap, num_h, W_std=0.001, lr=0.001, temperature=None, bottom=None,
                  loss_plotter=None, distr_plotter=None, filter_plotter=None, latent_sample_plotter=None,
-                 latent_space_explorer=None, session=None, name='SBM_Lower', seed=0, device='cuda'):
+                 latent_space_explorer=None, session=None, name='SBM_Lower', seed=None, device='cuda'):
         assert num_h % 4 == 0                                   # sbm_lower.py:24-26
         assert side % 2 == 0
         assert side_overlap % 2 == 0
@@ -86,7 +87,7 @@ class SBM_Lower(rbm.RBM):
         import os
         assert os.path.isdir(ckpt_dir), 'The directory does not exist: %s' % ckpt_dir
         path = os.path.join(ckpt_dir, '%s-%d' % (self.name, i))
-        torch.save({'params': self._shared.detach().cpu(), 'ckpt_iter': self.checkpoint_iter, 'lr': self.lr}, path)
+        layer.write_checkpoint({'params': self._shared.detach().cpu(), 'ckpt_iter': self.checkpoint_iter, 'lr': self.lr}, path)
         self.logger.info('State saved')
         return path
 

@@ -20,7 +20,8 @@ sys.path.insert(0, HERE)
 import tf_numpy_shim as shim  # noqa: E402
 
 tf = shim.install()
-sys.path.insert(0, '/root/reference')
+REFERENCE_ROOT = '/root/reference'
+sys.path.insert(0, REFERENCE_ROOT)
 import deepbelief.config as cfg  # noqa: E402
 from deepbelief import dist, preprocessing  # noqa: E402
 from deepbelief.layers import rbm as ref_rbm, bgrbm as ref_bgrbm, gbrbm as ref_gbrbm, ggrbm as ref_ggrbm  # noqa: E402
@@ -613,8 +614,24 @@ def misc_goldens(out):
     out['pre/inv_softplus'] = np.asarray(preprocessing.inverse_softplus(np.array([0.3, 1.0, 2.5])))
 
 
+def reference_example_fixtures():
+    """Byte copies of the reference's own example scripts (flags / train / test_generalisation of the three workflows
+    SURVEY.md section 8b names), stored as `*.py.fixture`: tests/test_gpu_reference_scripts.py runs them UNMODIFIED
+    through `python -m deepbelief_b200.run` (only iteration counts in the flags file are edited). Test inputs, like the
+    bundled .h5 datasets — not product source."""
+    import shutil
+    for ex in ('dbn_horses', 'gplvm_horses', 'gpdbn_horses'):
+        dst = os.path.join(HERE, 'reference_examples', ex)
+        os.makedirs(dst, exist_ok=True)
+        for f in ('flags', 'train', 'test_generalisation'):
+            shutil.copyfile(os.path.join(REFERENCE_ROOT, 'examples', ex, f + '.py'), os.path.join(dst, f + '.py.fixture'))
+        print('copied examples/%s/{flags,train,test_generalisation}.py' % ex)
+
+
 def main():
     only = sys.argv[1:]
+    if not only or 'reference_examples' in only:
+        reference_example_fixtures()
     for fn, name in ((rbm_goldens, 'rbm_golden.npz'), (gp_goldens, 'gp_golden.npz'), (misc_goldens, 'misc_golden.npz'),
                      (gpdbn_goldens, 'gpdbn_golden.npz'), (backprop_goldens, 'backprop_golden.npz'), (sbm_goldens, 'sbm_golden.npz'),
                      (latent_goldens, 'latent_golden.npz'), (ard_goldens, 'ard_golden.npz')):

@@ -201,10 +201,11 @@ def test_config4_size_properties():
     assert np.isfinite(float(loss2))
 
 
-def test_config4_layer_sizes_vs_oracle():
-    """The config-4 layer sizes (784->200->100->50, T=0.1, noise 0.01 fixed: cond(K) ~ 1e4) at N=1200, where the fp64
-    oracle takes seconds: every gradient array against the oracle."""
-    N = 1200
+@pytest.mark.parametrize('N', [1200, 5000])
+def test_config4_layer_sizes_vs_oracle(N):
+    """The config-4 stack (784->200->100->50, T=0.1, noise 0.01 fixed: cond(K) ~ 1e4-1e5) at N=1200 and at the FULL
+    BASELINE size N=5000 (the fp64 numpy oracle needs ~20 s there): loss pieces and every gradient array against
+    the oracle."""
     top, (l0, l1), V, draws = _config4_stack(N, seed=3)
     loss, pieces = top.loss_and_grads(draws=draws)
     cpu = lambda t: t.detach().cpu().numpy().astype(np.float64)  # noqa: E731

@@ -403,6 +403,72 @@ def test_full_size_config5_properties():
     assert _normrel(gW, gb[:, None] * sig(c.astype(np.float32).astype(np.float64))[None, :]) < 3e-5
 
 
+def test_full_size_config5_sampled_rows_vs_fp64_oracle():
+    """BASELINE config 5 at its own size (N=16384, V=4096, H=8192) with W ~ N(0, 0.01^2) — the accumulation depth
+    (K = 4096 / 8192 chain, K = 2N = 32768 dW), the 2^e weight scaling and the fp16 hi/lo split the metric runs on.
+    Rows of the chain are independent given (W, b, c) (rbm.py:628-646), so a SAMPLED set of 128 rows is followed
+    through the whole CD-1 chain by the fp64 oracle with margin uniforms injected for exactly those rows (every other
+    row draws plain random uniforms): h0 probabilities 1e-5, v1 / h1 states bit-exact, hk probabilities 1e-5. dW is
+    checked on a sampled 64 x 64 block (4096 entries) computed in fp64 from the chain ends of ALL 16384 rows
+    (K = 32768 deep) at 1e-4 of max|dW|, and db / dc in full."""
+    from deepbelief_b200 import ops
+    N, V, H, k = 16384, 4096, 8192, 1
+    R = 128
+    rs = np.random.RandomState(55)
+    W = (rs.normal(size=(V, H)) * 0.01).astype(np.float32)
+    b = (rs.normal(size=V) * 0.1).astype(np.float32)
+    c = (rs.normal(size=H) * 0.1).astype(np.float32)
+    gen = torch.Generator(device='cuda').manual_seed(0)
+    v0 = (torch.rand(N, V, device='cuda', generator=gen) < 0.5).float()
+    rows = np.sort(rs.choice(N, size=R, replace=False))
+    rows_t = torch.as_tensor(rows, device='cuda')
+    v0_rows = v0[rows_t].cpu().numpy().astype(np.float64)
+    orc = orbm.RBMOracle(W, b, c)                                   # fp64 ground truth of the sampled rows
+    u0, chain, _ = _margin_uniforms(orc, v0_rows, k, rs)
+    ref = orbm.cd_k(orc, v0_rows, k, u0, chain)
+    # injected draws for the whole batch: [U_h0 | U_v1 | U_h1], sampled rows overwritten with the margin uniforms
+    NH, NV = N * H, N * V
+    inj = torch.rand(NH + k * (NV + NH), device='cuda', generator=gen)
+    inj[:NH].view(N, H)[rows_t] = torch.as_tensor(u0.astype(np.float32)).cuda()
+    inj[NH:NH + NV].view(N, V)[rows_t] = torch.as_tensor(chain[0][0].astype(np.float32)).cuda()
+    inj[NH + NV:].view(N, H)[rows_t] = torch.as_tensor(chain[0][1].astype(np.float32)).cuda()
+    params = torch.as_tensor(np.concatenate([W.ravel(), b, c])).cuda()
+    plan = ops.CdTcPlan(N, V, H, k)
+    plan.refresh_weights(params)
+    grad = torch.zeros_like(params)
+    vk, hk = torch.empty(N, V, device='cuda'), torch.empty(N, H, device='cuda')
+    p0, pk = torch.empty(N, H, device='cuda'), torch.empty(N, H, device='cuda')
+    plan.step(v0, params, grad, injected=inj, vk_out=vk, hk_out=hk, p0_out=p0, pk_out=pk)
+    torch.cuda.synchronize()
+    del inj
+    # ---- the sampled rows against the oracle ----
+    np.testing.assert_allclose(_np(p0[rows_t]), ref['h0_probs'], rtol=PROB_RTOL)
+    np.testing.assert_array_equal(_np(vk[rows_t]), ref['vk'])            # bit-exact states (margin 1e-4)
+    np.testing.assert_array_equal(_np(hk[rows_t]), ref['hk'])
+    np.testing.assert_allclose(_np(pk[rows_t]), ref['hk_probs'], rtol=PROB_RTOL)
+    assert torch.all((vk == 0) | (vk == 1)) and torch.all((hk == 0) | (hk == 1))
+    # ---- gradient: sampled dW block in fp64 over all N rows (chain ends taken from the device, verified above on
+    # the sampled rows), db and dc in full ----
+    vs = np.sort(rs.choice(V, size=64, replace=False))
+    hs = np.sort(rs.choice(H, size=64, replace=False))
+    vs_t, hs_t = torch.as_tensor(vs, device='cuda'), torch.as_tensor(hs, device='cuda')
+    v0s, vks = _np(v0[:, vs_t]), _np(vk[:, vs_t])
+    p0s, pks = _np(p0[:, hs_t]), _np(pk[:, hs_t])
+    want_dW = -(v0s.T @ p0s - vks.T @ pks) / N                          # SURVEY.md section 8 R9
+    g = grad
+    got_dW = _np(g[:V * H].view(V, H)[vs_t][:, hs_t])
+    scale = float(g[:V * H].abs().max())
+    err_dW = np.max(np.abs(got_dW - want_dW)) / scale
+    assert err_dW < GRAD_NORMREL, err_dW
+    want_db = -(_np(v0.double().mean(0)) - _np(vk.double().mean(0)))
+    want_dc = -(_np(p0.double().mean(0)) - _np(pk.double().mean(0)))
+    assert _normrel(_np(g[V * H:V * H + V]), want_db) < GRAD_NORMREL
+    assert _normrel(_np(g[V * H + V:]), want_dc) < GRAD_NORMREL
+    print('config-5 parity: p0 %.2e pk %.2e dW(4096 entries) %.2e of max|dW| %.3g' % (
+        np.max(np.abs(_np(p0[rows_t]) - ref['h0_probs']) / ref['h0_probs']),
+        np.max(np.abs(_np(pk[rows_t]) - ref['hk_probs']) / ref['hk_probs']), err_dW, scale))
+
+
 @pytest.mark.parametrize('cname', ['concrete', 'prob'])
 def test_backprop_gradients_vs_oracle(cname):
     """RBM.backprop's loss and gradient (rbm.py:739-758) on a two-layer stack against the reference-pinned oracle."""

@@ -90,3 +90,35 @@ def test_philox_known_answer_and_row_sharding():
     np.testing.assert_array_equal(philox.uniform(32, 40, seed=7, draw=3, row_offset=32), u[32:])
     n = philox.normal(512, 64, seed=1, draw=0)
     assert abs(n.mean()) < 0.02 and abs(n.std() - 1.0) < 0.02
+
+
+def test_data_shard_tiles_the_global_batch():
+    """Data.shard (data-parallel view): the ranks' batches are the consecutive row blocks of the batch one process
+    draws (sorted rows, tail dropped, reshuffle per epoch — data.py:84-94), through several epochs."""
+    from deepbelief_b200.layers.data import Data
+    rs = np.random.RandomState(3)
+    arr = rs.normal(size=(50, 7)).astype(np.float32)
+    world, bs = 4, 16
+    one = Data.from_arrays(arr, batch_size=bs, log_epochs=False, pin=False)
+    one._cursor.random = np.random.RandomState(77)
+    shards = [Data.from_arrays(arr, batch_size=bs, log_epochs=False, pin=False).shard(r, world, shuffle_seed=77) for r in range(world)]
+    assert shards[0].batch_shape() == (bs // world, 7) and one.batch_shape() == (bs, 7)
+    staging = np.empty((bs // world, 7), np.float32)
+    for it in range(11):                                       # 3 batches per epoch: crosses epoch boundaries
+        want = one.next_batch()
+        got = [s.next_batch() if it % 2 else np.array(s.next_batch_into(staging)) for s in shards]
+        np.testing.assert_array_equal(np.concatenate(got), want)
+    assert one.epoch == shards[0].epoch == 3
+    try:
+        Data.from_arrays(arr, batch_size=10, pin=False).shard(0, 4)
+        assert False
+    except AssertionError:
+        pass
+
+
+def test_layers_get_distinct_default_streams():
+    """layers built without seed= must not share one Philox stream; explicit seeds are kept."""
+    from deepbelief_b200.layers import rbm
+    a, b = rbm.default_stream('BBRBM-200'), rbm.default_stream('BBRBM-200-100')
+    c = rbm.default_stream('BBRBM-200')
+    assert len({a, b, c}) == 3 and (a >> 32) == (c >> 32) != (b >> 32)
