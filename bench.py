@@ -94,6 +94,42 @@ class ClockSampler:
                 'samples': len(sm), 'power_w_max': power or None}
 
 
+def count_kernel_launches(fn):
+    """Kernels launched on the device by fn() (one untimed call under the CUPTI-backed torch profiler), or None."""
+    try:
+        import torch
+        from torch.profiler import profile, ProfilerActivity
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        names = [e.name for e in prof.events() if getattr(e, 'device_type', None) is not None and 'CUDA' in str(e.device_type)
+                 and not e.name.lower().startswith(('memcpy', 'memset'))]
+        return len(names), sorted(set(names))
+    except Exception:
+        return None
+
+
+def ncu_dram_bytes(csv_name, kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the first launch of a kernel in a committed `ncu --page raw --csv` file"""
+    import csv
+    path = os.path.join(ROOT, 'profiles', csv_name)
+    if not os.path.exists(path):
+        return None
+    mult = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    with open(path, newline='') as f:
+        rows = list(csv.reader(f))
+    head, units = rows[0], rows[1]
+    try:
+        ir, iw, ik = head.index('dram__bytes_read.sum'), head.index('dram__bytes_write.sum'), head.index('Kernel Name')
+    except ValueError:
+        return None
+    for r in rows[2:]:
+        if kernel_substr in r[ik]:
+            return float(r[ir].replace(',', '')) * mult.get(units[ir], 1.0) + float(r[iw].replace(',', '')) * mult.get(units[iw], 1.0)
+    return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -105,11 +141,52 @@ def load_peaks():
 
 
 # ---------------------------------------------------------------------------------------------------------
-# CPU side: the oracle port of one CD-k step (reference arm and cpu_baseline)
+# CPU side (SURVEY.md 8d "CPU side-by-side"): the reference's step restated with torch-CPU ops on all host threads
+# (oracle/torch_port.py, pinned to the numpy oracle by tests/test_oracle_torch_port.py); the numpy oracle stays as a
+# second, slower point of comparison. TensorFlow 1.8 is not installable here (DESIGN.md "Oracle").
 # ---------------------------------------------------------------------------------------------------------
-def cpu_cd_steps(n_rows, steps, warmup):
-    """CD-10 + Adam on `n_rows` rows of the workload with the numpy oracle (fp32), all host threads via BLAS.
-    Returns (seconds per step, cores)."""
+CPU_ROWS = 512          # rows of the 16384-row batch one CPU step processes (bounded sample; stated in every CPU line)
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must use every core it can (BLAS pools read the
+    variables at import, torch takes the explicit call)."""
+    n = host_threads()
+    for var in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OPENBLAS_NUM_THREADS'):
+        os.environ[var] = str(n)
+    import torch
+    torch.set_num_threads(n)
+    return n
+
+
+def cpu_cd_steps_torch(n_rows, steps, warmup):
+    """CD-10 + Adam on `n_rows` rows of the workload: torch.matmul (MKL sgemm), sigmoid, torch.rand draws inside the step
+    (the counterpart of tf.random_uniform in the graph, rbm.py:202,230), closed-form gradient, Adam. -> (s/step, threads)"""
+    import torch
+    from oracle import torch_port
+    threads = use_all_host_threads()
+    g = torch.Generator().manual_seed(0)
+    port = torch_port.CdStepTorch(torch.randn(V, H, generator=g) * 0.01, torch.zeros(V), torch.zeros(H), lr=1e-3)
+    v0 = (torch.rand(n_rows, V, generator=g) < 0.5).float()
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        port.step(v0, K_GIBBS, generator=g)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), threads
+
+
+def cpu_cd_steps_numpy(n_rows, steps, warmup):
+    """The same step with the numpy oracle (oracle/rbm.py, fp32, BLAS threads). -> (s/step, threads)"""
+    threads = use_all_host_threads()
     import numpy as np
     from oracle import rbm as orbm
     rs = np.random.RandomState(0)
@@ -120,7 +197,6 @@ def cpu_cd_steps(n_rows, steps, warmup):
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        # the reference draws its uniforms inside the graph (tf.random_uniform, rbm.py:202,230): part of the step
         draw_h0 = rs.random_sample((n_rows, H)).astype(np.float32)
         chain = [(rs.random_sample((n_rows, V)).astype(np.float32), rs.random_sample((n_rows, H)).astype(np.float32))
                  for _ in range(K_GIBBS)]
@@ -131,25 +207,52 @@ def cpu_cd_steps(n_rows, steps, warmup):
         model.c = theta[V * H + V:].reshape(1, H)
         if it >= warmup:
             times.append(time.perf_counter() - t0)
-    return sum(times) / len(times), os.cpu_count()
+    return sum(times) / len(times), threads
+
+
+def cpu_gplvm_evals(evals, warmup, n=GP_N):
+    """GPLVM loss + gradient at N = n, D = 784, Q = 2 in fp32 with torch-CPU ops: expanded-distance Gram, linalg.cholesky,
+    solve_triangular, autograd (what TF differentiated, gplvm.py:210-244, 425-428). -> (s/eval, threads)"""
+    import numpy as np
+    from oracle import torch_port
+    threads = use_all_host_threads()
+    rs = np.random.RandomState(0)
+    X = rs.normal(size=(n, GP_Q)).astype(np.float32)
+    Y = (rs.uniform(size=(n, GP_D)) < 0.13).astype(np.float32)
+    Y -= Y.mean(axis=0, keepdims=True)
+    isp = float(np.log(np.expm1(1.0)))
+    times = []
+    for it in range(warmup + evals):
+        t0 = time.perf_counter()
+        torch_port.gplvm_loss_and_grad(X, Y, isp, isp, isp, jitter=1e-6)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), threads
+
+
+def cd_cpu_sample_text(n_rows):
+    return ('CD-10 + Adam(1e-3) on %d of the %d rows of the 4096x8192 workload per step (the 33.6 M-parameter Adam update is '
+            'paid in full every step)' % (n_rows, N_GLOBAL))
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
-    n_rows = 512
-    sec, cores = cpu_cd_steps(n_rows, args.steps, args.warmup)
+    n_rows = CPU_ROWS
+    sec, cores = cpu_cd_steps_torch(n_rows, args.steps, args.warmup)
     value = n_rows * K_GIBBS / sec
-    sample = 'CD-10 + Adam on %d rows of the 4096x8192 workload per step (oracle port, numpy fp32)' % n_rows
+    sample = cd_cpu_sample_text(n_rows) + '; torch-CPU fp32 restatement of the reference graph (oracle/torch_port.py), all host threads'
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'strong',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': CONFIG,
-            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': dict(CONFIG, cpu_rows_per_step=n_rows, cpu_threads=cores),
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port-torch', 'sample': sample,
+                             'tflops': cd_flops(n_rows) / sec / 1e12},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0,
-            'note': 'TensorFlow 1.8 is not installable here; this is the numpy restatement pinned by goldens '
-                    'generated from the reference sources (oracle/__init__.py)'}
+            'note': 'TensorFlow 1.8 is not installable here; this is the torch-CPU restatement of the reference graph, pinned to '
+                    'the numpy oracle, itself pinned by goldens generated from the reference sources (oracle/__init__.py)'}
     print(json.dumps(line))
     return 0
 
@@ -233,7 +336,13 @@ def run_b200(args):
     chain_ms = parallel.max_over_ranks(chain_ms, device=dev)
     ms_per_step = ms_total / K
     value = N_GLOBAL * K_GIBBS / (ms_per_step * 1e-3)
-    launches_per_step = rbm.launches_per_cd_step(K_GIBBS) + 1 + 4      # chain + optimizer + weight refresh (4 kernels)
+    counted = count_kernel_launches(lambda: one_step(0))               # one extra untimed step under the profiler
+    if counted is not None:
+        launches_per_step, launch_names = counted
+        launches_how = 'counted: kernels of one step under torch.profiler (CUPTI), x steps'
+    else:
+        launches_per_step, launch_names = rbm.launches_per_cd_step(K_GIBBS) + 2, None
+        launches_how = 'formula (profiler unavailable): chain + dW + bias/optimizer kernels'
     del opt_state
 
     # ---- e2e: through RBM.train, batches in pinned host memory ----
@@ -318,11 +427,37 @@ def run_b200(args):
     gram_us = g0.elapsed_time(g1) / 30 * 1e3
     gram_gbs = (4.0 * GP_N * GP_N + 4.0 * GP_N * GP_Q) / 1e9 / (gram_us * 1e-6)
     gp_flop = float(GP_N) ** 3 + 3.0 * GP_N * GP_N * GP_D
+    gram_traffic = ncu_dram_bytes('r01_gram_full_raw.csv', 'gram_kernel')
+
+    # GPLVM end to end through the layer API (gplvm.py:414-468): Y and X0 come from HOST memory into the constructor, the
+    # optimisation loop runs `gp_e2e_iters` iterations (LML+grad + Adam on {X, hyper-parameters}), the final loss is read back
+    del gplan
+    torch.cuda.empty_cache()
+    from deepbelief_b200.layers.gplvm import GPLVM
+    Y_host = (gY + 0.0).cpu().numpy()
+    X_host = gX.cpu().numpy()
+    gp_e2e_iters = 20
+
+    def gplvm_e2e():
+        m = GPLVM(Y_host, GP_Q, X0=X_host, name='bench_gplvm', device=dev)
+        m.optimize(compat.AdamOptimizer(learning_rate=1e-3), num_iterations=gp_e2e_iters)
+        return float(m.loss_and_grad()[0].item())
+
+    gplvm_e2e()                                                       # warm-up (allocator, graph capture path)
+    barrier()
+    t_a = time.perf_counter()
+    e0.record()
+    gp_e2e_loss = gplvm_e2e()
+    e1.record()
+    barrier()
+    t_b = time.perf_counter()
+    windows.append((t_a, t_b))
+    gp_e2e_ms = parallel.max_over_ranks(e0.elapsed_time(e1), device=dev) / (gp_e2e_iters + 1)
 
     # ---- GPDBN (BASELINE configs[3]): synthetic binary 5000x784, stack 784->200->100->GPRBM(50), Q=2, T=0.1 ----
     gpdbn = None
     if world == 1:
-        del gplan, gX, gY
+        del gX, gY
         torch.cuda.empty_cache()
         from deepbelief_b200.layers.gprbm import GPRBM
         from deepbelief_b200.layers.gplvm import SEKernel
@@ -355,14 +490,22 @@ def run_b200(args):
         sampler.stop()
         clocks = sampler.summary(windows)
 
-    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same step with the oracle port ----
+    # ---- CPU baselines (rank 0, N=1 only): bounded samples of the same steps, torch-CPU ops on all host threads ----
     cpu = None
+    gp_cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        n_rows = 512
-        sec, cores = cpu_cd_steps(n_rows, steps=2, warmup=1)
-        cpu = {'value': n_rows * K_GIBBS / sec, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-               'sample': 'CD-10 + Adam on %d rows of the 4096x8192 workload, 2 timed steps after 1 warm-up '
-                         '(oracle port, numpy fp32, BLAS threads)' % n_rows}
+        sec, cores = cpu_cd_steps_torch(CPU_ROWS, steps=3, warmup=1)
+        sec_np, _ = cpu_cd_steps_numpy(CPU_ROWS, steps=1, warmup=1)
+        cpu = {'value': CPU_ROWS * K_GIBBS / sec, 'unit': UNIT, 'cores': cores, 'kind': 'port-torch',
+               'sample': cd_cpu_sample_text(CPU_ROWS) + ', 3 timed steps after 1 warm-up; torch-CPU fp32 (MKL sgemm) restatement, '
+                         'oracle/torch_port.py',
+               'tflops': cd_flops(CPU_ROWS) / sec / 1e12,
+               'numpy_port': {'value': CPU_ROWS * K_GIBBS / sec_np, 'unit': UNIT, 'kind': 'port',
+                              'sample': 'same step with the numpy oracle (oracle/rbm.py), 1 timed step'}}
+        gsec, gcores = cpu_gplvm_evals(evals=2, warmup=1)
+        gp_cpu = {'value': 1.0 / gsec, 'unit': 'evals/s', 'cores': gcores, 'kind': 'port-torch', 'ms_per_eval': gsec * 1e3,
+                  'sample': 'the full N=5000, D=784, Q=2 evaluation (not a sub-sample), 2 timed evaluations after 1 warm-up: '
+                            'torch-CPU fp32 Gram + linalg.cholesky + solve_triangular + autograd (oracle/torch_port.py)'}
 
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'r01_tc_gemm_traffic.json')
@@ -382,6 +525,7 @@ def run_b200(args):
                     'd2h_bytes_per_step': 4, 'api': 'RBM.train(AdamOptimizer, Data.from_arrays(pinned host), '
                     'num_gibbs_steps=10, pcd=False)', 'monitor_last': monitor[-1] if monitor else None},
             'gpu_launches': launches_per_step * K,
+            'gpu_launches_how': launches_how, 'gpu_launch_kernels': launch_names,
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                          'frac': achieved / peak, 'traffic': traffic,
                          'traffic_unit': 'bytes per tc_gemm_kernel launch (ncu dram read+write, profiles/r01_tc_gemm_traffic.json)',
@@ -403,17 +547,28 @@ def run_b200(args):
             'gplvm': {'metric': 'GPLVM LML+grad evals/s at N=5000', 'value': world * 1e3 / gp_ms, 'unit': 'evals/s',
                       'ms_per_eval': gp_ms, 'N': GP_N, 'D': GP_D, 'Q': GP_Q, 'info': gp_info, 'scaling': 'replicas only',
                       'algorithmic_tflops': gp_flop / (gp_ms * 1e-3) / 1e12,
-                      # N^3 + 3 N^2 D algorithmic FLOP against the fp32 FFMA peak that bounds the reference's
-                      # formulation (148 SMs x 128 FMA x 2 x max SM clock); the N^3-class stages run as 3xTF32 tcgen05 GEMMs
-                      'roofline': {'bound': 'fp32-ffma', 'achieved': gp_flop / (gp_ms * 1e-3) / 1e12,
-                                   'peak': 148 * 128 * 2 * 1.965e9 / 1e12, 'unit': 'TFLOP/s',
-                                   'frac': gp_flop / (gp_ms * 1e-3) / (148 * 128 * 2 * 1.965e9),
-                                   'note': 'latency-bound Cholesky critical path: 79 column-block steps of 16 us (DESIGN.md K4)'},
+                      # N^3 + 3 N^2 D algorithmic FLOP against the TF32 tensor peak north_star names = half the
+                      # measured sustained bf16 rate (kind::tf32 runs at half the 16-bit rate); the N^3-class stages run as 3xTF32
+                      # tcgen05 GEMMs, i.e. the tensor pipe executes ~3x the algorithmic product FLOP
+                      'roofline': {'bound': 'tensor', 'achieved': gp_flop / (gp_ms * 1e-3) / 1e12,
+                                   'peak': 0.5 * peaks['tensor_sustained'], 'unit': 'TFLOP/s',
+                                   'frac': gp_flop / (gp_ms * 1e-3) / 1e12 / (0.5 * peaks['tensor_sustained']),
+                                   'peak_source': '0.5 x MEASURED_PEAKS.json bf16 sustained (%s) = TF32 dense' % peaks['source'],
+                                   'frac_of_fp32_ffma_peak': gp_flop / (gp_ms * 1e-3) / (148 * 128 * 2 * 1.965e9),
+                                   'note': 'whole evaluation (Gram, Cholesky, triangular inverse, K^-1, K^-1 Y, A A^T, contraction), '
+                                           'not one kernel; see profiles/ for the per-kernel shares'},
+                      'e2e': {'value': world * 1e3 / gp_e2e_ms, 'unit': 'evals/s', 'ms_per_eval': gp_e2e_ms,
+                              'api': 'GPLVM(Y_host, Q, X0=X_host) + GPLVM.optimize(AdamOptimizer, num_iterations=%d) + loss read-back; '
+                                     'the constructor (host->device copy of Y and X0, workspace allocation) is inside the timed region and '
+                                     'amortised over the %d evaluations' % (gp_e2e_iters, gp_e2e_iters + 1),
+                              'h2d_bytes_per_eval': (GP_N * GP_D + GP_N * GP_Q) * 4 / (gp_e2e_iters + 1), 'd2h_bytes_per_eval': 4 / (gp_e2e_iters + 1),
+                              'final_loss': gp_e2e_loss},
+                      'cpu_baseline': gp_cpu,
                       'gram': {'kernel': 'gram_kernel<2>', 'us_per_launch': gram_us,
                                'roofline': {'bound': 'hbm', 'achieved': gram_gbs, 'peak': load_peaks()['hbm_gbs'], 'unit': 'GB/s',
                                             'frac': gram_gbs / load_peaks()['hbm_gbs'],
-                                            'traffic': 42781696.0,
-                                            'traffic_note': 'dram read+write inside the kernel (profiles/r01_gram_full_raw.csv); the '
+                                            'traffic': gram_traffic,
+                                            'traffic_note': 'dram read+write inside the kernel, read from profiles/r01_gram_full_raw.csv; the '
                                                             '126 MB L2 absorbs the rest of the 100 MB it writes'}}},
             'gpdbn': gpdbn,
         }

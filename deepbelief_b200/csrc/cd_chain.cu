@@ -45,11 +45,16 @@ inline WeightCacheView weight_cache_view(void* cache, int V, int H) {
   return v;
 }
 
-// K chunk of the dW GEMM: at most 4096 columns (= 512 accumulation steps over hi+lo) per TMEM
-// accumulator, at most 8 chunks; partial products are summed in fp32 by dw_reduce_kernel.
+// The dW GEMM runs over its whole K = 2 NP range in one work item per tile (gemm_tc.cu promotes the TMEM accumulator into
+// fp32 registers every 512 columns, so depth costs no accuracy and no partial tiles go through HBM). Only when the
+// [H, V] result has too few 128 x 256 tiles to occupy the GPU is the K range cut into up to 8 independent ranges of
+// >= 4096 columns whose partial products dw_reduce_kernel sums in a fixed order.
 constexpr int kDwChunk = 4096;
 constexpr int kDwMaxSplits = 8;
-inline int dw_splits(int ldT) {
+constexpr int kDwEnoughTiles = 96;
+inline int dw_splits(int ldT, int V, int H) {
+  const int tiles = ((H + 127) / 128) * ((V + 255) / 256);
+  if (tiles >= kDwEnoughTiles) return 1;
   int s = (ldT + kDwChunk - 1) / kDwChunk;
   return s < 1 ? 1 : (s > kDwMaxSplits ? kDwMaxSplits : s);
 }
@@ -71,7 +76,7 @@ inline ChainWorkspace chain_workspace(void* ws, int N, int V, int H) {
   w.vt = reinterpret_cast<__half*>(p); p += align256((size_t)V * 2 * w.NP * 2);
   w.pt_hi = reinterpret_cast<__half*>(p); p += align256((size_t)H * 2 * w.NP * 2);
   w.pt_lo = reinterpret_cast<__half*>(p); p += align256((size_t)H * 2 * w.NP * 2);
-  w.splits = dw_splits(2 * w.NP);
+  w.splits = dw_splits(2 * w.NP, V, H);
   w.dw_part = reinterpret_cast<float*>(p);
   if (w.splits > 1) p += align256((size_t)w.splits * V * H * sizeof(float));
   w.bytes = (size_t)(p - p0);

@@ -11,17 +11,27 @@
 // in fp16 (>= 22 significant bits), two kind::f16 MMA passes accumulate into the same TMEM tile.
 // That is fp32-level accuracy at 2 fp16 passes = the cost of ONE TF32 pass (fp16 runs at 2x TF32).
 //
-// Roles (256 threads, 1 CTA/SM, persistent over tiles):
-//   warp 0   : TMA producer   (A_hi, A_lo, B tiles -> 128B-swizzled smem ring, mbarrier complete_tx)
-//   warp 1   : MMA issuer     (one elected thread: tcgen05.mma, tcgen05.commit)
-//   warp 2   : TMEM allocator (512 columns = 2 accumulator stages of 128x256 fp32)
-//   warps 4-7: epilogue       (tcgen05.ld -> scale+bias -> logistic -> Philox/injected uniform ->
-//                              compare -> global stores), overlapped with the next tile's MMAs.
+// Accumulation: the tensor core adds into its fp32 TMEM accumulator with truncation toward zero, a bias that
+// grows with the number of adds (measured against fp64 on the pre-activation of a 4096 / 8192-deep layer: mean
+// 4e-6 / 8e-6 toward zero, probabilities off by up to 1.3e-5 / 3.5e-5 relative — outside the 1e-5 the path must hold).
+// K is therefore cut into chunks of kb_chunk k-blocks (512 columns): each chunk accumulates in one of the two TMEM
+// stages and is then PROMOTED — added in fp32 round-to-nearest into registers of the epilogue threads (128 partial
+// sums per thread) — while the next chunk runs in the other stage. The same mechanism lets the dW product run over
+// its whole K = 2 x batch range in one work item (no split-K partial tiles in HBM).
+//
+// Roles (384 threads, 1 CTA/SM, persistent over tiles; setmaxnreg moves registers from warps 0-3 to the epilogue):
+//   warp 0    : TMA producer   (A_hi, A_lo, B tiles -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1    : MMA issuer     (one elected thread: tcgen05.mma, tcgen05.commit)
+//   warp 2    : TMEM allocator (512 columns = 2 chunk accumulators of 128x256 fp32)
+//   warps 4-11: epilogue       (per chunk: tcgen05.ld + add; per tile: scale+bias -> logistic -> Philox/injected
+//                               uniform -> compare -> global stores), overlapped with the next tile's MMAs.
+//                               Warp w owns TMEM lanes 32 (w % 4) .. +32 and the column half (w - 4) / 4 of the tile.
 #include "gemm_tc.cuh"
 #include "ptx.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <cstdlib>
 
 namespace db {
 
@@ -37,8 +47,11 @@ constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KB
 constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + B_TILE_BYTES;   // 64 KB
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;       // 512
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
+constexpr int EPI_THREADS = 256;       // warps 4-11
+constexpr int KB_CHUNK = 8;            // k-blocks per TMEM accumulation chunk (512 columns = 64 truncating adds over hi + lo)
+constexpr int REGS_EPI = 216, REGS_CTRL = 40;   // 256 x 216 + 128 x 40 = 60416 <= 65536
 constexpr int GROUP_M = 8;
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
@@ -74,6 +87,106 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// One 32-column slice of the tile, values in registers (val[j] = accumulator of column nb0 + j for row m of D):
+// scale + bias -> logistic -> sample -> the requested outputs.
+__device__ __forceinline__ void epilogue_slice(const TcGemmParams& p, float (&val)[32], int nb0, int m, bool m_ok, float bias_m,
+                                               float acc_scale, float* __restrict__ out32) {
+  const float inv_pT = p.pT_scale;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float x = fmaf(val[j], acc_scale, bias_m);
+    val[j] = p.act ? __fdividef(1.0f, 1.0f + __expf(-x)) : x;
+  }
+
+  uint32_t sbits = 0;
+  if (p.sample) {
+    if (p.U != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int nb = nb0 + j;
+        float u = (m_ok && nb < p.Nb) ? __ldg(p.U + (size_t)nb * p.ldu + m) : 2.0f;
+        sbits |= (val[j] > u ? 1u : 0u) << j;
+      }
+    } else {
+      const uint32_t grow0 = p.rng.row_offset + (uint32_t)nb0;   // multiple of 4 by construction
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        Philox4 o = philox4x32_10((uint32_t)m, (grow0 >> 2) + q, p.rng.draw_lo, p.rng.draw_hi,
+                                  p.rng.seed_lo, p.rng.seed_hi);
+        sbits |= (val[4 * q + 0] > u32_to_uniform(o.x) ? 1u : 0u) << (4 * q + 0);
+        sbits |= (val[4 * q + 1] > u32_to_uniform(o.y) ? 1u : 0u) << (4 * q + 1);
+        sbits |= (val[4 * q + 2] > u32_to_uniform(o.z) ? 1u : 0u) << (4 * q + 2);
+        sbits |= (val[4 * q + 3] > u32_to_uniform(o.w) ? 1u : 0u) << (4 * q + 3);
+      }
+    }
+  }
+
+  // ---- [Nb, Ma] outputs: for fixed j the 32 lanes write 32 consecutive units ----
+  if (out32 != nullptr && m_ok) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (nb0 + j < p.Nb) out32[(size_t)(nb0 + j) * p.ld32 + m] = val[j];
+  }
+  if (p.out_s16 != nullptr && m_ok) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (nb0 + j < p.Nb) {
+        float s = p.sample ? (float)((sbits >> j) & 1u) : val[j];
+        p.out_s16[(size_t)(nb0 + j) * p.lds16 + m] = __float2half_rn(s);
+      }
+  }
+  // ---- [Ma, Nb] "T" outputs: each thread owns 32 consecutive columns of its row ----
+  const bool full_chunk = nb0 + 32 <= p.Nb;
+  if (p.out_sT16 != nullptr && m_ok) {
+    __half* dst = p.out_sT16 + (size_t)m * p.ldsT + tc_interleaved_col(nb0, p.sT_phase);
+    if (full_chunk) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 v;
+        uint32_t b = sbits >> (8 * g);
+        v.x = pack_h2((float)(b & 1u), (float)((b >> 1) & 1u));
+        v.y = pack_h2((float)((b >> 2) & 1u), (float)((b >> 3) & 1u));
+        v.z = pack_h2((float)((b >> 4) & 1u), (float)((b >> 5) & 1u));
+        v.w = pack_h2((float)((b >> 6) & 1u), (float)((b >> 7) & 1u));
+        reinterpret_cast<uint4*>(dst)[g] = v;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (nb0 + j < p.Nb) dst[j] = __float2half_rn((float)((sbits >> j) & 1u));
+    }
+  }
+  if (p.out_pT_hi != nullptr && m_ok) {
+    __half* dhi = p.out_pT_hi + (size_t)m * p.ldpT + tc_interleaved_col(nb0, p.pT_phase);
+    __half* dlo = p.out_pT_lo + (size_t)m * p.ldpT + tc_interleaved_col(nb0, p.pT_phase);
+    if (full_chunk) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __half h0, l0, h1, l1;
+          split_f16(val[8 * g + 2 * e] * inv_pT, h0, l0);
+          split_f16(val[8 * g + 2 * e + 1] * inv_pT, h1, l1);
+          __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+          hi[e] = *reinterpret_cast<uint32_t*>(&hh);
+          lo[e] = *reinterpret_cast<uint32_t*>(&ll);
+        }
+        reinterpret_cast<uint4*>(dhi)[g] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        reinterpret_cast<uint4*>(dlo)[g] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (nb0 + j < p.Nb) {
+          __half h0, l0;
+          split_f16(val[j] * inv_pT, h0, l0);
+          dhi[j] = h0; dlo[j] = l0;
+        }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_b_half,
@@ -97,7 +210,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   const int tiles_n = (p.Nb + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
-  // work item w = (k-split ks, tile t): all tiles of one K chunk run before the next chunk starts
+  const int kb_chunk = p.kb_chunk > 0 ? p.kb_chunk : KB_CHUNK;
+  // work item w = (k-split ks, tile t): all tiles of one K range run before the next range starts
   const int k_splits = p.k_splits > 1 ? p.k_splits : 1;
   const int kb_per_split = (num_kb + k_splits - 1) / k_splits;
   // Tail balancing: when the last wave would occupy at most half of the CTAs, its tiles are cut into two
@@ -114,7 +228,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < ACC_STAGES; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 128); }
+    for (int a = 0; a < ACC_STAGES; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], EPI_THREADS); }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -126,67 +240,75 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      const uint32_t a_bytes = two_pass ? 2 * A_TILE_BYTES : A_TILE_BYTES;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-        const WorkItem wi = decode_work(w, num_tiles, num_full, k_splits);
-        const int ks = wi.ks;
-        const TileCoord tc = tile_coord(wi.tile, tiles_m, tiles_n);
-        const int m0 = tc.m_blk * BLOCK_M, n0 = tc.n_blk * BLOCK_N + wi.n_off;
-        const uint32_t tx_bytes = a_bytes + (uint32_t)wi.bn * BLOCK_K * 2;
-        const int kb_end = min(num_kb, (ks + 1) * kb_per_split);
-        for (int kb = ks * kb_per_split; kb < kb_end; ++kb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-          ptx::tma_load_2d(st, &tm_a_hi, &full_bar[stage], kb * BLOCK_K, m0);
-          if (two_pass) ptx::tma_load_2d(st + A_TILE_BYTES, &tm_a_lo, &full_bar[stage], kb * BLOCK_K, m0);
-          ptx::tma_load_2d(st + 2 * A_TILE_BYTES, wi.bn == BLOCK_N ? &tm_b : &tm_b_half, &full_bar[stage], kb * BLOCK_K, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-        const WorkItem wi = decode_work(w, num_tiles, num_full, k_splits);
-        const int ks = wi.ks;
-        const uint32_t idesc = ptx::umma_idesc(/*F16*/ 0, BLOCK_M, (uint32_t)wi.bn);
-        const int kb_begin = ks * kb_per_split, kb_end = min(num_kb, (ks + 1) * kb_per_split);
-        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
-        ptx::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          ptx::mbar_wait(&full_bar[stage], phase);          // TMA bytes have landed
-          ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
-          const uint64_t d_ahi = ptx::umma_desc_k_sw128(sa);
-          const uint64_t d_alo = ptx::umma_desc_k_sw128(sa + A_TILE_BYTES);
-          const uint64_t d_b = ptx::umma_desc_k_sw128(sa + 2 * A_TILE_BYTES);
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // advance inside the swizzle row
-            ptx::mma_f16_ss(tmem_d, d_ahi + koff, d_b + koff, idesc, (kb != kb_begin || k != 0) ? 1u : 0u);
-            if (two_pass) ptx::mma_f16_ss(tmem_d, d_alo + koff, d_b + koff, idesc, 1u);
+  if (warp < EPI_WARP0) {
+    ptx::setmaxnreg_dec<REGS_CTRL>();
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (lane == 0) {
+        int stage = 0; uint32_t phase = 0;
+        const uint32_t a_bytes = two_pass ? 2 * A_TILE_BYTES : A_TILE_BYTES;
+        for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+          const WorkItem wi = decode_work(w, num_tiles, num_full, k_splits);
+          const int ks = wi.ks;
+          const TileCoord tc = tile_coord(wi.tile, tiles_m, tiles_n);
+          const int m0 = tc.m_blk * BLOCK_M, n0 = tc.n_blk * BLOCK_N + wi.n_off;
+          const uint32_t tx_bytes = a_bytes + (uint32_t)wi.bn * BLOCK_K * 2;
+          const int kb_end = min(num_kb, (ks + 1) * kb_per_split);
+          for (int kb = ks * kb_per_split; kb < kb_end; ++kb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+            ptx::tma_load_2d(st, &tm_a_hi, &full_bar[stage], kb * BLOCK_K, m0);
+            if (two_pass) ptx::tma_load_2d(st + A_TILE_BYTES, &tm_a_lo, &full_bar[stage], kb * BLOCK_K, m0);
+            ptx::tma_load_2d(st + 2 * A_TILE_BYTES, wi.bn == BLOCK_N ? &tm_b : &tm_b_half, &full_bar[stage], kb * BLOCK_K, n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          ptx::mma_commit(&empty_bar[stage]);               // frees the smem slot when the MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        ptx::mma_commit(&tfull_bar[acc]);                   // accumulator complete -> epilogue
-        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      if (lane == 0) {
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+          const WorkItem wi = decode_work(w, num_tiles, num_full, k_splits);
+          const int ks = wi.ks;
+          const uint32_t idesc = ptx::umma_idesc(/*F16*/ 0, BLOCK_M, (uint32_t)wi.bn);
+          const int kb_begin = ks * kb_per_split, kb_end = min(num_kb, (ks + 1) * kb_per_split);
+          for (int kc = kb_begin; kc < kb_end; kc += kb_chunk) {
+            const int kc_end = min(kb_end, kc + kb_chunk);
+            ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);   // the epilogue has promoted this accumulator
+            ptx::tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+            for (int kb = kc; kb < kc_end; ++kb) {
+              ptx::mbar_wait(&full_bar[stage], phase);          // TMA bytes have landed
+              ptx::tc_fence_after();
+              const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
+              const uint64_t d_ahi = ptx::umma_desc_k_sw128(sa);
+              const uint64_t d_alo = ptx::umma_desc_k_sw128(sa + A_TILE_BYTES);
+              const uint64_t d_b = ptx::umma_desc_k_sw128(sa + 2 * A_TILE_BYTES);
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // advance inside the swizzle row
+                ptx::mma_f16_ss(tmem_d, d_ahi + koff, d_b + koff, idesc, (kb != kc || k != 0) ? 1u : 0u);
+                if (two_pass) ptx::mma_f16_ss(tmem_d, d_alo + koff, d_b + koff, idesc, 1u);
+              }
+              ptx::mma_commit(&empty_bar[stage]);               // frees the smem slot when the MMAs retire
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            ptx::mma_commit(&tfull_bar[acc]);                   // chunk complete -> promotion
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+          }
+        }
       }
     }
-  } else if (warp >= EPI_WARP0) {
+  } else {
     // ===================== epilogue =====================
+    ptx::setmaxnreg_inc<REGS_EPI>();
     const int quarter = warp & 3;                   // TMEM lane quarter this warp may read
+    const int half = (warp - EPI_WARP0) >> 2;       // column half of the work item this warp owns
     int acc = 0; uint32_t acc_phase = 0;
-    const float inv_pT = p.pT_scale;
+    float accv[4][32];                              // 128 partial sums: row m, columns half * bn/2 + [0, bn/2)
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
       const WorkItem wi = decode_work(w, num_tiles, num_full, k_splits);
       const int ks = wi.ks;
@@ -194,121 +316,42 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       const TileCoord tc = tile_coord(wi.tile, tiles_m, tiles_n);
       const int m = tc.m_blk * BLOCK_M + quarter * 32 + lane;
       const bool m_ok = m < p.Ma;
-      const int n_tile0 = tc.n_blk * BLOCK_N + wi.n_off;
-      const int n_chunks = wi.bn / 32;
+      const int half_cols = wi.bn >> 1;             // 128, or 64 for a tail half-tile
+      const int n_slices = half_cols >> 5;          // 4 or 2
+      const int n_half0 = tc.n_blk * BLOCK_N + wi.n_off + half * half_cols;
       const float bias_m = (p.bias != nullptr && m_ok) ? __ldg(p.bias + m) : 0.0f;
       const float acc_scale = p.acc_scale_dev ? p.acc_scale * __ldg(p.acc_scale_dev) : p.acc_scale;
-
-      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
-      ptx::tc_fence_after();
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-
-#pragma unroll 1
-      for (int chunk = 0; chunk < n_chunks; ++chunk) {
-        const int nb0 = n_tile0 + chunk * 32;
-        if (nb0 >= p.Nb) break;                     // warp-uniform
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(taddr0 + (uint32_t)(chunk * 32), r);
-        ptx::tmem_ld_wait();
-
-        float val[32];
+      const int kb_begin = ks * kb_per_split, kb_end = min(num_kb, (ks + 1) * kb_per_split);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = fmaf(__uint_as_float(r[j]), acc_scale, bias_m);
-          val[j] = p.act ? __fdividef(1.0f, 1.0f + __expf(-x)) : x;
-        }
+      for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) accv[s][j] = 0.0f;
 
-        uint32_t sbits = 0;
-        if (p.sample) {
-          if (p.U != nullptr) {
+      for (int kc = kb_begin; kc < kb_end; kc += kb_chunk) {
+        ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * half_cols);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int nb = nb0 + j;
-              float u = (m_ok && nb < p.Nb) ? __ldg(p.U + (size_t)nb * p.ldu + m) : 2.0f;
-              sbits |= (val[j] > u ? 1u : 0u) << j;
-            }
-          } else {
-            const uint32_t grow0 = p.rng.row_offset + (uint32_t)nb0;   // multiple of 4 by construction
+        for (int s = 0; s < 4; ++s) {
+          if (s < n_slices) {                       // warp-uniform
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(taddr0 + (uint32_t)(s * 32), r);
+            ptx::tmem_ld_wait();
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              Philox4 o = philox4x32_10((uint32_t)m, (grow0 >> 2) + q, p.rng.draw_lo, p.rng.draw_hi,
-                                        p.rng.seed_lo, p.rng.seed_hi);
-              sbits |= (val[4 * q + 0] > u32_to_uniform(o.x) ? 1u : 0u) << (4 * q + 0);
-              sbits |= (val[4 * q + 1] > u32_to_uniform(o.y) ? 1u : 0u) << (4 * q + 1);
-              sbits |= (val[4 * q + 2] > u32_to_uniform(o.z) ? 1u : 0u) << (4 * q + 2);
-              sbits |= (val[4 * q + 3] > u32_to_uniform(o.w) ? 1u : 0u) << (4 * q + 3);
-            }
+            for (int j = 0; j < 32; ++j) accv[s][j] += __uint_as_float(r[j]);
           }
         }
-
-        // ---- [Nb, Ma] outputs: for fixed j the 32 lanes write 32 consecutive units ----
-        if (out32 != nullptr && m_ok) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb0 + j < p.Nb) out32[(size_t)(nb0 + j) * p.ld32 + m] = val[j];
-        }
-        if (p.out_s16 != nullptr && m_ok) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb0 + j < p.Nb) {
-              float s = p.sample ? (float)((sbits >> j) & 1u) : val[j];
-              p.out_s16[(size_t)(nb0 + j) * p.lds16 + m] = __float2half_rn(s);
-            }
-        }
-        // ---- [Ma, Nb] "T" outputs: each thread owns 32 consecutive columns of its row ----
-        const bool full_chunk = nb0 + 32 <= p.Nb;
-        if (p.out_sT16 != nullptr && m_ok) {
-          __half* dst = p.out_sT16 + (size_t)m * p.ldsT + tc_interleaved_col(nb0, p.sT_phase);
-          if (full_chunk) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 v;
-              uint32_t b = sbits >> (8 * g);
-              v.x = pack_h2((float)(b & 1u), (float)((b >> 1) & 1u));
-              v.y = pack_h2((float)((b >> 2) & 1u), (float)((b >> 3) & 1u));
-              v.z = pack_h2((float)((b >> 4) & 1u), (float)((b >> 5) & 1u));
-              v.w = pack_h2((float)((b >> 6) & 1u), (float)((b >> 7) & 1u));
-              reinterpret_cast<uint4*>(dst)[g] = v;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb0 + j < p.Nb) dst[j] = __float2half_rn((float)((sbits >> j) & 1u));
-          }
-        }
-        if (p.out_pT_hi != nullptr && m_ok) {
-          __half* dhi = p.out_pT_hi + (size_t)m * p.ldpT + tc_interleaved_col(nb0, p.pT_phase);
-          __half* dlo = p.out_pT_lo + (size_t)m * p.ldpT + tc_interleaved_col(nb0, p.pT_phase);
-          if (full_chunk) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint32_t hi[4], lo[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                __half h0, l0, h1, l1;
-                split_f16(val[8 * g + 2 * e] * inv_pT, h0, l0);
-                split_f16(val[8 * g + 2 * e + 1] * inv_pT, h1, l1);
-                __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
-                hi[e] = *reinterpret_cast<uint32_t*>(&hh);
-                lo[e] = *reinterpret_cast<uint32_t*>(&ll);
-              }
-              reinterpret_cast<uint4*>(dhi)[g] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              reinterpret_cast<uint4*>(dlo)[g] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb0 + j < p.Nb) {
-                __half h0, l0;
-                split_f16(val[j] * inv_pT, h0, l0);
-                dhi[j] = h0; dlo[j] = l0;
-              }
-          }
-        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&tempty_bar[acc]);         // 256 arrivals release the accumulator
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&tempty_bar[acc]);           // 128 arrivals release the accumulator
-      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const int nb0 = n_half0 + s * 32;
+        if (s < n_slices && nb0 < p.Nb)             // warp-uniform
+          epilogue_slice(p, accv[s], nb0, m, m_ok, bias_m, acc_scale, out32);
+      }
     }
   }
 
@@ -392,6 +435,10 @@ int tc_gemm_launch(const TcGemmParams& p, int num_sms, cudaStream_t stream) {
   TcGemmParams q = p;
   const int rem = base_tiles % grid;
   q.split_tail = (p.k_splits <= 1 && base_tiles > grid && rem > 0 && 2 * rem <= grid) ? 1 : 0;
+  if (q.kb_chunk <= 0) {
+    static const int env_chunk = [] { const char* e = getenv("DB_TC_KB_CHUNK"); return e ? atoi(e) : 0; }();   // diagnostics
+    q.kb_chunk = env_chunk > 0 ? env_chunk : KB_CHUNK;
+  }
   tc_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_a_hi, tm_a_lo, tm_b, tm_b_half, q);
   return (int)cudaGetLastError();
 }

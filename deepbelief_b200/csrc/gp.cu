@@ -1587,11 +1587,36 @@ __global__ void __launch_bounds__(256) mirror_lower_kernel(float* __restrict__ A
 // tr G = 0.5 (D |Linv|_F^2 - |A|_F^2) from two fp32 round-to-nearest reductions (scratch[0], scratch[1]) replaces the
 // trace summed from the tensor-core tiles: sums of squares are monotone, so the truncating accumulator biases them
 // one way (~3e-6), and tr G cancels ~50x. The diagonal also enters sum G o Kf (Kf_ii = alpha).
-__global__ void gp_fix_trace_kernel(GpAccum* acc, const float* __restrict__ scratch, const float* __restrict__ hyp, int D) {
-  const float tr = 0.5f * ((float)D * scratch[0] - scratch[1]);
-  acc->sumW += hyp[0] * (tr - acc->trG);
-  acc->trG = tr;
+// scratch (fp64): [0] |Linv|_F^2 = tr K^-1, [1] |A|_F^2, [2] sum Y o A, [3..8] off-diagonal contractions accumulated by
+// gp_contract_mem_kernel: K^-1 o K_f, K^-1 o K_f r^2, AA o K_f, AA o K_f r^2 (AA = -0.5 A A^T), sum K_f, sum K_f r^2.
+// The hyper-parameter gradients contract G = (D/2) K^-1 + AA with K_f: two terms far larger than their sum, each carrying the
+// one-sided error of the truncating tensor-core datapath (measured at N = 5000 against fp64: d_alpha off by 3.3e-4, d_gamma by
+// 1.5e-4). With K = K_f + s I and K A = Y the plain K_f contractions have closed forms,
+//   sum_ij (K^-1)_ij (K_f)_ij = N - s tr K^-1,      sum_ij (A A^T)_ij (K_f)_ij = sum Y o A - s |A|_F^2,
+// so sum G o K_f (d_alpha) is formed from the fp64 scalars alone. The r^2-weighted contraction (d_gamma) has no closed form; its
+// dominant error is a UNIFORM ADDITIVE shift of the A A^T tiles (A ~ Y - smooth(Y) with Y centred binary: most of the D products
+// of an entry are small and of one sign, and each loses its low bits toward zero when aligned inside the MMA; measured shift
+// -1.5e-6 per entry, sum AA o K_f off by +6.1 and sum AA o K_f r^2 by +8.0 = 6.1 x sum K_f r^2 / sum K_f). The closed form
+// calibrates that shift, delta = (measured - exact) / sum K_f, and delta sum K_f r^2 is removed from the weighted contraction.
+// The K^-1 tiles show no such pattern (errors ~1e-5 of d_gamma) and are used as they are.
+__global__ void gp_fix_trace_kernel(GpAccum* acc, const double* __restrict__ scratch, const float* __restrict__ hyp, int N, int D, int debug) {
+  const double alpha = hyp[0], s = hyp[2], half_d = 0.5 * (double)D;
+  const double trKinv = scratch[0], a2 = scratch[1], ya = scratch[2];
+  acc->trG = (float)(0.5 * ((double)D * trKinv - a2));                       // the cancelling difference itself in fp64
+  const double exactA = -0.5 * (ya - (s + alpha) * a2);                      // off-diagonal part of sum (-0.5 A A^T) o K_f
+  double shift = scratch[7] > 0.0 ? (scratch[5] - exactA) / scratch[7] : 0.0;
+  if (!(fabs(shift * scratch[7]) <= 1e-3 * fabs(exactA))) shift = 0.0;       // the calibration only ever moves parts per million
+  const double sumW = half_d * ((double)N - s * trKinv) - 0.5 * (ya - s * a2);
+  const double sumWr2 = half_d * scratch[4] + (scratch[6] - shift * scratch[8]);
+  if (debug)
+    printf("gp_fix_trace: trKinv %.9g |A|^2 %.9g YoA %.9g | K o Kf: meas %.9g exact %.9g | AA o Kf: meas %.9g exact %.9g shift %.3e | Kr2 %.9g Ar2 %.9g -> %.9g | "
+           "sumW %.9g -> %.9g, sumWr2 %.9g -> %.9g\n",
+           trKinv, a2, ya, scratch[3], ((double)N - s * trKinv) - alpha * trKinv, scratch[5], exactA, shift, scratch[4], scratch[6],
+           scratch[6] - shift * scratch[8], (double)acc->sumW, sumW, (double)acc->sumWr2, sumWr2);
+  acc->sumW = (float)sumW;
+  acc->sumWr2 = (float)sumWr2;
 }
+__global__ void gp_store_ssq_kernel(GpAccum* acc, const double* __restrict__ scratch) { acc->ssq = (float)scratch[2]; }
 // Kinv[i,i] = sum_k LinvT[i,k]^2 in fp32 round-to-nearest (one warp per row): the tensor-core value of this monotone
 // sum is biased low by the truncating accumulator, and A = K^-1 Y inherits a diagonal bias one-to-one.
 __global__ void kinv_diag_kernel(const float* __restrict__ LinvT, int N, float* __restrict__ Kinv, float* __restrict__ Kinv_lo) {
@@ -1606,23 +1631,29 @@ __global__ void kinv_diag_kernel(const float* __restrict__ LinvT, int N, float* 
     if (Kinv_lo) Kinv_lo[(size_t)i * N + i] = s - __uint_as_float(__float_as_uint(s) & 0xffffe000u);
   }
 }
+// sum_i a[i] * b[i] into a DOUBLE accumulator: ~10^4 warp partials added with fp32 atomics random-walk to ~3e-6 relative,
+// which the ~100x cancelling tr G = 0.5 (D tr K^-1 - |A|^2) turns into 3e-4 (measured at N = 5000 against the fp64 oracle).
+// Per-thread partial sums stay fp32 (a few hundred fused multiply-adds each), the cross-thread reduction is fp64.
 __global__ void __launch_bounds__(256) dot_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n,
-                                                      float* __restrict__ out) {
-  float s = 0.0f;
+                                                      double* __restrict__ out) {
+  double s = 0.0;
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
   if ((n & 3) == 0 && (((uintptr_t)a | (uintptr_t)b) & 15) == 0) {
     const float4* a4 = reinterpret_cast<const float4*>(a);
     const float4* b4 = reinterpret_cast<const float4*>(b);
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int run = 0;
     for (size_t i = tid; i < n / 4; i += nthr) {
       const float4 x = __ldg(a4 + i), y = __ldg(b4 + i);
       s0 = fmaf(x.x, y.x, s0); s1 = fmaf(x.y, y.y, s1); s2 = fmaf(x.z, y.z, s2); s3 = fmaf(x.w, y.w, s3);
+      if (++run == 16) { s += ((double)s0 + (double)s1) + ((double)s2 + (double)s3); s0 = s1 = s2 = s3 = 0.f; run = 0; }
     }
-    s = (s0 + s1) + (s2 + s3);
+    s += ((double)s0 + (double)s1) + ((double)s2 + (double)s3);
   } else {
-    for (size_t i = tid; i < n; i += nthr) s = fmaf(__ldg(a + i), __ldg(b + i), s);
+    for (size_t i = tid; i < n; i += nthr) s += (double)__ldg(a + i) * (double)__ldg(b + i);
   }
-  s = warp_sum(s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
 }
 // G tile = (D/2) Kinv + AA (AA = -0.5 A A^T, lower part valid; Kinv == nullptr: AA is G already) read from memory,
@@ -1630,7 +1661,7 @@ __global__ void __launch_bounds__(256) dot_sum_kernel(const float* __restrict__ 
 template <class T>
 __global__ void __launch_bounds__(256) gp_contract_mem_kernel(const float* __restrict__ Kinv, const float* __restrict__ AA, int N, int Q,
                                                               int D, const float* __restrict__ X, const float* __restrict__ hyp,
-                                                              float* __restrict__ dXacc, GpAccum* accum) {
+                                                              float* __restrict__ dXacc, GpAccum* accum, double* __restrict__ cal) {
   if (blockIdx.x > blockIdx.y) return;
   __shared__ float rowacc[T::BM][MAXQ];
   __shared__ float colacc[T::BN][MAXQ];
@@ -1639,6 +1670,9 @@ __global__ void __launch_bounds__(256) gp_contract_mem_kernel(const float* __res
   const bool diag_tile = blockIdx.x == blockIdx.y;
   for (int t = threadIdx.x; t < T::BM * MAXQ; t += 256) { (&rowacc[0][0])[t] = 0.0f; (&colacc[0][0])[t] = 0.0f; }
   const float half_d = 0.5f * (float)D;
+  const bool calibrate = cal != nullptr && Kinv != nullptr;
+  const float alpha = __ldg(hyp), nhalf_inv_g2 = -0.5f / (__ldg(hyp + 1) * __ldg(hyp + 1));
+  float cK = 0.0f, cKr = 0.0f, cA = 0.0f, cAr = 0.0f, cF = 0.0f, cFr = 0.0f;   // strictly-lower contractions (see gp_fix_trace_kernel)
   float gacc[T::TM][T::TN];
 #pragma unroll
   for (int i = 0; i < T::TM; ++i) {
@@ -1649,9 +1683,28 @@ __global__ void __launch_bounds__(256) gp_contract_mem_kernel(const float* __res
       float g = 0.0f;
       if (m < N && n < N && n <= m) {
         g = __ldg(AA + (size_t)m * N + n);
-        if (Kinv != nullptr) g = fmaf(half_d, __ldg(Kinv + (size_t)m * N + n), g);
+        if (Kinv != nullptr) {
+          const float kv = __ldg(Kinv + (size_t)m * N + n);
+          if (calibrate && n < m) {
+            float r2 = 0.0f;
+            for (int q = 0; q < Q; ++q) { const float d = __ldg(X + (size_t)m * Q + q) - __ldg(X + (size_t)n * Q + q); r2 = fmaf(d, d, r2); }
+            const float kf = alpha * __expf(nhalf_inv_g2 * r2);
+            cK = fmaf(kv, kf, cK); cKr = fmaf(kv * kf, r2, cKr); cA = fmaf(g, kf, cA); cAr = fmaf(g * kf, r2, cAr);
+            cF += kf; cFr = fmaf(kf, r2, cFr);
+          }
+          g = fmaf(half_d, kv, g);
+        }
       }
       gacc[i][jj] = g;
+    }
+  }
+  if (calibrate) {     // per-thread fp32 partials (<= TM*TN terms), everything across threads in fp64
+    double v[6] = {2.0 * (double)cK, 2.0 * (double)cKr, 2.0 * (double)cA, 2.0 * (double)cAr, 2.0 * (double)cF, 2.0 * (double)cFr};
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v[e] += __shfl_xor_sync(0xffffffffu, v[e], o);
+      if ((threadIdx.x & 31) == 0) atomicAdd(cal + e, v[e]);
     }
   }
   __syncthreads();
@@ -2030,8 +2083,8 @@ extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float*
   if (tc) {
     const size_t nn = (size_t)N * N, nd = (size_t)N * D;
     const int tiles32 = (N + 31) / 32;
-    float* frob = reinterpret_cast<float*>(w.acc) + 16;                          // two scratch floats behind the accumulators
-    cudaMemsetAsync(frob, 0, 2 * sizeof(float), st);
+    double* frob = reinterpret_cast<double*>(reinterpret_cast<char*>(w.acc) + 64);   // nine fp64 scratch sums behind the accumulators
+    cudaMemsetAsync(frob, 0, 9 * sizeof(double), st);
     // Tmp = Linv^T (upper triangular), Ulo = its tf32 remainder
     if ((rc = run_trinv_tc(h, st, w.K, w.Li, N, w.Li, w.Tmp, w.Ulo, w.WT, w.WTlo))) return rc;
     dot_sum_kernel<<<h->num_sms * 8, 256, 0, st>>>(w.Tmp, w.Tmp, nn, frob);       // |Linv|_F^2 = tr K^-1
@@ -2045,16 +2098,18 @@ extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float*
     trc = tf32_gemm_launch(h, st, D, N, N, 1.0f, w.B1, w.B2, N, w.Li, w.K, N, 0.0f, w.B3, N, 0, 0);          // B3 = (K^-1 Y)^T
     if (trc) return set_err(h, DB_ERR_CUDA, "tf32 K^-1 Y product failed (%d)", trc);
     transpose_f32(st, w.B3, D, N, N, w.Av, D);                                   // Av = A = K^-1 Y [N,D]
-    dot_sum_kernel<<<h->num_sms * 8, 256, 0, st>>>(Y, w.Av, nd, &w.acc->ssq);    // |L^-1 Y|^2 = sum Y o A
+    dot_sum_kernel<<<h->num_sms * 8, 256, 0, st>>>(Y, w.Av, nd, frob + 2);       // |L^-1 Y|^2 = sum Y o A
+    gp_store_ssq_kernel<<<1, 1, 0, st>>>(w.acc, frob);
     if (want_grad) {
       tf32_split_lo(h, st, w.Av, N, D, D, w.S);                                  // S buffer = remainder of A
       trc = tf32_gemm_launch(h, st, N, N, D, -0.5f, w.Av, w.S, D, w.Av, w.S, D, 0.0f, w.Tmp, N, 1, 0);       // Tmp = -0.5 A A^T (lower)
       if (trc) return set_err(h, DB_ERR_CUDA, "tf32 A A^T product failed (%d)", trc);
       cudaMemsetAsync(w.dXacc, 0, sizeof(float) * (size_t)N * Q, st);
       const int tiles = (N + TileLarge::BM - 1) / TileLarge::BM;
-      gp_contract_mem_kernel<TileLarge><<<dim3(tiles, tiles), 256, 0, st>>>(w.Li, w.Tmp, N, Q, D, X, w.hyp, w.dXacc, w.acc);
+      gp_contract_mem_kernel<TileLarge><<<dim3(tiles, tiles), 256, 0, st>>>(w.Li, w.Tmp, N, Q, D, X, w.hyp, w.dXacc, w.acc, frob + 3);
       dot_sum_kernel<<<h->num_sms * 8, 256, 0, st>>>(w.Av, w.Av, nd, frob + 1);   // |A|_F^2
-      gp_fix_trace_kernel<<<1, 1, 0, st>>>(w.acc, frob, w.hyp, D);
+      static const int dbg = [] { const char* e = getenv("DB_GP_DEBUG"); return (e && e[0] == '1') ? 1 : 0; }();
+      gp_fix_trace_kernel<<<1, 1, 0, st>>>(w.acc, frob, w.hyp, N, D, dbg);
     }
   } else {
   if ((rc = run_trmm<0>(h, st, w.Li, N, Y, D, D, w.S, D, &w.acc->ssq))) return rc;
@@ -2067,7 +2122,7 @@ extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float*
     if (splits > 1) {      // few tiles: cluster split-K into w.Tmp (free once Linv is formed), then the contraction from memory
       simt_launch_split(gp_g_split_kernel, dim3(tiles_s, tiles_s, splits), 256, st, (const float*)w.Li, N, (const float*)w.Av, D, N, D,
                         w.Tmp, splits);
-      gp_contract_mem_kernel<TileSmall><<<dim3(tiles_s, tiles_s), 256, 0, st>>>(nullptr, w.Tmp, N, Q, D, X, w.hyp, w.dXacc, w.acc);
+      gp_contract_mem_kernel<TileSmall><<<dim3(tiles_s, tiles_s), 256, 0, st>>>(nullptr, w.Tmp, N, Q, D, X, w.hyp, w.dXacc, w.acc, nullptr);
     } else {
       gp_grad_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(w.Li, N, w.Av, D, X, N, Q, D, w.hyp, w.dXacc, w.acc);
     }
@@ -2197,7 +2252,7 @@ extern "C" int db_gpdbn_backward_x(db_handle_t h, db_stream_t stream, const floa
     if (splits > 1) {       // few tiles (the horses runs, N = 328): cluster split-K into w.Ulo, contraction from memory
       simt_launch_split(gpdbn_g_split_kernel, dim3(tiles_s, tiles_s, splits), 256, st, (const float*)w.Kinv, g_pv, (const float*)w.P,
                         (const float*)w.B, N, D, (const float*)w.hyp, w.Ulo, splits);
-      gp_contract_mem_kernel<TileSmall><<<dim3(tiles_s, tiles_s), 256, 0, st>>>(nullptr, w.Ulo, N, Q, D, X, w.hyp, w.dXacc, w.acc);
+      gp_contract_mem_kernel<TileSmall><<<dim3(tiles_s, tiles_s), 256, 0, st>>>(nullptr, w.Ulo, N, Q, D, X, w.hyp, w.dXacc, w.acc, nullptr);
     } else {
       gpdbn_grad_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(w.Kinv, g_pv, w.P, w.B, X, N, Q, D, w.hyp, w.dXacc, w.acc);
     }

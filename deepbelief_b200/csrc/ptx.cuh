@@ -127,6 +127,16 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---- register reallocation between warpgroups (all four warps of the group execute it) -----------
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 // ---- UMMA descriptors ----------------------------------------------------------------------------
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle (what TMA SWIZZLE_128B writes):
 // rows are 128 B apart, 8-row groups 1024 B apart (SBO), LBO unused (=1), version 1 (Blackwell).

@@ -493,11 +493,15 @@ class GPRBM(bgrbm.BGRBM):
 
     # ---- test-time latent search (gprbm.py:468-562) ------------------------------------------------------------------
     def _latent_search_cache(self):
-        """K^-1 and B = K^-1 H2 for the frozen model (H2 / H1_mean are the snapshots of gprbm.py:149-153)."""
+        """L^-1 and B = K^-1 H2 for the frozen model (H2 / H1_mean are the snapshots of gprbm.py:149-153).
+        The predictive variance is formed as the reference forms it, alpha - |L^-1 k|^2 (gprbm.py:208-214): a sum of squares.
+        k^T (K^-1 k) through an explicit K^-1 cancels ~1/noise-fold and returned negative variances in fp32 at the horses
+        settings (noise 0.01, pred_var ~1e-4 next to the training points)."""
         self._factor(need_L=True)
         eye = torch.eye(self.N, device=self.device, dtype=torch.float32)
-        Kinv = ops.trsm_lower(self._Lfac, ops.trsm_lower(self._Lfac, eye), trans=True)
-        return Kinv, ops.gemm(Kinv, self.H2_var)
+        Linv = ops.trsm_lower(self._Lfac, eye)
+        B = ops.gemm(Linv, ops.gemm(Linv, self.H2_var), trans_a=True)
+        return Linv, B
 
     def _latent_forward(self, x, num_samples, cache=None, draws=None):
         """Frozen-model forward at test latents x [R,Q], S samples each (rows r * S + s): K_Xx, predictive variance,
@@ -505,7 +509,7 @@ class GPRBM(bgrbm.BGRBM):
         Concrete stack. Returns the tape the x-gradient needs."""
         if self.temperature is None:
             raise NotImplementedError('the latent search differentiates through Concrete units (temperature)')
-        Kinv, B = cache or self._latent_search_cache()
+        Linv, B = cache or self._latent_search_cache()
         dev, D, S = self.device, self.D, int(num_samples)
         x = to_device(x, dev)
         R = x.shape[0]
@@ -515,8 +519,9 @@ class GPRBM(bgrbm.BGRBM):
         alpha_h = self.alpha_h.reshape(-1)
         Kxs = ops.gram_rbf(self.X, x, hyp)                                   # [N,R]
         Hm = ops.gemm(Kxs, B, trans_a=True)                                  # (L^-1 K_Xx)^T (L^-1 H2)
-        Cv = ops.gemm(Kinv, Kxs)
-        pv, info = ops.testgen_pred_var(Kxs, Cv, hyp)
+        V1 = ops.gemm(Linv, Kxs)                                             # L^-1 K_Xx
+        pv, info = ops.testgen_pred_var(V1, V1, hyp)                         # alpha - colsum(V1^2)
+        Cv = ops.gemm(Linv, V1, trans_a=True)                                # K^-1 K_Xx (the x-gradient of pred_var needs it)
         rows = torch.arange(R, device=dev).repeat_interleave(S)
         Hm_rows, pv_rows = Hm[rows].contiguous(), pv[rows].contiguous()
         eps = inj(dr.get('eps'))
@@ -647,12 +652,13 @@ class GPRBM(bgrbm.BGRBM):
 
     def interp_objective(self, Xi, x_start, x_end, interp_lambda, cache=None):
         """Objective of interp_test (gprbm.py:651-660) at the path Xi [P,Q] and its gradient with respect to Xi."""
-        Kinv, _ = cache or self._latent_search_cache()
+        Linv, _ = cache or self._latent_search_cache()
         Xi = to_device(Xi, self.device)
         hyp = ops.gp_effective_hyp(self._hyp, self.flags, self.fixed_noise, self.noise_jitter or 0.0)
         Kxs = ops.gram_rbf(self.X, Xi, hyp)
-        Cv = ops.gemm(Kinv, Kxs)
-        pv, info = ops.testgen_pred_var(Kxs, Cv, hyp)
+        V1 = ops.gemm(Linv, Kxs)
+        pv, info = ops.testgen_pred_var(V1, V1, hyp)
+        Cv = ops.gemm(Linv, V1, trans_a=True)
         obj, g_seg, g_pv = ops.interp_objective(Xi, to_device(x_start, self.device).reshape(-1),
                                                 to_device(x_end, self.device).reshape(-1), pv, interp_lambda)
         g_x = ops.testgen_grad_x(torch.zeros_like(Kxs), Cv, Kxs, g_pv, self.X, Xi, hyp)

@@ -25,7 +25,7 @@ EDITS = {
     'gplvm_horses': {'num_iterations': 30, 'eval_interval': 15, 'test_generalisation_num_iterations': 5,
                      'test_generalisation_num_runs': 16},
     'gpdbn_horses': {'num_iterations': 24, 'fixed_X_num_iterations': 8, 'eval_interval': 12,
-                     'test_generalisation_num_iterations': 4, 'test_generalisation_num_runs': 8,
+                     'test_generalisation_num_iterations': 4,
                      'test_generalisation_num_samples_to_average': 10},
 }
 
