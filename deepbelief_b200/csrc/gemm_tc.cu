@@ -11,19 +11,23 @@
 // in fp16 (>= 22 significant bits), two kind::f16 MMA passes accumulate into the same TMEM tile.
 // That is fp32-level accuracy at 2 fp16 passes = the cost of ONE TF32 pass (fp16 runs at 2x TF32).
 //
-// Accumulation: the tensor core adds into its fp32 TMEM accumulator with truncation toward zero, a bias that
-// grows with the number of adds (measured against fp64 on the pre-activation of a 4096 / 8192-deep layer: mean
-// 4e-6 / 8e-6 toward zero, probabilities off by up to 1.3e-5 / 3.5e-5 relative — outside the 1e-5 the path must hold).
-// K is therefore cut into chunks of kb_chunk k-blocks (512 columns): each chunk accumulates in one of the two TMEM
-// stages and is then PROMOTED — added in fp32 round-to-nearest into registers of the epilogue threads (128 partial
-// sums per thread) — while the next chunk runs in the other stage. The same mechanism lets the dW product run over
-// its whole K = 2 x batch range in one work item (no split-K partial tiles in HBM).
+// Accumulation: the tensor core adds into its fp32 TMEM accumulator with truncation toward zero. The hi products
+// (an 11-bit fp16 value times {0,1}) land on or above the accumulator's last bit and add EXACTLY; the lo products (the
+// 2^-11 remainder) always fall below it, and every lo MMA shaves ~half an ulp off the running sum: measured against fp64
+// on the pre-activation of a 4096 / 8192-deep layer, a mean shrink of 4e-6 / 8e-6 and probabilities off by up to
+// 1.3e-5 / 3.5e-5 relative, outside the 1e-5 the path must hold. The two passes therefore accumulate into SEPARATE TMEM
+// tiles (H: columns 0-255, L: columns 256-511): in L the same truncation is relative to a 2^-11 times smaller sum. The
+// epilogue adds H + L once, in fp32 round-to-nearest, while it drains both into registers (128 sums per thread);
+// the TMEM is released as soon as the drain is done, and the epilogue math of tile t runs under the MMAs of tile t+1.
+// (Promoting one shared accumulator into registers every 512 / 1024 / 2048 columns instead was measured at 2e-6 / 4e-6 /
+// 9e-6 and +15 % / +7 % / +1 % time: the 20 us of epilogue math per tile delays the promotions of the next tile.)
+// The dW product runs over its whole K = 2 x batch range the same way (no split-K partial tiles in HBM).
 //
 // Roles (384 threads, 1 CTA/SM, persistent over tiles; setmaxnreg moves registers from warps 0-3 to the epilogue):
 //   warp 0    : TMA producer   (A_hi, A_lo, B tiles -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1    : MMA issuer     (one elected thread: tcgen05.mma, tcgen05.commit)
-//   warp 2    : TMEM allocator (512 columns = 2 chunk accumulators of 128x256 fp32)
-//   warps 4-11: epilogue       (per chunk: tcgen05.ld + add; per tile: scale+bias -> logistic -> Philox/injected
+//   warp 2    : TMEM allocator (512 columns = the hi and the lo accumulator of one 128x256 tile)
+//   warps 4-11: epilogue       (tcgen05.ld of H and L + add, release; then scale+bias -> logistic -> Philox/injected
 //                               uniform -> compare -> global stores), overlapped with the next tile's MMAs.
 //                               Warp w owns TMEM lanes 32 (w % 4) .. +32 and the column half (w - 4) / 4 of the tile.
 #include "gemm_tc.cuh"
@@ -45,12 +49,10 @@ constexpr int STAGES = 3;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
 constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KB
 constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + B_TILE_BYTES;   // 64 KB
-constexpr int ACC_STAGES = 2;
-constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;       // 512
+constexpr int TMEM_COLS = 2 * BLOCK_N;                // 512: H (hi products) | L (lo products)
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 256;       // warps 4-11
-constexpr int KB_CHUNK = 8;            // k-blocks per TMEM accumulation chunk (512 columns = 64 truncating adds over hi + lo)
 constexpr int REGS_EPI = 216, REGS_CTRL = 40;   // 256 x 216 + 128 x 40 = 60416 <= 65536
 constexpr int GROUP_M = 8;
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -127,6 +129,82 @@ __device__ __forceinline__ void epilogue_slice(const TcGemmParams& p, float (&va
     for (int j = 0; j < 32; ++j)
       if (nb0 + j < p.Nb) out32[(size_t)(nb0 + j) * p.ld32 + m] = val[j];
   }
+  // ---- fused K2 tail: val = gradient tile -> optimizer step on theta, split-weight cache rewritten ----
+  if (p.opt.kind >= 0) {
+    const TcOptArgs& o = p.opt;
+    const float sc = __ldg(o.scale_dev);
+    float mx = 0.0f;
+    if (m_ok) {
+#pragma unroll
+      for (int j0 = 0; j0 < 32; j0 += 8) {
+        float th[8], a[8], b[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {          // all loads of the group first
+          const bool ok = nb0 + j0 + jj < p.Nb;
+          const size_t idx = (size_t)(nb0 + j0 + jj) * p.ld32 + m;
+          th[jj] = ok ? o.theta[idx] : 0.0f;
+          a[jj] = (ok && o.kind != DB_OPT_SGD) ? o.st[idx] : 0.0f;
+          b[jj] = (ok && o.kind == DB_OPT_ADAM) ? o.st2[idx] : 0.0f;
+        }
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          if (nb0 + j0 + jj >= p.Nb) { val[j0 + jj] = 0.0f; continue; }
+          const size_t idx = (size_t)(nb0 + j0 + jj) * p.ld32 + m;
+          float t = th[jj];
+          const float gi = val[j0 + jj] + o.weight_decay * t;      // same expressions as optimizer_kernel (layer_simt.cu)
+          if (o.kind == DB_OPT_SGD) {
+            t -= o.lr * gi;
+          } else if (o.kind == DB_OPT_MOMENTUM) {
+            const float acc = o.momentum * a[jj] + gi;
+            o.st[idx] = acc;
+            t -= o.lr * acc;
+          } else {
+            const float mm = o.beta1 * a[jj] + (1.0f - o.beta1) * gi;
+            const float vv = o.beta2 * b[jj] + (1.0f - o.beta2) * gi * gi;
+            o.st[idx] = mm; o.st2[idx] = vv;
+            t -= o.lr_t * mm / (sqrtf(vv) + o.eps);
+          }
+          o.theta[idx] = t;
+          mx = fmaxf(mx, fabsf(t));
+          val[j0 + jj] = t * sc;
+          __half h, l;
+          split_f16(val[j0 + jj], h, l);
+          o.n_hi[idx] = h; o.n_lo[idx] = l;
+        }
+      }
+      __half* dhi = o.t_hi + (size_t)m * o.ldt + nb0;
+      __half* dlo = o.t_lo + (size_t)m * o.ldt + nb0;
+      if (nb0 + 32 <= p.Nb) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __half h0, l0, h1, l1;
+            split_f16(val[8 * g + 2 * e], h0, l0);
+            split_f16(val[8 * g + 2 * e + 1], h1, l1);
+            __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+            hi[e] = *reinterpret_cast<uint32_t*>(&hh);
+            lo[e] = *reinterpret_cast<uint32_t*>(&ll);
+          }
+          reinterpret_cast<uint4*>(dhi)[g] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          reinterpret_cast<uint4*>(dlo)[g] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nb0 + j < p.Nb) {
+            __half h0, l0;
+            split_f16(val[j], h0, l0);
+            dhi[j] = h0; dlo[j] = l0;
+          }
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    if ((threadIdx.x & 31) == 0 && mx > 0.0f) atomicMax(o.max_bits, __float_as_uint(mx));
+    return;
+  }
   if (p.out_s16 != nullptr && m_ok) {
 #pragma unroll
     for (int j = 0; j < 32; ++j)
@@ -198,9 +276,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
   uint64_t* full_bar = bars;                       // [STAGES]
   uint64_t* empty_bar = bars + STAGES;             // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * STAGES;         // [ACC_STAGES]
-  uint64_t* tempty_bar = tfull_bar + ACC_STAGES;   // [ACC_STAGES]
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tempty_bar + ACC_STAGES);
+  uint64_t* tfull_bar = bars + 2 * STAGES;         // accumulators complete -> epilogue
+  uint64_t* tempty_bar = tfull_bar + 1;            // accumulators drained -> MMA
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tempty_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -210,7 +288,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   const int tiles_n = (p.Nb + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
-  const int kb_chunk = p.kb_chunk > 0 ? p.kb_chunk : KB_CHUNK;
   // work item w = (k-split ks, tile t): all tiles of one K range run before the next range starts
   const int k_splits = p.k_splits > 1 ? p.k_splits : 1;
   const int kb_per_split = (num_kb + k_splits - 1) / k_splits;
@@ -228,7 +305,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < ACC_STAGES; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], EPI_THREADS); }
+    ptx::mbar_init(tfull_bar, 1); ptx::mbar_init(tempty_bar, EPI_THREADS);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -269,36 +346,34 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       // ===================== MMA issuer =====================
       if (lane == 0) {
         int stage = 0; uint32_t phase = 0;
-        int acc = 0; uint32_t acc_phase = 0;
+        uint32_t acc_phase = 0;
+        const uint32_t tmem_h = tmem_base, tmem_l = tmem_base + (uint32_t)BLOCK_N;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
           const WorkItem wi = decode_work(w, num_tiles, num_full, k_splits);
           const int ks = wi.ks;
           const uint32_t idesc = ptx::umma_idesc(/*F16*/ 0, BLOCK_M, (uint32_t)wi.bn);
           const int kb_begin = ks * kb_per_split, kb_end = min(num_kb, (ks + 1) * kb_per_split);
-          for (int kc = kb_begin; kc < kb_end; kc += kb_chunk) {
-            const int kc_end = min(kb_end, kc + kb_chunk);
-            ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);   // the epilogue has promoted this accumulator
+          ptx::mbar_wait(tempty_bar, acc_phase ^ 1);          // the epilogue has drained both accumulators
+          ptx::tc_fence_after();
+          for (int kb = kb_begin; kb < kb_end; ++kb) {
+            ptx::mbar_wait(&full_bar[stage], phase);          // TMA bytes have landed
             ptx::tc_fence_after();
-            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
-            for (int kb = kc; kb < kc_end; ++kb) {
-              ptx::mbar_wait(&full_bar[stage], phase);          // TMA bytes have landed
-              ptx::tc_fence_after();
-              const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
-              const uint64_t d_ahi = ptx::umma_desc_k_sw128(sa);
-              const uint64_t d_alo = ptx::umma_desc_k_sw128(sa + A_TILE_BYTES);
-              const uint64_t d_b = ptx::umma_desc_k_sw128(sa + 2 * A_TILE_BYTES);
+            const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
+            const uint64_t d_ahi = ptx::umma_desc_k_sw128(sa);
+            const uint64_t d_alo = ptx::umma_desc_k_sw128(sa + A_TILE_BYTES);
+            const uint64_t d_b = ptx::umma_desc_k_sw128(sa + 2 * A_TILE_BYTES);
 #pragma unroll
-              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // advance inside the swizzle row
-                ptx::mma_f16_ss(tmem_d, d_ahi + koff, d_b + koff, idesc, (kb != kc || k != 0) ? 1u : 0u);
-                if (two_pass) ptx::mma_f16_ss(tmem_d, d_alo + koff, d_b + koff, idesc, 1u);
-              }
-              ptx::mma_commit(&empty_bar[stage]);               // frees the smem slot when the MMAs retire
-              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // advance inside the swizzle row
+              const uint32_t accumulate = (kb != kb_begin || k != 0) ? 1u : 0u;
+              ptx::mma_f16_ss(tmem_h, d_ahi + koff, d_b + koff, idesc, accumulate);
+              if (two_pass) ptx::mma_f16_ss(tmem_l, d_alo + koff, d_b + koff, idesc, accumulate);
             }
-            ptx::mma_commit(&tfull_bar[acc]);                   // chunk complete -> promotion
-            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+            ptx::mma_commit(&empty_bar[stage]);               // frees the smem slot when the MMAs retire
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
+          ptx::mma_commit(tfull_bar);                         // accumulators complete -> epilogue
+          acc_phase ^= 1;
         }
       }
     }
@@ -307,8 +382,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     ptx::setmaxnreg_inc<REGS_EPI>();
     const int quarter = warp & 3;                   // TMEM lane quarter this warp may read
     const int half = (warp - EPI_WARP0) >> 2;       // column half of the work item this warp owns
-    int acc = 0; uint32_t acc_phase = 0;
-    float accv[4][32];                              // 128 partial sums: row m, columns half * bn/2 + [0, bn/2)
+    uint32_t acc_phase = 0;
+    float accv[4][32];                              // 128 sums: row m, columns half * bn/2 + [0, bn/2)
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
       const WorkItem wi = decode_work(w, num_tiles, num_full, k_splits);
       const int ks = wi.ks;
@@ -321,30 +396,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       const int n_half0 = tc.n_blk * BLOCK_N + wi.n_off + half * half_cols;
       const float bias_m = (p.bias != nullptr && m_ok) ? __ldg(p.bias + m) : 0.0f;
       const float acc_scale = p.acc_scale_dev ? p.acc_scale * __ldg(p.acc_scale_dev) : p.acc_scale;
-      const int kb_begin = ks * kb_per_split, kb_end = min(num_kb, (ks + 1) * kb_per_split);
-#pragma unroll
-      for (int s = 0; s < 4; ++s)
-#pragma unroll
-        for (int j = 0; j < 32; ++j) accv[s][j] = 0.0f;
 
-      for (int kc = kb_begin; kc < kb_end; kc += kb_chunk) {
-        ptx::mbar_wait(&tfull_bar[acc], acc_phase);
-        ptx::tc_fence_after();
-        const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * half_cols);
+      ptx::mbar_wait(tfull_bar, acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * half_cols);
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          if (s < n_slices) {                       // warp-uniform
-            uint32_t r[32];
-            ptx::tmem_ld_32x32(taddr0 + (uint32_t)(s * 32), r);
-            ptx::tmem_ld_wait();
+      for (int s = 0; s < 4; ++s) {
+        if (s < n_slices) {                         // warp-uniform
+          uint32_t rh[32], rl[32];
+          ptx::tmem_ld_32x32(taddr0 + (uint32_t)(s * 32), rh);
+          if (two_pass) ptx::tmem_ld_32x32(taddr0 + (uint32_t)(BLOCK_N + s * 32), rl);
+          ptx::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) accv[s][j] += __uint_as_float(r[j]);
-          }
+          for (int j = 0; j < 32; ++j) accv[s][j] = two_pass ? __uint_as_float(rh[j]) + __uint_as_float(rl[j]) : __uint_as_float(rh[j]);
         }
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&tempty_bar[acc]);         // 256 arrivals release the accumulator
-        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(tempty_bar);                 // 256 arrivals release the accumulators to the next tile's MMAs
+      acc_phase ^= 1;
 
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
@@ -412,6 +481,12 @@ int tc_gemm_launch(const TcGemmParams& p, int num_sms, cudaStream_t stream) {
     const int per = (num_kb + p.k_splits - 1) / p.k_splits;
     if ((p.k_splits - 1) * per >= num_kb) return -1000;     // an empty chunk would publish an unwritten accumulator
   }
+  if (p.opt.kind >= 0) {
+    if (p.k_splits > 1 || p.act || p.sample || !p.opt.theta || !p.opt.n_hi || !p.opt.n_lo || !p.opt.t_hi || !p.opt.t_lo ||
+        !p.opt.scale_dev || !p.opt.max_bits || (p.opt.ldt % 8) ||
+        ((reinterpret_cast<uintptr_t>(p.opt.t_hi) | reinterpret_cast<uintptr_t>(p.opt.t_lo)) & 15) ||
+        (p.opt.kind != DB_OPT_SGD && !p.opt.st) || (p.opt.kind == DB_OPT_ADAM && !p.opt.st2)) return -1000;
+  }
   if (p.out_sT16 && ((p.ldsT % 8) || (reinterpret_cast<uintptr_t>(p.out_sT16) & 15))) return -1000;
   if (p.out_pT_hi && ((p.ldpT % 8) || (reinterpret_cast<uintptr_t>(p.out_pT_hi) & 15) ||
                       (reinterpret_cast<uintptr_t>(p.out_pT_lo) & 15))) return -1000;
@@ -435,10 +510,6 @@ int tc_gemm_launch(const TcGemmParams& p, int num_sms, cudaStream_t stream) {
   TcGemmParams q = p;
   const int rem = base_tiles % grid;
   q.split_tail = (p.k_splits <= 1 && base_tiles > grid && rem > 0 && 2 * rem <= grid) ? 1 : 0;
-  if (q.kb_chunk <= 0) {
-    static const int env_chunk = [] { const char* e = getenv("DB_TC_KB_CHUNK"); return e ? atoi(e) : 0; }();   // diagnostics
-    q.kb_chunk = env_chunk > 0 ? env_chunk : KB_CHUNK;
-  }
   tc_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_a_hi, tm_a_lo, tm_b, tm_b_half, q);
   return (int)cudaGetLastError();
 }

@@ -5,12 +5,28 @@
 namespace db {
 
 // D[Ma, Nb] = A[Ma, K] * B[Nb, K]^T, both operands K-major fp16.
-//   A = the REAL operand, pre-scaled by a power of two and split into hi + lo (two MMA passes into
-//       one TMEM accumulator); a_lo == nullptr -> single pass.
+//   A = the REAL operand, pre-scaled by a power of two and split into hi + lo (two MMA passes, each into
+//       its own TMEM accumulator, summed once by the epilogue); a_lo == nullptr -> single pass.
 //   B = the EXACT operand (binary {0,1} states, exactly representable in fp16).
 // The epilogue sees D "transposed": thread <-> row m of D (a unit), registers <-> columns nb (batch
 // rows), so [Nb, Ma] row-major outputs (the layout every reference tensor uses, rbm.py:123-127) are
 // written with lane-contiguous stores and the [Ma, Nb] "T" outputs with per-thread vector stores.
+// Fused tail of the dW launch (north_star K2; rbm.py:664-670 cd_loss -> optimizer.minimize): the epilogue turns the
+// accumulated gradient tile straight into the parameter update and rewrites the split-weight cache, so W, the
+// optimizer slots and the four fp16 cache matrices make ONE pass through HBM per step, hidden under the MMAs.
+// Indexing is that of out32: element (nb, m) lives at nb * ld32 + m  ([V, H] row-major for the dW launch).
+struct TcOptArgs {
+  int kind;                   // -1: no fused update; else DB_OPT_SGD / DB_OPT_MOMENTUM / DB_OPT_ADAM
+  float lr, lr_t, momentum, beta1, beta2, eps, weight_decay;   // lr_t: bias-corrected Adam step size (host, fp64)
+  float* theta;               // parameters, updated in place
+  float* st; float* st2;      // optimizer slots (Momentum: st; Adam: st = m, st2 = v)
+  __half* n_hi; __half* n_lo; // [Nb, Ma] fp16 split of theta_new * scale   (W cache)
+  __half* t_hi; __half* t_lo; // [Ma, Nb] fp16 split of theta_new * scale   (W^T cache), leading dimension ldt
+  int ldt;
+  const float* scale_dev;     // power-of-two scale the cache is written with
+  unsigned int* max_bits;     // atomicMax of the bit pattern of |theta_new| (the next scale decision)
+};
+
 struct TcGemmParams {
   int Ma, Nb, K;
   const __half* a_hi; const __half* a_lo; int lda;   // [Ma, K]
@@ -28,7 +44,6 @@ struct TcGemmParams {
   // tensor core adds into its fp32 accumulator with truncation, a bias that grows with the number of
   // accumulation steps — chunking bounds it (measured: 1.2e-4 relative at K = 32768 unsplit).
   int k_splits; size_t split_stride;
-  int kb_chunk;               // k-blocks (64 columns) per TMEM accumulation chunk before the fp32 promotion; 0 = default (8)
   int split_tail;             // set by tc_gemm_launch: cut the tiles of a sparse last wave into 128-column halves
   __half* out_s16; int lds16;         // [Nb, Ma] fp16 sample (sample==1) or value
   // "T" outputs [Ma, 2*Nb_pad] hold the two ends of the CD chain INTERLEAVED in blocks of 64 columns:
@@ -36,6 +51,7 @@ struct TcGemmParams {
   // so the dW GEMM alternates +v0 p0 and -vk pk blocks along K and its fp32 partial sums stay small.
   __half* out_sT16; int ldsT; int sT_phase;    // fp16 sample, row-wise
   __half* out_pT_hi; __half* out_pT_lo; int ldpT; int pT_phase; float pT_scale;   // split of value*pT_scale
+  TcOptArgs opt;              // opt.kind < 0 (set by every caller but the fused dW launch): unused
 };
 
 __host__ __device__ __forceinline__ int tc_interleaved_col(int nb, int phase) {

@@ -6,7 +6,7 @@ from deepbelief_b200 import ops
 V, H, k = 4096, 8192, 10
 W = torch.randn(V, H, device='cuda') * 0.01
 params = torch.cat([W.reshape(-1), torch.zeros(V + H, device='cuda')]).contiguous()
-for N in (2048, 4096, 8192, 16384):
+for N in [int(x) for x in os.environ.get('NS', '2048,4096,8192,16384').split(',')]:
     v0 = (torch.rand(N, V, device='cuda') < 0.5).float()
     plan = ops.CdTcPlan(N, V, H, k, n_global=16384)
     plan.refresh_weights(params)
