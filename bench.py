@@ -309,15 +309,11 @@ def run_b200(args):
     def one_step(i, timed_idx=None):
         if timed_idx is not None:
             chain_ev[timed_idx][0].record()
-        if world == 1:
-            rbm.cd_step(pool[i % 2], K_GIBBS, grad=grad, n_global=N_GLOBAL)
-            if timed_idx is not None:
-                chain_ev[timed_idx][1].record()
-            rbm.apply_gradient(optimizer, grad, opt_state)
-        else:       # RBM.cd_update = cd_step + NCCL all-reduce + optimizer; the events bracket the whole update
-            rbm.cd_update(pool[i % 2], K_GIBBS, optimizer, opt_state, grad, n_global=N_GLOBAL)
-            if timed_idx is not None:
-                chain_ev[timed_idx][1].record()
+        # RBM.cd_update: one process = chain + dW with the optimizer and the split-weight refresh fused into its epilogue
+        # (db_cd_tc_step_update); several = chain + dW, NCCL all-reduce, optimizer, refresh. The events bracket the whole update.
+        rbm.cd_update(pool[i % 2], K_GIBBS, optimizer, opt_state, grad, n_global=N_GLOBAL)
+        if timed_idx is not None:
+            chain_ev[timed_idx][1].record()
 
     for i in range(Wm):
         one_step(i)
@@ -529,7 +525,7 @@ def run_b200(args):
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                          'frac': achieved / peak, 'traffic': traffic,
                          'traffic_unit': 'bytes per tc_gemm_kernel launch (ncu dram read+write, profiles/r01_tc_gemm_traffic.json)',
-                         'kernel': 'tc_gemm_kernel (22 launches per step: 21 chain GEMMs + dW)',
+                         'kernel': 'tc_gemm_kernel (22 launches per step: 21 chain GEMMs + dW with the fused update)',
                          'peak_source': 'MEASURED_PEAKS.json bf16 sustained (%s); fp16 runs at the bf16 rate'
                                         % peaks['source'],
                          'executed_tflops': 2.0 * achieved,
@@ -540,7 +536,7 @@ def run_b200(args):
                          'note': 'achieved counts ALGORITHMIC flop (2k+3)*2*N*V*H; every MMA is issued twice '
                                  '(hi and lo half of the split real operand), so the tensor pipe executes 2x',
                          'chain_ms_per_step': chain_ms,
-                         'timed_region': 'db_cd_tc_step call (chain + dW + weight refresh)' if world == 1 else
+                         'timed_region': 'db_cd_tc_step_update call (chain + dW with fused optimizer and cache rewrite)' if world == 1 else
                                          'whole update incl. NCCL all-reduce and optimizer (conservative)'},
             'cpu_baseline': cpu,
             'clocks': clocks,

@@ -72,6 +72,10 @@ SIGNATURES = {
     'db_cd_tc_step': (c_int, [c_void_p, c_void_p, ctypes.POINTER(db_cd_tc_desc_t), c_float_p, c_float_p, c_void_p,
                               c_void_p, c_float_p, ctypes.POINTER(db_rng_t), c_void_p, c_float_p, c_float_p,
                               c_float_p, c_float_p, c_float_p]),
+    'db_cd_tc_step_update': (c_int, [c_void_p, c_void_p, ctypes.POINTER(db_cd_tc_desc_t), c_float_p, c_float_p, c_void_p,
+                                     c_void_p, c_float_p, ctypes.POINTER(db_rng_t), c_void_p, c_float_p,
+                                     ctypes.POINTER(db_opt_t), c_float_p]),
+    'db_cd_tc_update_fusable': (c_int, [ctypes.POINTER(db_cd_tc_desc_t)]),
     'db_cd_tc_dw': (c_int, [c_void_p, c_void_p, ctypes.POINTER(db_cd_tc_desc_t), c_void_p, c_float_p, c_int, c_int]),
     'db_set_sm_limit': (c_int, [c_void_p, c_int]),
     'db_optimizer_step_range': (c_int, [c_void_p, c_void_p, ctypes.POINTER(db_opt_t), c_float_p, c_float_p, c_float_p,

@@ -21,8 +21,10 @@ constexpr float kProbScale = 16384.0f;   // 2^14: p in (0,1) -> fp16 normal rang
 struct WeightCacheHeader {
   float scale;       // 2^e
   float inv_scale;   // 2^-e
-  unsigned int max_bits;
-  unsigned int pad[61];
+  unsigned int max_bits;       // bit pattern of max |W| the scale was chosen from
+  unsigned int new_max_bits;   // max |W_new| collected by the fused dW epilogue (db_cd_tc_step_update)
+  unsigned int resplit;        // set by rescale_after_update_kernel: the scale moved, the cache must be re-split
+  unsigned int pad[59];
 };
 static_assert(sizeof(WeightCacheHeader) == 256, "header is one 256-byte slot");
 
@@ -92,16 +94,35 @@ __global__ void absmax_kernel(const float* __restrict__ x, size_t n, unsigned in
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));   // non-negative floats order as uints
 }
-__global__ void choose_scale_kernel(WeightCacheHeader* hdr) {
-  const float m = __uint_as_float(hdr->max_bits);
+__device__ __forceinline__ int scale_exponent(float m) {
   int e = 0;
   if (m > 0.0f && isfinite(m)) {
     int q; frexpf(m, &q);           // m = f * 2^q, f in [0.5, 1)  ->  m * 2^(14-q) in [2^13, 2^14)
     e = 14 - q;
     e = max(-100, min(100, e));
   }
+  return e;
+}
+__global__ void choose_scale_kernel(WeightCacheHeader* hdr) {
+  const int e = scale_exponent(__uint_as_float(hdr->max_bits));
   hdr->scale = ldexpf(1.0f, e);
   hdr->inv_scale = ldexpf(1.0f, -e);
+  hdr->new_max_bits = 0u;
+  hdr->resplit = 0u;
+}
+// After a fused update: the epilogue wrote the cache with the scale in the header and collected max |W_new|. The scale
+// rule is that of db_cd_tc_refresh_weights (a function of max |W| alone), so whenever the new maximum keeps the
+// exponent the cache is already what a refresh would produce; when it crosses a power of two the cache is re-split
+// by the guarded cvt_transpose launch that follows (values up to 4x over the old maximum are still finite fp16, and
+// anything beyond is overwritten by that re-split).
+__global__ void rescale_after_update_kernel(WeightCacheHeader* hdr) {
+  const float m = __uint_as_float(hdr->new_max_bits);
+  const float sc = ldexpf(1.0f, scale_exponent(m));
+  hdr->resplit = (sc != hdr->scale) ? 1u : 0u;
+  hdr->scale = sc;
+  hdr->inv_scale = 1.0f / sc;
+  hdr->max_bits = hdr->new_max_bits;
+  hdr->new_max_bits = 0u;
 }
 
 // ---- fp32 [R,C] -> fp16 row-major copy and/or fp16 transposed copy, optional hi/lo split ----------
@@ -110,7 +131,9 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(256) cvt_transpose_kernel(const float* __restrict__ src, int R, int C,
                                                             const float* __restrict__ scale_dev, __half* __restrict__ d_hi,
                                                             __half* __restrict__ d_lo, int ldd, __half* __restrict__ t_hi,
-                                                            __half* __restrict__ t_lo, int ldt, int t_interleave_phase) {
+                                                            __half* __restrict__ t_lo, int ldt, int t_interleave_phase,
+                                                            const unsigned int* __restrict__ guard) {
+  if (guard != nullptr && __ldg(guard) == 0u) return;      // conditional re-split (rescale_after_update_kernel)
   __shared__ float tile[32][33];
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
@@ -143,9 +166,24 @@ __global__ void __launch_bounds__(256) cvt_transpose_kernel(const float* __restr
 // ---- bias gradients from the interleaved T buffers: one warp per unit ------------------------------
 // gb[v] = -inv_n * (sum_n v0[n,v] - sum_n vk[n,v])          (sign from the phase of each 64-block)
 // gc[h] = -inv_n * 2^-14 * sum_cols (PT_hi + PT_lo)[h,:]     (phase-1 entries are stored negated)
+// upd.kind >= 0: the same thread then applies the optimizer rule to its bias (b | c are contiguous behind W in the packed
+// parameter vector, so unit indexes both; same expressions as optimizer_kernel, layer_simt.cu)
+struct BiasUpdate {
+  int kind;                    // -1: gradients only
+  float lr, lr_t, momentum, beta1, beta2, eps, weight_decay;
+  float* theta; float* st; float* st2;      // each already offset to the first bias
+};
+__device__ __forceinline__ void bias_update(const BiasUpdate& u, int unit, float g) {
+  if (u.kind < 0) return;
+  const OptRule rule{u.kind, u.lr, u.lr_t, u.momentum, u.beta1, u.beta2, u.eps, u.weight_decay};
+  float s1 = u.kind != DB_OPT_SGD ? u.st[unit] : 0.0f, s2 = u.kind == DB_OPT_ADAM ? u.st2[unit] : 0.0f;
+  u.theta[unit] = opt_apply(rule, u.theta[unit], g, s1, s2);
+  if (u.kind != DB_OPT_SGD) u.st[unit] = s1;
+  if (u.kind == DB_OPT_ADAM) u.st2[unit] = s2;
+}
 __global__ void tc_bias_grads_kernel(const __half* __restrict__ vt, const __half* __restrict__ pt_hi,
                                      const __half* __restrict__ pt_lo, int V, int H, int ld, float inv_n,
-                                     float* __restrict__ gb, float* __restrict__ gc) {
+                                     float* __restrict__ gb, float* __restrict__ gc, const BiasUpdate upd) {
   const int unit = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   const int lane = threadIdx.x & 31;
   if (unit >= V + H) return;
@@ -161,7 +199,7 @@ __global__ void tc_bias_grads_kernel(const __half* __restrict__ vt, const __half
       s += ((c >> 6) & 1) ? -t : t;
     }
     s = warp_sum(s);
-    if (lane == 0) gb[unit] = -inv_n * s;
+    if (lane == 0) { const float g = -inv_n * s; gb[unit] = g; bias_update(upd, unit, g); }
   } else {
     const int hrow = unit - V;
     const __half* rh = pt_hi + (size_t)hrow * ld;
@@ -179,7 +217,7 @@ __global__ void tc_bias_grads_kernel(const __half* __restrict__ vt, const __half
       }
     }
     s = warp_sum(shi) + warp_sum(slo);
-    if (lane == 0) gc[hrow] = -inv_n * (1.0f / kProbScale) * s;
+    if (lane == 0) { const float g = -inv_n * (1.0f / kProbScale) * s; gc[hrow] = g; bias_update(upd, unit, g); }
   }
 }
 
@@ -212,10 +250,12 @@ inline bool tc_shape_ok(int N, int V, int H) { return N >= 8 && (N % 8 == 0) && 
 // dW[v,h] = -(1/N) (v0^T p0 - vk^T pk) for rows v in [v_begin, v_begin + v_count): one GEMM over the interleaved
 // K = 2*NP axis (K-chunked, see dw_splits)
 int launch_dw(db_handle_t h, cudaStream_t st, const db_cd_tc_desc_t* d, const ChainWorkspace& ws, float* gW, int v_begin,
-              int v_count) {
+              int v_count, const TcOptArgs* fused = nullptr) {
   const int V = d->V, H = d->H;
   const int ldT = 2 * ws.NP;
   TcGemmParams p{};
+  p.opt.kind = -1;
+  if (fused) p.opt = *fused;
   p.Ma = H; p.Nb = v_count; p.K = ldT;
   p.a_hi = ws.pt_hi; p.a_lo = ws.pt_lo; p.lda = ldT; p.b = ws.vt + (size_t)v_begin * ldT; p.ldb = ldT;
   p.acc_scale = -d->inv_global_n / kProbScale; p.act = 0; p.sample = 0;
@@ -257,14 +297,16 @@ extern "C" int db_cd_tc_refresh_weights(db_handle_t h, db_stream_t stream, const
   absmax_kernel<<<ew_grid(n, h->num_sms), 256, 0, st>>>(W, n, &wc.hdr->max_bits);
   choose_scale_kernel<<<1, 1, 0, st>>>(wc.hdr);
   dim3 grid((H + 31) / 32, (V + 31) / 32);
-  cvt_transpose_kernel<true><<<grid, 256, 0, st>>>(W, V, H, &wc.hdr->scale, wc.w_hi, wc.w_lo, H, wc.wt_hi, wc.wt_lo, V, -1);
+  cvt_transpose_kernel<true><<<grid, 256, 0, st>>>(W, V, H, &wc.hdr->scale, wc.w_hi, wc.w_lo, H, wc.wt_hi, wc.wt_lo, V, -1, nullptr);
   return check_launch(h, "cd_tc_refresh_weights");
 }
 
-extern "C" int db_cd_tc_step(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, const float* v0,
-                             const float* params, const void* weight_cache, void* pcd_state, const float* injected,
-                             const db_rng_t* rng, void* workspace, float* grad, float* vk_out, float* hk_out,
-                             float* p0_out, float* pk_out) {
+// opt != nullptr: the fused update (db_cd_tc_step_update) — params, opt_state and the weight cache are rewritten by the
+// dW epilogue and the bias kernel; otherwise gradients only (db_cd_tc_step).
+static int cd_tc_step_impl(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, const float* v0,
+                           float* params, void* weight_cache, void* pcd_state, const float* injected,
+                           const db_rng_t* rng, void* workspace, float* grad, float* vk_out, float* hk_out,
+                           float* p0_out, float* pk_out, const db_opt_t* opt, float* opt_state) {
   DB_REQUIRE(h, d && v0 && params && weight_cache && workspace && grad, "null operand");
   DB_REQUIRE(h, d->k >= 1, "k must be > 0");   // rbm.py:364
   DB_REQUIRE(h, injected || rng, "sampling needs injected draws or an rng");
@@ -275,7 +317,7 @@ extern "C" int db_cd_tc_step(db_handle_t h, db_stream_t stream, const db_cd_tc_d
   if (!injected && (rng->row_offset & 3u)) return set_err(h, DB_ERR_UNSUPPORTED, "row_offset must be a multiple of 4");
   cudaStream_t st = (cudaStream_t)stream;
 
-  WeightCacheView wc = weight_cache_view(const_cast<void*>(weight_cache), V, H);
+  WeightCacheView wc = weight_cache_view(weight_cache, V, H);
   ChainWorkspace ws = chain_workspace(workspace, N, V, H);
   const int ldT = 2 * ws.NP;
   const float* b = params + (size_t)V * H;
@@ -298,12 +340,13 @@ extern "C" int db_cd_tc_step(db_handle_t h, db_stream_t stream, const db_cd_tc_d
   }
   {  // data batch -> fp16 [N,V] and interleaved phase 0 of VT
     dim3 grid((V + 31) / 32, (N + 31) / 32);
-    cvt_transpose_kernel<false><<<grid, 256, 0, st>>>(v0, N, V, nullptr, ws.v0b, nullptr, V, ws.vt, nullptr, ldT, 0);
+    cvt_transpose_kernel<false><<<grid, 256, 0, st>>>(v0, N, V, nullptr, ws.v0b, nullptr, V, ws.vt, nullptr, ldT, 0, nullptr);
   }
 
   auto up = [&](const __half* vin, int phase /*-1: middle of chain*/, bool write_sample, const float* U, uint64_t draw_i,
                 float* p_out) -> int {
     TcGemmParams p{};
+    p.opt.kind = -1;
     p.Ma = H; p.Nb = N; p.K = V;
     p.a_hi = wc.wt_hi; p.a_lo = wc.wt_lo; p.lda = V; p.b = vin; p.ldb = V;
     p.acc_scale = 1.0f; p.acc_scale_dev = &wc.hdr->inv_scale; p.bias = c; p.act = 1;
@@ -318,6 +361,7 @@ extern "C" int db_cd_tc_step(db_handle_t h, db_stream_t stream, const db_cd_tc_d
   };
   auto down = [&](bool last, const float* U, uint64_t draw_i) -> int {
     TcGemmParams p{};
+    p.opt.kind = -1;
     p.Ma = V; p.Nb = N; p.K = H;
     p.a_hi = wc.w_hi; p.a_lo = wc.w_lo; p.lda = H; p.b = hstate; p.ldb = H;
     p.acc_scale = 1.0f; p.acc_scale_dev = &wc.hdr->inv_scale; p.bias = b; p.act = 1;
@@ -337,14 +381,72 @@ extern "C" int db_cd_tc_step(db_handle_t h, db_stream_t stream, const db_cd_tc_d
     rc = up(ws.vb, s == k ? 1 : -1, true, Uh, (uint64_t)(2 * s), s == k ? pk_out : nullptr);
     if (rc) return set_err(h, DB_ERR_CUDA, "cd_tc up launch failed (%d)", rc);
   }
-  if (!d->defer_dw) {
+  BiasUpdate bu{};
+  bu.kind = -1;
+  if (opt) {
+    // north_star K2: dW accumulation and the optimizer update in ONE kernel. The epilogue of the dW GEMM applies the rule
+    // to W and rewrites the fp16 split-weight cache (W and W^T); the bias kernel does the same for b | c.
+    const size_t n_total = (size_t)V * H + V + H, nW = (size_t)V * H;
+    float lr_t = opt->lr;
+    if (opt->kind == DB_OPT_ADAM) {    // TF AdamOptimizer: lr_t = lr sqrt(1 - b2^t) / (1 - b1^t) [TF, not vendored]; as db_optimizer_step
+      const double b1t = pow((double)opt->beta1, opt->step), b2t = pow((double)opt->beta2, opt->step);
+      lr_t = (float)((double)opt->lr * sqrt(1.0 - b2t) / (1.0 - b1t));
+    }
+    TcOptArgs fo{};
+    fo.kind = opt->kind; fo.lr = opt->lr; fo.lr_t = lr_t; fo.momentum = opt->momentum; fo.beta1 = opt->beta1; fo.beta2 = opt->beta2;
+    fo.eps = opt->eps; fo.weight_decay = opt->weight_decay;
+    fo.theta = params;
+    fo.st = opt->kind != DB_OPT_SGD ? opt_state : nullptr;
+    fo.st2 = opt->kind == DB_OPT_ADAM ? opt_state + n_total : nullptr;
+    fo.n_hi = wc.w_hi; fo.n_lo = wc.w_lo; fo.t_hi = wc.wt_hi; fo.t_lo = wc.wt_lo; fo.ldt = V;
+    fo.scale_dev = &wc.hdr->scale; fo.max_bits = &wc.hdr->new_max_bits;
+    bu.kind = opt->kind; bu.lr = opt->lr; bu.lr_t = lr_t; bu.momentum = opt->momentum; bu.beta1 = opt->beta1; bu.beta2 = opt->beta2;
+    bu.eps = opt->eps; bu.weight_decay = opt->weight_decay;
+    bu.theta = params + nW; bu.st = fo.st ? fo.st + nW : nullptr; bu.st2 = fo.st2 ? fo.st2 + nW : nullptr;
+    rc = launch_dw(h, st, d, ws, gW, 0, V, &fo);
+    if (rc) return rc;
+  } else if (!d->defer_dw) {
     rc = launch_dw(h, st, d, ws, gW, 0, V);
     if (rc) return rc;
   }
-  tc_bias_grads_kernel<<<(V + H + 7) / 8, 256, 0, st>>>(ws.vt, ws.pt_hi, ws.pt_lo, V, H, ldT, d->inv_global_n, gb, gc);
+  tc_bias_grads_kernel<<<(V + H + 7) / 8, 256, 0, st>>>(ws.vt, ws.pt_hi, ws.pt_lo, V, H, ldT, d->inv_global_n, gb, gc, bu);
+  if (opt) {
+    rescale_after_update_kernel<<<1, 1, 0, st>>>(wc.hdr);
+    dim3 grid((H + 31) / 32, (V + 31) / 32);
+    cvt_transpose_kernel<true><<<grid, 256, 0, st>>>(params, V, H, &wc.hdr->scale, wc.w_hi, wc.w_lo, H, wc.wt_hi, wc.wt_lo, V, -1,
+                                                     &wc.hdr->resplit);
+  }
   if (vk_out) half_to_float_kernel<<<ew_grid(NV, h->num_sms), 256, 0, st>>>(ws.vb, NV, vk_out);
   if (hk_out) half_to_float_kernel<<<ew_grid(NH, h->num_sms), 256, 0, st>>>(hstate, NH, hk_out);
   return check_launch(h, "cd_tc_step");
+}
+
+extern "C" int db_cd_tc_step(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, const float* v0,
+                             const float* params, const void* weight_cache, void* pcd_state, const float* injected,
+                             const db_rng_t* rng, void* workspace, float* grad, float* vk_out, float* hk_out,
+                             float* p0_out, float* pk_out) {
+  return cd_tc_step_impl(h, stream, d, v0, const_cast<float*>(params), const_cast<void*>(weight_cache), pcd_state, injected, rng,
+                         workspace, grad, vk_out, hk_out, p0_out, pk_out, nullptr, nullptr);
+}
+
+extern "C" int db_cd_tc_update_fusable(const db_cd_tc_desc_t* d) {
+  if (!d || !tc_shape_ok(d->N, d->V, d->H)) return 0;
+  return dw_splits(2 * ((d->N + 63) / 64 * 64), d->V, d->H) == 1 ? 1 : 0;
+}
+
+extern "C" int db_cd_tc_step_update(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, const float* v0,
+                                    float* params, void* weight_cache, void* pcd_state, const float* injected,
+                                    const db_rng_t* rng, void* workspace, float* grad, const db_opt_t* opt,
+                                    float* opt_state) {
+  DB_REQUIRE(h, d && opt, "null operand");
+  DB_REQUIRE(h, opt->kind == DB_OPT_SGD || opt->kind == DB_OPT_MOMENTUM || opt->kind == DB_OPT_ADAM, "unknown optimizer kind");
+  DB_REQUIRE(h, opt->kind == DB_OPT_SGD || opt_state, "the optimizer rule needs its slot buffer");
+  if (opt->clock) return set_err(h, DB_ERR_UNSUPPORTED, "the fused update takes the step number by value (no device clock)");
+  if (d->defer_dw) return set_err(h, DB_ERR_UNSUPPORTED, "defer_dw and the fused update exclude each other");
+  if (!db_cd_tc_update_fusable(d))
+    return set_err(h, DB_ERR_UNSUPPORTED, "dW of this shape runs as K-split partial products; use db_cd_tc_step + db_optimizer_step");
+  return cd_tc_step_impl(h, stream, d, v0, params, weight_cache, pcd_state, injected, rng, workspace, grad, nullptr, nullptr,
+                         nullptr, nullptr, opt, opt_state);
 }
 
 extern "C" int db_cd_tc_dw(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, void* workspace, float* grad,

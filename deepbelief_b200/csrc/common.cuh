@@ -125,6 +125,24 @@ __device__ __forceinline__ void split_f16(float xs, __half& hi, __half& lo) {
   lo = __float2half_rn(xs - __half2float(hi));
 }
 
+// ---- optimizer rule (rbm.py:107-117, 664-670; TF GradientDescent / Momentum / Adam update formulas [TF, not vendored]) ----
+// One element: parameter t, gradient g, slots s1 / s2 (Momentum: accumulator; Adam: m, v). Written with explicit
+// round-to-nearest intrinsics so that the stand-alone optimizer kernel, the epilogue of the fused dW kernel and the bias
+// kernel produce the same bits whatever the compiler would otherwise contract into FMAs around them.
+// kind: 0 SGD, 1 Momentum, 2 Adam (DB_OPT_*). lr_t: bias-corrected Adam step size.
+struct OptRule { int kind; float lr, lr_t, momentum, beta1, beta2, eps, weight_decay; };
+__device__ __forceinline__ float opt_apply(const OptRule& o, float t, float g, float& s1, float& s2) {
+  const float gi = __fmaf_rn(o.weight_decay, t, g);
+  if (o.kind == 0) return __fmaf_rn(-o.lr, gi, t);
+  if (o.kind == 1) {
+    s1 = __fmaf_rn(o.momentum, s1, gi);
+    return __fmaf_rn(-o.lr, s1, t);
+  }
+  s1 = __fmaf_rn(o.beta1, s1, __fmul_rn(1.0f - o.beta1, gi));
+  s2 = __fmaf_rn(o.beta2, s2, __fmul_rn(__fmul_rn(1.0f - o.beta2, gi), gi));
+  return __fsub_rn(t, __fdiv_rn(__fmul_rn(o.lr_t, s1), __fadd_rn(__fsqrt_rn(s2), o.eps)));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

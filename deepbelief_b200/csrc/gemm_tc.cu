@@ -30,6 +30,7 @@
 //   warps 4-11: epilogue       (tcgen05.ld of H and L + add, release; then scale+bias -> logistic -> Philox/injected
 //                               uniform -> compare -> global stores), overlapped with the next tile's MMAs.
 //                               Warp w owns TMEM lanes 32 (w % 4) .. +32 and the column half (w - 4) / 4 of the tile.
+#include "../../include/deepbelief_b200.h"
 #include "gemm_tc.cuh"
 #include "ptx.cuh"
 #include <cuda.h>
@@ -133,13 +134,14 @@ __device__ __forceinline__ void epilogue_slice(const TcGemmParams& p, float (&va
   if (p.opt.kind >= 0) {
     const TcOptArgs& o = p.opt;
     const float sc = __ldg(o.scale_dev);
+    const OptRule rule{o.kind, o.lr, o.lr_t, o.momentum, o.beta1, o.beta2, o.eps, o.weight_decay};
     float mx = 0.0f;
     if (m_ok) {
 #pragma unroll
-      for (int j0 = 0; j0 < 32; j0 += 8) {
-        float th[8], a[8], b[8];
+      for (int j0 = 0; j0 < 32; j0 += 4) {
+        float th[4], a[4], b[4];
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {          // all loads of the group first
+        for (int jj = 0; jj < 4; ++jj) {          // all loads of the group first
           const bool ok = nb0 + j0 + jj < p.Nb;
           const size_t idx = (size_t)(nb0 + j0 + jj) * p.ld32 + m;
           th[jj] = ok ? o.theta[idx] : 0.0f;
@@ -147,23 +149,13 @@ __device__ __forceinline__ void epilogue_slice(const TcGemmParams& p, float (&va
           b[jj] = (ok && o.kind == DB_OPT_ADAM) ? o.st2[idx] : 0.0f;
         }
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
+        for (int jj = 0; jj < 4; ++jj) {
           if (nb0 + j0 + jj >= p.Nb) { val[j0 + jj] = 0.0f; continue; }
           const size_t idx = (size_t)(nb0 + j0 + jj) * p.ld32 + m;
-          float t = th[jj];
-          const float gi = val[j0 + jj] + o.weight_decay * t;      // same expressions as optimizer_kernel (layer_simt.cu)
-          if (o.kind == DB_OPT_SGD) {
-            t -= o.lr * gi;
-          } else if (o.kind == DB_OPT_MOMENTUM) {
-            const float acc = o.momentum * a[jj] + gi;
-            o.st[idx] = acc;
-            t -= o.lr * acc;
-          } else {
-            const float mm = o.beta1 * a[jj] + (1.0f - o.beta1) * gi;
-            const float vv = o.beta2 * b[jj] + (1.0f - o.beta2) * gi * gi;
-            o.st[idx] = mm; o.st2[idx] = vv;
-            t -= o.lr_t * mm / (sqrtf(vv) + o.eps);
-          }
+          float s1 = a[jj], s2 = b[jj];
+          const float t = opt_apply(rule, th[jj], val[j0 + jj], s1, s2);
+          if (o.kind != DB_OPT_SGD) o.st[idx] = s1;
+          if (o.kind == DB_OPT_ADAM) o.st2[idx] = s2;
           o.theta[idx] = t;
           mx = fmaxf(mx, fabsf(t));
           val[j0 + jj] = t * sc;

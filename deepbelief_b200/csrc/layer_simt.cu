@@ -289,22 +289,13 @@ __global__ void optimizer_kernel(db_opt_t o, float lr_t, float* __restrict__ p, 
     __syncthreads();
     lr_t = lr_sh;
   }
+  static_assert(DB_OPT_SGD == 0 && DB_OPT_MOMENTUM == 1 && DB_OPT_ADAM == 2, "opt_apply (common.cuh) uses these values");
+  const OptRule rule{o.kind, o.lr, lr_t, o.momentum, o.beta1, o.beta2, o.eps, o.weight_decay};
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    float th = p[i];
-    float gi = __ldg(g + i) + o.weight_decay * th;
-    if (o.kind == DB_OPT_SGD) {
-      th -= o.lr * gi;
-    } else if (o.kind == DB_OPT_MOMENTUM) {
-      float a = o.momentum * st[i] + gi;
-      st[i] = a;
-      th -= o.lr * a;
-    } else {
-      float m = o.beta1 * st[i] + (1.0f - o.beta1) * gi;
-      float v = o.beta2 * st2[i] + (1.0f - o.beta2) * gi * gi;
-      st[i] = m; st2[i] = v;
-      th -= lr_t * m / (sqrtf(v) + o.eps);
-    }
-    p[i] = th;
+    float s1 = o.kind != DB_OPT_SGD ? st[i] : 0.0f, s2 = o.kind == DB_OPT_ADAM ? st2[i] : 0.0f;
+    p[i] = opt_apply(rule, p[i], __ldg(g + i), s1, s2);
+    if (o.kind != DB_OPT_SGD) st[i] = s1;
+    if (o.kind == DB_OPT_ADAM) st2[i] = s2;
   }
 }
 

@@ -581,6 +581,8 @@ class RBM(layer.Layer):
     # one 134 MB call and the dW GEMM loses the reserved SMs, so the pipelined step (4.85-5.00 ms) is SLOWER than
     # the plain one (4.77 ms). The plain path is therefore the default; DW_CHUNKS > 1 enables the pipeline.
     DW_CHUNKS = 1
+    # single-process tensor-core steps run the optimizer inside the dW kernel (False: separate optimizer + refresh launches)
+    FUSED_UPDATE = True
 
     def cd_update(self, v_0_batch, k, optimizer, opt_state, grad, n_global=None, lr=None, persistent=None):
         """One full CD-k update: chain, gradient, (data-parallel) sum over ranks, optimizer step.
@@ -591,6 +593,16 @@ class RBM(layer.Layer):
         _, world = _dist_info()
         v0 = to_device(v_0_batch, self.device)
         n = v0.shape[0]
+        if (world == 1 and persistent is None and self._tc_eligible(n) and self.FUSED_UPDATE and
+                self._trainable_pair(grad)[0] is self._params):
+            # one process, tensor-core path: the dW kernel applies the optimizer rule and rewrites the split-weight cache
+            # in its epilogue (db_cd_tc_step_update); bit-identical to cd_step + apply_gradient + refresh_weights
+            plan = self._tc_plan_for(n, k, n_global or n)
+            if plan.update_fusable() and getattr(optimizer, 'clock', None) is None:
+                plan.step_update(v0, self._params, grad, optimizer.descriptor(lr), opt_state, rng=self.rng)
+                self._after_update()
+                plan.version = self._weights_version          # the cache already holds the updated weights
+                return
         chunk_rows = (self.num_v // max(self.DW_CHUNKS, 1)) // 256 * 256
         if world == 1 or self.DW_CHUNKS <= 1 or persistent is not None or not self._tc_eligible(n) or chunk_rows < 256:
             self.cd_step(v0, k, persistent, grad=grad, n_global=n_global)

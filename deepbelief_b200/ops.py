@@ -207,6 +207,23 @@ class CdTcPlan:
         L.check(rc, 'db_cd_tc_step')
         return grad
 
+    def update_fusable(self):
+        """True when the dW kernel of this shape can carry the optimizer update in its epilogue (db_cd_tc_step_update)."""
+        return bool(L.lib().db_cd_tc_update_fusable(ctypes.byref(self.desc)))
+
+    def step_update(self, v0, params, grad, opt, opt_state, injected=None, rng=None):
+        """step() + optimizer step + split-weight refresh in the chain's own launches (north-star K2): the dW epilogue
+        updates W / the optimizer slots / the fp16 cache, the bias kernel updates b | c. `params` and `opt_state` are
+        modified in place; `grad` receives the packed gradient as step() would."""
+        self.desc.defer_dw = 0
+        r = rng.next(2 * self.k + 1) if (rng is not None and injected is None) else None
+        rc = L.lib().db_cd_tc_step_update(
+            L.handle(), L.stream(), ctypes.byref(self.desc), L.fptr(v0), L.fptr(params), L.ptr(self.cache),
+            L.ptr(self.pcd_state), L.fptr(injected), ctypes.byref(r) if r is not None else None,
+            L.ptr(self.workspace), L.fptr(grad), ctypes.byref(opt), L.fptr(opt_state))
+        L.check(rc, 'db_cd_tc_step_update')
+        return grad
+
     def dw(self, grad, v_begin, v_count):
         """dW rows [v_begin, v_begin + v_count) of the packed gradient from the chain ends of the last step()."""
         rc = L.lib().db_cd_tc_dw(L.handle(), L.stream(), ctypes.byref(self.desc), L.ptr(self.workspace), L.fptr(grad),

@@ -174,6 +174,19 @@ int db_cd_tc_step(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, c
                   const float* injected, const db_rng_t* rng, void* workspace, float* grad,
                   float* vk_out, float* hk_out, float* p0_out, float* pk_out);
 
+/* North-star K2, fused: db_cd_tc_step whose dW kernel also applies the optimizer rule (rbm.py:664-670: cd_loss ->
+ * optimizer.minimize) to the packed parameters IN PLACE and rewrites the split-weight cache, so the following step needs no
+ * db_optimizer_step / db_cd_tc_refresh_weights. opt_state: as db_optimizer_step (Momentum n floats, Adam 2n, n = V*H+V+H).
+ * grad still receives the packed gradient. Results are bit-identical to db_cd_tc_step + db_optimizer_step +
+ * db_cd_tc_refresh_weights. opt->clock must be NULL. DB_ERR_UNSUPPORTED when db_cd_tc_update_fusable(d) == 0. */
+int db_cd_tc_step_update(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, const float* v0,
+                         float* params, void* weight_cache, void* pcd_state,
+                         const float* injected, const db_rng_t* rng, void* workspace, float* grad,
+                         const db_opt_t* opt, float* opt_state);
+/* 1 when the dW product of this shape runs as one work item per tile (enough 128x256 tiles to fill the GPU), which the
+ * fused update needs; 0 when it runs K-split (small layers). */
+int db_cd_tc_update_fusable(const db_cd_tc_desc_t* d);
+
 /* dW rows [v_begin, v_begin + v_count) of the packed gradient, from the chain ends left in `workspace` by a
  * db_cd_tc_step call made with defer_dw = 1. */
 int db_cd_tc_dw(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, void* workspace, float* grad,

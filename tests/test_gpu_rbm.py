@@ -671,3 +671,60 @@ def test_bgrbmsv_shared_sigma(horses):
               None, num_gibbs_steps=1, pcd=False, max_iterations=3)
     np.testing.assert_allclose(_np(fed.sigma_h), np.full((1, H), 0.7), rtol=1e-6)
     assert not np.array_equal(_np(fed.W), W)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_cuda(), reason='needs a CUDA device')
+@pytest.mark.parametrize('kind', ['sgd', 'momentum', 'adam'])
+def test_fused_update_is_bit_identical_to_step_plus_optimizer(kind):
+    """North-star K2 (db_cd_tc_step_update): the dW kernel whose epilogue applies the optimizer rule and rewrites the
+    split-weight cache, and the bias kernel that updates b | c, against db_cd_tc_step + db_optimizer_step +
+    db_cd_tc_refresh_weights (rbm.py:664-670) on the same Philox draws: parameters, optimizer slots, packed gradient
+    and the fp16 cache bytes must agree BIT FOR BIT over several steps. Ragged tile edges (V, H, N not multiples of the
+    128 x 256 tile / 64-row block) and a learning rate that moves max|W| across powers of two (the re-scale path)."""
+    from deepbelief_b200 import compat as tf, ops
+    N, V, H, k = 520, 2056, 1416, 2
+    rs = np.random.RandomState(9)
+    theta0 = np.concatenate([(rs.normal(size=V * H) * 0.01), rs.normal(size=V) * 0.1, rs.normal(size=H) * 0.1]).astype(np.float32)
+    v0 = torch.as_tensor((rs.uniform(size=(N, V)) < 0.4).astype(np.float32)).cuda()
+
+    def make():
+        if kind == 'sgd':
+            return tf.train.GradientDescentOptimizer(3.0)
+        if kind == 'momentum':
+            return tf.train.MomentumOptimizer(1.0, momentum=0.9, weight_decay=1e-4)
+        return tf.train.AdamOptimizer(2e-2)
+
+    runs = []
+    for fused in (False, True):
+        opt = make()
+        p = torch.as_tensor(theta0).cuda().clone()
+        state = torch.zeros(max(opt.state_multiple(), 1) * p.numel(), device='cuda')
+        grad = torch.zeros_like(p)
+        plan = ops.CdTcPlan(N, V, H, k)
+        assert plan.update_fusable()
+        plan.refresh_weights(p)
+        rng = ops.Rng(seed=21)
+        scale0 = float(plan.cache[:4].clone().view(torch.float32)[0])       # the scale chosen from the initial max|W|
+        snaps = []
+        for it in range(4):
+            if fused:
+                plan.step_update(v0, p, grad, opt.descriptor(), state, rng=rng)
+            else:
+                plan.step(v0, p, grad, rng=rng)
+                ops.optimizer_step(opt.descriptor(), p, grad, state)
+                plan.refresh_weights(p)
+            torch.cuda.synchronize()
+            mat = V * H * 2                                   # the four fp16 matrices sit at 256-byte aligned offsets behind the header
+            stride = (mat + 255) // 256 * 256
+            cache = torch.cat([plan.cache[256 + i * stride:256 + i * stride + mat] for i in range(4)])
+            snaps.append((p.clone(), state.clone(), grad.clone(), cache, plan.cache[:8].clone()))
+        runs.append(snaps)
+    scales = {scale0}
+    for it, (a, b) in enumerate(zip(*runs)):
+        for name, x, y in zip(('params', 'optimizer state', 'gradient', 'split-weight cache', 'cache scale'), a, b):
+            assert torch.equal(x, y), 'step %d: %s differs between the fused and the separate update' % (it, name)
+        scales.add(float(a[4].view(torch.float32)[0]))
+    assert np.all(np.isfinite(_np(runs[1][-1][0])))
+    if kind != 'adam':
+        assert len(scales) > 1, 'the test is meant to cross a power of two in max|W| (re-scale path)'
