@@ -382,8 +382,10 @@ def run_b200(args):
     windows.append((t_a, t_b))
     e2e_ms = parallel.max_over_ranks(e0.elapsed_time(e1), device=dev) / K
     e2e_value = N_GLOBAL * K_GIBBS / (e2e_ms * 1e-3)
-    h2d = n_local * V * 4
-    assert rbm.last_feeder.h2d_bytes == h2d * K, 'feeder copied %d bytes, expected %d' % (rbm.last_feeder.h2d_bytes, h2d * K)
+    # the synthetic batch is {0,1}: the feeder stages it as bytes (Data.binary_bytes) and the chain's first kernel reads uint8
+    h2d = rbm.last_feeder.h2d_bytes // K
+    assert h2d in (n_local * V, n_local * V * 4) and rbm.last_feeder.h2d_bytes == h2d * K, \
+        'feeder copied %d bytes over %d steps' % (rbm.last_feeder.h2d_bytes, K)
 
     # ---- second metric: GPLVM LML + gradient at N=5000 (replicas only across GPUs) ----
     del pool, data, host, grad
@@ -518,7 +520,7 @@ def run_b200(args):
             'config': dict(CONFIG, parallelism='dp%d (rows sharded, NCCL sum-all-reduce of dW|db|dc)' % world,
                            local_batch=n_local),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': e2e_ms, 'h2d_bytes_per_step': h2d,
-                    'd2h_bytes_per_step': 4, 'api': 'RBM.train(AdamOptimizer, Data.from_arrays(pinned host), '
+                    'd2h_bytes_per_step': 4, 'h2d_dtype': 'uint8' if h2d == n_local * V else 'float32', 'api': 'RBM.train(AdamOptimizer, Data.from_arrays(pinned host), '
                     'num_gibbs_steps=10, pcd=False)', 'monitor_last': monitor[-1] if monitor else None},
             'gpu_launches': launches_per_step * K,
             'gpu_launches_how': launches_how, 'gpu_launch_kernels': launch_names,

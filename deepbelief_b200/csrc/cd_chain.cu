@@ -127,8 +127,10 @@ __global__ void rescale_after_update_kernel(WeightCacheHeader* hdr) {
 
 // ---- fp32 [R,C] -> fp16 row-major copy and/or fp16 transposed copy, optional hi/lo split ----------
 // t_interleave_phase >= 0: the transposed copy is written at tc_interleaved_col(r, phase) (CD "T" layout)
-template <bool SPLIT>
-__global__ void __launch_bounds__(256) cvt_transpose_kernel(const float* __restrict__ src, int R, int C,
+__device__ __forceinline__ float load_as_float(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float load_as_float(const uint8_t* p) { return (float)__ldg(p); }
+template <bool SPLIT, typename SrcT = float>
+__global__ void __launch_bounds__(256) cvt_transpose_kernel(const SrcT* __restrict__ src, int R, int C,
                                                             const float* __restrict__ scale_dev, __half* __restrict__ d_hi,
                                                             __half* __restrict__ d_lo, int ldd, __half* __restrict__ t_hi,
                                                             __half* __restrict__ t_lo, int ldt, int t_interleave_phase,
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(256) cvt_transpose_kernel(const float* __restr
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = r0 + ty + 8 * i, c = c0 + tx;
-    float v = (r < R && c < C) ? __ldg(src + (size_t)r * C + c) * s : 0.0f;
+    float v = (r < R && c < C) ? load_as_float(src + (size_t)r * C + c) * s : 0.0f;
     tile[ty + 8 * i][tx] = v;
     if (d_hi != nullptr && r < R && c < C) {
       if (SPLIT) { __half hi, lo; split_f16(v, hi, lo); d_hi[(size_t)r * ldd + c] = hi; d_lo[(size_t)r * ldd + c] = lo; }
@@ -161,6 +163,71 @@ __global__ void __launch_bounds__(256) cvt_transpose_kernel(const float* __restr
       }
     }
   }
+}
+
+// ---- optimizer step on W + split-weight cache rewrite in ONE pass (the data-parallel step, after the gradient all-reduce) ----
+// 32 x 32 tile of W [V, H] per CTA: g, W and the optimizer slots are read once (coalesced along H), the rule is applied, W / slots
+// / the [V, H] fp16 split are written in place, and the [H, V] split goes through a shared-memory transpose. The cache is
+// written with the scale in the header and max |W_new| is collected, exactly as the fused dW epilogue does (gemm_tc.cu);
+// rescale_after_update_kernel + the guarded re-split then handle a moved scale. The last CTAs update b | c.
+struct ApplyArgs {
+  OptRule rule;
+  float* theta; const float* grad; float* st; float* st2;     // packed W | b | c and slots
+  int V, H;
+  __half *w_hi, *w_lo, *wt_hi, *wt_lo;
+  const float* scale_dev; unsigned int* max_bits;
+};
+__global__ void __launch_bounds__(256) apply_update_kernel(const ApplyArgs a) {
+  __shared__ float tile[32][33];
+  const int tiles_h = (a.H + 31) / 32, tiles_v = (a.V + 31) / 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if ((int)blockIdx.x >= tiles_h * tiles_v) {               // bias part: V + H elements behind W
+    const size_t nW = (size_t)a.V * a.H;
+    const int i = ((int)blockIdx.x - tiles_h * tiles_v) * 256 + threadIdx.x;
+    if (i < a.V + a.H) {
+      const size_t idx = nW + i;
+      float s1 = a.rule.kind != 0 ? a.st[idx] : 0.0f, s2 = a.rule.kind == 2 ? a.st2[idx] : 0.0f;
+      a.theta[idx] = opt_apply(a.rule, a.theta[idx], __ldg(a.grad + idx), s1, s2);
+      if (a.rule.kind != 0) a.st[idx] = s1;
+      if (a.rule.kind == 2) a.st2[idx] = s2;
+    }
+    return;
+  }
+  const int r0 = ((int)blockIdx.x / tiles_h) * 32, c0 = ((int)blockIdx.x % tiles_h) * 32;
+  const float sc = __ldg(a.scale_dev);
+  float mx = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + 8 * i, c = c0 + tx;
+    float v = 0.0f;
+    if (r < a.V && c < a.H) {
+      const size_t idx = (size_t)r * a.H + c;
+      float s1 = a.rule.kind != 0 ? a.st[idx] : 0.0f, s2 = a.rule.kind == 2 ? a.st2[idx] : 0.0f;
+      const float t = opt_apply(a.rule, a.theta[idx], __ldg(a.grad + idx), s1, s2);
+      if (a.rule.kind != 0) a.st[idx] = s1;
+      if (a.rule.kind == 2) a.st2[idx] = s2;
+      a.theta[idx] = t;
+      mx = fmaxf(mx, fabsf(t));
+      v = t * sc;
+      __half hi, lo;
+      split_f16(v, hi, lo);
+      a.w_hi[idx] = hi; a.w_lo[idx] = lo;
+    }
+    tile[ty + 8 * i][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, r = r0 + tx;
+    if (c < a.H && r < a.V) {
+      __half hi, lo;
+      split_f16(tile[tx][ty + 8 * i], hi, lo);
+      a.wt_hi[(size_t)c * a.V + r] = hi; a.wt_lo[(size_t)c * a.V + r] = lo;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (tx == 0 && mx > 0.0f) atomicMax(a.max_bits, __float_as_uint(mx));
 }
 
 // ---- bias gradients from the interleaved T buffers: one warp per unit ------------------------------
@@ -303,7 +370,7 @@ extern "C" int db_cd_tc_refresh_weights(db_handle_t h, db_stream_t stream, const
 
 // opt != nullptr: the fused update (db_cd_tc_step_update) — params, opt_state and the weight cache are rewritten by the
 // dW epilogue and the bias kernel; otherwise gradients only (db_cd_tc_step).
-static int cd_tc_step_impl(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, const float* v0,
+static int cd_tc_step_impl(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, const void* v0,
                            float* params, void* weight_cache, void* pcd_state, const float* injected,
                            const db_rng_t* rng, void* workspace, float* grad, float* vk_out, float* hk_out,
                            float* p0_out, float* pk_out, const db_opt_t* opt, float* opt_state) {
@@ -340,7 +407,12 @@ static int cd_tc_step_impl(db_handle_t h, db_stream_t stream, const db_cd_tc_des
   }
   {  // data batch -> fp16 [N,V] and interleaved phase 0 of VT
     dim3 grid((V + 31) / 32, (N + 31) / 32);
-    cvt_transpose_kernel<false><<<grid, 256, 0, st>>>(v0, N, V, nullptr, ws.v0b, nullptr, V, ws.vt, nullptr, ldT, 0, nullptr);
+    if (d->v0_u8)
+      cvt_transpose_kernel<false, uint8_t><<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(v0), N, V, nullptr, ws.v0b, nullptr, V,
+                                                                 ws.vt, nullptr, ldT, 0, nullptr);
+    else
+      cvt_transpose_kernel<false><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(v0), N, V, nullptr, ws.v0b, nullptr, V, ws.vt,
+                                                        nullptr, ldT, 0, nullptr);
   }
 
   auto up = [&](const __half* vin, int phase /*-1: middle of chain*/, bool write_sample, const float* U, uint64_t draw_i,
@@ -421,7 +493,7 @@ static int cd_tc_step_impl(db_handle_t h, db_stream_t stream, const db_cd_tc_des
   return check_launch(h, "cd_tc_step");
 }
 
-extern "C" int db_cd_tc_step(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, const float* v0,
+extern "C" int db_cd_tc_step(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, const void* v0,
                              const float* params, const void* weight_cache, void* pcd_state, const float* injected,
                              const db_rng_t* rng, void* workspace, float* grad, float* vk_out, float* hk_out,
                              float* p0_out, float* pk_out) {
@@ -434,7 +506,7 @@ extern "C" int db_cd_tc_update_fusable(const db_cd_tc_desc_t* d) {
   return dw_splits(2 * ((d->N + 63) / 64 * 64), d->V, d->H) == 1 ? 1 : 0;
 }
 
-extern "C" int db_cd_tc_step_update(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, const float* v0,
+extern "C" int db_cd_tc_step_update(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, const void* v0,
                                     float* params, void* weight_cache, void* pcd_state, const float* injected,
                                     const db_rng_t* rng, void* workspace, float* grad, const db_opt_t* opt,
                                     float* opt_state) {
@@ -447,6 +519,37 @@ extern "C" int db_cd_tc_step_update(db_handle_t h, db_stream_t stream, const db_
     return set_err(h, DB_ERR_UNSUPPORTED, "dW of this shape runs as K-split partial products; use db_cd_tc_step + db_optimizer_step");
   return cd_tc_step_impl(h, stream, d, v0, params, weight_cache, pcd_state, injected, rng, workspace, grad, nullptr, nullptr,
                          nullptr, nullptr, opt, opt_state);
+}
+
+extern "C" int db_cd_tc_apply_update(db_handle_t h, db_stream_t stream, int V, int H, float* params, const float* grad,
+                                     const db_opt_t* opt, float* opt_state, void* weight_cache) {
+  DB_REQUIRE(h, params && grad && opt && weight_cache && V > 0 && H > 0, "null operand or empty shape");
+  DB_REQUIRE(h, opt->kind == DB_OPT_SGD || opt->kind == DB_OPT_MOMENTUM || opt->kind == DB_OPT_ADAM, "unknown optimizer kind");
+  DB_REQUIRE(h, opt->kind == DB_OPT_SGD || opt_state, "the optimizer rule needs its slot buffer");
+  if (opt->clock) return set_err(h, DB_ERR_UNSUPPORTED, "the fused update takes the step number by value (no device clock)");
+  cudaStream_t st = (cudaStream_t)stream;
+  WeightCacheView wc = weight_cache_view(weight_cache, V, H);
+  const size_t n_total = (size_t)V * H + V + H;
+  float lr_t = opt->lr;
+  if (opt->kind == DB_OPT_ADAM) {
+    const double b1t = pow((double)opt->beta1, opt->step), b2t = pow((double)opt->beta2, opt->step);
+    lr_t = (float)((double)opt->lr * sqrt(1.0 - b2t) / (1.0 - b1t));
+  }
+  ApplyArgs a{};
+  a.rule = OptRule{opt->kind, opt->lr, lr_t, opt->momentum, opt->beta1, opt->beta2, opt->eps, opt->weight_decay};
+  a.theta = params; a.grad = grad;
+  a.st = opt->kind != DB_OPT_SGD ? opt_state : nullptr;
+  a.st2 = opt->kind == DB_OPT_ADAM ? opt_state + n_total : nullptr;
+  a.V = V; a.H = H;
+  a.w_hi = wc.w_hi; a.w_lo = wc.w_lo; a.wt_hi = wc.wt_hi; a.wt_lo = wc.wt_lo;
+  a.scale_dev = &wc.hdr->scale; a.max_bits = &wc.hdr->new_max_bits;
+  const int tiles = ((H + 31) / 32) * ((V + 31) / 32), bias_blocks = (V + H + 255) / 256;
+  apply_update_kernel<<<tiles + bias_blocks, 256, 0, st>>>(a);
+  rescale_after_update_kernel<<<1, 1, 0, st>>>(wc.hdr);
+  dim3 grid((H + 31) / 32, (V + 31) / 32);
+  cvt_transpose_kernel<true><<<grid, 256, 0, st>>>(params, V, H, &wc.hdr->scale, wc.w_hi, wc.w_lo, H, wc.wt_hi, wc.wt_lo, V, -1,
+                                                   &wc.hdr->resplit);
+  return check_launch(h, "cd_tc_apply_update");
 }
 
 extern "C" int db_cd_tc_dw(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, void* workspace, float* grad,

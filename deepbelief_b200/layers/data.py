@@ -93,6 +93,8 @@ class Data:
 
         self._cursor = _EpochCursor(self.num_datapoints, self.batch_size, shuffle_first)
         self._pinned = None
+        self._u8 = None             # uint8 copy of a {0,1} data set (binary_bytes), built on first request
+        self._u8_checked = False
         self._shard = None          # (rank, world, local rows) once shard() has been called
         self.logger.debug(self)
 
@@ -150,25 +152,48 @@ class Data:
             return self._take(self.datapoints, rows), self._take(self.labels, rows)
         return self._take(self.datapoints, rows)
 
-    def next_batch_into(self, out):
+    def binary_bytes(self):
+        """uint8 copy of the datapoints when every value is exactly 0 or 1 (the binary data sets the RBM examples train
+        on), else None. Built once, in page-locked memory when a CUDA runtime is present: the trainer's feeder then moves
+        1 byte per pixel to the device instead of 4 and the tensor-core chain reads the bytes directly (db_cd_tc_desc_t.v0_u8).
+        The float32 `datapoints` array the reference exposes is unchanged."""
+        if not self._u8_checked:
+            self._u8_checked = True
+            d = self.datapoints
+            if d.size and float(d.min()) >= 0.0 and float(d.max()) <= 1.0:
+                u8 = d.astype(np.uint8)
+                if np.array_equal(u8, d):
+                    try:
+                        import torch
+                        if torch.cuda.is_available():
+                            self._u8_store = torch.from_numpy(u8).pin_memory()
+                            u8 = self._u8_store.numpy()
+                    except Exception:       # pinning is an optimisation only
+                        pass
+                    self._u8 = u8
+        return self._u8
+
+    def next_batch_into(self, out, as_bytes=False):
         """The datapoints of next_batch() without the intermediate copy: a zero-copy view when the sorted
         rows are contiguous, otherwise gathered by the native multi-threaded row gather
-        (db_host_gather_rows) into `out` (a [batch_size, datapoint_size] float32 array, normally the
-        feeder's pinned staging buffer). Returns the array that holds the batch."""
+        (db_host_gather_rows) into `out` (a [batch_size, datapoint_size] array, normally the feeder's pinned staging
+        buffer: float32, or uint8 with as_bytes, which reads the binary_bytes() copy). Returns the array that holds the batch."""
         rows, wrapped = self._cursor.advance()
         rows = self._local(rows)
         if wrapped and self.log_epochs:
             self.logger.info('Epoch: %d', self._cursor.epoch)
+        src = self.binary_bytes() if as_bytes else self.datapoints
+        assert src is not None, 'as_bytes needs a {0,1} data set'
         if len(rows) and int(rows[-1]) - int(rows[0]) + 1 == len(rows):
-            return self.datapoints[int(rows[0]):int(rows[-1]) + 1]
-        src = self.datapoints
-        if src.dtype != np.float32 or not src.flags['C_CONTIGUOUS'] or not out.flags['C_CONTIGUOUS']:
+            return src[int(rows[0]):int(rows[-1]) + 1]
+        if (src.dtype != out.dtype or src.dtype not in (np.float32, np.uint8) or not src.flags['C_CONTIGUOUS'] or
+                not out.flags['C_CONTIGUOUS']):
             np.take(src, rows, axis=0, out=out)
             return out
         import ctypes
         from .. import _lib
         rows64 = np.ascontiguousarray(rows, dtype=np.int64)
-        rc = _lib.lib().db_host_gather_rows(ctypes.c_void_p(src.ctypes.data), src.shape[1] * 4,
+        rc = _lib.lib().db_host_gather_rows(ctypes.c_void_p(src.ctypes.data), src.shape[1] * src.itemsize,
                                             ctypes.c_void_p(rows64.ctypes.data), len(rows64), src.shape[0],
                                             ctypes.c_void_p(out.ctypes.data), 0)
         if rc != 0:

@@ -44,15 +44,15 @@ def default_stream(name):
 _BUFFER_POOL = {}
 
 
-def _pooled_buffers(device, shape):
-    key = (str(device), tuple(shape))
+def _pooled_buffers(device, shape, dtype=torch.float32):
+    key = (str(device), tuple(shape), dtype)
     bufs = _BUFFER_POOL.get(key)
     if bufs is None:
         if len(_BUFFER_POOL) >= 4:                 # a handful of batch shapes at most; do not hoard pinned memory
             _BUFFER_POOL.clear()
         bufs = _BUFFER_POOL[key] = {
-            'stage': [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(2)],
-            'dev': [torch.empty(shape, dtype=torch.float32, device=device) for _ in range(2)]}
+            'stage': [torch.empty(shape, dtype=dtype).pin_memory() for _ in range(2)],
+            'dev': [torch.empty(shape, dtype=dtype, device=device) for _ in range(2)]}
     return bufs
 
 
@@ -64,10 +64,15 @@ class BatchFeeder:
     gather into pinned staging, or a zero-copy view of pinned storage) and starts its host->device
     copy on a side stream, so both overlap the CD chain of the current batch. Device and staging
     buffers are double-buffered. Exactly `count` batches are drawn from the data source — the
-    reference's loop consumes one per iteration (rbm.py:695) and no more."""
+    reference's loop consumes one per iteration (rbm.py:695) and no more.
+    allow_bytes: the consumer reads uint8 batches (the tensor-core CD chain); a {0,1} data set is then staged and
+    copied as bytes (Data.binary_bytes), a quarter of the host->device traffic."""
 
-    def __init__(self, data, device, count):
+    def __init__(self, data, device, count, allow_bytes=False):
         self.data, self.device, self.left = data, device, int(count)
+        self.as_bytes = bool(allow_bytes and hasattr(data, 'binary_bytes') and hasattr(data, 'next_batch_into') and
+                             data.binary_bytes() is not None)
+        self.dtype = torch.uint8 if self.as_bytes else torch.float32
         self.copy_stream = torch.cuda.Stream(device=device)
         # pooled device buffers may still be read by work a previous trainer enqueued on the compute stream
         self.copy_stream.wait_stream(torch.cuda.current_stream())
@@ -82,7 +87,7 @@ class BatchFeeder:
 
     def _staging(self, s, shape):
         if self.stage[s] is None or tuple(self.stage[s].shape) != tuple(shape):
-            self.stage[s] = _pooled_buffers(self.device, shape)['stage'][s]
+            self.stage[s] = _pooled_buffers(self.device, shape, self.dtype)['stage'][s]
             torch.cuda.current_stream().synchronize()   # a previous feeder may still be copying out of it
         else:
             self.ready[s].synchronize()            # the last copy out of this staging buffer has finished
@@ -93,21 +98,24 @@ class BatchFeeder:
             return
         self.left -= 1
         s = self.slot
-        if hasattr(self.data, 'next_batch_into'):
+        if self.as_bytes:
+            host = self.data.next_batch_into(self._staging(s, self.data.batch_shape()).numpy(), as_bytes=True)
+        elif hasattr(self.data, 'next_batch_into'):
             shape = self.data.batch_shape()
             host = self.data.next_batch_into(self._staging(s, shape).numpy())
         else:
             host = self.data.next_batch()
             if isinstance(host, tuple):            # (datapoints, labels): the trainers use the datapoints only
                 host = host[0]
-        src = host if isinstance(host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(host, dtype=np.float32))
+        np_dtype = np.uint8 if self.as_bytes else np.float32
+        src = host if isinstance(host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(host, dtype=np_dtype))
         self._pending = True
         if src.is_cuda:
             self.dev[s] = src.to(dtype=torch.float32)
             self.ready[s].record(torch.cuda.current_stream())
             return
         if self.dev[s] is None or self.dev[s].shape != src.shape:
-            self.dev[s] = _pooled_buffers(self.device, src.shape)['dev'][s]
+            self.dev[s] = _pooled_buffers(self.device, src.shape, self.dtype)['dev'][s]
         if not src.is_pinned():
             stage = self._staging(s, src.shape)
             stage.copy_(src)
@@ -117,7 +125,7 @@ class BatchFeeder:
         with torch.cuda.stream(self.copy_stream):
             self.dev[s].copy_(src, non_blocking=True)
             self.ready[s].record(self.copy_stream)
-        self.h2d_bytes += src.numel() * 4
+        self.h2d_bytes += src.numel() * src.element_size()
 
     def next(self):
         if not self._pending:
@@ -528,11 +536,13 @@ class RBM(layer.Layer):
         """Positive phase + k Gibbs steps + packed CD gradient for one (local) batch; returns
         (grad, v_k, h_k). `persistent`: PCD chain state to start from and update (fp32 [N,H] tensor,
         general path only — the tensor-core path keeps its own fp16 state in the plan)."""
-        v0 = to_device(v_0_batch, self.device)
+        v0 = self._batch_on_device(v_0_batch)
         n = v0.shape[0]
         inv_n = 1.0 / float(n_global or n)
         if grad is None:
             grad = torch.empty_like(self._params)
+        if v0.dtype == torch.uint8 and not (self._tc_eligible(n) and not force_simt and persistent is None):
+            v0 = v0.float()
         if self._tc_eligible(n) and not force_simt and persistent is None:
             plan = self._tc_plan_for(n, k, n_global or n)
             plan.step(v0, self._params, grad, injected=injected, rng=self.rng)
@@ -564,6 +574,12 @@ class RBM(layer.Layer):
                          hidden_probs=(p0, pk) if reuse else None)
         return grad, vk, hk
 
+    def _batch_on_device(self, batch):
+        """Device batch for the chain: fp32, or the feeder's uint8 {0,1} bytes, which the tensor-core chain reads directly."""
+        if isinstance(batch, torch.Tensor) and batch.is_cuda and batch.dtype == torch.uint8:
+            return batch.contiguous()
+        return to_device(batch, self.device)
+
     def launches_per_cd_step(self, k):
         """Kernels of this library launched by one cd_step on the tensor-core path: batch conversion,
         2k+1 chain GEMMs, the dW GEMM and the bias-gradient reduction (csrc/cd_chain.cu)."""
@@ -591,7 +607,7 @@ class RBM(layer.Layer):
         arrive. Results are identical to cd_step + apply_gradient (same kernels, same reduction order)."""
         import torch.distributed as td
         _, world = _dist_info()
-        v0 = to_device(v_0_batch, self.device)
+        v0 = self._batch_on_device(v_0_batch)
         n = v0.shape[0]
         if (world == 1 and persistent is None and self._tc_eligible(n) and self.FUSED_UPDATE and
                 self._trainable_pair(grad)[0] is self._params):
@@ -606,6 +622,15 @@ class RBM(layer.Layer):
         chunk_rows = (self.num_v // max(self.DW_CHUNKS, 1)) // 256 * 256
         if world == 1 or self.DW_CHUNKS <= 1 or persistent is not None or not self._tc_eligible(n) or chunk_rows < 256:
             self.cd_step(v0, k, persistent, grad=grad, n_global=n_global)
+            if (persistent is None and self._tc_eligible(n) and self.FUSED_UPDATE and self._tc_plan is not None and
+                    self._trainable_pair(grad)[0] is self._params and getattr(optimizer, 'clock', None) is None):
+                # tensor-core path: all-reduce, then optimizer rule + split-weight cache rewrite in one pass over W
+                all_reduce_sum_(grad)
+                plan = self._tc_plan
+                plan.apply_update(self._params, grad, optimizer.descriptor(lr), opt_state)
+                self._after_update()
+                plan.version = self._weights_version
+                return
             self.apply_gradient(optimizer, grad, opt_state, lr)
             return
         plan = self._tc_plan_for(n, k, n_global or n)
@@ -715,14 +740,16 @@ class RBM(layer.Layer):
             self._eval_step(test_data, test_mean_fname, test_std_fname)
 
         lr_now = optimizer.learning_rate
-        feeder = BatchFeeder(training_data, self.device, max(0, max_iter - start_iter))
-        self.last_feeder = feeder
         graph_step = None
         width = self.layers[-1].num_v
         use_graph = (world == 1 and max_iter - start_iter >= self.GRAPH_MIN_ITERATIONS and
                      os.environ.get('DEEPBELIEF_B200_GRAPH', '1') != '0' and
                      (pcd or not self._tc_eligible(n_local)) and
                      n_local * max(l.num_v * l.num_h for l in self.layers) <= self.GRAPH_MAX_WORK)
+        # binary data of a single tensor-core layer travels to the device as bytes; the chain reads them directly
+        bytes_ok = self.bottom is None and not pcd and not use_graph and self._tc_eligible(n_local)
+        feeder = BatchFeeder(training_data, self.device, max(0, max_iter - start_iter), allow_bytes=bytes_ok)
+        self.last_feeder = feeder
         for self.iter in range(start_iter, max_iter):
             batch = feeder.next()
             if use_graph and graph_step is None:

@@ -182,7 +182,7 @@ class CdTcPlan:
     """Owns the workspace / split-weight cache of the fused tcgen05 CD-k step for one (N, V, H, k)."""
 
     def __init__(self, N, V, H, k, pcd=False, n_global=None, device='cuda'):
-        self.desc = L.db_cd_tc_desc_t(N, V, H, k, 1 if pcd else 0, 1.0 / float(n_global or N))
+        self.desc = L.db_cd_tc_desc_t(N, V, H, k, 1 if pcd else 0, 1.0 / float(n_global or N), 0, 0)
         wb = int(L.lib().db_cd_tc_workspace_bytes(ctypes.byref(self.desc)))
         if wb == 0:
             raise ValueError('tensor-core CD path needs N, V, H multiples of 8 (got %d, %d, %d)' % (N, V, H))
@@ -195,13 +195,20 @@ class CdTcPlan:
         rc = L.lib().db_cd_tc_refresh_weights(L.handle(), L.stream(), L.fptr(params), self.V, self.H, L.ptr(self.cache))
         L.check(rc, 'db_cd_tc_refresh_weights')
 
+    def _batch_ptr(self, v0):
+        """v0 [N,V]: fp32, or uint8 {0,1} (binary data staged as bytes by the feeder: 4x less host->device traffic)."""
+        assert v0.is_cuda and v0.is_contiguous() and tuple(v0.shape) == (self.N, self.V)
+        assert v0.dtype in (torch.float32, torch.uint8), 'the chain reads fp32 or uint8 batches, got %s' % v0.dtype
+        self.desc.v0_u8 = 1 if v0.dtype == torch.uint8 else 0
+        return L.ptr(v0)
+
     def step(self, v0, params, grad, injected=None, rng=None, vk_out=None, hk_out=None, p0_out=None, pk_out=None,
              defer_dw=False):
         """defer_dw: leave dW to later dw() calls (row chunks); the bias gradients are still written."""
         self.desc.defer_dw = 1 if defer_dw else 0
         r = rng.next(2 * self.k + 1) if (rng is not None and injected is None) else None
         rc = L.lib().db_cd_tc_step(
-            L.handle(), L.stream(), ctypes.byref(self.desc), L.fptr(v0), L.fptr(params), L.ptr(self.cache),
+            L.handle(), L.stream(), ctypes.byref(self.desc), self._batch_ptr(v0), L.fptr(params), L.ptr(self.cache),
             L.ptr(self.pcd_state), L.fptr(injected), ctypes.byref(r) if r is not None else None,
             L.ptr(self.workspace), L.fptr(grad), L.fptr(vk_out), L.fptr(hk_out), L.fptr(p0_out), L.fptr(pk_out))
         L.check(rc, 'db_cd_tc_step')
@@ -218,11 +225,19 @@ class CdTcPlan:
         self.desc.defer_dw = 0
         r = rng.next(2 * self.k + 1) if (rng is not None and injected is None) else None
         rc = L.lib().db_cd_tc_step_update(
-            L.handle(), L.stream(), ctypes.byref(self.desc), L.fptr(v0), L.fptr(params), L.ptr(self.cache),
+            L.handle(), L.stream(), ctypes.byref(self.desc), self._batch_ptr(v0), L.fptr(params), L.ptr(self.cache),
             L.ptr(self.pcd_state), L.fptr(injected), ctypes.byref(r) if r is not None else None,
             L.ptr(self.workspace), L.fptr(grad), ctypes.byref(opt), L.fptr(opt_state))
         L.check(rc, 'db_cd_tc_step_update')
         return grad
+
+    def apply_update(self, params, grad, opt, opt_state):
+        """Optimizer step on the packed parameters + rewrite of the split-weight cache in one pass over W — what follows the
+        gradient all-reduce of a data-parallel step (db_cd_tc_apply_update); bit-identical to optimizer_step +
+        refresh_weights."""
+        rc = L.lib().db_cd_tc_apply_update(L.handle(), L.stream(), self.V, self.H, L.fptr(params), L.fptr(grad),
+                                           ctypes.byref(opt), L.fptr(opt_state), L.ptr(self.cache))
+        L.check(rc, 'db_cd_tc_apply_update')
 
     def dw(self, grad, v_begin, v_count):
         """dW rows [v_begin, v_begin + v_count) of the packed gradient from the chain ends of the last step()."""

@@ -158,6 +158,7 @@ typedef struct {
   float inv_global_n; /* 1 / (batch rows over all ranks) */
   int defer_dw;       /* 1: db_cd_tc_step leaves dW to later db_cd_tc_dw calls (row chunks, so a data-parallel
                          caller can all-reduce chunk c while chunk c+1 is still being computed) */
+  int v0_u8;          /* 1: v0 is uint8 {0,1} instead of fp32 (binary data sets staged as bytes: 4x less host->device traffic) */
 } db_cd_tc_desc_t;
 
 size_t db_cd_tc_workspace_bytes(const db_cd_tc_desc_t* d);
@@ -165,11 +166,11 @@ size_t db_cd_tc_workspace_bytes(const db_cd_tc_desc_t* d);
 size_t db_cd_tc_weight_cache_bytes(int V, int H);
 /* refresh the cache after W changed (optimizer step / restore) */
 int db_cd_tc_refresh_weights(db_handle_t h, db_stream_t stream, const float* W, int V, int H, void* cache);
-/* v0: [N,V] fp32 {0,1}. params packed (W|b|c). pcd_state: [N,H] fp16 persistent chain (pcd=1) or NULL.
+/* v0: [N,V] fp32 {0,1} (uint8 when d->v0_u8). params packed (W|b|c). pcd_state: [N,H] fp16 persistent chain (pcd=1) or NULL.
  * injected: NULL (Philox) or uniforms laid out [U_h0 (N*H) | per step: U_v (N*V), U_h (N*H)].
  * grad: packed (W|b|c) sums * inv_global_n. Optional fp32 exports (may be NULL): vk_out [N,V],
  * hk_out [N,H] (last samples), p0_out / pk_out [N,H] (hidden probabilities at both chain ends). */
-int db_cd_tc_step(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, const float* v0,
+int db_cd_tc_step(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, const void* v0,
                   const float* params, const void* weight_cache, void* pcd_state,
                   const float* injected, const db_rng_t* rng, void* workspace, float* grad,
                   float* vk_out, float* hk_out, float* p0_out, float* pk_out);
@@ -179,10 +180,15 @@ int db_cd_tc_step(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, c
  * db_optimizer_step / db_cd_tc_refresh_weights. opt_state: as db_optimizer_step (Momentum n floats, Adam 2n, n = V*H+V+H).
  * grad still receives the packed gradient. Results are bit-identical to db_cd_tc_step + db_optimizer_step +
  * db_cd_tc_refresh_weights. opt->clock must be NULL. DB_ERR_UNSUPPORTED when db_cd_tc_update_fusable(d) == 0. */
-int db_cd_tc_step_update(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, const float* v0,
+int db_cd_tc_step_update(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, const void* v0,
                          float* params, void* weight_cache, void* pcd_state,
                          const float* injected, const db_rng_t* rng, void* workspace, float* grad,
                          const db_opt_t* opt, float* opt_state);
+/* The data-parallel form of the same tail, run after the caller has summed `grad` over the ranks (NCCL): optimizer rule
+ * on the packed parameters (W | b | c) and rewrite of the split-weight cache in ONE pass over W — replaces
+ * db_optimizer_step + db_cd_tc_refresh_weights, bit-identical to them. Any V, H. */
+int db_cd_tc_apply_update(db_handle_t h, db_stream_t stream, int V, int H, float* params, const float* grad,
+                          const db_opt_t* opt, float* opt_state, void* weight_cache);
 /* 1 when the dW product of this shape runs as one work item per tile (enough 128x256 tiles to fill the GPU), which the
  * fused update needs; 0 when it runs K-split (small layers). */
 int db_cd_tc_update_fusable(const db_cd_tc_desc_t* d);

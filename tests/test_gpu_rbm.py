@@ -728,3 +728,40 @@ def test_fused_update_is_bit_identical_to_step_plus_optimizer(kind):
     assert np.all(np.isfinite(_np(runs[1][-1][0])))
     if kind != 'adam':
         assert len(scales) > 1, 'the test is meant to cross a power of two in max|W| (re-scale path)'
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_cuda(), reason='needs a CUDA device')
+def test_apply_update_and_byte_batches_are_bit_identical():
+    """The data-parallel tail db_cd_tc_apply_update (optimizer rule + split-weight cache rewrite in one pass, run after the
+    gradient all-reduce) against db_optimizer_step + db_cd_tc_refresh_weights, and a uint8 {0,1} batch (what the feeder
+    stages for binary data sets) against the same batch in fp32: identical bits in every output."""
+    from deepbelief_b200 import compat as tf, ops
+    N, V, H, k = 264, 520, 392, 1                     # not fusable into the dW epilogue (few tiles): the stand-alone kernel's case
+    rs = np.random.RandomState(3)
+    theta0 = np.concatenate([(rs.normal(size=V * H) * 0.05), rs.normal(size=V) * 0.1, rs.normal(size=H) * 0.1]).astype(np.float32)
+    v_f32 = torch.as_tensor((rs.uniform(size=(N, V)) < 0.3).astype(np.float32)).cuda()
+    v_u8 = v_f32.to(torch.uint8)
+    out = []
+    for mode in ('separate', 'apply'):
+        opt = tf.train.MomentumOptimizer(0.5, momentum=0.9, weight_decay=1e-4)
+        p = torch.as_tensor(theta0).cuda().clone()
+        state = torch.zeros(opt.state_multiple() * p.numel(), device='cuda')
+        grad = torch.zeros_like(p)
+        plan = ops.CdTcPlan(N, V, H, k)
+        plan.refresh_weights(p)
+        rng = ops.Rng(seed=5)
+        for it in range(3):
+            plan.step(v_u8 if (mode == 'apply' and it % 2 == 0) else v_f32, p, grad, rng=rng)
+            if mode == 'apply':
+                plan.apply_update(p, grad, opt.descriptor(), state)
+            else:
+                ops.optimizer_step(opt.descriptor(), p, grad, state)
+                plan.refresh_weights(p)
+        torch.cuda.synchronize()
+        mat = V * H * 2
+        stride = (mat + 255) // 256 * 256
+        out.append((p.clone(), state.clone(), grad.clone(), plan.cache[:8].clone(),
+                    torch.cat([plan.cache[256 + i * stride:256 + i * stride + mat] for i in range(4)])))
+    for name, x, y in zip(('params', 'optimizer state', 'gradient', 'cache scale', 'split-weight cache'), *out):
+        assert torch.equal(x, y), name

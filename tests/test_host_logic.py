@@ -122,3 +122,28 @@ def test_layers_get_distinct_default_streams():
     a, b = rbm.default_stream('BBRBM-200'), rbm.default_stream('BBRBM-200-100')
     c = rbm.default_stream('BBRBM-200')
     assert len({a, b, c}) == 3 and (a >> 32) == (c >> 32) != (b >> 32)
+
+
+def test_data_binary_bytes_and_byte_batches():
+    """Data.binary_bytes(): a uint8 copy exists exactly for {0,1} data sets, and next_batch_into(as_bytes=True) walks the
+    same rows as next_batch() (data.py:78-105 batching rule) for contiguous windows and gathered ones."""
+    import numpy as np
+    from deepbelief_b200.layers.data import Data
+    rs = np.random.RandomState(0)
+    X = (rs.uniform(size=(37, 24)) < 0.5).astype(np.float32)
+    for shuffle in (False, True):
+        np.random.seed(4)                                            # the epoch reshuffles draw from the global numpy state
+        a = Data.from_arrays(X, batch_size=8, shuffle_first=shuffle, log_epochs=False, pin=False)
+        wanted = [np.array(a.next_batch()) for _ in range(12)]       # crosses epoch boundaries (reshuffles)
+        np.random.seed(4)
+        b = Data.from_arrays(X, batch_size=8, shuffle_first=shuffle, log_epochs=False, pin=False)
+        assert b.binary_bytes() is not None and b.binary_bytes().dtype == np.uint8
+        assert b.datapoints.dtype == np.float32                     # what the reference exposes is untouched
+        out = np.empty((8, 24), dtype=np.uint8)
+        for want in wanted:
+            got = b.next_batch_into(out, as_bytes=True)
+            assert got.dtype == np.uint8 and np.array_equal(got.astype(np.float32), want)
+    c = Data.from_arrays(X * 0.5, batch_size=8, log_epochs=False, pin=False)
+    assert c.binary_bytes() is None
+    d = Data.from_arrays(X - 1.0, batch_size=8, log_epochs=False, pin=False)
+    assert d.binary_bytes() is None
