@@ -347,22 +347,34 @@ def run_b200(args):
     host.copy_(torch.cat(pool).cpu())
     data = Data.from_arrays(host.numpy(), batch_size=n_local, log_epochs=False, name='bench_data', pin=False)
     data._pinned_store = host
+    data.shard(0, 1)               # every rank already holds ITS rows of the global batch: RBM.train must not shard them again
     monitor = []
-    mon_host = torch.zeros(2, dtype=torch.float32).pin_memory()
-    mon_ev = [torch.cuda.Event(), torch.cuda.Event()]
-    mon_state = {'n': 0}
+    LAG = 3                                    # the host consumes step i's monitor value while steps i+1..i+3 are in flight
+    mon_host = torch.zeros(LAG + 1, dtype=torch.float32).pin_memory()
+    mon_ev = [torch.cuda.Event(blocking=True) for _ in range(LAG + 1)]     # blocking: a waiting rank yields its core
+    mon_state = {'n': 0, 'read': 0}
 
     def step_callback(it, g):
-        # per-step monitor, device->host every step: L1 norm of the visible-bias gradient (|<v>_data - <v>_model|).
-        # The 4-byte copy of step i is enqueued now and read on the host one step later (logging lag of one
-        # step), so the host keeps enqueueing the next step while this one runs.
+        # per-step monitor, device->host EVERY step: L1 norm of the visible-bias gradient (|<v>_data - <v>_model|).
+        # The 4-byte copy of step i is enqueued now and read on the host LAG steps later (a logging lag), so the host
+        # keeps enqueueing while the device works and per-step host jitter (8 ranks share the box's cores) is absorbed.
         i = mon_state['n']
-        mon_host[i % 2:i % 2 + 1].copy_(g[V * H:V * H + V].abs().sum().reshape(1), non_blocking=True)
-        mon_ev[i % 2].record()
-        if i > 0:
-            mon_ev[(i - 1) % 2].synchronize()
-            monitor.append(float(mon_host[(i - 1) % 2]))
+        s = i % (LAG + 1)
+        mon_host[s:s + 1].copy_(g[V * H:V * H + V].abs().sum().reshape(1), non_blocking=True)
+        mon_ev[s].record()
         mon_state['n'] = i + 1
+        while mon_state['n'] - mon_state['read'] > LAG:
+            r = mon_state['read'] % (LAG + 1)
+            mon_ev[r].synchronize()
+            monitor.append(float(mon_host[r]))
+            mon_state['read'] += 1
+
+    def drain_monitor():
+        while mon_state['read'] < mon_state['n']:
+            r = mon_state['read'] % (LAG + 1)
+            mon_ev[r].synchronize()
+            monitor.append(float(mon_host[r]))
+            mon_state['read'] += 1
 
     def train(iters):
         rbm.checkpoint_iter = 1
@@ -370,12 +382,12 @@ def run_b200(args):
                   step_callback=step_callback)
 
     train(Wm)
+    drain_monitor()
     barrier()
     t_a = time.perf_counter()
     e0.record()
     train(K)
-    mon_ev[(mon_state['n'] - 1) % 2].synchronize()          # the last step's monitor value reaches the host inside the window
-    monitor.append(float(mon_host[(mon_state['n'] - 1) % 2]))
+    drain_monitor()                                         # every step's monitor value reaches the host inside the window
     e1.record()
     barrier()
     t_b = time.perf_counter()

@@ -33,7 +33,7 @@ class db_opt_t(ctypes.Structure):
 
 class db_cd_tc_desc_t(ctypes.Structure):
     _fields_ = [('N', c_int), ('V', c_int), ('H', c_int), ('k', c_int), ('pcd', c_int),
-                ('inv_global_n', c_float), ('defer_dw', c_int), ('v0_u8', c_int)]
+                ('inv_global_n', c_float), ('v0_u8', c_int)]
 
 
 # enums (mirror the header)
@@ -78,10 +78,6 @@ SIGNATURES = {
     'db_cd_tc_apply_update': (c_int, [c_void_p, c_void_p, c_int, c_int, c_float_p, c_float_p, ctypes.POINTER(db_opt_t), c_float_p,
                                       c_void_p]),
     'db_cd_tc_update_fusable': (c_int, [ctypes.POINTER(db_cd_tc_desc_t)]),
-    'db_cd_tc_dw': (c_int, [c_void_p, c_void_p, ctypes.POINTER(db_cd_tc_desc_t), c_void_p, c_float_p, c_int, c_int]),
-    'db_set_sm_limit': (c_int, [c_void_p, c_int]),
-    'db_optimizer_step_range': (c_int, [c_void_p, c_void_p, ctypes.POINTER(db_opt_t), c_float_p, c_float_p, c_float_p,
-                                        c_size_t, c_size_t, c_size_t]),
     'db_gram_rbf': (c_int, [c_void_p, c_void_p, c_float_p, c_float_p, c_int, c_int, c_int, c_float_p, c_int,
                             c_float_p, c_int]),
     'db_potrf_lower': (c_int, [c_void_p, c_void_p, c_float_p, c_int, c_int, c_void_p]),

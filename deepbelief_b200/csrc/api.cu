@@ -20,7 +20,6 @@ extern "C" int db_create(db_handle_t* out, int device) {
   c->num_sms = prop.multiProcessorCount;
   c->cc_major = prop.major;
   c->cc_minor = prop.minor;
-  c->sm_limit = 0;
   c->err[0] = 0;
   *out = c;
   return DB_OK;
@@ -35,8 +34,3 @@ extern "C" const char* db_last_error(db_handle_t h) { return h ? h->err : "null 
 
 extern "C" int db_num_sms(db_handle_t h) { return h ? h->num_sms : 0; }
 
-extern "C" int db_set_sm_limit(db_handle_t h, int max_ctas) {
-  if (!h || max_ctas < 0) return DB_ERR_BAD_ARG;
-  h->sm_limit = max_ctas;
-  return DB_OK;
-}

@@ -54,6 +54,7 @@ inline WeightCacheView weight_cache_view(void* cache, int V, int H) {
 constexpr int kDwChunk = 4096;
 constexpr int kDwMaxSplits = 8;
 constexpr int kDwEnoughTiles = 96;
+constexpr int kFuseMinK = 16384;
 inline int dw_splits(int ldT, int V, int H) {
   const int tiles = ((H + 127) / 128) * ((V + 255) / 256);
   if (tiles >= kDwEnoughTiles) return 1;
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(256) cvt_transpose_kernel(const SrcT* __restri
 }
 
 // ---- optimizer step on W + split-weight cache rewrite in ONE pass (the data-parallel step, after the gradient all-reduce) ----
-// 32 x 32 tile of W [V, H] per CTA: g, W and the optimizer slots are read once (coalesced along H), the rule is applied, W / slots
+// 64 x 64 tile of W [V, H] per CTA: g, W and the optimizer slots are read once (16-byte accesses along H), the rule is applied, W / slots
 // / the [V, H] fp16 split are written in place, and the [H, V] split goes through a shared-memory transpose. The cache is
 // written with the scale in the header and max |W_new| is collected, exactly as the fused dW epilogue does (gemm_tc.cu);
 // rescale_after_update_kernel + the guarded re-split then handle a moved scale. The last CTAs update b | c.
@@ -177,10 +178,10 @@ struct ApplyArgs {
   __half *w_hi, *w_lo, *wt_hi, *wt_lo;
   const float* scale_dev; unsigned int* max_bits;
 };
+constexpr int kApplyTile = 64;
 __global__ void __launch_bounds__(256) apply_update_kernel(const ApplyArgs a) {
-  __shared__ float tile[32][33];
-  const int tiles_h = (a.H + 31) / 32, tiles_v = (a.V + 31) / 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  __shared__ float tile[kApplyTile][kApplyTile + 1];        // scaled new weights, [v][h]
+  const int tiles_h = (a.H + kApplyTile - 1) / kApplyTile, tiles_v = (a.V + kApplyTile - 1) / kApplyTile;
   if ((int)blockIdx.x >= tiles_h * tiles_v) {               // bias part: V + H elements behind W
     const size_t nW = (size_t)a.V * a.H;
     const int i = ((int)blockIdx.x - tiles_h * tiles_v) * 256 + threadIdx.x;
@@ -193,41 +194,93 @@ __global__ void __launch_bounds__(256) apply_update_kernel(const ApplyArgs a) {
     }
     return;
   }
-  const int r0 = ((int)blockIdx.x / tiles_h) * 32, c0 = ((int)blockIdx.x % tiles_h) * 32;
+  const int r0 = ((int)blockIdx.x / tiles_h) * kApplyTile, c0 = ((int)blockIdx.x % tiles_h) * kApplyTile;
   const float sc = __ldg(a.scale_dev);
+  const bool full = r0 + kApplyTile <= a.V && c0 + kApplyTile <= a.H && (a.H % 4) == 0 && (a.V % 8) == 0;
   float mx = 0.0f;
+  if (full) {
+    // phase 1: thread = 4 consecutive h of one row v (16-byte accesses, 256 B per 16 threads), 16 rows per pass
+    const int c4 = (threadIdx.x & 15) * 4, rr = threadIdx.x >> 4;
+    float4 g[4], th[4], m1[4], m2[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = r0 + ty + 8 * i, c = c0 + tx;
-    float v = 0.0f;
-    if (r < a.V && c < a.H) {
-      const size_t idx = (size_t)r * a.H + c;
-      float s1 = a.rule.kind != 0 ? a.st[idx] : 0.0f, s2 = a.rule.kind == 2 ? a.st2[idx] : 0.0f;
-      const float t = opt_apply(a.rule, a.theta[idx], __ldg(a.grad + idx), s1, s2);
-      if (a.rule.kind != 0) a.st[idx] = s1;
-      if (a.rule.kind == 2) a.st2[idx] = s2;
-      a.theta[idx] = t;
-      mx = fmaxf(mx, fabsf(t));
-      v = t * sc;
-      __half hi, lo;
-      split_f16(v, hi, lo);
-      a.w_hi[idx] = hi; a.w_lo[idx] = lo;
+    for (int i = 0; i < 4; ++i) {                           // all loads first
+      const size_t idx = (size_t)(r0 + rr + 16 * i) * a.H + c0 + c4;
+      g[i] = __ldcs(reinterpret_cast<const float4*>(a.grad + idx));
+      th[i] = *reinterpret_cast<const float4*>(a.theta + idx);
+      m1[i] = a.rule.kind != 0 ? *reinterpret_cast<const float4*>(a.st + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      m2[i] = a.rule.kind == 2 ? *reinterpret_cast<const float4*>(a.st2 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    tile[ty + 8 * i][tx] = v;
-  }
-  __syncthreads();
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int c = c0 + ty + 8 * i, r = r0 + tx;
-    if (c < a.H && r < a.V) {
-      __half hi, lo;
-      split_f16(tile[tx][ty + 8 * i], hi, lo);
-      a.wt_hi[(size_t)c * a.V + r] = hi; a.wt_lo[(size_t)c * a.V + r] = lo;
+    for (int i = 0; i < 4; ++i) {
+      const int r = rr + 16 * i;
+      const size_t idx = (size_t)(r0 + r) * a.H + c0 + c4;
+      float4 t;
+      t.x = opt_apply(a.rule, th[i].x, g[i].x, m1[i].x, m2[i].x);
+      t.y = opt_apply(a.rule, th[i].y, g[i].y, m1[i].y, m2[i].y);
+      t.z = opt_apply(a.rule, th[i].z, g[i].z, m1[i].z, m2[i].z);
+      t.w = opt_apply(a.rule, th[i].w, g[i].w, m1[i].w, m2[i].w);
+      *reinterpret_cast<float4*>(a.theta + idx) = t;
+      if (a.rule.kind != 0) *reinterpret_cast<float4*>(a.st + idx) = m1[i];
+      if (a.rule.kind == 2) *reinterpret_cast<float4*>(a.st2 + idx) = m2[i];
+      mx = fmaxf(mx, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
+      const float v0 = t.x * sc, v1 = t.y * sc, v2 = t.z * sc, v3 = t.w * sc;
+      tile[r][c4] = v0; tile[r][c4 + 1] = v1; tile[r][c4 + 2] = v2; tile[r][c4 + 3] = v3;
+      __half h0, l0, h1, l1, h2, l2, h3, l3;
+      split_f16(v0, h0, l0); split_f16(v1, h1, l1); split_f16(v2, h2, l2); split_f16(v3, h3, l3);
+      __half2 ha = __halves2half2(h0, h1), hb = __halves2half2(h2, h3), la = __halves2half2(l0, l1), lb = __halves2half2(l2, l3);
+      *reinterpret_cast<uint2*>(a.w_hi + idx) = make_uint2(*reinterpret_cast<uint32_t*>(&ha), *reinterpret_cast<uint32_t*>(&hb));
+      *reinterpret_cast<uint2*>(a.w_lo + idx) = make_uint2(*reinterpret_cast<uint32_t*>(&la), *reinterpret_cast<uint32_t*>(&lb));
+    }
+    __syncthreads();
+    // phase 2: thread = 16 consecutive v of one column h -> 32 contiguous bytes of W^T hi and of W^T lo
+    const int c = threadIdx.x >> 2, rq = (threadIdx.x & 3) * 16;
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      __half h0, l0, h1, l1;
+      split_f16(tile[rq + 2 * e][c], h0, l0);
+      split_f16(tile[rq + 2 * e + 1][c], h1, l1);
+      __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+      hi[e] = *reinterpret_cast<uint32_t*>(&hh); lo[e] = *reinterpret_cast<uint32_t*>(&ll);
+    }
+    const size_t tidx = (size_t)(c0 + c) * a.V + r0 + rq;
+    reinterpret_cast<uint4*>(a.wt_hi + tidx)[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    reinterpret_cast<uint4*>(a.wt_hi + tidx)[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    reinterpret_cast<uint4*>(a.wt_lo + tidx)[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    reinterpret_cast<uint4*>(a.wt_lo + tidx)[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+  } else {
+    // ragged edge tiles: one element at a time
+    for (int e = threadIdx.x; e < kApplyTile * kApplyTile; e += 256) {
+      const int r = e / kApplyTile, c = e % kApplyTile;
+      float v = 0.0f;
+      if (r0 + r < a.V && c0 + c < a.H) {
+        const size_t idx = (size_t)(r0 + r) * a.H + c0 + c;
+        float s1 = a.rule.kind != 0 ? a.st[idx] : 0.0f, s2 = a.rule.kind == 2 ? a.st2[idx] : 0.0f;
+        const float t = opt_apply(a.rule, a.theta[idx], __ldg(a.grad + idx), s1, s2);
+        if (a.rule.kind != 0) a.st[idx] = s1;
+        if (a.rule.kind == 2) a.st2[idx] = s2;
+        a.theta[idx] = t;
+        mx = fmaxf(mx, fabsf(t));
+        v = t * sc;
+        __half hi, lo;
+        split_f16(v, hi, lo);
+        a.w_hi[idx] = hi; a.w_lo[idx] = lo;
+      }
+      tile[r][c] = v;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < kApplyTile * kApplyTile; e += 256) {
+      const int c = e / kApplyTile, r = e % kApplyTile;
+      if (r0 + r < a.V && c0 + c < a.H) {
+        __half hi, lo;
+        split_f16(tile[r][c], hi, lo);
+        a.wt_hi[(size_t)(c0 + c) * a.V + r0 + r] = hi; a.wt_lo[(size_t)(c0 + c) * a.V + r0 + r] = lo;
+      }
     }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if (tx == 0 && mx > 0.0f) atomicMax(a.max_bits, __float_as_uint(mx));
+  if ((threadIdx.x & 31) == 0 && mx > 0.0f) atomicMax(a.max_bits, __float_as_uint(mx));
 }
 
 // ---- bias gradients from the interleaved T buffers: one warp per unit ------------------------------
@@ -477,7 +530,7 @@ static int cd_tc_step_impl(db_handle_t h, db_stream_t stream, const db_cd_tc_des
     bu.theta = params + nW; bu.st = fo.st ? fo.st + nW : nullptr; bu.st2 = fo.st2 ? fo.st2 + nW : nullptr;
     rc = launch_dw(h, st, d, ws, gW, 0, V, &fo);
     if (rc) return rc;
-  } else if (!d->defer_dw) {
+  } else {
     rc = launch_dw(h, st, d, ws, gW, 0, V);
     if (rc) return rc;
   }
@@ -503,7 +556,11 @@ extern "C" int db_cd_tc_step(db_handle_t h, db_stream_t stream, const db_cd_tc_d
 
 extern "C" int db_cd_tc_update_fusable(const db_cd_tc_desc_t* d) {
   if (!d || !tc_shape_ok(d->N, d->V, d->H)) return 0;
-  return dw_splits(2 * ((d->N + 63) / 64 * 64), d->V, d->H) == 1 ? 1 : 0;
+  // the epilogue moves ~1.2 MB per 128 x 256 tile through HBM; it hides under the tile's MMAs only when K = 2 NP is deep
+  // (measured at V = 4096, H = 8192: N = 16384 -0.7 ms per step, N = 2048 +0.75 ms against the separate one-pass update)
+  const int ldT = 2 * ((d->N + 63) / 64 * 64);
+  if (dw_splits(ldT, d->V, d->H) != 1) return 0;
+  return ldT >= kFuseMinK ? 2 : 1;
 }
 
 extern "C" int db_cd_tc_step_update(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, const void* v0,
@@ -514,7 +571,6 @@ extern "C" int db_cd_tc_step_update(db_handle_t h, db_stream_t stream, const db_
   DB_REQUIRE(h, opt->kind == DB_OPT_SGD || opt->kind == DB_OPT_MOMENTUM || opt->kind == DB_OPT_ADAM, "unknown optimizer kind");
   DB_REQUIRE(h, opt->kind == DB_OPT_SGD || opt_state, "the optimizer rule needs its slot buffer");
   if (opt->clock) return set_err(h, DB_ERR_UNSUPPORTED, "the fused update takes the step number by value (no device clock)");
-  if (d->defer_dw) return set_err(h, DB_ERR_UNSUPPORTED, "defer_dw and the fused update exclude each other");
   if (!db_cd_tc_update_fusable(d))
     return set_err(h, DB_ERR_UNSUPPORTED, "dW of this shape runs as K-split partial products; use db_cd_tc_step + db_optimizer_step");
   return cd_tc_step_impl(h, stream, d, v0, params, weight_cache, pcd_state, injected, rng, workspace, grad, nullptr, nullptr,
@@ -543,23 +599,11 @@ extern "C" int db_cd_tc_apply_update(db_handle_t h, db_stream_t stream, int V, i
   a.V = V; a.H = H;
   a.w_hi = wc.w_hi; a.w_lo = wc.w_lo; a.wt_hi = wc.wt_hi; a.wt_lo = wc.wt_lo;
   a.scale_dev = &wc.hdr->scale; a.max_bits = &wc.hdr->new_max_bits;
-  const int tiles = ((H + 31) / 32) * ((V + 31) / 32), bias_blocks = (V + H + 255) / 256;
+  const int tiles = ((H + kApplyTile - 1) / kApplyTile) * ((V + kApplyTile - 1) / kApplyTile), bias_blocks = (V + H + 255) / 256;
   apply_update_kernel<<<tiles + bias_blocks, 256, 0, st>>>(a);
   rescale_after_update_kernel<<<1, 1, 0, st>>>(wc.hdr);
   dim3 grid((H + 31) / 32, (V + 31) / 32);
   cvt_transpose_kernel<true><<<grid, 256, 0, st>>>(params, V, H, &wc.hdr->scale, wc.w_hi, wc.w_lo, H, wc.wt_hi, wc.wt_lo, V, -1,
                                                    &wc.hdr->resplit);
   return check_launch(h, "cd_tc_apply_update");
-}
-
-extern "C" int db_cd_tc_dw(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, void* workspace, float* grad,
-                           int v_begin, int v_count) {
-  DB_REQUIRE(h, d && workspace && grad, "null operand");
-  DB_REQUIRE(h, v_begin >= 0 && v_count > 0 && v_begin + v_count <= d->V, "row range outside [0, V)");
-  if (h->cc_major < 10) return set_err(h, DB_ERR_UNSUPPORTED, "tcgen05 path needs sm_100a (device is sm_%d%d)", h->cc_major, h->cc_minor);
-  if (!tc_shape_ok(d->N, d->V, d->H)) return set_err(h, DB_ERR_UNSUPPORTED, "tensor path needs N, V, H multiples of 8");
-  ChainWorkspace ws = chain_workspace(workspace, d->N, d->V, d->H);
-  int rc = launch_dw(h, (cudaStream_t)stream, d, ws, grad, v_begin, v_count);
-  if (rc) return rc;
-  return check_launch(h, "cd_tc_dw");
 }

@@ -10,7 +10,6 @@ struct db_context_s {
   int device;
   int num_sms;
   int cc_major, cc_minor;
-  int sm_limit;          // 0 = use num_sms (db_set_sm_limit)
   char err[512];
 };
 
@@ -26,7 +25,7 @@ inline int set_err(db_handle_t h, int code, const char* fmt, ...) {
   return code;
 }
 
-inline int tc_ctas(db_handle_t h) { return (h->sm_limit > 0 && h->sm_limit < h->num_sms) ? h->sm_limit : h->num_sms; }
+inline int tc_ctas(db_handle_t h) { return h->num_sms; }     // persistent tensor-core kernels: one CTA per SM
 
 inline int check_launch(db_handle_t h, const char* what) {
   cudaError_t e = cudaGetLastError();

@@ -500,9 +500,10 @@ extern "C" int db_clock_advance(db_handle_t h, db_stream_t stream, uint64_t* clo
   return check_launch(h, "clock_advance");
 }
 
-extern "C" int db_optimizer_step_range(db_handle_t h, db_stream_t stream, const db_opt_t* opt, float* params, const float* grad,
-                                       float* state, size_t n_total, size_t begin, size_t count) {
-  DB_REQUIRE(h, opt && params && grad && n_total > 0 && count > 0 && begin + count <= n_total, "null operand or bad range");
+extern "C" int db_optimizer_step(db_handle_t h, db_stream_t stream, const db_opt_t* opt, float* params, const float* grad,
+                                 float* state, size_t n_total) {
+  const size_t begin = 0, count = n_total;
+  DB_REQUIRE(h, opt && params && grad && n_total > 0, "null operand or empty parameter vector");
   DB_REQUIRE(h, opt->kind == DB_OPT_SGD || state, "optimizer state required");
   float lr_t = opt->lr;
   if (opt->kind == DB_OPT_ADAM) {
@@ -515,11 +516,6 @@ extern "C" int db_optimizer_step_range(db_handle_t h, db_stream_t stream, const 
   float* v = (state && opt->kind == DB_OPT_ADAM) ? state + n_total + begin : nullptr;
   optimizer_kernel<<<ew_grid(count, h->num_sms), 256, 0, (cudaStream_t)stream>>>(*opt, lr_t, params + begin, grad + begin, m, v, count);
   return check_launch(h, "optimizer_step");
-}
-
-extern "C" int db_optimizer_step(db_handle_t h, db_stream_t stream, const db_opt_t* opt, float* params, const float* grad,
-                                 float* state, size_t n) {
-  return db_optimizer_step_range(h, stream, opt, params, grad, state, n, 0, n);
 }
 
 extern "C" int db_mse(db_handle_t h, db_stream_t stream, const float* a, const float* b, int N, int D, float* out) {

@@ -590,22 +590,16 @@ class RBM(layer.Layer):
     GRAPH_MAX_WORK = 1 << 31
     GRAPH_MIN_ITERATIONS = 64
 
-    # SMs left to the NCCL kernels while a dW chunk is computed next to an in-flight all-reduce (the persistent
-    # tcgen05 GEMM otherwise occupies every SM and the collective could not start until it has finished)
-    COMM_SMS = 16
-    # Measured on 8 B200 at config 5 (scripts/scale_probe.py): 4 chunked all-reduces cost 0.68 ms against 0.40 ms for
-    # one 134 MB call and the dW GEMM loses the reserved SMs, so the pipelined step (4.85-5.00 ms) is SLOWER than
-    # the plain one (4.77 ms). The plain path is therefore the default; DW_CHUNKS > 1 enables the pipeline.
-    DW_CHUNKS = 1
     # single-process tensor-core steps run the optimizer inside the dW kernel (False: separate optimizer + refresh launches)
     FUSED_UPDATE = True
 
     def cd_update(self, v_0_batch, k, optimizer, opt_state, grad, n_global=None, lr=None, persistent=None):
-        """One full CD-k update: chain, gradient, (data-parallel) sum over ranks, optimizer step.
-        With several ranks on the tensor-core path the dW GEMM is issued in DW_CHUNKS row chunks and the NCCL
-        all-reduce of chunk c runs while chunk c+1 is computed; the optimizer then consumes the chunks as they
-        arrive. Results are identical to cd_step + apply_gradient (same kernels, same reduction order)."""
-        import torch.distributed as td
+        """One full CD-k update: chain, gradient, (data-parallel) sum over ranks, optimizer step. On the tensor-core path
+        the optimizer rule and the split-weight cache rewrite run inside the dW kernel (one process, deep batch) or as one
+        pass over W after the NCCL all-reduce. Results are identical to cd_step + apply_gradient.
+        (A pipeline of row-chunked dW launches with the all-reduce of chunk c under chunk c+1 was measured SLOWER on
+        8 B200 — 4 chunked all-reduces 0.68 ms against 0.40 ms for one 134 MB call, and the dW GEMM loses the SMs left to
+        NCCL: 4.85-5.00 ms per step against 4.77 ms — and was removed.)"""
         _, world = _dist_info()
         v0 = self._batch_on_device(v_0_batch)
         n = v0.shape[0]
@@ -614,45 +608,22 @@ class RBM(layer.Layer):
             # one process, tensor-core path: the dW kernel applies the optimizer rule and rewrites the split-weight cache
             # in its epilogue (db_cd_tc_step_update); bit-identical to cd_step + apply_gradient + refresh_weights
             plan = self._tc_plan_for(n, k, n_global or n)
-            if plan.update_fusable() and getattr(optimizer, 'clock', None) is None:
+            if plan.update_fusion_pays() and getattr(optimizer, 'clock', None) is None:
                 plan.step_update(v0, self._params, grad, optimizer.descriptor(lr), opt_state, rng=self.rng)
                 self._after_update()
                 plan.version = self._weights_version          # the cache already holds the updated weights
                 return
-        chunk_rows = (self.num_v // max(self.DW_CHUNKS, 1)) // 256 * 256
-        if world == 1 or self.DW_CHUNKS <= 1 or persistent is not None or not self._tc_eligible(n) or chunk_rows < 256:
-            self.cd_step(v0, k, persistent, grad=grad, n_global=n_global)
-            if (persistent is None and self._tc_eligible(n) and self.FUSED_UPDATE and self._tc_plan is not None and
-                    self._trainable_pair(grad)[0] is self._params and getattr(optimizer, 'clock', None) is None):
-                # tensor-core path: all-reduce, then optimizer rule + split-weight cache rewrite in one pass over W
-                all_reduce_sum_(grad)
-                plan = self._tc_plan
-                plan.apply_update(self._params, grad, optimizer.descriptor(lr), opt_state)
-                self._after_update()
-                plan.version = self._weights_version
-                return
-            self.apply_gradient(optimizer, grad, opt_state, lr)
+        self.cd_step(v0, k, persistent, grad=grad, n_global=n_global)
+        if (persistent is None and self._tc_eligible(n) and self.FUSED_UPDATE and self._tc_plan is not None and
+                self._trainable_pair(grad)[0] is self._params and getattr(optimizer, 'clock', None) is None):
+            # tensor-core path: all-reduce, then optimizer rule + split-weight cache rewrite in one pass over W
+            all_reduce_sum_(grad)
+            plan = self._tc_plan
+            plan.apply_update(self._params, grad, optimizer.descriptor(lr), opt_state)
+            self._after_update()
+            plan.version = self._weights_version
             return
-        plan = self._tc_plan_for(n, k, n_global or n)
-        plan.step(v0, self._params, grad, rng=self.rng, defer_dw=True)
-        H, total = self.num_h, self._params.numel()
-        bounds = [(c * chunk_rows, chunk_rows) for c in range(self.DW_CHUNKS - 1)]
-        bounds.append(((self.DW_CHUNKS - 1) * chunk_rows, self.num_v - (self.DW_CHUNKS - 1) * chunk_rows))
-        works = []
-        ops.set_sm_limit(max(1, plan.num_sms - self.COMM_SMS))
-        try:
-            for c, (vb, vc) in enumerate(bounds):
-                plan.dw(grad, vb, vc)
-                lo = vb * H
-                hi = total if c == len(bounds) - 1 else (vb + vc) * H      # the last chunk carries db | dc as well
-                works.append((lo, hi, td.all_reduce(grad[lo:hi], op=td.ReduceOp.SUM, async_op=True)))
-        finally:
-            ops.set_sm_limit(0)
-        desc = optimizer.descriptor(lr)
-        for lo, hi, work in works:
-            work.wait()
-            ops.optimizer_step_range(desc, self._params, grad, opt_state, lo, hi - lo)
-        self._weights_version += 1
+        self.apply_gradient(optimizer, grad, opt_state, lr)
 
     def sync_replicas(self, training_data=None):
         """Data-parallel start-up (no counterpart in the single-process reference): every layer of the stack takes rank

@@ -140,17 +140,6 @@ def optimizer_step(opt, params, grad, state):
     L.check(rc, 'db_optimizer_step')
 
 
-def optimizer_step_range(opt, params, grad, state, begin, count):
-    """The same update on elements [begin, begin + count) only (chunk-pipelined data-parallel step)."""
-    rc = L.lib().db_optimizer_step_range(L.handle(), L.stream(), ctypes.byref(opt), L.fptr(params), L.fptr(grad),
-                                         L.fptr(state), params.numel(), int(begin), int(count))
-    L.check(rc, 'db_optimizer_step_range')
-
-
-def set_sm_limit(max_ctas):
-    L.check(L.lib().db_set_sm_limit(L.handle(), int(max_ctas)), 'db_set_sm_limit')
-
-
 def softplus(x):
     x = _f32(x)
     out = torch.empty_like(x)
@@ -182,7 +171,7 @@ class CdTcPlan:
     """Owns the workspace / split-weight cache of the fused tcgen05 CD-k step for one (N, V, H, k)."""
 
     def __init__(self, N, V, H, k, pcd=False, n_global=None, device='cuda'):
-        self.desc = L.db_cd_tc_desc_t(N, V, H, k, 1 if pcd else 0, 1.0 / float(n_global or N), 0, 0)
+        self.desc = L.db_cd_tc_desc_t(N, V, H, k, 1 if pcd else 0, 1.0 / float(n_global or N), 0)
         wb = int(L.lib().db_cd_tc_workspace_bytes(ctypes.byref(self.desc)))
         if wb == 0:
             raise ValueError('tensor-core CD path needs N, V, H multiples of 8 (got %d, %d, %d)' % (N, V, H))
@@ -202,10 +191,7 @@ class CdTcPlan:
         self.desc.v0_u8 = 1 if v0.dtype == torch.uint8 else 0
         return L.ptr(v0)
 
-    def step(self, v0, params, grad, injected=None, rng=None, vk_out=None, hk_out=None, p0_out=None, pk_out=None,
-             defer_dw=False):
-        """defer_dw: leave dW to later dw() calls (row chunks); the bias gradients are still written."""
-        self.desc.defer_dw = 1 if defer_dw else 0
+    def step(self, v0, params, grad, injected=None, rng=None, vk_out=None, hk_out=None, p0_out=None, pk_out=None):
         r = rng.next(2 * self.k + 1) if (rng is not None and injected is None) else None
         rc = L.lib().db_cd_tc_step(
             L.handle(), L.stream(), ctypes.byref(self.desc), self._batch_ptr(v0), L.fptr(params), L.ptr(self.cache),
@@ -216,13 +202,16 @@ class CdTcPlan:
 
     def update_fusable(self):
         """True when the dW kernel of this shape can carry the optimizer update in its epilogue (db_cd_tc_step_update)."""
-        return bool(L.lib().db_cd_tc_update_fusable(ctypes.byref(self.desc)))
+        return int(L.lib().db_cd_tc_update_fusable(ctypes.byref(self.desc))) >= 1
+
+    def update_fusion_pays(self):
+        """True when that fused form is also the faster one (deep batches); else step() + apply_update()."""
+        return int(L.lib().db_cd_tc_update_fusable(ctypes.byref(self.desc))) == 2
 
     def step_update(self, v0, params, grad, opt, opt_state, injected=None, rng=None):
         """step() + optimizer step + split-weight refresh in the chain's own launches (north-star K2): the dW epilogue
         updates W / the optimizer slots / the fp16 cache, the bias kernel updates b | c. `params` and `opt_state` are
         modified in place; `grad` receives the packed gradient as step() would."""
-        self.desc.defer_dw = 0
         r = rng.next(2 * self.k + 1) if (rng is not None and injected is None) else None
         rc = L.lib().db_cd_tc_step_update(
             L.handle(), L.stream(), ctypes.byref(self.desc), self._batch_ptr(v0), L.fptr(params), L.ptr(self.cache),
@@ -238,13 +227,6 @@ class CdTcPlan:
         rc = L.lib().db_cd_tc_apply_update(L.handle(), L.stream(), self.V, self.H, L.fptr(params), L.fptr(grad),
                                            ctypes.byref(opt), L.fptr(opt_state), L.ptr(self.cache))
         L.check(rc, 'db_cd_tc_apply_update')
-
-    def dw(self, grad, v_begin, v_count):
-        """dW rows [v_begin, v_begin + v_count) of the packed gradient from the chain ends of the last step()."""
-        rc = L.lib().db_cd_tc_dw(L.handle(), L.stream(), ctypes.byref(self.desc), L.ptr(self.workspace), L.fptr(grad),
-                                 int(v_begin), int(v_count))
-        L.check(rc, 'db_cd_tc_dw')
-        return grad
 
 
 # ---- GP ---------------------------------------------------------------------------------------------

@@ -156,8 +156,6 @@ typedef struct {
   int k;              /* Gibbs steps >= 1 */
   int pcd;            /* 1: chain starts from (and updates) the persistent hidden state */
   float inv_global_n; /* 1 / (batch rows over all ranks) */
-  int defer_dw;       /* 1: db_cd_tc_step leaves dW to later db_cd_tc_dw calls (row chunks, so a data-parallel
-                         caller can all-reduce chunk c while chunk c+1 is still being computed) */
   int v0_u8;          /* 1: v0 is uint8 {0,1} instead of fp32 (binary data sets staged as bytes: 4x less host->device traffic) */
 } db_cd_tc_desc_t;
 
@@ -189,21 +187,10 @@ int db_cd_tc_step_update(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_
  * db_optimizer_step + db_cd_tc_refresh_weights, bit-identical to them. Any V, H. */
 int db_cd_tc_apply_update(db_handle_t h, db_stream_t stream, int V, int H, float* params, const float* grad,
                           const db_opt_t* opt, float* opt_state, void* weight_cache);
-/* 1 when the dW product of this shape runs as one work item per tile (enough 128x256 tiles to fill the GPU), which the
- * fused update needs; 0 when it runs K-split (small layers). */
+/* 0: the dW product of this shape runs K-split (small layers), db_cd_tc_step_update is not available. 1: available (one work
+ * item per 128x256 tile). 2: available AND faster than db_cd_tc_step + db_cd_tc_apply_update — the epilogue's pass over W
+ * hides under the tile's MMAs only when the batch (K = 2N of the dW product) is deep enough (>= 16384). */
 int db_cd_tc_update_fusable(const db_cd_tc_desc_t* d);
-
-/* dW rows [v_begin, v_begin + v_count) of the packed gradient, from the chain ends left in `workspace` by a
- * db_cd_tc_step call made with defer_dw = 1. */
-int db_cd_tc_dw(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, void* workspace, float* grad,
-                int v_begin, int v_count);
-/* Upper bound on the CTAs the persistent tensor-core kernels launch (0 = one per SM). A caller that overlaps
- * its own collective kernels (NCCL) with db_cd_tc_dw leaves them a few SMs this way. */
-int db_set_sm_limit(db_handle_t h, int max_ctas);
-/* db_optimizer_step restricted to elements [begin, begin + count) of a packed buffer of n_total elements
- * (state layout unchanged: m | v, each n_total long). */
-int db_optimizer_step_range(db_handle_t h, db_stream_t stream, const db_opt_t* opt, float* params, const float* grad,
-                            float* state, size_t n_total, size_t begin, size_t count);
 
 /* ---- GP path (gplvm.py / gprbm.py) ----------------------------------------------------------- */
 /* hyp (device, 3 floats + workspace use): effective kernel variance alpha, length-scale gamma, noise
