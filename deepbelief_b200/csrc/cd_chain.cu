@@ -171,7 +171,16 @@ __global__ void __launch_bounds__(256) cvt_transpose_kernel(const SrcT* __restri
 // / the [V, H] fp16 split are written in place, and the [H, V] split goes through a shared-memory transpose. The cache is
 // written with the scale in the header and max |W_new| is collected, exactly as the fused dW epilogue does (gemm_tc.cu);
 // rescale_after_update_kernel + the guarded re-split then handle a moved scale. The last CTAs update b | c.
+// Adam step size with the step number taken from the device clock (CUDA-graph replay): lr sqrt(1 - b2^t) / (1 - b1^t), t = step + clock[1]
+__device__ __forceinline__ float adam_lr_from_clock(float lr, float beta1, float beta2, int step, const unsigned long long* clock) {
+  const double t = (double)step + (double)__ldg(clock + 1);
+  return (float)((double)lr * sqrt(1.0 - pow((double)beta2, t)) / (1.0 - pow((double)beta1, t)));
+}
+__global__ void adam_lr_kernel(float lr, float beta1, float beta2, int step, const unsigned long long* clock, float* out) {
+  *out = adam_lr_from_clock(lr, beta1, beta2, step, clock);
+}
 struct ApplyArgs {
+  const float* lr_t_dev;      // != nullptr: Adam's bias-corrected step size, formed on the device by adam_lr_kernel (graph replay)
   OptRule rule;
   float* theta; const float* grad; float* st; float* st2;     // packed W | b | c and slots
   int V, H;
@@ -179,8 +188,9 @@ struct ApplyArgs {
   const float* scale_dev; unsigned int* max_bits;
 };
 constexpr int kApplyTile = 64;
-__global__ void __launch_bounds__(256) apply_update_kernel(const ApplyArgs a) {
+__global__ void __launch_bounds__(256) apply_update_kernel(ApplyArgs a) {
   __shared__ float tile[kApplyTile][kApplyTile + 1];        // scaled new weights, [v][h]
+  if (a.lr_t_dev != nullptr) a.rule.lr_t = __ldg(a.lr_t_dev);
   const int tiles_h = (a.H + kApplyTile - 1) / kApplyTile, tiles_v = (a.V + kApplyTile - 1) / kApplyTile;
   if ((int)blockIdx.x >= tiles_h * tiles_v) {               // bias part: V + H elements behind W
     const size_t nW = (size_t)a.V * a.H;
@@ -445,7 +455,6 @@ static int cd_tc_step_impl(db_handle_t h, db_stream_t stream, const db_cd_tc_des
   float* gW = grad; float* gb = grad + (size_t)V * H; float* gc = gb + V;
   __half* hstate = d->pcd ? static_cast<__half*>(pcd_state) : ws.hb;
 
-  if (rng && rng->clock) return set_err(h, DB_ERR_UNSUPPORTED, "the tensor-core chain takes its draw ids by value (no device clock)");
   RngArgs r; to_rng(rng, r);
   const uint64_t draw0 = rng ? rng->draw : 0;
   auto set_draw = [&](TcGemmParams& p, uint64_t i) {
@@ -582,7 +591,6 @@ extern "C" int db_cd_tc_apply_update(db_handle_t h, db_stream_t stream, int V, i
   DB_REQUIRE(h, params && grad && opt && weight_cache && V > 0 && H > 0, "null operand or empty shape");
   DB_REQUIRE(h, opt->kind == DB_OPT_SGD || opt->kind == DB_OPT_MOMENTUM || opt->kind == DB_OPT_ADAM, "unknown optimizer kind");
   DB_REQUIRE(h, opt->kind == DB_OPT_SGD || opt_state, "the optimizer rule needs its slot buffer");
-  if (opt->clock) return set_err(h, DB_ERR_UNSUPPORTED, "the fused update takes the step number by value (no device clock)");
   cudaStream_t st = (cudaStream_t)stream;
   WeightCacheView wc = weight_cache_view(weight_cache, V, H);
   const size_t n_total = (size_t)V * H + V + H;
@@ -592,6 +600,12 @@ extern "C" int db_cd_tc_apply_update(db_handle_t h, db_stream_t stream, int V, i
     lr_t = (float)((double)opt->lr * sqrt(1.0 - b2t) / (1.0 - b1t));
   }
   ApplyArgs a{};
+  a.lr_t_dev = nullptr;
+  if (opt->clock && opt->kind == DB_OPT_ADAM) {      // fp64 pow is slow on this part: once, not per CTA
+    float* slot = reinterpret_cast<float*>(&wc.hdr->pad[0]);
+    adam_lr_kernel<<<1, 1, 0, st>>>(opt->lr, opt->beta1, opt->beta2, opt->step, (const unsigned long long*)opt->clock, slot);
+    a.lr_t_dev = slot;
+  }
   a.rule = OptRule{opt->kind, opt->lr, lr_t, opt->momentum, opt->beta1, opt->beta2, opt->eps, opt->weight_decay};
   a.theta = params; a.grad = grad;
   a.st = opt->kind != DB_OPT_SGD ? opt_state : nullptr;

@@ -43,7 +43,7 @@ namespace db {
 namespace {
 
 constexpr int BLOCK_M = 128;   // rows of A per tile  (TMEM lanes)
-constexpr int BLOCK_N = 256;   // rows of B per tile  (TMEM columns)
+constexpr int BLOCK_N = 256;   // rows of B per tile  (TMEM columns) at full width; p.tile_n = 256 / 128 / 64 is what a launch uses
 constexpr int BLOCK_K = 64;    // fp16 elements = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int STAGES = 3;
@@ -54,18 +54,18 @@ constexpr int TMEM_COLS = 2 * BLOCK_N;                // 512: H (hi products) | 
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 256;       // warps 4-11
-constexpr int REGS_EPI = 216, REGS_CTRL = 40;   // 256 x 216 + 128 x 40 = 60416 <= 65536
-constexpr int GROUP_M = 8;
+constexpr int REGS_EPI = 232, REGS_CTRL = 40;   // 256 x 232 + 128 x 40 = 64512 <= 65536
+constexpr int GROUP_M_DEFAULT = 16;   // measured at config 5 (V=4096, H=8192, N=16384): 8 / 16 / 32 / 64 -> 32.58 / 32.43 / 33.75 / 35.55 ms per step
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct TileCoord { int m_blk, n_blk; };
 
-__device__ __forceinline__ TileCoord tile_coord(int t, int tiles_m, int tiles_n) {
-  // groups of GROUP_M row-blocks sweep all column-blocks: CTAs running together share A and B tiles in L2
-  const int group_size = GROUP_M * tiles_n;
+__device__ __forceinline__ TileCoord tile_coord(int t, int tiles_m, int tiles_n, int group_m) {
+  // groups of group_m row-blocks sweep all column-blocks: CTAs running together share A and B tiles in L2
+  const int group_size = group_m * tiles_n;
   const int g = t / group_size;
-  const int first_m = g * GROUP_M;
-  const int gm = min(tiles_m - first_m, GROUP_M);
+  const int first_m = g * group_m;
+  const int gm = min(tiles_m - first_m, group_m);
   const int in_g = t - g * group_size;
   TileCoord c;
   c.m_blk = first_m + in_g % gm;
@@ -75,13 +75,13 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int tiles_m, int tiles_n)
 
 // work item -> (k-split, tile, column offset and width inside the tile)
 struct WorkItem { int ks, tile, n_off, bn; };
-__device__ __forceinline__ WorkItem decode_work(int w, int num_tiles, int num_full, int k_splits) {
+__device__ __forceinline__ WorkItem decode_work(int w, int num_tiles, int num_full, int k_splits, int tile_n) {
   WorkItem wi;
-  if (k_splits > 1) { wi.ks = w / num_tiles; wi.tile = w - wi.ks * num_tiles; wi.n_off = 0; wi.bn = BLOCK_N; return wi; }
+  if (k_splits > 1) { wi.ks = w / num_tiles; wi.tile = w - wi.ks * num_tiles; wi.n_off = 0; wi.bn = tile_n; return wi; }
   wi.ks = 0;
-  if (w < num_full) { wi.tile = w; wi.n_off = 0; wi.bn = BLOCK_N; return wi; }
+  if (w < num_full) { wi.tile = w; wi.n_off = 0; wi.bn = tile_n; return wi; }
   const int h = w - num_full;
-  wi.tile = num_full + (h >> 1); wi.n_off = (h & 1) * (BLOCK_N / 2); wi.bn = BLOCK_N / 2;
+  wi.tile = num_full + (h >> 1); wi.n_off = (h & 1) * (tile_n / 2); wi.bn = tile_n / 2;
   return wi;
 }
 
@@ -93,7 +93,7 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 // One 32-column slice of the tile, values in registers (val[j] = accumulator of column nb0 + j for row m of D):
 // scale + bias -> logistic -> sample -> the requested outputs.
 __device__ __forceinline__ void epilogue_slice(const TcGemmParams& p, float (&val)[32], int nb0, int m, bool m_ok, float bias_m,
-                                               float acc_scale, float* __restrict__ out32) {
+                                               float acc_scale, float* __restrict__ out32, uint32_t draw_lo, uint32_t draw_hi) {
   const float inv_pT = p.pT_scale;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
@@ -114,8 +114,7 @@ __device__ __forceinline__ void epilogue_slice(const TcGemmParams& p, float (&va
       const uint32_t grow0 = p.rng.row_offset + (uint32_t)nb0;   // multiple of 4 by construction
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        Philox4 o = philox4x32_10((uint32_t)m, (grow0 >> 2) + q, p.rng.draw_lo, p.rng.draw_hi,
-                                  p.rng.seed_lo, p.rng.seed_hi);
+        Philox4 o = philox4x32_10((uint32_t)m, (grow0 >> 2) + q, draw_lo, draw_hi, p.rng.seed_lo, p.rng.seed_hi);
         sbits |= (val[4 * q + 0] > u32_to_uniform(o.x) ? 1u : 0u) << (4 * q + 0);
         sbits |= (val[4 * q + 1] > u32_to_uniform(o.y) ? 1u : 0u) << (4 * q + 1);
         sbits |= (val[4 * q + 2] > u32_to_uniform(o.z) ? 1u : 0u) << (4 * q + 2);
@@ -277,7 +276,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   const bool two_pass = p.a_lo != nullptr;
 
   const int tiles_m = (p.Ma + BLOCK_M - 1) / BLOCK_M;
-  const int tiles_n = (p.Nb + BLOCK_N - 1) / BLOCK_N;
+  const int tile_n = p.tile_n;                       // 256, or 128 / 64 when wider tiles would leave most SMs without work
+  const int tiles_n = (p.Nb + tile_n - 1) / tile_n;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
   // work item w = (k-split ks, tile t): all tiles of one K range run before the next range starts
@@ -308,6 +308,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  // Programmatic dependent launch: everything above (descriptor prefetch, barrier init, TMEM allocation) overlaps the tail
+  // of the previous kernel of the chain; nothing below touches global memory before that kernel has completed. The next
+  // kernel may start its own prologue right away (it lands on idle SMs when this launch is a small one).
+  ptx::grid_launch_dependents();
+  ptx::grid_dependency_wait();
 
   if (warp < EPI_WARP0) {
     ptx::setmaxnreg_dec<REGS_CTRL>();
@@ -317,10 +322,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         int stage = 0; uint32_t phase = 0;
         const uint32_t a_bytes = two_pass ? 2 * A_TILE_BYTES : A_TILE_BYTES;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-          const WorkItem wi = decode_work(w, num_tiles, num_full, k_splits);
+          const WorkItem wi = decode_work(w, num_tiles, num_full, k_splits, tile_n);
           const int ks = wi.ks;
-          const TileCoord tc = tile_coord(wi.tile, tiles_m, tiles_n);
-          const int m0 = tc.m_blk * BLOCK_M, n0 = tc.n_blk * BLOCK_N + wi.n_off;
+          const TileCoord tc = tile_coord(wi.tile, tiles_m, tiles_n, p.group_m);
+          const int m0 = tc.m_blk * BLOCK_M, n0 = tc.n_blk * tile_n + wi.n_off;
           const uint32_t tx_bytes = a_bytes + (uint32_t)wi.bn * BLOCK_K * 2;
           const int kb_end = min(num_kb, (ks + 1) * kb_per_split);
           for (int kb = ks * kb_per_split; kb < kb_end; ++kb) {
@@ -329,7 +334,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
             ptx::tma_load_2d(st, &tm_a_hi, &full_bar[stage], kb * BLOCK_K, m0);
             if (two_pass) ptx::tma_load_2d(st + A_TILE_BYTES, &tm_a_lo, &full_bar[stage], kb * BLOCK_K, m0);
-            ptx::tma_load_2d(st + 2 * A_TILE_BYTES, wi.bn == BLOCK_N ? &tm_b : &tm_b_half, &full_bar[stage], kb * BLOCK_K, n0);
+            ptx::tma_load_2d(st + 2 * A_TILE_BYTES, wi.bn == tile_n ? &tm_b : &tm_b_half, &full_bar[stage], kb * BLOCK_K, n0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -341,7 +346,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         uint32_t acc_phase = 0;
         const uint32_t tmem_h = tmem_base, tmem_l = tmem_base + (uint32_t)BLOCK_N;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-          const WorkItem wi = decode_work(w, num_tiles, num_full, k_splits);
+          const WorkItem wi = decode_work(w, num_tiles, num_full, k_splits, tile_n);
           const int ks = wi.ks;
           const uint32_t idesc = ptx::umma_idesc(/*F16*/ 0, BLOCK_M, (uint32_t)wi.bn);
           const int kb_begin = ks * kb_per_split, kb_end = min(num_kb, (ks + 1) * kb_per_split);
@@ -375,17 +380,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const int quarter = warp & 3;                   // TMEM lane quarter this warp may read
     const int half = (warp - EPI_WARP0) >> 2;       // column half of the work item this warp owns
     uint32_t acc_phase = 0;
+    const RngArgs rng = rng_resolved(p.rng);        // draw id += device clock when the step runs from a CUDA graph
     float accv[4][32];                              // 128 sums: row m, columns half * bn/2 + [0, bn/2)
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-      const WorkItem wi = decode_work(w, num_tiles, num_full, k_splits);
+      const WorkItem wi = decode_work(w, num_tiles, num_full, k_splits, tile_n);
       const int ks = wi.ks;
       float* const out32 = p.out32 ? p.out32 + (size_t)ks * p.split_stride : nullptr;
-      const TileCoord tc = tile_coord(wi.tile, tiles_m, tiles_n);
+      const TileCoord tc = tile_coord(wi.tile, tiles_m, tiles_n, p.group_m);
       const int m = tc.m_blk * BLOCK_M + quarter * 32 + lane;
       const bool m_ok = m < p.Ma;
       const int half_cols = wi.bn >> 1;             // 128, or 64 for a tail half-tile
       const int n_slices = half_cols >> 5;          // 4 or 2
-      const int n_half0 = tc.n_blk * BLOCK_N + wi.n_off + half * half_cols;
+      const int n_half0 = tc.n_blk * tile_n + wi.n_off + half * half_cols;
       const float bias_m = (p.bias != nullptr && m_ok) ? __ldg(p.bias + m) : 0.0f;
       const float acc_scale = p.acc_scale_dev ? p.acc_scale * __ldg(p.acc_scale_dev) : p.acc_scale;
 
@@ -411,7 +417,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       for (int s = 0; s < 4; ++s) {
         const int nb0 = n_half0 + s * 32;
         if (s < n_slices && nb0 < p.Nb)             // warp-uniform
-          epilogue_slice(p, accv[s], nb0, m, m_ok, bias_m, acc_scale, out32);
+          epilogue_slice(p, accv[s], nb0, m, m_ok, bias_m, acc_scale, out32, rng.draw_lo, rng.draw_hi);
       }
     }
   }
@@ -486,8 +492,13 @@ int tc_gemm_launch(const TcGemmParams& p, int num_sms, cudaStream_t stream) {
   CUtensorMap tm_a_hi, tm_a_lo, tm_b, tm_b_half;
   if (!make_tmap_f16(&tm_a_hi, p.a_hi, p.Ma, p.K, p.lda, BLOCK_M)) return -1001;
   if (!make_tmap_f16(&tm_a_lo, p.a_lo ? p.a_lo : p.a_hi, p.Ma, p.K, p.lda, BLOCK_M)) return -1001;
-  if (!make_tmap_f16(&tm_b, p.b, p.Nb, p.K, p.ldb, BLOCK_N)) return -1001;
-  if (!make_tmap_f16(&tm_b_half, p.b, p.Nb, p.K, p.ldb, BLOCK_N / 2)) return -1001;
+  // Tile width: 128 x 256 tiles unless they would leave most of the SMs idle (the reference's own layer sizes: 328 rows x
+  // 500 units is 8 such tiles) — then 128 or 64 batch rows per tile, so more SMs share the work and each epilogue is shorter.
+  const int tiles_m_host = (p.Ma + BLOCK_M - 1) / BLOCK_M;
+  int tile_n = BLOCK_N;
+  while (tile_n > 64 && tiles_m_host * ((p.Nb + tile_n - 1) / tile_n) * (p.k_splits > 1 ? p.k_splits : 1) < num_sms / 2) tile_n >>= 1;
+  if (!make_tmap_f16(&tm_b, p.b, p.Nb, p.K, p.ldb, tile_n)) return -1001;
+  if (!make_tmap_f16(&tm_b_half, p.b, p.Nb, p.K, p.ldb, tile_n / 2)) return -1001;
 
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -496,14 +507,25 @@ int tc_gemm_launch(const TcGemmParams& p, int num_sms, cudaStream_t stream) {
   });
   if (attr_err != cudaSuccess) return (int)attr_err;
 
-  const int base_tiles = ((p.Ma + BLOCK_M - 1) / BLOCK_M) * ((p.Nb + BLOCK_N - 1) / BLOCK_N);
+  const int base_tiles = tiles_m_host * ((p.Nb + tile_n - 1) / tile_n);
   const int tiles = base_tiles * (p.k_splits > 1 ? p.k_splits : 1);
   const int grid = tiles < num_sms ? tiles : num_sms;
   TcGemmParams q = p;
   const int rem = base_tiles % grid;
-  q.split_tail = (p.k_splits <= 1 && base_tiles > grid && rem > 0 && 2 * rem <= grid) ? 1 : 0;
-  tc_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tm_a_hi, tm_a_lo, tm_b, tm_b_half, q);
-  return (int)cudaGetLastError();
+  {
+    static const int env_gm = [] { const char* e = getenv("DB_TC_GROUP_M"); return e ? atoi(e) : 0; }();   // diagnostics
+    q.group_m = env_gm > 0 ? env_gm : GROUP_M_DEFAULT;
+  }
+  q.tile_n = tile_n;
+  q.split_tail = (tile_n >= 128 && p.k_splits <= 1 && base_tiles > grid && rem > 0 && 2 * rem <= grid) ? 1 : 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  static const int pdl = [] { const char* e = getenv("DB_TC_PDL"); return (e && e[0] == '0') ? 0 : 1; }();   // diagnostics
+  attr[0].val.programmaticStreamSerializationAllowed = pdl;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, tc_gemm_kernel, tm_a_hi, tm_a_lo, tm_b, tm_b_half, q);
 }
 
 }  // namespace db

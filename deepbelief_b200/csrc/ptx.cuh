@@ -137,6 +137,12 @@ __device__ __forceinline__ void setmaxnreg_dec() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
+// ---- programmatic dependent launch ------------------------------------------------------------------
+// wait: blocks until the grids this one depends on have completed and their memory is visible (no-op without the
+// launch attribute). launch_dependents: the next kernel in the stream may start its prologue now.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- UMMA descriptors ----------------------------------------------------------------------------
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle (what TMA SWIZZLE_128B writes):
 // rows are 128 B apart, 8-row groups 1024 B apart (SBO), LBO unused (=1), version 1 (Blackwell).

@@ -144,8 +144,8 @@ class BatchFeeder:
 
 
 class CdGraphStep:
-    """One whole training iteration of the general (SIMT) path — lower layers re-sampled, CD-k chain, gradient,
-    optimizer — captured ONCE into a CUDA graph and replayed per batch. The reference-sized configurations
+    """One whole training iteration — lower layers re-sampled, CD-k chain (SIMT tiles, or the tcgen05 chain when the layer
+    qualifies), gradient, optimizer — captured ONCE into a CUDA graph and replayed per batch. The reference-sized configurations
     (328 x 1024 x 500, CD-1) are launch-bound: ~10 kernels of a few microseconds each behind a Python call chain.
     Draw ids and the Adam step number cannot be baked into a graph, so the captured kernels add a device clock
     (db_rng_t.clock / db_opt_t.clock) that the last node of the graph advances: replay j uses exactly the draw ids
@@ -160,8 +160,7 @@ class CdGraphStep:
 
         def iteration():
             v0 = lay.bottom.upprop(self.batch) if lay.bottom else self.batch
-            lay.cd_step(v0, k, persistent, grad=grad, n_global=n_global, force_simt=True)
-            lay.apply_gradient(optimizer, grad, opt_state, lr)
+            lay.cd_update(v0, k, optimizer, opt_state, grad, n_global=n_global, lr=lr, persistent=persistent)
 
         # one eager iteration on a snapshot: loads every kernel, counts the draws each layer consumes, changes nothing
         snap = (lay._trainable_pair(lay._params)[0].clone(), lay._params.clone(), opt_state.clone(),
@@ -180,6 +179,9 @@ class CdGraphStep:
             for r, d0 in zip(self.rngs, snap[4]):
                 r.draw = d0
             optimizer.step_count = snap[5]
+            if lay._tc_plan is not None:                             # the split-weight cache follows the restored weights, and
+                lay._tc_plan.refresh_weights(lay._params)            # the refresh stays OUT of the captured iteration
+                lay._tc_plan.version = lay._weights_version
         restore()
         self.graph = torch.cuda.CUDAGraph()
         # capture_begin / capture_end on a side stream rather than the torch.cuda.graph context manager: that one runs
@@ -219,6 +221,8 @@ class CdGraphStep:
             r.draw += n
         self.optimizer.step_count += 1
         self.lay._weights_version += 1
+        if self.lay._tc_plan is not None:                            # the captured apply_update keeps the cache current
+            self.lay._tc_plan.version = self.lay._weights_version
         self.synced = ([r.draw for r in self.rngs], self.optimizer.step_count)
 
 
@@ -523,14 +527,20 @@ class RBM(layer.Layer):
         return test_loss
 
     # ---- training ----------------------------------------------------------------------------------------------------------
-    # rows x V x H below which the general path (cluster split-K SIMT kernels replayed as one CUDA graph) beats the
-    # tensor-core chain, whose ~2k+3 launches cost ~30 us each however small the layer (scripts/probe_tc_crossover.py)
-    TC_MIN_WORK = 250_000_000
+    # rows x V x H from which the tensor-core chain is taken. Its launches cost ~10 us each however small the layer (64-row
+    # tiles, programmatic dependent launch), against 22-32 us for a cluster split-K SIMT launch at the reference's sizes, but
+    # an iteration also pays ~25 us of fixed work (batch conversion, one-pass update + cache rewrite). Measured in graph
+    # replay (scripts/probe_tc_crossover.py, scripts/profile_small_cd_timeline.py): 328 x 1024 x 200 CD-10 0.27 ms tcgen05 vs
+    # 0.45 SIMT, CD-1 0.15 vs 0.13; 328 x 1024 x 496 CD-10 0.31 vs 0.50, CD-1 0.10 vs 0.12; from 656 rows on tcgen05 wins 2-10x.
+    TC_MIN_WORK = 150_000_000          # CD-1 .. CD-3
+    TC_MIN_WORK_LONG_CHAIN = 50_000_000  # k >= 4: 2k+1 chain launches dominate the iteration
 
-    def _tc_eligible(self, n_rows):
+    def _tc_eligible(self, n_rows, k=None):
+        floor = self.TC_MIN_WORK_LONG_CHAIN if (k is not None and k >= 4) else self.TC_MIN_WORK
+        floor = min(floor, self.TC_MIN_WORK)
         return (self.layer_kind == L.LAYER_RBM and self.temperature is None and n_rows % 8 == 0 and
                 self.num_v % 8 == 0 and self.num_h % 8 == 0 and n_rows >= 8 and
-                n_rows * self.num_v * self.num_h >= self.TC_MIN_WORK)
+                n_rows * self.num_v * self.num_h >= floor)
 
     def cd_step(self, v_0_batch, k=1, persistent=None, *, grad=None, n_global=None, injected=None, force_simt=False):
         """Positive phase + k Gibbs steps + packed CD gradient for one (local) batch; returns
@@ -541,9 +551,9 @@ class RBM(layer.Layer):
         inv_n = 1.0 / float(n_global or n)
         if grad is None:
             grad = torch.empty_like(self._params)
-        if v0.dtype == torch.uint8 and not (self._tc_eligible(n) and not force_simt and persistent is None):
+        if v0.dtype == torch.uint8 and not (self._tc_eligible(n, k) and not force_simt and persistent is None):
             v0 = v0.float()
-        if self._tc_eligible(n) and not force_simt and persistent is None:
+        if self._tc_eligible(n, k) and not force_simt and persistent is None:
             plan = self._tc_plan_for(n, k, n_global or n)
             plan.step(v0, self._params, grad, injected=injected, rng=self.rng)
             return grad, None, None
@@ -603,7 +613,7 @@ class RBM(layer.Layer):
         _, world = _dist_info()
         v0 = self._batch_on_device(v_0_batch)
         n = v0.shape[0]
-        if (world == 1 and persistent is None and self._tc_eligible(n) and self.FUSED_UPDATE and
+        if (world == 1 and persistent is None and self._tc_eligible(n, k) and self.FUSED_UPDATE and
                 self._trainable_pair(grad)[0] is self._params):
             # one process, tensor-core path: the dW kernel applies the optimizer rule and rewrites the split-weight cache
             # in its epilogue (db_cd_tc_step_update); bit-identical to cd_step + apply_gradient + refresh_weights
@@ -614,8 +624,8 @@ class RBM(layer.Layer):
                 plan.version = self._weights_version          # the cache already holds the updated weights
                 return
         self.cd_step(v0, k, persistent, grad=grad, n_global=n_global)
-        if (persistent is None and self._tc_eligible(n) and self.FUSED_UPDATE and self._tc_plan is not None and
-                self._trainable_pair(grad)[0] is self._params and getattr(optimizer, 'clock', None) is None):
+        if (persistent is None and self._tc_eligible(n, k) and self.FUSED_UPDATE and self._tc_plan is not None and
+                self._trainable_pair(grad)[0] is self._params):
             # tensor-core path: all-reduce, then optimizer rule + split-weight cache rewrite in one pass over W
             all_reduce_sum_(grad)
             plan = self._tc_plan
@@ -715,10 +725,9 @@ class RBM(layer.Layer):
         width = self.layers[-1].num_v
         use_graph = (world == 1 and max_iter - start_iter >= self.GRAPH_MIN_ITERATIONS and
                      os.environ.get('DEEPBELIEF_B200_GRAPH', '1') != '0' and
-                     (pcd or not self._tc_eligible(n_local)) and
                      n_local * max(l.num_v * l.num_h for l in self.layers) <= self.GRAPH_MAX_WORK)
         # binary data of a single tensor-core layer travels to the device as bytes; the chain reads them directly
-        bytes_ok = self.bottom is None and not pcd and not use_graph and self._tc_eligible(n_local)
+        bytes_ok = self.bottom is None and not pcd and not use_graph and self._tc_eligible(n_local, num_gibbs_steps)
         feeder = BatchFeeder(training_data, self.device, max(0, max_iter - start_iter), allow_bytes=bytes_ok)
         self.last_feeder = feeder
         for self.iter in range(start_iter, max_iter):

@@ -1,4 +1,4 @@
-"""Two CD-10 steps at config 5 (V=4096, H=8192, N=16384) incl. optimizer + weight refresh (for ncu captures)."""
+"""Two CD-10 updates at config 5 (V=4096, H=8192, N=16384) + one stand-alone apply_update pass (for ncu captures)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -11,8 +11,9 @@ opt = compat.AdamOptimizer(1e-3)
 st = rbm.new_optimizer_state(opt)
 v0 = (torch.rand(N, V, device='cuda') < 0.5).float()
 grad = torch.empty_like(rbm._params)
-for _ in range(2):
-    rbm.cd_step(v0, k, grad=grad)
-    rbm.apply_gradient(opt, grad, st)
+for _ in range(2):                    # RBM.cd_update: chain + dW with the fused optimizer / cache rewrite (db_cd_tc_step_update)
+    rbm.cd_update(v0, k, opt, st, grad)
+plan = rbm._tc_plan                   # and the data-parallel tail as a stand-alone pass (db_cd_tc_apply_update), for its capture
+plan.apply_update(rbm._params, grad, opt.descriptor(), st)
 torch.cuda.synchronize()
 print('ok', float(grad.abs().max()))

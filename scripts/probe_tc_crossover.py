@@ -13,7 +13,7 @@ for (N, V, H) in ((328, 1024, 200), (328, 1024, 496), (656, 1024, 496), (1024, 1
     for k in (1, 10):
         row = []
         for name, min_work in (('tc', 0), ('simt', 1 << 62)):
-            RBM.TC_MIN_WORK = min_work
+            RBM.TC_MIN_WORK = RBM.TC_MIN_WORK_LONG_CHAIN = min_work
             lay = RBM(V, H, name='p', seed=1)
             opt = tf.train.AdamOptimizer(learning_rate=1e-3)
             data = Data.from_arrays(X, batch_size=N, log_epochs=False)

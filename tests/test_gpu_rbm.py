@@ -517,12 +517,13 @@ def test_backprop_loop_reduces_reconstruction_loss(horses):
     assert len(lay.loss_y_vals) == 3 and lay.loss_y_vals[-1] < lay.loss_y_vals[0]
 
 
-@pytest.mark.parametrize('case', ['rbm_adam_eval', 'gbrbm_momentum_pcd', 'stack_concrete'])
+@pytest.mark.parametrize('case', ['rbm_adam_eval', 'gbrbm_momentum_pcd', 'stack_concrete', 'rbm_tensor_chain'])
 def test_training_iteration_as_cuda_graph_is_bit_identical(horses, monkeypatch, case):
-    """RBM.train on the general path replays one captured CUDA graph per iteration (CdGraphStep: draw ids and the Adam
-    step number come from a device clock): the parameters after the loop must be bit-identical to the eager loop —
-    Adam with evaluation steps in between (which consume draws eagerly), Momentum + weight decay with PCD on a
-    Gaussian-visible layer, and a Concrete layer trained on top of a re-sampled bottom layer."""
+    """RBM.train replays one captured CUDA graph per iteration (CdGraphStep: draw ids and the Adam step number come from
+    a device clock): the parameters after the loop must be bit-identical to the eager loop — Adam with evaluation steps
+    in between (which consume draws eagerly), Momentum + weight decay with PCD on a Gaussian-visible layer, a Concrete
+    layer trained on top of a re-sampled bottom layer, and the tcgen05 chain (narrow 64-row tiles at this size, Philox
+    draws keyed by the device clock, db_cd_tc_apply_update with Adam's step size formed on the device)."""
     from deepbelief_b200 import compat as tf
     from deepbelief_b200.layers.data import Data
     from deepbelief_b200.layers.rbm import RBM, CdGraphStep
@@ -537,7 +538,13 @@ def test_training_iteration_as_cuda_graph_is_bit_identical(horses, monkeypatch, 
         np.random.seed(0)                           # Data reshuffles with the global numpy stream on every epoch wrap
         rs2 = np.random.RandomState(11)
         kw = {}
-        if case == 'rbm_adam_eval':
+        if case == 'rbm_tensor_chain':
+            monkeypatch.setattr(RBM, 'TC_MIN_WORK', 0)
+            lay = RBM(1024, 104, name='g3', seed=8)
+            lay.set_weights((rs2.normal(size=(1024, 104)) * 0.01).astype(np.float32), np.zeros(1024), np.zeros(104))
+            opt, data = tf.train.AdamOptimizer(learning_rate=1e-3), X[:296]
+            kw = dict(num_gibbs_steps=2, pcd=False, eval_interval=5)
+        elif case == 'rbm_adam_eval':
             lay = RBM(1024, 100, name='g0', seed=3)
             lay.set_weights((rs2.normal(size=(1024, 100)) * 0.01).astype(np.float32), np.zeros(1024), np.zeros(100))
             opt, data = tf.train.AdamOptimizer(learning_rate=1e-3), X
@@ -562,10 +569,11 @@ def test_training_iteration_as_cuda_graph_is_bit_identical(horses, monkeypatch, 
             created.append(1)
             orig(self, *a, **k)
         monkeypatch.setattr(CdGraphStep, '__init__', spy)
-        lay.train(opt, Data.from_arrays(data, batch_size=100, log_epochs=False), Data.from_arrays(test, batch_size=14, log_epochs=False),
-                  max_iterations=17, **kw)
+        lay.train(opt, Data.from_arrays(data, batch_size=104 if case == 'rbm_tensor_chain' else 100, log_epochs=False),
+                  Data.from_arrays(test, batch_size=14, log_epochs=False), max_iterations=17, **kw)
         monkeypatch.setattr(CdGraphStep, '__init__', orig)
         assert bool(created) == graph
+        assert (lay._tc_plan is not None) == (case == 'rbm_tensor_chain')
         return _np(lay._params), lay.rng.draw, opt.step_count
 
     p_graph, d_graph, s_graph = run(True)
