@@ -332,9 +332,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
             ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-            ptx::tma_load_2d(st, &tm_a_hi, &full_bar[stage], kb * BLOCK_K, m0);
-            if (two_pass) ptx::tma_load_2d(st + A_TILE_BYTES, &tm_a_lo, &full_bar[stage], kb * BLOCK_K, m0);
-            ptx::tma_load_2d(st + 2 * A_TILE_BYTES, wi.bn == tile_n ? &tm_b : &tm_b_half, &full_bar[stage], kb * BLOCK_K, n0);
+            if (p.l2_hints) {      // the row-block group of A stays in L2 while the column blocks of B stream past it
+              ptx::tma_load_2d_hint(st, &tm_a_hi, &full_bar[stage], kb * BLOCK_K, m0, ptx::kL2EvictLast);
+              if (two_pass) ptx::tma_load_2d_hint(st + A_TILE_BYTES, &tm_a_lo, &full_bar[stage], kb * BLOCK_K, m0, ptx::kL2EvictLast);
+              ptx::tma_load_2d_hint(st + 2 * A_TILE_BYTES, wi.bn == tile_n ? &tm_b : &tm_b_half, &full_bar[stage], kb * BLOCK_K, n0,
+                                    ptx::kL2EvictFirst);
+            } else {
+              ptx::tma_load_2d(st, &tm_a_hi, &full_bar[stage], kb * BLOCK_K, m0);
+              if (two_pass) ptx::tma_load_2d(st + A_TILE_BYTES, &tm_a_lo, &full_bar[stage], kb * BLOCK_K, m0);
+              ptx::tma_load_2d(st + 2 * A_TILE_BYTES, wi.bn == tile_n ? &tm_b : &tm_b_half, &full_bar[stage], kb * BLOCK_K, n0);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -517,6 +524,10 @@ int tc_gemm_launch(const TcGemmParams& p, int num_sms, cudaStream_t stream) {
     q.group_m = env_gm > 0 ? env_gm : GROUP_M_DEFAULT;
   }
   q.tile_n = tile_n;
+  {
+    static const int env_hints = [] { const char* e = getenv("DB_TC_L2_HINTS"); return e ? atoi(e) : 0; }();   // diagnostics
+    q.l2_hints = env_hints;
+  }
   q.split_tail = (tile_n >= 128 && p.k_splits <= 1 && base_tiles > grid && rem > 0 && 2 * rem <= grid) ? 1 : 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = stream;

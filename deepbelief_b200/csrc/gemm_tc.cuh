@@ -45,6 +45,7 @@ struct TcGemmParams {
   // accumulation steps — chunking bounds it (measured: 1.2e-4 relative at K = 32768 unsplit).
   int k_splits; size_t split_stride;
   int group_m;                // set by tc_gemm_launch: row-blocks per rasterisation group
+  int l2_hints;               // set by tc_gemm_launch: TMA loads carry L2 eviction priorities (A evict_last, B evict_first)
   int tile_n;                 // set by tc_gemm_launch: batch rows (TMEM columns) per tile: 256, 128 or 64
   int split_tail;             // set by tc_gemm_launch: cut the tiles of a sparse last wave into 128-column halves
   __half* out_s16; int lds16;         // [Nb, Ma] fp16 sample (sample==1) or value

@@ -61,7 +61,7 @@ for name, cls, kind, H, k, data_np in cases:
     cpu = cpu_cd(kind, 1024, H, k, data_np)
     flop = (2 * k + 3) * 2.0 * N * 1024 * H
     out[name] = {'gpu_ms_per_iter': sec * 1e3, 'gpu_ms_per_iter_best': best * 1e3, 'gpu_sample_steps_per_s': N * k / sec, 'gpu_algorithmic_tflops': flop / sec / 1e12,
-                 'cpu_ms_per_iter': cpu * 1e3, 'cpu_sample_steps_per_s': N * k / cpu, 'path': 'tcgen05' if lay._tc_eligible(N) else 'simt'}
+                 'cpu_ms_per_iter': cpu * 1e3, 'cpu_sample_steps_per_s': N * k / cpu, 'path': 'tcgen05' if lay._tc_eligible(N, k) else 'simt'}
 
 # config 3: GPLVM on horses, Q=2, alpha=gamma=1, noise 1 trainable
 g = GPLVM(horses, 2, noise_variance=1.0)
