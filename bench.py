@@ -110,8 +110,8 @@ def count_kernel_launches(fn):
         return None
 
 
-def ncu_dram_bytes(csv_name, kernel_substr):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the first launch of a kernel in a committed `ncu --page raw --csv` file"""
+def ncu_dram_bytes(csv_name, kernel_substr, nth=0):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the nth captured launch of a kernel in a committed `ncu --page raw --csv` file"""
     import csv
     path = os.path.join(ROOT, 'profiles', csv_name)
     if not os.path.exists(path):
@@ -124,9 +124,12 @@ def ncu_dram_bytes(csv_name, kernel_substr):
         ir, iw, ik = head.index('dram__bytes_read.sum'), head.index('dram__bytes_write.sum'), head.index('Kernel Name')
     except ValueError:
         return None
+    seen = 0
     for r in rows[2:]:
         if kernel_substr in r[ik]:
-            return float(r[ir].replace(',', '')) * mult.get(units[ir], 1.0) + float(r[iw].replace(',', '')) * mult.get(units[iw], 1.0)
+            if seen == nth:
+                return float(r[ir].replace(',', '')) * mult.get(units[ir], 1.0) + float(r[iw].replace(',', '')) * mult.get(units[iw], 1.0)
+            seen += 1
     return None
 
 
@@ -517,11 +520,13 @@ def run_b200(args):
                   'sample': 'the full N=5000, D=784, Q=2 evaluation (not a sub-sample), 2 timed evaluations after 1 warm-up: '
                             'torch-CPU fp32 Gram + linalg.cholesky + solve_triangular + autograd (oracle/torch_port.py)'}
 
+    # dram bytes per launch of the dominant kernel from the committed round-2 ncu capture: mean over the captured launches
+    # (a K = 8192 `down`, a K = 4096 `up`, the fused dW launch)
     traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'r01_tc_gemm_traffic.json')
-    if os.path.exists(tpath):                      # dram bytes per launch of the dominant kernel, from the committed ncu capture
-        with open(tpath) as f:
-            traffic = json.load(f).get('traffic_bytes_per_launch_mean')
+    tr = [ncu_dram_bytes('r02_prof_tc_gemm_raw.csv', 'tc_gemm_kernel', nth=i) for i in range(3)]
+    tr = [t for t in tr if t is not None]
+    if tr:
+        traffic = sum(tr) / len(tr)
     if rank == 0:
         achieved = cd_flops(n_local) / (chain_ms * 1e-3) / 1e12
         peak = peaks['tensor_sustained']
@@ -538,7 +543,8 @@ def run_b200(args):
             'gpu_launches_how': launches_how, 'gpu_launch_kernels': launch_names,
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                          'frac': achieved / peak, 'traffic': traffic,
-                         'traffic_unit': 'bytes per tc_gemm_kernel launch (ncu dram read+write, profiles/r01_tc_gemm_traffic.json)',
+                         'traffic_unit': 'bytes per tc_gemm_kernel launch (ncu dram read+write, mean of the three launches in '
+                                         'profiles/r02_prof_tc_gemm_raw.csv; algorithmic bytes of a chain launch ~0.54 GB)',
                          'kernel': 'tc_gemm_kernel (22 launches per step: 21 chain GEMMs + dW with the fused update)',
                          'peak_source': 'MEASURED_PEAKS.json bf16 sustained (%s); fp16 runs at the bf16 rate'
                                         % peaks['source'],

@@ -104,6 +104,10 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tm_y_hi, const __grid_con
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  // programmatic dependent launch (as in gemm_tc.cu): the prologue above overlaps the tail of the previous kernel of the GP
+  // chain; no global access before that kernel has completed
+  ptx::grid_launch_dependents();
+  ptx::grid_dependency_wait();
 
   // tile t -> (column block of C, row block of C); row-block-major so consecutive CTAs share the X rows in L2.
   // lower_only on a square tile grid enumerates the T (T + 1) / 2 lower tiles only (row block i, column block <= i, i
@@ -363,8 +367,14 @@ int tf32_gemm_launch(db_handle_t h, cudaStream_t st, int M, int N, int K, float 
   const int tiles = (lower_only && tm == tn) ? tn * (tn + 1) / 2 : tm * tn;
   const int ctas = tc_ctas(h);
   const int grid = tiles < ctas ? tiles : ctas;
-  tf32x3_gemm_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tyh, tyl, txh, txl, p);
-  return (int)cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  static const int pdl = [] { const char* e = getenv("DB_TF32_PDL"); return (e && e[0] == '0') ? 0 : 1; }();   // diagnostics
+  attr[0].val.programmaticStreamSerializationAllowed = pdl;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, tf32x3_gemm_kernel, tyh, tyl, txh, txl, p);
 }
 
 void tf32_split_lo(db_handle_t h, cudaStream_t st, const float* x, size_t rows, size_t cols, size_t ld, float* lo) {
