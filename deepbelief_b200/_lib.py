@@ -77,6 +77,15 @@ SIGNATURES = {
                                      ctypes.POINTER(db_opt_t), c_float_p]),
     'db_cd_tc_apply_update': (c_int, [c_void_p, c_void_p, c_int, c_int, c_float_p, c_float_p, ctypes.POINTER(db_opt_t), c_float_p,
                                       c_void_p]),
+    'db_enable_peer_access': (c_int, [c_void_p, c_int]),
+    'db_ipc_export': (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(ctypes.c_uint64)]),
+    'db_ipc_import': (c_int, [c_void_p, c_void_p, ctypes.c_uint64, ctypes.POINTER(c_void_p)]),
+    'db_cd_tc_push_ok': (c_int, [ctypes.POINTER(db_cd_tc_desc_t), c_int]),
+    'db_cd_tc_step_push': (c_int, [c_void_p, c_void_p, ctypes.POINTER(db_cd_tc_desc_t), c_void_p, c_float_p, c_void_p,
+                                   c_void_p, c_float_p, ctypes.POINTER(db_rng_t), c_void_p, c_float_p,
+                                   ctypes.POINTER(c_void_p), c_int, c_int]),
+    'db_cd_tc_apply_update_sharded': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p), c_float_p,
+                                              c_float_p, ctypes.POINTER(db_opt_t), c_float_p]),
     'db_cd_tc_update_fusable': (c_int, [ctypes.POINTER(db_cd_tc_desc_t)]),
     'db_gram_rbf': (c_int, [c_void_p, c_void_p, c_float_p, c_float_p, c_int, c_int, c_int, c_float_p, c_int,
                             c_float_p, c_int]),

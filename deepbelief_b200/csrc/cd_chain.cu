@@ -293,6 +293,52 @@ __global__ void __launch_bounds__(256) apply_update_kernel(ApplyArgs a) {
   if ((threadIdx.x & 31) == 0 && mx > 0.0f) atomicMax(a.max_bits, __float_as_uint(mx));
 }
 
+// ---- data-parallel update on this rank's rows of W, gradient reduce-scattered by the dW epilogues of all ranks ----------------
+// slots [world][rows_per * H]: slot s = rank s's partial gradient for MY rows (written by its dW epilogue over NVLink,
+// gemm_tc.cu peer_out). Summed in rank order (deterministic), the rule applied with this rank's slice of the optimizer
+// slots, and the new rows stored into EVERY rank's parameter vector (peer-mapped pointers; the all-gather by push). b | c
+// are updated identically on every rank from the all-reduced bias gradients in `grad`.
+struct ShardArgs {
+  OptRule rule; const float* lr_t_dev;
+  int V, H, world, rank, rows_per;
+  const float* slots; float* grad; float* st; float* st2;
+  float* peer_params[8];
+};
+__global__ void __launch_bounds__(256) apply_shard_kernel(ShardArgs a) {
+  if (a.lr_t_dev != nullptr) a.rule.lr_t = __ldg(a.lr_t_dev);
+  const size_t shard = (size_t)a.rows_per * a.H, n4 = shard / 4, base = (size_t)a.rank * shard;
+  const size_t nW = (size_t)a.V * a.H;
+  float* theta = a.peer_params[a.rank];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 g = __ldcs(reinterpret_cast<const float4*>(a.slots) + i);
+    for (int s = 1; s < a.world; ++s) {
+      const float4 b = __ldcs(reinterpret_cast<const float4*>(a.slots + (size_t)s * shard) + i);
+      g.x += b.x; g.y += b.y; g.z += b.z; g.w += b.w;
+    }
+    const size_t idx = base + 4 * i;
+    float4 th = *reinterpret_cast<const float4*>(theta + idx);
+    float4 m1 = a.rule.kind != 0 ? *reinterpret_cast<const float4*>(a.st + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 m2 = a.rule.kind == 2 ? *reinterpret_cast<const float4*>(a.st2 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 t;
+    t.x = opt_apply(a.rule, th.x, g.x, m1.x, m2.x);
+    t.y = opt_apply(a.rule, th.y, g.y, m1.y, m2.y);
+    t.z = opt_apply(a.rule, th.z, g.z, m1.z, m2.z);
+    t.w = opt_apply(a.rule, th.w, g.w, m1.w, m2.w);
+    if (a.rule.kind != 0) *reinterpret_cast<float4*>(a.st + idx) = m1;
+    if (a.rule.kind == 2) *reinterpret_cast<float4*>(a.st2 + idx) = m2;
+    *reinterpret_cast<float4*>(a.grad + idx) = g;
+    for (int r = 0; r < a.world; ++r) *reinterpret_cast<float4*>(a.peer_params[r] + idx) = t;
+  }
+  // biases: V + H elements behind W, the same on every rank
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)(a.V + a.H); i += (size_t)gridDim.x * blockDim.x) {
+    const size_t idx = nW + i;
+    float s1 = a.rule.kind != 0 ? a.st[idx] : 0.0f, s2 = a.rule.kind == 2 ? a.st2[idx] : 0.0f;
+    theta[idx] = opt_apply(a.rule, theta[idx], __ldg(a.grad + idx), s1, s2);
+    if (a.rule.kind != 0) a.st[idx] = s1;
+    if (a.rule.kind == 2) a.st2[idx] = s2;
+  }
+}
+
 // ---- bias gradients from the interleaved T buffers: one warp per unit ------------------------------
 // gb[v] = -inv_n * (sum_n v0[n,v] - sum_n vk[n,v])          (sign from the phase of each 64-block)
 // gc[h] = -inv_n * 2^-14 * sum_cols (PT_hi + PT_lo)[h,:]     (phase-1 entries are stored negated)
@@ -379,13 +425,18 @@ inline bool tc_shape_ok(int N, int V, int H) { return N >= 8 && (N % 8 == 0) && 
 
 // dW[v,h] = -(1/N) (v0^T p0 - vk^T pk) for rows v in [v_begin, v_begin + v_count): one GEMM over the interleaved
 // K = 2*NP axis (K-chunked, see dw_splits)
+struct PeerPush { float* const* slots; int world, rank; };
 int launch_dw(db_handle_t h, cudaStream_t st, const db_cd_tc_desc_t* d, const ChainWorkspace& ws, float* gW, int v_begin,
-              int v_count, const TcOptArgs* fused = nullptr) {
+              int v_count, const TcOptArgs* fused = nullptr, const PeerPush* push = nullptr) {
   const int V = d->V, H = d->H;
   const int ldT = 2 * ws.NP;
   TcGemmParams p{};
   p.opt.kind = -1;
   if (fused) p.opt = *fused;
+  if (push) {
+    p.peer_world = push->world; p.peer_rank = push->rank; p.peer_rows = V / push->world;
+    for (int r = 0; r < push->world && r < 8; ++r) p.peer_out[r] = push->slots[r];
+  }
   p.Ma = H; p.Nb = v_count; p.K = ldT;
   p.a_hi = ws.pt_hi; p.a_lo = ws.pt_lo; p.lda = ldT; p.b = ws.vt + (size_t)v_begin * ldT; p.ldb = ldT;
   p.acc_scale = -d->inv_global_n / kProbScale; p.act = 0; p.sample = 0;
@@ -436,7 +487,7 @@ extern "C" int db_cd_tc_refresh_weights(db_handle_t h, db_stream_t stream, const
 static int cd_tc_step_impl(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, const void* v0,
                            float* params, void* weight_cache, void* pcd_state, const float* injected,
                            const db_rng_t* rng, void* workspace, float* grad, float* vk_out, float* hk_out,
-                           float* p0_out, float* pk_out, const db_opt_t* opt, float* opt_state) {
+                           float* p0_out, float* pk_out, const db_opt_t* opt, float* opt_state, const PeerPush* push = nullptr) {
   DB_REQUIRE(h, d && v0 && params && weight_cache && workspace && grad, "null operand");
   DB_REQUIRE(h, d->k >= 1, "k must be > 0");   // rbm.py:364
   DB_REQUIRE(h, injected || rng, "sampling needs injected draws or an rng");
@@ -540,7 +591,7 @@ static int cd_tc_step_impl(db_handle_t h, db_stream_t stream, const db_cd_tc_des
     rc = launch_dw(h, st, d, ws, gW, 0, V, &fo);
     if (rc) return rc;
   } else {
-    rc = launch_dw(h, st, d, ws, gW, 0, V);
+    rc = launch_dw(h, st, d, ws, gW, 0, V, nullptr, push);
     if (rc) return rc;
   }
   tc_bias_grads_kernel<<<(V + H + 7) / 8, 256, 0, st>>>(ws.vt, ws.pt_hi, ws.pt_lo, V, H, ldT, d->inv_global_n, gb, gc, bu);
@@ -620,4 +671,50 @@ extern "C" int db_cd_tc_apply_update(db_handle_t h, db_stream_t stream, int V, i
   cvt_transpose_kernel<true><<<grid, 256, 0, st>>>(params, V, H, &wc.hdr->scale, wc.w_hi, wc.w_lo, H, wc.wt_hi, wc.wt_lo, V, -1,
                                                    &wc.hdr->resplit);
   return check_launch(h, "cd_tc_apply_update");
+}
+
+extern "C" int db_cd_tc_push_ok(const db_cd_tc_desc_t* d, int world) {
+  if (!d || world < 2 || world > 8 || !tc_shape_ok(d->N, d->V, d->H)) return 0;
+  if (d->V % (world * 256) != 0) return 0;                       // shard boundaries on tile boundaries
+  return dw_splits(2 * ((d->N + 63) / 64 * 64), d->V, d->H) == 1 ? 1 : 0;
+}
+
+extern "C" int db_cd_tc_step_push(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, const void* v0,
+                                  const float* params, const void* weight_cache, void* pcd_state, const float* injected,
+                                  const db_rng_t* rng, void* workspace, float* grad, float* const* peer_slots, int world,
+                                  int rank) {
+  DB_REQUIRE(h, d && peer_slots && rank >= 0 && rank < world, "null operand or bad rank");
+  if (!db_cd_tc_push_ok(d, world))
+    return set_err(h, DB_ERR_UNSUPPORTED, "peer push needs 2..8 ranks, V a multiple of 256 x ranks and an un-split dW product");
+  PeerPush push{peer_slots, world, rank};
+  return cd_tc_step_impl(h, stream, d, v0, const_cast<float*>(params), const_cast<void*>(weight_cache), pcd_state, injected, rng,
+                         workspace, grad, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &push);
+}
+
+extern "C" int db_cd_tc_apply_update_sharded(db_handle_t h, db_stream_t stream, int V, int H, int world, int rank,
+                                             float* const* peer_params, const float* slots, float* grad, const db_opt_t* opt,
+                                             float* opt_state) {
+  DB_REQUIRE(h, peer_params && slots && grad && opt && V > 0 && H > 0, "null operand or empty shape");
+  DB_REQUIRE(h, world >= 2 && world <= 8 && rank >= 0 && rank < world && V % world == 0 && H % 4 == 0, "bad rank layout");
+  DB_REQUIRE(h, opt->kind == DB_OPT_SGD || opt->kind == DB_OPT_MOMENTUM || opt->kind == DB_OPT_ADAM, "unknown optimizer kind");
+  DB_REQUIRE(h, opt->kind == DB_OPT_SGD || opt_state, "the optimizer rule needs its slot buffer");
+  if (opt->clock) return set_err(h, DB_ERR_UNSUPPORTED, "the sharded update takes the step number by value (no device clock)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n_total = (size_t)V * H + V + H;
+  float lr_t = opt->lr;
+  if (opt->kind == DB_OPT_ADAM) {
+    const double b1t = pow((double)opt->beta1, opt->step), b2t = pow((double)opt->beta2, opt->step);
+    lr_t = (float)((double)opt->lr * sqrt(1.0 - b2t) / (1.0 - b1t));
+  }
+  ShardArgs a{};
+  a.rule = OptRule{opt->kind, opt->lr, lr_t, opt->momentum, opt->beta1, opt->beta2, opt->eps, opt->weight_decay};
+  a.lr_t_dev = nullptr;
+  a.V = V; a.H = H; a.world = world; a.rank = rank; a.rows_per = V / world;
+  a.slots = slots; a.grad = grad;
+  a.st = opt->kind != DB_OPT_SGD ? opt_state : nullptr;
+  a.st2 = opt->kind == DB_OPT_ADAM ? opt_state + n_total : nullptr;
+  for (int r = 0; r < world; ++r) { DB_REQUIRE(h, peer_params[r], "null peer pointer"); a.peer_params[r] = peer_params[r]; }
+  const size_t n4 = (size_t)a.rows_per * H / 4;
+  apply_shard_kernel<<<ew_grid(n4, h->num_sms), 256, 0, st>>>(a);
+  return check_launch(h, "cd_tc_apply_update_sharded");
 }

@@ -423,8 +423,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
         const int nb0 = n_half0 + s * 32;
-        if (s < n_slices && nb0 < p.Nb)             // warp-uniform
-          epilogue_slice(p, accv[s], nb0, m, m_ok, bias_m, acc_scale, out32, rng.draw_lo, rng.draw_hi);
+        if (s < n_slices && nb0 < p.Nb) {           // warp-uniform
+          float* dst32 = out32;
+          if (p.peer_world > 0) {                   // this slice belongs to rank `owner`: store into its slot for this rank
+            const int owner = nb0 / p.peer_rows;
+            dst32 = p.peer_out[owner] + ((ptrdiff_t)p.peer_rank - (ptrdiff_t)owner) * (ptrdiff_t)p.peer_rows * (ptrdiff_t)p.ld32;
+          }
+          epilogue_slice(p, accv[s], nb0, m, m_ok, bias_m, acc_scale, dst32, rng.draw_lo, rng.draw_hi);
+        }
       }
     }
   }
@@ -485,6 +491,11 @@ int tc_gemm_launch(const TcGemmParams& p, int num_sms, cudaStream_t stream) {
     if (p.act || p.sample || p.bias || p.out_s16 || p.out_sT16 || p.out_pT_hi || !p.out32 || p.k_splits > num_kb) return -1000;
     const int per = (num_kb + p.k_splits - 1) / p.k_splits;
     if ((p.k_splits - 1) * per >= num_kb) return -1000;     // an empty chunk would publish an unwritten accumulator
+  }
+  if (p.peer_world > 0) {
+    if (p.peer_world > 8 || p.peer_rank < 0 || p.peer_rank >= p.peer_world || p.k_splits > 1 || p.opt.kind >= 0 || p.act || p.sample ||
+        p.peer_rows <= 0 || (p.peer_rows % BLOCK_N) || p.peer_rows * p.peer_world != p.Nb) return -1000;
+    for (int r = 0; r < p.peer_world; ++r) if (!p.peer_out[r]) return -1000;
   }
   if (p.opt.kind >= 0) {
     if (p.k_splits > 1 || p.act || p.sample || !p.opt.theta || !p.opt.n_hi || !p.opt.n_lo || !p.opt.t_hi || !p.opt.t_lo ||

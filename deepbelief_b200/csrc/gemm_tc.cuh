@@ -55,6 +55,12 @@ struct TcGemmParams {
   __half* out_sT16; int ldsT; int sT_phase;    // fp16 sample, row-wise
   __half* out_pT_hi; __half* out_pT_lo; int ldpT; int pT_phase; float pT_scale;   // split of value*pT_scale
   TcOptArgs opt;              // opt.kind < 0 (set by every caller but the fused dW launch): unused
+  // Data-parallel dW (reduce-scatter by PUSH over NVLink): with peer_world > 0 the fp32 result rows [r * peer_rows,
+  // (r + 1) * peer_rows) of the [Nb, Ma] output are not written to out32 but stored straight into rank r's slot buffer
+  // peer_out[r] (a peer-mapped pointer; this rank's own buffer for r == peer_rank) at slot peer_rank:
+  //   peer_out[r][(peer_rank * peer_rows + (nb - r * peer_rows)) * ld32 + m].
+  // peer_rows is a multiple of the tile width, so a 32-row slice never straddles two owners.
+  float* peer_out[8]; int peer_world, peer_rank, peer_rows;
 };
 
 __host__ __device__ __forceinline__ int tc_interleaved_col(int nb, int phase) {

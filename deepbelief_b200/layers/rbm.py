@@ -602,6 +602,27 @@ class RBM(layer.Layer):
 
     # single-process tensor-core steps run the optimizer inside the dW kernel (False: separate optimizer + refresh launches)
     FUSED_UPDATE = True
+    # data-parallel tensor-core steps on one node: the dW epilogue stores each rank's rows of the gradient straight into that
+    # rank's memory over NVLink and the owner pushes the updated rows back (False, or DEEPBELIEF_B200_PEER_PUSH=0: NCCL all-reduce
+    # of the whole gradient + replicated update)
+    PEER_PUSH = True
+
+    def _peer_state(self, plan, world):
+        """Peer-mapped slot buffers and parameter vectors of all ranks (built once per layer), or None when the shape or the
+        environment does not qualify."""
+        st = getattr(self, '_peer', None)
+        if st is not None and st.get('params_ptr', self._params.data_ptr()) == self._params.data_ptr():
+            return st if st else None
+        self._peer = {}
+        if os.environ.get('DEEPBELIEF_B200_PEER_PUSH', '1') == '0' or not plan.push_ok(world):
+            return None
+        from ..parallel import PeerBuffers
+        slots = torch.zeros(self.num_v * self.num_h, dtype=torch.float32, device=self.device)   # [world][V / world * H]
+        sb, pb = PeerBuffers(slots), PeerBuffers(self._params)
+        self._peer = {'slots': slots, 'slot_ptrs': sb.ptrs, 'param_ptrs': pb.ptrs, 'buffers': (sb, pb),
+                      'params_ptr': self._params.data_ptr(),
+                      'flag': torch.zeros(1, dtype=torch.float32, device=self.device)}
+        return self._peer
 
     def cd_update(self, v_0_batch, k, optimizer, opt_state, grad, n_global=None, lr=None, persistent=None):
         """One full CD-k update: chain, gradient, (data-parallel) sum over ranks, optimizer step. On the tensor-core path
@@ -623,17 +644,44 @@ class RBM(layer.Layer):
                 self._after_update()
                 plan.version = self._weights_version          # the cache already holds the updated weights
                 return
+        if (world > 1 and persistent is None and self._tc_eligible(n, k) and self.FUSED_UPDATE and self.PEER_PUSH and
+                self._trainable_pair(grad)[0] is self._params and getattr(optimizer, 'clock', None) is None):
+            plan = self._tc_plan_for(n, k, n_global or n)
+            peer = self._peer_state(plan, world)
+            if peer is not None:
+                # reduce-scatter by push from the dW epilogue, update of this rank's rows of W, all-gather by push; the two
+                # small NCCL calls carry db | dc and order the ranks (every peer store has landed before it is read)
+                import torch.distributed as td
+                rank = _dist_info()[0]
+                in_sync = getattr(self, '_replica_version', None) == self._weights_version
+                nW = self.num_v * self.num_h
+                plan.step_push(v0, self._params, grad, peer['slot_ptrs'], world, rank, rng=self.rng)
+                td.all_reduce(grad[nW:], op=td.ReduceOp.SUM)
+                plan.apply_update_sharded(peer['param_ptrs'], peer['slots'], grad, optimizer.descriptor(lr), opt_state, world, rank)
+                td.all_reduce(peer['flag'], op=td.ReduceOp.SUM)
+                self._after_update()
+                plan.refresh_weights(self._params)
+                plan.version = self._weights_version
+                if in_sync:
+                    self._replica_version = self._weights_version
+                return
         self.cd_step(v0, k, persistent, grad=grad, n_global=n_global)
         if (persistent is None and self._tc_eligible(n, k) and self.FUSED_UPDATE and self._tc_plan is not None and
                 self._trainable_pair(grad)[0] is self._params):
             # tensor-core path: all-reduce, then optimizer rule + split-weight cache rewrite in one pass over W
+            in_sync = getattr(self, '_replica_version', None) == self._weights_version
             all_reduce_sum_(grad)
             plan = self._tc_plan
             plan.apply_update(self._params, grad, optimizer.descriptor(lr), opt_state)
             self._after_update()
             plan.version = self._weights_version
+            if in_sync:
+                self._replica_version = self._weights_version
             return
+        in_sync = getattr(self, '_replica_version', None) == self._weights_version
         self.apply_gradient(optimizer, grad, opt_state, lr)
+        if in_sync:
+            self._replica_version = self._weights_version
 
     def sync_replicas(self, training_data=None):
         """Data-parallel start-up (no counterpart in the single-process reference): every layer of the stack takes rank
@@ -645,8 +693,13 @@ class RBM(layer.Layer):
         if world == 1:
             return
         for lay in self.layers:
+            # a layer whose parameters only moved through data-parallel updates since the last broadcast is still identical
+            # on every rank (same all-reduced gradient, same rule): repeated train() calls do not re-send 134 MB
+            if getattr(lay, '_replica_version', None) == lay._weights_version:
+                continue
             td.broadcast(lay._params, 0)
             lay._after_update()
+            lay._replica_version = lay._weights_version
         if training_data is not None and hasattr(training_data, 'shard') and getattr(training_data, '_shard', None) is None:
             seed = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int64, device=self._params.device)
             td.broadcast(seed, 0)

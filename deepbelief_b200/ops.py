@@ -220,6 +220,28 @@ class CdTcPlan:
         L.check(rc, 'db_cd_tc_step_update')
         return grad
 
+    def push_ok(self, world):
+        """True when the data-parallel step can reduce-scatter dW by peer stores from the dW epilogue (db_cd_tc_step_push)."""
+        return bool(L.lib().db_cd_tc_push_ok(ctypes.byref(self.desc), int(world)))
+
+    def step_push(self, v0, params, grad, peer_slot_ptrs, world, rank, injected=None, rng=None):
+        """step() whose dW epilogue stores the rows of dW owned by rank r into rank r's slot buffer (peer-mapped pointers);
+        grad receives db | dc only."""
+        r = rng.next(2 * self.k + 1) if (rng is not None and injected is None) else None
+        rc = L.lib().db_cd_tc_step_push(
+            L.handle(), L.stream(), ctypes.byref(self.desc), self._batch_ptr(v0), L.fptr(params), L.ptr(self.cache),
+            L.ptr(self.pcd_state), L.fptr(injected), ctypes.byref(r) if r is not None else None,
+            L.ptr(self.workspace), L.fptr(grad), peer_slot_ptrs, int(world), int(rank))
+        L.check(rc, 'db_cd_tc_step_push')
+        return grad
+
+    def apply_update_sharded(self, peer_param_ptrs, slots, grad, opt, opt_state, world, rank):
+        """Sum this rank's slots, apply the optimizer rule to its rows of W and store the new rows into every rank's
+        parameter vector; b | c from the all-reduced bias gradients in grad (db_cd_tc_apply_update_sharded)."""
+        rc = L.lib().db_cd_tc_apply_update_sharded(L.handle(), L.stream(), self.V, self.H, int(world), int(rank), peer_param_ptrs,
+                                                   L.fptr(slots), L.fptr(grad), ctypes.byref(opt), L.fptr(opt_state))
+        L.check(rc, 'db_cd_tc_apply_update_sharded')
+
     def apply_update(self, params, grad, opt, opt_state):
         """Optimizer step on the packed parameters + rewrite of the split-weight cache in one pass over W — what follows the
         gradient all-reduce of a data-parallel step (db_cd_tc_apply_update); bit-identical to optimizer_step +

@@ -59,3 +59,42 @@ def max_over_ranks(value, device=None):
                      device=device or ('cuda' if td.get_backend() == 'nccl' else 'cpu'))
     td.all_reduce(t, op=td.ReduceOp.MAX)
     return float(t.item())
+
+
+class PeerBuffers:
+    """One device tensor per rank of the node, every one of them mapped into THIS process (CUDA IPC), so that a kernel can store
+    straight into a peer's memory over NVLink (the dW epilogue's reduce-scatter by push, csrc/gemm_tc.cu `peer_out`, and the
+    sharded update's all-gather by push, `apply_shard_kernel`). All ranks must run on one node and see every GPU.
+
+    .ptrs: ctypes array of the world device pointers (this rank's own tensor for r == rank), valid for kernels launched on this
+    rank's device. The handles are opened through the library (db_ipc_import: in this rank's OWN device context with lazy peer
+    access) — a tensor rebuilt by torch.multiprocessing lives in the exporting device's context and raw kernels of this
+    device fault on it."""
+
+    def __init__(self, tensor):
+        import ctypes
+        from . import _lib as L
+        rank, world = dist_info()
+        assert world > 1 and tensor.is_cuda and tensor.is_contiguous()
+        self.tensor = tensor                                            # keeps the exported allocation alive
+        handle = ctypes.create_string_buffer(64)
+        offset = ctypes.c_uint64(0)
+        L.check(L.lib().db_ipc_export(L.handle(), ctypes.c_void_p(int(tensor.data_ptr())), handle, ctypes.byref(offset)), 'db_ipc_export')
+        gathered = [None] * world
+        td.all_gather_object(gathered, (bytes(handle.raw), int(offset.value), int(tensor.device.index)))
+        ptrs = []
+        probe = torch.empty(1, dtype=torch.float32, device=tensor.device)
+        for r, (hb, off, dev_index) in enumerate(gathered):
+            if r == rank:
+                ptrs.append(int(tensor.data_ptr()))
+                continue
+            L.check(L.lib().db_enable_peer_access(L.handle(), dev_index), 'db_enable_peer_access')
+            out = ctypes.c_void_p()
+            L.check(L.lib().db_ipc_import(L.handle(), ctypes.create_string_buffer(hb, 64), ctypes.c_uint64(off), ctypes.byref(out)),
+                    'db_ipc_import')
+            ptrs.append(int(out.value))
+            if tensor.dtype == torch.float32:                           # one raw-kernel read of the peer pointer: fails loudly here
+                L.check(L.lib().db_softplus(L.handle(), L.stream(), ctypes.c_void_p(ptrs[-1]), 1, L.fptr(probe)), 'peer read')
+                torch.cuda.synchronize(tensor.device)
+        td.barrier()
+        self.ptrs = (ctypes.c_void_p * world)(*ptrs)

@@ -87,6 +87,15 @@ int db_destroy(db_handle_t h);
 const char* db_last_error(db_handle_t h);
 int db_version(void);
 int db_num_sms(db_handle_t h);
+/* Lets kernels of this context's device dereference pointers into `peer_device`'s memory (cudaDeviceEnablePeerAccess); needed
+ * once per peer before db_cd_tc_step_push / db_cd_tc_apply_update_sharded are given peer-mapped pointers. */
+int db_enable_peer_access(db_handle_t h, int peer_device);
+/* CUDA IPC for the peer-push data-parallel step (all ranks on one node): db_ipc_export gives the 64-byte handle of the
+ * allocation that contains ptr and ptr's offset inside it; the other ranks exchange these by any means and map the buffer
+ * with db_ipc_import, which opens it in the calling rank's own device context (kernels of that device may then store
+ * into it over NVLink). */
+int db_ipc_export(db_handle_t h, const void* ptr, void* handle_out64, unsigned long long* offset_out);
+int db_ipc_import(db_handle_t h, const void* handle64, unsigned long long offset, void** ptr_out);
 
 /* ---- K1: fused unit layer  out = sample(act(col_scale * ((A / a_div) @ op(W)) + bias)) --------
  * Replaces, in one launch: rbm.py:119-131 h_net_input, rbm.py:133-147 v_net_input (transW=1, no
@@ -191,6 +200,26 @@ int db_cd_tc_apply_update(db_handle_t h, db_stream_t stream, int V, int H, float
  * item per 128x256 tile). 2: available AND faster than db_cd_tc_step + db_cd_tc_apply_update — the epilogue's pass over W
  * hides under the tile's MMAs only when the batch (K = 2N of the dW product) is deep enough (>= 16384). */
 int db_cd_tc_update_fusable(const db_cd_tc_desc_t* d);
+
+/* Data-parallel CD step with the gradient reduce-scattered by PUSH from the dW kernel (no counterpart in the single-process
+ * reference; replaces the NCCL all-reduce of the 4 V H byte gradient of db_cd_tc_step + db_cd_tc_apply_update):
+ *  - db_cd_tc_step_push: db_cd_tc_step whose dW epilogue stores the rows of dW owned by rank r (V / world consecutive rows
+ *    of W each) straight into rank r's slot buffer peer_slots[r] (peer-mapped device pointers, [world][V/world * H] floats,
+ *    slot index = the writing rank) while the MMAs of the next tile run; grad receives db | dc only.
+ *  - the caller then sums db | dc over the ranks and orders the ranks (any stream-ordered collective, e.g. NCCL);
+ *  - db_cd_tc_apply_update_sharded: sums the world slots of this rank in rank order, applies the optimizer rule to its rows
+ *    of W with its slice of opt_state, writes the reduced rows into grad and the NEW rows into every rank's parameter
+ *    vector peer_params[r] (the all-gather, by push), and updates b | c identically on every rank;
+ *  - after a second ordering of the ranks every rank refreshes its split-weight cache (db_cd_tc_refresh_weights).
+ * db_cd_tc_push_ok: 1 when the shape qualifies (2..8 ranks, V a multiple of 256 x ranks, dW not K-split). */
+int db_cd_tc_push_ok(const db_cd_tc_desc_t* d, int world);
+int db_cd_tc_step_push(db_handle_t h, db_stream_t stream, const db_cd_tc_desc_t* d, const void* v0,
+                       const float* params, const void* weight_cache, void* pcd_state,
+                       const float* injected, const db_rng_t* rng, void* workspace, float* grad,
+                       float* const* peer_slots, int world, int rank);
+int db_cd_tc_apply_update_sharded(db_handle_t h, db_stream_t stream, int V, int H, int world, int rank,
+                                  float* const* peer_params, const float* slots, float* grad, const db_opt_t* opt,
+                                  float* opt_state);
 
 /* ---- GP path (gplvm.py / gprbm.py) ----------------------------------------------------------- */
 /* hyp (device, 3 floats + workspace use): effective kernel variance alpha, length-scale gamma, noise
