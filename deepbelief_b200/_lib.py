@@ -77,6 +77,9 @@ SIGNATURES = {
                                      ctypes.POINTER(db_opt_t), c_float_p]),
     'db_cd_tc_apply_update': (c_int, [c_void_p, c_void_p, c_int, c_int, c_float_p, c_float_p, ctypes.POINTER(db_opt_t), c_float_p,
                                       c_void_p]),
+    'db_gemm_f16x3_scratch_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'db_gemm_f16x3_nt': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float_p, c_int, c_float_p, c_int, c_float,
+                                 c_float_p, c_int, c_int, c_void_p]),
     'db_enable_peer_access': (c_int, [c_void_p, c_int]),
     'db_ipc_export': (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(ctypes.c_uint64)]),
     'db_ipc_import': (c_int, [c_void_p, c_void_p, ctypes.c_uint64, ctypes.POINTER(c_void_p)]),

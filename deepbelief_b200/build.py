@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(HERE, 'libdeepbelief_b200.so')
 STAMP = os.path.join(HERE, 'csrc', '.build_stamp')
 
-SOURCES = ['api.cu', 'host_io.cu', 'layer_simt.cu', 'gemm_tc.cu', 'gemm_tf32.cu', 'cd_chain.cu', 'gp.cu', 'gpdbn.cu']
+SOURCES = ['api.cu', 'host_io.cu', 'layer_simt.cu', 'gemm_tc.cu', 'gemm_tf32.cu', 'gemm_f16x3.cu', 'cd_chain.cu', 'gp.cu', 'gpdbn.cu']
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',

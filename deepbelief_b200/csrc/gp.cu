@@ -16,6 +16,7 @@
 #include "simt_gemm.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tf32.cuh"
+#include "gemm_f16x3.cuh"
 #include "ptx.cuh"
 #include <cstdlib>
 #include <mutex>
@@ -1310,7 +1311,37 @@ int run_gram(db_handle_t h, cudaStream_t st, const float* X, const float* Y, int
 
 // lo_buf (optional, same shape / leading dimension as A): scratch for the tf32 remainders of the panels; when given
 // and the operands are TMA-addressable, the wide K = 512 trailing updates run on the tensor cores (3xTF32).
-int run_potrf(db_handle_t h, cudaStream_t st, float* A, int lda, int N, int* info, float* lo_buf = nullptr) {
+// Scratch of the 3 x fp16 products (gemm_f16x3.cu): scales[0..2] a-priori (L panels, L^-1, K^-1), [3] Y, [4] A from their
+// measured maxima; fp16 hi/lo pairs of the current Cholesky panel, of U = L^-T, of K^-1, of Y^T and of A.
+struct F16Scratch {
+  float* scales; unsigned int* bits;
+  __half *l_hi, *l_lo;      // [N,N]: the Cholesky panels (strictly lower 512-blocks, scale[0]); diagonal blocks: Linv_jj (scale[1])
+  __half *u_hi, *u_lo;      // [N,N]: U = L^-T (scale[1])
+  __half *wt_hi, *wt_lo;    // [N,OB]: block-row products of the triangular inverse (scale[5])
+  __half *k_hi, *k_lo, *y_hi, *y_lo, *a_hi, *a_lo;   // K^-1 [N,N] (scale[2]), Y^T [D,N] (scale[3]), A [N,D] (scale[4])
+};
+inline size_t f16_scratch_bytes(int N, int D) {
+  const size_t nn = (size_t)N * N, nd = (size_t)N * D, no = (size_t)N * OB;
+  return 256 + 2 * sizeof(__half) * (no + 3 * nn + 2 * nd) + 12 * 256;
+}
+inline F16Scratch f16_scratch(void* base, int N, int D) {
+  F16Scratch f;
+  uint8_t* p = static_cast<uint8_t*>(base);
+  auto take = [&](size_t halves) { __half* q = reinterpret_cast<__half*>(p); p += (halves * sizeof(__half) + 255) & ~size_t(255); return q; };
+  f.scales = reinterpret_cast<float*>(p); f.bits = reinterpret_cast<unsigned int*>(p + 64); p += 256;
+  const size_t nn = (size_t)N * N, nd = (size_t)N * D, no = (size_t)N * OB;
+  f.l_hi = take(nn); f.l_lo = take(nn); f.u_hi = take(nn); f.u_lo = take(nn); f.wt_hi = take(no); f.wt_lo = take(no);
+  f.k_hi = take(nn); f.k_lo = take(nn); f.y_hi = take(nd); f.y_lo = take(nd); f.a_hi = take(nd); f.a_lo = take(nd);
+  return f;
+}
+// the fp16 form needs 16-byte row pitches of the fp16 matrices (N, D multiples of 8); DB_GP_F16=0 keeps 3xTF32 everywhere
+inline bool gp_use_f16(int N, int D) {
+  static const bool off = [] { const char* e = getenv("DB_GP_F16"); return e && e[0] == '0'; }();
+  return !off && (N % 8) == 0 && (D % 8) == 0;
+}
+
+int run_potrf(db_handle_t h, cudaStream_t st, float* A, int lda, int N, int* info, float* lo_buf = nullptr,
+              const F16Scratch* f16 = nullptr) {
   cudaMemsetAsync(info, 0, sizeof(int), st);
   static const bool legacy = [] { const char* e = getenv("DB_POTRF_LEGACY"); return e && e[0] == '1'; }();
   static const bool pdl = [] { const char* e = getenv("DB_POTRF_PDL"); return !(e && e[0] == '0'); }();
@@ -1380,8 +1411,20 @@ int run_potrf(db_handle_t h, cudaStream_t st, float* A, int lda, int N, int* inf
       if (lo_buf != nullptr && h->cc_major >= 10) {
         // the remainders are kept for every panel: the tensor-core triangular inverse reads them again (run_trinv_tc)
         float* Plo = lo_buf + (size_t)b1 * lda + b0;
-        tf32_split_lo(h, st, P, rows, b1 - b0, lda, Plo);
-        if (rows >= 512 && tf32_gemm_supported(rows, rows, b1 - b0, P, Plo, lda, P, Plo, lda)) {
+        if (f16 == nullptr) tf32_split_lo(h, st, P, rows, b1 - b0, lda, Plo);
+        if (f16 != nullptr) {
+          // the panel as a scaled fp16 pair (|L_ij| <= sqrt(alpha + s), scales[0]), kept in the N x N pair for the triangular
+          // inverse; trailing update as 3 x fp16
+          const F16Operand P16 = F16Operand{f16->l_hi, f16->l_lo, f16->scales}.at((size_t)b1 * lda + b0);
+          f16_split(h, st, P, rows, b1 - b0, lda, P16, lda);
+          int rc = -1000;
+          if (rows >= 512)
+            rc = f16_gemm_launch(h, st, rows, rows, b1 - b0, -1.0f, P16, lda, P16, lda, 1.0f, A + (size_t)b1 * lda + b1, lda,
+                                 /*lower_only=*/1, /*tri_k=*/0);
+          if (rc != 0 && rc != -1000) return set_err(h, DB_ERR_CUDA, "f16x3 trailing update failed (%d)", rc);
+          done = rc == 0;
+        }
+        if (!done && f16 == nullptr && rows >= 512 && tf32_gemm_supported(rows, rows, b1 - b0, P, Plo, lda, P, Plo, lda)) {
           const int rc = tf32_gemm_launch(h, st, rows, rows, b1 - b0, -1.0f, P, Plo, lda, P, Plo, lda, 1.0f,
                                           A + (size_t)b1 * lda + b1, lda, /*lower_only=*/1, /*tri_k=*/0);
           if (rc != 0 && rc != -1000) return set_err(h, DB_ERR_CUDA, "tf32 trailing update failed (%d)", rc);
@@ -1433,9 +1476,15 @@ int run_trinv(db_handle_t h, cudaStream_t st, const float* L, int ldl, int N, fl
 // L and the remainders of its panels (left behind by run_potrf in lo_buf) are the only inputs; the diagonal blocks of the
 // L buffer are overwritten with the remainders of Linv_jj (L_jj is dead once Linv_jj exists).
 // grid (16, 16, nblk): 32x32 tiles of diagonal block z
+// f16 form (li_hi != nullptr): instead of the tf32 remainders, Linv_jj and U_jj are written again as scaled fp16 pairs (scale
+// *sc16 for both: |L^-1| <= 1/sqrt(s)) at the same positions of the N x N fp16 matrices.
 __global__ void __launch_bounds__(256) trinv_diag_finish_kernel(const float* __restrict__ Li, int N, float* __restrict__ LiLo,
-                                                                float* __restrict__ U, float* __restrict__ Ulo) {
+                                                                float* __restrict__ U, float* __restrict__ Ulo,
+                                                                __half* __restrict__ li_hi = nullptr, __half* __restrict__ li_lo = nullptr,
+                                                                __half* __restrict__ u_hi = nullptr, __half* __restrict__ u_lo = nullptr,
+                                                                const float* __restrict__ sc16 = nullptr) {
   __shared__ float tile[32][33];
+  const float sc = li_hi != nullptr ? __ldg(sc16) : 0.0f;
   const int b0 = blockIdx.z * OB;
   const int nb = min(OB, N - b0);
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
@@ -1448,7 +1497,8 @@ __global__ void __launch_bounds__(256) trinv_diag_finish_kernel(const float* __r
     if (r < nb && c < nb) {
       const size_t idx = (size_t)(b0 + r) * N + b0 + c;
       v = c <= r ? Li[idx] : 0.0f;
-      LiLo[idx] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+      if (li_hi != nullptr) { __half hh, ll; split_f16(v * sc, hh, ll); li_hi[idx] = hh; li_lo[idx] = ll; }
+      else LiLo[idx] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
     }
     tile[ty + 8 * i][tx] = v;
   }
@@ -1460,7 +1510,8 @@ __global__ void __launch_bounds__(256) trinv_diag_finish_kernel(const float* __r
       const float v = tile[tx][ty + 8 * i];
       const size_t idx = (size_t)(b0 + c) * N + b0 + r;
       U[idx] = v;
-      Ulo[idx] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+      if (u_hi != nullptr) { __half hh, ll; split_f16(v * sc, hh, ll); u_hi[idx] = hh; u_lo[idx] = ll; }
+      else Ulo[idx] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
     }
   }
 }
@@ -1495,6 +1546,39 @@ int run_trinv_tc(db_handle_t h, cudaStream_t st, float* L, const float* Llo, int
   return check_launch(h, "trinv_tc");
 }
 
+// The same block-row scheme on the 3 x fp16 GEMM: operands are the scaled fp16 pairs run_potrf left in F16Scratch (panels of
+// L), the ones trinv_diag_finish_kernel writes (Linv_jj into the diagonal blocks of the L pair, U_jj), and the ones the GEMM
+// epilogues emit (W^T, the off-diagonal blocks of U). U is also written in fp32 (exact diagonal of K^-1, tr K^-1).
+int run_trinv_tc_f16(db_handle_t h, cudaStream_t st, float* L, int N, float* Li, float* U, const F16Scratch& f) {
+  const int nblk = (N + OB - 1) / OB;
+  cudaMemsetAsync(U, 0, sizeof(float) * (size_t)N * N, st);
+  for (int j = 0; j < nblk; ++j) {
+    const int b0 = j * OB, nb = std::min(OB, N - b0);
+    cudaMemset2DAsync(Li + (size_t)b0 * N + b0, sizeof(float) * (size_t)N, 0, sizeof(float) * (size_t)nb, nb, st);
+  }
+  trinv_diag_kernel<<<(N + NB - 1) / NB, 64, 0, st>>>(L, N, N, Li, N);
+  for (int s = NB; s < OB && s < N; s *= 2) {
+    const int pairs = (N + 2 * s - 1) / (2 * s);
+    dim3 grid((s + TileSmall::BN - 1) / TileSmall::BN, (s + TileSmall::BM - 1) / TileSmall::BM, pairs);
+    trinv_level_kernel<0, TileSmall><<<grid, 256, 0, st>>>(L, N, N, s, Li, N, U, N);
+    trinv_level_kernel<1, TileSmall><<<grid, 256, 0, st>>>(L, N, N, s, Li, N, U, N);
+  }
+  trinv_diag_finish_kernel<<<dim3(OB / 32, OB / 32, nblk), 256, 0, st>>>(Li, N, nullptr, U, nullptr, f.l_hi, f.l_lo, f.u_hi, f.u_lo,
+                                                                         f.scales + 1);
+  const F16Operand U16{f.u_hi, f.u_lo, f.scales + 1}, L16{f.l_hi, f.l_lo, f.scales}, Lid16{f.l_hi, f.l_lo, f.scales + 1};
+  const F16Operand WT16{f.wt_hi, f.wt_lo, f.scales + 5};
+  for (int j = 1; j < nblk; ++j) {
+    const int P = j * OB, nb = std::min(OB, N - P);
+    int rc = f16_gemm_launch(h, st, P, nb, P, 1.0f, U16, N, L16.at((size_t)P * N), N, 0.0f, nullptr, OB, /*lower_only=*/0, /*tri_k=*/2,
+                             &WT16, OB);
+    if (rc) return set_err(h, DB_ERR_CUDA, "f16x3 triangular inverse (block row product) failed (%d)", rc);
+    const F16Operand Uout = U16.at(P);
+    rc = f16_gemm_launch(h, st, P, nb, nb, -1.0f, WT16, OB, Lid16.at((size_t)P * N + P), N, 0.0f, U + P, N, 0, 0, &Uout, N);
+    if (rc) return set_err(h, DB_ERR_CUDA, "f16x3 triangular inverse (block column) failed (%d)", rc);
+  }
+  return check_launch(h, "trinv_tc_f16");
+}
+
 template <int TRANS>
 int run_trmm(db_handle_t h, cudaStream_t st, const float* Li, int N, const float* B, int ldb, int nrhs, float* out, int ldo,
              float* ssq) {
@@ -1522,6 +1606,7 @@ inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 struct GplvmWorkspace {
   float *K, *Li, *Tmp, *S, *Av, *B1, *B2, *B3, *dXacc, *hyp, *Ulo, *WT, *WTlo;
   GpAccum* acc;
+  void* f16;              // F16Scratch region (3 x fp16 products)
   size_t bytes;
 };
 GplvmWorkspace gplvm_workspace(void* ws, int N, int Q, int D) {
@@ -1543,6 +1628,7 @@ GplvmWorkspace gplvm_workspace(void* ws, int N, int Q, int D) {
   w.Ulo = reinterpret_cast<float*>(p); p += nn;       // tensor-core path: tf32 remainder of Linv^T
   w.WT = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)N * OB);     // block-row products of run_trinv_tc
   w.WTlo = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)N * OB);
+  w.f16 = p; p += align256(f16_scratch_bytes(N, D));
   w.bytes = (size_t)(p - p0);
   return w;
 }
@@ -1988,6 +2074,7 @@ __global__ void gpdbn_finalize_kernel(const GpAccum* __restrict__ acc, const flo
 struct GpdbnWorkspace {
   float *K, *Li, *Kinv, *B, *P, *dXacc, *hyp, *U, *Ulo, *WT, *WTlo;
   GpAccum* acc;
+  void* f16;              // F16Scratch region (3 x fp16 factorisation, triangular inverse and K^-1 product)
   size_t bytes;
 };
 GpdbnWorkspace gpdbn_workspace(void* ws, int N, int Q, int D) {
@@ -2008,6 +2095,7 @@ GpdbnWorkspace gpdbn_workspace(void* ws, int N, int Q, int D) {
   w.Ulo = reinterpret_cast<float*>(p); p += nn;
   w.WT = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)N * OB);
   w.WTlo = reinterpret_cast<float*>(p); p += align256(sizeof(float) * (size_t)N * OB);
+  w.f16 = p; p += align256(f16_scratch_bytes(N, 8));
   w.bytes = (size_t)(p - p0);
   return w;
 }
@@ -2076,7 +2164,10 @@ extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float*
   cudaMemsetAsync(w.acc, 0, sizeof(GpAccum), st);
   if ((rc = run_gram(h, st, X, nullptr, N, N, Q, w.hyp, 1, w.K, N))) return rc;
   const bool tc = gp_use_tensor_path(h, N, D);
-  if ((rc = run_potrf(h, st, w.K, N, N, info, tc ? w.Li : nullptr))) return rc;
+  const bool f16 = tc && gp_use_f16(N, D);
+  F16Scratch fs{};
+  if (f16) { fs = f16_scratch(w.f16, N, D); f16_gp_bounds(st, w.hyp, N, fs.scales); }
+  if ((rc = run_potrf(h, st, w.K, N, N, info, tc ? w.Li : nullptr, f16 ? &fs : nullptr))) return rc;
   if (L_out) cudaMemcpyAsync(L_out, w.K, sizeof(float) * (size_t)N * N, cudaMemcpyDeviceToDevice, st);
   logdet_xsq_kernel<<<1, 1024, 0, st>>>(w.K, N, N, X, N * Q, w.acc);
   if (!tc && (rc = run_trinv(h, st, w.K, N, N, w.Li, w.Tmp))) return rc;
@@ -2085,11 +2176,37 @@ extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float*
     const int tiles32 = (N + 31) / 32;
     double* frob = reinterpret_cast<double*>(reinterpret_cast<char*>(w.acc) + 64);   // nine fp64 scratch sums behind the accumulators
     cudaMemsetAsync(frob, 0, 9 * sizeof(double), st);
-    // Tmp = Linv^T (upper triangular), Ulo = its tf32 remainder
-    if ((rc = run_trinv_tc(h, st, w.K, w.Li, N, w.Li, w.Tmp, w.Ulo, w.WT, w.WTlo))) return rc;
+    // Tmp = Linv^T (upper triangular), Ulo = its tf32 remainder (3 x fp16 form: its scaled fp16 pair in the scratch)
+    if (f16) { if ((rc = run_trinv_tc_f16(h, st, w.K, N, w.Li, w.Tmp, fs))) return rc; }
+    else if ((rc = run_trinv_tc(h, st, w.K, w.Li, N, w.Li, w.Tmp, w.Ulo, w.WT, w.WTlo))) return rc;
     dot_sum_kernel<<<h->num_sms * 8, 256, 0, st>>>(w.Tmp, w.Tmp, nn, frob);       // |Linv|_F^2 = tr K^-1
+    int trc;
+    if (f16) {
+      // the three big products as 3 x fp16 (gemm_f16x3.cu): operands converted once into scaled fp16 pairs
+      F16Operand U16{fs.u_hi, fs.u_lo, fs.scales + 1}, K16{fs.k_hi, fs.k_lo, fs.scales + 2};
+      F16Operand Y16{fs.y_hi, fs.y_lo, fs.scales + 3}, A16{fs.a_hi, fs.a_lo, fs.scales + 4};
+      trc = f16_gemm_launch(h, st, N, N, N, 1.0f, U16, N, U16, N, 0.0f, w.Li, N, 1, 1);        // Li = K^-1 (lower)
+      if (trc) return set_err(h, DB_ERR_CUDA, "f16x3 K^-1 product failed (%d)", trc);
+      mirror_lower_kernel<<<dim3(tiles32, tiles32), 256, 0, st>>>(w.Li, nullptr, N);
+      kinv_diag_kernel<<<(N + 7) / 8, 256, 0, st>>>(w.Tmp, N, w.Li, nullptr);
+      f16_split(h, st, w.Li, N, N, N, K16, N);                                     // |K^-1_ij| <= 1 / s
+      transpose_f32(st, Y, N, D, D, w.B1, N);                                      // B1 = Y^T [D,N]
+      f16_scale_from_absmax(h, st, Y, N, D, D, fs.bits, fs.scales + 3);
+      f16_split(h, st, w.B1, D, N, N, Y16, N);
+      trc = f16_gemm_launch(h, st, D, N, N, 1.0f, Y16, N, K16, N, 0.0f, w.B3, N, 0, 0);        // B3 = (K^-1 Y)^T
+      if (trc) return set_err(h, DB_ERR_CUDA, "f16x3 K^-1 Y product failed (%d)", trc);
+      transpose_f32(st, w.B3, D, N, N, w.Av, D);                                   // Av = A = K^-1 Y [N,D]
+      dot_sum_kernel<<<h->num_sms * 8, 256, 0, st>>>(Y, w.Av, nd, frob + 2);       // |L^-1 Y|^2 = sum Y o A
+      gp_store_ssq_kernel<<<1, 1, 0, st>>>(w.acc, frob);
+      if (want_grad) {
+        f16_scale_from_absmax(h, st, w.Av, N, D, D, fs.bits + 1, fs.scales + 4);
+        f16_split(h, st, w.Av, N, D, D, A16, D);
+        trc = f16_gemm_launch(h, st, N, N, D, -0.5f, A16, D, A16, D, 0.0f, w.Tmp, N, 1, 0);     // Tmp = -0.5 A A^T (lower)
+        if (trc) return set_err(h, DB_ERR_CUDA, "f16x3 A A^T product failed (%d)", trc);
+      }
+    } else {
     // Li = K^-1 (lower), K buffer (L is dead) = its tf32 remainder, written by the same epilogue
-    int trc = tf32_gemm_launch(h, st, N, N, N, 1.0f, w.Tmp, w.Ulo, N, w.Tmp, w.Ulo, N, 0.0f, w.Li, N, 1, 1, w.K);
+    trc = tf32_gemm_launch(h, st, N, N, N, 1.0f, w.Tmp, w.Ulo, N, w.Tmp, w.Ulo, N, 0.0f, w.Li, N, 1, 1, w.K);
     if (trc) return set_err(h, DB_ERR_CUDA, "tf32 K^-1 product failed (%d)", trc);
     mirror_lower_kernel<<<dim3(tiles32, tiles32), 256, 0, st>>>(w.Li, w.K, N);
     kinv_diag_kernel<<<(N + 7) / 8, 256, 0, st>>>(w.Tmp, N, w.Li, w.K);
@@ -2104,6 +2221,9 @@ extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float*
       tf32_split_lo(h, st, w.Av, N, D, D, w.S);                                  // S buffer = remainder of A
       trc = tf32_gemm_launch(h, st, N, N, D, -0.5f, w.Av, w.S, D, w.Av, w.S, D, 0.0f, w.Tmp, N, 1, 0);       // Tmp = -0.5 A A^T (lower)
       if (trc) return set_err(h, DB_ERR_CUDA, "tf32 A A^T product failed (%d)", trc);
+    }
+    }
+    if (want_grad) {
       cudaMemsetAsync(w.dXacc, 0, sizeof(float) * (size_t)N * Q, st);
       const int tiles = (N + TileLarge::BM - 1) / TileLarge::BM;
       gp_contract_mem_kernel<TileLarge><<<dim3(tiles, tiles), 256, 0, st>>>(w.Li, w.Tmp, N, Q, D, X, w.hyp, w.dXacc, w.acc, frob + 3);
@@ -2171,18 +2291,31 @@ extern "C" int db_gpdbn_factor(db_handle_t h, db_stream_t stream, const float* X
   cudaMemsetAsync(info, 0, 2 * sizeof(int), st);
   if ((rc = run_gram(h, st, X, nullptr, N, N, Q, w.hyp, 1, w.K, N))) return rc;
   const bool tc = gp_use_tensor_path(h, N, 32) && gpdbn_tensor_factor();
-  if ((rc = run_potrf(h, st, w.K, N, N, info, tc ? w.Li : nullptr))) return rc;      // clears info[0] itself
+  F16Scratch fs{};
+  const bool f16 = tc && gp_use_f16(N, 8);
+  if (f16) { fs = f16_scratch(w.f16, N, 8); f16_gp_bounds(st, w.hyp, N, fs.scales); }
+  if ((rc = run_potrf(h, st, w.K, N, N, info, tc ? w.Li : nullptr, f16 ? &fs : nullptr))) return rc;      // clears info[0] itself
   if (L_out) cudaMemcpyAsync(L_out, w.K, sizeof(float) * (size_t)N * N, cudaMemcpyDeviceToDevice, st);
   logdet_xsq_kernel<<<1, 1024, 0, st>>>(w.K, N, N, X, N * Q, w.acc);
   if (tc) {
-    // Linv^T and K^-1 = Linv^T Linv on the tensor cores (3xTF32), diagonal of K^-1 in exact fp32 (it carries pred_var)
+    // Linv^T and K^-1 = Linv^T Linv on the tensor cores, diagonal of K^-1 in exact fp32 (it carries pred_var)
+    const int tiles32 = (N + 31) / 32;
+    if (f16) {
+      if ((rc = run_trinv_tc_f16(h, st, w.K, N, w.Li, w.U, fs))) return rc;
+      const F16Operand U16{fs.u_hi, fs.u_lo, fs.scales + 1};
+      const int trc = f16_gemm_launch(h, st, N, N, N, 1.0f, U16, N, U16, N, 0.0f, w.Kinv, N, 1, 1);
+      if (trc) return set_err(h, DB_ERR_CUDA, "f16x3 K^-1 product failed (%d)", trc);
+      mirror_lower_kernel<<<dim3(tiles32, tiles32), 256, 0, st>>>(w.Kinv, nullptr, N);
+      kinv_diag_kernel<<<(N + 7) / 8, 256, 0, st>>>(w.U, N, w.Kinv, nullptr);
+      tf32_split_lo(h, st, w.Kinv, N, N, N, w.K);     // the backward GEMM (db_gpdbn_backward_x, 3xTF32) reads the remainder of K^-1
+    } else {
     if ((rc = run_trinv_tc(h, st, w.K, w.Li, N, w.Li, w.U, w.Ulo, w.WT, w.WTlo))) return rc;
     // the K buffer (L is dead) keeps the tf32 remainder of K^-1 for the backward GEMM (db_gpdbn_backward_x)
     const int trc = tf32_gemm_launch(h, st, N, N, N, 1.0f, w.U, w.Ulo, N, w.U, w.Ulo, N, 0.0f, w.Kinv, N, 1, 1, w.K);
     if (trc) return set_err(h, DB_ERR_CUDA, "tf32 K^-1 product failed (%d)", trc);
-    const int tiles32 = (N + 31) / 32;
     mirror_lower_kernel<<<dim3(tiles32, tiles32), 256, 0, st>>>(w.Kinv, w.K, N);
     kinv_diag_kernel<<<(N + 7) / 8, 256, 0, st>>>(w.U, N, w.Kinv, w.K);
+    }
   } else {
     if ((rc = run_trinv(h, st, w.K, N, N, w.Li, w.Kinv))) return rc;
     const int tiles = (N + TileLarge::BM - 1) / TileLarge::BM;

@@ -640,3 +640,21 @@ def gemm_tf32x3_nt(X, Y, alpha=1.0, beta=0.0, out=None, lower_only=False, X_lo=N
                                    L.fptr(Y_lo), K, float(beta), L.fptr(out), N, 1 if lower_only else 0)
     L.check(rc, 'db_gemm_tf32x3_nt')
     return out
+
+
+def gemm_f16x3_nt(X, Y, alpha=1.0, beta=0.0, out=None, lower_only=False):
+    """out[M,N] = alpha * X[M,K] @ Y[N,K]^T + beta * out on the tensor cores from scaled fp16 hi/lo pairs (three kind::f16
+    passes, fp32-level accuracy at twice the rate of the 3xTF32 form)."""
+    X, Y = _f32(X), _f32(Y)
+    M, K = X.shape
+    N = Y.shape[0]
+    assert Y.shape[1] == K
+    if out is None:
+        assert beta == 0.0
+        out = torch.zeros((M, N), device=X.device, dtype=torch.float32) if lower_only else \
+            torch.empty((M, N), device=X.device, dtype=torch.float32)
+    scratch = torch.empty(int(L.lib().db_gemm_f16x3_scratch_bytes(M, N, K)), dtype=torch.uint8, device=X.device)
+    rc = L.lib().db_gemm_f16x3_nt(L.handle(), L.stream(), M, N, K, float(alpha), L.fptr(X), K, L.fptr(Y), K, float(beta),
+                                  L.fptr(out), N, 1 if lower_only else 0, L.ptr(scratch))
+    L.check(rc, 'db_gemm_f16x3_nt')
+    return out

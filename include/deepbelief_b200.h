@@ -287,6 +287,12 @@ int db_tf32_split_lo(db_handle_t h, db_stream_t stream, const float* x, int rows
 int db_gemm_tf32x3_nt(db_handle_t h, db_stream_t stream, int M, int N, int K, float alpha, const float* X,
                       const float* X_lo, int ldx, const float* Y, const float* Y_lo, int ldy, float beta, float* C,
                       int ldc, int lower_only);
+/* The same product from power-of-two scaled fp16 pairs (x 2^e = hi + lo, three kind::f16 passes: twice the tensor rate
+ * of the 3xTF32 form at the same accuracy): the operands are converted into `scratch` (db_gemm_f16x3_scratch_bytes) with
+ * scales taken from their largest entries. The GP chain uses the kernel with operands it keeps in that form. */
+size_t db_gemm_f16x3_scratch_bytes(int M, int N, int K);
+int db_gemm_f16x3_nt(db_handle_t h, db_stream_t stream, int M, int N, int K, float alpha, const float* X, int ldx,
+                     const float* Y, int ldy, float beta, float* C, int ldc, int lower_only, void* scratch);
 
 /* ---- GPDBN top layer (gprbm.py) in training mode (x_ph = X, gprbm.py:106) ---------------------------
  * One optimisation step of GPRBM.optimize (gprbm.py:375-438) evaluates loss = CE(downprop(sample_mean), V)

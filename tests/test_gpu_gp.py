@@ -409,3 +409,41 @@ def test_gram_kernel_every_latent_dimension(N, M, Q):
         want[np.arange(N), np.arange(N)] += noise
         assert np.all(got.diagonal().cpu().numpy() == np.float32(np.float32(alpha) + np.float32(noise)))
     np.testing.assert_allclose(got.cpu().numpy(), want, rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_cuda(), reason='needs a CUDA device')
+@pytest.mark.parametrize('form', ['f16x3', 'tf32x3'])
+@pytest.mark.parametrize('M,N,K', [(512, 384, 1000), (784, 1300, 2500), (130, 70, 96)])
+def test_split_precision_tensor_gemms_vs_fp64(form, M, N, K):
+    """The two fp32-accurate tensor-core products of the GP chain (db_gemm_f16x3_nt: scaled fp16 hi/lo pairs, three
+    kind::f16 passes; db_gemm_tf32x3_nt: 3xTF32) against fp64, on Gaussian operands and on operands whose entries span six
+    decades (L^-1, K^-1 have such rows): error at most 2e-6 of the largest entry of the result, i.e. at the level of an fp32
+    accumulation (tf.matmul in the reference, gplvm.py:235-244), far below the 1e-4 the losses and gradients must hold."""
+    from deepbelief_b200 import ops
+    rs = np.random.RandomState(M + N + K)
+    if K % 8:                                     # the 3xTF32 form needs a 16-byte row pitch: pad K with zeros for both
+        K = (K + 7) // 8 * 8
+    for wide in (False, True):
+        X = rs.normal(size=(M, K))
+        Y = rs.normal(size=(N, K))
+        if wide:
+            X *= 10.0 ** rs.uniform(-6, 0, size=(M, K))
+            Y *= 10.0 ** rs.uniform(-6, 0, size=(N, K))
+        X32, Y32 = X.astype(np.float32), Y.astype(np.float32)
+        want = X32.astype(np.float64) @ Y32.astype(np.float64).T
+        fn = ops.gemm_f16x3_nt if form == 'f16x3' else ops.gemm_tf32x3_nt
+        got = _np(fn(_cu(X32), _cu(Y32), alpha=1.0))
+        err = np.abs(got - want).max() / np.abs(want).max()
+        assert err < 2e-6, (form, wide, err)
+        C0 = rs.normal(size=(M, N)).astype(np.float32)
+        got = _np(fn(_cu(X32), _cu(Y32), alpha=-0.5, beta=1.0, out=_cu(C0).clone()))
+        err = np.abs(got - (C0 - 0.5 * want)).max() / np.abs(want).max()
+        assert err < 2e-6, (form, wide, 'beta', err)
+    if M == N:
+        return
+    S = rs.normal(size=(M, K)).astype(np.float32)                     # lower_only on a square product
+    want = np.tril(S.astype(np.float64) @ S.astype(np.float64).T)
+    fn = ops.gemm_f16x3_nt if form == 'f16x3' else ops.gemm_tf32x3_nt
+    got = np.tril(_np(fn(_cu(S), _cu(S), lower_only=True)))
+    assert np.abs(got - want).max() / np.abs(want).max() < 2e-6
