@@ -1418,7 +1418,7 @@ int run_potrf(db_handle_t h, cudaStream_t st, float* A, int lda, int N, int* inf
           const F16Operand P16 = F16Operand{f16->l_hi, f16->l_lo, f16->scales}.at((size_t)b1 * lda + b0);
           f16_split(h, st, P, rows, b1 - b0, lda, P16, lda);
           int rc = -1000;
-          if (rows >= 512)
+          if (rows >= 128)       // (the 3xTF32 form kept the SIMT kernel below 512 rows: 71 us for the 392-row tail at N = 5000)
             rc = f16_gemm_launch(h, st, rows, rows, b1 - b0, -1.0f, P16, lda, P16, lda, 1.0f, A + (size_t)b1 * lda + b1, lda,
                                  /*lower_only=*/1, /*tri_k=*/0);
           if (rc != 0 && rc != -1000) return set_err(h, DB_ERR_CUDA, "f16x3 trailing update failed (%d)", rc);
