@@ -22,4 +22,9 @@ python scripts/gp_once.py > $O/r02_plain_gp_once.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/r02_launches_gplvm_n5000.csv python scripts/gp_once.py > $O/r02_ncu_gp.log 2>&1
 ncu --set full --clock-control none -k regex:"gp_contract_mem|dot_sum" -s 0 -c 4 -o $O/r02_prof_gp_contract python scripts/gp_once.py > $O/r02_ncu_gp2.log 2>&1
 export_rep r02_prof_gp_contract
+# the three big 3 x fp16 products of one evaluation: K^-1 = U U^T (launch 26), K^-1 Y (27), A A^T (28); and one K = 512 trailing update (0)
+ncu --set full --clock-control none -k regex:f16x3_gemm -s 26 -c 3 -o $O/r02_prof_f16x3_big python scripts/gp_once.py > $O/r02_ncu_gp3.log 2>&1
+export_rep r02_prof_f16x3_big
+ncu --set full --clock-control none -k regex:f16x3_gemm -s 0 -c 1 -o $O/r02_prof_f16x3_trailing python scripts/gp_once.py > $O/r02_ncu_gp4.log 2>&1
+export_rep r02_prof_f16x3_trailing
 du -sh $O
