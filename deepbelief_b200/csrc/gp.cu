@@ -585,7 +585,47 @@ __global__ void __launch_bounds__(STEP_THREADS) potrf_step_kernel(float* __restr
   const int strip = blockIdx.x;
   const int nb = min(NB, N - j);
   const int row0 = j + strip * NB;
-  {
+  if (vec && nb == NB) {
+    // Full 64-column blocks (every step but a ragged last one): the two factorisation operands are read COALESCED (16 threads
+    // per 256-byte row, like the tensor-core operands) into a row-major staging tile of pitch 65 and transposed from there.
+    // The direct transposed load below touches 32 different rows per warp instruction (~66 cycles of L1 replays each, 8 such
+    // instructions per thread): it made the load phase 7.5k of the step's ~30k cycles.
+    float (*T2s)[65] = reinterpret_cast<float (*)[65]>(smem + 136 * 1024);
+    float (*T2p)[65] = T2s + NB;
+    BlockRegsRM rs2, rp2, rdp, rop;
+    block_load_rm(rs2, t, A, lda, j, j, nb, vec);
+    if (strip > 0) block_load_rm(rp2, t, A, lda, row0, j, N - row0, vec);
+    if (use_tc) {
+      block_load_rm(rdp, t, A, lda, j, jprev, nb, vec);
+      block_load_rm(rop, t, A, lda, row0, jprev, strip > 0 ? N - row0 : 0, vec);
+    }
+    {
+      const int c4 = t & 15, rr = t >> 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = rr + 16 * i;
+        T2s[r][4 * c4] = rs2.v[i].x; T2s[r][4 * c4 + 1] = rs2.v[i].y; T2s[r][4 * c4 + 2] = rs2.v[i].z; T2s[r][4 * c4 + 3] = rs2.v[i].w;
+        if (strip > 0) {
+          T2p[r][4 * c4] = rp2.v[i].x; T2p[r][4 * c4 + 1] = rp2.v[i].y; T2p[r][4 * c4 + 2] = rp2.v[i].z; T2p[r][4 * c4 + 3] = rp2.v[i].w;
+        }
+      }
+    }
+    if (use_tc) {
+      block_store_sw(a_hi, a_lo, 128, 0, t, rdp);
+      block_store_sw(a_hi, a_lo, 128, NB, t, rop);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    {
+      const int r = t & 63, q = t >> 6;        // lanes along r: conflict-free reads of pitch 65 and writes of T[c][r]
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int c = 16 * q + e;
+        S[c][r] = T2s[r][c];
+        if (strip > 0) P[c][r] = T2p[r][c];
+      }
+    }
+  } else {
     BlockRegs<256> rs, rp;
     BlockRegsRM rdp, rop;
     block_load<256>(rs, t, A, lda, j, j, nb, nb, vec);
