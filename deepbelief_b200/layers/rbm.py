@@ -747,7 +747,9 @@ class RBM(layer.Layer):
         re-sampled, rbm.py:621-623) -> chain -> gradient -> optimizer. Under torch.distributed every
         rank feeds its own row shard and the packed gradient is summed over NCCL.
         Extension: step_callback(iteration, grad) is called after every update with the packed
-        (all-reduced) gradient still on the device — a monitoring hook; the reference has none."""
+        (all-reduced) gradient still on the device — a monitoring hook; the reference has none. (With the peer-push
+        exchange of a multi-rank tensor-core step, the dW part of `grad` holds the summed gradient for THIS rank's rows of W
+        only; db | dc are complete on every rank.)"""
         rank, world = _dist_info()
         opt_state = self.new_optimizer_state(optimizer)
         if world > 1:
