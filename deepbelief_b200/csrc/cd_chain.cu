@@ -29,6 +29,10 @@ struct WeightCacheHeader {
 static_assert(sizeof(WeightCacheHeader) == 256, "header is one 256-byte slot");
 
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+// Row pitch (elements) of the INTERNAL fp16 matrices: TMA needs 16-byte row pitches, so widths that are not multiples of 8
+// (the reference's own 500-unit layer) are padded; the padding is never read (the tensor maps carry the true width and
+// zero-fill beyond it) and the fp32 tensors the caller sees keep their natural layout.
+inline int pad8(int x) { return (x + 7) & ~7; }
 
 struct WeightCacheView {
   WeightCacheHeader* hdr;
@@ -38,11 +42,11 @@ struct WeightCacheView {
 inline WeightCacheView weight_cache_view(void* cache, int V, int H) {
   WeightCacheView v;
   uint8_t* p = static_cast<uint8_t*>(cache);
-  const size_t mat = align256((size_t)V * H * sizeof(__half));
+  const size_t mat = align256((size_t)V * pad8(H) * sizeof(__half)), mat_t = align256((size_t)H * pad8(V) * sizeof(__half));
   v.hdr = reinterpret_cast<WeightCacheHeader*>(p); p += 256;
-  v.w_hi = reinterpret_cast<__half*>(p); p += mat;
+  v.w_hi = reinterpret_cast<__half*>(p); p += mat;       // [V, pad8(H)]
   v.w_lo = reinterpret_cast<__half*>(p); p += mat;
-  v.wt_hi = reinterpret_cast<__half*>(p); p += mat;
+  v.wt_hi = reinterpret_cast<__half*>(p); p += mat_t;    // [H, pad8(V)]
   v.wt_lo = reinterpret_cast<__half*>(p);
   return v;
 }
@@ -73,9 +77,9 @@ inline ChainWorkspace chain_workspace(void* ws, int N, int V, int H) {
   w.NP = (N + 63) / 64 * 64;
   uint8_t* p = static_cast<uint8_t*>(ws);
   uint8_t* p0 = p;
-  w.v0b = reinterpret_cast<__half*>(p); p += align256((size_t)N * V * 2);
-  w.vb = reinterpret_cast<__half*>(p); p += align256((size_t)N * V * 2);
-  w.hb = reinterpret_cast<__half*>(p); p += align256((size_t)N * H * 2);
+  w.v0b = reinterpret_cast<__half*>(p); p += align256((size_t)N * pad8(V) * 2);
+  w.vb = reinterpret_cast<__half*>(p); p += align256((size_t)N * pad8(V) * 2);
+  w.hb = reinterpret_cast<__half*>(p); p += align256((size_t)N * pad8(H) * 2);
   w.vt = reinterpret_cast<__half*>(p); p += align256((size_t)V * 2 * w.NP * 2);
   w.pt_hi = reinterpret_cast<__half*>(p); p += align256((size_t)H * 2 * w.NP * 2);
   w.pt_lo = reinterpret_cast<__half*>(p); p += align256((size_t)H * 2 * w.NP * 2);
@@ -183,7 +187,8 @@ struct ApplyArgs {
   const float* lr_t_dev;      // != nullptr: Adam's bias-corrected step size, formed on the device by adam_lr_kernel (graph replay)
   OptRule rule;
   float* theta; const float* grad; float* st; float* st2;     // packed W | b | c and slots
-  int V, H;
+  int V, H, ldw, ldwt;        // ldw / ldwt: row pitches of the [V, H] and [H, V] fp16 cache matrices
+  int vec_ok;                 // 16-byte accesses allowed (H % 4 == 0 and theta / grad / slot pointers 16-byte aligned)
   __half *w_hi, *w_lo, *wt_hi, *wt_lo;
   const float* scale_dev; unsigned int* max_bits;
 };
@@ -206,7 +211,7 @@ __global__ void __launch_bounds__(256) apply_update_kernel(ApplyArgs a) {
   }
   const int r0 = ((int)blockIdx.x / tiles_h) * kApplyTile, c0 = ((int)blockIdx.x % tiles_h) * kApplyTile;
   const float sc = __ldg(a.scale_dev);
-  const bool full = r0 + kApplyTile <= a.V && c0 + kApplyTile <= a.H && (a.H % 4) == 0 && (a.V % 8) == 0;
+  const bool full = a.vec_ok && r0 + kApplyTile <= a.V && c0 + kApplyTile <= a.H;
   float mx = 0.0f;
   if (full) {
     // phase 1: thread = 4 consecutive h of one row v (16-byte accesses, 256 B per 16 threads), 16 rows per pass
@@ -238,8 +243,9 @@ __global__ void __launch_bounds__(256) apply_update_kernel(ApplyArgs a) {
       __half h0, l0, h1, l1, h2, l2, h3, l3;
       split_f16(v0, h0, l0); split_f16(v1, h1, l1); split_f16(v2, h2, l2); split_f16(v3, h3, l3);
       __half2 ha = __halves2half2(h0, h1), hb = __halves2half2(h2, h3), la = __halves2half2(l0, l1), lb = __halves2half2(l2, l3);
-      *reinterpret_cast<uint2*>(a.w_hi + idx) = make_uint2(*reinterpret_cast<uint32_t*>(&ha), *reinterpret_cast<uint32_t*>(&hb));
-      *reinterpret_cast<uint2*>(a.w_lo + idx) = make_uint2(*reinterpret_cast<uint32_t*>(&la), *reinterpret_cast<uint32_t*>(&lb));
+      const size_t widx = (size_t)(r0 + r) * a.ldw + c0 + c4;
+      *reinterpret_cast<uint2*>(a.w_hi + widx) = make_uint2(*reinterpret_cast<uint32_t*>(&ha), *reinterpret_cast<uint32_t*>(&hb));
+      *reinterpret_cast<uint2*>(a.w_lo + widx) = make_uint2(*reinterpret_cast<uint32_t*>(&la), *reinterpret_cast<uint32_t*>(&lb));
     }
     __syncthreads();
     // phase 2: thread = 16 consecutive v of one column h -> 32 contiguous bytes of W^T hi and of W^T lo
@@ -253,7 +259,7 @@ __global__ void __launch_bounds__(256) apply_update_kernel(ApplyArgs a) {
       __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
       hi[e] = *reinterpret_cast<uint32_t*>(&hh); lo[e] = *reinterpret_cast<uint32_t*>(&ll);
     }
-    const size_t tidx = (size_t)(c0 + c) * a.V + r0 + rq;
+    const size_t tidx = (size_t)(c0 + c) * a.ldwt + r0 + rq;
     reinterpret_cast<uint4*>(a.wt_hi + tidx)[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     reinterpret_cast<uint4*>(a.wt_hi + tidx)[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
     reinterpret_cast<uint4*>(a.wt_lo + tidx)[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -274,7 +280,7 @@ __global__ void __launch_bounds__(256) apply_update_kernel(ApplyArgs a) {
         v = t * sc;
         __half hi, lo;
         split_f16(v, hi, lo);
-        a.w_hi[idx] = hi; a.w_lo[idx] = lo;
+        a.w_hi[(size_t)(r0 + r) * a.ldw + c0 + c] = hi; a.w_lo[(size_t)(r0 + r) * a.ldw + c0 + c] = lo;
       }
       tile[r][c] = v;
     }
@@ -284,7 +290,7 @@ __global__ void __launch_bounds__(256) apply_update_kernel(ApplyArgs a) {
       if (r0 + r < a.V && c0 + c < a.H) {
         __half hi, lo;
         split_f16(tile[r][c], hi, lo);
-        a.wt_hi[(size_t)(c0 + c) * a.V + r0 + r] = hi; a.wt_lo[(size_t)(c0 + c) * a.V + r0 + r] = lo;
+        a.wt_hi[(size_t)(c0 + c) * a.ldwt + r0 + r] = hi; a.wt_lo[(size_t)(c0 + c) * a.ldwt + r0 + r] = lo;
       }
     }
   }
@@ -410,9 +416,13 @@ __global__ void dw_reduce_kernel(const float4* __restrict__ part, size_t n4, siz
   }
 }
 
-__global__ void half_to_float_kernel(const __half* __restrict__ src, size_t n, float* __restrict__ dst) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    dst[i] = __half2float(src[i]);
+// [rows, cols] fp16 with row pitch ld -> dense fp32
+__global__ void half_to_float_kernel(const __half* __restrict__ src, size_t rows, size_t cols, size_t ld, float* __restrict__ dst) {
+  const size_t n = rows * cols;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / cols, c = i - r * cols;
+    dst[i] = __half2float(src[r * ld + c]);
+  }
 }
 
 inline int ew_grid(size_t n, int num_sms) {
@@ -420,7 +430,8 @@ inline int ew_grid(size_t n, int num_sms) {
   return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
 }
 
-inline bool tc_shape_ok(int N, int V, int H) { return N >= 8 && (N % 8 == 0) && (V % 8 == 0) && (H % 8 == 0) && V >= 8 && H >= 8; }
+// N a multiple of 8 (Philox draws are keyed by 4-row groups, the interleaved buffers by 64-row blocks); any V, H >= 8
+inline bool tc_shape_ok(int N, int V, int H) { return N >= 8 && (N % 8 == 0) && V >= 8 && H >= 8; }
 
 
 // dW[v,h] = -(1/N) (v0^T p0 - vk^T pk) for rows v in [v_begin, v_begin + v_count): one GEMM over the interleaved
@@ -465,7 +476,7 @@ extern "C" size_t db_cd_tc_workspace_bytes(const db_cd_tc_desc_t* d) {
 }
 
 extern "C" size_t db_cd_tc_weight_cache_bytes(int V, int H) {
-  return 256 + 4 * align256((size_t)V * H * sizeof(__half));
+  return 256 + 2 * align256((size_t)V * pad8(H) * sizeof(__half)) + 2 * align256((size_t)H * pad8(V) * sizeof(__half));
 }
 
 extern "C" int db_cd_tc_refresh_weights(db_handle_t h, db_stream_t stream, const float* W, int V, int H, void* cache) {
@@ -478,7 +489,7 @@ extern "C" int db_cd_tc_refresh_weights(db_handle_t h, db_stream_t stream, const
   absmax_kernel<<<ew_grid(n, h->num_sms), 256, 0, st>>>(W, n, &wc.hdr->max_bits);
   choose_scale_kernel<<<1, 1, 0, st>>>(wc.hdr);
   dim3 grid((H + 31) / 32, (V + 31) / 32);
-  cvt_transpose_kernel<true><<<grid, 256, 0, st>>>(W, V, H, &wc.hdr->scale, wc.w_hi, wc.w_lo, H, wc.wt_hi, wc.wt_lo, V, -1, nullptr);
+  cvt_transpose_kernel<true><<<grid, 256, 0, st>>>(W, V, H, &wc.hdr->scale, wc.w_hi, wc.w_lo, pad8(H), wc.wt_hi, wc.wt_lo, pad8(V), -1, nullptr);
   return check_launch(h, "cd_tc_refresh_weights");
 }
 
@@ -512,6 +523,7 @@ static int cd_tc_step_impl(db_handle_t h, db_stream_t stream, const db_cd_tc_des
     p.rng = r; const uint64_t dr = draw0 + i; p.rng.draw_lo = (uint32_t)dr; p.rng.draw_hi = (uint32_t)(dr >> 32);
   };
   const size_t NH = (size_t)N * H, NV = (size_t)N * V;
+  const int Vp = pad8(V), Hp = pad8(H);
 
   if (N != ws.NP) {   // padded columns of the interleaved buffers must not contribute to dW
     cudaMemsetAsync(ws.vt, 0, (size_t)V * ldT * 2, st);
@@ -521,10 +533,10 @@ static int cd_tc_step_impl(db_handle_t h, db_stream_t stream, const db_cd_tc_des
   {  // data batch -> fp16 [N,V] and interleaved phase 0 of VT
     dim3 grid((V + 31) / 32, (N + 31) / 32);
     if (d->v0_u8)
-      cvt_transpose_kernel<false, uint8_t><<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(v0), N, V, nullptr, ws.v0b, nullptr, V,
+      cvt_transpose_kernel<false, uint8_t><<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(v0), N, V, nullptr, ws.v0b, nullptr, Vp,
                                                                  ws.vt, nullptr, ldT, 0, nullptr);
     else
-      cvt_transpose_kernel<false><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(v0), N, V, nullptr, ws.v0b, nullptr, V, ws.vt,
+      cvt_transpose_kernel<false><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(v0), N, V, nullptr, ws.v0b, nullptr, Vp, ws.vt,
                                                         nullptr, ldT, 0, nullptr);
   }
 
@@ -533,11 +545,11 @@ static int cd_tc_step_impl(db_handle_t h, db_stream_t stream, const db_cd_tc_des
     TcGemmParams p{};
     p.opt.kind = -1;
     p.Ma = H; p.Nb = N; p.K = V;
-    p.a_hi = wc.wt_hi; p.a_lo = wc.wt_lo; p.lda = V; p.b = vin; p.ldb = V;
+    p.a_hi = wc.wt_hi; p.a_lo = wc.wt_lo; p.lda = Vp; p.b = vin; p.ldb = Vp;
     p.acc_scale = 1.0f; p.acc_scale_dev = &wc.hdr->inv_scale; p.bias = c; p.act = 1;
     p.sample = write_sample ? 1 : 0; p.U = U; p.ldu = H; set_draw(p, draw_i);
     p.out32 = p_out; p.ld32 = H;
-    p.out_s16 = write_sample ? hstate : nullptr; p.lds16 = H;
+    p.out_s16 = write_sample ? hstate : nullptr; p.lds16 = Hp;
     if (phase >= 0) {
       p.out_pT_hi = ws.pt_hi; p.out_pT_lo = ws.pt_lo; p.ldpT = ldT; p.pT_phase = phase;
       p.pT_scale = phase == 0 ? kProbScale : -kProbScale;
@@ -548,10 +560,10 @@ static int cd_tc_step_impl(db_handle_t h, db_stream_t stream, const db_cd_tc_des
     TcGemmParams p{};
     p.opt.kind = -1;
     p.Ma = V; p.Nb = N; p.K = H;
-    p.a_hi = wc.w_hi; p.a_lo = wc.w_lo; p.lda = H; p.b = hstate; p.ldb = H;
+    p.a_hi = wc.w_hi; p.a_lo = wc.w_lo; p.lda = Hp; p.b = hstate; p.ldb = Hp;
     p.acc_scale = 1.0f; p.acc_scale_dev = &wc.hdr->inv_scale; p.bias = b; p.act = 1;
     p.sample = 1; p.U = U; p.ldu = V; set_draw(p, draw_i);
-    p.out_s16 = ws.vb; p.lds16 = V;
+    p.out_s16 = ws.vb; p.lds16 = Vp;
     if (last) { p.out_sT16 = ws.vt; p.ldsT = ldT; p.sT_phase = 1; }
     return tc_gemm_launch(p, tc_ctas(h), st);
   };
@@ -583,7 +595,7 @@ static int cd_tc_step_impl(db_handle_t h, db_stream_t stream, const db_cd_tc_des
     fo.theta = params;
     fo.st = opt->kind != DB_OPT_SGD ? opt_state : nullptr;
     fo.st2 = opt->kind == DB_OPT_ADAM ? opt_state + n_total : nullptr;
-    fo.n_hi = wc.w_hi; fo.n_lo = wc.w_lo; fo.t_hi = wc.wt_hi; fo.t_lo = wc.wt_lo; fo.ldt = V;
+    fo.n_hi = wc.w_hi; fo.n_lo = wc.w_lo; fo.ldn = Hp; fo.t_hi = wc.wt_hi; fo.t_lo = wc.wt_lo; fo.ldt = Vp;
     fo.scale_dev = &wc.hdr->scale; fo.max_bits = &wc.hdr->new_max_bits;
     bu.kind = opt->kind; bu.lr = opt->lr; bu.lr_t = lr_t; bu.momentum = opt->momentum; bu.beta1 = opt->beta1; bu.beta2 = opt->beta2;
     bu.eps = opt->eps; bu.weight_decay = opt->weight_decay;
@@ -598,11 +610,11 @@ static int cd_tc_step_impl(db_handle_t h, db_stream_t stream, const db_cd_tc_des
   if (opt) {
     rescale_after_update_kernel<<<1, 1, 0, st>>>(wc.hdr);
     dim3 grid((H + 31) / 32, (V + 31) / 32);
-    cvt_transpose_kernel<true><<<grid, 256, 0, st>>>(params, V, H, &wc.hdr->scale, wc.w_hi, wc.w_lo, H, wc.wt_hi, wc.wt_lo, V, -1,
+    cvt_transpose_kernel<true><<<grid, 256, 0, st>>>(params, V, H, &wc.hdr->scale, wc.w_hi, wc.w_lo, Hp, wc.wt_hi, wc.wt_lo, Vp, -1,
                                                      &wc.hdr->resplit);
   }
-  if (vk_out) half_to_float_kernel<<<ew_grid(NV, h->num_sms), 256, 0, st>>>(ws.vb, NV, vk_out);
-  if (hk_out) half_to_float_kernel<<<ew_grid(NH, h->num_sms), 256, 0, st>>>(hstate, NH, hk_out);
+  if (vk_out) half_to_float_kernel<<<ew_grid(NV, h->num_sms), 256, 0, st>>>(ws.vb, N, V, Vp, vk_out);
+  if (hk_out) half_to_float_kernel<<<ew_grid(NH, h->num_sms), 256, 0, st>>>(hstate, N, H, Hp, hk_out);
   return check_launch(h, "cd_tc_step");
 }
 
@@ -661,14 +673,16 @@ extern "C" int db_cd_tc_apply_update(db_handle_t h, db_stream_t stream, int V, i
   a.theta = params; a.grad = grad;
   a.st = opt->kind != DB_OPT_SGD ? opt_state : nullptr;
   a.st2 = opt->kind == DB_OPT_ADAM ? opt_state + n_total : nullptr;
-  a.V = V; a.H = H;
+  a.V = V; a.H = H; a.ldw = pad8(H); a.ldwt = pad8(V);
+  a.vec_ok = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(a.st) |
+                               reinterpret_cast<uintptr_t>(a.st2)) & 15) == 0;
   a.w_hi = wc.w_hi; a.w_lo = wc.w_lo; a.wt_hi = wc.wt_hi; a.wt_lo = wc.wt_lo;
   a.scale_dev = &wc.hdr->scale; a.max_bits = &wc.hdr->new_max_bits;
   const int tiles = ((H + kApplyTile - 1) / kApplyTile) * ((V + kApplyTile - 1) / kApplyTile), bias_blocks = (V + H + 255) / 256;
   apply_update_kernel<<<tiles + bias_blocks, 256, 0, st>>>(a);
   rescale_after_update_kernel<<<1, 1, 0, st>>>(wc.hdr);
   dim3 grid((H + 31) / 32, (V + 31) / 32);
-  cvt_transpose_kernel<true><<<grid, 256, 0, st>>>(params, V, H, &wc.hdr->scale, wc.w_hi, wc.w_lo, H, wc.wt_hi, wc.wt_lo, V, -1,
+  cvt_transpose_kernel<true><<<grid, 256, 0, st>>>(params, V, H, &wc.hdr->scale, wc.w_hi, wc.w_lo, pad8(H), wc.wt_hi, wc.wt_lo, pad8(V), -1,
                                                    &wc.hdr->resplit);
   return check_launch(h, "cd_tc_apply_update");
 }
@@ -676,6 +690,7 @@ extern "C" int db_cd_tc_apply_update(db_handle_t h, db_stream_t stream, int V, i
 extern "C" int db_cd_tc_push_ok(const db_cd_tc_desc_t* d, int world) {
   if (!d || world < 2 || world > 8 || !tc_shape_ok(d->N, d->V, d->H)) return 0;
   if (d->V % (world * 256) != 0) return 0;                       // shard boundaries on tile boundaries
+  if (d->H % 4 != 0 || ((size_t)d->V * d->H + d->V + d->H) % 4 != 0) return 0;   // 16-byte accesses of the sharded update
   return dw_splits(2 * ((d->N + 63) / 64 * 64), d->V, d->H) == 1 ? 1 : 0;
 }
 

@@ -160,7 +160,8 @@ __device__ __forceinline__ void epilogue_slice(const TcGemmParams& p, float (&va
           val[j0 + jj] = t * sc;
           __half h, l;
           split_f16(val[j0 + jj], h, l);
-          o.n_hi[idx] = h; o.n_lo[idx] = l;
+          const size_t nidx = (size_t)(nb0 + j0 + jj) * o.ldn + m;
+          o.n_hi[nidx] = h; o.n_lo[nidx] = l;
         }
       }
       __half* dhi = o.t_hi + (size_t)m * o.ldt + nb0;
@@ -499,7 +500,7 @@ int tc_gemm_launch(const TcGemmParams& p, int num_sms, cudaStream_t stream) {
   }
   if (p.opt.kind >= 0) {
     if (p.k_splits > 1 || p.act || p.sample || !p.opt.theta || !p.opt.n_hi || !p.opt.n_lo || !p.opt.t_hi || !p.opt.t_lo ||
-        !p.opt.scale_dev || !p.opt.max_bits || (p.opt.ldt % 8) ||
+        !p.opt.scale_dev || !p.opt.max_bits || (p.opt.ldt % 8) || p.opt.ldn < p.Ma ||
         ((reinterpret_cast<uintptr_t>(p.opt.t_hi) | reinterpret_cast<uintptr_t>(p.opt.t_lo)) & 15) ||
         (p.opt.kind != DB_OPT_SGD && !p.opt.st) || (p.opt.kind == DB_OPT_ADAM && !p.opt.st2)) return -1000;
   }

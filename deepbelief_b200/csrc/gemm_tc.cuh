@@ -20,7 +20,8 @@ struct TcOptArgs {
   float lr, lr_t, momentum, beta1, beta2, eps, weight_decay;   // lr_t: bias-corrected Adam step size (host, fp64)
   float* theta;               // parameters, updated in place
   float* st; float* st2;      // optimizer slots (Momentum: st; Adam: st = m, st2 = v)
-  __half* n_hi; __half* n_lo; // [Nb, Ma] fp16 split of theta_new * scale   (W cache)
+  __half* n_hi; __half* n_lo; // [Nb, Ma] fp16 split of theta_new * scale   (W cache), leading dimension ldn
+  int ldn;
   __half* t_hi; __half* t_lo; // [Ma, Nb] fp16 split of theta_new * scale   (W^T cache), leading dimension ldt
   int ldt;
   const float* scale_dev;     // power-of-two scale the cache is written with

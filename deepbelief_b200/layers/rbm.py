@@ -539,7 +539,7 @@ class RBM(layer.Layer):
         floor = self.TC_MIN_WORK_LONG_CHAIN if (k is not None and k >= 4) else self.TC_MIN_WORK
         floor = min(floor, self.TC_MIN_WORK)
         return (self.layer_kind == L.LAYER_RBM and self.temperature is None and n_rows % 8 == 0 and
-                self.num_v % 8 == 0 and self.num_h % 8 == 0 and n_rows >= 8 and
+                self.num_v >= 8 and self.num_h >= 8 and n_rows >= 8 and
                 n_rows * self.num_v * self.num_h >= floor)
 
     def cd_step(self, v_0_batch, k=1, persistent=None, *, grad=None, n_global=None, injected=None, force_simt=False):

@@ -174,10 +174,10 @@ class CdTcPlan:
         self.desc = L.db_cd_tc_desc_t(N, V, H, k, 1 if pcd else 0, 1.0 / float(n_global or N), 0)
         wb = int(L.lib().db_cd_tc_workspace_bytes(ctypes.byref(self.desc)))
         if wb == 0:
-            raise ValueError('tensor-core CD path needs N, V, H multiples of 8 (got %d, %d, %d)' % (N, V, H))
+            raise ValueError('tensor-core CD path needs N a multiple of 8 and V, H >= 8 (got %d, %d, %d)' % (N, V, H))
         self.workspace = torch.empty(wb, dtype=torch.uint8, device=device)
         self.cache = torch.empty(int(L.lib().db_cd_tc_weight_cache_bytes(V, H)), dtype=torch.uint8, device=device)
-        self.pcd_state = torch.zeros((N, H), dtype=torch.float16, device=device) if pcd else None
+        self.pcd_state = torch.zeros((N, (H + 7) // 8 * 8), dtype=torch.float16, device=device) if pcd else None   # row pitch pad8(H)
         self.N, self.V, self.H, self.k = N, V, H, k
 
     def refresh_weights(self, params):

@@ -161,7 +161,7 @@ int db_optimizer_step(db_handle_t h, db_stream_t stream, const db_opt_t* opt, fl
  * DB_ERR_UNSUPPORTED when the shape does not qualify (caller then uses db_layer_forward et al.). */
 typedef struct {
   int N;              /* local batch rows (multiple of 8) */
-  int V, H;           /* multiples of 8 */
+  int V, H;           /* >= 8 (internal fp16 buffers pad their row pitch to a multiple of 8) */
   int k;              /* Gibbs steps >= 1 */
   int pcd;            /* 1: chain starts from (and updates) the persistent hidden state */
   float inv_global_n; /* 1 / (batch rows over all ranks) */
@@ -173,7 +173,8 @@ size_t db_cd_tc_workspace_bytes(const db_cd_tc_desc_t* d);
 size_t db_cd_tc_weight_cache_bytes(int V, int H);
 /* refresh the cache after W changed (optimizer step / restore) */
 int db_cd_tc_refresh_weights(db_handle_t h, db_stream_t stream, const float* W, int V, int H, void* cache);
-/* v0: [N,V] fp32 {0,1} (uint8 when d->v0_u8). params packed (W|b|c). pcd_state: [N,H] fp16 persistent chain (pcd=1) or NULL.
+/* v0: [N,V] fp32 {0,1} (uint8 when d->v0_u8). params packed (W|b|c). pcd_state: fp16 persistent chain [N, H rounded up to 8]
+ * (pcd=1) or NULL.
  * injected: NULL (Philox) or uniforms laid out [U_h0 (N*H) | per step: U_v (N*V), U_h (N*H)].
  * grad: packed (W|b|c) sums * inv_global_n. Optional fp32 exports (may be NULL): vk_out [N,V],
  * hk_out [N,H] (last samples), p0_out / pk_out [N,H] (hidden probabilities at both chain ends). */

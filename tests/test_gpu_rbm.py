@@ -217,7 +217,8 @@ def _margin_uniforms(orc, v0, k, rs, margin=1e-4):
 
 
 # the last case has 160 up-GEMM tiles on 148 SMs: its sparse last wave runs as 128-column half tiles (ragged edges)
-@pytest.mark.parametrize('N,V,H,k', [(64, 64, 64, 1), (328, 1024, 496, 3), (200, 264, 136, 2), (2504, 136, 2040, 1)])
+@pytest.mark.parametrize('N,V,H,k', [(64, 64, 64, 1), (328, 1024, 496, 3), (200, 264, 136, 2), (2504, 136, 2040, 1),
+                                     (328, 1024, 500, 2), (104, 76, 50, 1)])
 def test_tc_chain_bit_exact_with_injected_uniforms(horses, N, V, H, k):
     from deepbelief_b200 import ops
     rs = np.random.RandomState(N + V + H)
@@ -740,12 +741,14 @@ def test_fused_update_is_bit_identical_to_step_plus_optimizer(kind):
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not has_cuda(), reason='needs a CUDA device')
-def test_apply_update_and_byte_batches_are_bit_identical():
+@pytest.mark.parametrize('V,H', [(520, 392), (1024, 500), (76, 50)])
+def test_apply_update_and_byte_batches_are_bit_identical(V, H):
     """The data-parallel tail db_cd_tc_apply_update (optimizer rule + split-weight cache rewrite in one pass, run after the
     gradient all-reduce) against db_optimizer_step + db_cd_tc_refresh_weights, and a uint8 {0,1} batch (what the feeder
     stages for binary data sets) against the same batch in fp32: identical bits in every output."""
     from deepbelief_b200 import compat as tf, ops
-    N, V, H, k = 264, 520, 392, 1                     # not fusable into the dW epilogue (few tiles): the stand-alone kernel's case
+    N, k = 264, 1                                     # not fusable into the dW epilogue (few tiles): the stand-alone kernel's case;
+    # widths that are not multiples of 8 (the reference's 500-unit layer): padded row pitches of the internal fp16 buffers
     rs = np.random.RandomState(3)
     theta0 = np.concatenate([(rs.normal(size=V * H) * 0.05), rs.normal(size=V) * 0.1, rs.normal(size=H) * 0.1]).astype(np.float32)
     v_f32 = torch.as_tensor((rs.uniform(size=(N, V)) < 0.3).astype(np.float32)).cuda()
@@ -767,9 +770,13 @@ def test_apply_update_and_byte_batches_are_bit_identical():
                 ops.optimizer_step(opt.descriptor(), p, grad, state)
                 plan.refresh_weights(p)
         torch.cuda.synchronize()
-        mat = V * H * 2
-        stride = (mat + 255) // 256 * 256
-        out.append((p.clone(), state.clone(), grad.clone(), plan.cache[:8].clone(),
-                    torch.cat([plan.cache[256 + i * stride:256 + i * stride + mat] for i in range(4)])))
+        Hp, Vp = (H + 7) // 8 * 8, (V + 7) // 8 * 8
+        sizes = [V * Hp * 2, V * Hp * 2, H * Vp * 2, H * Vp * 2]          # W hi, W lo [V, Hp]; W^T hi, lo [H, Vp]
+        off, parts = 256, []
+        for i, nbytes in enumerate(sizes):
+            m = plan.cache[off:off + nbytes].view(torch.float16).view(V if i < 2 else H, Hp if i < 2 else Vp)
+            parts.append(m[:, :H if i < 2 else V].contiguous().view(-1))    # the padding columns are never written
+            off += (nbytes + 255) // 256 * 256
+        out.append((p.clone(), state.clone(), grad.clone(), plan.cache[:8].clone(), torch.cat(parts)))
     for name, x, y in zip(('params', 'optimizer state', 'gradient', 'cache scale', 'split-weight cache'), *out):
         assert torch.equal(x, y), name
