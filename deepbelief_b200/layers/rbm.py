@@ -618,7 +618,11 @@ class RBM(layer.Layer):
             return None
         from ..parallel import PeerBuffers
         slots = torch.zeros(self.num_v * self.num_h, dtype=torch.float32, device=self.device)   # [world][V / world * H]
-        sb, pb = PeerBuffers(slots), PeerBuffers(self._params)
+        try:
+            sb, pb = PeerBuffers(slots), PeerBuffers(self._params)
+        except RuntimeError as e:                # raised on every rank together: all of them take the NCCL path
+            self.logger.warning('peer-push exchange unavailable (%s); using the NCCL all-reduce path', e)
+            return None
         self._peer = {'slots': slots, 'slot_ptrs': sb.ptrs, 'param_ptrs': pb.ptrs, 'buffers': (sb, pb),
                       'params_ptr': self._params.data_ptr(),
                       'flag': torch.zeros(1, dtype=torch.float32, device=self.device)}

@@ -72,6 +72,8 @@ class PeerBuffers:
     device fault on it."""
 
     def __init__(self, tensor):
+        """Collective over the default group. Raises RuntimeError on EVERY rank when the mapping failed on any of them (no
+        peer path between two devices, IPC not permitted in this container, ...), so callers can fall back together."""
         import ctypes
         from . import _lib as L
         rank, world = dist_info()
@@ -79,22 +81,36 @@ class PeerBuffers:
         self.tensor = tensor                                            # keeps the exported allocation alive
         handle = ctypes.create_string_buffer(64)
         offset = ctypes.c_uint64(0)
-        L.check(L.lib().db_ipc_export(L.handle(), ctypes.c_void_p(int(tensor.data_ptr())), handle, ctypes.byref(offset)), 'db_ipc_export')
+        err = None
+        try:
+            L.check(L.lib().db_ipc_export(L.handle(), ctypes.c_void_p(int(tensor.data_ptr())), handle, ctypes.byref(offset)),
+                    'db_ipc_export')
+        except Exception as e:                                          # still take part in the collectives below
+            err = e
         gathered = [None] * world
-        td.all_gather_object(gathered, (bytes(handle.raw), int(offset.value), int(tensor.device.index)))
+        td.all_gather_object(gathered, (bytes(handle.raw), int(offset.value), int(tensor.device.index), err is None))
         ptrs = []
-        probe = torch.empty(1, dtype=torch.float32, device=tensor.device)
-        for r, (hb, off, dev_index) in enumerate(gathered):
-            if r == rank:
-                ptrs.append(int(tensor.data_ptr()))
-                continue
-            L.check(L.lib().db_enable_peer_access(L.handle(), dev_index), 'db_enable_peer_access')
-            out = ctypes.c_void_p()
-            L.check(L.lib().db_ipc_import(L.handle(), ctypes.create_string_buffer(hb, 64), ctypes.c_uint64(off), ctypes.byref(out)),
-                    'db_ipc_import')
-            ptrs.append(int(out.value))
-            if tensor.dtype == torch.float32:                           # one raw-kernel read of the peer pointer: fails loudly here
-                L.check(L.lib().db_softplus(L.handle(), L.stream(), ctypes.c_void_p(ptrs[-1]), 1, L.fptr(probe)), 'peer read')
-                torch.cuda.synchronize(tensor.device)
-        td.barrier()
+        if err is None and all(g[3] for g in gathered):
+            try:
+                probe = torch.empty(1, dtype=torch.float32, device=tensor.device)
+                for r, (hb, off, dev_index, _) in enumerate(gathered):
+                    if r == rank:
+                        ptrs.append(int(tensor.data_ptr()))
+                        continue
+                    L.check(L.lib().db_enable_peer_access(L.handle(), dev_index), 'db_enable_peer_access')
+                    out = ctypes.c_void_p()
+                    L.check(L.lib().db_ipc_import(L.handle(), ctypes.create_string_buffer(hb, 64), ctypes.c_uint64(off),
+                                                  ctypes.byref(out)), 'db_ipc_import')
+                    ptrs.append(int(out.value))
+                    if tensor.dtype == torch.float32:                   # one raw-kernel read of the peer pointer: fails loudly here
+                        L.check(L.lib().db_softplus(L.handle(), L.stream(), ctypes.c_void_p(ptrs[-1]), 1, L.fptr(probe)), 'peer read')
+                        torch.cuda.synchronize(tensor.device)
+            except Exception as e:
+                err = e
+        elif err is None:
+            err = RuntimeError('another rank could not export its buffer')
+        ok = torch.tensor([0.0 if err is not None else 1.0], device=tensor.device)
+        td.all_reduce(ok, op=td.ReduceOp.MIN)                           # also the barrier: every mapping is in place
+        if float(ok.item()) < 1.0:
+            raise RuntimeError('peer mapping of the data-parallel buffers failed on at least one rank: %s' % (err,))
         self.ptrs = (ctypes.c_void_p * world)(*ptrs)
