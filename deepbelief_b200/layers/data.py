@@ -177,7 +177,8 @@ class Data:
         """The datapoints of next_batch() without the intermediate copy: a zero-copy view when the sorted
         rows are contiguous, otherwise gathered by the native multi-threaded row gather
         (db_host_gather_rows) into `out` (a [batch_size, datapoint_size] array, normally the feeder's pinned staging
-        buffer: float32, or uint8 with as_bytes, which reads the binary_bytes() copy). Returns the array that holds the batch."""
+        buffer: float32, or uint8 with as_bytes, which reads the binary_bytes() copy; or a callable returning that array,
+        called only when a gather is needed). Returns the array that holds the batch."""
         rows, wrapped = self._cursor.advance()
         rows = self._local(rows)
         if wrapped and self.log_epochs:
@@ -186,6 +187,8 @@ class Data:
         assert src is not None, 'as_bytes needs a {0,1} data set'
         if len(rows) and int(rows[-1]) - int(rows[0]) + 1 == len(rows):
             return src[int(rows[0]):int(rows[-1]) + 1]
+        if callable(out):
+            out = out()
         if (src.dtype != out.dtype or src.dtype not in (np.float32, np.uint8) or not src.flags['C_CONTIGUOUS'] or
                 not out.flags['C_CONTIGUOUS']):
             np.take(src, rows, axis=0, out=out)

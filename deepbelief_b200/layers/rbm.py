@@ -13,6 +13,8 @@ Randomness: a counter-based Philox stream per layer (`seed`), or injected draws 
 `draw=` arguments (parity tests).
 """
 import os
+import sys
+import time
 import pickle
 
 import numpy as np
@@ -42,6 +44,7 @@ def default_stream(name):
 # page-locked staging and device batch buffers are kept across train() calls: cudaHostAlloc of a
 # 256 MB buffer costs ~100 ms, far more than a CD step
 _BUFFER_POOL = {}
+_COPY_STREAMS = {}
 
 
 def _pooled_buffers(device, shape, dtype=torch.float32):
@@ -52,7 +55,9 @@ def _pooled_buffers(device, shape, dtype=torch.float32):
             _BUFFER_POOL.clear()
         bufs = _BUFFER_POOL[key] = {
             'stage': [torch.empty(shape, dtype=dtype).pin_memory() for _ in range(2)],
-            'dev': [torch.empty(shape, dtype=dtype, device=device) for _ in range(2)]}
+            'dev': [torch.empty(shape, dtype=dtype, device=device) for _ in range(2)],
+            # recorded after every copy OUT of a staging buffer, by whichever feeder made it: the next writer waits on it
+            'stage_free': [torch.cuda.Event() for _ in range(2)]}
     return bufs
 
 
@@ -73,7 +78,9 @@ class BatchFeeder:
         self.as_bytes = bool(allow_bytes and hasattr(data, 'binary_bytes') and hasattr(data, 'next_batch_into') and
                              data.binary_bytes() is not None)
         self.dtype = torch.uint8 if self.as_bytes else torch.float32
-        self.copy_stream = torch.cuda.Stream(device=device)
+        self.copy_stream = _COPY_STREAMS.get(str(device))          # one side stream per device, kept across train() calls
+        if self.copy_stream is None:
+            self.copy_stream = _COPY_STREAMS[str(device)] = torch.cuda.Stream(device=device)
         # pooled device buffers may still be read by work a previous trainer enqueued on the compute stream
         self.copy_stream.wait_stream(torch.cuda.current_stream())
         self.dev = [None, None]
@@ -86,11 +93,13 @@ class BatchFeeder:
         self.prefetch()
 
     def _staging(self, s, shape):
-        if self.stage[s] is None or tuple(self.stage[s].shape) != tuple(shape):
-            self.stage[s] = _pooled_buffers(self.device, shape, self.dtype)['stage'][s]
-            torch.cuda.current_stream().synchronize()   # a previous feeder may still be copying out of it
-        else:
-            self.ready[s].synchronize()            # the last copy out of this staging buffer has finished
+        """Pinned staging buffer of slot s, safe to overwrite: the last host->device copy out of it (this feeder's or a
+        previous one's) has finished. Only called when a batch really has to be assembled on the host — a full-stream
+        synchronise here (as the first version did) stalled the launch queue for one step at the start of every train()."""
+        pooled = _pooled_buffers(self.device, shape, self.dtype)
+        self.stage[s] = pooled['stage'][s]
+        self._stage_free = pooled['stage_free']
+        pooled['stage_free'][s].synchronize()
         return self.stage[s]
 
     def prefetch(self):
@@ -98,11 +107,15 @@ class BatchFeeder:
             return
         self.left -= 1
         s = self.slot
+        used_stage = [False]
+
+        def staging_array():                       # evaluated by Data only when the rows are not one contiguous block
+            used_stage[0] = True
+            return self._staging(s, self.data.batch_shape()).numpy()
         if self.as_bytes:
-            host = self.data.next_batch_into(self._staging(s, self.data.batch_shape()).numpy(), as_bytes=True)
+            host = self.data.next_batch_into(staging_array, as_bytes=True)
         elif hasattr(self.data, 'next_batch_into'):
-            shape = self.data.batch_shape()
-            host = self.data.next_batch_into(self._staging(s, shape).numpy())
+            host = self.data.next_batch_into(staging_array)
         else:
             host = self.data.next_batch()
             if isinstance(host, tuple):            # (datapoints, labels): the trainers use the datapoints only
@@ -120,11 +133,14 @@ class BatchFeeder:
             stage = self._staging(s, src.shape)
             stage.copy_(src)
             src = stage
+            used_stage[0] = True
         if self.released[s] is not None:
             self.copy_stream.wait_event(self.released[s])     # the step that read dev[s] has finished
         with torch.cuda.stream(self.copy_stream):
             self.dev[s].copy_(src, non_blocking=True)
             self.ready[s].record(self.copy_stream)
+            if used_stage[0]:
+                self._stage_free[s].record(self.copy_stream)
         self.h2d_bytes += src.numel() * src.element_size()
 
     def next(self):
@@ -755,9 +771,12 @@ class RBM(layer.Layer):
         exchange of a multi-rank tensor-core step, the dW part of `grad` holds the summed gradient for THIS rank's rows of W
         only; db | dc are complete on every rank.)"""
         rank, world = _dist_info()
+        _tt = [time.perf_counter()] if os.environ.get('DEEPBELIEF_B200_TRAIN_TIMING') else None
         opt_state = self.new_optimizer_state(optimizer)
         if world > 1:
             self.sync_replicas(training_data)
+        if _tt is not None:
+            _tt.append(time.perf_counter())
         n_local = training_data.batch_shape()[0]
         n_global = n_local * world
         for lay in self.layers:                          # G-invariant draws (SURVEY §8e): the lower layers re-sampled by
@@ -789,6 +808,8 @@ class RBM(layer.Layer):
         bytes_ok = self.bottom is None and not pcd and not use_graph and self._tc_eligible(n_local, num_gibbs_steps)
         feeder = BatchFeeder(training_data, self.device, max(0, max_iter - start_iter), allow_bytes=bytes_ok)
         self.last_feeder = feeder
+        if _tt is not None:
+            _tt.append(time.perf_counter())
         for self.iter in range(start_iter, max_iter):
             batch = feeder.next()
             if use_graph and graph_step is None:
@@ -804,9 +825,15 @@ class RBM(layer.Layer):
                 v0 = self.bottom.upprop(batch) if self.bottom else batch
                 self.cd_update(v0, num_gibbs_steps, optimizer, opt_state, grad, n_global=n_global, lr=lr_now,
                                persistent=persistent)
+            if _tt is not None and len(_tt) < 40:
+                _tt.append(time.perf_counter())
             feeder.prefetch()              # host gather + H2D of the next batch overlap this step's kernels
+            if _tt is not None and len(_tt) < 40:
+                _tt.append(time.perf_counter())
             if step_callback is not None:
                 step_callback(self.iter, grad)
+            if _tt is not None and len(_tt) < 40:
+                _tt.append(time.perf_counter())
             if lr_interval and lr_drop and self.iter % lr_interval == 0:
                 self.lr *= lr_drop                         # rbm.py:672-673, 703-704: only layer.lr changes
             if eval_interval and self.iter % eval_interval == 0:
@@ -814,6 +841,10 @@ class RBM(layer.Layer):
             if ckpt_dir and ckpt_interval and self.iter % ckpt_interval == 0:
                 self.checkpoint_iter += ckpt_interval      # rbm.py:676, 709-711
                 self.save(self.iter, ckpt_dir)
+        if _tt is not None and rank == 0:                  # host-side phase times of this call (diagnostics)
+            d = [1e3 * (b - a) for a, b in zip(_tt[:-1], _tt[1:])]
+            sys.stderr.write('train() host ms: state+sync %.2f, setup+feeder %.2f, per step [update, prefetch, callback]: %s\n'
+                             % (d[0], d[1], ' | '.join('%.2f %.2f %.2f' % tuple(d[i:i + 3]) for i in range(2, len(d) - 2, 3))))
 
     # ---- fine-tuning through propagate() --------------------------------------------------------------------------------
     def _stack_bottom_first(self):
