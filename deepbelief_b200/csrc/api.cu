@@ -1,5 +1,6 @@
 // Context management of the C ABI (include/deepbelief_b200.h). The library is stateless apart from
-// this handle (device id, SM count, last error text); it never owns device memory.
+// this handle (device id, SM count, last error text, and — once the GP chain has run — two auxiliary
+// streams with their fork/join events); it never owns device memory.
 #include "context.h"
 #include <cstring>
 #include <cstdint>
@@ -23,11 +24,17 @@ extern "C" int db_create(db_handle_t* out, int device) {
   c->cc_major = prop.major;
   c->cc_minor = prop.minor;
   c->err[0] = 0;
+  c->side_ready = 0;
   *out = c;
   return DB_OK;
 }
 
 extern "C" int db_destroy(db_handle_t h) {
+  if (h && h->side_ready > 0) {
+    for (int i = 0; i < db_context_s::kSideEvents; ++i) cudaEventDestroy(h->side_events[i]);
+    cudaStreamDestroy(h->side_stream);
+    cudaStreamDestroy(h->side_stream2);
+  }
   delete h;
   return DB_OK;
 }

@@ -375,7 +375,7 @@ bool f16_gemm_supported(int M, int N, int K, const F16Operand& X, int ldx, const
 
 int f16_gemm_launch(db_handle_t h, cudaStream_t st, int M, int N, int K, float alpha, const F16Operand& X, int ldx,
                     const F16Operand& Y, int ldy, float beta, float* C, int ldc, int lower_only, int tri_k, const F16Operand* C16,
-                    int ldc16) {
+                    int ldc16, int max_ctas, int allow_pdl) {
   if (!f16_gemm_supported(M, N, K, X, ldx, Y, ldy)) return -1000;
   if (C == nullptr && (C16 == nullptr || beta != 0.0f)) return -1000;
   CUtensorMap tyh, tyl, txh, txl;
@@ -403,13 +403,15 @@ int f16_gemm_launch(db_handle_t h, cudaStream_t st, int M, int N, int K, float a
   }
   const int tm = (N + BM - 1) / BM, tn = (M + BN - 1) / BN;
   const int tiles = (lower_only && tm == tn) ? tn * (tn + 1) / 2 : tm * tn;
-  const int ctas = tc_ctas(h);
+  int ctas = tc_ctas(h);
+  if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
   const int grid = tiles < ctas ? tiles : ctas;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
   cudaLaunchAttribute attr[1];
+  static const int pdl = [] { const char* e = getenv("DB_F16_PDL"); return (e && e[0] == '0') ? 0 : 1; }();   // diagnostics
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[0].val.programmaticStreamSerializationAllowed = (pdl && allow_pdl) ? 1 : 0;
   cfg.attrs = attr; cfg.numAttrs = 1;
   return (int)cudaLaunchKernelEx(&cfg, f16x3_gemm_kernel, tyh, tyl, txh, txl, p);
 }

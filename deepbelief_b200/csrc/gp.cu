@@ -1380,8 +1380,36 @@ inline bool gp_use_f16(int N, int D) {
   return !off && (N % 8) == 0 && (D % 8) == 0;
 }
 
+// Triangular inverse riding along the factorisation on the handle's two auxiliary streams (3 x fp16 chain only; see
+// run_trinv_f16_side_block below). reserve(blk): SMs the launches of outer block blk leave to those streams.
+struct TrinvOverlap {
+  static constexpr int kMaxBlocks = 44;
+  static constexpr int kMinReserve = 16;
+  cudaStream_t diag, prod;  // lane of the diagonal-block inverses, lane of the block-row products
+  cudaEvent_t* ev;          // [0] fork, [1 + blk] "outer block blk is final", [1 + kMaxBlocks + blk] "Linv_blk is ready", [94] join
+  float* Li; float* U;
+  int mode;                 // 1: the lanes also run under the trailing updates (whose grid is capped), 2: only under the steps
+  int trail_reserve;        // SMs a trailing update leaves free in mode 1
+  int num_sms, N;
+  int pending;              // first slice not issued yet (slices wait while the step launches need every SM)
+  // The step launches of outer block blk want one strip CTA per 64 rows below the diagonal plus about as many in-panel update
+  // CTAs; what is left belongs to the lanes. Below kMinReserve nothing is reserved and the slices are deferred.
+  int reserve(int blk) const {
+    const int strips0 = (N - blk * OB + NB - 1) / NB;
+    const int r = num_sms - 2 * strips0;
+    if (r < kMinReserve) return 0;
+    return r > num_sms - 8 ? num_sms - 8 : r;
+  }
+  cudaEvent_t block_final(int blk) const { return ev[1 + blk]; }
+  cudaEvent_t linv_ready(int blk) const { return ev[1 + kMaxBlocks + blk]; }
+  cudaEvent_t join() const { return ev[94]; }
+};
+static_assert(2 * TrinvOverlap::kMaxBlocks + 1 < 94 && db_context_s::kSideEvents > 94, "event pool layout");
+// issues the slices that can start now; returns true when any was issued (the lanes are then busy beside the next launches)
+bool run_trinv_f16_side_blocks(db_handle_t h, TrinvOverlap& ov, cudaStream_t main, float* L, int blk, const F16Scratch& f);
+
 int run_potrf(db_handle_t h, cudaStream_t st, float* A, int lda, int N, int* info, float* lo_buf = nullptr,
-              const F16Scratch* f16 = nullptr) {
+              const F16Scratch* f16 = nullptr, TrinvOverlap* ov = nullptr) {
   cudaMemsetAsync(info, 0, sizeof(int), st);
   static const bool legacy = [] { const char* e = getenv("DB_POTRF_LEGACY"); return e && e[0] == '1'; }();
   static const bool pdl = [] { const char* e = getenv("DB_POTRF_PDL"); return !(e && e[0] == '0'); }();
@@ -1406,7 +1434,7 @@ int run_potrf(db_handle_t h, cudaStream_t st, float* A, int lda, int N, int* inf
       if (jprev >= 0 && j + NB < b1) {
         int tiles = 0;
         for (int cb = j + NB; cb < b1; cb += NB) tiles += (N - cb + 2 * NB - 1) / (2 * NB);
-        const int free_sms = h->num_sms - strips;
+        const int free_sms = h->num_sms - strips - (ov ? ov->reserve(b0 / OB) : 0);
         updates = tiles;
         const int cap = free_sms > 8 ? free_sms : 8;
         if (updates > cap) updates = cap;
@@ -1457,10 +1485,14 @@ int run_potrf(db_handle_t h, cudaStream_t st, float* A, int lda, int N, int* inf
           // inverse; trailing update as 3 x fp16
           const F16Operand P16 = F16Operand{f16->l_hi, f16->l_lo, f16->scales}.at((size_t)b1 * lda + b0);
           f16_split(h, st, P, rows, b1 - b0, lda, P16, lda);
+          int cap = 0;
+          if (ov && ov->mode == 1) {       // block b0 / OB is final and converted: its part of the inverse starts now
+            if (run_trinv_f16_side_blocks(h, *ov, st, A, b0 / OB, *f16)) cap = h->num_sms - ov->trail_reserve;
+          }
           int rc = -1000;
           if (rows >= 128)       // (the 3xTF32 form kept the SIMT kernel below 512 rows: 71 us for the 392-row tail at N = 5000)
             rc = f16_gemm_launch(h, st, rows, rows, b1 - b0, -1.0f, P16, lda, P16, lda, 1.0f, A + (size_t)b1 * lda + b1, lda,
-                                 /*lower_only=*/1, /*tri_k=*/0);
+                                 /*lower_only=*/1, /*tri_k=*/0, nullptr, 0, cap);
           if (rc != 0 && rc != -1000) return set_err(h, DB_ERR_CUDA, "f16x3 trailing update failed (%d)", rc);
           done = rc == 0;
         }
@@ -1475,6 +1507,9 @@ int run_potrf(db_handle_t h, cudaStream_t st, float* A, int lda, int N, int* inf
         const int t = (rows + TileLarge::BM - 1) / TileLarge::BM;
         syrk_block_kernel<<<dim3(t, t), 256, 0, st>>>(A, lda, N, b1, b1, N, b0, b1);
       }
+    }
+    if (ov && f16 != nullptr && (ov->mode != 1 || b1 >= N)) {     // mode 2, and the last block (no trailing update) in either mode
+      run_trinv_f16_side_blocks(h, *ov, st, A, b0 / OB, *f16);
     }
   }
   return check_launch(h, "potrf_lower");
@@ -1522,10 +1557,10 @@ __global__ void __launch_bounds__(256) trinv_diag_finish_kernel(const float* __r
                                                                 float* __restrict__ U, float* __restrict__ Ulo,
                                                                 __half* __restrict__ li_hi = nullptr, __half* __restrict__ li_lo = nullptr,
                                                                 __half* __restrict__ u_hi = nullptr, __half* __restrict__ u_lo = nullptr,
-                                                                const float* __restrict__ sc16 = nullptr) {
+                                                                const float* __restrict__ sc16 = nullptr, int first_block = 0) {
   __shared__ float tile[32][33];
   const float sc = li_hi != nullptr ? __ldg(sc16) : 0.0f;
-  const int b0 = blockIdx.z * OB;
+  const int b0 = (blockIdx.z + first_block) * OB;
   const int nb = min(OB, N - b0);
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   if (r0 >= nb || c0 >= nb) return;
@@ -1617,6 +1652,105 @@ int run_trinv_tc_f16(db_handle_t h, cudaStream_t st, float* L, int N, float* Li,
     if (rc) return set_err(h, DB_ERR_CUDA, "f16x3 triangular inverse (block column) failed (%d)", rc);
   }
   return check_launch(h, "trinv_tc_f16");
+}
+
+// ---- the same inverse riding along the factorisation (round 2) ------------------------------------------------------
+// Block row j of the scheme above needs L_jj (final after the column-block steps of outer block j) and the converted panels
+// 0..j-1, not the rest of the factorisation, and the Cholesky is a latency chain that leaves most of the GPU idle (SM
+// throughput 15 %). So the inverse is issued on the handle's two auxiliary streams, one slice per outer block, behind an
+// event the factorisation records when that block is final (run_potrf, TrinvOverlap):
+//   diagonal lane, slice j: Linv_jj (64x64 solves + SIMT levels on that block alone), finish (fp16 pairs, U_jj) -> event
+//   product lane,  slice j: U[:P_j, B_j] = -WT_j Linv_jj^T (j >= 1), then WT_{j+1} = U[:P_{j+1},:P_{j+1}] L[B_{j+1},:P_{j+1}]^T
+//                           (the long product of the NEXT block row: all its inputs exist already)
+// so that after the last step only Linv_jj of the last block and one K = 512 product remain. The streams share the SMs by
+// construction, not by priority: the step launches of outer block b leave reserve(b) SMs free (their in-panel update CTAs are
+// capped at one per strip CTA) and the side products run on at most that many CTAs (persistent grid cap) — every kernel
+// involved owns its SM through its shared-memory footprint, so an over-subscribed launch would simply queue behind the other
+// stream and stretch the critical path.
+void run_trinv_f16_side_prologue(db_handle_t h, const TrinvOverlap& ov, cudaStream_t main, int N) {
+  cudaEventRecord(ov.ev[0], main);
+  cudaStreamWaitEvent(ov.diag, ov.ev[0], 0);
+  cudaStreamWaitEvent(ov.prod, ov.ev[0], 0);
+  const int nblk = (N + OB - 1) / OB;
+  cudaMemsetAsync(ov.U, 0, sizeof(float) * (size_t)N * N, ov.diag);
+  for (int j = 0; j < nblk; ++j) {
+    const int b0 = j * OB, nb = std::min(OB, N - b0);
+    cudaMemset2DAsync(ov.Li + (size_t)b0 * N + b0, sizeof(float) * (size_t)N, 0, sizeof(float) * (size_t)nb, nb, ov.diag);
+  }
+}
+
+// slice blk, behind the event of outer block ev_blk >= blk (a deferred slice starts with a later block's event)
+static void run_trinv_f16_side_block(db_handle_t h, const TrinvOverlap& ov, float* L, int blk, int ev_blk, const F16Scratch& f) {
+  const int N = ov.N;
+  const int nblk = (N + OB - 1) / OB;
+  const int b0 = blk * OB, nb = std::min(OB, N - b0);
+  const size_t d = (size_t)b0 * N + b0;
+  {
+    cudaStream_t st = ov.diag;
+    cudaStreamWaitEvent(st, ov.block_final(ev_blk), 0);
+    trinv_diag_kernel<<<(nb + NB - 1) / NB, 64, 0, st>>>(L + d, N, nb, ov.Li + d, N);
+    for (int s = NB; s < OB && s < nb; s *= 2) {
+      const int pairs = (nb + 2 * s - 1) / (2 * s);
+      dim3 grid((s + TileSmall::BN - 1) / TileSmall::BN, (s + TileSmall::BM - 1) / TileSmall::BM, pairs);
+      const int splits = simt_splits((long)grid.x * grid.y * pairs, s, h->num_sms, 32);
+      if (splits > 1) {          // one 512-block is 1-16 tiles per level: split K over a cluster (as run_trinv does at small N)
+        const int tiles_y = (int)grid.y;
+        dim3 g2(grid.x, grid.y * pairs, splits);
+        simt_launch_split(trinv_level_split_kernel<0>, g2, 256, st, (const float*)(L + d), N, nb, s, ov.Li + d, N, ov.U + d, N, tiles_y, splits);
+        simt_launch_split(trinv_level_split_kernel<1>, g2, 256, st, (const float*)(L + d), N, nb, s, ov.Li + d, N, ov.U + d, N, tiles_y, splits);
+      } else {
+        trinv_level_kernel<0, TileSmall><<<grid, 256, 0, st>>>(L + d, N, nb, s, ov.Li + d, N, ov.U + d, N);
+        trinv_level_kernel<1, TileSmall><<<grid, 256, 0, st>>>(L + d, N, nb, s, ov.Li + d, N, ov.U + d, N);
+      }
+    }
+    trinv_diag_finish_kernel<<<dim3(OB / 32, OB / 32, 1), 256, 0, st>>>(ov.Li, N, nullptr, ov.U, nullptr, f.l_hi, f.l_lo, f.u_hi, f.u_lo,
+                                                                         f.scales + 1, blk);
+    cudaEventRecord(ov.linv_ready(blk), st);
+  }
+  cudaStream_t st = ov.prod;
+  cudaStreamWaitEvent(st, ov.linv_ready(blk), 0);       // (behind block_final(ev_blk): the converted panels up to ev_blk exist as well)
+  const F16Operand U16{f.u_hi, f.u_lo, f.scales + 1}, L16{f.l_hi, f.l_lo, f.scales}, Lid16{f.l_hi, f.l_lo, f.scales + 1};
+  const F16Operand WT16{f.wt_hi, f.wt_lo, f.scales + 5};
+  // the launches of outer block ev_blk + 1 run beside these products; after the last block the GPU is theirs
+  const int cap = ev_blk + 1 < nblk ? ov.reserve(ev_blk + 1) : 0;
+  int first = 1;       // the first launch behind the event wait is a plain one (gemm_f16x3.cuh, allow_pdl)
+  if (blk >= 1) {
+    const F16Operand Uout = U16.at(b0);
+    f16_gemm_launch(h, st, b0, nb, nb, -1.0f, WT16, OB, Lid16.at(d), N, 0.0f, ov.U + b0, N, 0, 0, &Uout, N, cap, /*allow_pdl=*/0);
+    first = 0;
+  }
+  if (blk + 1 < nblk) {
+    const int P = b0 + OB, nb1 = std::min(OB, N - P);
+    f16_gemm_launch(h, st, P, nb1, P, 1.0f, U16, N, L16.at((size_t)P * N), N, 0.0f, nullptr, OB, /*lower_only=*/0, /*tri_k=*/2, &WT16, OB, cap,
+                    /*allow_pdl=*/first ? 0 : 1);
+  }
+}
+
+bool run_trinv_f16_side_blocks(db_handle_t h, TrinvOverlap& ov, cudaStream_t main, float* L, int blk, const F16Scratch& f) {
+  const int nblk = (ov.N + OB - 1) / OB;
+  if (blk + 1 < nblk && ov.reserve(blk + 1) == 0) return false;       // no room beside the next block's launches: later
+  cudaEventRecord(ov.block_final(blk), main);
+  for (int j = ov.pending; j <= blk; ++j) run_trinv_f16_side_block(h, ov, L, j, blk, f);
+  ov.pending = blk + 1;
+  return true;
+}
+
+// every diagonal-lane slice is behind an event the product lane has waited for, so joining the product lane joins both
+void run_trinv_f16_side_join(const TrinvOverlap& ov, cudaStream_t main) {
+  cudaEventRecord(ov.join(), ov.prod);
+  cudaStreamWaitEvent(main, ov.join(), 0);
+}
+
+// 0: one stream (as before); 1 / 2: TrinvOverlap::mode. DB_GP_OVERLAP overrides.
+inline int gp_overlap_mode(db_handle_t h, cudaStream_t st, int N) {
+  static const int env = [] { const char* e = getenv("DB_GP_OVERLAP"); return e ? atoi(e) : 1; }();
+  const int nblk = (N + OB - 1) / OB;
+  if (env <= 0 || nblk < 3 || nblk > TrinvOverlap::kMaxBlocks) return 0;
+  return side_lane(h, st) ? env : 0;
+}
+inline TrinvOverlap gp_overlap(db_handle_t h, float* Li, float* U, int mode, int N) {
+  static const int trail = [] { const char* e = getenv("DB_GP_TRAIL_RESERVE"); return e ? atoi(e) : TrinvOverlap::kMinReserve; }();
+  return TrinvOverlap{h->side_stream, h->side_stream2, h->side_events, Li, U, mode, trail, h->num_sms, N, 0};
 }
 
 template <int TRANS>
@@ -2207,7 +2341,21 @@ extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float*
   const bool f16 = tc && gp_use_f16(N, D);
   F16Scratch fs{};
   if (f16) { fs = f16_scratch(w.f16, N, D); f16_gp_bounds(st, w.hyp, N, fs.scales); }
-  if ((rc = run_potrf(h, st, w.K, N, N, info, tc ? w.Li : nullptr, f16 ? &fs : nullptr))) return rc;
+  const int overlap = f16 ? gp_overlap_mode(h, st, N) : 0;
+  TrinvOverlap ov{};
+  if (overlap) {
+    // the triangular inverse and the conversion of Y ride along the factorisation on the auxiliary stream
+    ov = gp_overlap(h, w.Li, w.Tmp, overlap, N);
+    run_trinv_f16_side_prologue(h, ov, st, N);
+    const F16Operand Y16{fs.y_hi, fs.y_lo, fs.scales + 3};
+    transpose_f32(ov.prod, Y, N, D, D, w.B1, N);                                   // B1 = Y^T [D,N]
+    f16_scale_from_absmax(h, ov.prod, Y, N, D, D, fs.bits, fs.scales + 3);
+    f16_split(h, ov.prod, w.B1, D, N, N, Y16, N);
+  }
+  if ((rc = run_potrf(h, st, w.K, N, N, info, tc ? w.Li : nullptr, f16 ? &fs : nullptr, overlap ? &ov : nullptr))) {
+    if (overlap) run_trinv_f16_side_join(ov, st);
+    return rc;
+  }
   if (L_out) cudaMemcpyAsync(L_out, w.K, sizeof(float) * (size_t)N * N, cudaMemcpyDeviceToDevice, st);
   logdet_xsq_kernel<<<1, 1024, 0, st>>>(w.K, N, N, X, N * Q, w.acc);
   if (!tc && (rc = run_trinv(h, st, w.K, N, N, w.Li, w.Tmp))) return rc;
@@ -2217,7 +2365,8 @@ extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float*
     double* frob = reinterpret_cast<double*>(reinterpret_cast<char*>(w.acc) + 64);   // nine fp64 scratch sums behind the accumulators
     cudaMemsetAsync(frob, 0, 9 * sizeof(double), st);
     // Tmp = Linv^T (upper triangular), Ulo = its tf32 remainder (3 x fp16 form: its scaled fp16 pair in the scratch)
-    if (f16) { if ((rc = run_trinv_tc_f16(h, st, w.K, N, w.Li, w.Tmp, fs))) return rc; }
+    if (overlap) run_trinv_f16_side_join(ov, st);
+    else if (f16) { if ((rc = run_trinv_tc_f16(h, st, w.K, N, w.Li, w.Tmp, fs))) return rc; }
     else if ((rc = run_trinv_tc(h, st, w.K, w.Li, N, w.Li, w.Tmp, w.Ulo, w.WT, w.WTlo))) return rc;
     dot_sum_kernel<<<h->num_sms * 8, 256, 0, st>>>(w.Tmp, w.Tmp, nn, frob);       // |Linv|_F^2 = tr K^-1
     int trc;
@@ -2230,9 +2379,11 @@ extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float*
       mirror_lower_kernel<<<dim3(tiles32, tiles32), 256, 0, st>>>(w.Li, nullptr, N);
       kinv_diag_kernel<<<(N + 7) / 8, 256, 0, st>>>(w.Tmp, N, w.Li, nullptr);
       f16_split(h, st, w.Li, N, N, N, K16, N);                                     // |K^-1_ij| <= 1 / s
-      transpose_f32(st, Y, N, D, D, w.B1, N);                                      // B1 = Y^T [D,N]
-      f16_scale_from_absmax(h, st, Y, N, D, D, fs.bits, fs.scales + 3);
-      f16_split(h, st, w.B1, D, N, N, Y16, N);
+      if (!overlap) {
+        transpose_f32(st, Y, N, D, D, w.B1, N);                                    // B1 = Y^T [D,N]
+        f16_scale_from_absmax(h, st, Y, N, D, D, fs.bits, fs.scales + 3);
+        f16_split(h, st, w.B1, D, N, N, Y16, N);
+      }
       trc = f16_gemm_launch(h, st, D, N, N, 1.0f, Y16, N, K16, N, 0.0f, w.B3, N, 0, 0);        // B3 = (K^-1 Y)^T
       if (trc) return set_err(h, DB_ERR_CUDA, "f16x3 K^-1 Y product failed (%d)", trc);
       transpose_f32(st, w.B3, D, N, N, w.Av, D);                                   // Av = A = K^-1 Y [N,D]
@@ -2334,14 +2485,24 @@ extern "C" int db_gpdbn_factor(db_handle_t h, db_stream_t stream, const float* X
   F16Scratch fs{};
   const bool f16 = tc && gp_use_f16(N, 8);
   if (f16) { fs = f16_scratch(w.f16, N, 8); f16_gp_bounds(st, w.hyp, N, fs.scales); }
-  if ((rc = run_potrf(h, st, w.K, N, N, info, tc ? w.Li : nullptr, f16 ? &fs : nullptr))) return rc;      // clears info[0] itself
+  const int overlap = f16 ? gp_overlap_mode(h, st, N) : 0;
+  TrinvOverlap ov{};
+  if (overlap) {
+    ov = gp_overlap(h, w.Li, w.U, overlap, N);
+    run_trinv_f16_side_prologue(h, ov, st, N);
+  }
+  if ((rc = run_potrf(h, st, w.K, N, N, info, tc ? w.Li : nullptr, f16 ? &fs : nullptr, overlap ? &ov : nullptr))) {      // clears info[0] itself
+    if (overlap) run_trinv_f16_side_join(ov, st);
+    return rc;
+  }
   if (L_out) cudaMemcpyAsync(L_out, w.K, sizeof(float) * (size_t)N * N, cudaMemcpyDeviceToDevice, st);
   logdet_xsq_kernel<<<1, 1024, 0, st>>>(w.K, N, N, X, N * Q, w.acc);
   if (tc) {
     // Linv^T and K^-1 = Linv^T Linv on the tensor cores, diagonal of K^-1 in exact fp32 (it carries pred_var)
     const int tiles32 = (N + 31) / 32;
     if (f16) {
-      if ((rc = run_trinv_tc_f16(h, st, w.K, N, w.Li, w.U, fs))) return rc;
+      if (overlap) run_trinv_f16_side_join(ov, st);
+      else if ((rc = run_trinv_tc_f16(h, st, w.K, N, w.Li, w.U, fs))) return rc;
       const F16Operand U16{fs.u_hi, fs.u_lo, fs.scales + 1};
       const int trc = f16_gemm_launch(h, st, N, N, N, 1.0f, U16, N, U16, N, 0.0f, w.Kinv, N, 1, 1);
       if (trc) return set_err(h, DB_ERR_CUDA, "f16x3 K^-1 product failed (%d)", trc);
