@@ -1746,6 +1746,14 @@ inline int gp_overlap_mode(db_handle_t h, cudaStream_t st, int N) {
   static const int env = [] { const char* e = getenv("DB_GP_OVERLAP"); return e ? atoi(e) : 1; }();
   const int nblk = (N + OB - 1) / OB;
   if (env <= 0 || nblk < 3 || nblk > TrinvOverlap::kMaxBlocks) return 0;
+  // The lanes open with the first outer block whose step launches leave SMs free (TrinvOverlap::reserve). When that is late
+  // in the factorisation (N = 8192: block 8 of 16) most of the inverse is still ahead when the Cholesky ends, the slices issued
+  // until then run on the few SMs reserved at their issue time, and the evaluation is slower than on one stream (measured
+  // 6.84 against 6.59 ms; N = 6144: 3.43 against 3.86 ms): one stream then.
+  TrinvOverlap probe{}; probe.num_sms = h->num_sms; probe.N = N;
+  int first = 1;
+  while (first < nblk && probe.reserve(first) == 0) ++first;
+  if (first - 1 > nblk / 3) return 0;
   return side_lane(h, st) ? env : 0;
 }
 inline TrinvOverlap gp_overlap(db_handle_t h, float* Li, float* U, int mode, int N) {
@@ -1844,6 +1852,37 @@ __global__ void __launch_bounds__(256) mirror_lower_kernel(float* __restrict__ A
     }
   }
 }
+// The same mirror for the 3 x fp16 chain: the full symmetric matrix is also written as the scaled fp16 pair the next product
+// reads (a separate conversion pass over the mirrored matrix cost 31 us at N = 5000). The diagonal must be final already.
+__global__ void __launch_bounds__(256) mirror_lower_split_kernel(float* __restrict__ A, int N, __half* __restrict__ hi,
+                                                                 __half* __restrict__ lo, const float* __restrict__ scale) {
+  __shared__ float tile[32][33];
+  if (blockIdx.x > blockIdx.y) return;
+  const float sc = __ldg(scale);
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + 8 * i, c = c0 + tx;
+    float v = 0.0f;
+    if (r < N && c < N) {
+      v = A[(size_t)r * N + c];
+      if (c <= r) { __half hh, ll; split_f16(v * sc, hh, ll); hi[(size_t)r * N + c] = hh; lo[(size_t)r * N + c] = ll; }
+    }
+    tile[ty + 8 * i][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, r = r0 + tx;           // writes element (c, r) = (r, c)^T
+    if (c < N && r < N && c < r) {
+      const float v = tile[tx][ty + 8 * i];
+      A[(size_t)c * N + r] = v;
+      __half hh, ll; split_f16(v * sc, hh, ll);
+      hi[(size_t)c * N + r] = hh; lo[(size_t)c * N + r] = ll;
+    }
+  }
+}
 // tr G = 0.5 (D |Linv|_F^2 - |A|_F^2) from two fp32 round-to-nearest reductions (scratch[0], scratch[1]) replaces the
 // trace summed from the tensor-core tiles: sums of squares are monotone, so the truncating accumulator biases them
 // one way (~3e-6), and tr G cancels ~50x. The diagonal also enters sum G o Kf (Kf_ii = alpha).
@@ -1879,16 +1918,25 @@ __global__ void gp_fix_trace_kernel(GpAccum* acc, const double* __restrict__ scr
 __global__ void gp_store_ssq_kernel(GpAccum* acc, const double* __restrict__ scratch) { acc->ssq = (float)scratch[2]; }
 // Kinv[i,i] = sum_k LinvT[i,k]^2 in fp32 round-to-nearest (one warp per row): the tensor-core value of this monotone
 // sum is biased low by the truncating accumulator, and A = K^-1 Y inherits a diagonal bias one-to-one.
-__global__ void kinv_diag_kernel(const float* __restrict__ LinvT, int N, float* __restrict__ Kinv, float* __restrict__ Kinv_lo) {
+// trace (optional): tr K^-1 = |Linv|_F^2 = the sum of these diagonal entries, accumulated in fp64 (per-lane fp32 partials of
+// at most N / 32 terms, as in dot_sum_kernel) — a separate pass over the N x N factor cost 35 us at N = 5000.
+__global__ void kinv_diag_kernel(const float* __restrict__ LinvT, int N, float* __restrict__ Kinv, float* __restrict__ Kinv_lo,
+                                 double* __restrict__ trace = nullptr) {
   const int i = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
   if (i >= N) return;
   const float* row = LinvT + (size_t)i * N;
   float s = 0.0f;
   for (int k = i + lane; k < N; k += 32) { const float v = __ldg(row + k); s = fmaf(v, v, s); }
+  double sd = (double)s;
   s = warp_sum(s);
+  if (trace != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
+  }
   if (lane == 0) {
     Kinv[(size_t)i * N + i] = s;
     if (Kinv_lo) Kinv_lo[(size_t)i * N + i] = s - __uint_as_float(__float_as_uint(s) & 0xffffe000u);
+    if (trace != nullptr) atomicAdd(trace, sd);
   }
 }
 // sum_i a[i] * b[i] into a DOUBLE accumulator: ~10^4 warp partials added with fp32 atomics random-walk to ~3e-6 relative,
@@ -2368,7 +2416,6 @@ extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float*
     if (overlap) run_trinv_f16_side_join(ov, st);
     else if (f16) { if ((rc = run_trinv_tc_f16(h, st, w.K, N, w.Li, w.Tmp, fs))) return rc; }
     else if ((rc = run_trinv_tc(h, st, w.K, w.Li, N, w.Li, w.Tmp, w.Ulo, w.WT, w.WTlo))) return rc;
-    dot_sum_kernel<<<h->num_sms * 8, 256, 0, st>>>(w.Tmp, w.Tmp, nn, frob);       // |Linv|_F^2 = tr K^-1
     int trc;
     if (f16) {
       // the three big products as 3 x fp16 (gemm_f16x3.cu): operands converted once into scaled fp16 pairs
@@ -2376,9 +2423,8 @@ extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float*
       F16Operand Y16{fs.y_hi, fs.y_lo, fs.scales + 3}, A16{fs.a_hi, fs.a_lo, fs.scales + 4};
       trc = f16_gemm_launch(h, st, N, N, N, 1.0f, U16, N, U16, N, 0.0f, w.Li, N, 1, 1);        // Li = K^-1 (lower)
       if (trc) return set_err(h, DB_ERR_CUDA, "f16x3 K^-1 product failed (%d)", trc);
-      mirror_lower_kernel<<<dim3(tiles32, tiles32), 256, 0, st>>>(w.Li, nullptr, N);
-      kinv_diag_kernel<<<(N + 7) / 8, 256, 0, st>>>(w.Tmp, N, w.Li, nullptr);
-      f16_split(h, st, w.Li, N, N, N, K16, N);                                     // |K^-1_ij| <= 1 / s
+      kinv_diag_kernel<<<(N + 7) / 8, 256, 0, st>>>(w.Tmp, N, w.Li, nullptr, frob);     // + |Linv|_F^2 = tr K^-1
+      mirror_lower_split_kernel<<<dim3(tiles32, tiles32), 256, 0, st>>>(w.Li, N, K16.hi, K16.lo, K16.scale);   // |K^-1_ij| <= 1 / s
       if (!overlap) {
         transpose_f32(st, Y, N, D, D, w.B1, N);                                    // B1 = Y^T [D,N]
         f16_scale_from_absmax(h, st, Y, N, D, D, fs.bits, fs.scales + 3);
@@ -2400,7 +2446,7 @@ extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float*
     trc = tf32_gemm_launch(h, st, N, N, N, 1.0f, w.Tmp, w.Ulo, N, w.Tmp, w.Ulo, N, 0.0f, w.Li, N, 1, 1, w.K);
     if (trc) return set_err(h, DB_ERR_CUDA, "tf32 K^-1 product failed (%d)", trc);
     mirror_lower_kernel<<<dim3(tiles32, tiles32), 256, 0, st>>>(w.Li, w.K, N);
-    kinv_diag_kernel<<<(N + 7) / 8, 256, 0, st>>>(w.Tmp, N, w.Li, w.K);
+    kinv_diag_kernel<<<(N + 7) / 8, 256, 0, st>>>(w.Tmp, N, w.Li, w.K, frob);        // + |Linv|_F^2 = tr K^-1
     transpose_f32(st, Y, N, D, D, w.B1, N);                                      // B1 = Y^T [D,N]
     tf32_split_lo(h, st, w.B1, D, N, N, w.B2);
     trc = tf32_gemm_launch(h, st, D, N, N, 1.0f, w.B1, w.B2, N, w.Li, w.K, N, 0.0f, w.B3, N, 0, 0);          // B3 = (K^-1 Y)^T
