@@ -449,7 +449,7 @@ def run_b200(args):
     from deepbelief_b200.layers.gplvm import GPLVM
     Y_host = (gY + 0.0).cpu().numpy()
     X_host = gX.cpu().numpy()
-    gp_e2e_iters = 20
+    gp_e2e_iters = 100          # 1 % of the reference example's run (examples/gplvm_horses/flags.py:35, num_iterations = 10000)
 
     def gplvm_e2e():
         m = GPLVM(Y_host, GP_Q, X0=X_host, name='bench_gplvm', device=dev)

@@ -2019,6 +2019,122 @@ __global__ void __launch_bounds__(256) gp_contract_mem_kernel(const float* __res
   gp_contract_tile<T>(gacc, m0, n0, diag_tile, X, N, Q, hyp, dXacc, accum, rowacc, colacc, red);
 }
 
+// The tensor-core chain's contraction for Q <= 2 (every example) in ONE pass over the tile: gp_contract_mem_kernel first walks
+// its 8 x 8 entries per thread for the calibration sums (K_f evaluated per entry with run-time-Q loads of X) and then again
+// inside gp_contract_tile (K_f a second time) — 170 us at N = 5000 with issue slots 27 % busy and DRAM at 7 %. Here the rows'
+// and columns' latents sit in registers, every entry costs two loads and one exponential, and the calibration sums ride along.
+template <class T>
+__global__ void __launch_bounds__(256) gp_contract_fused_kernel(const float* __restrict__ Kinv, const float* __restrict__ AA, int N, int Q,
+                                                                int D, const float* __restrict__ X, const float* __restrict__ hyp,
+                                                                float* __restrict__ dXacc, GpAccum* accum, double* __restrict__ cal) {
+  if (blockIdx.x > blockIdx.y) return;
+  __shared__ float rowacc[T::BM][2];
+  __shared__ float colacc[T::BN][2];
+  __shared__ float red[3][8];
+  static_assert(T::BM == T::BN, "square tiles");
+  const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
+  const bool diag_tile = blockIdx.x == blockIdx.y;
+  for (int t = threadIdx.x; t < T::BM * 2; t += 256) { (&rowacc[0][0])[t] = 0.0f; (&colacc[0][0])[t] = 0.0f; }
+  const float half_d = 0.5f * (float)D;
+  const float alpha = __ldg(hyp), inv_g2 = 1.0f / (__ldg(hyp + 1) * __ldg(hyp + 1));
+  float cK = 0.0f, cKr = 0.0f, cA = 0.0f, cAr = 0.0f, cF = 0.0f, cFr = 0.0f;   // strictly-lower contractions (see gp_fix_trace_kernel)
+  float trg = 0.0f, sw = 0.0f, swr = 0.0f;
+  float racc[T::TM][2], cacc[T::TN][2], xn[T::TN][2];
+#pragma unroll
+  for (int i = 0; i < T::TM; ++i) { racc[i][0] = racc[i][1] = 0.0f; }
+#pragma unroll
+  for (int jj = 0; jj < T::TN; ++jj) {
+    cacc[jj][0] = cacc[jj][1] = 0.0f;
+    const int n = simt_col<T>(n0, jj);
+    xn[jj][0] = n < N ? __ldg(X + (size_t)n * Q) : 0.0f;
+    xn[jj][1] = (n < N && Q > 1) ? __ldg(X + (size_t)n * Q + 1) : 0.0f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < T::TM; ++i) {
+    const int m = simt_row<T>(m0, i);
+    if (m >= N) continue;
+    const float xm0 = __ldg(X + (size_t)m * Q);
+    const float xm1 = Q > 1 ? __ldg(X + (size_t)m * Q + 1) : 0.0f;
+    float aa[T::TN], kv[T::TN];
+    static_assert(T::TN % 4 == 0, "a thread's columns come in aligned groups of four");
+#pragma unroll
+    for (int g4 = 0; g4 < T::TN / 4; ++g4) {                // the row's loads first, 16 bytes each (N % 4 == 0 on this path)
+      const int n = simt_col<T>(n0, 4 * g4);
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), k = a;
+      if (n < N && n <= m) {
+        a = __ldg(reinterpret_cast<const float4*>(AA + (size_t)m * N + n));
+        k = __ldg(reinterpret_cast<const float4*>(Kinv + (size_t)m * N + n));
+      }
+      aa[4 * g4] = a.x; aa[4 * g4 + 1] = a.y; aa[4 * g4 + 2] = a.z; aa[4 * g4 + 3] = a.w;
+      kv[4 * g4] = k.x; kv[4 * g4 + 1] = k.y; kv[4 * g4 + 2] = k.z; kv[4 * g4 + 3] = k.w;
+    }
+#pragma unroll
+    for (int jj = 0; jj < T::TN; ++jj) {
+      const int n = simt_col<T>(n0, jj);
+      if (n >= N || n > m) continue;
+      const float g = fmaf(half_d, kv[jj], aa[jj]);
+      if (m == n) { trg += g; sw += g * alpha; continue; }   // Kf_ii = alpha, r = 0: no dX contribution
+      const float d0 = xm0 - xn[jj][0], d1 = xm1 - xn[jj][1];
+      const float r2 = fmaf(d0, d0, d1 * d1);
+      const float kf = alpha * __expf(-0.5f * r2 * inv_g2);
+      const float kfr = kf * r2;
+      cK = fmaf(kv[jj], kf, cK); cKr = fmaf(kv[jj], kfr, cKr); cA = fmaf(aa[jj], kf, cA); cAr = fmaf(aa[jj], kfr, cAr);
+      cF += kf; cFr += kfr;
+      const float w = g * kf;
+      sw += 2.0f * w; swr += 2.0f * w * r2;                  // (i,j) and (j,i)
+      racc[i][0] = fmaf(w, d0, racc[i][0]); racc[i][1] = fmaf(w, d1, racc[i][1]);
+      cacc[jj][0] = fmaf(-w, d0, cacc[jj][0]); cacc[jj][1] = fmaf(-w, d1, cacc[jj][1]);
+    }
+  }
+  (void)diag_tile;
+  {     // per-thread fp32 partials (<= TM*TN terms), everything across threads in fp64
+    double v[6] = {2.0 * (double)cK, 2.0 * (double)cKr, 2.0 * (double)cA, 2.0 * (double)cAr, 2.0 * (double)cF, 2.0 * (double)cFr};
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v[e] += __shfl_xor_sync(0xffffffffu, v[e], o);
+      if ((threadIdx.x & 31) == 0) atomicAdd(cal + e, v[e]);
+    }
+  }
+  const int tx = threadIdx.x % (T::BN / T::TN), lane = threadIdx.x & 31;
+  static_assert(T::BN / T::TN == 16, "row reduction assumes 16 threads per tile row");
+#pragma unroll
+  for (int i = 0; i < T::TM; ++i) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float v = racc[i][q];
+      v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8);
+      if (tx == 0) rowacc[simt_row<T>(0, i)][q] = v;        // rows are owned by one 16-thread group
+    }
+  }
+#pragma unroll
+  for (int jj = 0; jj < T::TN; ++jj) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float v = cacc[jj][q];
+      v += __shfl_xor_sync(0xffffffffu, v, 16);             // the two tile rows held by this warp
+      if (lane < 16) atomicAdd(&colacc[simt_col<T>(0, jj)][q], v);
+    }
+  }
+  __syncthreads();
+  const float sc = -2.0f * inv_g2;
+  for (int t = threadIdx.x; t < T::BM * Q; t += 256) {
+    const int r = t / Q, q = t % Q;
+    if (m0 + r < N) atomicAdd(dXacc + (size_t)(m0 + r) * Q + q, sc * rowacc[r][q]);
+    if (n0 + r < N) atomicAdd(dXacc + (size_t)(n0 + r) * Q + q, sc * colacc[r][q]);
+  }
+  trg = warp_sum(trg); sw = warp_sum(sw); swr = warp_sum(swr);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = trg; red[1][threadIdx.x >> 5] = sw; red[2][threadIdx.x >> 5] = swr; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f, c = 0.f;
+    for (int w = 0; w < 8; ++w) { a += red[0][w]; b += red[1][w]; c += red[2][w]; }
+    atomicAdd(&accum->trG, a); atomicAdd(&accum->sumW, b); atomicAdd(&accum->sumWr2, c);
+  }
+}
+
 // ---- GPDBN top layer (gprbm.py), training mode x_ph = X ------------------------------------------------
 // With K_Xx = K_f = K - s I (s = noise variance) the reference's quantities collapse to (after GP14):
 //   pred_var = s - s^2 diag(K^-1)        (gprbm.py:208-218)
@@ -2463,7 +2579,8 @@ extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float*
     if (want_grad) {
       cudaMemsetAsync(w.dXacc, 0, sizeof(float) * (size_t)N * Q, st);
       const int tiles = (N + TileLarge::BM - 1) / TileLarge::BM;
-      gp_contract_mem_kernel<TileLarge><<<dim3(tiles, tiles), 256, 0, st>>>(w.Li, w.Tmp, N, Q, D, X, w.hyp, w.dXacc, w.acc, frob + 3);
+      if (Q <= 2 && (N % 4) == 0) gp_contract_fused_kernel<TileLarge><<<dim3(tiles, tiles), 256, 0, st>>>(w.Li, w.Tmp, N, Q, D, X, w.hyp, w.dXacc, w.acc, frob + 3);
+      else gp_contract_mem_kernel<TileLarge><<<dim3(tiles, tiles), 256, 0, st>>>(w.Li, w.Tmp, N, Q, D, X, w.hyp, w.dXacc, w.acc, frob + 3);
       dot_sum_kernel<<<h->num_sms * 8, 256, 0, st>>>(w.Av, w.Av, nd, frob + 1);   // |A|_F^2
       static const int dbg = [] { const char* e = getenv("DB_GP_DEBUG"); return (e && e[0] == '1') ? 1 : 0; }();
       gp_fix_trace_kernel<<<1, 1, 0, st>>>(w.acc, frob, w.hyp, N, D, dbg);
