@@ -323,8 +323,8 @@ __device__ __forceinline__ float scale_for_bound(float b) {
   if (f == 0.5f) --q;                               // exact power of two: b = 2^(q-1)
   return ldexpf(1.0f, max(-100, min(100, 14 - q)));
 }
-__global__ void f16_scale_from_bits_kernel(const unsigned int* __restrict__ bits, float* __restrict__ scale) {
-  *scale = scale_for_bound(__uint_as_float(*bits));
+__global__ void f16_scale_from_bits_kernel(const unsigned int* __restrict__ bits, float* __restrict__ scale, const float* __restrict__ mul) {
+  *scale = scale_for_bound(__uint_as_float(*bits) * (mul != nullptr ? fabsf(*mul) : 1.0f));
 }
 // scales[0] L panels, [1] L^-1 / U, [2] K^-1 from the effective hyper-parameters (alpha, gamma, s)
 __global__ void f16_gp_bounds_kernel(const float* __restrict__ hyp, int N, float* __restrict__ scales) {
@@ -422,11 +422,11 @@ void f16_split(db_handle_t h, cudaStream_t st, const float* x, size_t rows, size
   f16_split_kernel<<<ew_blocks(rows * cols / (vec ? 4 : 1), h->num_sms), 256, 0, st>>>(x, rows, cols, ld, out.scale, out.hi, out.lo, ld16, vec);
 }
 void f16_scale_from_absmax(db_handle_t h, cudaStream_t st, const float* x, size_t rows, size_t cols, size_t ld, unsigned int* bits_scratch,
-                           float* scale_out) {
+                           float* scale_out, const float* bound_mul) {
   cudaMemsetAsync(bits_scratch, 0, sizeof(unsigned int), st);
   const int vec = (cols % 4 == 0) && (ld % 4 == 0) && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
   f16_absmax_kernel<<<ew_blocks(rows * cols / (vec ? 4 : 1), h->num_sms), 256, 0, st>>>(x, rows, cols, ld, bits_scratch, vec);
-  f16_scale_from_bits_kernel<<<1, 1, 0, st>>>(bits_scratch, scale_out);
+  f16_scale_from_bits_kernel<<<1, 1, 0, st>>>(bits_scratch, scale_out, bound_mul);
 }
 void f16_gp_bounds(cudaStream_t st, const float* hyp, int N, float* scales) { f16_gp_bounds_kernel<<<1, 1, 0, st>>>(hyp, N, scales); }
 

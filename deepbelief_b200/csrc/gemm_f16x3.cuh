@@ -25,9 +25,10 @@ int f16_gemm_launch(db_handle_t h, cudaStream_t st, int M, int N, int K, float a
 bool f16_gemm_supported(int M, int N, int K, const F16Operand& X, int ldx, const F16Operand& Y, int ldy);
 // out = split(x * (*out.scale)) over a [rows, cols] block (x: leading dimension ld, out: ld16)
 void f16_split(db_handle_t h, cudaStream_t st, const float* x, size_t rows, size_t cols, size_t ld, const F16Operand& out, size_t ld16);
-// *scale_out = 2^(14 - ceil(log2 max|x|)) (bits_scratch: one device word)
+// *scale_out = 2^(14 - ceil(log2 (max|x| * m))) (bits_scratch: one device word; m = |*bound_mul| on the device, 1 when null: the
+// scale of a matrix that is bounded by max|x| times a device scalar)
 void f16_scale_from_absmax(db_handle_t h, cudaStream_t st, const float* x, size_t rows, size_t cols, size_t ld, unsigned int* bits_scratch,
-                           float* scale_out);
+                           float* scale_out, const float* bound_mul = nullptr);
 // a-priori scales from the effective hyper-parameters: [0] Cholesky panels, [1] L^-1 (U), [2] K^-1, [5] L_21 L_11^-1 products
 void f16_gp_bounds(cudaStream_t st, const float* hyp, int N, float* scales);
 

@@ -2357,6 +2357,23 @@ __global__ void __launch_bounds__(256) kinv_scale_cols_kernel(const float4* __re
                            v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u), v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
   }
 }
+// 3 x fp16 form: Xs directly as the scaled fp16 pair the product reads (|Xs_ij| <= s^2 max|g_pv| / s: *scale from that bound)
+__global__ void __launch_bounds__(256) kinv_scale_cols_f16_kernel(const float4* __restrict__ Kinv, const float* __restrict__ gpv, int N,
+                                                                  const float* __restrict__ hyp, const float* __restrict__ scale,
+                                                                  __half* __restrict__ hi, __half* __restrict__ lo) {
+  const float f = __ldg(hyp + 2) * __ldg(hyp + 2) * __ldg(scale);
+  const size_t n4 = (size_t)N * N / 4, row4 = (size_t)N / 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % row4) * 4;
+    const float4 k = __ldg(Kinv + i);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gpv + c));
+    __half h0, l0, h1, l1, h2, l2, h3, l3;
+    split_f16(f * g.x * k.x, h0, l0); split_f16(f * g.y * k.y, h1, l1); split_f16(f * g.z * k.z, h2, l2); split_f16(f * g.w * k.w, h3, l3);
+    __half2 ha = __halves2half2(h0, h1), hb = __halves2half2(h2, h3), la = __halves2half2(l0, l1), lb = __halves2half2(l2, l3);
+    *reinterpret_cast<uint2*>(hi + 4 * i) = make_uint2(*reinterpret_cast<uint32_t*>(&ha), *reinterpret_cast<uint32_t*>(&hb));
+    *reinterpret_cast<uint2*>(lo + 4 * i) = make_uint2(*reinterpret_cast<uint32_t*>(&la), *reinterpret_cast<uint32_t*>(&lb));
+  }
+}
 __global__ void __launch_bounds__(256) gpdbn_grad_mem_kernel(const float* __restrict__ G1, const float* __restrict__ Kinv,
                                                              const float* __restrict__ P, const float* __restrict__ B,
                                                              const float* __restrict__ X, int N, int Q, int D,
@@ -2669,9 +2686,9 @@ extern "C" int db_gpdbn_factor(db_handle_t h, db_stream_t stream, const float* X
       const F16Operand U16{fs.u_hi, fs.u_lo, fs.scales + 1};
       const int trc = f16_gemm_launch(h, st, N, N, N, 1.0f, U16, N, U16, N, 0.0f, w.Kinv, N, 1, 1);
       if (trc) return set_err(h, DB_ERR_CUDA, "f16x3 K^-1 product failed (%d)", trc);
-      mirror_lower_kernel<<<dim3(tiles32, tiles32), 256, 0, st>>>(w.Kinv, nullptr, N);
       kinv_diag_kernel<<<(N + 7) / 8, 256, 0, st>>>(w.U, N, w.Kinv, nullptr);
-      tf32_split_lo(h, st, w.Kinv, N, N, N, w.K);     // the backward GEMM (db_gpdbn_backward_x, 3xTF32) reads the remainder of K^-1
+      // mirrored, and again as the fp16 pair the backward product (db_gpdbn_backward_x, 3 x fp16) reads
+      mirror_lower_split_kernel<<<dim3(tiles32, tiles32), 256, 0, st>>>(w.Kinv, N, fs.k_hi, fs.k_lo, fs.scales + 2);
     } else {
     if ((rc = run_trinv_tc(h, st, w.K, w.Li, N, w.Li, w.U, w.Ulo, w.WT, w.WTlo))) return rc;
     // the K buffer (L is dead) keeps the tf32 remainder of K^-1 for the backward GEMM (db_gpdbn_backward_x)
@@ -2732,7 +2749,22 @@ extern "C" int db_gpdbn_backward_x(db_handle_t h, db_stream_t stream, const floa
   gpdbn_gpv_scalar_kernel<<<(N + 255) / 256 > 64 ? 64 : (N + 255) / 256, 256, 0, st>>>(g_pv, w.Kinv, N, w.hyp, w.acc);
   const int tiles = (N + TileLarge::BM - 1) / TileLarge::BM;
   bool done = false;
-  if (gp_use_tensor_path(h, N, 32) && gpdbn_tensor_factor() && (reinterpret_cast<uintptr_t>(g_pv) & 15) == 0) {
+  if (gp_use_tensor_path(h, N, 32) && gpdbn_tensor_factor() && gp_use_f16(N, 8) && (reinterpret_cast<uintptr_t>(g_pv) & 15) == 0) {
+    // same decision as db_gpdbn_factor: the scratch holds K^-1 as a scaled fp16 pair (scale [2]); Xs goes where U was (dead
+    // since the K^-1 product), scale [6] from its bound s max|g_pv|. 688 us as 3xTF32 at N = 5000.
+    const F16Scratch fs = f16_scratch(w.f16, N, 8);
+    const F16Operand K16{fs.k_hi, fs.k_lo, fs.scales + 2}, Xs16{fs.u_hi, fs.u_lo, fs.scales + 6};
+    f16_scale_from_absmax(h, st, g_pv, 1, N, N, fs.bits + 2, fs.scales + 6, w.hyp + 2);
+    kinv_scale_cols_f16_kernel<<<h->num_sms * 8, 256, 0, st>>>(reinterpret_cast<const float4*>(w.Kinv), g_pv, N, w.hyp, fs.scales + 6,
+                                                              fs.u_hi, fs.u_lo);
+    const int trc = f16_gemm_launch(h, st, N, N, N, 1.0f, Xs16, N, K16, N, 0.0f, w.Ulo, N, 1, 0);
+    if (trc != 0 && trc != -1000) return set_err(h, DB_ERR_CUDA, "f16x3 gradient product failed (%d)", trc);
+    if (trc == 0) {
+      gpdbn_grad_mem_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(w.Ulo, w.Kinv, w.P, w.B, X, N, Q, D, w.hyp, w.dXacc, w.acc);
+      done = true;
+    }
+  }
+  if (!done && gp_use_tensor_path(h, N, 32) && gpdbn_tensor_factor() && !gp_use_f16(N, 8) && (reinterpret_cast<uintptr_t>(g_pv) & 15) == 0) {
     // same decision as db_gpdbn_factor: the K buffer holds the remainder of K^-1
     kinv_scale_cols_kernel<<<h->num_sms * 8, 256, 0, st>>>(reinterpret_cast<const float4*>(w.Kinv), g_pv, N, w.hyp,
                                                           reinterpret_cast<float4*>(w.Li), reinterpret_cast<float4*>(w.U));
