@@ -457,15 +457,22 @@ def run_b200(args):
         return float(m.loss_and_grad()[0].item())
 
     gplvm_e2e()                                                       # warm-up (allocator, graph capture path)
-    barrier()
-    t_a = time.perf_counter()
-    e0.record()
-    gp_e2e_loss = gplvm_e2e()
-    e1.record()
-    barrier()
-    t_b = time.perf_counter()
-    windows.append((t_a, t_b))
-    gp_e2e_ms = parallel.max_over_ranks(e0.elapsed_time(e1), device=dev) / (gp_e2e_iters + 1)
+    # three whole runs, the median reported: a run builds and drops a 1.3 GB model, and one cyclic-garbage collection or
+    # allocator round trip landing inside a run (observed once: +200 ms) is not a property of the path
+    import gc
+    gp_e2e_runs = []
+    for _ in range(3):
+        gc.collect()
+        barrier()
+        t_a = time.perf_counter()
+        e0.record()
+        gp_e2e_loss = gplvm_e2e()
+        e1.record()
+        barrier()
+        t_b = time.perf_counter()
+        windows.append((t_a, t_b))
+        gp_e2e_runs.append(parallel.max_over_ranks(e0.elapsed_time(e1), device=dev) / (gp_e2e_iters + 1))
+    gp_e2e_ms = sorted(gp_e2e_runs)[1]
 
     # ---- GPDBN (BASELINE configs[3]): synthetic binary 5000x784, stack 784->200->100->GPRBM(50), Q=2, T=0.1 ----
     gpdbn = None
@@ -576,7 +583,8 @@ def run_b200(args):
                       'e2e': {'value': world * 1e3 / gp_e2e_ms, 'unit': 'evals/s', 'ms_per_eval': gp_e2e_ms,
                               'api': 'GPLVM(Y_host, Q, X0=X_host) + GPLVM.optimize(AdamOptimizer, num_iterations=%d) + loss read-back; '
                                      'the constructor (host->device copy of Y and X0, workspace allocation) is inside the timed region and '
-                                     'amortised over the %d evaluations' % (gp_e2e_iters, gp_e2e_iters + 1),
+                                     'amortised over the %d evaluations; median of 3 such runs' % (gp_e2e_iters, gp_e2e_iters + 1),
+                              'ms_per_eval_runs': gp_e2e_runs,
                               'h2d_bytes_per_eval': (GP_N * GP_D + GP_N * GP_Q) * 4 / (gp_e2e_iters + 1), 'd2h_bytes_per_eval': 4 / (gp_e2e_iters + 1),
                               'final_loss': gp_e2e_loss},
                       'cpu_baseline': gp_cpu,

@@ -1883,6 +1883,43 @@ __global__ void __launch_bounds__(256) mirror_lower_split_kernel(float* __restri
     }
   }
 }
+// A = (K^-1 Y) arrives transposed from the product ([D, N]); this transposition also forms the two reductions that read A
+// next to Y — sum Y o A (dots[1]) and |A|_F^2 (dots[0]) — in fp64 (per-thread fp32 partials of four terms): two separate
+// dot_sum passes over N x D cost 2 x 17.5 us at N = 5000, D = 784.
+__global__ void __launch_bounds__(256) transpose_dots_kernel(const float* __restrict__ in, int R, int C, int ld_in, float* __restrict__ out,
+                                                             int ld_out, const float* __restrict__ Y, double* __restrict__ dots) {
+  __shared__ float tile[32][33];
+  __shared__ double red[2][8];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + 8 * i, c = c0 + tx;
+    tile[ty + 8 * i][tx] = (r < R && c < C) ? __ldg(in + (size_t)r * ld_in + c) : 0.0f;
+  }
+  __syncthreads();
+  float aa = 0.0f, ya = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, r = r0 + tx;
+    if (c < C && r < R) {
+      const float v = tile[tx][ty + 8 * i];
+      out[(size_t)c * ld_out + r] = v;
+      aa = fmaf(v, v, aa);
+      ya = fmaf(v, __ldg(Y + (size_t)c * ld_out + r), ya);
+    }
+  }
+  double a = (double)aa, b = (double)ya;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  if (tx == 0) { red[0][ty] = a; red[1][ty] = b; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+    atomicAdd(dots + threadIdx.x, t);
+  }
+}
 // tr G = 0.5 (D |Linv|_F^2 - |A|_F^2) from two fp32 round-to-nearest reductions (scratch[0], scratch[1]) replaces the
 // trace summed from the tensor-core tiles: sums of squares are monotone, so the truncating accumulator biases them
 // one way (~3e-6), and tr G cancels ~50x. The diagonal also enters sum G o Kf (Kf_ii = alpha).
@@ -1939,31 +1976,10 @@ __global__ void kinv_diag_kernel(const float* __restrict__ LinvT, int N, float* 
     if (trace != nullptr) atomicAdd(trace, sd);
   }
 }
-// sum_i a[i] * b[i] into a DOUBLE accumulator: ~10^4 warp partials added with fp32 atomics random-walk to ~3e-6 relative,
-// which the ~100x cancelling tr G = 0.5 (D tr K^-1 - |A|^2) turns into 3e-4 (measured at N = 5000 against the fp64 oracle).
-// Per-thread partial sums stay fp32 (a few hundred fused multiply-adds each), the cross-thread reduction is fp64.
-__global__ void __launch_bounds__(256) dot_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n,
-                                                      double* __restrict__ out) {
-  double s = 0.0;
-  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
-  if ((n & 3) == 0 && (((uintptr_t)a | (uintptr_t)b) & 15) == 0) {
-    const float4* a4 = reinterpret_cast<const float4*>(a);
-    const float4* b4 = reinterpret_cast<const float4*>(b);
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int run = 0;
-    for (size_t i = tid; i < n / 4; i += nthr) {
-      const float4 x = __ldg(a4 + i), y = __ldg(b4 + i);
-      s0 = fmaf(x.x, y.x, s0); s1 = fmaf(x.y, y.y, s1); s2 = fmaf(x.z, y.z, s2); s3 = fmaf(x.w, y.w, s3);
-      if (++run == 16) { s += ((double)s0 + (double)s1) + ((double)s2 + (double)s3); s0 = s1 = s2 = s3 = 0.f; run = 0; }
-    }
-    s += ((double)s0 + (double)s1) + ((double)s2 + (double)s3);
-  } else {
-    for (size_t i = tid; i < n; i += nthr) s += (double)__ldg(a + i) * (double)__ldg(b + i);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
-}
+// Reductions that feed the hyper-parameter gradients (tr K^-1, |A|_F^2, sum Y o A) are accumulated in DOUBLE across threads:
+// ~10^4 warp partials added with fp32 atomics random-walk to ~3e-6 relative, which the ~100x cancelling
+// tr G = 0.5 (D tr K^-1 - |A|^2) turns into 3e-4 (measured at N = 5000 against the fp64 oracle). Per-thread partial sums stay
+// fp32 (a few fused multiply-adds each). They ride on passes that exist anyway: kinv_diag_kernel, transpose_dots_kernel.
 // G tile = (D/2) Kinv + AA (AA = -0.5 A A^T, lower part valid; Kinv == nullptr: AA is G already) read from memory,
 // contracted with K_f
 template <class T>
@@ -2541,7 +2557,6 @@ extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float*
   logdet_xsq_kernel<<<1, 1024, 0, st>>>(w.K, N, N, X, N * Q, w.acc);
   if (!tc && (rc = run_trinv(h, st, w.K, N, N, w.Li, w.Tmp))) return rc;
   if (tc) {
-    const size_t nn = (size_t)N * N, nd = (size_t)N * D;
     const int tiles32 = (N + 31) / 32;
     double* frob = reinterpret_cast<double*>(reinterpret_cast<char*>(w.acc) + 64);   // nine fp64 scratch sums behind the accumulators
     cudaMemsetAsync(frob, 0, 9 * sizeof(double), st);
@@ -2565,8 +2580,8 @@ extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float*
       }
       trc = f16_gemm_launch(h, st, D, N, N, 1.0f, Y16, N, K16, N, 0.0f, w.B3, N, 0, 0);        // B3 = (K^-1 Y)^T
       if (trc) return set_err(h, DB_ERR_CUDA, "f16x3 K^-1 Y product failed (%d)", trc);
-      transpose_f32(st, w.B3, D, N, N, w.Av, D);                                   // Av = A = K^-1 Y [N,D]
-      dot_sum_kernel<<<h->num_sms * 8, 256, 0, st>>>(Y, w.Av, nd, frob + 2);       // |L^-1 Y|^2 = sum Y o A
+      // Av = A = K^-1 Y [N,D]; frob[1] = |A|_F^2, frob[2] = sum Y o A = |L^-1 Y|^2
+      transpose_dots_kernel<<<dim3((N + 31) / 32, (D + 31) / 32), 256, 0, st>>>(w.B3, D, N, N, w.Av, D, Y, frob + 1);
       gp_store_ssq_kernel<<<1, 1, 0, st>>>(w.acc, frob);
       if (want_grad) {
         f16_scale_from_absmax(h, st, w.Av, N, D, D, fs.bits + 1, fs.scales + 4);
@@ -2584,8 +2599,7 @@ extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float*
     tf32_split_lo(h, st, w.B1, D, N, N, w.B2);
     trc = tf32_gemm_launch(h, st, D, N, N, 1.0f, w.B1, w.B2, N, w.Li, w.K, N, 0.0f, w.B3, N, 0, 0);          // B3 = (K^-1 Y)^T
     if (trc) return set_err(h, DB_ERR_CUDA, "tf32 K^-1 Y product failed (%d)", trc);
-    transpose_f32(st, w.B3, D, N, N, w.Av, D);                                   // Av = A = K^-1 Y [N,D]
-    dot_sum_kernel<<<h->num_sms * 8, 256, 0, st>>>(Y, w.Av, nd, frob + 2);       // |L^-1 Y|^2 = sum Y o A
+    transpose_dots_kernel<<<dim3((N + 31) / 32, (D + 31) / 32), 256, 0, st>>>(w.B3, D, N, N, w.Av, D, Y, frob + 1);   // as above
     gp_store_ssq_kernel<<<1, 1, 0, st>>>(w.acc, frob);
     if (want_grad) {
       tf32_split_lo(h, st, w.Av, N, D, D, w.S);                                  // S buffer = remainder of A
@@ -2598,7 +2612,6 @@ extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float*
       const int tiles = (N + TileLarge::BM - 1) / TileLarge::BM;
       if (Q <= 2 && (N % 4) == 0) gp_contract_fused_kernel<TileLarge><<<dim3(tiles, tiles), 256, 0, st>>>(w.Li, w.Tmp, N, Q, D, X, w.hyp, w.dXacc, w.acc, frob + 3);
       else gp_contract_mem_kernel<TileLarge><<<dim3(tiles, tiles), 256, 0, st>>>(w.Li, w.Tmp, N, Q, D, X, w.hyp, w.dXacc, w.acc, frob + 3);
-      dot_sum_kernel<<<h->num_sms * 8, 256, 0, st>>>(w.Av, w.Av, nd, frob + 1);   // |A|_F^2
       static const int dbg = [] { const char* e = getenv("DB_GP_DEBUG"); return (e && e[0] == '1') ? 1 : 0; }();
       gp_fix_trace_kernel<<<1, 1, 0, st>>>(w.acc, frob, w.hyp, N, D, dbg);
     }

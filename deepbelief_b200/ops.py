@@ -329,9 +329,20 @@ class GplvmPlan:
                 return self.scalars, self.dX, self.info
             if key in self._seen and len(self._graphs) < self.MAX_GRAPHS:
                 graph = torch.cuda.CUDAGraph()
+                # capture_begin / capture_end on a side stream: the torch.cuda.graph context manager synchronises, runs
+                # gc.collect() and empties the allocator cache first (20-230 ms measured, replay.py); nothing is allocated
+                # inside the capture (workspace and outputs belong to the plan)
+                main = torch.cuda.current_stream()
+                side = torch.cuda.Stream()
+                side.wait_stream(main)
                 try:
-                    with torch.cuda.graph(graph):
-                        self._launch(*args)
+                    with torch.cuda.stream(side):
+                        graph.capture_begin()
+                        try:
+                            self._launch(*args)
+                        finally:
+                            graph.capture_end()
+                    main.wait_stream(side)
                 except Exception:                                  # capture not possible here: plain launches from now on
                     self.use_graph = False
                     torch.cuda.synchronize()

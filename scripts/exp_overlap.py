@@ -43,7 +43,7 @@ if os.environ.get('REPEAT'):
     print('replay spread', [float((o - outs[0]).abs().max() / outs[0].abs().max()) for o in outs[1:]], 'scalars g-vs-e %.1e' % g_sc)
 msg = 'mode %s N=%d D=%d: eager %.3f ms  graph %.3f ms (graphs captured: %d)  info %d  graph-vs-eager dX %.1e' % (
     mode, N, D, t_eager, t_graph, len(plan2._graphs), int(out['info'][0]), g_vs_e)
-ref_path = os.path.join('gpurun_out', 'overlap_ref_%d_%d.npz' % (N, D))
+ref_path = os.path.join(os.environ.get('OVERLAP_REF_DIR', 'gpurun_out'), 'overlap_ref_%d_%d.npz' % (N, D))
 if mode == '0':
     np.savez(ref_path, **out)
 elif os.path.exists(ref_path):
