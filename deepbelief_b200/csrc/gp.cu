@@ -1395,8 +1395,11 @@ struct TrinvOverlap {
   // The step launches of outer block blk want one strip CTA per 64 rows below the diagonal plus about as many in-panel update
   // CTAs; what is left belongs to the lanes. Below kMinReserve nothing is reserved and the slices are deferred.
   int reserve(int blk) const {
+    // strip + update CTAs per strip CTA; measured at N = 5000 (ms per evaluation): 1.5 / 1.75 / 2 / 2.5 / 3 -> 2.44 / 2.34 / 2.30 /
+    // 2.36 / 2.74 (N = 6144: 3.35 / - / 3.19 / 3.62 / -)
+    static const float ratio = [] { const char* e = getenv("DB_GP_UPD_RATIO"); return e ? (float)atof(e) : 2.0f; }();
     const int strips0 = (N - blk * OB + NB - 1) / NB;
-    const int r = num_sms - 2 * strips0;
+    const int r = num_sms - (int)(ratio * (float)strips0 + 0.5f);
     if (r < kMinReserve) return 0;
     return r > num_sms - 8 ? num_sms - 8 : r;
   }
