@@ -9,7 +9,7 @@ python scripts/gp_once.py > $O/r02f_plain_gp_once.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/r02_launches_gplvm_n5000.csv python scripts/gp_once.py > $O/r02f_ncu_gp.log 2>&1
 ncu --set full --clock-control none -k regex:potrf_step -s 40 -c 2 -o $O/r02_prof_potrf_step python scripts/gp_once.py > $O/r02f_ncu_potrf.log 2>&1
 export_rep r02_prof_potrf_step
-ncu --set full --clock-control none -k regex:"gp_contract_fused|mirror_lower_split|kinv_diag_kernel|trinv_diag_kernel" -s 0 -c 5 -o $O/r02_prof_gp_tail python scripts/gp_once.py > $O/r02f_ncu_tail.log 2>&1
+ncu --set full --clock-control none -k regex:"gp_contract_fused|mirror_lower_split|kinv_diag_kernel|transpose_dots" -s 0 -c 4 -o $O/r02_prof_gp_tail python scripts/gp_once.py > $O/r02f_ncu_tail.log 2>&1
 export_rep r02_prof_gp_tail
 DB_GP_OVERLAP=0 python scripts/timeline_gp.py 2>/dev/null > $O/r02_timeline_gplvm_n5000_one_stream.txt
 DB_GP_OVERLAP=1 python scripts/timeline_gp.py 2>/dev/null > $O/r02_timeline_gplvm_n5000_lanes.txt
