@@ -424,7 +424,8 @@ __device__ __forceinline__ void factor8(const float (*blk)[8], float (&l)[8][8],
 #pragma unroll
     for (int m = 0; m < jc; ++m) s = fmaf(-l[jc][m], l[jc][m], s);
     if (!(s > 0.0f) && fail == 0) fail = c0 + jc + 1;
-    float y = rsqrtf(s);
+    float y;                                               // one MUFU (rsqrtf adds a denormal-range fix-up to the dependent chain;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(s));   //  s is a pivot of magnitude ~noise variance or the step has failed)
     y = y * fmaf(-0.5f * s * y, y, 1.5f);
     inv[jc] = y;
     l[jc][jc] = s * y;

@@ -8,7 +8,9 @@
  * Conventions
  *   - all matrices fp32, row-major, device pointers, leading dimension in elements (config.py:1);
  *   - the library never allocates or frees device memory: callers pass outputs and a workspace
- *     (size from the matching *_workspace_bytes); calls are asynchronous on `stream`;
+ *     (size from the matching *_workspace_bytes); calls are asynchronous on `stream`. The GP entries
+ *     (db_gplvm_lml_grad, db_gpdbn_factor) fork onto two auxiliary streams owned by the handle and join
+ *     back before they return, so `stream` order is all a caller sees (also under stream capture);
  *   - return value: 0 ok; < 0 error (DB_ERR_*), message via db_last_error(); > 0 LAPACK-style info
  *     (1-based index of the failing Cholesky pivot / first negative predictive variance);
  *   - no entry point has a CPU fallback: without a CUDA device db_create fails.
