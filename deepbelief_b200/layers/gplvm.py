@@ -134,26 +134,28 @@ class GPLVM(layer.Layer):
         self.subtract_Y_mean = subtract_Y_mean
         self.device = device
 
-        Y_np = Y.astype(np.float32)
         if uppropagate_Y and bottom is not None:
             # the reference keeps this as a stochastic graph tensor re-sampled per run (gplvm.py:117-118,
             # SURVEY §8 a'.10, exercised by no example); here it is one draw
-            Y_np = to_numpy(bottom.upprop(Y_np))
+            Y_dev = to_device(bottom.upprop(Y.astype(np.float32)), device)
+        else:
+            Y_dev = to_device(Y, device)          # one host->device copy of the caller's array (no host-side passes over it)
         if self.subtract_Y_mean:
-            self.Y_mean = to_device(Y_np.mean(axis=0, keepdims=True), device)      # gplvm.py:122-124
-            Y_np = Y_np - Y_np.mean(axis=0, keepdims=True)
+            # gplvm.py:122-124, on the device: the host version cost three passes over Y and 13-63 ms of a constructor call
+            self.Y_mean = Y_dev.mean(dim=0, keepdim=True)
+            Y_dev = Y_dev - self.Y_mean
         else:
             self.Y_mean = None
-        self.Y_np = Y_np
-        self.Y = to_device(Y_np, device)
+        self.Y = Y_dev
+        self._Y_np = None
 
         if X0 is not None:
             self.X0 = np.asarray(X0, dtype=np.float32)
         else:
             self.X0 = preprocessing.standardize(preprocessing.PCA(self.Y_np, self.Q))   # gplvm.py:131-132
-        assert self.X0.shape[0] == self.Y_np.shape[0]
+        assert self.X0.shape[0] == self.Y.shape[0]
         assert self.X0.shape[1] == self.Q
-        self.N, self.D = self.X0.shape[0], self.Y_np.shape[1]
+        self.N, self.D = self.X0.shape[0], int(self.Y.shape[1])
 
         # packed trainables [X | opt_alpha, opt_gamma, opt_noise | ARD opt_gamma [Q]]
         nq = self.N * self.Q
@@ -195,6 +197,13 @@ class GPLVM(layer.Layer):
         self._factor_version = -1
         params = {'X': self.X, 'noise_variance': lambda: self.noise_variance}
         super().__init__(params=params, bottom=bottom, session=session, name=name)
+
+    @property
+    def Y_np(self):
+        """The (centred) observations as a host array, fetched on first use (PCA initialisation, diagnostics)."""
+        if self._Y_np is None:
+            self._Y_np = to_numpy(self.Y)
+        return self._Y_np
 
     # ---- hyper-parameters -------------------------------------------------------------------------------------
     @property
