@@ -541,7 +541,10 @@ def run_b200(args):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': Wm,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f32 (fp16 hi/lo split operands, fp32 TMEM accumulate)', 'data': 'synthetic',
-            'config': dict(CONFIG, parallelism='dp%d (rows sharded, NCCL sum-all-reduce of dW|db|dc)' % world,
+            'config': dict(CONFIG, parallelism=('dp1 (one process: optimizer fused into the dW kernel)' if world == 1 else
+                                                'dp%d (rows sharded; %s)' % (world, 'dW reduce-scattered by peer stores from the dW epilogue over NVLink, '
+                                                'sharded update, rows pushed back; NCCL all-reduce of db|dc' if getattr(rbm, '_peer', None)
+                                                else 'NCCL sum-all-reduce of dW|db|dc')),
                            local_batch=n_local),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': e2e_ms, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': 4, 'h2d_dtype': 'uint8' if h2d == n_local * V else 'float32', 'api': 'RBM.train(AdamOptimizer, Data.from_arrays(pinned host), '

@@ -1393,6 +1393,7 @@ struct TrinvOverlap {
   int trail_reserve;        // SMs a trailing update leaves free in mode 1
   int num_sms, N;
   int pending;              // first slice not issued yet (slices wait while the step launches need every SM)
+  int err;                  // first non-zero return code of a side product launch (checked by the caller after the join)
   // The step launches of outer block blk want one strip CTA per 64 rows below the diagonal plus about as many in-panel update
   // CTAs; what is left belongs to the lanes. Below kMinReserve nothing is reserved and the slices are deferred.
   int reserve(int blk) const {
@@ -1684,7 +1685,7 @@ void run_trinv_f16_side_prologue(db_handle_t h, const TrinvOverlap& ov, cudaStre
 }
 
 // slice blk, behind the event of outer block ev_blk >= blk (a deferred slice starts with a later block's event)
-static void run_trinv_f16_side_block(db_handle_t h, const TrinvOverlap& ov, float* L, int blk, int ev_blk, const F16Scratch& f) {
+static void run_trinv_f16_side_block(db_handle_t h, TrinvOverlap& ov, float* L, int blk, int ev_blk, const F16Scratch& f) {
   const int N = ov.N;
   const int nblk = (N + OB - 1) / OB;
   const int b0 = blk * OB, nb = std::min(OB, N - b0);
@@ -1720,13 +1721,15 @@ static void run_trinv_f16_side_block(db_handle_t h, const TrinvOverlap& ov, floa
   int first = 1;       // the first launch behind the event wait is a plain one (gemm_f16x3.cuh, allow_pdl)
   if (blk >= 1) {
     const F16Operand Uout = U16.at(b0);
-    f16_gemm_launch(h, st, b0, nb, nb, -1.0f, WT16, OB, Lid16.at(d), N, 0.0f, ov.U + b0, N, 0, 0, &Uout, N, cap, /*allow_pdl=*/0);
+    const int rc = f16_gemm_launch(h, st, b0, nb, nb, -1.0f, WT16, OB, Lid16.at(d), N, 0.0f, ov.U + b0, N, 0, 0, &Uout, N, cap, /*allow_pdl=*/0);
+    if (rc && !ov.err) ov.err = rc;
     first = 0;
   }
   if (blk + 1 < nblk) {
     const int P = b0 + OB, nb1 = std::min(OB, N - P);
-    f16_gemm_launch(h, st, P, nb1, P, 1.0f, U16, N, L16.at((size_t)P * N), N, 0.0f, nullptr, OB, /*lower_only=*/0, /*tri_k=*/2, &WT16, OB, cap,
-                    /*allow_pdl=*/first ? 0 : 1);
+    const int rc = f16_gemm_launch(h, st, P, nb1, P, 1.0f, U16, N, L16.at((size_t)P * N), N, 0.0f, nullptr, OB, /*lower_only=*/0, /*tri_k=*/2,
+                                   &WT16, OB, cap, /*allow_pdl=*/first ? 0 : 1);
+    if (rc && !ov.err) ov.err = rc;
   }
 }
 
@@ -1762,7 +1765,7 @@ inline int gp_overlap_mode(db_handle_t h, cudaStream_t st, int N) {
 }
 inline TrinvOverlap gp_overlap(db_handle_t h, float* Li, float* U, int mode, int N) {
   static const int trail = [] { const char* e = getenv("DB_GP_TRAIL_RESERVE"); return e ? atoi(e) : TrinvOverlap::kMinReserve; }();
-  return TrinvOverlap{h->side_stream, h->side_stream2, h->side_events, Li, U, mode, trail, h->num_sms, N, 0};
+  return TrinvOverlap{h->side_stream, h->side_stream2, h->side_events, Li, U, mode, trail, h->num_sms, N, 0, 0};
 }
 
 template <int TRANS>
@@ -2565,7 +2568,10 @@ extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float*
     double* frob = reinterpret_cast<double*>(reinterpret_cast<char*>(w.acc) + 64);   // nine fp64 scratch sums behind the accumulators
     cudaMemsetAsync(frob, 0, 9 * sizeof(double), st);
     // Tmp = Linv^T (upper triangular), Ulo = its tf32 remainder (3 x fp16 form: its scaled fp16 pair in the scratch)
-    if (overlap) run_trinv_f16_side_join(ov, st);
+    if (overlap) {
+      run_trinv_f16_side_join(ov, st);
+      if (ov.err) return set_err(h, DB_ERR_CUDA, "f16x3 triangular inverse (side lanes) failed (%d)", ov.err);
+    }
     else if (f16) { if ((rc = run_trinv_tc_f16(h, st, w.K, N, w.Li, w.Tmp, fs))) return rc; }
     else if ((rc = run_trinv_tc(h, st, w.K, w.Li, N, w.Li, w.Tmp, w.Ulo, w.WT, w.WTlo))) return rc;
     int trc;
@@ -2698,7 +2704,10 @@ extern "C" int db_gpdbn_factor(db_handle_t h, db_stream_t stream, const float* X
     // Linv^T and K^-1 = Linv^T Linv on the tensor cores, diagonal of K^-1 in exact fp32 (it carries pred_var)
     const int tiles32 = (N + 31) / 32;
     if (f16) {
-      if (overlap) run_trinv_f16_side_join(ov, st);
+      if (overlap) {
+        run_trinv_f16_side_join(ov, st);
+        if (ov.err) return set_err(h, DB_ERR_CUDA, "f16x3 triangular inverse (side lanes) failed (%d)", ov.err);
+      }
       else if ((rc = run_trinv_tc_f16(h, st, w.K, N, w.Li, w.U, fs))) return rc;
       const F16Operand U16{fs.u_hi, fs.u_lo, fs.scales + 1};
       const int trc = f16_gemm_launch(h, st, N, N, N, 1.0f, U16, N, U16, N, 0.0f, w.Kinv, N, 1, 1);
