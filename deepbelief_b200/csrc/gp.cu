@@ -1,16 +1,24 @@
 // GP path: RBF Gram (K3), blocked Cholesky (K4), triangular solves / inverse (K5) and the fused
 // log-marginal-likelihood + analytic gradient (K6) behind gplvm.py:61-86, 210-288 and gprbm.py:193-245.
-// All fp32 SIMT; nothing here calls cuBLAS / cuSOLVER.
+// Nothing here calls cuBLAS / cuSOLVER. Two forms of the same evaluation live in this file:
 //
-// Pipeline of one LML+gradient evaluation (N points, D outputs, Q latent dims):
+// fp32 SIMT form (N < 512, odd shapes, the reference's own N = 328 runs) — N points, D outputs, Q latent dims:
 //   hyp      = softplus(opt) (+ jitter)                                    gplvm.py:39,49,152,219-221
 //   K        = alpha * exp(-|xi-xj|^2 / (2 gamma^2)) + noise * I           gplvm.py:61-86, 218-224
 //   L        = chol(K)           right-looking, 64-wide panels             gplvm.py:212
 //   Linv     = L^-1              recursive block inversion (log-depth, batched GEMMs)
 //   S        = Linv Y ; |S|^2 ; logdet = 2 sum log Lii                     gplvm.py:226-236
 //   A        = Linv^T S = K^-1 Y
-//   G        = 0.5 (D Linv^T Linv - A A^T), W = G o K_f  -> dX, d alpha, d gamma, d noise, all in ONE
-//              kernel over the lower tile pairs; neither K^-1 nor G is ever written to HBM.
+//   G        = 0.5 (D Linv^T Linv - A A^T), W = G o K_f  -> dX, d alpha, d gamma, d noise over the lower tile pairs
+//
+// tensor-core form (N >= 512, N and D multiples of 4; 3 x fp16 products when multiples of 8, else 3xTF32):
+//   L        = one potrf_step_kernel launch per 64-wide column block + one tcgen05 trailing update per 512-wide outer block
+//   U        = L^-T block row by block row (run_trinv_tc_f16) — on two auxiliary streams BESIDE the factorisation when the
+//              step launches leave SMs free (TrinvOverlap, run_trinv_f16_side_block)
+//   K^-1     = U U^T (exact fp32 diagonal, tr K^-1 from it), mirrored and converted in one pass
+//   A        = K^-1 Y, sum Y o A and |A|^2 formed by the transposition that produces A;  -0.5 A A^T
+//   dX, d alpha, d gamma, d noise: one pass over the tiles of G = (D/2) K^-1 - 0.5 A A^T (gp_contract_fused_kernel), the
+//              hyper-parameter sums from fp64 closed forms (gp_fix_trace_kernel)
 // Algorithmic work: N^3 + 3 N^2 D FLOP (SURVEY.md §8 d).
 #include "context.h"
 #include "simt_gemm.cuh"

@@ -291,7 +291,8 @@ def trsm_lower(Lmat, B, trans=False):
 class GplvmPlan:
     """Workspace owner for the fused LML + gradient evaluation at a fixed (N, Q, D).
 
-    The evaluation is ~150 dependent launches (79 Cholesky steps at N = 5000, 60 at N = 328). When the same argument
+    The evaluation is ~230 launches on three streams at N = 5000 (79 Cholesky steps; the triangular inverse runs beside them on
+    two auxiliary streams of the library handle and joins before the K^-1 product), ~60 at N = 328. When the same argument
     set (pointers and scalars) comes back a second time — the optimisation loop of GPLVM.optimize updates X and the
     hyper-parameters in place — the launch sequence is captured into a CUDA graph and replayed from then on
     (DEEPBELIEF_B200_GRAPH=0 keeps the plain launches)."""
