@@ -1869,32 +1869,54 @@ __global__ void __launch_bounds__(256) mirror_lower_kernel(float* __restrict__ A
 }
 // The same mirror for the 3 x fp16 chain: the full symmetric matrix is also written as the scaled fp16 pair the next product
 // reads (a separate conversion pass over the mirrored matrix cost 31 us at N = 5000). The diagonal must be final already.
+// 64 x 64 tiles, 16-byte loads / stores of A and 8-byte stores of the pair (N % 4 == 0 on this path); the first version moved
+// 32 x 32 tiles with 4-byte loads and 2-byte stores: 52 us for the 148 MB it touches.
+__device__ __forceinline__ void store_pair4(__half* __restrict__ hi, __half* __restrict__ lo, size_t idx, float4 v, float sc) {
+  __half h0, l0, h1, l1, h2, l2, h3, l3;
+  split_f16(v.x * sc, h0, l0); split_f16(v.y * sc, h1, l1); split_f16(v.z * sc, h2, l2); split_f16(v.w * sc, h3, l3);
+  __half2 ha = __halves2half2(h0, h1), hb = __halves2half2(h2, h3), la = __halves2half2(l0, l1), lb = __halves2half2(l2, l3);
+  *reinterpret_cast<uint2*>(hi + idx) = make_uint2(*reinterpret_cast<uint32_t*>(&ha), *reinterpret_cast<uint32_t*>(&hb));
+  *reinterpret_cast<uint2*>(lo + idx) = make_uint2(*reinterpret_cast<uint32_t*>(&la), *reinterpret_cast<uint32_t*>(&lb));
+}
 __global__ void __launch_bounds__(256) mirror_lower_split_kernel(float* __restrict__ A, int N, __half* __restrict__ hi,
                                                                  __half* __restrict__ lo, const float* __restrict__ scale) {
-  __shared__ float tile[32][33];
-  if (blockIdx.x > blockIdx.y) return;
+  __shared__ float tile[64][65];
+  if (blockIdx.x > blockIdx.y) return;                       // tile (by, bx) of the lower triangle -> (bx, by)
+  const bool diag = blockIdx.x == blockIdx.y;
   const float sc = __ldg(scale);
-  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const int q = threadIdx.x & 15, rr = threadIdx.x >> 4;     // sixteen float4 per tile row, sixteen rows per pass
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int r = r0 + ty + 8 * i, c = c0 + tx;
-    float v = 0.0f;
-    if (r < N && c < N) {
-      v = A[(size_t)r * N + c];
-      if (c <= r) { __half hh, ll; split_f16(v * sc, hh, ll); hi[(size_t)r * N + c] = hh; lo[(size_t)r * N + c] = ll; }
+    const int r = rr + 16 * i, gr = r0 + r, gc = c0 + 4 * q;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gr < N && gc < N) {
+      v = *reinterpret_cast<const float4*>(A + (size_t)gr * N + gc);
+      if (!diag) store_pair4(hi, lo, (size_t)gr * N + gc, v, sc);      // strictly lower block: its pair as it is
     }
-    tile[ty + 8 * i][tx] = v;
+    tile[r][4 * q] = v.x; tile[r][4 * q + 1] = v.y; tile[r][4 * q + 2] = v.z; tile[r][4 * q + 3] = v.w;
   }
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int c = c0 + ty + 8 * i, r = r0 + tx;           // writes element (c, r) = (r, c)^T
-    if (c < N && r < N && c < r) {
-      const float v = tile[tx][ty + 8 * i];
-      A[(size_t)c * N + r] = v;
-      __half hh, ll; split_f16(v * sc, hh, ll);
-      hi[(size_t)c * N + r] = hh; lo[(size_t)c * N + r] = ll;
+    const int r = rr + 16 * i;
+    if (diag) {                                              // symmetric fill of the diagonal tile, whole rows
+      const int gr = r0 + r, gc = c0 + 4 * q;
+      if (gr < N && gc < N) {
+        float e[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) e[k] = (4 * q + k <= r) ? tile[r][4 * q + k] : tile[4 * q + k][r];
+        const float4 v = make_float4(e[0], e[1], e[2], e[3]);
+        *reinterpret_cast<float4*>(A + (size_t)gr * N + gc) = v;
+        store_pair4(hi, lo, (size_t)gr * N + gc, v, sc);
+      }
+    } else {                                                 // row c0 + r of the transposed block: columns r0 + 4q ..
+      const int gr = c0 + r, gc = r0 + 4 * q;
+      if (gr < N && gc < N) {
+        const float4 v = make_float4(tile[4 * q][r], tile[4 * q + 1][r], tile[4 * q + 2][r], tile[4 * q + 3][r]);
+        *reinterpret_cast<float4*>(A + (size_t)gr * N + gc) = v;
+        store_pair4(hi, lo, (size_t)gr * N + gc, v, sc);
+      }
     }
   }
 }
@@ -2064,7 +2086,6 @@ __global__ void __launch_bounds__(256) gp_contract_fused_kernel(const float* __r
   __shared__ float red[3][8];
   static_assert(T::BM == T::BN, "square tiles");
   const int m0 = blockIdx.y * T::BM, n0 = blockIdx.x * T::BN;
-  const bool diag_tile = blockIdx.x == blockIdx.y;
   for (int t = threadIdx.x; t < T::BM * 2; t += 256) { (&rowacc[0][0])[t] = 0.0f; (&colacc[0][0])[t] = 0.0f; }
   const float half_d = 0.5f * (float)D;
   const float alpha = __ldg(hyp), inv_g2 = 1.0f / (__ldg(hyp + 1) * __ldg(hyp + 1));
@@ -2118,7 +2139,7 @@ __global__ void __launch_bounds__(256) gp_contract_fused_kernel(const float* __r
       cacc[jj][0] = fmaf(-w, d0, cacc[jj][0]); cacc[jj][1] = fmaf(-w, d1, cacc[jj][1]);
     }
   }
-  (void)diag_tile;
+
   {     // per-thread fp32 partials (<= TM*TN terms), everything across threads in fp64
     double v[6] = {2.0 * (double)cK, 2.0 * (double)cKr, 2.0 * (double)cA, 2.0 * (double)cAr, 2.0 * (double)cF, 2.0 * (double)cFr};
 #pragma unroll
@@ -2590,7 +2611,7 @@ extern "C" int db_gplvm_lml_grad(db_handle_t h, db_stream_t stream, const float*
       trc = f16_gemm_launch(h, st, N, N, N, 1.0f, U16, N, U16, N, 0.0f, w.Li, N, 1, 1);        // Li = K^-1 (lower)
       if (trc) return set_err(h, DB_ERR_CUDA, "f16x3 K^-1 product failed (%d)", trc);
       kinv_diag_kernel<<<(N + 7) / 8, 256, 0, st>>>(w.Tmp, N, w.Li, nullptr, frob);     // + |Linv|_F^2 = tr K^-1
-      mirror_lower_split_kernel<<<dim3(tiles32, tiles32), 256, 0, st>>>(w.Li, N, K16.hi, K16.lo, K16.scale);   // |K^-1_ij| <= 1 / s
+      mirror_lower_split_kernel<<<dim3((N + 63) / 64, (N + 63) / 64), 256, 0, st>>>(w.Li, N, K16.hi, K16.lo, K16.scale);   // |K^-1_ij| <= 1 / s
       if (!overlap) {
         transpose_f32(st, Y, N, D, D, w.B1, N);                                    // B1 = Y^T [D,N]
         f16_scale_from_absmax(h, st, Y, N, D, D, fs.bits, fs.scales + 3);
@@ -2722,7 +2743,7 @@ extern "C" int db_gpdbn_factor(db_handle_t h, db_stream_t stream, const float* X
       if (trc) return set_err(h, DB_ERR_CUDA, "f16x3 K^-1 product failed (%d)", trc);
       kinv_diag_kernel<<<(N + 7) / 8, 256, 0, st>>>(w.U, N, w.Kinv, nullptr);
       // mirrored, and again as the fp16 pair the backward product (db_gpdbn_backward_x, 3 x fp16) reads
-      mirror_lower_split_kernel<<<dim3(tiles32, tiles32), 256, 0, st>>>(w.Kinv, N, fs.k_hi, fs.k_lo, fs.scales + 2);
+      mirror_lower_split_kernel<<<dim3((N + 63) / 64, (N + 63) / 64), 256, 0, st>>>(w.Kinv, N, fs.k_hi, fs.k_lo, fs.scales + 2);
     } else {
     if ((rc = run_trinv_tc(h, st, w.K, w.Li, N, w.Li, w.U, w.Ulo, w.WT, w.WTlo))) return rc;
     // the K buffer (L is dead) keeps the tf32 remainder of K^-1 for the backward GEMM (db_gpdbn_backward_x)
