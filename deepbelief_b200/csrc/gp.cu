@@ -1428,8 +1428,16 @@ int run_potrf(db_handle_t h, cudaStream_t st, float* A, int lda, int N, int* inf
   static const bool pdl = [] { const char* e = getenv("DB_POTRF_PDL"); return !(e && e[0] == '0'); }();
   static std::once_flag smem_once;
   std::call_once(smem_once, [] { cudaFuncSetAttribute(potrf_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEP_SMEM); });
+  // Tail merge (3 x fp16 chain): once at most tail_rows rows remain, the outer blocks stop handing their trailing update to a
+  // GEMM launch (~20 us of launch latency for ~1 us of work there); the update CTAs of the step launches apply every panel
+  // to ALL remaining columns instead. Measured at N = 5000 (ms per evaluation, DB_POTRF_TAIL_ROWS = 0 / 1000 / 1500 / 2000 /
+  // 3000): 2.273 / 2.257 / 2.269 / 2.349 / 2.722 with the side lanes, 2.711 / - / 2.684 on one stream.
+  static const int tail_rows = [] { const char* e = getenv("DB_POTRF_TAIL_ROWS"); return e ? atoi(e) : 1000; }();
   for (int b0 = 0; b0 < N; b0 += OB) {
     const int b1 = b0 + OB < N ? b0 + OB : N;
+    const bool merged = f16 != nullptr && tail_rows > 0 && b0 > 0 && N - b0 <= tail_rows;
+    const bool prev_merged = merged && b0 - OB > 0 && N - (b0 - OB) <= tail_rows;
+    const int upd_end = merged ? N : b1;          // columns the update CTAs of this block's launches cover
     static const bool skip_steps = [] { const char* e = getenv("DB_POTRF_SKIP_STEPS"); return e && e[0] == '1'; }();   // timing diagnostics only
     for (int j = b0; j < b1 && !skip_steps; j += NB) {
       if (legacy) {
@@ -1442,13 +1450,13 @@ int run_potrf(db_handle_t h, cudaStream_t st, float* A, int lda, int N, int* inf
         continue;
       }
       const int strips = (N - j + NB - 1) / NB;
-      const int jprev = j > b0 ? j - NB : -1;
-      int updates = 0;                 // update CTAs: each loops over 128x64 tiles of the columns [j + 64, b1)
-      if (jprev >= 0 && j + NB < b1) {
+      const int jprev = j > b0 ? j - NB : (prev_merged ? j - NB : -1);
+      int updates = 0;                 // update CTAs: each loops over 128x64 tiles of the columns [j + 64, upd_end)
+      if (jprev >= 0 && j + NB < upd_end) {
         int tiles = 0;
-        for (int cb = j + NB; cb < b1; cb += NB) tiles += (N - cb + 2 * NB - 1) / (2 * NB);
+        for (int cb = j + NB; cb < upd_end; cb += NB) tiles += (N - cb + 2 * NB - 1) / (2 * NB);
         const int free_sms = h->num_sms - strips - (ov ? ov->reserve(b0 / OB) : 0);
-        updates = tiles;
+        updates = merged ? (tiles + 2) / 3 : tiles;
         const int cap = free_sms > 8 ? free_sms : 8;
         if (updates > cap) updates = cap;
       }
@@ -1482,7 +1490,7 @@ int run_potrf(db_handle_t h, cudaStream_t st, float* A, int lda, int N, int* inf
         ++dbg_step;
       }
 #endif
-      cudaLaunchKernelEx(&cfg, potrf_step_kernel, A, lda, N, j, jprev, b1, strips, info, dbg);
+      cudaLaunchKernelEx(&cfg, potrf_step_kernel, A, lda, N, j, jprev, upd_end, strips, info, dbg);
     }
     static const bool skip_wide = [] { const char* e = getenv("DB_POTRF_SKIP_WIDE"); return e && e[0] == '1'; }();   // timing diagnostics only
     if (b1 < N && !skip_wide) {        // wide update of everything right of the outer block, K = b1 - b0
@@ -1503,7 +1511,8 @@ int run_potrf(db_handle_t h, cudaStream_t st, float* A, int lda, int N, int* inf
             if (run_trinv_f16_side_blocks(h, *ov, st, A, b0 / OB, *f16)) cap = h->num_sms - ov->trail_reserve;
           }
           int rc = -1000;
-          if (rows >= 128)       // (the 3xTF32 form kept the SIMT kernel below 512 rows: 71 us for the 392-row tail at N = 5000)
+          if (merged) rc = 0;    // the step launches of this and the following blocks carry the update
+          else if (rows >= 128)       // (the 3xTF32 form kept the SIMT kernel below 512 rows: 71 us for the 392-row tail at N = 5000)
             rc = f16_gemm_launch(h, st, rows, rows, b1 - b0, -1.0f, P16, lda, P16, lda, 1.0f, A + (size_t)b1 * lda + b1, lda,
                                  /*lower_only=*/1, /*tri_k=*/0, nullptr, 0, cap);
           if (rc != 0 && rc != -1000) return set_err(h, DB_ERR_CUDA, "f16x3 trailing update failed (%d)", rc);
